@@ -1,0 +1,95 @@
+/*
+ * libecc_b200.h — C ABI of the B200-native batched scalar-multiplication / ECDSA-verification engine.
+ *
+ * This is the drop-in boundary for the hot path of ANSSI-FR/libecc.  The reference has no FFI:
+ * its boundary is the C symbol + struct ABI of libec.a / libsign.a.  Two layers are exported:
+ *
+ *  (1) this header: a flat, struct-free batch API on libecc's WIRE FORMATS (big-endian byte strings exactly as
+ *      produced by nn_export_to_buf  src/nn/nn.c:511  and  prj_pt_export_to_aff_buf  src/curves/prj_pt.c:600).
+ *      Each entry point names the reference function it replaces.
+ *  (2) libecc_b200_dropin.h: the reference's own entry points (prj_pt_mul, prj_pt_mul_blind, and the ECDSA
+ *      verify_batch slot) on the reference's own structs, implemented on top of (1).
+ *
+ * Conventions kept from the reference: int return, 0 = success, -1 = error (src/utils/utils.h:137-143); the caller
+ * owns every buffer; nothing is retained after return; callable from any thread (one context may be used by one
+ * thread at a time; create one context per thread or guard it).  All arithmetic runs on the GPU; if no CUDA device
+ * or the wrong architecture is present every call fails with -1 (there is NO CPU fallback).
+ */
+#ifndef LIBECC_B200_H
+#define LIBECC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Curve identifiers = the reference's ec_curve_type values (src/lib_ecc_types.h:147-). */
+#define ECCB200_FRP256V1 1
+#define ECCB200_SECP256R1 4
+#define ECCB200_SECP384R1 5
+
+/* Per-item status codes written by the batch calls. */
+#define ECCB200_OK 0        /* finite result / valid signature                                          */
+#define ECCB200_INFINITY 1  /* result is the point at infinity (prj_pt_iszero), output bytes are zero    */
+#define ECCB200_ERR (-1)    /* what the reference reports with ret = -1 (bad point, r/s range, bad sig)  */
+
+typedef struct eccb200_ctx eccb200_ctx;
+
+/*
+ * Create an engine context for one curve on one device: uploads the curve constants and builds the fixed-base
+ * comb table T[i][d] = d * 2^(w*i) * G on the GPU.  Replaces import_params (src/curves/ec_params.c:24) as the
+ * place where per-curve state is derived.  comb_window: bits per fixed-base window (4..16), 0 = default.
+ */
+int eccb200_ctx_create(eccb200_ctx **ctx, int curve_id, int device, int comb_window);
+void eccb200_ctx_destroy(eccb200_ctx *ctx);
+
+/* ceil(bitlen(p)/8) and ceil(bitlen(q)/8) for a curve id; -1 if unknown. */
+int eccb200_curve_sizes(int curve_id, uint32_t *plen, uint32_t *qlen);
+/* Reference curve name ("SECP256R1", ...) for an id, or NULL. */
+const char *eccb200_curve_name(int curve_id);
+
+/*
+ * Batched prj_pt_mul + prj_pt_unique + prj_pt_export_to_aff_buf
+ *   (src/curves/prj_pt.c:1759 prj_pt_mul; :241 prj_pt_unique; :600 prj_pt_export_to_aff_buf).
+ *   scalars : n * qlen bytes, big-endian, any value in [0, 2^(8*qlen)) (reduced mod q like the reference's ladder)
+ *   points  : n * 2*plen bytes affine big-endian x||y, or NULL for the curve generator G (params->ec_gen)
+ *   out     : n * 2*plen bytes affine big-endian x||y (zero for non-OK items)
+ *   status  : n bytes, ECCB200_OK / ECCB200_INFINITY / ECCB200_ERR (point not on curve or coordinate >= p:
+ *             the reference fails prj_pt_import_from_aff_buf :541-545 / prj_pt_mul :1767)
+ * Host-pointer version: blocking, includes the host<->device copies (pipelined in chunks).
+ */
+int eccb200_prj_pt_mul_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *scalars, const uint8_t *points,
+			     uint8_t *out, int8_t *status);
+
+/* Same, on device-resident buffers, enqueued on `stream` (a cudaStream_t; NULL = default stream); asynchronous. */
+int eccb200_prj_pt_mul_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_scalars, const uint8_t *d_points,
+				 uint8_t *d_out, int8_t *d_status, void *stream);
+
+/*
+ * Batched ECDSA verification on pre-hashed messages: replaces, per signature, __ecdsa_verify_init's checks
+ * (src/sig/ecdsa_common.c:645-658) and __ecdsa_verify_finalize steps 3-10 (:760-810); hashing (step 2) stays on
+ * the host in the reference's src/hash.  This is what fills the ECDSA verify_batch slot the reference leaves
+ * unsupported (src/sig/sig_algs_internal.h:294).
+ *   sigs    : n * 2*qlen bytes r||s;  pubkeys : n * 2*plen bytes affine x||y;  digests : n * hlen bytes
+ *   verdict : n bytes, ECCB200_OK (valid) / ECCB200_ERR (invalid, or any error such as key not on curve)
+ */
+int eccb200_ecdsa_verify_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys,
+			       const uint8_t *digests, uint32_t hlen, int8_t *verdict);
+int eccb200_ecdsa_verify_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_sigs, const uint8_t *d_pubkeys,
+				   const uint8_t *d_digests, uint32_t hlen, int8_t *d_verdict, void *stream);
+
+/* Field-level entry point used by the arithmetic unit tests (pattern: src/arithmetic_tests FP_MUL_MONTY):
+ * out[i] = a[i]*b[i]*R^-1 mod p (which = 0) or mod q (which = 1), R = 2^(8*plen); inputs must be < modulus. */
+int eccb200_fp_mul_monty_batch(eccb200_ctx *ctx, int which, uint32_t n, const uint8_t *a, const uint8_t *b,
+			       uint8_t *out);
+
+/* Introspection for bench.py / tests. */
+int eccb200_comb_window(const eccb200_ctx *ctx);
+uint64_t eccb200_kernel_launches(const eccb200_ctx *ctx);  /* kernels launched by this context so far */
+const char *eccb200_last_error(void);                      /* thread-local message for the last -1 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,164 @@
+"""libecc_b200 — ctypes binding of the C ABI in include/libecc_b200.h (used by tests/ and bench.py).
+
+The product is the shared library ``libecc_b200/libecc_b200.so`` (hand-written sm_100a CUDA behind a C ABI that
+mirrors libecc's prj_pt_mul / ECDSA-verify entry points).  This module only loads it and marshals buffers; it
+contains no arithmetic and has no CPU fallback: if the library is missing or no B200 is visible, it raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libecc_b200.so")
+
+CURVE_IDS = {"FRP256V1": 1, "SECP256R1": 4, "SECP384R1": 5}  # libecc ec_curve_type (src/lib_ecc_types.h:147-)
+
+# Every symbol include/libecc_b200.h and include/libecc_b200_dropin.h declare (tests check they are exported).
+ABI_SYMBOLS = [
+    "eccb200_ctx_create", "eccb200_ctx_destroy", "eccb200_curve_sizes", "eccb200_curve_name",
+    "eccb200_prj_pt_mul_batch", "eccb200_prj_pt_mul_batch_dev", "eccb200_ecdsa_verify_batch",
+    "eccb200_ecdsa_verify_batch_dev", "eccb200_fp_mul_monty_batch", "eccb200_comb_window",
+    "eccb200_kernel_launches", "eccb200_last_error",
+]
+
+_lib = None
+
+
+class EccB200Error(RuntimeError):
+    pass
+
+
+def load_library() -> ctypes.CDLL:
+    """Load libecc_b200.so (fails loudly when it has not been built: there is no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EccB200Error(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = ctypes.CDLL(LIB_PATH)
+    u8p, i8p, u32 = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32
+    lib.eccb200_ctx_create.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.eccb200_ctx_create.restype = ctypes.c_int
+    lib.eccb200_ctx_destroy.argtypes = [ctypes.c_void_p]
+    lib.eccb200_ctx_destroy.restype = None
+    lib.eccb200_curve_sizes.argtypes = [ctypes.c_int, ctypes.POINTER(u32), ctypes.POINTER(u32)]
+    lib.eccb200_curve_name.argtypes = [ctypes.c_int]
+    lib.eccb200_curve_name.restype = ctypes.c_char_p
+    lib.eccb200_prj_pt_mul_batch.argtypes = [ctypes.c_void_p, u32, u8p, u8p, u8p, i8p]
+    lib.eccb200_prj_pt_mul_batch_dev.argtypes = [ctypes.c_void_p, u32, u8p, u8p, u8p, i8p, ctypes.c_void_p]
+    lib.eccb200_ecdsa_verify_batch.argtypes = [ctypes.c_void_p, u32, u8p, u8p, u8p, u32, i8p]
+    lib.eccb200_ecdsa_verify_batch_dev.argtypes = [ctypes.c_void_p, u32, u8p, u8p, u8p, u32, i8p, ctypes.c_void_p]
+    lib.eccb200_fp_mul_monty_batch.argtypes = [ctypes.c_void_p, ctypes.c_int, u32, u8p, u8p, u8p]
+    lib.eccb200_comb_window.argtypes = [ctypes.c_void_p]
+    lib.eccb200_kernel_launches.argtypes = [ctypes.c_void_p]
+    lib.eccb200_kernel_launches.restype = ctypes.c_uint64
+    lib.eccb200_last_error.restype = ctypes.c_char_p
+    _lib = lib
+    return lib
+
+
+def curve_sizes(curve: str) -> Tuple[int, int]:
+    lib = load_library()
+    plen, qlen = ctypes.c_uint32(), ctypes.c_uint32()
+    if lib.eccb200_curve_sizes(CURVE_IDS[curve], ctypes.byref(plen), ctypes.byref(qlen)):
+        raise EccB200Error("unknown curve")
+    return plen.value, qlen.value
+
+
+def _as_u8(a, nbytes: Optional[int] = None) -> np.ndarray:
+    arr = np.frombuffer(a, dtype=np.uint8) if isinstance(a, (bytes, bytearray, memoryview)) else np.asarray(a)
+    arr = np.ascontiguousarray(arr.reshape(-1).view(np.uint8))
+    if nbytes is not None and arr.size != nbytes:
+        raise ValueError(f"expected {nbytes} bytes, got {arr.size}")
+    return arr
+
+
+class Engine:
+    """One engine context = one curve on one GPU (eccb200_ctx)."""
+
+    def __init__(self, curve: str, device: int = 0, comb_window: int = 0):
+        self.lib = load_library()
+        self.curve = curve
+        self.curve_id = CURVE_IDS[curve]
+        self.plen, self.qlen = curve_sizes(curve)
+        self.device = device
+        h = ctypes.c_void_p()
+        if self.lib.eccb200_ctx_create(ctypes.byref(h), self.curve_id, device, comb_window):
+            raise EccB200Error("eccb200_ctx_create: " + self.lib.eccb200_last_error().decode())
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.eccb200_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc:
+            raise EccB200Error(f"{what}: " + self.lib.eccb200_last_error().decode())
+
+    @property
+    def comb_window(self) -> int:
+        return self.lib.eccb200_comb_window(self._h)
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.lib.eccb200_kernel_launches(self._h))
+
+    # ---- host-buffer API (H2D / D2H inside the call) -------------------------------------------------------
+    def prj_pt_mul_batch(self, scalars, points=None) -> Tuple[np.ndarray, np.ndarray]:
+        """scalars: n*qlen big-endian bytes; points: n*2*plen affine bytes or None (=G).
+        Returns (out[n, 2*plen] uint8, status[n] int8)."""
+        sc = _as_u8(scalars)
+        n = sc.size // self.qlen
+        if sc.size != n * self.qlen:
+            raise ValueError("scalars length is not a multiple of qlen")
+        pt = _as_u8(points, n * 2 * self.plen) if points is not None else None
+        out = np.zeros((n, 2 * self.plen), dtype=np.uint8)
+        status = np.zeros(n, dtype=np.int8)
+        self._check(self.lib.eccb200_prj_pt_mul_batch(
+            self._h, n, sc.ctypes.data, pt.ctypes.data if pt is not None else None,
+            out.ctypes.data, status.ctypes.data), "eccb200_prj_pt_mul_batch")
+        return out, status
+
+    def ecdsa_verify_batch(self, sigs, pubkeys, digests, hlen: int) -> np.ndarray:
+        sg = _as_u8(sigs)
+        n = sg.size // (2 * self.qlen)
+        pk = _as_u8(pubkeys, n * 2 * self.plen)
+        dg = _as_u8(digests, n * hlen)
+        verdict = np.zeros(n, dtype=np.int8)
+        self._check(self.lib.eccb200_ecdsa_verify_batch(
+            self._h, n, sg.ctypes.data, pk.ctypes.data, dg.ctypes.data, hlen, verdict.ctypes.data),
+            "eccb200_ecdsa_verify_batch")
+        return verdict
+
+    def fp_mul_monty_batch(self, a, b, which: int = 0) -> np.ndarray:
+        x = _as_u8(a)
+        n = x.size // self.plen
+        y = _as_u8(b, n * self.plen)
+        out = np.zeros((n, self.plen), dtype=np.uint8)
+        self._check(self.lib.eccb200_fp_mul_monty_batch(self._h, which, n, x.ctypes.data, y.ctypes.data,
+                                                        out.ctypes.data), "eccb200_fp_mul_monty_batch")
+        return out
+
+    # ---- device-buffer API (torch uint8/int8 CUDA tensors; asynchronous on torch's current stream) ---------
+    def prj_pt_mul_batch_dev(self, d_scalars, d_points, d_out, d_status, stream_handle: int = 0):
+        n = d_scalars.numel() // self.qlen
+        self._check(self.lib.eccb200_prj_pt_mul_batch_dev(
+            self._h, n, d_scalars.data_ptr(), d_points.data_ptr() if d_points is not None else None,
+            d_out.data_ptr(), d_status.data_ptr(), ctypes.c_void_p(stream_handle)), "eccb200_prj_pt_mul_batch_dev")
+
+    def ecdsa_verify_batch_dev(self, d_sigs, d_pubkeys, d_digests, hlen: int, d_verdict, stream_handle: int = 0):
+        n = d_sigs.numel() // (2 * self.qlen)
+        self._check(self.lib.eccb200_ecdsa_verify_batch_dev(
+            self._h, n, d_sigs.data_ptr(), d_pubkeys.data_ptr(), d_digests.data_ptr(), hlen,
+            d_verdict.data_ptr(), ctypes.c_void_p(stream_handle)), "eccb200_ecdsa_verify_batch_dev")

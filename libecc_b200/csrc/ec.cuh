@@ -1,0 +1,455 @@
+/*
+ * ec.cuh — short-Weierstrass group law on the device (replaces the reference's src/curves/prj_pt.c hot path).
+ *
+ * The reference computes prj_pt_mul with a masked Montgomery ladder over the Renes-Costello-Batina complete
+ * addition in homogeneous projective coordinates (curves/prj_pt.c:971-1071, :1569-1720): 513 complete additions
+ * = 8 724 field multiplications per 256-bit scalar.  Its result is only defined up to the projective class (the
+ * input is blinded with a random lambda, :1266-1291), i.e. by the affine point.  The device is therefore free
+ * to use a different algorithm as long as the affine output / infinity flag / error code agree:
+ *
+ *   - Jacobian coordinates (X/Z^2, Y/Z^3), a = -3 doubling (dbl-2001-b, 3M+5S), general add (12M+4S) and mixed
+ *     add with an affine operand (8M+3S);
+ *   - every exceptional case of the incomplete formulas is handled explicitly (P = inf, Q = inf, P = Q -> double,
+ *     P = -Q -> inf), so the result is the group-law result for ALL inputs, like the reference's complete formulas;
+ *   - fixed base (k*G): comb over a precomputed affine table T[i][d] = d * 2^(w*i) * G, one mixed add per
+ *     window, no doublings (K1);
+ *   - variable base (k*P): signed 4-bit fixed window, 8-entry Jacobian table per thread (K2).
+ *
+ * All three target curves have a = p - 3 (curves/known/ec_params_secp256r1.h:78-83, ..._frp256v1.h:84-89,
+ * ..._secp384r1.h); tools/gen_curve_constants.py asserts it.
+ */
+#pragma once
+#include "fp.cuh"
+
+namespace eccb200 {
+
+template <class C> struct Jac {
+	Fe<C::N> X, Y, Z; /* Z == 0 <=> point at infinity (prj_pt_iszero, curves/prj_pt.c:107) */
+};
+
+template <class C> struct Aff {
+	Fe<C::N> x, y; /* Montgomery form */
+};
+
+template <class C> struct EC {
+	static constexpr int N = C::N;
+	typedef Field<typename C::Fp> F;
+	typedef Fe<N> E;
+	typedef Jac<C> J;
+	typedef Aff<C> A;
+
+	static ECC_HD void set_inf(J &p)
+	{
+		F::set_one(p.X);
+		F::set_one(p.Y);
+		F::set_zero(p.Z);
+	}
+	static ECC_HD bool is_inf(const J &p) { return F::is_zero(p.Z); }
+
+	static ECC_HD void from_affine(J &p, const A &a)
+	{
+		p.X = a.x;
+		p.Y = a.y;
+		F::set_one(p.Z);
+	}
+
+	/* y^2 == x^3 - 3x + b (all Montgomery form); affine form of prj_pt_is_on_curve (curves/prj_pt.c:144-190) */
+	static ECC_HD bool on_curve(const A &a)
+	{
+		E t, u, b;
+		F::sqr(t, a.x);
+		F::mul(u, t, a.x);      /* x^3 */
+		F::add(t, a.x, a.x);
+		F::add(t, t, a.x);      /* 3x */
+		F::sub(u, u, t);
+#pragma unroll
+		for (int i = 0; i < N; i++) b.w[i] = C::B_MONT(i);
+		F::add(u, u, b);
+		F::sqr(t, a.y);
+		return F::eq(t, u);
+	}
+
+	/* Out-of-line copy of dbl for the exceptional (P == Q) branches of the additions: keeps the rarely taken
+	 * path from being inlined into every hot loop. */
+	static ECC_NOINLINE void dbl_slow(J &r, const J &p) { dbl(r, p); }
+
+	/* Jacobian doubling for a = -3 (dbl-2001-b): 3M + 5S.  inf -> inf (Z3 = 0).  r may alias p. */
+	static ECC_HD void dbl(J &r, const J &p)
+	{
+		E delta, gamma, beta, alpha, t0, t1;
+		F::sqr(delta, p.Z);
+		F::sqr(gamma, p.Y);
+		F::mul(beta, p.X, gamma);
+		F::sub(t0, p.X, delta);
+		F::add(t1, p.X, delta);
+		F::mul(alpha, t0, t1);
+		F::add(t0, alpha, alpha);
+		F::add(alpha, t0, alpha); /* 3 (X-delta)(X+delta) */
+		F::add(t1, p.Y, p.Z);
+		F::sqr(t0, t1);
+		F::sub(t0, t0, gamma);
+		F::sub(r.Z, t0, delta);   /* Z3 = (Y+Z)^2 - gamma - delta */
+		F::add(t0, beta, beta);
+		F::add(t0, t0, t0);       /* 4 beta */
+		F::add(t1, t0, t0);       /* 8 beta */
+		F::sqr(r.X, alpha);
+		F::sub(r.X, r.X, t1);     /* X3 = alpha^2 - 8 beta */
+		F::sub(t0, t0, r.X);
+		F::mul(t1, alpha, t0);
+		F::sqr(t0, gamma);
+		F::add(t0, t0, t0);
+		F::add(t0, t0, t0);
+		F::add(t0, t0, t0);       /* 8 gamma^2 */
+		F::sub(r.Y, t1, t0);
+	}
+
+	/*
+	 * r = p + q, q affine (Z2 = 1): 8M + 3S.  Exceptional cases resolved explicitly so that the result equals the
+	 * group law for every input, matching what prj_pt_add's complete formulas give (curves/prj_pt.c:1204).
+	 */
+	static ECC_HD void add_mixed(J &r, const J &p, const A &q)
+	{
+		E z1z1, u2, s2, h, rr, hh, hhh, v, t;
+		F::sqr(z1z1, p.Z);
+		F::mul(u2, q.x, z1z1);
+		F::mul(t, q.y, p.Z);
+		F::mul(s2, t, z1z1);
+		F::sub(h, u2, p.X);
+		F::sub(rr, s2, p.Y);
+		bool p_inf = F::is_zero(p.Z);
+		bool h0 = F::is_zero(h);
+		if (p_inf) {
+			from_affine(r, q);
+			return;
+		}
+		if (h0) {
+			if (F::is_zero(rr)) {
+				J qq;
+				from_affine(qq, q);
+				dbl_slow(r, qq);
+			} else {
+				set_inf(r);
+			}
+			return;
+		}
+		F::sqr(hh, h);
+		F::mul(hhh, h, hh);
+		F::mul(v, p.X, hh);
+		E x3, y3, z3;
+		F::sqr(x3, rr);
+		F::sub(x3, x3, hhh);
+		F::sub(x3, x3, v);
+		F::sub(x3, x3, v);
+		F::sub(t, v, x3);
+		F::mul(y3, rr, t);
+		F::mul(t, p.Y, hhh);
+		F::sub(y3, y3, t);
+		F::mul(z3, p.Z, h);
+		r.X = x3;
+		r.Y = y3;
+		r.Z = z3;
+	}
+
+	/* r = p + q, both Jacobian (add-1998-cmo-2): 12M + 4S, exceptional cases resolved explicitly. */
+	static ECC_HD void add_full(J &r, const J &p, const J &q)
+	{
+		E z1z1, z2z2, u1, u2, s1, s2, h, rr, hh, hhh, v, t;
+		F::sqr(z1z1, p.Z);
+		F::sqr(z2z2, q.Z);
+		F::mul(u1, p.X, z2z2);
+		F::mul(u2, q.X, z1z1);
+		F::mul(t, p.Y, q.Z);
+		F::mul(s1, t, z2z2);
+		F::mul(t, q.Y, p.Z);
+		F::mul(s2, t, z1z1);
+		F::sub(h, u2, u1);
+		F::sub(rr, s2, s1);
+		bool p_inf = F::is_zero(p.Z), q_inf = F::is_zero(q.Z);
+		if (p_inf) {
+			r = q;
+			return;
+		}
+		if (q_inf) {
+			r = p;
+			return;
+		}
+		if (F::is_zero(h)) {
+			if (F::is_zero(rr)) {
+				J pp = p;
+				dbl_slow(r, pp);
+			} else {
+				set_inf(r);
+			}
+			return;
+		}
+		F::sqr(hh, h);
+		F::mul(hhh, h, hh);
+		F::mul(v, u1, hh);
+		E x3, y3, z3;
+		F::sqr(x3, rr);
+		F::sub(x3, x3, hhh);
+		F::sub(x3, x3, v);
+		F::sub(x3, x3, v);
+		F::sub(t, v, x3);
+		F::mul(y3, rr, t);
+		F::mul(t, s1, hhh);
+		F::sub(y3, y3, t);
+		F::mul(t, p.Z, q.Z);
+		F::mul(z3, t, h);
+		r.X = x3;
+		r.Y = y3;
+		r.Z = z3;
+	}
+
+	/* out-of-line copy for once-per-item uses (e.g. the final uG + vY of a verification) */
+	static ECC_NOINLINE void add_full_slow(J &r, const J &p, const J &q) { add_full(r, p, q); }
+
+	static ECC_HD void neg(J &r, const J &p)
+	{
+		r.X = p.X;
+		r.Z = p.Z;
+		F::neg(r.Y, p.Y);
+	}
+};
+
+/* ---------------------------------------------------------------------------------------------- wire format */
+
+/* big-endian bytes (libecc wire format, nn_init_from_buf nn/nn.c:479) -> N little-endian 32-bit words */
+template <int N> ECC_HD void load_be(Fe<N> &r, const uint8_t *buf)
+{
+#pragma unroll
+	for (int i = 0; i < N; i++) {
+		const uint8_t *b = buf + 4 * (N - 1 - i);
+		r.w[i] = ((uint32_t)b[0] << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | (uint32_t)b[3];
+	}
+}
+
+/* nn_export_to_buf (nn/nn.c:511) */
+template <int N> ECC_HD void store_be(uint8_t *buf, const Fe<N> &a)
+{
+#pragma unroll
+	for (int i = 0; i < N; i++) {
+		uint8_t *b = buf + 4 * (N - 1 - i);
+		uint32_t v = a.w[i];
+		b[0] = (uint8_t)(v >> 24);
+		b[1] = (uint8_t)(v >> 16);
+		b[2] = (uint8_t)(v >> 8);
+		b[3] = (uint8_t)v;
+	}
+}
+
+/* ---------------------------------------------------------------------------------------------- scalars */
+
+/* Reduce a raw N-word scalar modulo q (all target curves have 2^(32N) < 2q, but loop to be general: the
+ * reference's ladder yields (k mod q)*P for any k, curves/prj_pt.c:1591-1619). */
+template <class C> ECC_HD void scalar_reduce(Fe<C::N> &k)
+{
+	typedef Field<typename C::Fq> Fq;
+	for (int it = 0; it < 4; it++) Fq::cond_sub_mod(k, k);
+}
+
+/* w-bit unsigned digit i of k (bits [w*i, w*i+w)), w <= 16 */
+template <int N> ECC_HD uint32_t comb_digit(const Fe<N> &k, int i, int w)
+{
+	int bit = i * w;
+	int wi = bit >> 5, sh = bit & 31;
+	uint32_t lo = 0, hi = 0;
+#pragma unroll
+	for (int j = 0; j < N; j++) {
+		lo = (j == wi) ? k.w[j] : lo;
+		hi = (j == wi + 1) ? k.w[j] : hi;
+	}
+	uint64_t v = ((uint64_t)hi << 32) | lo;
+	return (uint32_t)(v >> sh) & ((1u << w) - 1u);
+}
+
+/*
+ * Fixed-base comb: acc = sum_i T[i][digit_i(k)],  T[i][d] = d * 2^(w*i) * G  (affine, Montgomery form, entry
+ * (i << w) + d; d == 0 unused).  One mixed addition per non-zero window, no doublings.  k must be < q.
+ * For k < q the accumulator before window i is (k mod 2^(w*i))*G with 0 <= k mod 2^(w*i) < 2^(w*i) <= d*2^(w*i) < q,
+ * so the add never meets P = +-Q; add_mixed resolves those cases anyway.
+ */
+template <class C> ECC_HD void load_table_entry(Aff<C> &t, const uint32_t *__restrict__ table, size_t e)
+{
+	constexpr int N = C::N;
+	const uint32_t *base = table + e * (2 * N);
+#if defined(__CUDA_ARCH__)
+	const uint4 *src = reinterpret_cast<const uint4 *>(base);
+#pragma unroll
+	for (int j = 0; j < N / 4; j++) {
+		uint4 v = __ldg(src + j);
+		t.x.w[4 * j] = v.x;
+		t.x.w[4 * j + 1] = v.y;
+		t.x.w[4 * j + 2] = v.z;
+		t.x.w[4 * j + 3] = v.w;
+	}
+#pragma unroll
+	for (int j = 0; j < N / 4; j++) {
+		uint4 v = __ldg(src + N / 4 + j);
+		t.y.w[4 * j] = v.x;
+		t.y.w[4 * j + 1] = v.y;
+		t.y.w[4 * j + 2] = v.z;
+		t.y.w[4 * j + 3] = v.w;
+	}
+#else
+	for (int j = 0; j < N; j++) {
+		t.x.w[j] = base[j];
+		t.y.w[j] = base[N + j];
+	}
+#endif
+}
+
+template <class C> ECC_HD void comb_mul(Jac<C> &acc, const Fe<C::N> &k, const uint32_t *__restrict__ table, int w)
+{
+	typedef EC<C> G;
+	constexpr int N = C::N;
+	G::set_inf(acc);
+	const int nwin = (C::QBITS + w - 1) / w;
+#pragma unroll 1
+	for (int i = 0; i < nwin; i++) {
+		uint32_t d = comb_digit<N>(k, i, w);
+		if (d != 0) {
+			Aff<C> t;
+			load_table_entry<C>(t, table, ((size_t)i << w) + d);
+			Jac<C> r;
+			G::add_mixed(r, acc, t);
+			acc = r;
+		}
+	}
+}
+
+/*
+ * Variable base: acc = k*P, P affine and on the curve, k < q.  Signed 4-bit fixed window:
+ * K' = k + 0x88..8 (one 8 per nibble); digit_i = nibble_i(K') - 8 in [-8, 7] for i < 2N*... , top digit = carry.
+ * Table tbl[j] = (j+1)*P, j = 0..7 (Jacobian).
+ */
+template <class C> ECC_HD void window_mul(Jac<C> &acc, const Fe<C::N> &k, const Aff<C> &P)
+{
+	typedef EC<C> G;
+	typedef Field<typename C::Fp> F;
+	constexpr int N = C::N;
+	Jac<C> tbl[8];
+	G::from_affine(tbl[0], P);
+#pragma unroll 1
+	for (int j = 1; j < 8; j++) G::add_mixed(tbl[j], tbl[j - 1], P); /* j == 1 takes the P == Q (doubling) branch */
+
+	/* K' = k + 0x8888...8 with carry-out */
+	uint32_t kk[N];
+	uint64_t c = 0;
+#pragma unroll
+	for (int i = 0; i < N; i++) {
+		uint64_t s = (uint64_t)k.w[i] + 0x88888888u + c;
+		kk[i] = (uint32_t)s;
+		c = s >> 32;
+	}
+	G::set_inf(acc);
+	if (c) acc = tbl[0]; /* top digit (weight 16^(8N)) is 0 or 1 */
+#pragma unroll 1
+	for (int wi = N - 1; wi >= 0; wi--) {
+		uint32_t word = 0;
+#pragma unroll
+		for (int j = 0; j < N; j++) word = (j == wi) ? kk[j] : word;
+#pragma unroll 1
+		for (int nb = 7; nb >= 0; nb--) {
+			Jac<C> t;
+#pragma unroll 1
+			for (int q = 0; q < 4; q++) G::dbl(acc, acc);
+			int d = (int)((word >> (4 * nb)) & 15u) - 8;
+			if (d != 0) {
+				int ad = d < 0 ? -d : d;
+				Jac<C> e = tbl[ad - 1];
+				if (d < 0) F::neg(e.Y, e.Y);
+				G::add_full(t, acc, e);
+				acc = t;
+			}
+		}
+	}
+}
+
+/* ---------------------------------------------------------------------------------------------- ECDSA */
+
+/*
+ * e = leftmost min(8*hlen, bitlen(q)) bits of the digest as an integer, reduced mod q:
+ * steps 3-4 of __ecdsa_verify_finalize (sig/ecdsa_common.c:760-777).  Byte loads: hlen is arbitrary.
+ */
+template <class C> ECC_HD void digest_to_scalar(Fe<C::N> &e, const uint8_t *h, uint32_t hlen)
+{
+	constexpr int N = C::N;
+	uint32_t qbytes = (C::QBITS + 7) / 8;
+	uint32_t take = hlen < qbytes ? hlen : qbytes;
+#pragma unroll
+	for (int i = 0; i < N; i++) e.w[i] = 0;
+	for (uint32_t i = 0; i < take; i++) {
+		uint32_t pos = take - 1 - i; /* byte significance */
+		uint32_t v = (uint32_t)h[i] << (8 * (pos & 3));
+#pragma unroll
+		for (int j = 0; j < N; j++) e.w[j] |= (j == (int)(pos >> 2)) ? v : 0u;
+	}
+	int sh = (int)(8 * take) - C::QBITS; /* > 0 only when bitlen(q) is not a multiple of 8 */
+	if (sh > 0) {
+#pragma unroll
+		for (int j = 0; j < N; j++) {
+			uint32_t hi = (j + 1 < N) ? e.w[j + 1] : 0u;
+			e.w[j] = (e.w[j] >> sh) | (hi << (32 - sh));
+		}
+	}
+	scalar_reduce<C>(e);
+}
+
+/*
+ * ECDSA verification of one signature (r, s) on the reduced digest e under the public key Y (affine, validated,
+ * Montgomery form).  Follows __ecdsa_verify_init's range checks (sig/ecdsa_common.c:653-658) and
+ * __ecdsa_verify_finalize steps 5-10 (:781-810); differences that do not change the verdict:
+ *   - s^-1 mod q by Fermat in the Montgomery domain of q instead of nn_modinv's xgcd (:781);
+ *   - W' = uG + vY stays Jacobian and "x(W') mod q == r" is tested without an inversion as X == c * Z^2 for the
+ *     candidates c in {r, r+q} that are < p (:803-810);
+ *   - uG through the comb table (K1), vY through the signed window (K2) instead of two ladders (:788,793).
+ */
+template <class C>
+ECC_HD bool ecdsa_verify_core(const Fe<C::N> &r, const Fe<C::N> &s, const Fe<C::N> &e, const Aff<C> &Y,
+			      const uint32_t *__restrict__ table, int w)
+{
+	typedef Field<typename C::Fp> F;
+	typedef Field<typename C::Fq> Fq;
+	constexpr int N = C::N;
+	if (Fq::is_zero(r) || Fq::is_zero(s) || Fq::geq_mod(r) || Fq::geq_mod(s)) return false;
+
+	Fe<N> sm, wm, u, v;
+	Fq::to_mont(sm, s);
+	Fq::inv(wm, sm);   /* s^-1 * R mod q */
+	Fq::mul(u, e, wm); /* u = e * s^-1 mod q, plain form  (:786) */
+	Fq::mul(v, r, wm); /* v = r * s^-1 mod q, plain form  (:791) */
+
+	Jac<C> uG, vY, W;
+	comb_mul<C>(uG, u, table, w);
+	window_mul<C>(vY, v, Y);
+	EC<C>::add_full_slow(W, uG, vY);
+	if (EC<C>::is_inf(W)) return false; /* (:799-800) */
+
+	Fe<N> z2, c, t;
+	F::sqr(z2, W.Z);
+	bool match = false;
+	if (!F::geq_mod(r)) { /* candidate x = r */
+		F::to_mont(c, r);
+		F::mul(t, c, z2);
+		match = F::eq(t, W.X);
+	}
+	{ /* candidate x = r + q, when it is still a field element */
+		Fe<N> rq;
+		uint64_t cy = 0;
+#pragma unroll
+		for (int i = 0; i < N; i++) {
+			uint64_t sum = (uint64_t)r.w[i] + C::Fq::P(i) + cy;
+			rq.w[i] = (uint32_t)sum;
+			cy = sum >> 32;
+		}
+		if (cy == 0 && !F::geq_mod(rq)) {
+			F::to_mont(c, rq);
+			F::mul(t, c, z2);
+			match = match || F::eq(t, W.X);
+		}
+	}
+	return match;
+}
+
+} // namespace eccb200

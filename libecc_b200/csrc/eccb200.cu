@@ -1,0 +1,376 @@
+/*
+ * eccb200.cu — C-ABI implementation (include/libecc_b200.h): context management, kernel dispatch, and the
+ * chunked host<->device pipeline of the host-pointer entry points.  No arithmetic happens on the host.
+ */
+#include "../../include/libecc_b200.h"
+#include "kernels.cuh"
+
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace eccb200;
+
+static thread_local std::string g_err;
+static int fail(const std::string &m)
+{
+	g_err = m;
+	return -1;
+}
+#define CUDA_OK(expr)                                                                                      \
+	do {                                                                                               \
+		cudaError_t e_ = (expr);                                                                   \
+		if (e_ != cudaSuccess)                                                                     \
+			return fail(std::string(#expr) + ": " + cudaGetErrorString(e_));                   \
+	} while (0)
+
+extern "C" const char *eccb200_last_error(void) { return g_err.c_str(); }
+
+static const uint32_t kChunk = 1u << 18; /* items per pipeline stage of the host-pointer API */
+static const int kStages = 3;
+
+struct eccb200_ctx {
+	int curve_id = 0;
+	int device = 0;
+	int N = 0;           /* 32-bit words per element */
+	uint32_t plen = 0, qlen = 0;
+	int w = 0;           /* comb window */
+	int nwin = 0;
+	int sm_count = 0;
+	uint32_t *table = nullptr;
+	/* work buffers (grown on demand) */
+	uint32_t cap = 0;
+	uint32_t *jac = nullptr;
+	uint32_t *prefix = nullptr;
+	/* host-pointer pipeline */
+	cudaStream_t streams[kStages] = { nullptr, nullptr, nullptr };
+	uint8_t *h_in[kStages] = { nullptr, nullptr, nullptr };   /* pinned */
+	uint8_t *h_out[kStages] = { nullptr, nullptr, nullptr };  /* pinned */
+	uint8_t *d_in[kStages] = { nullptr, nullptr, nullptr };
+	uint8_t *d_out[kStages] = { nullptr, nullptr, nullptr };
+	size_t stage_in_bytes = 0, stage_out_bytes = 0;
+	uint32_t *stage_jac[kStages] = { nullptr, nullptr, nullptr };
+	uint32_t *stage_prefix[kStages] = { nullptr, nullptr, nullptr };
+	uint64_t launches = 0;
+};
+
+template <class Fn> static int dispatch(int curve_id, Fn &&fn)
+{
+	switch (curve_id) {
+	case ECCB200_SECP256R1: return fn(Curve_SECP256R1());
+	case ECCB200_FRP256V1: return fn(Curve_FRP256V1());
+	case ECCB200_SECP384R1: return fn(Curve_SECP384R1());
+	default: return fail("unknown curve id");
+	}
+}
+
+extern "C" int eccb200_curve_sizes(int curve_id, uint32_t *plen, uint32_t *qlen)
+{
+	return dispatch(curve_id, [&](auto c) {
+		typedef decltype(c) C;
+		*plen = C::PLEN;
+		*qlen = C::QLEN;
+		return 0;
+	});
+}
+
+extern "C" const char *eccb200_curve_name(int curve_id)
+{
+	const char *n = nullptr;
+	dispatch(curve_id, [&](auto c) {
+		n = decltype(c)::name();
+		return 0;
+	});
+	return n;
+}
+
+/* threads for the batched normalisation: enough to fill the machine, few enough that every thread amortises its
+ * inversion over many items */
+static uint32_t affine_grid(const eccb200_ctx *ctx, uint32_t n)
+{
+	uint32_t want = grid_for(n);
+	uint32_t cap = (uint32_t)ctx->sm_count * 4u; /* 4 CTAs of 128 threads per SM */
+	return std::max(1u, std::min(want, cap));
+}
+
+static int ensure_work(eccb200_ctx *ctx, uint32_t n)
+{
+	if (n <= ctx->cap) return 0;
+	if (ctx->jac) cudaFree(ctx->jac);
+	if (ctx->prefix) cudaFree(ctx->prefix);
+	ctx->jac = ctx->prefix = nullptr;
+	ctx->cap = 0;
+	CUDA_OK(cudaMalloc(&ctx->jac, (size_t)n * 3 * ctx->N * sizeof(uint32_t)));
+	CUDA_OK(cudaMalloc(&ctx->prefix, (size_t)n * ctx->N * sizeof(uint32_t)));
+	ctx->cap = n;
+	return 0;
+}
+
+extern "C" int eccb200_ctx_create(eccb200_ctx **out, int curve_id, int device, int comb_window)
+{
+	if (!out) return fail("null ctx pointer");
+	*out = nullptr;
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+		return fail("no CUDA device: libecc_b200 has no CPU fallback");
+	if (device < 0 || device >= ndev) return fail("bad device index");
+	CUDA_OK(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	CUDA_OK(cudaGetDeviceProperties(&prop, device));
+	if (prop.major != 10) return fail("libecc_b200 is built for sm_100a (B200) only");
+	int w = comb_window ? comb_window : 16;
+	if (w < 4 || w > 16) return fail("comb_window must be in [4,16]");
+
+	eccb200_ctx *ctx = new eccb200_ctx();
+	ctx->curve_id = curve_id;
+	ctx->device = device;
+	ctx->w = w;
+	ctx->sm_count = prop.multiProcessorCount;
+	int rc = dispatch(curve_id, [&](auto c) {
+		typedef decltype(c) C;
+		ctx->N = C::N;
+		ctx->plen = C::PLEN;
+		ctx->qlen = C::QLEN;
+		ctx->nwin = (C::QBITS + w - 1) / w;
+		uint32_t entries = (uint32_t)ctx->nwin << w;
+		CUDA_OK(cudaMalloc(&ctx->table, (size_t)entries * 2 * C::N * sizeof(uint32_t)));
+		if (ensure_work(ctx, entries)) return -1;
+		LaunchSmul<C>::table_points(entries, w, ctx->jac, 0);
+		LaunchMisc<C>::to_table(affine_grid(ctx, entries), entries, ctx->jac, ctx->prefix, ctx->table, 0);
+		ctx->launches += 2;
+		CUDA_OK(cudaGetLastError());
+		CUDA_OK(cudaDeviceSynchronize());
+		return 0;
+	});
+	if (rc) {
+		eccb200_ctx_destroy(ctx);
+		return -1;
+	}
+	for (int s = 0; s < kStages; s++) {
+		if (cudaStreamCreateWithFlags(&ctx->streams[s], cudaStreamNonBlocking) != cudaSuccess) {
+			eccb200_ctx_destroy(ctx);
+			return fail("cudaStreamCreate failed");
+		}
+	}
+	*out = ctx;
+	return 0;
+}
+
+extern "C" void eccb200_ctx_destroy(eccb200_ctx *ctx)
+{
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaDeviceSynchronize();
+	for (int s = 0; s < kStages; s++) {
+		if (ctx->streams[s]) cudaStreamDestroy(ctx->streams[s]);
+		if (ctx->h_in[s]) cudaFreeHost(ctx->h_in[s]);
+		if (ctx->h_out[s]) cudaFreeHost(ctx->h_out[s]);
+		if (ctx->d_in[s]) cudaFree(ctx->d_in[s]);
+		if (ctx->d_out[s]) cudaFree(ctx->d_out[s]);
+		if (ctx->stage_jac[s]) cudaFree(ctx->stage_jac[s]);
+		if (ctx->stage_prefix[s]) cudaFree(ctx->stage_prefix[s]);
+	}
+	if (ctx->table) cudaFree(ctx->table);
+	if (ctx->jac) cudaFree(ctx->jac);
+	if (ctx->prefix) cudaFree(ctx->prefix);
+	delete ctx;
+}
+
+extern "C" int eccb200_comb_window(const eccb200_ctx *ctx) { return ctx ? ctx->w : -1; }
+extern "C" uint64_t eccb200_kernel_launches(const eccb200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+/* ------------------------------------------------------------------------------------------ device-pointer API */
+
+static int smul_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_scalars, const uint8_t *d_points, uint8_t *d_out,
+		    int8_t *d_status, uint32_t *jac, uint32_t *prefix, cudaStream_t st)
+{
+	if (n == 0) return 0;
+	return dispatch(ctx->curve_id, [&](auto c) {
+		typedef decltype(c) C;
+		if (d_points)
+			LaunchSmul<C>::var(n, d_scalars, d_points, jac, d_status, st);
+		else
+			LaunchSmul<C>::fixed(n, d_scalars, ctx->table, ctx->w, jac, d_status, st);
+		LaunchMisc<C>::to_affine(affine_grid(ctx, n), n, jac, prefix, d_out, d_status, st);
+		ctx->launches += 2;
+		CUDA_OK(cudaGetLastError());
+		return 0;
+	});
+}
+
+extern "C" int eccb200_prj_pt_mul_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_scalars,
+					    const uint8_t *d_points, uint8_t *d_out, int8_t *d_status, void *stream)
+{
+	if (!ctx || (n && (!d_scalars || !d_out || !d_status))) return fail("null argument");
+	CUDA_OK(cudaSetDevice(ctx->device));
+	if (ensure_work(ctx, n)) return -1;
+	return smul_dev(ctx, n, d_scalars, d_points, d_out, d_status, ctx->jac, ctx->prefix, (cudaStream_t)stream);
+}
+
+static int verify_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_sigs, const uint8_t *d_pubkeys,
+		      const uint8_t *d_digests, uint32_t hlen, int8_t *d_verdict, cudaStream_t st)
+{
+	if (n == 0) return 0;
+	return dispatch(ctx->curve_id, [&](auto c) {
+		typedef decltype(c) C;
+		LaunchVerify<C>::verify(n, d_sigs, d_pubkeys, d_digests, hlen, ctx->table, ctx->w, d_verdict, st);
+		ctx->launches += 1;
+		CUDA_OK(cudaGetLastError());
+		return 0;
+	});
+}
+
+extern "C" int eccb200_ecdsa_verify_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_sigs,
+					      const uint8_t *d_pubkeys, const uint8_t *d_digests, uint32_t hlen,
+					      int8_t *d_verdict, void *stream)
+{
+	if (!ctx || (n && (!d_sigs || !d_pubkeys || !d_digests || !d_verdict))) return fail("null argument");
+	if (hlen == 0 || hlen > 128) return fail("bad digest length");
+	CUDA_OK(cudaSetDevice(ctx->device));
+	return verify_dev(ctx, n, d_sigs, d_pubkeys, d_digests, hlen, d_verdict, (cudaStream_t)stream);
+}
+
+/* ------------------------------------------------------------------------------------------ host-pointer API */
+
+static int ensure_stages(eccb200_ctx *ctx, size_t in_bytes, size_t out_bytes)
+{
+	if (in_bytes <= ctx->stage_in_bytes && out_bytes <= ctx->stage_out_bytes && ctx->stage_jac[0]) return 0;
+	size_t ib = std::max(in_bytes, ctx->stage_in_bytes), ob = std::max(out_bytes, ctx->stage_out_bytes);
+	for (int s = 0; s < kStages; s++) {
+		if (ctx->h_in[s]) cudaFreeHost(ctx->h_in[s]);
+		if (ctx->h_out[s]) cudaFreeHost(ctx->h_out[s]);
+		if (ctx->d_in[s]) cudaFree(ctx->d_in[s]);
+		if (ctx->d_out[s]) cudaFree(ctx->d_out[s]);
+		ctx->h_in[s] = ctx->h_out[s] = ctx->d_in[s] = ctx->d_out[s] = nullptr;
+		CUDA_OK(cudaMallocHost(&ctx->h_in[s], ib));
+		CUDA_OK(cudaMallocHost(&ctx->h_out[s], ob));
+		CUDA_OK(cudaMalloc(&ctx->d_in[s], ib));
+		CUDA_OK(cudaMalloc(&ctx->d_out[s], ob));
+		if (!ctx->stage_jac[s]) {
+			CUDA_OK(cudaMalloc(&ctx->stage_jac[s], (size_t)kChunk * 3 * ctx->N * sizeof(uint32_t)));
+			CUDA_OK(cudaMalloc(&ctx->stage_prefix[s], (size_t)kChunk * ctx->N * sizeof(uint32_t)));
+		}
+	}
+	ctx->stage_in_bytes = ib;
+	ctx->stage_out_bytes = ob;
+	return 0;
+}
+
+/*
+ * Generic chunked pipeline: chunk c uses stage c % kStages: memcpy into pinned -> H2D -> kernels -> D2H -> memcpy
+ * out.  With kStages streams the copies of one chunk overlap the kernels of another.
+ * in_item / out_item: bytes per item in the staged input / output records.
+ */
+template <class Pack, class Launch, class Unpack>
+static int run_pipeline(eccb200_ctx *ctx, uint32_t n, size_t in_item, size_t out_item, Pack pack, Launch launch,
+			Unpack unpack)
+{
+	CUDA_OK(cudaSetDevice(ctx->device));
+	if (ensure_stages(ctx, (size_t)kChunk * in_item, (size_t)kChunk * out_item)) return -1;
+	uint32_t nchunks = (n + kChunk - 1) / kChunk;
+	std::vector<uint32_t> pending_lo(kStages, 0), pending_cnt(kStages, 0);
+	for (uint32_t c = 0; c < nchunks + kStages; c++) {
+		int s = (int)(c % kStages);
+		/* retire what this stage was doing */
+		if (pending_cnt[s]) {
+			CUDA_OK(cudaStreamSynchronize(ctx->streams[s]));
+			unpack(ctx->h_out[s], pending_lo[s], pending_cnt[s]);
+			pending_cnt[s] = 0;
+		}
+		if (c >= nchunks) continue;
+		uint32_t lo = c * kChunk, cnt = std::min(kChunk, n - lo);
+		pack(ctx->h_in[s], lo, cnt);
+		CUDA_OK(cudaMemcpyAsync(ctx->d_in[s], ctx->h_in[s], (size_t)cnt * in_item, cudaMemcpyHostToDevice,
+					ctx->streams[s]));
+		if (launch(s, cnt)) return -1;
+		CUDA_OK(cudaMemcpyAsync(ctx->h_out[s], ctx->d_out[s], (size_t)cnt * out_item, cudaMemcpyDeviceToHost,
+					ctx->streams[s]));
+		pending_lo[s] = lo;
+		pending_cnt[s] = cnt;
+	}
+	return 0;
+}
+
+extern "C" int eccb200_prj_pt_mul_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *scalars, const uint8_t *points,
+					uint8_t *out, int8_t *status)
+{
+	if (!ctx || (n && (!scalars || !out || !status))) return fail("null argument");
+	const size_t sl = ctx->qlen, pl = 2 * (size_t)ctx->plen;
+	/* staged input record layout per chunk: [cnt][qlen] scalars, then [cnt][2*plen] points (if any);
+	 * staged output: [cnt][2*plen] affine, then [cnt] status */
+	const size_t in_item = sl + (points ? pl : 0), out_item = pl + 1;
+	return run_pipeline(
+		ctx, n, in_item, out_item,
+		[&](uint8_t *h, uint32_t lo, uint32_t cnt) {
+			memcpy(h, scalars + (size_t)lo * sl, (size_t)cnt * sl);
+			if (points) memcpy(h + (size_t)cnt * sl, points + (size_t)lo * pl, (size_t)cnt * pl);
+		},
+		[&](int s, uint32_t cnt) {
+			const uint8_t *d_sc = ctx->d_in[s];
+			const uint8_t *d_pt = points ? ctx->d_in[s] + (size_t)cnt * sl : nullptr;
+			uint8_t *d_o = ctx->d_out[s];
+			int8_t *d_st = (int8_t *)(ctx->d_out[s] + (size_t)cnt * pl);
+			return smul_dev(ctx, cnt, d_sc, d_pt, d_o, d_st, ctx->stage_jac[s], ctx->stage_prefix[s],
+					ctx->streams[s]);
+		},
+		[&](const uint8_t *h, uint32_t lo, uint32_t cnt) {
+			memcpy(out + (size_t)lo * pl, h, (size_t)cnt * pl);
+			memcpy(status + lo, h + (size_t)cnt * pl, cnt);
+		});
+}
+
+extern "C" int eccb200_ecdsa_verify_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys,
+					  const uint8_t *digests, uint32_t hlen, int8_t *verdict)
+{
+	if (!ctx || (n && (!sigs || !pubkeys || !digests || !verdict))) return fail("null argument");
+	if (hlen == 0 || hlen > 128) return fail("bad digest length");
+	const size_t sg = 2 * (size_t)ctx->qlen, pk = 2 * (size_t)ctx->plen;
+	/* the digest block goes last: it is the only one whose item size need not be a multiple of 16 */
+	const size_t in_item = sg + pk + hlen, out_item = 1;
+	return run_pipeline(
+		ctx, n, in_item, out_item,
+		[&](uint8_t *h, uint32_t lo, uint32_t cnt) {
+			memcpy(h, sigs + (size_t)lo * sg, (size_t)cnt * sg);
+			memcpy(h + (size_t)cnt * sg, pubkeys + (size_t)lo * pk, (size_t)cnt * pk);
+			memcpy(h + (size_t)cnt * (sg + pk), digests + (size_t)lo * hlen, (size_t)cnt * hlen);
+		},
+		[&](int s, uint32_t cnt) {
+			const uint8_t *d = ctx->d_in[s];
+			return verify_dev(ctx, cnt, d, d + (size_t)cnt * sg, d + (size_t)cnt * (sg + pk), hlen,
+					  (int8_t *)ctx->d_out[s], ctx->streams[s]);
+		},
+		[&](const uint8_t *h, uint32_t lo, uint32_t cnt) { memcpy(verdict + lo, h, cnt); });
+}
+
+extern "C" int eccb200_fp_mul_monty_batch(eccb200_ctx *ctx, int which, uint32_t n, const uint8_t *a, const uint8_t *b,
+					  uint8_t *out)
+{
+	if (!ctx || (n && (!a || !b || !out))) return fail("null argument");
+	if (n == 0) return 0;
+	CUDA_OK(cudaSetDevice(ctx->device));
+	size_t bytes = (size_t)n * ctx->plen;
+	uint8_t *d = nullptr;
+	CUDA_OK(cudaMalloc(&d, 3 * bytes));
+	int rc = 0;
+	do {
+		if (cudaMemcpy(d, a, bytes, cudaMemcpyHostToDevice) != cudaSuccess ||
+		    cudaMemcpy(d + bytes, b, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+			rc = fail("H2D copy failed");
+			break;
+		}
+		rc = dispatch(ctx->curve_id, [&](auto c) {
+			typedef decltype(c) C;
+			LaunchMisc<C>::fp_mul(which, n, d, d + bytes, d + 2 * bytes, 0);
+			ctx->launches += 1;
+			CUDA_OK(cudaGetLastError());
+			CUDA_OK(cudaMemcpy(out, d + 2 * bytes, bytes, cudaMemcpyDeviceToHost));
+			return 0;
+		});
+	} while (0);
+	cudaFree(d);
+	return rc;
+}

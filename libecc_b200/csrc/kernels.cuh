@@ -1,0 +1,396 @@
+/*
+ * kernels.cuh — the sm_100a kernels of the engine (SURVEY.md §2 "new kernel" table: K1..K5).
+ *
+ * Layout in HBM (all produced / consumed by these kernels):
+ *   wire buffers   : libecc big-endian byte strings, array-of-structures (scalars [n][qlen], affine points
+ *                    [n][2*plen], signatures [n][2*qlen], digests [n][hlen]); a warp reads 32 consecutive items, i.e.
+ *                    contiguous 1-3 KiB, each thread with 16-byte vector loads.
+ *   Jacobian buffer: [n][3N] 32-bit words (X, Y, Z in Montgomery form) between the scalar-mult kernels and the
+ *                    batched normalisation.
+ *   comb table     : [(nwin << w)][2N] words, entry (i << w) + d = d * 2^(w*i) * G affine, Montgomery form
+ *                    (64 B per entry for 256-bit curves = half a 128 B line, fetched with four 16 B loads).
+ *   prefix buffer  : [n][N] words of running products for the simultaneous inversion.
+ */
+#pragma once
+#include "ec.cuh"
+
+namespace eccb200 {
+
+/* ------------------------------------------------------------------------------------------ device wire helpers */
+
+__device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+
+/* N words from a 16-byte-aligned big-endian field (4N bytes) */
+template <int N> __device__ __forceinline__ void load_be16(Fe<N> &r, const uint8_t *buf)
+{
+	const uint4 *p = reinterpret_cast<const uint4 *>(buf);
+#pragma unroll
+	for (int j = 0; j < N / 4; j++) {
+		uint4 v = __ldg(p + j);
+		/* bytes [16j, 16j+16) hold words N-1-4j .. N-4-4j (most significant first) */
+		r.w[N - 1 - 4 * j] = bswap32(v.x);
+		r.w[N - 2 - 4 * j] = bswap32(v.y);
+		r.w[N - 3 - 4 * j] = bswap32(v.z);
+		r.w[N - 4 - 4 * j] = bswap32(v.w);
+	}
+}
+
+template <int N> __device__ __forceinline__ void store_be16(uint8_t *buf, const Fe<N> &a)
+{
+	uint4 *p = reinterpret_cast<uint4 *>(buf);
+#pragma unroll
+	for (int j = 0; j < N / 4; j++) {
+		uint4 v;
+		v.x = bswap32(a.w[N - 1 - 4 * j]);
+		v.y = bswap32(a.w[N - 2 - 4 * j]);
+		v.z = bswap32(a.w[N - 3 - 4 * j]);
+		v.w = bswap32(a.w[N - 4 - 4 * j]);
+		p[j] = v;
+	}
+}
+
+template <int N> __device__ __forceinline__ void load_words(Fe<N> &r, const uint32_t *src)
+{
+	const uint4 *p = reinterpret_cast<const uint4 *>(src);
+#pragma unroll
+	for (int j = 0; j < N / 4; j++) {
+		uint4 v = p[j];
+		r.w[4 * j] = v.x;
+		r.w[4 * j + 1] = v.y;
+		r.w[4 * j + 2] = v.z;
+		r.w[4 * j + 3] = v.w;
+	}
+}
+
+template <int N> __device__ __forceinline__ void store_words(uint32_t *dst, const Fe<N> &a)
+{
+	uint4 *p = reinterpret_cast<uint4 *>(dst);
+#pragma unroll
+	for (int j = 0; j < N / 4; j++) {
+		uint4 v;
+		v.x = a.w[4 * j];
+		v.y = a.w[4 * j + 1];
+		v.z = a.w[4 * j + 2];
+		v.w = a.w[4 * j + 3];
+		p[j] = v;
+	}
+}
+
+template <class C> __device__ __forceinline__ void store_jac(uint32_t *jac, uint32_t idx, const Jac<C> &p)
+{
+	uint32_t *b = jac + (size_t)idx * (3 * C::N);
+	store_words<C::N>(b, p.X);
+	store_words<C::N>(b + C::N, p.Y);
+	store_words<C::N>(b + 2 * C::N, p.Z);
+}
+
+/* Load an affine wire point, validate it the way the reference's import does (coordinates < p,
+ * fp_import_from_buf; on the curve, curves/prj_pt.c:541-545) and convert it to Montgomery form. */
+template <class C> __device__ __forceinline__ bool load_affine_checked(Aff<C> &P, const uint8_t *buf)
+{
+	typedef Field<typename C::Fp> F;
+	Fe<C::N> x, y;
+	load_be16<C::N>(x, buf);
+	load_be16<C::N>(y, buf + 4 * C::N);
+	bool ok = !F::geq_mod(x) && !F::geq_mod(y);
+	F::to_mont(P.x, x);
+	F::to_mont(P.y, y);
+	ok = ok && EC<C>::on_curve(P);
+	return ok;
+}
+
+/* ------------------------------------------------------------------------------------------ K1: fixed base */
+
+template <class C>
+__global__ void __launch_bounds__(128) k_smul_fixed(uint32_t n, const uint8_t *__restrict__ scalars,
+						    const uint32_t *__restrict__ table, int w,
+						    uint32_t *__restrict__ jac, int8_t *__restrict__ status)
+{
+	uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= n) return;
+	Fe<C::N> k;
+	load_be16<C::N>(k, scalars + (size_t)idx * (4 * C::N));
+	scalar_reduce<C>(k);
+	Jac<C> acc;
+	comb_mul<C>(acc, k, table, w);
+	store_jac<C>(jac, idx, acc);
+	status[idx] = 0;
+}
+
+/* ------------------------------------------------------------------------------------------ K2: variable base */
+
+template <class C>
+__global__ void __launch_bounds__(128) k_smul_var(uint32_t n, const uint8_t *__restrict__ scalars,
+						  const uint8_t *__restrict__ points, uint32_t *__restrict__ jac,
+						  int8_t *__restrict__ status)
+{
+	uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= n) return;
+	Fe<C::N> k;
+	load_be16<C::N>(k, scalars + (size_t)idx * (4 * C::N));
+	scalar_reduce<C>(k);
+	Aff<C> P;
+	bool ok = load_affine_checked<C>(P, points + (size_t)idx * (8 * C::N));
+	Jac<C> acc;
+	if (ok) {
+		window_mul<C>(acc, k, P);
+	} else {
+		EC<C>::set_inf(acc);
+	}
+	store_jac<C>(jac, idx, acc);
+	status[idx] = ok ? 0 : -1;
+}
+
+/* Comb-table build: entry e = (i << w) + d  ->  (d << (w*i)) * G, through the same window_mul as K2. */
+template <class C>
+__global__ void __launch_bounds__(128) k_table_points(uint32_t n_entries, int w, uint32_t *__restrict__ jac)
+{
+	uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= n_entries) return;
+	constexpr int N = C::N;
+	uint32_t d = e & ((1u << w) - 1u);
+	int i = (int)(e >> w);
+	int bit = i * w;
+	Fe<N> k;
+#pragma unroll
+	for (int j = 0; j < N; j++) k.w[j] = 0;
+	Jac<C> acc;
+	EC<C>::set_inf(acc);
+	if (d != 0 && bit < 32 * N) {
+		uint64_t v = (uint64_t)d << (bit & 31);
+		int wi = bit >> 5;
+#pragma unroll
+		for (int j = 0; j < N; j++) {
+			if (j == wi) k.w[j] = (uint32_t)v;
+			if (j == wi + 1) k.w[j] = (uint32_t)(v >> 32);
+		}
+		/* entries whose scalar would not be < q are never addressed by a reduced scalar; leave them at infinity */
+		if (!Field<typename C::Fq>::geq_mod(k)) {
+			Aff<C> G;
+#pragma unroll
+			for (int j = 0; j < N; j++) {
+				G.x.w[j] = C::GX_MONT(j);
+				G.y.w[j] = C::GY_MONT(j);
+			}
+			window_mul<C>(acc, k, G);
+		}
+	}
+	store_jac<C>(jac, e, acc);
+}
+
+/* ------------------------------------------------------------------------------------------ K4: normalisation */
+
+/*
+ * Jacobian -> affine for a whole batch with ONE field inversion per thread (Montgomery's simultaneous inversion):
+ * thread t owns items t, t+T, t+2T, ... (T = total threads, so every pass over the batch is coalesced), keeps the
+ * running product of their Z in registers, stores the prefix products, inverts once, and walks back.
+ * Replaces n calls of prj_pt_unique (curves/prj_pt.c:241) -> fp_inv (fp/fp_mul.c:51, ~1.5*bitlen(p) products each).
+ * TABLE = false: writes big-endian affine bytes + status (0 -> stays 0, infinity -> 1, -1 untouched).
+ * TABLE = true : writes Montgomery-form words (comb table entry format), infinity as all-zero.
+ */
+template <class C, bool TABLE>
+__global__ void __launch_bounds__(128) k_to_affine(uint32_t n, const uint32_t *__restrict__ jac,
+						   uint32_t *__restrict__ prefix, uint8_t *__restrict__ out,
+						   int8_t *__restrict__ status, uint32_t *__restrict__ table_out)
+{
+	typedef Field<typename C::Fp> F;
+	constexpr int N = C::N;
+	const uint32_t T = gridDim.x * blockDim.x;
+	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+	if (tid >= n) return;
+	Fe<N> acc;
+	F::set_one(acc);
+	uint32_t last = tid;
+	for (uint32_t e = tid; e < n; e += T) {
+		Fe<N> z;
+		load_words<N>(z, jac + (size_t)e * (3 * N) + 2 * N);
+		store_words<N>(prefix + (size_t)e * N, acc);
+		if (!F::is_zero(z)) {
+			Fe<N> t;
+			F::mul(t, acc, z);
+			acc = t;
+		}
+		last = e;
+		if (n - e <= T) break; /* avoid uint32 overflow of e += T */
+	}
+	Fe<N> inv;
+	F::inv(inv, acc);
+	for (uint32_t e = last;; e -= T) {
+		Fe<N> z, pre, X, Y;
+		const uint32_t *b = jac + (size_t)e * (3 * N);
+		load_words<N>(z, b + 2 * N);
+		bool inf = F::is_zero(z);
+		bool err = (!TABLE) && (status[e] < 0);
+		if (!inf) {
+			Fe<N> zi, zi2, zi3, t;
+			load_words<N>(pre, prefix + (size_t)e * N);
+			load_words<N>(X, b);
+			load_words<N>(Y, b + N);
+			F::mul(zi, inv, pre);  /* 1/z_e */
+			F::mul(t, inv, z);
+			inv = t;               /* drop z_e from the running inverse */
+			F::sqr(zi2, zi);
+			F::mul(zi3, zi2, zi);
+			F::mul(t, X, zi2);
+			X = t;
+			F::mul(t, Y, zi3);
+			Y = t;
+			if (TABLE) {
+				store_words<N>(table_out + (size_t)e * (2 * N), X);
+				store_words<N>(table_out + (size_t)e * (2 * N) + N, Y);
+			} else {
+				F::from_mont(t, X);
+				store_be16<N>(out + (size_t)e * (8 * N), t);
+				F::from_mont(t, Y);
+				store_be16<N>(out + (size_t)e * (8 * N) + 4 * N, t);
+			}
+		} else {
+			Fe<N> zero;
+			F::set_zero(zero);
+			if (TABLE) {
+				store_words<N>(table_out + (size_t)e * (2 * N), zero);
+				store_words<N>(table_out + (size_t)e * (2 * N) + N, zero);
+			} else {
+				store_be16<N>(out + (size_t)e * (8 * N), zero);
+				store_be16<N>(out + (size_t)e * (8 * N) + 4 * N, zero);
+				if (!err) status[e] = 1;
+			}
+		}
+		if (e < T || e - T < tid) break;
+	}
+}
+
+/* ------------------------------------------------------------------------------------------ K3: ECDSA verify */
+
+/*
+ * One signature per thread.  Follows __ecdsa_verify_init (sig/ecdsa_common.c:645-658) and
+ * __ecdsa_verify_finalize (:760-810) step by step; differences that do not change the verdict:
+ *   - s^-1 mod q by Fermat in the Montgomery domain of q instead of nn_modinv's xgcd (:781);
+ *   - W' = uG + vY is kept Jacobian and "x(W') mod q == r" is tested without an inversion as
+ *     X == c * Z^2 for the candidates c in {r, r+q} that are < p (:803-810);
+ *   - uG via the comb table (K1), vY via the signed window (K2) instead of two ladders (:788,793).
+ * digests: hlen bytes each; e = leftmost min(8*hlen, bitlen(q)) bits (:760-775), reduced mod q (:777).
+ */
+template <class C>
+__global__ void __launch_bounds__(128) k_ecdsa_verify(uint32_t n, const uint8_t *__restrict__ sigs,
+						      const uint8_t *__restrict__ pubkeys,
+						      const uint8_t *__restrict__ digests, uint32_t hlen,
+						      const uint32_t *__restrict__ table, int w,
+						      int8_t *__restrict__ verdict)
+{
+	constexpr int N = C::N;
+	uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= n) return;
+
+	Fe<N> r, s, e;
+	load_be16<N>(r, sigs + (size_t)idx * (8 * N));
+	load_be16<N>(s, sigs + (size_t)idx * (8 * N) + 4 * N);
+	Aff<C> Y;
+	bool key_ok = load_affine_checked<C>(Y, pubkeys + (size_t)idx * (8 * N));
+	digest_to_scalar<C>(e, digests + (size_t)idx * hlen, hlen);
+	bool valid = key_ok && ecdsa_verify_core<C>(r, s, e, Y, table, w);
+	verdict[idx] = valid ? 0 : -1;
+}
+
+/* ------------------------------------------------------------------------------------------ unit-test kernel */
+
+template <class FT>
+__global__ void k_fp_mul_monty(uint32_t n, const uint8_t *__restrict__ a, const uint8_t *__restrict__ b,
+			       uint8_t *__restrict__ out)
+{
+	constexpr int N = FT::N;
+	uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= n) return;
+	Fe<N> x, y, z;
+	load_be16<N>(x, a + (size_t)idx * (4 * N));
+	load_be16<N>(y, b + (size_t)idx * (4 * N));
+	Field<FT>::mul(z, x, y);
+	store_be16<N>(out + (size_t)idx * (4 * N), z);
+}
+
+} // namespace eccb200
+
+/* ------------------------------------------------------------------------------------------ launchers */
+/*
+ * Host-side launch wrappers, one struct per kernel group so that each (group, curve) pair can live in its own
+ * translation unit (tu_*.cu) and the groups compile in parallel; eccb200.cu only sees the declarations.
+ */
+#include <cuda_runtime.h>
+namespace eccb200 {
+
+static const int kThreads = 128;
+static inline uint32_t grid_for(uint32_t n) { return (n + kThreads - 1) / kThreads; }
+
+template <class C> struct LaunchSmul {
+	static void fixed(uint32_t n, const uint8_t *scalars, const uint32_t *table, int w, uint32_t *jac,
+			  int8_t *status, cudaStream_t st);
+	static void var(uint32_t n, const uint8_t *scalars, const uint8_t *points, uint32_t *jac, int8_t *status,
+			cudaStream_t st);
+	static void table_points(uint32_t entries, int w, uint32_t *jac, cudaStream_t st);
+};
+
+template <class C> struct LaunchMisc {
+	static void to_affine(uint32_t blocks, uint32_t n, const uint32_t *jac, uint32_t *prefix, uint8_t *out,
+			      int8_t *status, cudaStream_t st);
+	static void to_table(uint32_t blocks, uint32_t n, const uint32_t *jac, uint32_t *prefix, uint32_t *table,
+			     cudaStream_t st);
+	static void fp_mul(int which, uint32_t n, const uint8_t *a, const uint8_t *b, uint8_t *out, cudaStream_t st);
+};
+
+template <class C> struct LaunchVerify {
+	static void verify(uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys, const uint8_t *digests,
+			   uint32_t hlen, const uint32_t *table, int w, int8_t *verdict, cudaStream_t st);
+};
+
+#if defined(ECC_TU_SMUL)
+template <class C>
+void LaunchSmul<C>::fixed(uint32_t n, const uint8_t *scalars, const uint32_t *table, int w, uint32_t *jac,
+			  int8_t *status, cudaStream_t st)
+{
+	k_smul_fixed<C><<<grid_for(n), kThreads, 0, st>>>(n, scalars, table, w, jac, status);
+}
+template <class C>
+void LaunchSmul<C>::var(uint32_t n, const uint8_t *scalars, const uint8_t *points, uint32_t *jac, int8_t *status,
+			cudaStream_t st)
+{
+	k_smul_var<C><<<grid_for(n), kThreads, 0, st>>>(n, scalars, points, jac, status);
+}
+template <class C> void LaunchSmul<C>::table_points(uint32_t entries, int w, uint32_t *jac, cudaStream_t st)
+{
+	k_table_points<C><<<grid_for(entries), kThreads, 0, st>>>(entries, w, jac);
+}
+#endif
+
+#if defined(ECC_TU_MISC)
+template <class C>
+void LaunchMisc<C>::to_affine(uint32_t blocks, uint32_t n, const uint32_t *jac, uint32_t *prefix, uint8_t *out,
+			      int8_t *status, cudaStream_t st)
+{
+	k_to_affine<C, false><<<blocks, kThreads, 0, st>>>(n, jac, prefix, out, status, nullptr);
+}
+template <class C>
+void LaunchMisc<C>::to_table(uint32_t blocks, uint32_t n, const uint32_t *jac, uint32_t *prefix, uint32_t *table,
+			     cudaStream_t st)
+{
+	k_to_affine<C, true><<<blocks, kThreads, 0, st>>>(n, jac, prefix, nullptr, nullptr, table);
+}
+template <class C>
+void LaunchMisc<C>::fp_mul(int which, uint32_t n, const uint8_t *a, const uint8_t *b, uint8_t *out, cudaStream_t st)
+{
+	if (which == 0)
+		k_fp_mul_monty<typename C::Fp><<<grid_for(n), kThreads, 0, st>>>(n, a, b, out);
+	else
+		k_fp_mul_monty<typename C::Fq><<<grid_for(n), kThreads, 0, st>>>(n, a, b, out);
+}
+#endif
+
+#if defined(ECC_TU_VERIFY)
+template <class C>
+void LaunchVerify<C>::verify(uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys, const uint8_t *digests,
+			     uint32_t hlen, const uint32_t *table, int w, int8_t *verdict, cudaStream_t st)
+{
+	k_ecdsa_verify<C><<<grid_for(n), kThreads, 0, st>>>(n, sigs, pubkeys, digests, hlen, table, w, verdict);
+}
+#endif
+
+} // namespace eccb200

@@ -1,0 +1,202 @@
+"""Shared helpers for the test-suite: loaders for the checkers (oracle port, compiled reference, host build of
+the device algorithms), the golden fixtures, and seeded input generators.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/ (see oracle/ecc_oracle.h)."""
+from __future__ import annotations
+
+import ctypes
+import gzip
+import json
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+ORACLE_SO = os.path.join(ROOT, "oracle", "_ref", "libecc_oracle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libecc_ref.so")
+HOSTSIM_SO = os.path.join(ROOT, "tests", "hostsim", "_build", "libecc_hostsim.so")
+SEED = 0x6C69626563632D31  # "libecc-1" 
+
+CURVES = {"SECP256R1": (4, 32, 32), "FRP256V1": (1, 32, 32), "SECP384R1": (5, 48, 48)}  # id, plen, qlen
+ORDER = {
+    "SECP256R1": 0xffffffff00000000ffffffffffffffffbce6faada7179e84f3b9cac2fc632551,
+    "FRP256V1": 0xf1fd178c0b3ad58f10126de8ce42435b53dc67e140d2bf941ffdd459c6d655e1,
+    "SECP384R1": 0xffffffffffffffffffffffffffffffffffffffffffffffffc7634d81f4372ddf581a0db248b0a77aecec196accc52973,
+}
+PRIME = {
+    "SECP256R1": 0xffffffff00000001000000000000000000000000ffffffffffffffffffffffff,
+    "FRP256V1": 0xf1fd178c0b3ad58f10126de8ce42435b3961adbcabc8ca6de8fcf353d86e9c03,
+    "SECP384R1": 0xfffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffeffffffff0000000000000000ffffffff,
+}
+HASHLEN = {"SHA224": 28, "SHA256": 32, "SHA384": 48, "SHA512": 64, "SHA3_224": 28, "SHA3_256": 32,
+           "SHA3_384": 48, "SHA3_512": 64}
+
+_cache = {}
+
+
+def _build_oracle():
+    if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(
+            os.path.join(ROOT, "oracle", "ecc_oracle.c")):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True, capture_output=True)
+
+
+def oracle_lib() -> ctypes.CDLL:
+    if "oracle" not in _cache:
+        _build_oracle()
+        lib = ctypes.CDLL(ORACLE_SO)
+        lib.ora_last_mul_count.restype = ctypes.c_uint64
+        _cache["oracle"] = lib
+    return _cache["oracle"]
+
+
+def ref_lib():
+    """The unmodified reference compiled by oracle/Makefile, or None when it is not available (it is built in
+    the container that has /root/reference and travels to the GPU box as a prebuilt .so)."""
+    if "ref" not in _cache:
+        if not os.path.exists(REF_SO) and os.path.exists("/root/reference/src/libsig.h"):
+            subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "ref"], check=True,
+                           capture_output=True)
+        _cache["ref"] = ctypes.CDLL(REF_SO) if os.path.exists(REF_SO) else None
+    return _cache["ref"]
+
+
+def hostsim_lib() -> ctypes.CDLL:
+    if "hostsim" not in _cache:
+        src = os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")
+        deps = [src] + [os.path.join(ROOT, "libecc_b200", "csrc", f) for f in
+                        ("fp.cuh", "ec.cuh", "curve_constants.inc")]
+        if not os.path.exists(HOSTSIM_SO) or os.path.getmtime(HOSTSIM_SO) < max(os.path.getmtime(d) for d in deps):
+            os.makedirs(os.path.dirname(HOSTSIM_SO), exist_ok=True)
+            subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", src, "-o", HOSTSIM_SO],
+                           check=True, capture_output=True)
+        lib = ctypes.CDLL(HOSTSIM_SO)
+        lib.hostsim_last_mul_count.restype = ctypes.c_ulonglong
+        _cache["hostsim"] = lib
+    return _cache["hostsim"]
+
+
+def golden(name: str):
+    path = os.path.join(GOLDEN, name)
+    if path.endswith(".gz"):
+        with gzip.open(path, "rt") as f:
+            return json.load(f)
+    with open(path) as f:
+        return json.load(f)
+
+
+def rng(tag: int = 0) -> np.random.Generator:
+    return np.random.default_rng([SEED & 0xFFFFFFFF, SEED >> 32, tag])
+
+
+def random_scalars(curve: str, n: int, tag: int = 0, below_q: bool = True) -> np.ndarray:
+    """n big-endian qlen-byte scalars, uniform in [1, q-1] (rejection sampling) or raw bytes."""
+    _, _, qlen = CURVES[curve]
+    g = rng(tag)
+    raw = g.integers(0, 256, size=(n, qlen), dtype=np.uint8)
+    if below_q:
+        q = ORDER[curve]
+        for i in range(n):
+            while True:
+                v = int.from_bytes(raw[i].tobytes(), "big")
+                if 0 < v < q:
+                    break
+                raw[i] = g.integers(0, 256, size=qlen, dtype=np.uint8)
+    return raw
+
+
+def edge_scalars(curve: str) -> np.ndarray:
+    """The adversarial scalars of SURVEY.md §8a's edge table."""
+    _, _, qlen = CURVES[curve]
+    q = ORDER[curve]
+    vals = [0, 1, 2, 3, q - 2, q - 1, q, q + 1, (1 << (8 * qlen)) - 1, 1 << (8 * qlen - 1), 0x10, 0x100, 1 << 16,
+            (1 << 16) - 1, 1 << 64, q >> 1, (q >> 1) + 1]
+    vals = [v % (1 << (8 * qlen)) for v in vals]
+    return np.frombuffer(b"".join(v.to_bytes(qlen, "big") for v in vals), dtype=np.uint8).reshape(-1, qlen).copy()
+
+
+def _buf(a):
+    a = np.ascontiguousarray(a)
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def oracle_smul(curve: str, scalars: np.ndarray, points=None, nthreads: int = 8, lib=None):
+    """(out[n,2plen], status[n]) from the oracle port (or the compiled reference with lib=ref_lib())."""
+    _, plen, qlen = CURVES[curve]
+    sc = np.ascontiguousarray(scalars, dtype=np.uint8).reshape(-1, qlen)
+    n = sc.shape[0]
+    out = np.zeros((n, 2 * plen), dtype=np.uint8)
+    st = np.zeros(n, dtype=np.int8)
+    pts = np.ascontiguousarray(points, dtype=np.uint8) if points is not None else None
+    if lib is None:
+        fn = oracle_lib().ora_prj_pt_mul_batch
+    else:
+        fn = lib.ref_prj_pt_mul_batch
+    rc = fn(curve.encode(), n, _buf(sc), qlen, _buf(pts) if pts is not None else None, _buf(out), _buf(st), nthreads)
+    assert rc == 0
+    return out, st
+
+
+def oracle_verify(curve: str, sigs, pubkeys, digests, hlen: int, nthreads: int = 8) -> np.ndarray:
+    _, plen, qlen = CURVES[curve]
+    sg = np.ascontiguousarray(sigs, dtype=np.uint8).reshape(-1, 2 * qlen)
+    n = sg.shape[0]
+    pk = np.ascontiguousarray(pubkeys, dtype=np.uint8).reshape(n, 2 * plen)
+    dg = np.ascontiguousarray(digests, dtype=np.uint8).reshape(n, hlen)
+    v = np.zeros(n, dtype=np.int8)
+    rc = oracle_lib().ora_ecdsa_verify_digest_batch(curve.encode(), n, _buf(sg), _buf(pk), _buf(dg), hlen, _buf(v),
+                                                    nthreads)
+    assert rc == 0
+    return v
+
+
+def oracle_sign(curve: str, privkeys, nonces, digests, hlen: int, nthreads: int = 8):
+    _, plen, qlen = CURVES[curve]
+    d = np.ascontiguousarray(privkeys, dtype=np.uint8).reshape(-1, qlen)
+    n = d.shape[0]
+    k = np.ascontiguousarray(nonces, dtype=np.uint8).reshape(n, qlen)
+    dg = np.ascontiguousarray(digests, dtype=np.uint8).reshape(n, hlen)
+    sig = np.zeros((n, 2 * qlen), dtype=np.uint8)
+    st = np.zeros(n, dtype=np.int8)
+    rc = oracle_lib().ora_ecdsa_sign_digest_batch(curve.encode(), n, _buf(d), _buf(k), _buf(dg), hlen, _buf(sig),
+                                                  _buf(st), nthreads)
+    assert rc == 0
+    return sig, st
+
+
+def hx(s: str) -> np.ndarray:
+    return np.frombuffer(bytes.fromhex(s), dtype=np.uint8)
+
+
+def make_signatures(curve: str, n: int, tag: int = 0, hlen: int = 32, corrupt_every: int = 0):
+    """Synthetic ECDSA workload: n tuples (sig, pubkey, digest) with distinct random keys,
+    produced with the oracle's deterministic signer; every `corrupt_every`-th tuple is corrupted in a way that
+    rotates over {flip bit in r, in s, in digest, in key, r = 0, s >= q}.  Returns (sigs, pubs, digests, expected)
+    where expected comes from the oracle's verifier."""
+    _, plen, qlen = CURVES[curve]
+    d = random_scalars(curve, n, tag=1000 + tag)
+    k = random_scalars(curve, n, tag=2000 + tag)
+    dg = rng(3000 + tag).integers(0, 256, size=(n, hlen), dtype=np.uint8)
+    pubs, st = oracle_smul(curve, d)
+    assert (st == 0).all()
+    sigs, st = oracle_sign(curve, d, k, dg, hlen)
+    assert (st == 0).all()
+    if corrupt_every:
+        q = ORDER[curve]
+        for j, i in enumerate(range(0, n, corrupt_every)):
+            kind = j % 6
+            if kind == 0:
+                sigs[i, qlen - 1] ^= 1
+            elif kind == 1:
+                sigs[i, 2 * qlen - 1] ^= 1
+            elif kind == 2:
+                dg[i, 0] ^= 0x80
+            elif kind == 3:
+                pubs[i, plen - 1] ^= 1  # almost surely off the curve
+            elif kind == 4:
+                sigs[i, :qlen] = 0
+            else:
+                sigs[i, qlen:] = np.frombuffer(q.to_bytes(qlen, "big"), dtype=np.uint8)
+    expected = oracle_verify(curve, sigs, pubs, dg, hlen)
+    return sigs, pubs, dg, expected

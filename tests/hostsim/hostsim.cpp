@@ -1,0 +1,257 @@
+/*
+ * tests/hostsim/hostsim.cpp — TEST-ONLY host build of the device arithmetic (fp.cuh / ec.cuh compiled by g++).
+ *
+ * Purpose: let the CPU test-suite (`pytest -m "not gpu"`) check the ALGORITHMS the kernels use — word-level
+ * Montgomery product, Jacobian formulas and their exceptional branches, comb / signed-window scalar
+ * multiplication, the ECDSA verification core — against the oracle and the golden vectors without a GPU, and
+ * count the field multiplications the implemented algorithm performs (M_impl).
+ *
+ * This is NOT a CPU fallback: it is built into tests/hostsim/_build/libecc_hostsim.so by the tests only, it is
+ * never loaded by libecc_b200/, and the product library fails with -1 when no B200 is present.
+ */
+#define ECC_COUNT_MULS
+#include "../../libecc_b200/csrc/ec.cuh"
+#include <cstring>
+#include <vector>
+
+namespace eccb200 {
+thread_local unsigned long long g_fe_mul_count = 0;
+}
+using namespace eccb200;
+
+template <class Fn> static int dispatch(int curve_id, Fn &&fn)
+{
+	switch (curve_id) {
+	case 4: return fn(Curve_SECP256R1());
+	case 1: return fn(Curve_FRP256V1());
+	case 5: return fn(Curve_SECP384R1());
+	default: return -1;
+	}
+}
+
+/* Jacobian -> affine big-endian bytes with a per-item inversion (the batched variant is kernel-only) */
+template <class C> static int jac_to_wire(const Jac<C> &p, uint8_t *out)
+{
+	typedef Field<typename C::Fp> F;
+	constexpr int N = C::N;
+	memset(out, 0, 8 * N);
+	if (F::is_zero(p.Z)) return 1;
+	Fe<N> zi, zi2, zi3, x, y, t;
+	F::inv(zi, p.Z);
+	F::sqr(zi2, zi);
+	F::mul(zi3, zi2, zi);
+	F::mul(t, p.X, zi2);
+	F::from_mont(x, t);
+	F::mul(t, p.Y, zi3);
+	F::from_mont(y, t);
+	store_be<N>(out, x);
+	store_be<N>(out + 4 * N, y);
+	return 0;
+}
+
+template <class C> static bool load_point(Aff<C> &P, const uint8_t *buf)
+{
+	typedef Field<typename C::Fp> F;
+	Fe<C::N> x, y;
+	load_be<C::N>(x, buf);
+	load_be<C::N>(y, buf + 4 * C::N);
+	bool ok = !F::geq_mod(x) && !F::geq_mod(y);
+	F::to_mont(P.x, x);
+	F::to_mont(P.y, y);
+	return ok && EC<C>::on_curve(P);
+}
+
+/* comb table built with the same window_mul the device table kernel uses (small w only: this is a CPU) */
+template <class C> static std::vector<uint32_t> build_table(int w)
+{
+	typedef Field<typename C::Fp> F;
+	constexpr int N = C::N;
+	int nwin = (C::QBITS + w - 1) / w;
+	std::vector<uint32_t> tab((size_t)(nwin << w) * 2 * N, 0);
+	Aff<C> G;
+	for (int j = 0; j < N; j++) {
+		G.x.w[j] = C::GX_MONT(j);
+		G.y.w[j] = C::GY_MONT(j);
+	}
+	for (int i = 0; i < nwin; i++) {
+		for (uint32_t d = 1; d < (1u << w); d++) {
+			int bit = i * w;
+			if (bit >= 32 * N) continue;
+			Fe<N> k;
+			for (int j = 0; j < N; j++) k.w[j] = 0;
+			uint64_t v = (uint64_t)d << (bit & 31);
+			k.w[bit >> 5] = (uint32_t)v;
+			if ((bit >> 5) + 1 < N) k.w[(bit >> 5) + 1] = (uint32_t)(v >> 32);
+			else if ((uint32_t)(v >> 32)) continue;
+			if (Field<typename C::Fq>::geq_mod(k)) continue;
+			Jac<C> acc;
+			window_mul<C>(acc, k, G);
+			Fe<N> zi, zi2, zi3, x, y;
+			F::inv(zi, acc.Z);
+			F::sqr(zi2, zi);
+			F::mul(zi3, zi2, zi);
+			F::mul(x, acc.X, zi2);
+			F::mul(y, acc.Y, zi3);
+			uint32_t *e = &tab[((size_t)(i << w) + d) * 2 * N];
+			for (int j = 0; j < N; j++) {
+				e[j] = x.w[j];
+				e[N + j] = y.w[j];
+			}
+		}
+	}
+	return tab;
+}
+
+template <class C> static const std::vector<uint32_t> &table_for(int w)
+{
+	static std::vector<uint32_t> tabs[17];
+	if (tabs[w].empty()) tabs[w] = build_table<C>(w);
+	return tabs[w];
+}
+
+extern "C" {
+
+int hostsim_fp_mul(int curve_id, int which, uint32_t n, const uint8_t *a, const uint8_t *b, uint8_t *out)
+{
+	return dispatch(curve_id, [&](auto c) {
+		typedef decltype(c) C;
+		constexpr int N = C::N;
+		for (uint32_t i = 0; i < n; i++) {
+			Fe<N> x, y, z;
+			load_be<N>(x, a + (size_t)i * 4 * N);
+			load_be<N>(y, b + (size_t)i * 4 * N);
+			if (which == 0) Field<typename C::Fp>::mul(z, x, y);
+			else Field<typename C::Fq>::mul(z, x, y);
+			store_be<N>(out + (size_t)i * 4 * N, z);
+		}
+		return 0;
+	});
+}
+
+/* (a op b) mod p on plain values: op 0 add, 1 sub, 2 inverse of a (through the Montgomery domain) */
+int hostsim_fp_op(int curve_id, int op, uint32_t n, const uint8_t *a, const uint8_t *b, uint8_t *out)
+{
+	return dispatch(curve_id, [&](auto c) {
+		typedef decltype(c) C;
+		typedef Field<typename C::Fp> F;
+		constexpr int N = C::N;
+		for (uint32_t i = 0; i < n; i++) {
+			Fe<N> x, y, z;
+			load_be<N>(x, a + (size_t)i * 4 * N);
+			load_be<N>(y, b + (size_t)i * 4 * N);
+			if (op == 0) F::add(z, x, y);
+			else if (op == 1) F::sub(z, x, y);
+			else {
+				Fe<N> xm, zi;
+				F::to_mont(xm, x);
+				F::inv(zi, xm);
+				F::from_mont(z, zi);
+			}
+			store_be<N>(out + (size_t)i * 4 * N, z);
+		}
+		return 0;
+	});
+}
+
+/* same contract as eccb200_prj_pt_mul_batch; w = comb window used for the fixed-base path */
+int hostsim_prj_pt_mul_batch(int curve_id, int w, uint32_t n, const uint8_t *scalars, const uint8_t *points,
+			     uint8_t *out, int8_t *status)
+{
+	return dispatch(curve_id, [&](auto c) {
+		typedef decltype(c) C;
+		constexpr int N = C::N;
+		for (uint32_t i = 0; i < n; i++) {
+			Fe<N> k;
+			load_be<N>(k, scalars + (size_t)i * 4 * N);
+			scalar_reduce<C>(k);
+			Jac<C> acc;
+			uint8_t *o = out + (size_t)i * 8 * N;
+			if (points) {
+				Aff<C> P;
+				if (!load_point<C>(P, points + (size_t)i * 8 * N)) {
+					memset(o, 0, 8 * N);
+					status[i] = -1;
+					continue;
+				}
+				g_fe_mul_count = 0;
+				window_mul<C>(acc, k, P);
+			} else {
+				const std::vector<uint32_t> &tab = table_for<C>(w);
+				g_fe_mul_count = 0;
+				comb_mul<C>(acc, k, tab.data(), w);
+			}
+			status[i] = (int8_t)jac_to_wire<C>(acc, o);
+		}
+		return 0;
+	});
+}
+
+int hostsim_ecdsa_verify_batch(int curve_id, int w, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys,
+			       const uint8_t *digests, uint32_t hlen, int8_t *verdict)
+{
+	return dispatch(curve_id, [&](auto c) {
+		typedef decltype(c) C;
+		constexpr int N = C::N;
+		const std::vector<uint32_t> &tab = table_for<C>(w);
+		for (uint32_t i = 0; i < n; i++) {
+			Fe<N> r, s, e;
+			load_be<N>(r, sigs + (size_t)i * 8 * N);
+			load_be<N>(s, sigs + (size_t)i * 8 * N + 4 * N);
+			Aff<C> Y;
+			bool ok = load_point<C>(Y, pubkeys + (size_t)i * 8 * N);
+			digest_to_scalar<C>(e, digests + (size_t)i * hlen, hlen);
+			g_fe_mul_count = 0;
+			ok = ok && ecdsa_verify_core<C>(r, s, e, Y, tab.data(), w);
+			verdict[i] = ok ? 0 : -1;
+		}
+		return 0;
+	});
+}
+
+/* group-law unit test: out = P1 + P2 on affine wire points through add_full / add_mixed (which = 0 / 1),
+ * or 2*P1 through dbl (which = 2); infinity operands are encoded as all-zero wire points */
+int hostsim_point_op(int curve_id, int which, const uint8_t *p1, const uint8_t *p2, uint8_t *out, int8_t *status)
+{
+	return dispatch(curve_id, [&](auto c) {
+		typedef decltype(c) C;
+		typedef EC<C> G;
+		constexpr int N = C::N;
+		auto is_zero_buf = [](const uint8_t *b, int len) {
+			for (int i = 0; i < len; i++)
+				if (b[i]) return false;
+			return true;
+		};
+		Jac<C> A, B, R;
+		Aff<C> a, b;
+		bool a_inf = is_zero_buf(p1, 8 * N), b_inf = is_zero_buf(p2, 8 * N);
+		if (a_inf) G::set_inf(A);
+		else {
+			if (!load_point<C>(a, p1)) return -1;
+			G::from_affine(A, a);
+			/* use a non-trivial Z so the projective paths are exercised: (X,Y,Z) -> (4X, 8Y, 2Z) */
+			typedef Field<typename C::Fp> F;
+			F::dbl(A.Z, A.Z);
+			F::dbl(A.X, A.X);
+			F::dbl(A.X, A.X);
+			F::dbl(A.Y, A.Y);
+			F::dbl(A.Y, A.Y);
+			F::dbl(A.Y, A.Y);
+		}
+		if (b_inf) G::set_inf(B);
+		else {
+			if (!load_point<C>(b, p2)) return -1;
+			G::from_affine(B, b);
+		}
+		if (which == 0) G::add_full(R, A, B);
+		else if (which == 1) {
+			if (b_inf) return -1;
+			G::add_mixed(R, A, b);
+		} else G::dbl(R, A);
+		*status = (int8_t)jac_to_wire<C>(R, out);
+		return 0;
+	});
+}
+
+unsigned long long hostsim_last_mul_count(void) { return g_fe_mul_count; }
+
+} /* extern "C" */

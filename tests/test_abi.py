@@ -1,0 +1,57 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads, exports every symbol the headers under
+include/ declare, and refuses to work without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import libecc_b200
+from common import ROOT
+
+
+def declared_symbols():
+    names = set()
+    for h in os.listdir(os.path.join(ROOT, "include")):
+        txt = open(os.path.join(ROOT, "include", h)).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        for m in re.finditer(r"\b(eccb200_\w+|prj_pt_mul\w*|ecdsa_verify_batch\w*|eccb200\w*)\s*\(", txt):
+            names.add(m.group(1))
+    return names
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(libecc_b200.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = ctypes.CDLL(libecc_b200.LIB_PATH)
+    decl = declared_symbols()
+    assert set(libecc_b200.ABI_SYMBOLS) <= decl
+    for name in sorted(decl):
+        assert hasattr(lib, name), f"{name} declared in include/ but not exported"
+
+
+def test_curve_metadata_without_gpu():
+    assert libecc_b200.curve_sizes("SECP256R1") == (32, 32)
+    assert libecc_b200.curve_sizes("FRP256V1") == (32, 32)
+    assert libecc_b200.curve_sizes("SECP384R1") == (48, 48)
+    lib = libecc_b200.load_library()
+    assert lib.eccb200_curve_name(4) == b"SECP256R1" and lib.eccb200_curve_name(99) is None
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(libecc_b200.EccB200Error, match="no CUDA device"):
+        libecc_b200.Engine("SECP256R1")
+
+
+def test_product_does_not_reference_the_oracle():
+    """The product sources must not include, link or load anything under oracle/ or tests/hostsim."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "libecc_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".c", ".h", ".inc")) or f == "Makefile":
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                code = re.sub(r"/\*.*?\*/|#.*?$|//.*?$|\"\"\".*?\"\"\"", "", txt, flags=re.S | re.M)
+                assert "ecc_oracle" not in code and "libecc_ref" not in code and "hostsim" not in code, f

@@ -1,0 +1,178 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (include/libecc_b200.h), against the golden
+vectors and the oracle.  Bit-exact (integer/byte work): affine bytes, infinity flag, error code, verdicts."""
+import numpy as np
+import pytest
+
+from common import (CURVES, HASHLEN, ORDER, PRIME, edge_scalars, golden, hx, make_signatures, oracle_smul,
+                    oracle_verify, random_scalars, rng)
+
+pytestmark = pytest.mark.gpu
+
+_engines = {}
+
+
+def engine(curve, w=0):
+    import libecc_b200
+    key = (curve, w)
+    if key not in _engines:
+        _engines[key] = libecc_b200.Engine(curve, device=0, comb_window=w)
+    return _engines[key]
+
+
+def be(vals, nbytes):
+    return np.frombuffer(b"".join(int(v).to_bytes(nbytes, "big") for v in vals), dtype=np.uint8).copy()
+
+
+@pytest.mark.parametrize("curve", list(CURVES))
+def test_fp_mul_monty_against_integers(curve):
+    """fp_mul_monty unit test in the pattern of src/arithmetic_tests (NN_MUL_REDC1 / FP_MUL_MONTY)."""
+    eng = engine(curve, 8)
+    _, plen, _ = CURVES[curve]
+    g = rng(31)
+    for which, mod in ((0, PRIME[curve]), (1, ORDER[curve])):
+        a = [int.from_bytes(g.bytes(plen + 8), "big") % mod for _ in range(4096)] + [0, 1, mod - 1, mod - 1]
+        b = [int.from_bytes(g.bytes(plen + 8), "big") % mod for _ in range(4096)] + [mod - 1, 1, mod - 1, 0]
+        out = eng.fp_mul_monty_batch(be(a, plen), be(b, plen), which)
+        rinv = pow(1 << (8 * plen), -1, mod)
+        got = [int.from_bytes(o.tobytes(), "big") for o in out]
+        assert got == [x * y * rinv % mod for x, y in zip(a, b)]
+
+
+@pytest.mark.parametrize("curve", ["SECP256R1", "SECP384R1"])
+def test_ecccdh_kat(curve):
+    """NIST ECC-CDH vectors (reference: src/tests/ecccdh_test_vectors.h:1501-2999)."""
+    _, plen, _ = CURVES[curve]
+    vecs = [v for v in golden("ecccdh_kat.json") if v["curve"] == curve]
+    d = np.stack([hx(v["priv"]) for v in vecs]); peers = np.stack([hx(v["peer_pub"]) for v in vecs])
+    for w in (8, 0):
+        out, st = engine(curve, w).prj_pt_mul_batch(d)
+        assert (st == 0).all() and [o.tobytes().hex() for o in out] == [v["our_pub"] for v in vecs]
+    out, st = engine(curve).prj_pt_mul_batch(d, peers)
+    assert (st == 0).all() and [o[:plen].tobytes().hex() for o in out] == [v["shared"] for v in vecs]
+
+
+@pytest.mark.parametrize("curve", list(CURVES))
+@pytest.mark.parametrize("w", [5, 8, 13, 0])
+def test_fixed_base_vs_oracle(curve, w):
+    sc = np.concatenate([random_scalars(curve, 1024 if w else 4096, tag=41 + w, below_q=False), edge_scalars(curve)])
+    want, wst = oracle_smul(curve, sc)
+    out, st = engine(curve, w).prj_pt_mul_batch(sc)
+    assert (st == wst).all()
+    assert (out == want).all()
+
+
+@pytest.mark.parametrize("curve", list(CURVES))
+def test_variable_base_vs_oracle(curve):
+    _, plen, qlen = CURVES[curve]
+    base_sc = random_scalars(curve, 2048, tag=51)
+    pts, st0 = oracle_smul(curve, base_sc)
+    sc = random_scalars(curve, 2048, tag=52, below_q=False)
+    es = edge_scalars(curve)
+    sc[: es.shape[0]] = es
+    pts[100, 7] ^= 0x04          # off the curve
+    pts[101, :plen] = 0xFF       # x >= p
+    pts[102, plen:] = 0xFF       # y >= p
+    pts[103, :] = 0              # (0,0) is not on these curves
+    want, wst = oracle_smul(curve, sc, pts)
+    out, st = engine(curve).prj_pt_mul_batch(sc, pts)
+    assert (st == wst).all() and (wst[100:104] == -1).all()
+    assert (out == want).all()
+
+
+@pytest.mark.parametrize("curve", ["SECP256R1", "SECP384R1"])
+def test_wycheproof_ecdh(curve):
+    _, plen, qlen = CURVES[curve]
+    vecs = [v for v in golden("wycheproof_ecdh.json.gz") if v["curve"] == curve and len(v["priv"]) <= 2 * qlen]
+    d = np.stack([hx(v["priv"].rjust(2 * qlen, "0")) for v in vecs]); q = np.stack([hx(v["peer_pub"]) for v in vecs])
+    out, st = engine(curve).prj_pt_mul_batch(d, q)
+    assert [int(s) for s in st] == [v["ref_status"] for v in vecs]
+    assert [o.tobytes().hex() for o in out] == [v["ref_point"] for v in vecs]
+
+
+def test_ecdsa_kat():
+    for v in golden("ecdsa_kat.json"):
+        got = engine(v["curve"]).ecdsa_verify_batch(hx(v["sig"]), hx(v["pub"]), hx(v["digest"]), HASHLEN[v["hash"]])
+        assert got[0] == 0 == v["ref_verdict"], v["name"]
+        bad = hx(v["digest"]).copy(); bad[0] ^= 1
+        assert engine(v["curve"]).ecdsa_verify_batch(hx(v["sig"]), hx(v["pub"]), bad, HASHLEN[v["hash"]])[0] == -1
+
+
+@pytest.mark.parametrize("curve", ["SECP256R1", "SECP384R1"])
+def test_wycheproof_ecdsa_all(curve):
+    """Every Wycheproof ECDSA vector the reference ships for the curve: verdict == the reference's own ec_verify."""
+    _, plen, qlen = CURVES[curve]
+    vecs = [v for v in golden("wycheproof_ecdsa.json.gz")
+            if v["curve"] == curve and len(v["sig"]) == 4 * qlen and len(v["pub"]) == 4 * plen]
+    assert len(vecs) > 1500
+    for h in sorted({v["hash"] for v in vecs}):
+        vs = [v for v in vecs if v["hash"] == h]
+        sig = np.stack([hx(v["sig"]) for v in vs]); pub = np.stack([hx(v["pub"]) for v in vs])
+        dg = np.stack([hx(v["digest"]) for v in vs])
+        got = engine(curve).ecdsa_verify_batch(sig, pub, dg, HASHLEN[h])
+        want = np.array([v["ref_verdict"] for v in vs], dtype=np.int8)
+        assert (got == want).all(), [v["name"] for v, g_, w_ in zip(vs, got, want) if g_ != w_][:5]
+
+
+@pytest.mark.parametrize("curve,hlen", [("FRP256V1", 32), ("SECP256R1", 32), ("SECP384R1", 48), ("SECP256R1", 64),
+                                        ("SECP384R1", 20)])
+def test_ecdsa_synthetic_with_corruptions(curve, hlen):
+    sigs, pubs, dg, expected = make_signatures(curve, 512, tag=hlen, hlen=hlen, corrupt_every=8)
+    got = engine(curve).ecdsa_verify_batch(sigs, pubs, dg, hlen)
+    assert (got == expected).all()
+    assert (expected[::8] == -1).all() and (np.delete(expected, np.s_[::8]) == 0).all()
+
+
+def test_device_pointer_api_and_ragged_sizes():
+    import torch
+    curve = "SECP256R1"
+    eng = engine(curve)
+    for n in (0, 1, 31, 129, 1000):
+        sc = random_scalars(curve, max(n, 1), tag=60 + n)[:n]
+        want, wst = oracle_smul(curve, sc) if n else (np.zeros((0, 64), np.uint8), np.zeros(0, np.int8))
+        d_sc = torch.from_numpy(sc.copy()).cuda().reshape(-1)
+        d_out = torch.zeros(n * 64, dtype=torch.uint8, device="cuda")
+        d_st = torch.full((n,), 7, dtype=torch.int8, device="cuda")
+        eng.prj_pt_mul_batch_dev(d_sc, None, d_out, d_st, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert (d_st.cpu().numpy() == wst).all()
+        assert (d_out.cpu().numpy().reshape(n, 64) == want).all()
+        out, st = eng.prj_pt_mul_batch(sc)
+        assert (out == want).all() and (st == wst).all()
+
+
+def test_full_size_batch_properties_and_sample():
+    """BASELINE.json config 2 at full size (2^20 scalars on G): the oracle cannot run 2^20 items in seconds, so
+    (i) a seeded sample is compared bit-exactly with the oracle, (ii) size-independent properties are checked on the
+    whole batch: k and q-k give the same x and y + y' = p (negation), all outputs are on the curve."""
+    curve = "SECP256R1"
+    n = 1 << 20
+    p, q = PRIME[curve], ORDER[curve]
+    sc = random_scalars(curve, n // 2, tag=70, below_q=False)
+    sc[:, 0] &= 0x7F  # keep k < q so that q - k is in range
+    ks = [int.from_bytes(r.tobytes(), "big") for r in sc[:4096]]
+    neg = sc.copy()
+    # q - k computed with numpy on 32-byte big-endian rows (vectorised borrow chain)
+    qb = np.frombuffer(q.to_bytes(32, "big"), dtype=np.uint8).astype(np.int32)
+    borrow = np.zeros(n // 2, dtype=np.int32)
+    for j in range(31, -1, -1):
+        dj = qb[j] - sc[:, j].astype(np.int32) - borrow
+        borrow = (dj < 0).astype(np.int32)
+        neg[:, j] = (dj + 256 * borrow).astype(np.uint8)
+    assert int.from_bytes(neg[0].tobytes(), "big") == q - ks[0]
+    allsc = np.concatenate([sc, neg])
+    out, st = engine(curve).prj_pt_mul_batch(allsc)
+    assert (st == 0).all()
+    a, b = out[: n // 2], out[n // 2:]
+    assert (a[:, :32] == b[:, :32]).all()                       # same x
+    # y + y' == p : byte-wise big-endian addition with carry
+    pb = np.frombuffer(p.to_bytes(32, "big"), dtype=np.uint8).astype(np.int32)
+    carry = np.zeros(n // 2, dtype=np.int32)
+    ok = np.ones(n // 2, dtype=bool)
+    for j in range(31, -1, -1):
+        s = a[:, 32 + j].astype(np.int32) + b[:, 32 + j].astype(np.int32) + carry
+        ok &= (s & 0xFF) == pb[j]
+        carry = s >> 8
+    assert ok.all() and (carry == 0).all()
+    idx = rng(71).choice(n, size=2048, replace=False)
+    want, wst = oracle_smul(curve, allsc[idx])
+    assert (out[idx] == want).all() and (st[idx] == wst).all()
