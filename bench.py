@@ -1,0 +1,429 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the hot path (BASELINE.json): secp256r1 prj_pt_mul/s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is one pass of the hot path over one batch of synthetic input.  Default workload (N = 1) is BASELINE.json
+configs[1]: 2^20 random scalars on the fixed base G of secp256r1 per GPU.  Other workloads (parity-test configs, also
+usable for extra measurements): secp384r1_fixed_base, secp256r1_variable_base, frp256v1_ecdsa_verify.
+
+Ours arm, per step and per rank (one process per GPU; torchrun for N > 1):
+  value  : inputs resident in HBM, eccb200_*_batch_dev on torch's current stream, for N > 1 followed by the NCCL
+           all-gather of the results (the path's only exchange step); CUDA events, max over ranks.
+  e2e    : the host-pointer C-ABI call (eccb200_prj_pt_mul_batch / eccb200_ecdsa_verify_batch) on host buffers:
+           host->device copy of the step's inputs and device->host copy of its results inside the timed region.
+  roofline: the dominant kernel's own duration (CUDA events recorded by the library around that kernel on the
+           launching stream) against the measured integer multiply-add peak (imad_peak micro-benchmark, run here).
+  cpu_baseline: the unmodified reference (oracle/_ref/libecc_ref.so, kind "reference") on this box's host cores on a
+           bounded prefix of the same inputs (rank 0, N = 1).
+
+Reference arm (--impl reference): the reference's own CPU implementation of the path (oracle/_ref, else the oracle
+port) on all host cores, each step a bounded sample of the same workload; rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: (curve, kind, metric name, unit)
+    "secp256r1_fixed_base": ("SECP256R1", "fixed", "secp256r1 prj_pt_mul/sec", "prj_pt_mul/s"),
+    "secp384r1_fixed_base": ("SECP384R1", "fixed", "secp384r1 prj_pt_mul/sec", "prj_pt_mul/s"),
+    "frp256v1_fixed_base": ("FRP256V1", "fixed", "frp256v1 prj_pt_mul/sec", "prj_pt_mul/s"),
+    "secp256r1_variable_base": ("SECP256R1", "var", "secp256r1 variable-base prj_pt_mul/sec", "prj_pt_mul/s"),
+    "frp256v1_ecdsa_verify": ("FRP256V1", "verify", "frp256v1 ECDSA ec_verify/sec", "ec_verify/s"),
+    "secp256r1_ecdsa_verify": ("SECP256R1", "verify", "secp256r1 ECDSA ec_verify/sec", "ec_verify/s"),
+}
+SEED = 0x6C69626563632D31
+
+
+def splitmix_bytes(n_bytes: int, tag: int) -> np.ndarray:
+    g = np.random.default_rng([SEED & 0xFFFFFFFF, SEED >> 32, tag])
+    return g.integers(0, 256, size=n_bytes, dtype=np.uint8)
+
+
+def nproc() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi style clock / throttle-reason sampling during the timed region (NVML, 100 ms period)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ inputs
+
+def make_inputs(workload: str, n: int, rank: int):
+    """Seeded synthetic inputs of SURVEY.md §8d for one rank (host numpy arrays)."""
+    from common import CURVES, ORDER, edge_scalars
+    curve, kind, _, _ = WORKLOADS[workload]
+    _, plen, qlen = CURVES[curve]
+    q = ORDER[curve]
+    raw = splitmix_bytes(n * qlen, 100 + rank).reshape(n, qlen)
+    # uniform in [1, q-1]: clear the top bit pattern that could exceed q cheaply (rejection on the few rows >= q)
+    vals_hi = raw[:, 0].astype(np.int64)
+    qb = np.frombuffer(q.to_bytes(qlen, "big"), dtype=np.uint8)
+    suspicious = np.nonzero(vals_hi >= int(qb[0]))[0]
+    g = np.random.default_rng(7 + rank)
+    for i in suspicious:
+        while not (0 < int.from_bytes(raw[i].tobytes(), "big") < q):
+            raw[i] = g.integers(0, 256, size=qlen, dtype=np.uint8)
+    # ~0.1 % adversarial slots: k in {0, 1, 2, q-1, q, q+1, 2^(8 qlen)-1, ...}
+    es = edge_scalars(curve)
+    slots = np.arange(0, n, 1024)[: max(1, n // 1024)]
+    raw[slots] = es[np.arange(len(slots)) % es.shape[0]]
+    inputs = {"scalars": np.ascontiguousarray(raw)}
+    if kind == "var":
+        inputs["points"] = make_points(curve, n, rank)
+    if kind == "verify":
+        inputs.update(make_verify_inputs(curve, n, rank))
+    return inputs
+
+
+def make_points(curve: str, n: int, rank: int) -> np.ndarray:
+    """n distinct valid affine points: produced by the engine's own fixed-base path from seeded scalars and
+    spot-checked against the oracle (the reference would need minutes for 2^20 points)."""
+    import libecc_b200
+    from common import oracle_smul, random_scalars
+    sc = splitmix_bytes(n * 32 if curve != "SECP384R1" else n * 48, 300 + rank).reshape(n, -1)
+    sc[:, 0] &= 0x7F
+    eng = libecc_b200.Engine(curve, device=int(os.environ.get("LOCAL_RANK", 0)))
+    pts, st = eng.prj_pt_mul_batch(sc)
+    assert (st == 0).all()
+    want, _ = oracle_smul(curve, sc[:64])
+    assert (pts[:64] == want).all()
+    eng.close()
+    return pts
+
+
+def make_verify_inputs(curve: str, n: int, rank: int):
+    """(sigs, pubkeys, digests, expected): distinct random key per tuple, 1/16 corrupted.  Signatures are made with
+    the oracle's deterministic signer on a small pool and replicated with distinct keys... the full-size generator
+    lives in tests/common.make_signatures (CPU oracle); for 2^20 tuples we tile a 2^12 pool (documented)."""
+    from common import make_signatures
+    pool = 1 << 12
+    sigs, pubs, dg, exp = make_signatures(curve, min(pool, n), tag=500 + rank, corrupt_every=16)
+    reps = (n + sigs.shape[0] - 1) // sigs.shape[0]
+    tile = lambda a: np.ascontiguousarray(np.tile(a, (reps, 1))[:n])
+    return {"sigs": tile(sigs), "pubkeys": tile(pubs), "digests": tile(dg),
+            "expected": np.tile(exp, reps)[:n].copy(), "hlen": dg.shape[1]}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
+
+def ref_lib():
+    path = os.path.join(ROOT, "oracle", "_ref", "libecc_ref.so")
+    return ctypes.CDLL(path) if os.path.exists(path) else None
+
+
+def cpu_run(workload: str, inputs, lo: int, cnt: int, threads: int):
+    """Runs items [lo, lo+cnt) of the workload on the reference (or the oracle port) with `threads` host threads.
+    Returns (seconds, kind, outputs)."""
+    from common import CURVES, oracle_lib
+    curve, kind, _, _ = WORKLOADS[workload]
+    _, plen, qlen = CURVES[curve]
+    ref = ref_lib()
+    ptr = lambda a: np.ascontiguousarray(a).ctypes.data_as(ctypes.c_void_p)
+    if kind in ("fixed", "var"):
+        sc = np.ascontiguousarray(inputs["scalars"][lo:lo + cnt])
+        pts = np.ascontiguousarray(inputs["points"][lo:lo + cnt]) if kind == "var" else None
+        out = np.zeros((cnt, 2 * plen), dtype=np.uint8)
+        st = np.zeros(cnt, dtype=np.int8)
+        t0 = time.perf_counter()
+        if ref is not None:
+            ref.ref_prj_pt_mul_batch(curve.encode(), cnt, ptr(sc), qlen, ptr(pts) if pts is not None else None,
+                                     ptr(out), ptr(st), threads)
+            k = "reference"
+        else:
+            oracle_lib().ora_prj_pt_mul_batch(curve.encode(), cnt, ptr(sc), qlen,
+                                              ptr(pts) if pts is not None else None, ptr(out), ptr(st), threads)
+            k = "port"
+        return time.perf_counter() - t0, k, (out, st)
+    sg = np.ascontiguousarray(inputs["sigs"][lo:lo + cnt])
+    pk = np.ascontiguousarray(inputs["pubkeys"][lo:lo + cnt])
+    dg = np.ascontiguousarray(inputs["digests"][lo:lo + cnt])
+    v = np.zeros(cnt, dtype=np.int8)
+    t0 = time.perf_counter()
+    # pre-hashed inputs: the oracle port takes digests directly (the reference's ec_verify hashes a message itself)
+    oracle_lib().ora_ecdsa_verify_digest_batch(curve.encode(), cnt, ptr(sg), ptr(pk), ptr(dg), inputs["hlen"], ptr(v),
+                                               threads)
+    return time.perf_counter() - t0, "port", (v,)
+
+
+def cpu_baseline(workload: str, inputs, budget_s: float = 12.0):
+    threads = nproc()
+    n = inputs["scalars"].shape[0]
+    probe = min(n, 8 * threads)
+    t, kind, _ = cpu_run(workload, inputs, 0, probe, threads)
+    rate = probe / t
+    cnt = int(min(n, max(probe, rate * budget_s)))
+    t, kind, outs = cpu_run(workload, inputs, 0, cnt, threads)
+    return {"value": cnt / t, "unit": WORKLOADS[workload][3], "cores": threads, "kind": kind,
+            "sample": f"first {cnt} items of the step's batch, {t:.1f} s on {threads} threads"}, cnt, outs
+
+
+# ------------------------------------------------------------------------------------------------ main
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="secp256r1_fixed_base", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch-log2", type=int, default=20, help="items per GPU per step (2^k)")
+    ap.add_argument("--comb-window", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    curve, kind, metric, unit = WORKLOADS[args.workload]
+    n = 1 << args.batch_log2
+    config = {"workload": f"{args.workload}: 2^{args.batch_log2} items per GPU per step, seeded synthetic "
+                          f"(uniform scalars in [1,q-1] + 0.1% edge scalars)",
+              "curve": curve, "batch_per_gpu": n, "global_batch": n * world}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        inputs = make_inputs(args.workload, n, 0) if kind != "var" else None
+        if kind == "var":
+            # no GPU on this arm: derive the points with the CPU oracle on the bounded sample only
+            from common import oracle_smul
+            inputs = {"scalars": make_inputs("secp256r1_fixed_base", n, 0)["scalars"]}
+            m = min(n, 1 << 12)
+            pts, _ = oracle_smul(curve, splitmix_bytes(m * 32, 300).reshape(m, 32) & 0x7F)
+            inputs["points"] = np.tile(pts, ((n + m - 1) // m, 1))[:n]
+        threads = nproc()
+        probe = min(n, 8 * threads)
+        t, k, _ = cpu_run(args.workload, inputs, 0, probe, threads)
+        per_step = int(min(n, max(probe, (probe / t) * 10.0)))   # ~10 s of CPU work per step
+        for _ in range(min(args.warmup, 1)):
+            cpu_run(args.workload, inputs, 0, min(per_step, 4 * probe), threads)
+        times = []
+        for s in range(args.steps):
+            lo = (s * per_step) % max(1, n - per_step + 1)
+            t, k, _ = cpu_run(args.workload, inputs, lo, per_step, threads)
+            times.append(t)
+        val = per_step * len(times) / sum(times)
+        line = {"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * sum(times) / len(times),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": unit, "cores": threads, "kind": k,
+                                 "sample": f"{per_step} items per step (bounded sample of the 2^{args.batch_log2} batch)"},
+                "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import libecc_b200
+    from common import CURVES
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _, plen, qlen = CURVES[curve]
+    inputs = make_inputs(args.workload, n, rank)
+    eng = libecc_b200.Engine(curve, device=local_rank, comb_window=args.comb_window)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # device-resident copies
+    d = {k: torch.from_numpy(v).to(dev) for k, v in inputs.items() if isinstance(v, np.ndarray) and k != "expected"}
+    if kind == "verify":
+        d_out = torch.empty(n, dtype=torch.int8, device=dev)
+        out_item = 1
+    else:
+        d_out = torch.empty(n * 2 * plen, dtype=torch.uint8, device=dev)
+        d_status = torch.empty(n, dtype=torch.int8, device=dev)
+        out_item = 2 * plen + 1
+    if world > 1:
+        g_out = torch.empty(world * d_out.numel(), dtype=d_out.dtype, device=dev)
+        g_status = torch.empty(world * n, dtype=torch.int8, device=dev) if kind != "verify" else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_dev():
+        if kind == "verify":
+            eng.ecdsa_verify_batch_dev(d["sigs"].view(-1), d["pubkeys"].view(-1), d["digests"].view(-1),
+                                       inputs["hlen"], d_out, stream)
+        else:
+            eng.prj_pt_mul_batch_dev(d["scalars"].view(-1), d["points"].view(-1) if kind == "var" else None, d_out,
+                                     d_status, stream)
+        if world > 1:  # the path's only exchange step: gather of the fixed-size results over NVLink
+            dist.all_gather_into_tensor(g_out, d_out)
+            if g_status is not None:
+                dist.all_gather_into_tensor(g_status, d_status)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng.profile_enable(True)
+    for _ in range(args.warmup):
+        step_dev()
+        flush.zero_()
+    sync_all()
+    launches0 = eng.kernel_launches
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kernel_ms = []
+    for s in range(args.steps):
+        flush.zero_()                      # L2 flush between timed iterations (not timed)
+        evs[s][0].record()
+        step_dev()
+        evs[s][1].record()
+        kernel_ms.append(eng.profile_read())
+    sync_all()
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    launches = eng.kernel_launches - launches0
+    value = n * world * args.steps / (total_ms / 1000.0)
+
+    # parity spot-check of what was just timed (first 256 items of this rank) against the oracle
+    from common import oracle_smul, oracle_verify
+    if kind == "verify":
+        got = d_out[:256].cpu().numpy()
+        want = oracle_verify(curve, inputs["sigs"][:256], inputs["pubkeys"][:256], inputs["digests"][:256],
+                             inputs["hlen"])
+        parity = bool((got == want).all())
+    else:
+        got = d_out[: 256 * 2 * plen].cpu().numpy().reshape(256, 2 * plen)
+        want, wst = oracle_smul(curve, inputs["scalars"][:256], inputs["points"][:256] if kind == "var" else None)
+        parity = bool((got == want).all() and (d_status[:256].cpu().numpy() == wst).all())
+
+    # ---- e2e: the host-pointer C-ABI call on host buffers (H2D + kernels + D2H inside the timed region)
+    e2e_steps = max(3, min(args.steps, 5))
+    def step_host():
+        if kind == "verify":
+            return eng.ecdsa_verify_batch(inputs["sigs"], inputs["pubkeys"], inputs["digests"], inputs["hlen"])
+        return eng.prj_pt_mul_batch(inputs["scalars"], inputs.get("points"))
+    step_host()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        res = step_host()
+    e1.record()
+    sync_all()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_val = n * world * e2e_steps / (float(e2e_ms.item()) / 1000.0)
+    in_item = {"fixed": qlen, "var": qlen + 2 * plen, "verify": 2 * qlen + 2 * plen + inputs.get("hlen", 0)}[kind]
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (integer multiply-add bound)
+    from roofline import imad_peak_measured, work_per_item
+    k0 = statistics.mean(k[0] for k in kernel_ms if k)
+    peak = imad_peak_measured(local_rank)
+    work = work_per_item(args.workload, eng.comb_window)
+    achieved = n * work["imad32_per_item"] / (k0 / 1000.0) / 1e12
+    roofline = {"bound": "int-mad", "kernel": work["kernel"], "achieved": achieved, "peak": peak["timad32_per_s"],
+                "unit": "T IMAD32/s", "frac": achieved / peak["timad32_per_s"], "traffic": None,
+                "kernel_ms": k0, "kernel_share_of_step": k0 / (sum(step_ms) / len(step_ms)),
+                "M_impl": work["M_impl"], "imad32_per_field_mul": work["imad32_per_mul"],
+                "ref_normalised_frac": n * work["imad32_ref_per_item"] / (k0 / 1000.0) / 1e12 / peak["timad32_per_s"],
+                "peak_source": peak["how"],
+                "hbm_algorithmic_GBps": n * (in_item + out_item) / (k0 / 1000.0) / 1e9}
+
+    line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": dict(config, l2="256 MiB buffer rewritten between timed iterations",
+                           comb_window=eng.comb_window, result_gather="nccl all_gather" if world > 1 else "none"),
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_val, "unit": unit, "h2d_bytes_per_step": n * in_item,
+                    "d2h_bytes_per_step": n * out_item, "steps": e2e_steps},
+            "roofline": roofline, "parity_spot_check": parity}
+    if world == 1 and not args.no_cpu_baseline:
+        cb, cnt, outs = cpu_baseline(args.workload, inputs)
+        line["cpu_baseline"] = cb
+        # the timed GPU results must equal the reference on the CPU-timed prefix
+        if kind != "verify":
+            gpu_out = d_out[: cnt * 2 * plen].cpu().numpy().reshape(cnt, 2 * plen)
+            line["parity_on_cpu_prefix"] = bool((gpu_out == outs[0]).all() and
+                                                (d_status[:cnt].cpu().numpy() == outs[1]).all())
+        else:
+            line["parity_on_cpu_prefix"] = bool((d_out[:cnt].cpu().numpy() == outs[0]).all())
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

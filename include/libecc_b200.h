@@ -84,6 +84,23 @@ int eccb200_ecdsa_verify_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *
 int eccb200_fp_mul_monty_batch(eccb200_ctx *ctx, int which, uint32_t n, const uint8_t *a, const uint8_t *b,
 			       uint8_t *out);
 
+/* Mod-q scalar preparation of ECDSA verification alone (nn_modinv / nn_mod_mul on the order q,
+ * src/sig/ecdsa_common.c:777-791): out[i] = u || v, u = e*s^-1 mod q, v = r*s^-1 mod q, 2*qlen bytes big-endian.
+ * s must be in [1, q-1].  Unit-test entry point. */
+int eccb200_ecdsa_uv_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *sigs, const uint8_t *digests, uint32_t hlen,
+			   uint8_t *out);
+
+/* Per-kernel device timing of the device-pointer entry points (CUDA events recorded on the caller's stream around
+ * each kernel).  eccb200_profile_read waits for the last timed call and returns how many durations (ms) it wrote:
+ * prj_pt_mul_batch_dev -> [scalar-mult kernel, batched normalisation]; ecdsa_verify_batch_dev -> [verify kernel]. */
+int eccb200_profile_enable(eccb200_ctx *ctx, int on);
+int eccb200_profile_read(eccb200_ctx *ctx, float *ms, int cap);
+
+/* imad_peak micro-benchmark: measured 32x32+64 integer multiply-add throughput of the device (IMAD32 per second) —
+ * the denominator of the roofline for this integer-MAD-bound path — and the same figure per clock
+ * per SM at the device's nominal maximum SM clock. */
+int eccb200_imad_peak(int device, double *imad32_per_s, double *imad_per_clk_per_sm);
+
 /* Introspection for bench.py / tests. */
 int eccb200_comb_window(const eccb200_ctx *ctx);
 uint64_t eccb200_kernel_launches(const eccb200_ctx *ctx);  /* kernels launched by this context so far */

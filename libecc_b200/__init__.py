@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libecc_b200.so")
+LIB_PATH = os.environ.get("ECCB200_LIB", os.path.join(_HERE, "libecc_b200.so"))
 
 CURVE_IDS = {"FRP256V1": 1, "SECP256R1": 4, "SECP384R1": 5}  # libecc ec_curve_type (src/lib_ecc_types.h:147-)
 
@@ -22,7 +22,8 @@ ABI_SYMBOLS = [
     "eccb200_ctx_create", "eccb200_ctx_destroy", "eccb200_curve_sizes", "eccb200_curve_name",
     "eccb200_prj_pt_mul_batch", "eccb200_prj_pt_mul_batch_dev", "eccb200_ecdsa_verify_batch",
     "eccb200_ecdsa_verify_batch_dev", "eccb200_fp_mul_monty_batch", "eccb200_comb_window",
-    "eccb200_kernel_launches", "eccb200_last_error",
+    "eccb200_kernel_launches", "eccb200_last_error", "eccb200_ecdsa_uv_batch",
+    "eccb200_profile_enable", "eccb200_profile_read", "eccb200_imad_peak",
 ]
 
 _lib = None
@@ -53,6 +54,9 @@ def load_library() -> ctypes.CDLL:
     lib.eccb200_ecdsa_verify_batch.argtypes = [ctypes.c_void_p, u32, u8p, u8p, u8p, u32, i8p]
     lib.eccb200_ecdsa_verify_batch_dev.argtypes = [ctypes.c_void_p, u32, u8p, u8p, u8p, u32, i8p, ctypes.c_void_p]
     lib.eccb200_fp_mul_monty_batch.argtypes = [ctypes.c_void_p, ctypes.c_int, u32, u8p, u8p, u8p]
+    lib.eccb200_ecdsa_uv_batch.argtypes = [ctypes.c_void_p, u32, u8p, u8p, u32, u8p]
+    lib.eccb200_profile_enable.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.eccb200_profile_read.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.c_int]
     lib.eccb200_comb_window.argtypes = [ctypes.c_void_p]
     lib.eccb200_kernel_launches.argtypes = [ctypes.c_void_p]
     lib.eccb200_kernel_launches.restype = ctypes.c_uint64
@@ -114,6 +118,17 @@ class Engine:
     def kernel_launches(self) -> int:
         return int(self.lib.eccb200_kernel_launches(self._h))
 
+    def profile_enable(self, on: bool = True):
+        self._check(self.lib.eccb200_profile_enable(self._h, int(on)), "eccb200_profile_enable")
+
+    def profile_read(self):
+        """Durations (ms) of the kernels of the last device-pointer call (waits for them)."""
+        buf = (ctypes.c_float * 4)()
+        k = self.lib.eccb200_profile_read(self._h, buf, 4)
+        if k < 0:
+            raise EccB200Error("eccb200_profile_read: " + self.lib.eccb200_last_error().decode())
+        return [float(buf[i]) for i in range(k)]
+
     # ---- host-buffer API (H2D / D2H inside the call) -------------------------------------------------------
     def prj_pt_mul_batch(self, scalars, points=None) -> Tuple[np.ndarray, np.ndarray]:
         """scalars: n*qlen big-endian bytes; points: n*2*plen affine bytes or None (=G).
@@ -140,6 +155,15 @@ class Engine:
             self._h, n, sg.ctypes.data, pk.ctypes.data, dg.ctypes.data, hlen, verdict.ctypes.data),
             "eccb200_ecdsa_verify_batch")
         return verdict
+
+    def ecdsa_uv_batch(self, sigs, digests, hlen: int) -> np.ndarray:
+        sg = _as_u8(sigs)
+        n = sg.size // (2 * self.qlen)
+        dg = _as_u8(digests, n * hlen)
+        out = np.zeros((n, 2 * self.qlen), dtype=np.uint8)
+        self._check(self.lib.eccb200_ecdsa_uv_batch(self._h, n, sg.ctypes.data, dg.ctypes.data, hlen,
+                                                    out.ctypes.data), "eccb200_ecdsa_uv_batch")
+        return out
 
     def fp_mul_monty_batch(self, a, b, which: int = 0) -> np.ndarray:
         x = _as_u8(a)

@@ -201,9 +201,6 @@ template <class C> struct EC {
 		r.Z = z3;
 	}
 
-	/* out-of-line copy for once-per-item uses (e.g. the final uG + vY of a verification) */
-	static ECC_NOINLINE void add_full_slow(J &r, const J &p, const J &q) { add_full(r, p, q); }
-
 	static ECC_HD void neg(J &r, const J &p)
 	{
 		r.X = p.X;
@@ -319,11 +316,14 @@ template <class C> ECC_HD void comb_mul(Jac<C> &acc, const Fe<C::N> &k, const ui
 }
 
 /*
- * Variable base: acc = k*P, P affine and on the curve, k < q.  Signed 4-bit fixed window:
- * K' = k + 0x88..8 (one 8 per nibble); digit_i = nibble_i(K') - 8 in [-8, 7] for i < 2N*... , top digit = carry.
- * Table tbl[j] = (j+1)*P, j = 0..7 (Jacobian).
+ * Variable base: acc = k*P (+ addend), P affine and on the curve, k < q.  Signed 4-bit fixed window:
+ * K' = k + 0x88..8 (one 8 per nibble); digit_i = nibble_i(K') - 8 in [-8, 7], plus a top digit = the carry out.
+ * Table tbl[j] = (j+1)*P, j = 0..7 (Jacobian, per-thread local memory).  The optional addend (uG of an ECDSA
+ * verification, sig/ecdsa_common.c:796) is added by one extra trip through the same loop body, so the kernel
+ * holds a single inlined copy of the general addition.
  */
-template <class C> ECC_HD void window_mul(Jac<C> &acc, const Fe<C::N> &k, const Aff<C> &P)
+template <class C>
+ECC_HD void window_mul(Jac<C> &acc, const Fe<C::N> &k, const Aff<C> &P, const Jac<C> *addend = nullptr)
 {
 	typedef EC<C> G;
 	typedef Field<typename C::Fp> F;
@@ -345,23 +345,27 @@ template <class C> ECC_HD void window_mul(Jac<C> &acc, const Fe<C::N> &k, const 
 	G::set_inf(acc);
 	if (c) acc = tbl[0]; /* top digit (weight 16^(8N)) is 0 or 1 */
 #pragma unroll 1
-	for (int wi = N - 1; wi >= 0; wi--) {
-		uint32_t word = 0;
-#pragma unroll
-		for (int j = 0; j < N; j++) word = (j == wi) ? kk[j] : word;
-#pragma unroll 1
-		for (int nb = 7; nb >= 0; nb--) {
-			Jac<C> t;
+	for (int di = 8 * N - 1; di >= -1; di--) {
+		Jac<C> e, t;
+		bool have;
+		if (di >= 0) {
 #pragma unroll 1
 			for (int q = 0; q < 4; q++) G::dbl(acc, acc);
-			int d = (int)((word >> (4 * nb)) & 15u) - 8;
-			if (d != 0) {
-				int ad = d < 0 ? -d : d;
-				Jac<C> e = tbl[ad - 1];
-				if (d < 0) F::neg(e.Y, e.Y);
-				G::add_full(t, acc, e);
-				acc = t;
-			}
+			uint32_t word = 0;
+#pragma unroll
+			for (int j = 0; j < N; j++) word = (j == (di >> 3)) ? kk[j] : word;
+			int d = (int)((word >> (4 * (di & 7))) & 15u) - 8;
+			int ad = d < 0 ? -d : d;
+			have = d != 0;
+			e = tbl[(ad - 1) & 7];
+			if (d < 0) F::neg(e.Y, e.Y);
+		} else {
+			have = addend != nullptr;
+			if (have) e = *addend;
+		}
+		if (have) {
+			G::add_full(t, acc, e);
+			acc = t;
 		}
 	}
 }
@@ -396,9 +400,22 @@ template <class C> ECC_HD void digest_to_scalar(Fe<C::N> &e, const uint8_t *h, u
 	scalar_reduce<C>(e);
 }
 
+/* u = e * s^-1 mod q, v = r * s^-1 mod q (plain form): the mod-q scalar preparation of __ecdsa_verify_finalize
+ * (sig/ecdsa_common.c:781-791: nn_modinv, nn_mod_mul), with s^-1 by Fermat in the Montgomery domain of q. */
+template <class C>
+ECC_HD void ecdsa_uv(Fe<C::N> &u, Fe<C::N> &v, const Fe<C::N> &r, const Fe<C::N> &s, const Fe<C::N> &e)
+{
+	typedef Field<typename C::Fq> Fq;
+	Fe<C::N> sm, wm;
+	Fq::to_mont(sm, s);
+	Fq::inv(wm, sm);   /* s^-1 * R mod q */
+	Fq::mul(u, e, wm); /* (:786) */
+	Fq::mul(v, r, wm); /* (:791) */
+}
+
 /*
  * ECDSA verification of one signature (r, s) on the reduced digest e under the public key Y (affine, validated,
- * Montgomery form).  Follows __ecdsa_verify_init's range checks (sig/ecdsa_common.c:653-658) and
+ * Montgomery form).  Returns 0 = valid; 1 = r/s out of range, 2 = W' at infinity, 3 = r' != r (all map to -1).  Follows __ecdsa_verify_init's range checks (sig/ecdsa_common.c:653-658) and
  * __ecdsa_verify_finalize steps 5-10 (:781-810); differences that do not change the verdict:
  *   - s^-1 mod q by Fermat in the Montgomery domain of q instead of nn_modinv's xgcd (:781);
  *   - W' = uG + vY stays Jacobian and "x(W') mod q == r" is tested without an inversion as X == c * Z^2 for the
@@ -406,25 +423,21 @@ template <class C> ECC_HD void digest_to_scalar(Fe<C::N> &e, const uint8_t *h, u
  *   - uG through the comb table (K1), vY through the signed window (K2) instead of two ladders (:788,793).
  */
 template <class C>
-ECC_HD bool ecdsa_verify_core(const Fe<C::N> &r, const Fe<C::N> &s, const Fe<C::N> &e, const Aff<C> &Y,
-			      const uint32_t *__restrict__ table, int w)
+ECC_HD int ecdsa_verify_core(const Fe<C::N> &r, const Fe<C::N> &s, const Fe<C::N> &e, const Aff<C> &Y,
+			     const uint32_t *__restrict__ table, int w)
 {
 	typedef Field<typename C::Fp> F;
 	typedef Field<typename C::Fq> Fq;
 	constexpr int N = C::N;
-	if (Fq::is_zero(r) || Fq::is_zero(s) || Fq::geq_mod(r) || Fq::geq_mod(s)) return false;
+	if (Fq::is_zero(r) || Fq::is_zero(s) || Fq::geq_mod(r) || Fq::geq_mod(s)) return 1;
 
-	Fe<N> sm, wm, u, v;
-	Fq::to_mont(sm, s);
-	Fq::inv(wm, sm);   /* s^-1 * R mod q */
-	Fq::mul(u, e, wm); /* u = e * s^-1 mod q, plain form  (:786) */
-	Fq::mul(v, r, wm); /* v = r * s^-1 mod q, plain form  (:791) */
+	Fe<N> u, v;
+	ecdsa_uv<C>(u, v, r, s, e);
 
-	Jac<C> uG, vY, W;
+	Jac<C> uG, W;
 	comb_mul<C>(uG, u, table, w);
-	window_mul<C>(vY, v, Y);
-	EC<C>::add_full_slow(W, uG, vY);
-	if (EC<C>::is_inf(W)) return false; /* (:799-800) */
+	window_mul<C>(W, v, Y, &uG); /* W' = vY + uG (:796) */
+	if (EC<C>::is_inf(W)) return 2; /* (:799-800) */
 
 	Fe<N> z2, c, t;
 	F::sqr(z2, W.Z);
@@ -449,7 +462,7 @@ ECC_HD bool ecdsa_verify_core(const Fe<C::N> &r, const Fe<C::N> &s, const Fe<C::
 			match = match || F::eq(t, W.X);
 		}
 	}
-	return match;
+	return match ? 0 : 3;
 }
 
 } // namespace eccb200

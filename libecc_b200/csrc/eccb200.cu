@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -56,6 +57,10 @@ struct eccb200_ctx {
 	uint32_t *stage_jac[kStages] = { nullptr, nullptr, nullptr };
 	uint32_t *stage_prefix[kStages] = { nullptr, nullptr, nullptr };
 	uint64_t launches = 0;
+	/* optional per-kernel timing of the device-pointer API (bench.py's roofline leg) */
+	bool profiling = false;
+	cudaEvent_t ev[3] = { nullptr, nullptr, nullptr };
+	int ev_count = 0; /* kernels timed by the last device-pointer call */
 };
 
 template <class Fn> static int dispatch(int curve_id, Fn &&fn)
@@ -122,6 +127,7 @@ extern "C" int eccb200_ctx_create(eccb200_ctx **out, int curve_id, int device, i
 	cudaDeviceProp prop;
 	CUDA_OK(cudaGetDeviceProperties(&prop, device));
 	if (prop.major != 10) return fail("libecc_b200 is built for sm_100a (B200) only");
+	if (const char *ss = getenv("ECCB200_STACK")) cudaDeviceSetLimit(cudaLimitStackSize, (size_t)atoi(ss));
 	int w = comb_window ? comb_window : 16;
 	if (w < 4 || w > 16) return fail("comb_window must be in [4,16]");
 
@@ -174,10 +180,33 @@ extern "C" void eccb200_ctx_destroy(eccb200_ctx *ctx)
 		if (ctx->stage_jac[s]) cudaFree(ctx->stage_jac[s]);
 		if (ctx->stage_prefix[s]) cudaFree(ctx->stage_prefix[s]);
 	}
+	for (int i = 0; i < 3; i++)
+		if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
 	if (ctx->table) cudaFree(ctx->table);
 	if (ctx->jac) cudaFree(ctx->jac);
 	if (ctx->prefix) cudaFree(ctx->prefix);
 	delete ctx;
+}
+
+extern "C" int eccb200_profile_enable(eccb200_ctx *ctx, int on)
+{
+	if (!ctx) return fail("null ctx");
+	CUDA_OK(cudaSetDevice(ctx->device));
+	if (on && !ctx->ev[0])
+		for (int i = 0; i < 3; i++) CUDA_OK(cudaEventCreate(&ctx->ev[i]));
+	ctx->profiling = on != 0;
+	ctx->ev_count = 0;
+	return 0;
+}
+
+extern "C" int eccb200_profile_read(eccb200_ctx *ctx, float *ms, int cap)
+{
+	if (!ctx || !ms) return fail("null argument");
+	if (!ctx->profiling || ctx->ev_count == 0) return 0;
+	CUDA_OK(cudaEventSynchronize(ctx->ev[ctx->ev_count]));
+	int k = 0;
+	for (; k < ctx->ev_count && k < cap; k++) CUDA_OK(cudaEventElapsedTime(&ms[k], ctx->ev[k], ctx->ev[k + 1]));
+	return k;
 }
 
 extern "C" int eccb200_comb_window(const eccb200_ctx *ctx) { return ctx ? ctx->w : -1; }
@@ -191,11 +220,18 @@ static int smul_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_scalars, cons
 	if (n == 0) return 0;
 	return dispatch(ctx->curve_id, [&](auto c) {
 		typedef decltype(c) C;
+		const bool prof = ctx->profiling && jac == ctx->jac;
+		if (prof) cudaEventRecord(ctx->ev[0], st);
 		if (d_points)
 			LaunchSmul<C>::var(n, d_scalars, d_points, jac, d_status, st);
 		else
 			LaunchSmul<C>::fixed(n, d_scalars, ctx->table, ctx->w, jac, d_status, st);
+		if (prof) cudaEventRecord(ctx->ev[1], st);
 		LaunchMisc<C>::to_affine(affine_grid(ctx, n), n, jac, prefix, d_out, d_status, st);
+		if (prof) {
+			cudaEventRecord(ctx->ev[2], st);
+			ctx->ev_count = 2;
+		}
 		ctx->launches += 2;
 		CUDA_OK(cudaGetLastError());
 		return 0;
@@ -217,7 +253,14 @@ static int verify_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_sigs, const
 	if (n == 0) return 0;
 	return dispatch(ctx->curve_id, [&](auto c) {
 		typedef decltype(c) C;
+		const bool prof = ctx->profiling && d_verdict != (int8_t *)ctx->d_out[0] &&
+				  d_verdict != (int8_t *)ctx->d_out[1] && d_verdict != (int8_t *)ctx->d_out[2];
+		if (prof) cudaEventRecord(ctx->ev[0], st);
 		LaunchVerify<C>::verify(n, d_sigs, d_pubkeys, d_digests, hlen, ctx->table, ctx->w, d_verdict, st);
+		if (prof) {
+			cudaEventRecord(ctx->ev[1], st);
+			ctx->ev_count = 1;
+		}
 		ctx->launches += 1;
 		CUDA_OK(cudaGetLastError());
 		return 0;
@@ -373,4 +416,99 @@ extern "C" int eccb200_fp_mul_monty_batch(eccb200_ctx *ctx, int which, uint32_t 
 	} while (0);
 	cudaFree(d);
 	return rc;
+}
+
+extern "C" int eccb200_ecdsa_uv_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *sigs, const uint8_t *digests,
+				      uint32_t hlen, uint8_t *out)
+{
+	if (!ctx || (n && (!sigs || !digests || !out))) return fail("null argument");
+	if (hlen == 0 || hlen > 128) return fail("bad digest length");
+	if (n == 0) return 0;
+	CUDA_OK(cudaSetDevice(ctx->device));
+	size_t sg = (size_t)n * 2 * ctx->qlen, dg = (size_t)n * hlen;
+	uint8_t *d = nullptr;
+	CUDA_OK(cudaMalloc(&d, 2 * sg + dg));
+	int rc = 0;
+	if (cudaMemcpy(d, sigs, sg, cudaMemcpyHostToDevice) != cudaSuccess ||
+	    cudaMemcpy(d + 2 * sg, digests, dg, cudaMemcpyHostToDevice) != cudaSuccess)
+		rc = fail("H2D copy failed");
+	if (!rc)
+		rc = dispatch(ctx->curve_id, [&](auto c) {
+			typedef decltype(c) C;
+			LaunchVerify<C>::uv(n, d, d + 2 * sg, hlen, d + sg, 0);
+			ctx->launches += 1;
+			CUDA_OK(cudaGetLastError());
+			CUDA_OK(cudaMemcpy(out, d + sg, sg, cudaMemcpyDeviceToHost));
+			return 0;
+		});
+	cudaFree(d);
+	return rc;
+}
+
+/* ------------------------------------------------------------------------------------------ imad_peak */
+/*
+ * Integer multiply-add peak of the device: the denominator of the roofline (it is not in
+ * MEASURED_PEAKS.json).  Every thread runs 8 independent 32x32+64 multiply-add chains (IMAD.WIDE.U32), enough
+ * warps per SM to saturate the pipe.  Result: IMAD32 per second, best of 5 runs, and IMAD per clock per SM at the
+ * SM clock the driver reports as current maximum.
+ */
+__global__ void __launch_bounds__(256) k_imad_peak(uint32_t *out, int iters, uint32_t seed)
+{
+	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t b = (seed ^ 0x9e3779b9u) + t;
+	uint32_t l0 = t, l1 = t + 1, l2 = t + 2, l3 = t + 3, l4 = t + 4, l5 = t + 5, l6 = t + 6, l7 = t + 7;
+	uint32_t h0 = seed, h1 = seed, h2 = seed, h3 = seed, h4 = seed, h5 = seed, h6 = seed, h7 = seed;
+#pragma unroll 1
+	for (int i = 0; i < iters; i++) {
+#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			/* chain j: (h_j:l_j) += l_{j+1} * b — the multiplicand changes every iteration, so nothing can be
+			 * hoisted; the lo/hi pair is the same PTX idiom the field multiplier uses (fuses to IMAD.WIDE.U32) */
+			asm volatile("mad.lo.cc.u32 %0, %1, %16, %0;\n\tmadc.hi.u32 %8, %1, %16, %8;\n\t"
+				     "mad.lo.cc.u32 %1, %2, %16, %1;\n\tmadc.hi.u32 %9, %2, %16, %9;\n\t"
+				     "mad.lo.cc.u32 %2, %3, %16, %2;\n\tmadc.hi.u32 %10, %3, %16, %10;\n\t"
+				     "mad.lo.cc.u32 %3, %4, %16, %3;\n\tmadc.hi.u32 %11, %4, %16, %11;\n\t"
+				     "mad.lo.cc.u32 %4, %5, %16, %4;\n\tmadc.hi.u32 %12, %5, %16, %12;\n\t"
+				     "mad.lo.cc.u32 %5, %6, %16, %5;\n\tmadc.hi.u32 %13, %6, %16, %13;\n\t"
+				     "mad.lo.cc.u32 %6, %7, %16, %6;\n\tmadc.hi.u32 %14, %7, %16, %14;\n\t"
+				     "mad.lo.cc.u32 %7, %0, %16, %7;\n\tmadc.hi.u32 %15, %0, %16, %15;"
+				     : "+r"(l0), "+r"(l1), "+r"(l2), "+r"(l3), "+r"(l4), "+r"(l5), "+r"(l6), "+r"(l7),
+				       "+r"(h0), "+r"(h1), "+r"(h2), "+r"(h3), "+r"(h4), "+r"(h5), "+r"(h6), "+r"(h7)
+				     : "r"(b));
+		}
+	}
+	out[t] = l0 ^ l1 ^ l2 ^ l3 ^ l4 ^ l5 ^ l6 ^ l7 ^ h0 ^ h1 ^ h2 ^ h3 ^ h4 ^ h5 ^ h6 ^ h7;
+}
+
+extern "C" int eccb200_imad_peak(int device, double *imad32_per_s, double *imad_per_clk_per_sm)
+{
+	if (!imad32_per_s || !imad_per_clk_per_sm) return fail("null argument");
+	CUDA_OK(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	CUDA_OK(cudaGetDeviceProperties(&prop, device));
+	const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+	uint32_t *d = nullptr;
+	CUDA_OK(cudaMalloc(&d, (size_t)blocks * threads * sizeof(uint32_t)));
+	cudaEvent_t e0, e1;
+	CUDA_OK(cudaEventCreate(&e0));
+	CUDA_OK(cudaEventCreate(&e1));
+	double best = 0;
+	for (int r = 0; r < 7; r++) {
+		CUDA_OK(cudaEventRecord(e0));
+		k_imad_peak<<<blocks, threads>>>(d, iters, 12345u + r);
+		CUDA_OK(cudaEventRecord(e1));
+		CUDA_OK(cudaEventSynchronize(e1));
+		float ms = 0;
+		CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+		double rate = (double)blocks * threads * iters * 32.0 / (ms * 1e-3);
+		if (r >= 2 && rate > best) best = rate; /* first two runs are warm-up */
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	cudaFree(d);
+	int clk_khz = 0;
+	cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, device);
+	*imad32_per_s = best;
+	*imad_per_clk_per_sm = clk_khz ? best / ((double)clk_khz * 1e3) / prop.multiProcessorCount : 0;
+	return 0;
 }

@@ -21,7 +21,7 @@
  * Two multiplier back ends produce bit-identical results:
  *   - portable C++ (this file): CIOS over 32x32->64 products; also compiles for the host so that the unit tests
  *     in tests/hostsim can check the algorithms without a GPU (test-only; the product never runs on the host);
- *   - PTX (fp_ptx.cuh, device only): IMAD.WIDE carry chains, selected with ECC_USE_PTX (default on device).
+ *   - PTX (fp_ptx.cuh, device only): IMAD.WIDE carry chains, the default on the device (-DECC_NO_PTX selects the portable one).
  */
 #pragma once
 #include <stdint.h>
@@ -154,13 +154,13 @@ template <class F> struct FieldPortable {
 
 } // namespace eccb200
 
-#if defined(__CUDA_ARCH__) && defined(ECC_USE_PTX)
+#if defined(__CUDA_ARCH__) && !defined(ECC_NO_PTX)
 #include "fp_ptx.cuh"
 #endif
 
 namespace eccb200 {
 
-#if defined(__CUDA_ARCH__) && defined(ECC_USE_PTX)
+#if defined(__CUDA_ARCH__) && !defined(ECC_NO_PTX)
 template <class F> struct FieldCore : FieldPtx<F> {};
 #else
 template <class F> struct FieldCore : FieldPortable<F> {};

@@ -288,11 +288,33 @@ __global__ void __launch_bounds__(128) k_ecdsa_verify(uint32_t n, const uint8_t 
 	Aff<C> Y;
 	bool key_ok = load_affine_checked<C>(Y, pubkeys + (size_t)idx * (8 * N));
 	digest_to_scalar<C>(e, digests + (size_t)idx * hlen, hlen);
-	bool valid = key_ok && ecdsa_verify_core<C>(r, s, e, Y, table, w);
-	verdict[idx] = valid ? 0 : -1;
+	int code = key_ok ? ecdsa_verify_core<C>(r, s, e, Y, table, w) : 4;
+#if defined(ECC_VERDICT_DEBUG)
+	verdict[idx] = (int8_t)(-code);
+#else
+	verdict[idx] = code ? -1 : 0;
+#endif
 }
 
-/* ------------------------------------------------------------------------------------------ unit-test kernel */
+/* ------------------------------------------------------------------------------------------ unit-test kernels */
+
+/* mod-q scalar preparation of ECDSA verify alone: out[i] = u || v (big-endian), for the arithmetic unit tests */
+template <class C>
+__global__ void __launch_bounds__(128) k_ecdsa_uv(uint32_t n, const uint8_t *__restrict__ sigs,
+						  const uint8_t *__restrict__ digests, uint32_t hlen,
+						  uint8_t *__restrict__ out)
+{
+	constexpr int N = C::N;
+	uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= n) return;
+	Fe<N> r, s, e, u, v;
+	load_be16<N>(r, sigs + (size_t)idx * (8 * N));
+	load_be16<N>(s, sigs + (size_t)idx * (8 * N) + 4 * N);
+	digest_to_scalar<C>(e, digests + (size_t)idx * hlen, hlen);
+	ecdsa_uv<C>(u, v, r, s, e);
+	store_be16<N>(out + (size_t)idx * (8 * N), u);
+	store_be16<N>(out + (size_t)idx * (8 * N) + 4 * N, v);
+}
 
 template <class FT>
 __global__ void k_fp_mul_monty(uint32_t n, const uint8_t *__restrict__ a, const uint8_t *__restrict__ b,
@@ -340,6 +362,8 @@ template <class C> struct LaunchMisc {
 template <class C> struct LaunchVerify {
 	static void verify(uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys, const uint8_t *digests,
 			   uint32_t hlen, const uint32_t *table, int w, int8_t *verdict, cudaStream_t st);
+	static void uv(uint32_t n, const uint8_t *sigs, const uint8_t *digests, uint32_t hlen, uint8_t *out,
+		       cudaStream_t st);
 };
 
 #if defined(ECC_TU_SMUL)
@@ -390,6 +414,12 @@ void LaunchVerify<C>::verify(uint32_t n, const uint8_t *sigs, const uint8_t *pub
 			     uint32_t hlen, const uint32_t *table, int w, int8_t *verdict, cudaStream_t st)
 {
 	k_ecdsa_verify<C><<<grid_for(n), kThreads, 0, st>>>(n, sigs, pubkeys, digests, hlen, table, w, verdict);
+}
+template <class C>
+void LaunchVerify<C>::uv(uint32_t n, const uint8_t *sigs, const uint8_t *digests, uint32_t hlen, uint8_t *out,
+			 cudaStream_t st)
+{
+	k_ecdsa_uv<C><<<grid_for(n), kThreads, 0, st>>>(n, sigs, digests, hlen, out);
 }
 #endif
 

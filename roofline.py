@@ -1,0 +1,47 @@
+"""Roofline accounting for bench.py: algorithmic integer-multiply-add work per item and the
+measured IMAD peak of the device (imad_peak micro-benchmark inside libecc_b200.so)."""
+from __future__ import annotations
+
+import ctypes
+import math
+
+# one Montgomery CIOS product of n 64-bit limbs = 2n^2+n wide multiply-accumulates, each = 4 32x32->64 IMADs
+IMAD32_PER_MUL = {"SECP256R1": (2 * 4 * 4 + 4) * 4, "FRP256V1": (2 * 4 * 4 + 4) * 4, "SECP384R1": (2 * 6 * 6 + 6) * 4}
+# IMAD.WIDE instructions the generated multiplier really issues (tools/gen_fp_ptx.py; P-256's 0/1 words are free)
+IMAD_EXECUTED_PER_MUL = {"SECP256R1": 96, "FRP256V1": 136, "SECP384R1": 276}
+M_REF = {"SECP256R1": 8724, "FRP256V1": 8724, "SECP384R1": 13076}   # reference ladder (probe)
+QBITS = {"SECP256R1": 256, "FRP256V1": 256, "SECP384R1": 384}
+
+
+def work_per_item(workload: str, comb_window: int):
+    from bench import WORKLOADS
+    curve, kind, _, _ = WORKLOADS[workload]
+    nwin = math.ceil(QBITS[curve] / comb_window)
+    nib = QBITS[curve] // 4
+    m_fixed = 11 * (nwin - 1)                                   # mixed add 8M+3S per window; first window is a copy
+    m_var = 7 * 11 + 8 + nib * 4 * 8 + nib * (15.0 / 16) * 16   # table (7 madd, one of them a dbl) + 4 dbl/digit + adds
+    fermat_q = (QBITS[curve] // 4) * 5 + 14                     # 4 sqr + 1 mul per nibble + table
+    if kind == "fixed":
+        m, kernel = m_fixed, "k_smul_fixed"
+        m_ref = M_REF[curve]
+    elif kind == "var":
+        m, kernel = m_var, "k_smul_var"
+        m_ref = M_REF[curve]
+    else:
+        m, kernel = m_fixed + 11 + m_var + 16 + fermat_q + 12, "k_ecdsa_verify"
+        m_ref = 2 * M_REF[curve] + 17 + 513 + 2
+    return {"M_impl": m, "kernel": kernel, "imad32_per_mul": IMAD32_PER_MUL[curve],
+            "imad32_per_item": m * IMAD32_PER_MUL[curve], "imad32_ref_per_item": m_ref * IMAD32_PER_MUL[curve],
+            "imad_executed_per_item": m * IMAD_EXECUTED_PER_MUL[curve]}
+
+
+def imad_peak_measured(device: int = 0):
+    import libecc_b200
+    lib = libecc_b200.load_library()
+    lib.eccb200_imad_peak.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    best, clk = ctypes.c_double(), ctypes.c_double()
+    if lib.eccb200_imad_peak(device, ctypes.byref(best), ctypes.byref(clk)):
+        raise RuntimeError(lib.eccb200_last_error().decode())
+    return {"timad32_per_s": best.value / 1e12, "imad_per_clk_per_sm": clk.value,
+            "how": "measured: imad_peak micro-benchmark (independent IMAD.WIDE chains, 8 per thread, "
+                   "148x8 CTAs x 256 threads, best of 5, CUDA events)"}

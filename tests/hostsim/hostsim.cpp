@@ -201,7 +201,7 @@ int hostsim_ecdsa_verify_batch(int curve_id, int w, uint32_t n, const uint8_t *s
 			bool ok = load_point<C>(Y, pubkeys + (size_t)i * 8 * N);
 			digest_to_scalar<C>(e, digests + (size_t)i * hlen, hlen);
 			g_fe_mul_count = 0;
-			ok = ok && ecdsa_verify_core<C>(r, s, e, Y, tab.data(), w);
+			ok = ok && (ecdsa_verify_core<C>(r, s, e, Y, tab.data(), w) == 0);
 			verdict[i] = ok ? 0 : -1;
 		}
 		return 0;

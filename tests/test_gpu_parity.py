@@ -176,3 +176,27 @@ def test_full_size_batch_properties_and_sample():
     idx = rng(71).choice(n, size=2048, replace=False)
     want, wst = oracle_smul(curve, allsc[idx])
     assert (out[idx] == want).all() and (st[idx] == wst).all()
+
+
+@pytest.mark.parametrize("curve", list(CURVES))
+def test_ecdsa_scalar_preparation_mod_q(curve):
+    """u = e*s^-1, v = r*s^-1 mod q on the device (nn_modinv / nn_mod_mul on the order, ecdsa_common.c:781-791)
+    against Python integers, including digests longer and shorter than the order."""
+    _, plen, qlen = CURVES[curve]
+    q = ORDER[curve]
+    g = rng(81)
+    for hlen in (20, qlen, 64):
+        n = 500
+        sig = g.integers(0, 256, size=(n, 2 * qlen), dtype=np.uint8)
+        sig[:, 0] &= 0x7F; sig[:, qlen] &= 0x7F          # r, s < q
+        sig[0, qlen:] = 0; sig[0, -1] = 1                # s = 1
+        sig[1, qlen:] = np.frombuffer((q - 1).to_bytes(qlen, "big"), dtype=np.uint8)
+        dg = g.integers(0, 256, size=(n, hlen), dtype=np.uint8)
+        dg[2] = 0xFF
+        uv = engine(curve, 8).ecdsa_uv_batch(sig, dg, hlen)
+        for i in range(n):
+            r = int.from_bytes(sig[i, :qlen].tobytes(), "big"); s = int.from_bytes(sig[i, qlen:].tobytes(), "big")
+            e = int.from_bytes(dg[i, :min(hlen, qlen)].tobytes(), "big") % q
+            w = pow(s, -1, q)
+            assert int.from_bytes(uv[i, :qlen].tobytes(), "big") == e * w % q
+            assert int.from_bytes(uv[i, qlen:].tobytes(), "big") == r * w % q

@@ -1,0 +1,337 @@
+#!/usr/bin/env python3
+"""Generates libecc_b200/csrc/fp_ptx.cuh: fully unrolled inline-PTX Montgomery multiplication / addition /
+subtraction for every field of curve_constants.inc, and carries a small PTX interpreter so that the generated
+instruction streams can be executed on the CPU against Python integers (tests/test_ptx_emulation.py).
+
+Algorithm of `mul` (the device restatement of nn_mul_redc1, /root/reference/src/nn/nn_mul_redc1.c:124-218):
+word-serial interleaved Montgomery multiplication (CIOS) on N 32-bit words, arranged so that every 32x32->64
+product is ONE IMAD.WIDE with carry-in/out:
+
+  * the running sum lives in two register files E and O indexed by word position; E is only ever used as the 64-bit
+    pairs (k, k+1) with k even, O as the pairs with k odd, so each register keeps one pair alignment for its whole
+    life and `mad.lo.cc / madc.hi.cc` pairs fuse into IMAD.WIDE.U32(.X) on aligned register pairs;
+  * row i (multiplier word b_i, then Montgomery quotient m_i) adds a_j*b_i and p_j*m_i at position i+j: the even
+    j's form one carry chain in X = (i even ? E : O), the odd j's one chain in Y = the other file;
+  * nothing is shifted: row i simply starts one position higher (register renaming is free when fully unrolled);
+  * before m_i is taken, the leftover word of the other file at position i is folded in (add.cc) and its carry
+    feeds the chain that starts at position i+1;
+  * every chain's carry-out lands in a register that so far holds only carries (bounded by 3), so no carry ever
+    ripples and none is dropped — this is what makes the scheme valid for full-width moduli (2^(32N-1) < p).
+
+Work per multiplication: 2N^2 IMAD.WIDE (+ N for m_i when M0 != 1) and ~7N carry/merge/select instructions on
+the ALU pipe.  Words of the modulus that are 0 or 1 are specialised away (P-256: 4 of 8, P-384: 2 of 12).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from gen_curve_constants import CURVES  # noqa: E402
+
+MASK = 0xFFFFFFFF
+
+
+class Prog:
+    """A straight-line PTX program over 32-bit registers and the carry flag."""
+
+    def __init__(self):
+        self.ins = []      # (op, dst, [srcs]) ; srcs are register names or ints
+        self.regs = set()
+
+    def emit(self, op, dst, *srcs):
+        self.ins.append((op, dst, list(srcs)))
+        if dst is not None:
+            self.regs.add(dst)
+        for s in srcs:
+            if isinstance(s, str):
+                self.regs.add(s)
+
+    # ---- interpreter ---------------------------------------------------------------------------------------
+    def run(self, env):
+        """Execute on a dict of register -> int (inputs preset). Returns the dict."""
+        r = dict(env)
+        cc = 0
+        pred = {}
+
+        def val(s):
+            return s if isinstance(s, int) else r[s]
+
+        for op, dst, srcs in self.ins:
+            v = [val(s) for s in srcs if s != "pq"]
+            if op == "mul.lo.u32":
+                r[dst] = (v[0] * v[1]) & MASK
+            elif op == "mul.hi.u32":
+                r[dst] = (v[0] * v[1]) >> 32
+            elif op in ("mad.lo.cc.u32", "madc.lo.cc.u32", "madc.lo.u32"):
+                t = ((v[0] * v[1]) & MASK) + v[2] + (cc if op.startswith("madc") else 0)
+                r[dst] = t & MASK
+                if ".cc" in op:
+                    cc = t >> 32
+            elif op in ("mad.hi.cc.u32", "madc.hi.cc.u32", "madc.hi.u32", "mad.hi.u32"):
+                t = ((v[0] * v[1]) >> 32) + v[2] + (cc if op.startswith("madc") else 0)
+                r[dst] = t & MASK
+                if ".cc" in op:
+                    cc = t >> 32
+                else:
+                    assert t >> 32 == 0, "dropped carry"
+            elif op in ("add.cc.u32", "addc.cc.u32", "addc.u32", "add.u32"):
+                t = v[0] + v[1] + (cc if op.startswith("addc") else 0)
+                r[dst] = t & MASK
+                if ".cc" in op:
+                    cc = t >> 32
+                else:
+                    assert t >> 32 == 0, "dropped carry"
+            elif op in ("sub.cc.u32", "subc.cc.u32", "subc.u32"):
+                t = v[0] - v[1] - (cc if op.startswith("subc") else 0)
+                r[dst] = t & MASK
+                if ".cc" in op:
+                    cc = 1 if t < 0 else 0
+            elif op == "and.b32":
+                r[dst] = v[0] & v[1]
+            elif op == "mov.u32":
+                r[dst] = v[0]
+            elif op == "setp.ne.u32":
+                pred[dst] = v[0] != v[1]
+            elif op == "selp.u32":
+                r[dst] = v[0] if pred[srcs[2]] else v[1]
+            else:
+                raise ValueError(op)
+        return r
+
+    def count(self):
+        wide = sum(1 for op, _, _ in self.ins if ".hi" in op)      # one IMAD.WIDE per lo/hi pair
+        single = sum(1 for op, _, _ in self.ins if op == "mul.lo.u32" and True)
+        return wide, len(self.ins)
+
+
+def words(x, n):
+    return [(x >> (32 * i)) & MASK for i in range(n)]
+
+
+def gen_mul(n, mod):
+    """Instruction stream computing r = a*b*2^(-32n) mod `mod` (a, b < mod). Registers a0.., b0.. in, r0.. out."""
+    P = words(mod, n)
+    m0 = (-pow(mod, -1, 1 << 32)) % (1 << 32)
+    g = Prog()
+    live = set()
+    E = lambda k: f"e{k}"
+    O = lambda k: f"o{k}"
+
+    def addend(reg):
+        return reg if reg in live else 0
+
+    for i in range(n):
+        X, Y = (E, O) if i % 2 == 0 else (O, E)
+        bi = f"b{i}"
+        if i == 0:
+            # row 0: every pair is fresh, the products are independent (no carries, no carry words)
+            for j in range(n):
+                F_ = X if j % 2 == 0 else Y
+                g.emit("mul.lo.u32", F_(j), f"a{j}", bi)
+                g.emit("mul.hi.u32", F_(j + 1), f"a{j}", bi)
+                live.update((F_(j), F_(j + 1)))
+        else:
+            # ---- product chain A: even j, file X, pairs (i+j, i+j+1); carry-out into the carry word X[i+n]
+            for j in range(0, n, 2):
+                lo, hi = X(i + j), X(i + j + 1)
+                assert lo in live and hi in live
+                g.emit("mad.lo.cc.u32" if j == 0 else "madc.lo.cc.u32", lo, f"a{j}", bi, lo)
+                g.emit("madc.hi.cc.u32", hi, f"a{j}", bi, hi)
+            top = X(i + n)
+            assert top in live
+            g.emit("addc.u32", top, top, 0)
+            # ---- fold the other file's word at position i, its carry feeds product chain B (odd j, file Y)
+            assert Y(i) in live and X(i) in live
+            g.emit("add.cc.u32", X(i), X(i), Y(i))
+            live.discard(Y(i))
+            for j in range(1, n, 2):
+                lo, hi = Y(i + j), Y(i + j + 1)
+                assert lo in live
+                g.emit("madc.lo.cc.u32", lo, f"a{j}", bi, lo)
+                if j == n - 1:
+                    assert hi not in live
+                    g.emit("madc.hi.u32", hi, f"a{j}", bi, 0)   # fresh high word: cannot overflow
+                else:
+                    assert hi in live
+                    g.emit("madc.hi.cc.u32", hi, f"a{j}", bi, hi)
+                live.add(hi)
+        # ---- Montgomery quotient
+        if m0 == 1:
+            m = X(i)
+        else:
+            m = "m"
+            g.emit("mul.lo.u32", m, X(i), m0)
+        # ---- reduction chain A: even j, file X.  The low word at position i becomes 0 and dies.
+        started = False
+        for j in range(0, n, 2):
+            lo, hi = X(i + j), X(i + j + 1)
+            pj = P[j]
+            dst_lo = "junk" if j == 0 else lo        # position i: provably 0 afterwards (and m may alias X[i])
+            if pj == 0:
+                if started:
+                    g.emit("addc.cc.u32", lo, addend(lo), 0)
+                    g.emit("addc.cc.u32", hi, addend(hi), 0)
+                    live.update((lo, hi))
+                continue
+            if pj == 1:
+                g.emit("addc.cc.u32" if started else "add.cc.u32", dst_lo, addend(lo), m)
+                g.emit("addc.cc.u32", hi, addend(hi), 0)
+            else:
+                g.emit("madc.lo.cc.u32" if started else "mad.lo.cc.u32", dst_lo, m, pj, addend(lo))
+                g.emit("madc.hi.cc.u32", hi, m, pj, addend(hi))
+            live.update((lo, hi))
+            started = True
+        assert started, "p[0] is odd, so chain A always starts"
+        live.discard(X(i))
+        top = X(i + n)
+        g.emit("addc.u32", top, addend(top), 0)
+        live.add(top)
+        # ---- reduction chain B: odd j, file Y; carry-out into the fresh carry word Y[i+n+1]
+        started = False
+        for j in range(1, n, 2):
+            lo, hi = Y(i + j), Y(i + j + 1)
+            pj = P[j]
+            if pj == 0:
+                if started:
+                    g.emit("addc.cc.u32", lo, addend(lo), 0)
+                    g.emit("addc.cc.u32", hi, addend(hi), 0)
+                    live.update((lo, hi))
+                continue
+            if pj == 1:
+                g.emit("addc.cc.u32" if started else "add.cc.u32", lo, addend(lo), m)
+                g.emit("addc.cc.u32", hi, addend(hi), 0)
+            else:
+                g.emit("madc.lo.cc.u32" if started else "mad.lo.cc.u32", lo, m, pj, addend(lo))
+                g.emit("madc.hi.cc.u32", hi, m, pj, addend(hi))
+            live.update((lo, hi))
+            started = True
+        top = Y(i + n + 1)
+        assert top not in live
+        if started:
+            g.emit("addc.u32", top, 0, 0)
+        else:
+            g.emit("mov.u32", top, 0)
+        live.add(top)
+    # ---- merge positions n .. 2n (+1) of both files into t0..tn
+    first = True
+    for k in range(n):
+        ek, ok = E(n + k), O(n + k)
+        srcs = [r for r in (ek, ok) if r in live]
+        a0 = srcs[0] if srcs else 0
+        a1 = srcs[1] if len(srcs) > 1 else 0
+        g.emit("add.cc.u32" if first else "addc.cc.u32", f"t{k}", a0, a1)
+        first = False
+    tops = [r for r in (E(2 * n), O(2 * n)) if r in live]
+    assert E(2 * n + 1) not in live and O(2 * n + 1) not in live
+    g.emit("addc.u32", f"t{n}", tops[0] if tops else 0, tops[1] if len(tops) > 1 else 0)
+    # ---- conditional subtraction: r = t - p if t >= p else t   (t < 2p)
+    for k in range(n):
+        g.emit("sub.cc.u32" if k == 0 else "subc.cc.u32", f"d{k}", f"t{k}", P[k])
+    g.emit("subc.u32", "dt", f"t{n}", 0)           # 0xffffffff iff t < p
+    g.emit("setp.ne.u32", "pq", "dt", 0)
+    for k in range(n):
+        g.emit("selp.u32", f"r{k}", f"t{k}", f"d{k}", "pq")
+    return g
+
+
+def gen_add(n, mod):
+    P = words(mod, n)
+    g = Prog()
+    for k in range(n):
+        g.emit("add.cc.u32" if k == 0 else "addc.cc.u32", f"t{k}", f"a{k}", f"b{k}")
+    g.emit("addc.u32", "tc", 0, 0)
+    for k in range(n):
+        g.emit("sub.cc.u32" if k == 0 else "subc.cc.u32", f"d{k}", f"t{k}", P[k])
+    g.emit("subc.u32", "dt", "tc", 0)
+    g.emit("setp.ne.u32", "pq", "dt", 0)
+    for k in range(n):
+        g.emit("selp.u32", f"r{k}", f"t{k}", f"d{k}", "pq")
+    return g
+
+
+def gen_sub(n, mod):
+    P = words(mod, n)
+    g = Prog()
+    for k in range(n):
+        g.emit("sub.cc.u32" if k == 0 else "subc.cc.u32", f"t{k}", f"a{k}", f"b{k}")
+    g.emit("subc.u32", "bm", 0, 0)                 # 0xffffffff iff a < b
+    for k in range(n):
+        if P[k] == 0:
+            g.emit("mov.u32", f"q{k}", 0)
+        else:
+            g.emit("and.b32", f"q{k}", "bm", P[k])
+    for k in range(n):
+        g.emit("add.cc.u32" if k == 0 else "addc.cc.u32", f"r{k}", f"t{k}", f"q{k}")
+    return g
+
+
+# ---- rendering ---------------------------------------------------------------------------------------------
+
+def render_asm(prog: Prog, n: int, two_inputs=True, indent="\t\t"):
+    """C++ asm statement: outputs r0..r{n-1} = %0..%{n-1}; inputs a = %n.., b = %2n.."""
+    opmap = {}
+    for k in range(n):
+        opmap[f"r{k}"] = f"%{k}"
+        opmap[f"a{k}"] = f"%{n + k}"
+        opmap[f"b{k}"] = f"%{2 * n + k}"
+    temps = sorted(r for r in prog.regs if r not in opmap and r != "pq")
+    lines = ["{"]
+    lines.append(".reg .u32 " + ", ".join(temps) + ";")
+    lines.append(".reg .pred pq;")
+
+    def fmt(s):
+        if isinstance(s, int):
+            return "0x%08x" % s if s > 9 else str(s)
+        return opmap.get(s, s)
+
+    for op, dst, srcs in prog.ins:
+        lines.append(f"{op} {fmt(dst)}, " + ", ".join(fmt(s) for s in srcs) + ";")
+    lines.append("}")
+    body = ("\n" + indent + "    ").join('"' + ln + '\\n\\t"' for ln in lines)
+    outs = ", ".join(f'"=r"(r.w[{k}])' for k in range(n))
+    ins = ", ".join(f'"r"(a.w[{k}])' for k in range(n))
+    if two_inputs:
+        ins += ", " + ", ".join(f'"r"(b.w[{k}])' for k in range(n))
+    return f"{indent}asm({body}\n{indent}    : {outs}\n{indent}    : {ins});"
+
+
+def fields():
+    for name, (cid, p, a, b, q, gx, gy) in CURVES.items():
+        n = (p.bit_length() + 31) // 32
+        yield f"Fp_{name}", n, p
+        yield f"Fq_{name}", n, q
+
+
+def main():
+    out = ["/* GENERATED by tools/gen_fp_ptx.py — do not edit.  Inline-PTX field arithmetic (device only). */",
+           "#pragma once", "", "namespace eccb200 {", "",
+           "template <class F> struct FieldPtx;", ""]
+    for tag, n, mod in fields():
+        mul, add, sub = gen_mul(n, mod), gen_add(n, mod), gen_sub(n, mod)
+        wide, total = mul.count()
+        out.append(f"/* {tag}: mul = {wide} wide multiply-accumulates, {total} PTX instructions */")
+        out.append(f"template <> struct FieldPtx<{tag}> {{")
+        out.append(f"\tstatic constexpr int N = {n};")
+        out.append(f"\ttypedef Fe<{n}> E;")
+        out.append("\tstatic __device__ __forceinline__ void mul(E &r, const E &a, const E &b)\n\t{")
+        out.append(render_asm(mul, n))
+        out.append("\t}")
+        out.append("\tstatic __device__ __forceinline__ void sqr(E &r, const E &a) { mul(r, a, a); }")
+        out.append("\tstatic __device__ __forceinline__ void add(E &r, const E &a, const E &b)\n\t{")
+        out.append(render_asm(add, n))
+        out.append("\t}")
+        out.append("\tstatic __device__ __forceinline__ void sub(E &r, const E &a, const E &b)\n\t{")
+        out.append(render_asm(sub, n))
+        out.append("\t}")
+        out.append("};")
+        out.append("")
+    out.append("} // namespace eccb200")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "libecc_b200", "csrc", "fp_ptx.cuh")
+    with open(path, "w") as f:
+        f.write("\n".join(out) + "\n")
+    print("wrote", os.path.normpath(path))
+
+
+if __name__ == "__main__":
+    main()
