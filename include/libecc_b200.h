@@ -18,6 +18,7 @@
 #ifndef LIBECC_B200_H
 #define LIBECC_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -57,7 +58,9 @@ const char *eccb200_curve_name(int curve_id);
  *   out     : n * 2*plen bytes affine big-endian x||y (zero for non-OK items)
  *   status  : n bytes, ECCB200_OK / ECCB200_INFINITY / ECCB200_ERR (point not on curve or coordinate >= p:
  *             the reference fails prj_pt_import_from_aff_buf :541-545 / prj_pt_mul :1767)
- * Host-pointer version: blocking, includes the host<->device copies (pipelined in chunks).
+ * Host-pointer version: blocking, includes the host<->device copies (pipelined in 2^18-item chunks over three
+ * streams).  Page-locked caller buffers (eccb200_host_alloc, cudaHostAlloc, cudaHostRegister) are DMA'd directly;
+ * pageable ones are staged through the context's own pinned buffers at the cost of one memcpy each way.
  */
 int eccb200_prj_pt_mul_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *scalars, const uint8_t *points,
 			     uint8_t *out, int8_t *status);
@@ -65,6 +68,15 @@ int eccb200_prj_pt_mul_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *scalar
 /* Same, on device-resident buffers, enqueued on `stream` (a cudaStream_t; NULL = default stream); asynchronous. */
 int eccb200_prj_pt_mul_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_scalars, const uint8_t *d_points,
 				 uint8_t *d_out, int8_t *d_status, void *stream);
+
+/*
+ * Batched prj_pt_unique + prj_pt_export_to_aff_buf (src/curves/prj_pt.c:241, :600) on the reference's homogeneous
+ * projective wire format (X||Y||Z big-endian, 3*plen bytes, prj_pt_export_to_buf :562): one simultaneous inversion
+ * per GPU thread instead of one fp_inv per point.  Points are validated like prj_pt_import_from_buf (:462-500).
+ *   status: ECCB200_OK / ECCB200_INFINITY (Z == 0; the reference's prj_pt_unique errors on it) / ECCB200_ERR.
+ */
+int eccb200_prj_pt_unique_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *prj_points, uint8_t *out_aff,
+				int8_t *status);
 
 /*
  * Batched ECDSA verification on pre-hashed messages: replaces, per signature, __ecdsa_verify_init's checks
@@ -78,6 +90,11 @@ int eccb200_ecdsa_verify_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *sigs
 			       const uint8_t *digests, uint32_t hlen, int8_t *verdict);
 int eccb200_ecdsa_verify_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_sigs, const uint8_t *d_pubkeys,
 				   const uint8_t *d_digests, uint32_t hlen, int8_t *d_verdict, void *stream);
+
+/* Page-locked host memory for the host-pointer entry points (wrappers of cudaHostAlloc / cudaFreeHost so that a C
+ * caller need not link the CUDA runtime).  NULL on failure. */
+void *eccb200_host_alloc(size_t bytes);
+void eccb200_host_free(void *p);
 
 /* Field-level entry point used by the arithmetic unit tests (pattern: src/arithmetic_tests FP_MUL_MONTY):
  * out[i] = a[i]*b[i]*R^-1 mod p (which = 0) or mod q (which = 1), R = 2^(8*plen); inputs must be < modulus. */

@@ -1,0 +1,136 @@
+/*
+ * libecc_b200_dropin.h — the reference's OWN entry points for the hot path, on the reference's own structs,
+ * implemented on the GPU engine (libecc_b200.h).  Built as libecc_b200/libecc_b200_dropin.so.
+ *
+ * What a libecc maintainer gets (see INTEGRATION.md for the exact link lines):
+ *   - `prj_pt_mul` / `prj_pt_mul_blind` with the reference's exact signatures (src/curves/prj_pt.h:61-62).  Linked
+ *     (or LD_PRELOADed) ahead of a shared libsign/libec, they interpose the reference's definitions, so every
+ *     caller — ECDSA sign/verify (src/sig/ecdsa_common.c:479,788,793), ECC-CDH (src/ecdh/ecccdh.c:80,209), all
+ *     other schemes of src/sig — runs its scalar multiplications on the B200 without being recompiled.
+ *   - `eccb200_dropin_prj_pt_mul_batch`: the same on arrays of reference structs (one launch for the batch).
+ *   - `eccb200_dropin_ecdsa_verify_batch`: a function with the signature of the reference's per-scheme
+ *     `verify_batch` slot (src/sig/sig_algs_internal.h:78-81), to put in ec_sig_maps[] where the reference has
+ *     `unsupported_verify_batch` for ECDSA (:294).  Hashing stays in the reference's src/hash (resolved from the
+ *     host application through get_hash_by_type, src/hash/hash_algs.h:550).
+ *
+ * The structs below MIRROR the reference's layout for its default configuration (WORDSIZE = 64,
+ * NN_MAX_WORD_LEN = 27: src/nn/nn_config.h:154, complete formulas on).  They are declarations of an ABI, written for
+ * this header; tests/test_dropin_layout.py checks every size and offset against the reference's own headers
+ * (through oracle/ref_shim.c: ref_abi_facts) so that a configuration drift is caught.
+ */
+#ifndef LIBECC_B200_DROPIN_H
+#define LIBECC_B200_DROPIN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECCB200_NN_MAX_WORD_LEN 27
+
+typedef uint64_t eccb200_word_t; /* word_t, src/words/words_64.h:25 */
+typedef uint16_t eccb200_bitcnt_t; /* bitcnt_t, src/words/words.h:71 */
+
+/* nn, src/nn/nn.h:67-71; magic = 0xb4cf5d56e2023316 ^ (NN_MAX_WORD_LEN + WORDSIZE)  (src/nn/nn.c:28) */
+typedef struct {
+	eccb200_word_t val[ECCB200_NN_MAX_WORD_LEN];
+	eccb200_word_t magic;
+	uint8_t wlen;
+} eccb200_nn;
+
+/* fp_ctx, src/fp/fp.h:31-57 */
+typedef struct {
+	eccb200_nn p;
+	eccb200_bitcnt_t p_bitlen;
+	eccb200_word_t mpinv;
+	eccb200_nn r;
+	eccb200_nn r_square;
+	eccb200_bitcnt_t p_shift;
+	eccb200_nn p_normalized;
+	eccb200_word_t p_reciprocal;
+	eccb200_word_t magic;
+} eccb200_fp_ctx;
+
+/* fp, src/fp/fp.h:73-77; magic 0x14e96c8ab28221ef (src/fp/fp.c:127) */
+typedef struct {
+	eccb200_nn fp_val;
+	const eccb200_fp_ctx *ctx;
+	eccb200_word_t magic;
+} eccb200_fp;
+
+/* ec_shortw_crv, src/curves/ec_shortw.h:25-36 (complete formulas enabled) */
+typedef struct {
+	eccb200_fp a;
+	eccb200_fp b;
+	eccb200_fp a_monty;
+	eccb200_fp b3;
+	eccb200_fp b_monty;
+	eccb200_fp b3_monty;
+	eccb200_nn order;
+	eccb200_word_t magic;
+} eccb200_ec_shortw_crv;
+
+/* prj_pt, src/curves/prj_pt.h:26-32; magic 0xe1cd70babb1d5afe (src/curves/prj_pt.c:26) */
+typedef struct {
+	eccb200_fp X;
+	eccb200_fp Y;
+	eccb200_fp Z;
+	const eccb200_ec_shortw_crv *crv;
+	eccb200_word_t magic;
+} eccb200_prj_pt;
+
+/* head of ec_pub_key, src/sig/ec_key.h:120-131 (params is an opaque const ec_params *) */
+typedef struct {
+	int key_type; /* ec_alg_type */
+	const void *params;
+	eccb200_prj_pt y;
+	eccb200_word_t magic;
+} eccb200_ec_pub_key;
+
+/*
+ * Drop-in replacements with the reference's exact prototypes (src/curves/prj_pt.h:61-62):
+ *     int prj_pt_mul(prj_pt_t out, nn_src_t m, prj_pt_src_t in);
+ *     int prj_pt_mul_blind(prj_pt_t out, nn_src_t m, prj_pt_src_t in);
+ * Semantics kept (SURVEY.md §8a edge table): 0 / -1; `in` must be initialised and on its curve (else -1); any
+ * scalar m (up to 27 words) gives (m mod order)*in; out may alias in; out is a valid initialised struct, canonical
+ * (x, y, 1) for finite results and (0, 1, 0) for the point at infinity.  Supported curves: those of libecc_b200.h
+ * (identified by p and the order); any other curve returns -1.
+ */
+int prj_pt_mul(eccb200_prj_pt *out, const eccb200_nn *m, const eccb200_prj_pt *in);
+int prj_pt_mul_blind(eccb200_prj_pt *out, const eccb200_nn *m, const eccb200_prj_pt *in);
+
+/* The same under non-clashing names (for callers that link the reference statically and choose per call). */
+int eccb200_dropin_prj_pt_mul(eccb200_prj_pt *out, const eccb200_nn *m, const eccb200_prj_pt *in);
+
+/* Batched form on arrays of reference structs: out[i] = m[i] * in[i], all on the same curve; ret[i] (optional, may
+ * be NULL) receives the per-item 0 / -1; returns 0 iff every item succeeded. */
+int eccb200_dropin_prj_pt_mul_batch(eccb200_prj_pt *out, const eccb200_nn *m, const eccb200_prj_pt *in, uint32_t n,
+				    int *ret);
+
+/*
+ * ECDSA back end for the reference's `verify_batch` slot (src/sig/sig_algs_internal.h:78-81; generic entry
+ * ec_verify_batch src/sig/sig_algs.c:675).  Same contract as the other schemes' implementations
+ * (e.g. src/sig/ecfsdsa.c:711-1074): returns 0 iff ALL num signatures verify, -1 otherwise; scratch_pad_area may be
+ * NULL (it is not used); all keys must share one curve.  adata must be NULL (ECDSA takes none).
+ */
+int eccb200_dropin_ecdsa_verify_batch(const uint8_t **s, const uint8_t *s_len, const eccb200_ec_pub_key **pub_keys,
+				      const uint8_t **m, const uint32_t *m_len, uint32_t num, int sig_type,
+				      int hash_type, const uint8_t **adata, const uint16_t *adata_len,
+				      void *scratch_pad_area, uint32_t *scratch_pad_area_len);
+
+/* Per-signature verdicts of the last eccb200_dropin_ecdsa_verify_batch call on this thread (0 / -1), for callers
+ * that want to know WHICH signature failed; returns the number of verdicts copied. */
+uint32_t eccb200_dropin_last_verdicts(int8_t *verdicts, uint32_t cap);
+
+/* Number of scalar multiplications the drop-in layer has served in this process (lets a caller confirm that the
+ * interposed prj_pt_mul, not the CPU one, was reached). */
+unsigned long long eccb200_dropin_call_count(void);
+
+/* Device the drop-in layer uses (default 0; also settable with the ECCB200_DEVICE environment variable). */
+int eccb200_dropin_set_device(int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

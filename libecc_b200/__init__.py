@@ -23,7 +23,8 @@ ABI_SYMBOLS = [
     "eccb200_prj_pt_mul_batch", "eccb200_prj_pt_mul_batch_dev", "eccb200_ecdsa_verify_batch",
     "eccb200_ecdsa_verify_batch_dev", "eccb200_fp_mul_monty_batch", "eccb200_comb_window",
     "eccb200_kernel_launches", "eccb200_last_error", "eccb200_ecdsa_uv_batch",
-    "eccb200_profile_enable", "eccb200_profile_read", "eccb200_imad_peak",
+    "eccb200_profile_enable", "eccb200_profile_read", "eccb200_imad_peak", "eccb200_prj_pt_unique_batch",
+    "eccb200_host_alloc", "eccb200_host_free",
 ]
 
 _lib = None
@@ -54,9 +55,14 @@ def load_library() -> ctypes.CDLL:
     lib.eccb200_ecdsa_verify_batch.argtypes = [ctypes.c_void_p, u32, u8p, u8p, u8p, u32, i8p]
     lib.eccb200_ecdsa_verify_batch_dev.argtypes = [ctypes.c_void_p, u32, u8p, u8p, u8p, u32, i8p, ctypes.c_void_p]
     lib.eccb200_fp_mul_monty_batch.argtypes = [ctypes.c_void_p, ctypes.c_int, u32, u8p, u8p, u8p]
+    lib.eccb200_prj_pt_unique_batch.argtypes = [ctypes.c_void_p, u32, u8p, u8p, i8p]
     lib.eccb200_ecdsa_uv_batch.argtypes = [ctypes.c_void_p, u32, u8p, u8p, u32, u8p]
     lib.eccb200_profile_enable.argtypes = [ctypes.c_void_p, ctypes.c_int]
     lib.eccb200_profile_read.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.c_int]
+    lib.eccb200_host_alloc.argtypes = [ctypes.c_size_t]
+    lib.eccb200_host_alloc.restype = ctypes.c_void_p
+    lib.eccb200_host_free.argtypes = [ctypes.c_void_p]
+    lib.eccb200_host_free.restype = None
     lib.eccb200_comb_window.argtypes = [ctypes.c_void_p]
     lib.eccb200_kernel_launches.argtypes = [ctypes.c_void_p]
     lib.eccb200_kernel_launches.restype = ctypes.c_uint64
@@ -79,6 +85,27 @@ def _as_u8(a, nbytes: Optional[int] = None) -> np.ndarray:
     if nbytes is not None and arr.size != nbytes:
         raise ValueError(f"expected {nbytes} bytes, got {arr.size}")
     return arr
+
+
+def pinned_empty(shape, dtype=np.uint8) -> np.ndarray:
+    """numpy array backed by page-locked memory from eccb200_host_alloc (freed with the array)."""
+    lib = load_library()
+    shape = (shape,) if isinstance(shape, int) else tuple(shape)
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = lib.eccb200_host_alloc(max(nbytes, 1))
+    if not p:
+        raise EccB200Error("eccb200_host_alloc failed")
+    buf = (ctypes.c_uint8 * max(nbytes, 1)).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    class _Owner:
+        def __del__(self, p=p, lib=lib):
+            lib.eccb200_host_free(p)
+    _PIN_OWNERS[id(buf)] = (buf, _Owner())
+    return arr
+
+
+_PIN_OWNERS = {}
 
 
 class Engine:
@@ -130,31 +157,44 @@ class Engine:
         return [float(buf[i]) for i in range(k)]
 
     # ---- host-buffer API (H2D / D2H inside the call) -------------------------------------------------------
-    def prj_pt_mul_batch(self, scalars, points=None) -> Tuple[np.ndarray, np.ndarray]:
+    def prj_pt_mul_batch(self, scalars, points=None, out=None, status=None) -> Tuple[np.ndarray, np.ndarray]:
         """scalars: n*qlen big-endian bytes; points: n*2*plen affine bytes or None (=G).
-        Returns (out[n, 2*plen] uint8, status[n] int8)."""
+        Returns (out[n, 2*plen] uint8, status[n] int8); pass `out` / `status` to reuse (e.g. pinned) buffers."""
         sc = _as_u8(scalars)
         n = sc.size // self.qlen
         if sc.size != n * self.qlen:
             raise ValueError("scalars length is not a multiple of qlen")
         pt = _as_u8(points, n * 2 * self.plen) if points is not None else None
-        out = np.zeros((n, 2 * self.plen), dtype=np.uint8)
-        status = np.zeros(n, dtype=np.int8)
+        if out is None:
+            out = np.zeros((n, 2 * self.plen), dtype=np.uint8)
+        if status is None:
+            status = np.zeros(n, dtype=np.int8)
+        assert out.nbytes == n * 2 * self.plen and status.nbytes == n and out.flags.c_contiguous
         self._check(self.lib.eccb200_prj_pt_mul_batch(
             self._h, n, sc.ctypes.data, pt.ctypes.data if pt is not None else None,
             out.ctypes.data, status.ctypes.data), "eccb200_prj_pt_mul_batch")
         return out, status
 
-    def ecdsa_verify_batch(self, sigs, pubkeys, digests, hlen: int) -> np.ndarray:
+    def ecdsa_verify_batch(self, sigs, pubkeys, digests, hlen: int, verdict=None) -> np.ndarray:
         sg = _as_u8(sigs)
         n = sg.size // (2 * self.qlen)
         pk = _as_u8(pubkeys, n * 2 * self.plen)
         dg = _as_u8(digests, n * hlen)
-        verdict = np.zeros(n, dtype=np.int8)
+        if verdict is None:
+            verdict = np.zeros(n, dtype=np.int8)
         self._check(self.lib.eccb200_ecdsa_verify_batch(
             self._h, n, sg.ctypes.data, pk.ctypes.data, dg.ctypes.data, hlen, verdict.ctypes.data),
             "eccb200_ecdsa_verify_batch")
         return verdict
+
+    def prj_pt_unique_batch(self, prj_points) -> Tuple[np.ndarray, np.ndarray]:
+        pp = _as_u8(prj_points)
+        n = pp.size // (3 * self.plen)
+        out = np.zeros((n, 2 * self.plen), dtype=np.uint8)
+        status = np.zeros(n, dtype=np.int8)
+        self._check(self.lib.eccb200_prj_pt_unique_batch(self._h, n, pp.ctypes.data, out.ctypes.data,
+                                                         status.ctypes.data), "eccb200_prj_pt_unique_batch")
+        return out, status
 
     def ecdsa_uv_batch(self, sigs, digests, hlen: int) -> np.ndarray:
         sg = _as_u8(sigs)

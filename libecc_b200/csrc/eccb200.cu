@@ -303,35 +303,83 @@ static int ensure_stages(eccb200_ctx *ctx, size_t in_bytes, size_t out_bytes)
 	return 0;
 }
 
+/* One array of fixed-size records on the host side of a batch call. */
+struct HostCol {
+	uint8_t *host;   /* caller's buffer (inputs are only read) */
+	size_t item;     /* bytes per item */
+	bool pinned;     /* page-locked (cudaHostAlloc / cudaHostRegister / eccb200_host_alloc): DMA straight from/to it */
+};
+
+static bool is_pinned(const void *p)
+{
+	cudaPointerAttributes at;
+	if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+		cudaGetLastError();
+		return false;
+	}
+	return at.type == cudaMemoryTypeHost;
+}
+
 /*
- * Generic chunked pipeline: chunk c uses stage c % kStages: memcpy into pinned -> H2D -> kernels -> D2H -> memcpy
- * out.  With kStages streams the copies of one chunk overlap the kernels of another.
- * in_item / out_item: bytes per item in the staged input / output records.
+ * Chunked, multi-stream pipeline of the host-pointer entry points.  Chunk c uses stage c % kStages:
+ *   H2D of the chunk's input columns -> kernels -> D2H of its output columns, all on the stage's stream, so the
+ *   copies of one chunk overlap the kernels of the others.  In the stage buffers the columns of a chunk are stored
+ *   one after the other ([cnt][item0], [cnt][item1], ...), every item size except possibly the last input column's
+ *   being a multiple of 16 bytes, which keeps each column 16-byte aligned for the kernels' vector loads.
+ * Page-locked caller buffers are copied directly by the DMA engines; pageable ones go through the context's pinned
+ * staging buffers (one extra memcpy each way).
  */
-template <class Pack, class Launch, class Unpack>
-static int run_pipeline(eccb200_ctx *ctx, uint32_t n, size_t in_item, size_t out_item, Pack pack, Launch launch,
-			Unpack unpack)
+template <class Launch>
+static int run_pipeline(eccb200_ctx *ctx, uint32_t n, std::vector<HostCol> &in, std::vector<HostCol> &out,
+			Launch launch)
 {
 	CUDA_OK(cudaSetDevice(ctx->device));
+	size_t in_item = 0, out_item = 0;
+	for (auto &c : in) {
+		in_item += c.item;
+		c.pinned = is_pinned(c.host);
+	}
+	for (auto &c : out) {
+		out_item += c.item;
+		c.pinned = is_pinned(c.host);
+	}
 	if (ensure_stages(ctx, (size_t)kChunk * in_item, (size_t)kChunk * out_item)) return -1;
 	uint32_t nchunks = (n + kChunk - 1) / kChunk;
 	std::vector<uint32_t> pending_lo(kStages, 0), pending_cnt(kStages, 0);
 	for (uint32_t c = 0; c < nchunks + kStages; c++) {
 		int s = (int)(c % kStages);
-		/* retire what this stage was doing */
-		if (pending_cnt[s]) {
+		if (pending_cnt[s]) { /* retire what this stage was doing */
 			CUDA_OK(cudaStreamSynchronize(ctx->streams[s]));
-			unpack(ctx->h_out[s], pending_lo[s], pending_cnt[s]);
+			size_t off = 0;
+			for (auto &col : out) {
+				if (!col.pinned)
+					memcpy(col.host + (size_t)pending_lo[s] * col.item, ctx->h_out[s] + off,
+					       (size_t)pending_cnt[s] * col.item);
+				off += (size_t)pending_cnt[s] * col.item;
+			}
 			pending_cnt[s] = 0;
 		}
 		if (c >= nchunks) continue;
 		uint32_t lo = c * kChunk, cnt = std::min(kChunk, n - lo);
-		pack(ctx->h_in[s], lo, cnt);
-		CUDA_OK(cudaMemcpyAsync(ctx->d_in[s], ctx->h_in[s], (size_t)cnt * in_item, cudaMemcpyHostToDevice,
-					ctx->streams[s]));
+		size_t off = 0;
+		for (auto &col : in) {
+			const uint8_t *src = col.host + (size_t)lo * col.item;
+			size_t bytes = (size_t)cnt * col.item;
+			if (!col.pinned) {
+				memcpy(ctx->h_in[s] + off, src, bytes);
+				src = ctx->h_in[s] + off;
+			}
+			CUDA_OK(cudaMemcpyAsync(ctx->d_in[s] + off, src, bytes, cudaMemcpyHostToDevice, ctx->streams[s]));
+			off += bytes;
+		}
 		if (launch(s, cnt)) return -1;
-		CUDA_OK(cudaMemcpyAsync(ctx->h_out[s], ctx->d_out[s], (size_t)cnt * out_item, cudaMemcpyDeviceToHost,
-					ctx->streams[s]));
+		off = 0;
+		for (auto &col : out) {
+			size_t bytes = (size_t)cnt * col.item;
+			uint8_t *dst = col.pinned ? col.host + (size_t)lo * col.item : ctx->h_out[s] + off;
+			CUDA_OK(cudaMemcpyAsync(dst, ctx->d_out[s] + off, bytes, cudaMemcpyDeviceToHost, ctx->streams[s]));
+			off += bytes;
+		}
 		pending_lo[s] = lo;
 		pending_cnt[s] = cnt;
 	}
@@ -342,28 +390,18 @@ extern "C" int eccb200_prj_pt_mul_batch(eccb200_ctx *ctx, uint32_t n, const uint
 					uint8_t *out, int8_t *status)
 {
 	if (!ctx || (n && (!scalars || !out || !status))) return fail("null argument");
+	if (n == 0) return 0;
 	const size_t sl = ctx->qlen, pl = 2 * (size_t)ctx->plen;
-	/* staged input record layout per chunk: [cnt][qlen] scalars, then [cnt][2*plen] points (if any);
-	 * staged output: [cnt][2*plen] affine, then [cnt] status */
-	const size_t in_item = sl + (points ? pl : 0), out_item = pl + 1;
-	return run_pipeline(
-		ctx, n, in_item, out_item,
-		[&](uint8_t *h, uint32_t lo, uint32_t cnt) {
-			memcpy(h, scalars + (size_t)lo * sl, (size_t)cnt * sl);
-			if (points) memcpy(h + (size_t)cnt * sl, points + (size_t)lo * pl, (size_t)cnt * pl);
-		},
-		[&](int s, uint32_t cnt) {
-			const uint8_t *d_sc = ctx->d_in[s];
-			const uint8_t *d_pt = points ? ctx->d_in[s] + (size_t)cnt * sl : nullptr;
-			uint8_t *d_o = ctx->d_out[s];
-			int8_t *d_st = (int8_t *)(ctx->d_out[s] + (size_t)cnt * pl);
-			return smul_dev(ctx, cnt, d_sc, d_pt, d_o, d_st, ctx->stage_jac[s], ctx->stage_prefix[s],
-					ctx->streams[s]);
-		},
-		[&](const uint8_t *h, uint32_t lo, uint32_t cnt) {
-			memcpy(out + (size_t)lo * pl, h, (size_t)cnt * pl);
-			memcpy(status + lo, h + (size_t)cnt * pl, cnt);
-		});
+	std::vector<HostCol> in = { { (uint8_t *)scalars, sl, false } };
+	if (points) in.push_back({ (uint8_t *)points, pl, false });
+	std::vector<HostCol> outc = { { out, pl, false }, { (uint8_t *)status, 1, false } };
+	return run_pipeline(ctx, n, in, outc, [&](int s, uint32_t cnt) {
+		const uint8_t *d_sc = ctx->d_in[s];
+		const uint8_t *d_pt = points ? ctx->d_in[s] + (size_t)cnt * sl : nullptr;
+		uint8_t *d_o = ctx->d_out[s];
+		int8_t *d_st = (int8_t *)(ctx->d_out[s] + (size_t)cnt * pl);
+		return smul_dev(ctx, cnt, d_sc, d_pt, d_o, d_st, ctx->stage_jac[s], ctx->stage_prefix[s], ctx->streams[s]);
+	});
 }
 
 extern "C" int eccb200_ecdsa_verify_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys,
@@ -371,22 +409,62 @@ extern "C" int eccb200_ecdsa_verify_batch(eccb200_ctx *ctx, uint32_t n, const ui
 {
 	if (!ctx || (n && (!sigs || !pubkeys || !digests || !verdict))) return fail("null argument");
 	if (hlen == 0 || hlen > 128) return fail("bad digest length");
+	if (n == 0) return 0;
 	const size_t sg = 2 * (size_t)ctx->qlen, pk = 2 * (size_t)ctx->plen;
-	/* the digest block goes last: it is the only one whose item size need not be a multiple of 16 */
-	const size_t in_item = sg + pk + hlen, out_item = 1;
-	return run_pipeline(
-		ctx, n, in_item, out_item,
-		[&](uint8_t *h, uint32_t lo, uint32_t cnt) {
-			memcpy(h, sigs + (size_t)lo * sg, (size_t)cnt * sg);
-			memcpy(h + (size_t)cnt * sg, pubkeys + (size_t)lo * pk, (size_t)cnt * pk);
-			memcpy(h + (size_t)cnt * (sg + pk), digests + (size_t)lo * hlen, (size_t)cnt * hlen);
-		},
-		[&](int s, uint32_t cnt) {
-			const uint8_t *d = ctx->d_in[s];
-			return verify_dev(ctx, cnt, d, d + (size_t)cnt * sg, d + (size_t)cnt * (sg + pk), hlen,
-					  (int8_t *)ctx->d_out[s], ctx->streams[s]);
-		},
-		[&](const uint8_t *h, uint32_t lo, uint32_t cnt) { memcpy(verdict + lo, h, cnt); });
+	/* the digest column goes last: it is the only one whose item size need not be a multiple of 16 */
+	std::vector<HostCol> in = { { (uint8_t *)sigs, sg, false }, { (uint8_t *)pubkeys, pk, false },
+				    { (uint8_t *)digests, hlen, false } };
+	std::vector<HostCol> outc = { { (uint8_t *)verdict, 1, false } };
+	return run_pipeline(ctx, n, in, outc, [&](int s, uint32_t cnt) {
+		const uint8_t *d = ctx->d_in[s];
+		return verify_dev(ctx, cnt, d, d + (size_t)cnt * sg, d + (size_t)cnt * (sg + pk), hlen,
+				  (int8_t *)ctx->d_out[s], ctx->streams[s]);
+	});
+}
+
+/* Page-locked host memory for callers that do not link CUDA themselves (cudaHostAlloc / cudaFreeHost). */
+extern "C" void *eccb200_host_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+		cudaGetLastError();
+		g_err = "cudaHostAlloc failed";
+		return nullptr;
+	}
+	return p;
+}
+
+extern "C" void eccb200_host_free(void *p)
+{
+	if (p) cudaFreeHost(p);
+}
+
+/* batched prj_pt_unique on homogeneous projective wire points; small host-pointer helper (not pipelined) */
+extern "C" int eccb200_prj_pt_unique_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *prj, uint8_t *out,
+					   int8_t *status)
+{
+	if (!ctx || (n && (!prj || !out || !status))) return fail("null argument");
+	if (n == 0) return 0;
+	CUDA_OK(cudaSetDevice(ctx->device));
+	if (ensure_work(ctx, n)) return -1;
+	const size_t in_b = (size_t)n * 3 * ctx->plen, out_b = (size_t)n * 2 * ctx->plen;
+	uint8_t *d = nullptr;
+	CUDA_OK(cudaMalloc(&d, in_b + out_b + n));
+	int rc = 0;
+	if (cudaMemcpy(d, prj, in_b, cudaMemcpyHostToDevice) != cudaSuccess) rc = fail("H2D copy failed");
+	if (!rc)
+		rc = dispatch(ctx->curve_id, [&](auto c) {
+			typedef decltype(c) C;
+			LaunchMisc<C>::prj_unique(affine_grid(ctx, n), n, d, ctx->jac, ctx->prefix, d + in_b,
+						  (int8_t *)(d + in_b + out_b), 0);
+			ctx->launches += 2;
+			CUDA_OK(cudaGetLastError());
+			CUDA_OK(cudaMemcpy(out, d + in_b, out_b, cudaMemcpyDeviceToHost));
+			CUDA_OK(cudaMemcpy(status, d + in_b + out_b, n, cudaMemcpyDeviceToHost));
+			return 0;
+		});
+	cudaFree(d);
+	return rc;
 }
 
 extern "C" int eccb200_fp_mul_monty_batch(eccb200_ctx *ctx, int which, uint32_t n, const uint8_t *a, const uint8_t *b,

@@ -185,16 +185,19 @@ __global__ void __launch_bounds__(128) k_table_points(uint32_t n_entries, int w,
  * thread t owns items t, t+T, t+2T, ... (T = total threads, so every pass over the batch is coalesced), keeps the
  * running product of their Z in registers, stores the prefix products, inverts once, and walks back.
  * Replaces n calls of prj_pt_unique (curves/prj_pt.c:241) -> fp_inv (fp/fp_mul.c:51, ~1.5*bitlen(p) products each).
- * TABLE = false: writes big-endian affine bytes + status (0 -> stays 0, infinity -> 1, -1 untouched).
- * TABLE = true : writes Montgomery-form words (comb table entry format), infinity as all-zero.
+ * MODE 0: Jacobian in, writes big-endian affine bytes + status (0 -> stays 0, infinity -> 1, -1 untouched).
+ * MODE 1: Jacobian in, writes Montgomery-form words (comb table entry format), infinity as all-zero.
+ * MODE 2: homogeneous projective in (x = X/Z, y = Y/Z, the reference's prj_pt), output as MODE 0: the batched
+ *         prj_pt_unique + prj_pt_export_to_aff_buf (curves/prj_pt.c:241, :600).
  */
-template <class C, bool TABLE>
+template <class C, int MODE>
 __global__ void __launch_bounds__(128) k_to_affine(uint32_t n, const uint32_t *__restrict__ jac,
 						   uint32_t *__restrict__ prefix, uint8_t *__restrict__ out,
 						   int8_t *__restrict__ status, uint32_t *__restrict__ table_out)
 {
 	typedef Field<typename C::Fp> F;
 	constexpr int N = C::N;
+	constexpr bool TABLE = (MODE == 1);
 	const uint32_t T = gridDim.x * blockDim.x;
 	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
 	if (tid >= n) return;
@@ -229,8 +232,13 @@ __global__ void __launch_bounds__(128) k_to_affine(uint32_t n, const uint32_t *_
 			F::mul(zi, inv, pre);  /* 1/z_e */
 			F::mul(t, inv, z);
 			inv = t;               /* drop z_e from the running inverse */
-			F::sqr(zi2, zi);
-			F::mul(zi3, zi2, zi);
+			if (MODE == 2) {
+				zi2 = zi;
+				zi3 = zi;
+			} else {
+				F::sqr(zi2, zi);
+				F::mul(zi3, zi2, zi);
+			}
 			F::mul(t, X, zi2);
 			X = t;
 			F::mul(t, Y, zi3);
@@ -258,6 +266,50 @@ __global__ void __launch_bounds__(128) k_to_affine(uint32_t n, const uint32_t *_
 		}
 		if (e < T || e - T < tid) break;
 	}
+}
+
+/* Loads homogeneous projective wire points (X||Y||Z big-endian, prj_pt_export_to_buf curves/prj_pt.c:562), checks
+ * them like prj_pt_import_from_buf (:462-500: coordinates < p, Y^2 Z == X^3 - 3 X Z^2 + b Z^3) and writes
+ * Montgomery-form words for k_to_affine<MODE 2>.  status: 0 ok, -1 rejected (then Z is written as 0). */
+template <class C>
+__global__ void __launch_bounds__(128) k_prj_load(uint32_t n, const uint8_t *__restrict__ prj,
+						  uint32_t *__restrict__ jac, int8_t *__restrict__ status)
+{
+	typedef Field<typename C::Fp> F;
+	constexpr int N = C::N;
+	uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= n) return;
+	Fe<N> x, y, z;
+	const uint8_t *b = prj + (size_t)idx * (12 * N);
+	load_be16<N>(x, b);
+	load_be16<N>(y, b + 4 * N);
+	load_be16<N>(z, b + 8 * N);
+	bool ok = !F::geq_mod(x) && !F::geq_mod(y) && !F::geq_mod(z);
+	Jac<C> P;
+	F::to_mont(P.X, x);
+	F::to_mont(P.Y, y);
+	F::to_mont(P.Z, z);
+	{ /* Y^2 Z == X^3 - 3 X Z^2 + b Z^3 */
+		Fe<N> l, r, t, z2, bm;
+		F::sqr(t, P.Y);
+		F::mul(l, t, P.Z);
+		F::sqr(t, P.X);
+		F::mul(r, t, P.X);
+		F::sqr(z2, P.Z);
+		F::mul(t, P.X, z2);
+		F::sub(r, r, t);
+		F::sub(r, r, t);
+		F::sub(r, r, t);
+#pragma unroll
+		for (int i = 0; i < N; i++) bm.w[i] = C::B_MONT(i);
+		F::mul(t, z2, P.Z);
+		F::mul(z2, t, bm);
+		F::add(r, r, z2);
+		ok = ok && F::eq(l, r);
+	}
+	if (!ok) F::set_zero(P.Z);
+	store_jac<C>(jac, idx, P);
+	status[idx] = ok ? 0 : -1;
 }
 
 /* ------------------------------------------------------------------------------------------ K3: ECDSA verify */
@@ -356,6 +408,8 @@ template <class C> struct LaunchMisc {
 			      int8_t *status, cudaStream_t st);
 	static void to_table(uint32_t blocks, uint32_t n, const uint32_t *jac, uint32_t *prefix, uint32_t *table,
 			     cudaStream_t st);
+	static void prj_unique(uint32_t blocks, uint32_t n, const uint8_t *prj, uint32_t *jac, uint32_t *prefix,
+			       uint8_t *out, int8_t *status, cudaStream_t st);
 	static void fp_mul(int which, uint32_t n, const uint8_t *a, const uint8_t *b, uint8_t *out, cudaStream_t st);
 };
 
@@ -390,13 +444,20 @@ template <class C>
 void LaunchMisc<C>::to_affine(uint32_t blocks, uint32_t n, const uint32_t *jac, uint32_t *prefix, uint8_t *out,
 			      int8_t *status, cudaStream_t st)
 {
-	k_to_affine<C, false><<<blocks, kThreads, 0, st>>>(n, jac, prefix, out, status, nullptr);
+	k_to_affine<C, 0><<<blocks, kThreads, 0, st>>>(n, jac, prefix, out, status, nullptr);
+}
+template <class C>
+void LaunchMisc<C>::prj_unique(uint32_t blocks, uint32_t n, const uint8_t *prj, uint32_t *jac, uint32_t *prefix,
+			       uint8_t *out, int8_t *status, cudaStream_t st)
+{
+	k_prj_load<C><<<grid_for(n), kThreads, 0, st>>>(n, prj, jac, status);
+	k_to_affine<C, 2><<<blocks, kThreads, 0, st>>>(n, jac, prefix, out, status, nullptr);
 }
 template <class C>
 void LaunchMisc<C>::to_table(uint32_t blocks, uint32_t n, const uint32_t *jac, uint32_t *prefix, uint32_t *table,
 			     cudaStream_t st)
 {
-	k_to_affine<C, true><<<blocks, kThreads, 0, st>>>(n, jac, prefix, nullptr, nullptr, table);
+	k_to_affine<C, 1><<<blocks, kThreads, 0, st>>>(n, jac, prefix, nullptr, nullptr, table);
 }
 template <class C>
 void LaunchMisc<C>::fp_mul(int which, uint32_t n, const uint8_t *a, const uint8_t *b, uint8_t *out, cudaStream_t st)

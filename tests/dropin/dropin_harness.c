@@ -1,0 +1,255 @@
+/*
+ * tests/dropin/dropin_harness.c — exercises include/libecc_b200_dropin.h against the UNMODIFIED reference.
+ *
+ * Compiled in the build container against the reference's own headers (-I/root/reference/src) and linked with
+ * oracle/_ref/libecc_ref.so, so every struct passed to the drop-in is a REAL reference struct (import_params,
+ * prj_pt_import_from_aff_buf, nn_init_from_buf, ec_key_pair_gen ...) and every result is judged by the reference's own
+ * predicates (prj_pt_check_initialized, prj_pt_is_on_curve, prj_pt_cmp, prj_pt_iszero, ec_verify).
+ * The binary (oracle/_ref/dropin_harness) travels to the GPU box; tests/test_gpu_dropin.py runs it there.
+ *
+ * Modes:
+ *   direct   the drop-in is dlopen'ed privately; its prj_pt_mul / batch / verify_batch entry points are compared with
+ *            the reference's own functions on identical inputs.
+ *   preload  run with LD_PRELOAD=libecc_b200_dropin.so: the reference's ec_sign / ec_verify / ECC-CDH code then
+ *            calls the interposed prj_pt_mul, i.e. the GPU, without being recompiled; results must still satisfy
+ *            the reference's known-answer expectations.
+ */
+#define _GNU_SOURCE
+#include "libsig.h"
+#include <dlfcn.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef int (*mul_fn)(prj_pt_t, nn_src_t, prj_pt_src_t);
+typedef int (*mul_batch_fn)(prj_pt *, const nn *, const prj_pt *, u32, int *);
+typedef int (*vbatch_fn)(const u8 **, const u8 *, const ec_pub_key **, const u8 **, const u32 *, u32, ec_alg_type,
+			 hash_alg_type, const u8 **, const u16 *, verify_batch_scratch_pad *, u32 *);
+typedef u32 (*verdicts_fn)(signed char *, u32);
+typedef unsigned long long (*count_fn)(void);
+
+static int failures = 0;
+#define CHECK(cond, ...)                                      \
+	do {                                                  \
+		if (!(cond)) {                                \
+			failures++;                           \
+			printf("FAIL %s:%d: ", __FILE__, __LINE__); \
+			printf(__VA_ARGS__);                  \
+			printf("\n");                         \
+		}                                             \
+	} while (0)
+
+static unsigned long long rng_state = 0x6c69626563632d31ULL;
+static u8 rnd8(void)
+{
+	rng_state += 0x9e3779b97f4a7c15ULL;
+	unsigned long long z = rng_state;
+	z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+	z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+	return (u8)((z ^ (z >> 31)) >> 24);
+}
+
+static int load_params(ec_params *params, const char *name)
+{
+	const ec_str_params *sp = NULL;
+	if (ec_get_curve_params_by_name((const u8 *)name, (u8)(strlen(name) + 1), &sp) || !sp) return -1;
+	return import_params(params, sp);
+}
+
+static void compare(const char *what, const char *curve, int r_ref, prj_pt_src_t o_ref, int r_gpu, prj_pt_src_t o_gpu)
+{
+	int z1 = 0, z2 = 0, cmp = 1, on = 0;
+	CHECK(r_ref == r_gpu, "%s %s: return %d vs reference %d", curve, what, r_gpu, r_ref);
+	if (r_ref || r_gpu) return;
+	CHECK(!prj_pt_check_initialized(o_gpu), "%s %s: output not a valid initialised prj_pt", curve, what);
+	CHECK(!prj_pt_is_on_curve(o_gpu, &on) && on, "%s %s: output fails the reference's on-curve check", curve, what);
+	CHECK(!prj_pt_iszero(o_ref, &z1) && !prj_pt_iszero(o_gpu, &z2) && z1 == z2, "%s %s: infinity flag", curve, what);
+	if (!z1 && !z2) CHECK(!prj_pt_cmp(o_ref, o_gpu, &cmp) && cmp == 0, "%s %s: prj_pt_cmp != 0", curve, what);
+}
+
+static int run_direct(const char *dropin_path)
+{
+	void *h = dlopen(dropin_path, RTLD_NOW | RTLD_LOCAL);
+	if (!h) {
+		printf("FAIL dlopen %s: %s\n", dropin_path, dlerror());
+		return 1;
+	}
+	mul_fn gpu_mul = (mul_fn)dlsym(h, "prj_pt_mul");
+	mul_fn gpu_mul_blind = (mul_fn)dlsym(h, "prj_pt_mul_blind");
+	mul_batch_fn gpu_batch = (mul_batch_fn)dlsym(h, "eccb200_dropin_prj_pt_mul_batch");
+	vbatch_fn gpu_vbatch = (vbatch_fn)dlsym(h, "eccb200_dropin_ecdsa_verify_batch");
+	verdicts_fn gpu_verdicts = (verdicts_fn)dlsym(h, "eccb200_dropin_last_verdicts");
+	if (!gpu_mul || !gpu_mul_blind || !gpu_batch || !gpu_vbatch || !gpu_verdicts) {
+		printf("FAIL missing drop-in symbols\n");
+		return 1;
+	}
+	const char *names[3] = { "SECP256R1", "FRP256V1", "SECP384R1" };
+	for (int c = 0; c < 3; c++) {
+		ec_params params;
+		CHECK(!load_params(&params, names[c]), "import_params %s", names[c]);
+		u8 qlen = (u8)BYTECEIL(params.ec_gen_order_bitlen);
+		/* ---- scalars of several widths on G, on a reference-made projective point (Z != 1), aliasing */
+		prj_pt base2, tmp;
+		CHECK(!prj_pt_dbl(&tmp, &params.ec_gen), "dbl");
+		CHECK(!prj_pt_add(&base2, &tmp, &params.ec_gen), "add"); /* 3G with Z != 1 */
+		u16 lens[5] = { qlen, 1, (u16)(qlen + 8), 72, (u16)(2 * qlen) };
+		for (int t = 0; t < 10; t++) {
+			u8 kb[96];
+			u16 kl = lens[t % 5];
+			for (u16 i = 0; i < kl; i++) kb[i] = rnd8();
+			nn k;
+			CHECK(!nn_init_from_buf(&k, kb, kl), "nn_init_from_buf");
+			prj_pt o_ref, o_gpu;
+			prj_pt_src_t b = (t & 1) ? &base2 : &params.ec_gen;
+			int r1 = prj_pt_mul(&o_ref, &k, b);
+			int r2 = gpu_mul(&o_gpu, &k, b);
+			compare("prj_pt_mul", names[c], r1, &o_ref, r2, &o_gpu);
+			r2 = gpu_mul_blind(&o_gpu, &k, b);
+			compare("prj_pt_mul_blind", names[c], r1, &o_ref, r2, &o_gpu);
+			/* out == in */
+			prj_pt alias;
+			CHECK(!prj_pt_copy(&alias, b), "copy");
+			r2 = gpu_mul(&alias, &k, &alias);
+			compare("prj_pt_mul(out==in)", names[c], r1, &o_ref, r2, &alias);
+		}
+		/* ---- edge scalars: 0, 1, q-1, q, q+1 */
+		{
+			nn q, one, k;
+			prj_pt o_ref, o_gpu;
+			CHECK(!nn_copy(&q, &params.ec_gen_order) && !nn_init(&one, 0) && !nn_one(&one), "nn setup");
+			CHECK(!nn_init(&k, 0) && !nn_zero(&k), "zero");
+			compare("k=0", names[c], prj_pt_mul(&o_ref, &k, &params.ec_gen), &o_ref, gpu_mul(&o_gpu, &k, &params.ec_gen), &o_gpu);
+			compare("k=1", names[c], prj_pt_mul(&o_ref, &one, &params.ec_gen), &o_ref, gpu_mul(&o_gpu, &one, &params.ec_gen), &o_gpu);
+			compare("k=q", names[c], prj_pt_mul(&o_ref, &q, &params.ec_gen), &o_ref, gpu_mul(&o_gpu, &q, &params.ec_gen), &o_gpu);
+			CHECK(!nn_sub(&k, &q, &one), "q-1");
+			compare("k=q-1", names[c], prj_pt_mul(&o_ref, &k, &base2), &o_ref, gpu_mul(&o_gpu, &k, &base2), &o_gpu);
+			CHECK(!nn_add(&k, &q, &one), "q+1");
+			compare("k=q+1", names[c], prj_pt_mul(&o_ref, &k, &base2), &o_ref, gpu_mul(&o_gpu, &k, &base2), &o_gpu);
+			/* in = infinity */
+			prj_pt inf;
+			CHECK(!prj_pt_init(&inf, &params.ec_curve) && !prj_pt_zero(&inf), "inf");
+			compare("in=inf", names[c], prj_pt_mul(&o_ref, &one, &inf), &o_ref, gpu_mul(&o_gpu, &one, &inf), &o_gpu);
+			/* point not on the curve: both must fail */
+			prj_pt bad;
+			CHECK(!prj_pt_copy(&bad, &params.ec_gen), "copy");
+			bad.Y.fp_val.val[0] ^= 1;
+			compare("off-curve", names[c], prj_pt_mul(&o_ref, &one, &bad), &o_ref, gpu_mul(&o_gpu, &one, &bad), &o_gpu);
+			/* uninitialised input */
+			prj_pt junk;
+			memset(&junk, 0, sizeof(junk));
+			CHECK(gpu_mul(&o_gpu, &one, &junk) == -1, "%s: uninitialised input accepted", names[c]);
+		}
+		/* ---- batch on arrays of structs */
+		{
+			enum { NB = 64 };
+			static prj_pt in[NB], out[NB], ref_out[NB];
+			static nn ks[NB];
+			int rets[NB];
+			for (int i = 0; i < NB; i++) {
+				u8 kb[64];
+				for (int j = 0; j < qlen; j++) kb[j] = rnd8();
+				CHECK(!nn_init_from_buf(&ks[i], kb, qlen), "nn");
+				CHECK(!prj_pt_copy(&in[i], (i % 3) ? &base2 : &params.ec_gen), "copy");
+				if (i == 7) in[i].X.fp_val.val[1] ^= 4; /* one bad item must not poison the batch */
+			}
+			int rb = gpu_batch(out, ks, in, NB, rets);
+			CHECK(rb == -1, "%s batch: expected overall -1 because of the bad item", names[c]);
+			for (int i = 0; i < NB; i++) {
+				int r1 = prj_pt_mul(&ref_out[i], &ks[i], &in[i]);
+				compare("batch item", names[c], r1, &ref_out[i], rets[i], &out[i]);
+			}
+		}
+		/* ---- ECDSA verify_batch slot */
+		{
+			enum { NS = 48 };
+			static ec_key_pair kp[NS];
+			static u8 sigs[NS][2 * 66], msgs[NS][40];
+			const u8 *sp[NS], *mp[NS];
+			const ec_pub_key *pk[NS];
+			u8 sl[NS];
+			u32 ml[NS];
+			hash_alg_type ht = (c == 2) ? SHA384 : SHA256;
+			for (int i = 0; i < NS; i++) {
+				CHECK(!ec_key_pair_gen(&kp[i], &params, ECDSA), "keygen");
+				ml[i] = (u32)(1 + (rnd8() % 39));
+				for (u32 j = 0; j < ml[i]; j++) msgs[i][j] = rnd8();
+				sl[i] = (u8)(2 * qlen);
+				CHECK(!ec_sign(sigs[i], sl[i], &kp[i], msgs[i], ml[i], ECDSA, ht, NULL, 0), "ec_sign");
+				sp[i] = sigs[i];
+				mp[i] = msgs[i];
+				pk[i] = &kp[i].pub_key; /* y is a prj_pt_mul output: Z != 1 */
+			}
+			int r = gpu_vbatch(sp, sl, pk, mp, ml, NS, ECDSA, ht, NULL, NULL, NULL, NULL);
+			CHECK(r == 0, "%s verify_batch: valid batch rejected", names[c]);
+			sigs[5][3] ^= 0x20;
+			msgs[9][0] ^= 1;
+			r = gpu_vbatch(sp, sl, pk, mp, ml, NS, ECDSA, ht, NULL, NULL, NULL, NULL);
+			CHECK(r == -1, "%s verify_batch: corrupted batch accepted", names[c]);
+			signed char v[NS];
+			CHECK(gpu_verdicts(v, NS) == NS, "verdict count");
+			for (int i = 0; i < NS; i++) {
+				int want = ec_verify(sigs[i], sl[i], pk[i], msgs[i], ml[i], ECDSA, ht, NULL, 0) ? -1 : 0;
+				CHECK(v[i] == want, "%s verify_batch verdict[%d] = %d, reference ec_verify says %d", names[c], i, v[i], want);
+			}
+			CHECK(v[5] == -1 && v[9] == -1, "corrupted items not flagged");
+			/* the generic entry point still reports ECDSA batch as unsupported in the unmodified reference */
+			CHECK(ec_verify_batch(sp, sl, pk, mp, ml, NS, ECDSA, ht, NULL, NULL, NULL, NULL) == -1,
+			      "reference ec_verify_batch(ECDSA) unexpectedly supported");
+		}
+		printf("direct %s done, failures so far %d\n", names[c], failures);
+	}
+	return failures != 0;
+}
+
+/* preload mode: the reference's own high-level code, with prj_pt_mul interposed by the GPU drop-in */
+static int run_preload(void)
+{
+	count_fn calls = (count_fn)dlsym(RTLD_DEFAULT, "eccb200_dropin_call_count");
+	if (!calls) {
+		printf("FAIL: drop-in not preloaded (eccb200_dropin_call_count missing)\n");
+		return 1;
+	}
+	unsigned long long c0 = calls();
+	const char *names[3] = { "SECP256R1", "FRP256V1", "SECP384R1" };
+	for (int c = 0; c < 3; c++) {
+		ec_params params;
+		CHECK(!load_params(&params, names[c]), "import_params");
+		u8 qlen = (u8)BYTECEIL(params.ec_gen_order_bitlen);
+		hash_alg_type ht = (c == 2) ? SHA384 : SHA256;
+		for (int t = 0; t < 6; t++) {
+			ec_key_pair kp;
+			u8 sig[2 * 66], msg[32];
+			CHECK(!ec_key_pair_gen(&kp, &params, ECDSA), "keygen through the GPU");
+			for (int j = 0; j < 32; j++) msg[j] = rnd8();
+			CHECK(!ec_sign(sig, (u8)(2 * qlen), &kp, msg, 32, ECDSA, ht, NULL, 0), "ec_sign through the GPU");
+			CHECK(!ec_verify(sig, (u8)(2 * qlen), &kp.pub_key, msg, 32, ECDSA, ht, NULL, 0), "ec_verify through the GPU");
+			sig[1] ^= 1;
+			CHECK(ec_verify(sig, (u8)(2 * qlen), &kp.pub_key, msg, 32, ECDSA, ht, NULL, 0) == -1, "forged signature accepted");
+		}
+		/* ECC-CDH both ways must agree (two variable-base multiplications through the GPU) */
+		ec_key_pair a, b;
+		u8 sa[66], sb[66], pa[2 * 66], pb[2 * 66], plen = (u8)BYTECEIL(params.ec_fp.p_bitlen);
+		CHECK(!ecccdh_gen_key_pair(&a, &params) && !ecccdh_gen_key_pair(&b, &params), "ecccdh keygen");
+		CHECK(!ecccdh_serialize_pub_key(&a.pub_key, pa, (u8)(2 * plen)) && !ecccdh_serialize_pub_key(&b.pub_key, pb, (u8)(2 * plen)), "serialize");
+		CHECK(!ecccdh_derive_secret(&a.priv_key, pb, (u8)(2 * plen), sa, plen), "derive a");
+		CHECK(!ecccdh_derive_secret(&b.priv_key, pa, (u8)(2 * plen), sb, plen), "derive b");
+		CHECK(!memcmp(sa, sb, plen), "%s: ECC-CDH secrets differ", names[c]);
+	}
+	unsigned long long used = calls() - c0;
+	printf("preload: %llu prj_pt_mul calls served by the GPU drop-in\n", used);
+	CHECK(used >= 3 * (6 * 4 + 4), "too few interposed calls (%llu): the reference did not go through the drop-in", used);
+	return failures != 0;
+}
+
+int main(int argc, char **argv)
+{
+	int rc;
+	if (argc >= 2 && !strcmp(argv[1], "preload")) rc = run_preload();
+	else if (argc >= 3 && !strcmp(argv[1], "direct")) rc = run_direct(argv[2]);
+	else {
+		printf("usage: %s direct <path to libecc_b200_dropin.so> | preload\n", argv[0]);
+		return 2;
+	}
+	printf(rc ? "HARNESS FAILED (%d failures)\n" : "HARNESS OK (%d failures)\n", failures);
+	return rc;
+}

@@ -10,14 +10,10 @@ import libecc_b200
 from common import ROOT
 
 
-def declared_symbols():
-    names = set()
-    for h in os.listdir(os.path.join(ROOT, "include")):
-        txt = open(os.path.join(ROOT, "include", h)).read()
-        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-        for m in re.finditer(r"\b(eccb200_\w+|prj_pt_mul\w*|ecdsa_verify_batch\w*|eccb200\w*)\s*\(", txt):
-            names.add(m.group(1))
-    return names
+def declared_symbols(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return {m.group(1) for m in re.finditer(r"\b(eccb200_\w+|prj_pt_mul\w*)\s*\(", txt)}
 
 
 def test_library_exports_every_declared_symbol():
@@ -25,10 +21,16 @@ def test_library_exports_every_declared_symbol():
         import __graft_entry__
         __graft_entry__.build()
     lib = ctypes.CDLL(libecc_b200.LIB_PATH)
-    decl = declared_symbols()
-    assert set(libecc_b200.ABI_SYMBOLS) <= decl
+    decl = declared_symbols("libecc_b200.h")
+    assert set(libecc_b200.ABI_SYMBOLS) == decl
     for name in sorted(decl):
-        assert hasattr(lib, name), f"{name} declared in include/ but not exported"
+        assert hasattr(lib, name), f"{name} declared in include/libecc_b200.h but not exported"
+    drop = ctypes.CDLL(os.path.join(os.path.dirname(libecc_b200.LIB_PATH), "libecc_b200_dropin.so"))
+    decl2 = declared_symbols("libecc_b200_dropin.h")
+    assert {"prj_pt_mul", "prj_pt_mul_blind", "eccb200_dropin_ecdsa_verify_batch"} <= decl2
+    for name in sorted(decl2):
+        assert hasattr(drop, name), f"{name} declared in include/libecc_b200_dropin.h but not exported"
+    assert set(os.listdir(os.path.join(ROOT, "include"))) == {"libecc_b200.h", "libecc_b200_dropin.h"}
 
 
 def test_curve_metadata_without_gpu():
