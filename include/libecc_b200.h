@@ -40,7 +40,8 @@ typedef struct eccb200_ctx eccb200_ctx;
 /*
  * Create an engine context for one curve on one device: uploads the curve constants and builds the fixed-base
  * comb table T[i][d] = d * 2^(w*i) * G on the GPU.  Replaces import_params (src/curves/ec_params.c:24) as the
- * place where per-curve state is derived.  comb_window: bits per fixed-base window (4..16), 0 = default.
+ * place where per-curve state is derived.  comb_window: bits per fixed-base window: 4..16, or an even value in
+ * 18..24 (table of ceil(qbits/w) * 2^w * 2*plen bytes, built from a half-width table); 0 = default.
  */
 int eccb200_ctx_create(eccb200_ctx **ctx, int curve_id, int device, int comb_window);
 void eccb200_ctx_destroy(eccb200_ctx *ctx);

@@ -129,7 +129,7 @@ extern "C" int eccb200_ctx_create(eccb200_ctx **out, int curve_id, int device, i
 	if (prop.major != 10) return fail("libecc_b200 is built for sm_100a (B200) only");
 	if (const char *ss = getenv("ECCB200_STACK")) cudaDeviceSetLimit(cudaLimitStackSize, (size_t)atoi(ss));
 	int w = comb_window ? comb_window : 16;
-	if (w < 4 || w > 16) return fail("comb_window must be in [4,16]");
+	if (w < 4 || w > 24 || (w > 16 && (w & 1))) return fail("comb_window must be in [4,16] or even in [18,24]");
 
 	eccb200_ctx *ctx = new eccb200_ctx();
 	ctx->curve_id = curve_id;
@@ -142,12 +142,34 @@ extern "C" int eccb200_ctx_create(eccb200_ctx **out, int curve_id, int device, i
 		ctx->plen = C::PLEN;
 		ctx->qlen = C::QLEN;
 		ctx->nwin = (C::QBITS + w - 1) / w;
-		uint32_t entries = (uint32_t)ctx->nwin << w;
-		CUDA_OK(cudaMalloc(&ctx->table, (size_t)entries * 2 * C::N * sizeof(uint32_t)));
-		if (ensure_work(ctx, entries)) return -1;
-		LaunchSmul<C>::table_points(entries, w, ctx->jac, 0);
-		LaunchMisc<C>::to_table(affine_grid(ctx, entries), entries, ctx->jac, ctx->prefix, ctx->table, 0);
-		ctx->launches += 2;
+		const size_t entries = (size_t)ctx->nwin << w;
+		CUDA_OK(cudaMalloc(&ctx->table, entries * 2 * C::N * sizeof(uint32_t)));
+		if (w <= 16) {
+			/* direct build: every entry is a scalar multiplication d * 2^(w*i) * G (K2's window_mul) */
+			if (ensure_work(ctx, (uint32_t)entries)) return -1;
+			LaunchSmul<C>::table_points((uint32_t)entries, w, ctx->jac, 0);
+			LaunchMisc<C>::to_table(affine_grid(ctx, (uint32_t)entries), (uint32_t)entries, ctx->jac, ctx->prefix,
+						ctx->table, 0);
+			ctx->launches += 2;
+		} else {
+			/* wide table from a half-width one: one addition per entry (k_table_merge), window by window */
+			const int h = w / 2, nwin_half = (C::QBITS + h - 1) / h;
+			const uint32_t half_entries = (uint32_t)nwin_half << h, per_win = 1u << w;
+			uint32_t *half = nullptr;
+			CUDA_OK(cudaMalloc(&half, (size_t)half_entries * 2 * C::N * sizeof(uint32_t)));
+			if (ensure_work(ctx, std::max(half_entries, per_win))) return -1;
+			LaunchSmul<C>::table_points(half_entries, h, ctx->jac, 0);
+			LaunchMisc<C>::to_table(affine_grid(ctx, half_entries), half_entries, ctx->jac, ctx->prefix, half, 0);
+			ctx->launches += 2;
+			for (int i = 0; i < ctx->nwin; i++) {
+				LaunchSmul<C>::table_merge(per_win, (uint64_t)i << w, w, nwin_half, half, ctx->jac, 0);
+				LaunchMisc<C>::to_table(affine_grid(ctx, per_win), per_win, ctx->jac, ctx->prefix,
+							ctx->table + ((size_t)i << w) * 2 * C::N, 0);
+				ctx->launches += 2;
+			}
+			CUDA_OK(cudaDeviceSynchronize());
+			cudaFree(half);
+		}
 		CUDA_OK(cudaGetLastError());
 		CUDA_OK(cudaDeviceSynchronize());
 		return 0;

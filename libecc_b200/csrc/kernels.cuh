@@ -178,6 +178,48 @@ __global__ void __launch_bounds__(128) k_table_points(uint32_t n_entries, int w,
 	store_jac<C>(jac, e, acc);
 }
 
+/*
+ * Wide comb tables (w > 16) are built from a half-width one: entry (i, d) of the w-bit table is
+ * T_h[2i][d mod 2^h] + T_h[2i+1][d >> h] with h = w/2 — one affine+affine addition per entry instead of a scalar
+ * multiplication, then the batched normalisation.  An all-zero base entry stands for the point at infinity.
+ * count entries starting at wide index first_entry; results (Jacobian) go to jac[0 .. count).
+ */
+template <class C>
+__global__ void __launch_bounds__(128) k_table_merge(uint32_t count, uint64_t first_entry, int w, int nwin_half,
+						     const uint32_t *__restrict__ half_table,
+						     uint32_t *__restrict__ jac)
+{
+	typedef Field<typename C::Fp> F;
+	uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= count) return;
+	const int h = w >> 1;
+	uint64_t e = first_entry + idx;
+	uint32_t i = (uint32_t)(e >> w);
+	uint32_t d = (uint32_t)(e & ((1ull << w) - 1ull));
+	uint32_t lo = d & ((1u << h) - 1u), hi = d >> h;
+	Jac<C> acc;
+	EC<C>::set_inf(acc);
+	bool valid = !(hi != 0 && (int)(2 * i + 1) >= nwin_half) && (int)(2 * i) < nwin_half;
+	if (valid && lo != 0) {
+		Aff<C> a;
+		load_table_entry<C>(a, half_table, ((size_t)(2 * i) << h) + lo);
+		if (F::is_zero(a.x) && F::is_zero(a.y)) valid = false;
+		else EC<C>::from_affine(acc, a);
+	}
+	if (valid && hi != 0) {
+		Aff<C> b;
+		load_table_entry<C>(b, half_table, ((size_t)(2 * i + 1) << h) + hi);
+		if (F::is_zero(b.x) && F::is_zero(b.y)) valid = false;
+		else {
+			Jac<C> r;
+			EC<C>::add_mixed(r, acc, b);
+			acc = r;
+		}
+	}
+	if (!valid) EC<C>::set_inf(acc);
+	store_jac<C>(jac, idx, acc);
+}
+
 /* ------------------------------------------------------------------------------------------ K4: normalisation */
 
 /*
@@ -401,6 +443,8 @@ template <class C> struct LaunchSmul {
 	static void var(uint32_t n, const uint8_t *scalars, const uint8_t *points, uint32_t *jac, int8_t *status,
 			cudaStream_t st);
 	static void table_points(uint32_t entries, int w, uint32_t *jac, cudaStream_t st);
+	static void table_merge(uint32_t count, uint64_t first_entry, int w, int nwin_half, const uint32_t *half_table,
+				uint32_t *jac, cudaStream_t st);
 };
 
 template <class C> struct LaunchMisc {
@@ -436,6 +480,12 @@ void LaunchSmul<C>::var(uint32_t n, const uint8_t *scalars, const uint8_t *point
 template <class C> void LaunchSmul<C>::table_points(uint32_t entries, int w, uint32_t *jac, cudaStream_t st)
 {
 	k_table_points<C><<<grid_for(entries), kThreads, 0, st>>>(entries, w, jac);
+}
+template <class C>
+void LaunchSmul<C>::table_merge(uint32_t count, uint64_t first_entry, int w, int nwin_half,
+				const uint32_t *half_table, uint32_t *jac, cudaStream_t st)
+{
+	k_table_merge<C><<<grid_for(count), kThreads, 0, st>>>(count, first_entry, w, nwin_half, half_table, jac);
 }
 #endif
 

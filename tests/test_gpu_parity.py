@@ -61,6 +61,18 @@ def test_fixed_base_vs_oracle(curve, w):
     assert (out == want).all()
 
 
+@pytest.mark.parametrize("curve,w", [("SECP256R1", 20), ("FRP256V1", 18), ("SECP384R1", 18), ("SECP256R1", 22)])
+def test_fixed_base_wide_window_tables(curve, w):
+    """Comb windows wider than 16 bits are built by merging a half-width table (k_table_merge): same results."""
+    sc = np.concatenate([random_scalars(curve, 2048, tag=45 + w, below_q=False), edge_scalars(curve)])
+    want, wst = oracle_smul(curve, sc)
+    eng = engine(curve, w)
+    assert eng.comb_window == w
+    out, st = eng.prj_pt_mul_batch(sc)
+    assert (st == wst).all() and (out == want).all()
+    _engines.pop((curve, w)).close()   # give the table memory back
+
+
 @pytest.mark.parametrize("curve", list(CURVES))
 def test_variable_base_vs_oracle(curve):
     _, plen, qlen = CURVES[curve]

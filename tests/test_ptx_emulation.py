@@ -30,6 +30,7 @@ def result(n, r):
 def test_generated_streams(tag, n, mod):
     rnd = random.Random(hash(tag) & 0xFFFF)
     mul, add, sub = gen_fp_ptx.gen_mul(n, mod), gen_fp_ptx.gen_add(n, mod), gen_fp_ptx.gen_sub(n, mod)
+    sqr = gen_fp_ptx.gen_sqr(n, mod)
     rinv = pow(1 << (32 * n), -1, mod)
     special = [0, 1, 2, mod - 1, mod - 2, (1 << (32 * n - 1)) % mod, (mod >> 1), (1 << 32) - 1, ((1 << 32) - 1) << 32,
                mod - (1 << 32), int("ffffffff" * n, 16) % mod, int("ffffffff" * n, 16) - mod if int("ffffffff" * n, 16) - mod < mod else 5]
@@ -39,9 +40,12 @@ def test_generated_streams(tag, n, mod):
         assert result(n, mul.run(env(n, a, b))) == a * b * rinv % mod
         assert result(n, add.run(env(n, a, b))) == (a + b) % mod
         assert result(n, sub.run(env(n, a, b))) == (a - b) % mod
+        assert result(n, sqr.run(env(n, a, b))) == a * a * rinv % mod
     wide, total = mul.count()
     m0_is_one = (-pow(mod, -1, 1 << 32)) % (1 << 32) == 1
     assert wide <= 2 * n * n and total <= 2 * (2 * n * n) + 8 * n + (0 if m0_is_one else n) + 8
+    swide, _ = sqr.count()
+    assert swide <= n * (n + 1) // 2 + n * n   # symmetric product + full reduction
 
 
 def test_header_is_up_to_date():

@@ -235,6 +235,171 @@ def gen_mul(n, mod):
     return g
 
 
+def gen_sqr(n, mod):
+    """r = a*a*2^(-32n) mod `mod`.  The product phase uses the symmetry of squaring: the n(n-1)/2 cross products
+    a_i*a_j (i < j) are accumulated once, doubled by a one-bit shift, and the n squares a_i^2 are added — n(n+1)/2
+    wide multiplies instead of n^2.  The double-width product then sits in file E (even-aligned pairs); the n
+    reduction rows run as in gen_mul with file O collecting the odd-position products.  Because E's upper words are
+    full product words, carry-outs of chains that end in E are collected in separate registers k<pos> (each at most
+    2) and added after the final merge."""
+    P = words(mod, n)
+    m0 = (-pow(mod, -1, 1 << 32)) % (1 << 32)
+    g = Prog()
+    live = set()
+    E = lambda k: f"e{k}"
+    O = lambda k: f"o{k}"
+    K = lambda k: f"k{k}"
+
+    def addend(reg):
+        return reg if reg in live else 0
+
+    # ---- phase 1: cross products sum_{i<j} a_i a_j 2^(32(i+j)); position i+j even -> file E, odd -> file O
+    for i in range(n - 1):
+        for parity in (0, 1):
+            F = E if parity == 0 else O
+            js = [j for j in range(i + 1, n) if (i + j) % 2 == parity]
+            if not js:
+                continue
+            fresh_all = all(F(i + j) not in live and F(i + j + 1) not in live for j in js)
+            if fresh_all:
+                for j in js:
+                    g.emit("mul.lo.u32", F(i + j), f"a{i}", f"a{j}")
+                    g.emit("mul.hi.u32", F(i + j + 1), f"a{i}", f"a{j}")
+                    live.update((F(i + j), F(i + j + 1)))
+                continue
+            for idx, j in enumerate(js):
+                lo, hi = F(i + j), F(i + j + 1)
+                last = idx == len(js) - 1
+                g.emit("mad.lo.cc.u32" if idx == 0 else "madc.lo.cc.u32", lo, f"a{i}", f"a{j}", addend(lo))
+                if last and hi not in live:
+                    g.emit("madc.hi.u32", hi, f"a{i}", f"a{j}", 0)          # fresh high word: cannot overflow
+                    live.update((lo, hi))
+                else:
+                    g.emit("madc.hi.cc.u32", hi, f"a{i}", f"a{j}", addend(hi))
+                    live.update((lo, hi))
+                    if last:
+                        top = F(i + j + 2)
+                        assert top not in live
+                        g.emit("addc.u32", top, 0, 0)                        # carry word for the next row's top pair
+                        live.add(top)
+    # ---- merge O into E (positions 1 .. 2n-1), then double (shift left by one bit)
+    first = True
+    for k in range(1, 2 * n):
+        srcs = [r for r in (E(k), O(k)) if r in live]
+        if not srcs:
+            g.emit("addc.u32" if not first else "mov.u32", E(k), *([0, 0] if not first else [0]))
+            live.add(E(k))
+            continue
+        a0 = srcs[0]
+        a1 = srcs[1] if len(srcs) > 1 else 0
+        if k == 2 * n - 1:
+            g.emit("add.u32" if first else "addc.u32", E(k), a0, a1)
+        else:
+            g.emit("add.cc.u32" if first else "addc.cc.u32", E(k), a0, a1)
+        first = False
+        live.add(E(k))
+    for r in list(live):
+        if r.startswith("o"):
+            live.discard(r)
+    for k in range(1, 2 * n):
+        if k == 2 * n - 1:
+            g.emit("add.u32" if k == 1 else "addc.u32", E(k), E(k), E(k))
+        else:
+            g.emit("add.cc.u32" if k == 1 else "addc.cc.u32", E(k), E(k), E(k))
+    # ---- squares a_i^2 at position 2i: one chain over the even-aligned pairs of E
+    g.emit("mul.lo.u32", E(0), "a0", "a0")
+    g.emit("mad.hi.cc.u32", E(1), "a0", "a0", E(1))
+    live.add(E(0))
+    for i in range(1, n):
+        g.emit("madc.lo.cc.u32", E(2 * i), f"a{i}", f"a{i}", E(2 * i))
+        if i == n - 1:
+            g.emit("madc.hi.u32", E(2 * i + 1), f"a{i}", f"a{i}", E(2 * i + 1))   # a^2 < 2^(64n): no carry out
+        else:
+            g.emit("madc.hi.cc.u32", E(2 * i + 1), f"a{i}", f"a{i}", E(2 * i + 1))
+    # ---- phase 3: n reduction rows
+    klive = set()
+    for i in range(n):
+        X, Y = (E, O) if i % 2 == 0 else (O, E)
+        x_is_e = (i % 2 == 0)
+        if i > 0:
+            # fold; carry feeds chain B (it starts at position i+1 in Y).  A word that was never written is 0
+            # (moduli with zero words, e.g. P-384, leave gaps in file O).
+            g.emit("add.cc.u32", X(i), addend(X(i)), addend(Y(i)))
+            live.add(X(i))
+            live.discard(Y(i))
+        if m0 == 1:
+            m = X(i)
+        else:
+            m = "m"
+            g.emit("mul.lo.u32", m, X(i), m0)
+        # chain B first when there is a fold carry pending (i > 0); chain A afterwards (it starts its own chain)
+        def chain(F, js, carry_in, f_is_e, top_pos):
+            started = carry_in
+            for j in js:
+                lo, hi = F(i + j), F(i + j + 1)
+                pj = P[j]
+                is_pos_i = (j == 0)
+                dst_lo = "junk" if is_pos_i else lo
+                if pj == 0:
+                    if started:
+                        g.emit("addc.cc.u32", lo, addend(lo), 0)
+                        g.emit("addc.cc.u32", hi, addend(hi), 0)
+                        live.update((lo, hi))
+                    continue
+                if pj == 1:
+                    g.emit("addc.cc.u32" if started else "add.cc.u32", dst_lo, addend(lo), m)
+                    g.emit("addc.cc.u32", hi, addend(hi), 0)
+                else:
+                    g.emit("madc.lo.cc.u32" if started else "mad.lo.cc.u32", dst_lo, m, pj, addend(lo))
+                    g.emit("madc.hi.cc.u32", hi, m, pj, addend(hi))
+                live.update((lo, hi))
+                started = True
+            # carry-out at position top_pos
+            if f_is_e:
+                kreg = K(top_pos)
+                if started:
+                    g.emit("addc.u32", kreg, kreg if kreg in klive else 0, 0)
+                    klive.add(kreg)
+            else:
+                top = F(top_pos)
+                if started:
+                    g.emit("addc.u32", top, addend(top), 0)
+                    live.add(top)
+        if i > 0:
+            chain(Y, list(range(1, n, 2)), True, not x_is_e, i + n + 1)
+            chain(X, list(range(0, n, 2)), False, x_is_e, i + n)
+        else:
+            chain(X, list(range(0, n, 2)), False, x_is_e, i + n)
+            chain(Y, list(range(1, n, 2)), False, not x_is_e, i + n + 1)
+        live.discard(X(i))
+    # ---- final: t = E[n..2n-1] + O[n..2n-1] (+ carry into t_n), then t += K
+    first = True
+    for k in range(n):
+        srcs = [r for r in (E(n + k), O(n + k)) if r in live]
+        a0 = srcs[0] if srcs else 0
+        a1 = srcs[1] if len(srcs) > 1 else 0
+        g.emit("add.cc.u32" if first else "addc.cc.u32", f"t{k}", a0, a1)
+        first = False
+    tops = [r for r in (E(2 * n), O(2 * n)) if r in live]
+    g.emit("addc.u32", f"t{n}", tops[0] if tops else 0, tops[1] if len(tops) > 1 else 0)
+    first = True
+    for k in range(n + 1):
+        kreg = K(n + k)
+        src = kreg if kreg in klive else 0
+        if k == n:
+            g.emit("add.u32" if first else "addc.u32", f"t{k}", f"t{k}", src)
+        else:
+            g.emit("add.cc.u32" if first else "addc.cc.u32", f"t{k}", f"t{k}", src)
+        first = False
+    for k in range(n):
+        g.emit("sub.cc.u32" if k == 0 else "subc.cc.u32", f"d{k}", f"t{k}", P[k])
+    g.emit("subc.u32", "dt", f"t{n}", 0)
+    g.emit("setp.ne.u32", "pq", "dt", 0)
+    for k in range(n):
+        g.emit("selp.u32", f"r{k}", f"t{k}", f"d{k}", "pq")
+    return g
+
+
 def gen_add(n, mod):
     P = words(mod, n)
     g = Prog()
@@ -308,16 +473,20 @@ def main():
            "#pragma once", "", "namespace eccb200 {", "",
            "template <class F> struct FieldPtx;", ""]
     for tag, n, mod in fields():
-        mul, add, sub = gen_mul(n, mod), gen_add(n, mod), gen_sub(n, mod)
+        mul, sqr, add, sub = gen_mul(n, mod), gen_sqr(n, mod), gen_add(n, mod), gen_sub(n, mod)
         wide, total = mul.count()
-        out.append(f"/* {tag}: mul = {wide} wide multiply-accumulates, {total} PTX instructions */")
+        swide, stotal = sqr.count()
+        out.append(f"/* {tag}: mul = {wide} wide multiply-accumulates, {total} PTX instructions; "
+                   f"sqr = {swide} wide, {stotal} PTX instructions */")
         out.append(f"template <> struct FieldPtx<{tag}> {{")
         out.append(f"\tstatic constexpr int N = {n};")
         out.append(f"\ttypedef Fe<{n}> E;")
         out.append("\tstatic __device__ __forceinline__ void mul(E &r, const E &a, const E &b)\n\t{")
         out.append(render_asm(mul, n))
         out.append("\t}")
-        out.append("\tstatic __device__ __forceinline__ void sqr(E &r, const E &a) { mul(r, a, a); }")
+        out.append("\tstatic __device__ __forceinline__ void sqr(E &r, const E &a)\n\t{")
+        out.append(render_asm(sqr, n, two_inputs=False))
+        out.append("\t}")
         out.append("\tstatic __device__ __forceinline__ void add(E &r, const E &a, const E &b)\n\t{")
         out.append(render_asm(add, n))
         out.append("\t}")
