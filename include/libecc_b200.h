@@ -34,6 +34,7 @@ extern "C" {
 #define ECCB200_OK 0        /* finite result / valid signature                                          */
 #define ECCB200_INFINITY 1  /* result is the point at infinity (prj_pt_iszero), output bytes are zero    */
 #define ECCB200_ERR (-1)    /* what the reference reports with ret = -1 (bad point, r/s range, bad sig)  */
+#define ECCB200_RETRY 2     /* signing only: the reference would restart with a fresh nonce (r = 0, s = 0, ...) */
 
 typedef struct eccb200_ctx eccb200_ctx;
 
@@ -91,6 +92,33 @@ int eccb200_ecdsa_verify_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *sigs
 			       const uint8_t *digests, uint32_t hlen, int8_t *verdict);
 int eccb200_ecdsa_verify_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_sigs, const uint8_t *d_pubkeys,
 				   const uint8_t *d_digests, uint32_t hlen, int8_t *d_verdict, void *stream);
+
+/*
+ * Batched ECDSA signing on pre-hashed messages with caller-supplied nonces: replaces, per signature,
+ * __ecdsa_sign_finalize steps 3-11 (src/sig/ecdsa_common.c:403-560): k*G (:479), prj_pt_unique (:481), r = x mod q,
+ * s = k^-1 (e + r*d) mod q (:537-540).  The nonce comes from the caller exactly as the reference's signing context
+ * takes it from its `rand` callback (src/sig/sig_algs_internal.h:158; RFC 6979 generation, src/sig/ecdsa_common.c,
+ * stays on the host).  Key generation is eccb200_prj_pt_mul_batch with points == NULL (src/sig/ec_key.c, d*G).
+ *   privkeys, nonces : n * qlen bytes each, values in [1, q-1] (else ECCB200_ERR);  digests : n * hlen bytes
+ *   sigs : n * 2*qlen bytes r||s (zero unless status is OK);  status : ECCB200_OK / ECCB200_RETRY / ECCB200_ERR
+ * NOTE: like every entry point of this library this is a throughput path, NOT a constant-time one.
+ */
+int eccb200_ecdsa_sign_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *privkeys, const uint8_t *nonces,
+			     const uint8_t *digests, uint32_t hlen, uint8_t *sigs, int8_t *status);
+int eccb200_ecdsa_sign_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_privkeys, const uint8_t *d_nonces,
+				 const uint8_t *d_digests, uint32_t hlen, uint8_t *d_sigs, int8_t *d_status,
+				 void *stream);
+
+/*
+ * Batched ECC-CDH shared-secret derivation: ecccdh_derive_secret (src/ecdh/ecccdh.c:167-233) per item — peer key
+ * import with on-curve check (src/sig/ec_key.c:181-214), prj_pt_mul(d, Q) (:209), reject infinity (:216-217),
+ * export of the affine x coordinate (:220-224).
+ *   privkeys : n * qlen;  peer_pubkeys : n * 2*plen affine;  shared : n * plen (x coordinate);  status OK / ERR
+ */
+int eccb200_ecccdh_derive_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *privkeys, const uint8_t *peer_pubkeys,
+				uint8_t *shared, int8_t *status);
+int eccb200_ecccdh_derive_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_privkeys,
+				    const uint8_t *d_peer_pubkeys, uint8_t *d_shared, int8_t *d_status, void *stream);
 
 /* Page-locked host memory for the host-pointer entry points (wrappers of cudaHostAlloc / cudaFreeHost so that a C
  * caller need not link the CUDA runtime).  NULL on failure. */

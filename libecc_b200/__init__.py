@@ -24,7 +24,8 @@ ABI_SYMBOLS = [
     "eccb200_ecdsa_verify_batch_dev", "eccb200_fp_mul_monty_batch", "eccb200_comb_window",
     "eccb200_kernel_launches", "eccb200_last_error", "eccb200_ecdsa_uv_batch",
     "eccb200_profile_enable", "eccb200_profile_read", "eccb200_imad_peak", "eccb200_prj_pt_unique_batch",
-    "eccb200_host_alloc", "eccb200_host_free",
+    "eccb200_host_alloc", "eccb200_host_free", "eccb200_ecdsa_sign_batch", "eccb200_ecdsa_sign_batch_dev",
+    "eccb200_ecccdh_derive_batch", "eccb200_ecccdh_derive_batch_dev",
 ]
 
 _lib = None
@@ -59,6 +60,10 @@ def load_library() -> ctypes.CDLL:
     lib.eccb200_ecdsa_uv_batch.argtypes = [ctypes.c_void_p, u32, u8p, u8p, u32, u8p]
     lib.eccb200_profile_enable.argtypes = [ctypes.c_void_p, ctypes.c_int]
     lib.eccb200_profile_read.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.c_int]
+    lib.eccb200_ecdsa_sign_batch.argtypes = [ctypes.c_void_p, u32, u8p, u8p, u8p, u32, u8p, i8p]
+    lib.eccb200_ecdsa_sign_batch_dev.argtypes = [ctypes.c_void_p, u32, u8p, u8p, u8p, u32, u8p, i8p, ctypes.c_void_p]
+    lib.eccb200_ecccdh_derive_batch.argtypes = [ctypes.c_void_p, u32, u8p, u8p, u8p, i8p]
+    lib.eccb200_ecccdh_derive_batch_dev.argtypes = [ctypes.c_void_p, u32, u8p, u8p, u8p, i8p, ctypes.c_void_p]
     lib.eccb200_host_alloc.argtypes = [ctypes.c_size_t]
     lib.eccb200_host_alloc.restype = ctypes.c_void_p
     lib.eccb200_host_free.argtypes = [ctypes.c_void_p]
@@ -186,6 +191,28 @@ class Engine:
             self._h, n, sg.ctypes.data, pk.ctypes.data, dg.ctypes.data, hlen, verdict.ctypes.data),
             "eccb200_ecdsa_verify_batch")
         return verdict
+
+    def ecdsa_sign_batch(self, privkeys, nonces, digests, hlen: int) -> Tuple[np.ndarray, np.ndarray]:
+        d = _as_u8(privkeys)
+        n = d.size // self.qlen
+        k = _as_u8(nonces, n * self.qlen)
+        dg = _as_u8(digests, n * hlen)
+        sigs = np.zeros((n, 2 * self.qlen), dtype=np.uint8)
+        status = np.zeros(n, dtype=np.int8)
+        self._check(self.lib.eccb200_ecdsa_sign_batch(self._h, n, d.ctypes.data, k.ctypes.data, dg.ctypes.data, hlen,
+                                                      sigs.ctypes.data, status.ctypes.data), "eccb200_ecdsa_sign_batch")
+        return sigs, status
+
+    def ecccdh_derive_batch(self, privkeys, peer_pubkeys) -> Tuple[np.ndarray, np.ndarray]:
+        d = _as_u8(privkeys)
+        n = d.size // self.qlen
+        pk = _as_u8(peer_pubkeys, n * 2 * self.plen)
+        shared = np.zeros((n, self.plen), dtype=np.uint8)
+        status = np.zeros(n, dtype=np.int8)
+        self._check(self.lib.eccb200_ecccdh_derive_batch(self._h, n, d.ctypes.data, pk.ctypes.data,
+                                                         shared.ctypes.data, status.ctypes.data),
+                    "eccb200_ecccdh_derive_batch")
+        return shared, status
 
     def prj_pt_unique_batch(self, prj_points) -> Tuple[np.ndarray, np.ndarray]:
         pp = _as_u8(prj_points)

@@ -47,6 +47,7 @@ struct eccb200_ctx {
 	uint32_t cap = 0;
 	uint32_t *jac = nullptr;
 	uint32_t *prefix = nullptr;
+	uint8_t *aff = nullptr;  /* [cap][2*plen] scratch (k*G of the signing path) */
 	/* host-pointer pipeline */
 	cudaStream_t streams[kStages] = { nullptr, nullptr, nullptr };
 	uint8_t *h_in[kStages] = { nullptr, nullptr, nullptr };   /* pinned */
@@ -56,6 +57,7 @@ struct eccb200_ctx {
 	size_t stage_in_bytes = 0, stage_out_bytes = 0;
 	uint32_t *stage_jac[kStages] = { nullptr, nullptr, nullptr };
 	uint32_t *stage_prefix[kStages] = { nullptr, nullptr, nullptr };
+	uint8_t *stage_aff[kStages] = { nullptr, nullptr, nullptr };
 	uint64_t launches = 0;
 	/* optional per-kernel timing of the device-pointer API (bench.py's roofline leg) */
 	bool profiling = false;
@@ -107,10 +109,13 @@ static int ensure_work(eccb200_ctx *ctx, uint32_t n)
 	if (n <= ctx->cap) return 0;
 	if (ctx->jac) cudaFree(ctx->jac);
 	if (ctx->prefix) cudaFree(ctx->prefix);
+	if (ctx->aff) cudaFree(ctx->aff);
 	ctx->jac = ctx->prefix = nullptr;
+	ctx->aff = nullptr;
 	ctx->cap = 0;
 	CUDA_OK(cudaMalloc(&ctx->jac, (size_t)n * 3 * ctx->N * sizeof(uint32_t)));
 	CUDA_OK(cudaMalloc(&ctx->prefix, (size_t)n * ctx->N * sizeof(uint32_t)));
+	CUDA_OK(cudaMalloc(&ctx->aff, (size_t)n * 2 * ctx->plen));
 	ctx->cap = n;
 	return 0;
 }
@@ -128,7 +133,7 @@ extern "C" int eccb200_ctx_create(eccb200_ctx **out, int curve_id, int device, i
 	CUDA_OK(cudaGetDeviceProperties(&prop, device));
 	if (prop.major != 10) return fail("libecc_b200 is built for sm_100a (B200) only");
 	if (const char *ss = getenv("ECCB200_STACK")) cudaDeviceSetLimit(cudaLimitStackSize, (size_t)atoi(ss));
-	int w = comb_window ? comb_window : 16;
+	int w = comb_window ? comb_window : 22; /* default: 22-bit windows (12 adds per 256-bit scalar, 3.2 GB table) */
 	if (w < 4 || w > 24 || (w > 16 && (w & 1))) return fail("comb_window must be in [4,16] or even in [18,24]");
 
 	eccb200_ctx *ctx = new eccb200_ctx();
@@ -201,12 +206,14 @@ extern "C" void eccb200_ctx_destroy(eccb200_ctx *ctx)
 		if (ctx->d_out[s]) cudaFree(ctx->d_out[s]);
 		if (ctx->stage_jac[s]) cudaFree(ctx->stage_jac[s]);
 		if (ctx->stage_prefix[s]) cudaFree(ctx->stage_prefix[s]);
+		if (ctx->stage_aff[s]) cudaFree(ctx->stage_aff[s]);
 	}
 	for (int i = 0; i < 3; i++)
 		if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
 	if (ctx->table) cudaFree(ctx->table);
 	if (ctx->jac) cudaFree(ctx->jac);
 	if (ctx->prefix) cudaFree(ctx->prefix);
+	if (ctx->aff) cudaFree(ctx->aff);
 	delete ctx;
 }
 
@@ -318,6 +325,7 @@ static int ensure_stages(eccb200_ctx *ctx, size_t in_bytes, size_t out_bytes)
 		if (!ctx->stage_jac[s]) {
 			CUDA_OK(cudaMalloc(&ctx->stage_jac[s], (size_t)kChunk * 3 * ctx->N * sizeof(uint32_t)));
 			CUDA_OK(cudaMalloc(&ctx->stage_prefix[s], (size_t)kChunk * ctx->N * sizeof(uint32_t)));
+			CUDA_OK(cudaMalloc(&ctx->stage_aff[s], (size_t)kChunk * 2 * ctx->plen));
 		}
 	}
 	ctx->stage_in_bytes = ib;
@@ -441,6 +449,96 @@ extern "C" int eccb200_ecdsa_verify_batch(eccb200_ctx *ctx, uint32_t n, const ui
 		const uint8_t *d = ctx->d_in[s];
 		return verify_dev(ctx, cnt, d, d + (size_t)cnt * sg, d + (size_t)cnt * (sg + pk), hlen,
 				  (int8_t *)ctx->d_out[s], ctx->streams[s]);
+	});
+}
+
+/* ------------------------------------------------------------------------------------------ sign / ECC-CDH (§8f) */
+
+static int sign_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_priv, const uint8_t *d_nonce, const uint8_t *d_dig,
+		    uint32_t hlen, uint8_t *d_sigs, int8_t *d_status, uint32_t *jac, uint32_t *prefix, uint8_t *aff,
+		    cudaStream_t st)
+{
+	if (n == 0) return 0;
+	return dispatch(ctx->curve_id, [&](auto c) {
+		typedef decltype(c) C;
+		LaunchSmul<C>::fixed(n, d_nonce, ctx->table, ctx->w, jac, d_status, st);       /* k*G          */
+		LaunchMisc<C>::to_affine(affine_grid(ctx, n), n, jac, prefix, aff, d_status, st); /* affine (x, y) */
+		LaunchMisc<C>::sign_finish(affine_grid(ctx, n), n, d_priv, d_nonce, d_dig, hlen, aff, prefix, d_sigs,
+					   d_status, st);                                        /* r, s          */
+		ctx->launches += 3;
+		CUDA_OK(cudaGetLastError());
+		return 0;
+	});
+}
+
+extern "C" int eccb200_ecdsa_sign_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_privkeys,
+					    const uint8_t *d_nonces, const uint8_t *d_digests, uint32_t hlen,
+					    uint8_t *d_sigs, int8_t *d_status, void *stream)
+{
+	if (!ctx || (n && (!d_privkeys || !d_nonces || !d_digests || !d_sigs || !d_status))) return fail("null argument");
+	if (hlen == 0 || hlen > 128) return fail("bad digest length");
+	CUDA_OK(cudaSetDevice(ctx->device));
+	if (ensure_work(ctx, n)) return -1;
+	return sign_dev(ctx, n, d_privkeys, d_nonces, d_digests, hlen, d_sigs, d_status, ctx->jac, ctx->prefix, ctx->aff,
+			(cudaStream_t)stream);
+}
+
+extern "C" int eccb200_ecdsa_sign_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *privkeys, const uint8_t *nonces,
+					const uint8_t *digests, uint32_t hlen, uint8_t *sigs, int8_t *status)
+{
+	if (!ctx || (n && (!privkeys || !nonces || !digests || !sigs || !status))) return fail("null argument");
+	if (hlen == 0 || hlen > 128) return fail("bad digest length");
+	if (n == 0) return 0;
+	const size_t ql = ctx->qlen;
+	std::vector<HostCol> in = { { (uint8_t *)privkeys, ql, false }, { (uint8_t *)nonces, ql, false },
+				    { (uint8_t *)digests, hlen, false } };
+	std::vector<HostCol> outc = { { sigs, 2 * ql, false }, { (uint8_t *)status, 1, false } };
+	return run_pipeline(ctx, n, in, outc, [&](int s, uint32_t cnt) {
+		const uint8_t *d = ctx->d_in[s];
+		return sign_dev(ctx, cnt, d, d + (size_t)cnt * ql, d + (size_t)cnt * 2 * ql, hlen, ctx->d_out[s],
+				(int8_t *)(ctx->d_out[s] + (size_t)cnt * 2 * ql), ctx->stage_jac[s], ctx->stage_prefix[s],
+				ctx->stage_aff[s], ctx->streams[s]);
+	});
+}
+
+static int ecdh_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_priv, const uint8_t *d_peers, uint8_t *d_shared,
+		    int8_t *d_status, uint32_t *jac, uint32_t *prefix, cudaStream_t st)
+{
+	if (n == 0) return 0;
+	return dispatch(ctx->curve_id, [&](auto c) {
+		typedef decltype(c) C;
+		LaunchSmul<C>::var(n, d_priv, d_peers, jac, d_status, st);
+		LaunchMisc<C>::to_x_only(affine_grid(ctx, n), n, jac, prefix, d_shared, d_status, st);
+		ctx->launches += 2;
+		CUDA_OK(cudaGetLastError());
+		return 0;
+	});
+}
+
+extern "C" int eccb200_ecccdh_derive_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_privkeys,
+					       const uint8_t *d_peer_pubkeys, uint8_t *d_shared, int8_t *d_status,
+					       void *stream)
+{
+	if (!ctx || (n && (!d_privkeys || !d_peer_pubkeys || !d_shared || !d_status))) return fail("null argument");
+	CUDA_OK(cudaSetDevice(ctx->device));
+	if (ensure_work(ctx, n)) return -1;
+	return ecdh_dev(ctx, n, d_privkeys, d_peer_pubkeys, d_shared, d_status, ctx->jac, ctx->prefix,
+			(cudaStream_t)stream);
+}
+
+extern "C" int eccb200_ecccdh_derive_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *privkeys,
+					   const uint8_t *peer_pubkeys, uint8_t *shared, int8_t *status)
+{
+	if (!ctx || (n && (!privkeys || !peer_pubkeys || !shared || !status))) return fail("null argument");
+	if (n == 0) return 0;
+	const size_t ql = ctx->qlen, pl = ctx->plen;
+	std::vector<HostCol> in = { { (uint8_t *)privkeys, ql, false }, { (uint8_t *)peer_pubkeys, 2 * pl, false } };
+	std::vector<HostCol> outc = { { shared, pl, false }, { (uint8_t *)status, 1, false } };
+	return run_pipeline(ctx, n, in, outc, [&](int s, uint32_t cnt) {
+		const uint8_t *d = ctx->d_in[s];
+		return ecdh_dev(ctx, cnt, d, d + (size_t)cnt * ql, ctx->d_out[s],
+				(int8_t *)(ctx->d_out[s] + (size_t)cnt * pl), ctx->stage_jac[s], ctx->stage_prefix[s],
+				ctx->streams[s]);
 	});
 }
 

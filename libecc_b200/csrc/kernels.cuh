@@ -231,6 +231,8 @@ __global__ void __launch_bounds__(128) k_table_merge(uint32_t count, uint64_t fi
  * MODE 1: Jacobian in, writes Montgomery-form words (comb table entry format), infinity as all-zero.
  * MODE 2: homogeneous projective in (x = X/Z, y = Y/Z, the reference's prj_pt), output as MODE 0: the batched
  *         prj_pt_unique + prj_pt_export_to_aff_buf (curves/prj_pt.c:241, :600).
+ * MODE 3: Jacobian in, writes only the big-endian x coordinate ([n][plen]); infinity is an error (-1): the shared
+ *         secret of ecccdh_derive_secret (ecdh/ecccdh.c:209-224).
  */
 template <class C, int MODE>
 __global__ void __launch_bounds__(128) k_to_affine(uint32_t n, const uint32_t *__restrict__ jac,
@@ -288,6 +290,9 @@ __global__ void __launch_bounds__(128) k_to_affine(uint32_t n, const uint32_t *_
 			if (TABLE) {
 				store_words<N>(table_out + (size_t)e * (2 * N), X);
 				store_words<N>(table_out + (size_t)e * (2 * N) + N, Y);
+			} else if (MODE == 3) {
+				F::from_mont(t, X);
+				store_be16<N>(out + (size_t)e * (4 * N), t);
 			} else {
 				F::from_mont(t, X);
 				store_be16<N>(out + (size_t)e * (8 * N), t);
@@ -300,6 +305,9 @@ __global__ void __launch_bounds__(128) k_to_affine(uint32_t n, const uint32_t *_
 			if (TABLE) {
 				store_words<N>(table_out + (size_t)e * (2 * N), zero);
 				store_words<N>(table_out + (size_t)e * (2 * N) + N, zero);
+			} else if (MODE == 3) {
+				store_be16<N>(out + (size_t)e * (4 * N), zero);
+				status[e] = -1;
 			} else {
 				store_be16<N>(out + (size_t)e * (8 * N), zero);
 				store_be16<N>(out + (size_t)e * (8 * N) + 4 * N, zero);
@@ -390,6 +398,88 @@ __global__ void __launch_bounds__(128) k_ecdsa_verify(uint32_t n, const uint8_t 
 #endif
 }
 
+/* ------------------------------------------------------------------------------------------ ECDSA sign (next row f.1) */
+
+/*
+ * Second half of a batched ECDSA signature (__ecdsa_sign_finalize steps 6-11, sig/ecdsa_common.c:479-560), after K1
+ * computed k*G and K4 normalised it:  r = x(kG) mod q,  s = k^-1 (e + r*d) mod q.
+ * k^-1 mod q uses the same simultaneous inversion as K4 (one Fermat inversion mod q per thread; the reference does
+ * one nn_modinv_fermat per signature, :537).  status: 0 ok; 2 = the reference's "restart with a new nonce" cases
+ * (r == 0 :487, e == r*d :513, s == 0 :545); -1 = d or k outside [1, q-1].
+ */
+template <class C>
+__global__ void __launch_bounds__(128) k_ecdsa_sign_finish(uint32_t n, const uint8_t *__restrict__ privkeys,
+							    const uint8_t *__restrict__ nonces,
+							    const uint8_t *__restrict__ digests, uint32_t hlen,
+							    const uint8_t *__restrict__ kG_aff,
+							    uint32_t *__restrict__ prefix, uint8_t *__restrict__ sigs,
+							    int8_t *__restrict__ status)
+{
+	typedef Field<typename C::Fq> Fq;
+	constexpr int N = C::N;
+	const uint32_t T = gridDim.x * blockDim.x;
+	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+	if (tid >= n) return;
+	Fe<N> acc;
+	Fq::set_one(acc);
+	uint32_t last = tid;
+	for (uint32_t e = tid; e < n; e += T) {
+		Fe<N> kk, km;
+		load_be16<N>(kk, nonces + (size_t)e * (4 * N));
+		store_words<N>(prefix + (size_t)e * N, acc);
+		if (!Fq::is_zero(kk) && !Fq::geq_mod(kk)) {
+			Fe<N> t;
+			Fq::to_mont(km, kk);
+			Fq::mul(t, acc, km);
+			acc = t;
+		}
+		last = e;
+		if (n - e <= T) break;
+	}
+	Fe<N> inv;
+	Fq::inv(inv, acc);
+	for (uint32_t e = last;; e -= T) {
+		Fe<N> kk, d, x, r, ev, s, zero;
+		Fq::set_zero(zero);
+		load_be16<N>(kk, nonces + (size_t)e * (4 * N));
+		load_be16<N>(d, privkeys + (size_t)e * (4 * N));
+		bool k_ok = !Fq::is_zero(kk) && !Fq::geq_mod(kk);
+		bool d_ok = !Fq::is_zero(d) && !Fq::geq_mod(d);
+		int st = 0;
+		r = zero;
+		s = zero;
+		if (k_ok) {
+			Fe<N> km, pre, kinv, t, dm;
+			load_words<N>(pre, prefix + (size_t)e * N);
+			Fq::to_mont(km, kk);
+			Fq::mul(kinv, inv, pre);  /* k^-1 in Montgomery form */
+			Fq::mul(t, inv, km);
+			inv = t;
+			load_be16<N>(x, kG_aff + (size_t)e * (8 * N));
+			r = x;
+			scalar_reduce<C>(r);                        /* r = W_x mod q          (:483) */
+			digest_to_scalar<C>(ev, digests + (size_t)e * hlen, hlen);
+			Fq::to_mont(dm, d);
+			Fq::mul(t, r, dm);                          /* x*r mod q              (:510) */
+			bool restart = Fq::is_zero(r) || Fq::eq(t, ev);
+			Fq::add(t, t, ev);                          /* e + x*r                (:521) */
+			Fq::mul(s, t, kinv);                        /* s = k^-1 (e + x*r)     (:540) */
+			restart = restart || Fq::is_zero(s);
+			st = d_ok ? (restart ? 2 : 0) : -1;
+		} else {
+			st = -1;
+		}
+		if (st != 0) {
+			r = zero;
+			s = zero;
+		}
+		store_be16<N>(sigs + (size_t)e * (8 * N), r);
+		store_be16<N>(sigs + (size_t)e * (8 * N) + 4 * N, s);
+		status[e] = (int8_t)st;
+		if (e < T) break;
+	}
+}
+
 /* ------------------------------------------------------------------------------------------ unit-test kernels */
 
 /* mod-q scalar preparation of ECDSA verify alone: out[i] = u || v (big-endian), for the arithmetic unit tests */
@@ -454,6 +544,11 @@ template <class C> struct LaunchMisc {
 			     cudaStream_t st);
 	static void prj_unique(uint32_t blocks, uint32_t n, const uint8_t *prj, uint32_t *jac, uint32_t *prefix,
 			       uint8_t *out, int8_t *status, cudaStream_t st);
+	static void to_x_only(uint32_t blocks, uint32_t n, const uint32_t *jac, uint32_t *prefix, uint8_t *out,
+			      int8_t *status, cudaStream_t st);
+	static void sign_finish(uint32_t blocks, uint32_t n, const uint8_t *privkeys, const uint8_t *nonces,
+				const uint8_t *digests, uint32_t hlen, const uint8_t *kG_aff, uint32_t *prefix,
+				uint8_t *sigs, int8_t *status, cudaStream_t st);
 	static void fp_mul(int which, uint32_t n, const uint8_t *a, const uint8_t *b, uint8_t *out, cudaStream_t st);
 };
 
@@ -495,6 +590,20 @@ void LaunchMisc<C>::to_affine(uint32_t blocks, uint32_t n, const uint32_t *jac, 
 			      int8_t *status, cudaStream_t st)
 {
 	k_to_affine<C, 0><<<blocks, kThreads, 0, st>>>(n, jac, prefix, out, status, nullptr);
+}
+template <class C>
+void LaunchMisc<C>::to_x_only(uint32_t blocks, uint32_t n, const uint32_t *jac, uint32_t *prefix, uint8_t *out,
+			      int8_t *status, cudaStream_t st)
+{
+	k_to_affine<C, 3><<<blocks, kThreads, 0, st>>>(n, jac, prefix, out, status, nullptr);
+}
+template <class C>
+void LaunchMisc<C>::sign_finish(uint32_t blocks, uint32_t n, const uint8_t *privkeys, const uint8_t *nonces,
+				const uint8_t *digests, uint32_t hlen, const uint8_t *kG_aff, uint32_t *prefix,
+				uint8_t *sigs, int8_t *status, cudaStream_t st)
+{
+	k_ecdsa_sign_finish<C><<<blocks, kThreads, 0, st>>>(n, privkeys, nonces, digests, hlen, kG_aff, prefix, sigs,
+							     status);
 }
 template <class C>
 void LaunchMisc<C>::prj_unique(uint32_t blocks, uint32_t n, const uint8_t *prj, uint32_t *jac, uint32_t *prefix,

@@ -634,7 +634,8 @@ static void *verify_worker(void *arg)
 }
 
 /* __ecdsa_sign_finalize (sig/ecdsa_common.c:318-586) with the nonce supplied by the caller (the reference's
- * test harness injects it the same way, tests/ec_self_tests_core.h:34): r = x(kG) mod q, s = k^-1 (x r + e) mod q */
+ * test harness injects it the same way, tests/ec_self_tests_core.h:34): r = x(kG) mod q, s = k^-1 (x r + e) mod q.
+ * Returns 0, -1 (d or k out of range) or 2 where the reference would "goto restart" with a new nonce. */
 static int ecdsa_sign_one(uint8_t *sig, const uint8_t *priv, const uint8_t *nonce, const uint8_t *h,
 			  uint32_t hlen, const curve_t *c)
 {
@@ -654,12 +655,13 @@ static int ecdsa_sign_one(uint8_t *sig, const uint8_t *priv, const uint8_t *nonc
 	if (pt_unique(&A, &kG, c)) return -1;
 	memcpy(r, A.X, sizeof(r));
 	reduce_mod_q(r, c);
-	if (nn_iszero_n(r, n)) return -1;
+	if (nn_iszero_n(r, n)) return 2;               /* 7. r == 0 -> restart (:487) */
 	mod_mul(t, d, r, &c->fq);
+	if (nn_cmp_n(e, t, n) == 0) return 2;          /* 8. e == rx -> restart (:513) */
 	mod_add(t, t, e, &c->fq);
 	mod_inv_fermat(kinv, k, &c->fq);
 	mod_mul(s, kinv, t, &c->fq);
-	if (nn_iszero_n(s, n)) return -1;
+	if (nn_iszero_n(s, n)) return 2;               /* 10. s == 0 -> restart (:545) */
 	nn_to_be(sig, c->qlen, r, n);
 	nn_to_be(sig + c->qlen, c->qlen, s, n);
 	return 0;

@@ -212,3 +212,48 @@ def test_ecdsa_scalar_preparation_mod_q(curve):
             w = pow(s, -1, q)
             assert int.from_bytes(uv[i, :qlen].tobytes(), "big") == e * w % q
             assert int.from_bytes(uv[i, qlen:].tobytes(), "big") == r * w % q
+
+
+def test_ecdsa_sign_batch_kat_and_oracle():
+    """Row (f).1: batched ECDSA signing.  The reference's own KATs inject the nonce (ec_self_tests_core.h:34); with
+    the same nonce the device must reproduce the expected signature bit for bit."""
+    from common import oracle_sign
+    for v in golden("ecdsa_kat.json"):
+        if "nonce" not in v:
+            continue
+        sig, st = engine(v["curve"]).ecdsa_sign_batch(hx(v["priv"]), hx(v["nonce"]), hx(v["digest"]), HASHLEN[v["hash"]])
+        assert st[0] == 0 and sig[0].tobytes().hex() == v["sig"], v["name"]
+    for curve, hlen in (("SECP256R1", 32), ("FRP256V1", 32), ("SECP384R1", 48), ("SECP256R1", 64)):
+        _, plen, qlen = CURVES[curve]
+        q = ORDER[curve]
+        n = 3000
+        d = random_scalars(curve, n, tag=91); k = random_scalars(curve, n, tag=92)
+        dg = rng(93).integers(0, 256, size=(n, hlen), dtype=np.uint8)
+        k[0] = 0                                                      # k = 0      -> -1
+        k[1] = np.frombuffer(q.to_bytes(qlen, "big"), dtype=np.uint8)  # k = q      -> -1
+        d[2] = 0                                                      # d = 0      -> -1
+        d[3] = 0xFF                                                   # d >= q     -> -1
+        want, wst = oracle_sign(curve, d, k, dg, hlen)
+        sig, st = engine(curve).ecdsa_sign_batch(d, k, dg, hlen)
+        assert (st == wst).all() and (wst[:4] == -1).all() and (wst[4:] == 0).all()
+        assert (sig[4:] == want[4:]).all() and (sig[:4] == 0).all()
+        pubs, pst = engine(curve).prj_pt_mul_batch(d[4:])             # key generation = fixed-base batch
+        assert (engine(curve).ecdsa_verify_batch(sig[4:], pubs, dg[4:], hlen) == 0).all()
+
+
+@pytest.mark.parametrize("curve", ["SECP256R1", "SECP384R1"])
+def test_ecccdh_derive_batch(curve):
+    """Row (f).2: batched ecccdh_derive_secret — NIST KATs and every uncompressed Wycheproof ECDH vector."""
+    _, plen, qlen = CURVES[curve]
+    vecs = [v for v in golden("ecccdh_kat.json") if v["curve"] == curve]
+    sh, st = engine(curve).ecccdh_derive_batch(np.stack([hx(v["priv"]) for v in vecs]),
+                                               np.stack([hx(v["peer_pub"]) for v in vecs]))
+    assert (st == 0).all() and [s.tobytes().hex() for s in sh] == [v["shared"] for v in vecs]
+    vecs = [v for v in golden("wycheproof_ecdh.json.gz") if v["curve"] == curve and len(v["priv"]) <= 2 * qlen]
+    sh, st = engine(curve).ecccdh_derive_batch(np.stack([hx(v["priv"].rjust(2 * qlen, "0")) for v in vecs]),
+                                               np.stack([hx(v["peer_pub"]) for v in vecs]))
+    for v, s, t in zip(vecs, sh, st):
+        if v["ref_status"] == 0:
+            assert t == 0 and s.tobytes().hex() == v["ref_point"][: 2 * plen], v["name"]
+        else:  # off-curve peer key (-1) or infinity result (1): ecccdh_derive_secret fails in both cases
+            assert t == -1 and not s.any(), v["name"]
