@@ -142,6 +142,12 @@ int eccb200_ecdsa_uv_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *sigs, co
 int eccb200_profile_enable(eccb200_ctx *ctx, int on);
 int eccb200_profile_read(eccb200_ctx *ctx, float *ms, int cap);
 
+/* Layout experiment behind DESIGN.md §3: `iters` dependent Montgomery products per element with the production
+ * one-thread-per-element multiplier (striped = 0) or with the words of an element striped over 8 lanes and
+ * __shfl_sync carries (striped = 1; 256-bit curves).  Results are identical; *ms is the kernel time. */
+int eccb200_fp_mul_chain_bench(eccb200_ctx *ctx, int striped, uint32_t n, const uint8_t *a, const uint8_t *b,
+			       uint8_t *out, int iters, float *ms);
+
 /* imad_peak micro-benchmark: measured 32x32+64 integer multiply-add throughput of the device (IMAD32 per second) —
  * the denominator of the roofline for this integer-MAD-bound path — and the same figure per clock
  * per SM at the device's nominal maximum SM clock. */

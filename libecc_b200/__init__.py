@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "eccb200_kernel_launches", "eccb200_last_error", "eccb200_ecdsa_uv_batch",
     "eccb200_profile_enable", "eccb200_profile_read", "eccb200_imad_peak", "eccb200_prj_pt_unique_batch",
     "eccb200_host_alloc", "eccb200_host_free", "eccb200_ecdsa_sign_batch", "eccb200_ecdsa_sign_batch_dev",
-    "eccb200_ecccdh_derive_batch", "eccb200_ecccdh_derive_batch_dev",
+    "eccb200_ecccdh_derive_batch", "eccb200_ecccdh_derive_batch_dev", "eccb200_fp_mul_chain_bench",
 ]
 
 _lib = None
@@ -64,6 +64,8 @@ def load_library() -> ctypes.CDLL:
     lib.eccb200_ecdsa_sign_batch_dev.argtypes = [ctypes.c_void_p, u32, u8p, u8p, u8p, u32, u8p, i8p, ctypes.c_void_p]
     lib.eccb200_ecccdh_derive_batch.argtypes = [ctypes.c_void_p, u32, u8p, u8p, u8p, i8p]
     lib.eccb200_ecccdh_derive_batch_dev.argtypes = [ctypes.c_void_p, u32, u8p, u8p, u8p, i8p, ctypes.c_void_p]
+    lib.eccb200_fp_mul_chain_bench.argtypes = [ctypes.c_void_p, ctypes.c_int, u32, u8p, u8p, u8p, ctypes.c_int,
+                                               ctypes.POINTER(ctypes.c_float)]
     lib.eccb200_host_alloc.argtypes = [ctypes.c_size_t]
     lib.eccb200_host_alloc.restype = ctypes.c_void_p
     lib.eccb200_host_free.argtypes = [ctypes.c_void_p]
@@ -231,6 +233,17 @@ class Engine:
         self._check(self.lib.eccb200_ecdsa_uv_batch(self._h, n, sg.ctypes.data, dg.ctypes.data, hlen,
                                                     out.ctypes.data), "eccb200_ecdsa_uv_batch")
         return out
+
+    def fp_mul_chain_bench(self, a, b, iters: int, striped: bool):
+        x = _as_u8(a)
+        n = x.size // self.plen
+        y = _as_u8(b, n * self.plen)
+        out = np.zeros((n, self.plen), dtype=np.uint8)
+        ms = ctypes.c_float()
+        self._check(self.lib.eccb200_fp_mul_chain_bench(self._h, int(striped), n, x.ctypes.data, y.ctypes.data,
+                                                        out.ctypes.data, iters, ctypes.byref(ms)),
+                    "eccb200_fp_mul_chain_bench")
+        return out, float(ms.value)
 
     def fp_mul_monty_batch(self, a, b, which: int = 0) -> np.ndarray:
         x = _as_u8(a)

@@ -245,24 +245,36 @@ template <class C> ECC_HD void scalar_reduce(Fe<C::N> &k)
 	for (int it = 0; it < 4; it++) Fq::cond_sub_mod(k, k);
 }
 
-/* w-bit unsigned digit i of k (bits [w*i, w*i+w)), w <= 16 */
-template <int N> ECC_HD uint32_t comb_digit(const Fe<N> &k, int i, int w)
+/* 64-bit funnel shifts on word pairs (static register indices only: the scalar walks through the window loop by
+ * being shifted, never by dynamic indexing — see DESIGN.md §8, "nvcc stack-colouring hazard"). */
+ECC_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) /* low word of ((hi:lo) >> sh), 0 <= sh < 32 */
 {
-	int bit = i * w;
-	int wi = bit >> 5, sh = bit & 31;
-	uint32_t lo = 0, hi = 0;
+#if defined(__CUDA_ARCH__)
+	return __funnelshift_r(lo, hi, sh);
+#else
+	return (uint32_t)((((uint64_t)hi << 32) | lo) >> sh);
+#endif
+}
+ECC_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, int sh) /* high word of ((hi:lo) << sh), 0 <= sh < 32 */
+{
+#if defined(__CUDA_ARCH__)
+	return __funnelshift_l(lo, hi, sh);
+#else
+	return (uint32_t)(((((uint64_t)hi << 32) | lo) << sh) >> 32);
+#endif
+}
+
+/* k >>= w (0 < w < 32) */
+template <int N> ECC_HD void shift_right(Fe<N> &k, int w)
+{
 #pragma unroll
-	for (int j = 0; j < N; j++) {
-		lo = (j == wi) ? k.w[j] : lo;
-		hi = (j == wi + 1) ? k.w[j] : hi;
-	}
-	uint64_t v = ((uint64_t)hi << 32) | lo;
-	return (uint32_t)(v >> sh) & ((1u << w) - 1u);
+	for (int j = 0; j < N - 1; j++) k.w[j] = funnel_r(k.w[j], k.w[j + 1], w);
+	k.w[N - 1] >>= w;
 }
 
 /*
  * Fixed-base comb: acc = sum_i T[i][digit_i(k)],  T[i][d] = d * 2^(w*i) * G  (affine, Montgomery form, entry
- * (i << w) + d; d == 0 unused).  One mixed addition per non-zero window, no doublings.  k must be < q.
+ * (i << w) + d; d == 0 unused), 4 <= w <= 24.  One mixed addition per non-zero window, no doublings.  k must be < q.
  * For k < q the accumulator before window i is (k mod 2^(w*i))*G with 0 <= k mod 2^(w*i) < 2^(w*i) <= d*2^(w*i) < q,
  * so the add never meets P = +-Q; add_mixed resolves those cases anyway.
  */
@@ -302,9 +314,12 @@ template <class C> ECC_HD void comb_mul(Jac<C> &acc, const Fe<C::N> &k, const ui
 	constexpr int N = C::N;
 	G::set_inf(acc);
 	const int nwin = (C::QBITS + w - 1) / w;
+	const uint32_t mask = (1u << w) - 1u;
+	Fe<N> kk = k; /* consumed w bits at a time from the least significant end */
 #pragma unroll 1
 	for (int i = 0; i < nwin; i++) {
-		uint32_t d = comb_digit<N>(k, i, w);
+		uint32_t d = kk.w[0] & mask;
+		shift_right<N>(kk, w);
 		if (d != 0) {
 			Aff<C> t;
 			load_table_entry<C>(t, table, ((size_t)i << w) + d);
@@ -351,10 +366,10 @@ ECC_HD void window_mul(Jac<C> &acc, const Fe<C::N> &k, const Aff<C> &P, const Ja
 		if (di >= 0) {
 #pragma unroll 1
 			for (int q = 0; q < 4; q++) G::dbl(acc, acc);
-			uint32_t word = 0;
+			int d = (int)(kk[N - 1] >> 28) - 8; /* most significant nibble, then K' <<= 4 */
 #pragma unroll
-			for (int j = 0; j < N; j++) word = (j == (di >> 3)) ? kk[j] : word;
-			int d = (int)((word >> (4 * (di & 7))) & 15u) - 8;
+			for (int j = N - 1; j > 0; j--) kk[j] = funnel_l(kk[j - 1], kk[j], 4);
+			kk[0] <<= 4;
 			int ad = d < 0 ? -d : d;
 			have = d != 0;
 			e = tbl[(ad - 1) & 7];

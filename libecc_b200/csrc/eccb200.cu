@@ -643,6 +643,46 @@ extern "C" int eccb200_ecdsa_uv_batch(eccb200_ctx *ctx, uint32_t n, const uint8_
 	return rc;
 }
 
+/* Layout experiment entry point: out[i] = a[i] * b[i]^iters in the Montgomery sense, computed by the
+ * production thread-per-element multiplier (striped = 0) or by the 8-lanes-per-element shuffle variant (striped = 1,
+ * 256-bit curves only); *ms receives the kernel's device time. */
+extern "C" int eccb200_fp_mul_chain_bench(eccb200_ctx *ctx, int striped, uint32_t n, const uint8_t *a,
+					  const uint8_t *b, uint8_t *out, int iters, float *ms)
+{
+	if (!ctx || !a || !b || !out || !ms || n == 0 || (n & 3)) return fail("bad argument (n must be a multiple of 4)");
+	if (striped && ctx->N != 8) return fail("striped variant exists for 8-word fields only");
+	CUDA_OK(cudaSetDevice(ctx->device));
+	size_t bytes = (size_t)n * ctx->plen;
+	uint8_t *d = nullptr;
+	CUDA_OK(cudaMalloc(&d, 3 * bytes));
+	cudaEvent_t e0, e1;
+	CUDA_OK(cudaEventCreate(&e0));
+	CUDA_OK(cudaEventCreate(&e1));
+	int rc = 0;
+	if (cudaMemcpy(d, a, bytes, cudaMemcpyHostToDevice) != cudaSuccess ||
+	    cudaMemcpy(d + bytes, b, bytes, cudaMemcpyHostToDevice) != cudaSuccess)
+		rc = fail("H2D copy failed");
+	if (!rc)
+		rc = dispatch(ctx->curve_id, [&](auto c) {
+			typedef decltype(c) C;
+			for (int r = 0; r < 3; r++) { /* two warm-ups, keep the last timing */
+				cudaEventRecord(e0, 0);
+				LaunchMisc<C>::fp_mul_chain(striped, n, d, d + bytes, d + 2 * bytes, iters, 0);
+				cudaEventRecord(e1, 0);
+				CUDA_OK(cudaEventSynchronize(e1));
+				ctx->launches += 1;
+			}
+			CUDA_OK(cudaGetLastError());
+			CUDA_OK(cudaEventElapsedTime(ms, e0, e1));
+			CUDA_OK(cudaMemcpy(out, d + 2 * bytes, bytes, cudaMemcpyDeviceToHost));
+			return 0;
+		});
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	cudaFree(d);
+	return rc;
+}
+
 /* ------------------------------------------------------------------------------------------ imad_peak */
 /*
  * Integer multiply-add peak of the device: the denominator of the roofline (it is not in

@@ -119,8 +119,14 @@ __global__ void __launch_bounds__(128) k_smul_fixed(uint32_t n, const uint8_t *_
 
 /* ------------------------------------------------------------------------------------------ K2: variable base */
 
+#ifndef ECC_MINB_VAR
+#define ECC_MINB_VAR 1
+#endif
+#ifndef ECC_MINB_VERIFY
+#define ECC_MINB_VERIFY 1
+#endif
 template <class C>
-__global__ void __launch_bounds__(128) k_smul_var(uint32_t n, const uint8_t *__restrict__ scalars,
+__global__ void __launch_bounds__(128, ECC_MINB_VAR) k_smul_var(uint32_t n, const uint8_t *__restrict__ scalars,
 						  const uint8_t *__restrict__ points, uint32_t *__restrict__ jac,
 						  int8_t *__restrict__ status)
 {
@@ -374,7 +380,7 @@ __global__ void __launch_bounds__(128) k_prj_load(uint32_t n, const uint8_t *__r
  * digests: hlen bytes each; e = leftmost min(8*hlen, bitlen(q)) bits (:760-775), reduced mod q (:777).
  */
 template <class C>
-__global__ void __launch_bounds__(128) k_ecdsa_verify(uint32_t n, const uint8_t *__restrict__ sigs,
+__global__ void __launch_bounds__(128, ECC_MINB_VERIFY) k_ecdsa_verify(uint32_t n, const uint8_t *__restrict__ sigs,
 						      const uint8_t *__restrict__ pubkeys,
 						      const uint8_t *__restrict__ digests, uint32_t hlen,
 						      const uint32_t *__restrict__ table, int w,
@@ -514,6 +520,112 @@ __global__ void k_fp_mul_monty(uint32_t n, const uint8_t *__restrict__ a, const 
 	store_be16<N>(out + (size_t)idx * (4 * N), z);
 }
 
+/*
+ * Layout experiment: the SAME Montgomery product with the N = 8 words of an element striped across
+ * 8 lanes (4 elements per warp) and every cross-word carry / broadcast done with __shfl_sync, as the north star
+ * sketches — versus the production layout (one thread owns the element).  Both kernels run `iters` dependent
+ * products x <- x*y per element so that only arithmetic is timed; k_fp_mul_chain is the production multiplier.
+ * Striped algorithm per row i: b_i broadcast; t_j += lo(a_j b_i), t_{j+1} += hi(a_j b_i) (shfl_up); m = t_0*M0
+ * broadcast; the same with p_j m; one-word right shift (shfl_down).  t_j are 64-bit with deferred carries; a final
+ * ripple normalises and subtracts p.  8-word fields only.
+ */
+template <class FT>
+__global__ void __launch_bounds__(128) k_fp_mul_chain(uint32_t n, const uint8_t *__restrict__ a,
+						      const uint8_t *__restrict__ b, uint8_t *__restrict__ out, int iters)
+{
+	constexpr int N = FT::N;
+	uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= n) return;
+	Fe<N> x, y;
+	load_be16<N>(x, a + (size_t)idx * (4 * N));
+	load_be16<N>(y, b + (size_t)idx * (4 * N));
+#pragma unroll 1
+	for (int i = 0; i < iters; i++) Field<FT>::mul(x, x, y);
+	store_be16<N>(out + (size_t)idx * (4 * N), x);
+}
+
+template <class FT>
+__global__ void __launch_bounds__(128) k_fp_mul_striped_chain(uint32_t n, const uint8_t *__restrict__ a,
+							      const uint8_t *__restrict__ b,
+							      uint8_t *__restrict__ out, int iters)
+{
+	static_assert(FT::N == 8, "striped experiment is written for 8-word fields");
+	constexpr int N = 8;
+	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t elem = gtid / N;
+	const int j = (int)(gtid % N); /* word index = lane within the 8-lane group */
+	if (elem >= n) return;         /* n is a multiple of 4 in the benchmark, so whole groups exit together */
+	/* big-endian wire: word j (little-endian index) sits at byte offset 4*(N-1-j) */
+	auto ldw = [&](const uint8_t *base) {
+		uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(base + (size_t)elem * (4 * N) + 4 * (N - 1 - j)));
+		return bswap32(v);
+	};
+	uint32_t x = ldw(a), y = ldw(b);
+	uint32_t pj = 0;
+#pragma unroll
+	for (int k = 0; k < N; k++) pj = (k == j) ? FT::P(k) : pj;
+	const unsigned full = 0xffffffffu;
+#pragma unroll 1
+	for (int it = 0; it < iters; it++) {
+		uint64_t t = 0, tN = 0; /* position j, and (lane N-1 only) position N */
+#pragma unroll
+		for (int i = 0; i < N; i++) {
+			uint32_t bi = __shfl_sync(full, y, i, N);
+			uint64_t pr = (uint64_t)x * bi;
+			t += (uint32_t)pr;
+			uint32_t hi = (uint32_t)(pr >> 32);
+			uint32_t up = __shfl_up_sync(full, hi, 1, N);
+			if (j > 0) t += up;
+			if (j == N - 1) tN += hi;
+			uint32_t m = __shfl_sync(full, (uint32_t)t * FT::M0, 0, N);
+			pr = (uint64_t)pj * m;
+			t += (uint32_t)pr;
+			hi = (uint32_t)(pr >> 32);
+			up = __shfl_up_sync(full, hi, 1, N);
+			if (j > 0) t += up;
+			if (j == N - 1) tN += hi;
+			/* shift right by one word; lane 0 keeps the carry of the word that drops out */
+			uint64_t c0 = t >> 32;
+			uint32_t dlo = __shfl_down_sync(full, (uint32_t)t, 1, N);
+			uint32_t dhi = __shfl_down_sync(full, (uint32_t)(t >> 32), 1, N);
+			uint64_t nt = ((uint64_t)dhi << 32) | dlo;
+			if (j == N - 1) {
+				nt = tN;
+				tN = 0;
+			}
+			if (j == 0) nt += c0;
+			t = nt;
+		}
+		/* ripple the deferred carries, word by word */
+		uint32_t topc = 0;
+#pragma unroll
+		for (int k = 0; k < N; k++) {
+			uint32_t c = (uint32_t)(t >> 32);
+			uint32_t cin = __shfl_up_sync(full, c, 1, N);
+			if (j == k) t &= 0xffffffffull;
+			if (j == k + 1) t += cin;
+			if (k == N - 1) topc = __shfl_sync(full, c, N - 1, N);
+		}
+		uint32_t r = (uint32_t)t;
+		/* d = r - p with a rippled borrow; take d when r >= p or the carry word is set */
+		uint32_t borrow = 0, dword = r;
+#pragma unroll
+		for (int k = 0; k < N; k++) {
+			uint32_t bin = __shfl_sync(full, borrow, (k == 0) ? 0 : k - 1, N);
+			if (k == 0) bin = 0;
+			if (j == k) {
+				uint64_t dd = (uint64_t)r - pj - bin;
+				dword = (uint32_t)dd;
+				borrow = (uint32_t)(dd >> 63);
+			}
+		}
+		uint32_t last_borrow = __shfl_sync(full, borrow, N - 1, N);
+		x = (topc != 0 || last_borrow == 0) ? dword : r;
+	}
+	uint32_t *o = reinterpret_cast<uint32_t *>(out + (size_t)elem * (4 * N) + 4 * (N - 1 - j));
+	*o = bswap32(x);
+}
+
 } // namespace eccb200
 
 /* ------------------------------------------------------------------------------------------ launchers */
@@ -550,6 +662,8 @@ template <class C> struct LaunchMisc {
 				const uint8_t *digests, uint32_t hlen, const uint8_t *kG_aff, uint32_t *prefix,
 				uint8_t *sigs, int8_t *status, cudaStream_t st);
 	static void fp_mul(int which, uint32_t n, const uint8_t *a, const uint8_t *b, uint8_t *out, cudaStream_t st);
+	static void fp_mul_chain(int striped, uint32_t n, const uint8_t *a, const uint8_t *b, uint8_t *out, int iters,
+				 cudaStream_t st);
 };
 
 template <class C> struct LaunchVerify {
@@ -625,6 +739,27 @@ void LaunchMisc<C>::fp_mul(int which, uint32_t n, const uint8_t *a, const uint8_
 		k_fp_mul_monty<typename C::Fp><<<grid_for(n), kThreads, 0, st>>>(n, a, b, out);
 	else
 		k_fp_mul_monty<typename C::Fq><<<grid_for(n), kThreads, 0, st>>>(n, a, b, out);
+}
+#endif
+
+#if defined(ECC_TU_MISC)
+template <class C, int NW> struct StripedLaunch {
+	static void go(uint32_t, const uint8_t *, const uint8_t *, uint8_t *, int, cudaStream_t) {}
+};
+template <class C> struct StripedLaunch<C, 8> {
+	static void go(uint32_t n, const uint8_t *a, const uint8_t *b, uint8_t *out, int iters, cudaStream_t st)
+	{
+		k_fp_mul_striped_chain<typename C::Fp><<<grid_for(n * 8), kThreads, 0, st>>>(n, a, b, out, iters);
+	}
+};
+template <class C>
+void LaunchMisc<C>::fp_mul_chain(int striped, uint32_t n, const uint8_t *a, const uint8_t *b, uint8_t *out,
+				 int iters, cudaStream_t st)
+{
+	if (striped)
+		StripedLaunch<C, C::N>::go(n, a, b, out, iters, st);
+	else
+		k_fp_mul_chain<typename C::Fp><<<grid_for(n), kThreads, 0, st>>>(n, a, b, out, iters);
 }
 #endif
 

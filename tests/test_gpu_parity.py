@@ -125,11 +125,13 @@ def test_wycheproof_ecdsa_all(curve):
         assert (got == want).all(), [v["name"] for v, g_, w_ in zip(vs, got, want) if g_ != w_][:5]
 
 
-@pytest.mark.parametrize("curve,hlen", [("FRP256V1", 32), ("SECP256R1", 32), ("SECP384R1", 48), ("SECP256R1", 64),
-                                        ("SECP384R1", 20)])
-def test_ecdsa_synthetic_with_corruptions(curve, hlen):
+@pytest.mark.parametrize("curve,hlen,w", [("FRP256V1", 32, 0), ("SECP256R1", 32, 0), ("SECP384R1", 48, 0),
+                                          ("SECP256R1", 64, 13), ("SECP384R1", 20, 8), ("FRP256V1", 32, 16),
+                                          ("SECP256R1", 32, 18)])
+def test_ecdsa_synthetic_with_corruptions(curve, hlen, w):
+    """Includes comb windows that straddle 32-bit words (13, 18, default 22) and ones that do not (8, 16)."""
     sigs, pubs, dg, expected = make_signatures(curve, 512, tag=hlen, hlen=hlen, corrupt_every=8)
-    got = engine(curve).ecdsa_verify_batch(sigs, pubs, dg, hlen)
+    got = engine(curve, w).ecdsa_verify_batch(sigs, pubs, dg, hlen)
     assert (got == expected).all()
     assert (expected[::8] == -1).all() and (np.delete(expected, np.s_[::8]) == 0).all()
 
@@ -257,3 +259,23 @@ def test_ecccdh_derive_batch(curve):
             assert t == 0 and s.tobytes().hex() == v["ref_point"][: 2 * plen], v["name"]
         else:  # off-curve peer key (-1) or infinity result (1): ecccdh_derive_secret fails in both cases
             assert t == -1 and not s.any(), v["name"]
+
+
+@pytest.mark.parametrize("curve", ["SECP256R1", "FRP256V1"])
+def test_layout_experiment_kernels_agree(curve):
+    """the lane-striped (__shfl_sync) multiplier computes the same products as the production one."""
+    _, plen, _ = CURVES[curve]
+    p = PRIME[curve]
+    g = rng(97)
+    n = 4096
+    a = [int.from_bytes(g.bytes(plen + 8), "big") % p for _ in range(n)]
+    b = [int.from_bytes(g.bytes(plen + 8), "big") % p for _ in range(n)]
+    a[0], b[0] = p - 1, p - 1
+    a[1], b[1] = 0, 5
+    iters = 3
+    o0, _ = engine(curve, 8).fp_mul_chain_bench(be(a, plen), be(b, plen), iters, striped=False)
+    o1, _ = engine(curve, 8).fp_mul_chain_bench(be(a, plen), be(b, plen), iters, striped=True)
+    rinv = pow(1 << (8 * plen), -1, p)
+    want = [x * pow(y * rinv, iters, p) % p for x, y in zip(a, b)]
+    assert [int.from_bytes(o.tobytes(), "big") for o in o0] == want
+    assert (o0 == o1).all()
