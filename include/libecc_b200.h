@@ -137,7 +137,8 @@ int eccb200_ecdsa_uv_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *sigs, co
 			   uint8_t *out);
 
 /* Per-kernel device timing of the device-pointer entry points (CUDA events recorded on the caller's stream around
- * each kernel).  eccb200_profile_read waits for the last timed call and returns how many durations (ms) it wrote:
+ * each kernel).  eccb200_profile_read waits for the timed calls issued since the previous read (up to 64), sums their
+ * durations per kernel position and returns how many values (ms) it wrote:
  * prj_pt_mul_batch_dev -> [scalar-mult kernel, batched normalisation]; ecdsa_verify_batch_dev -> [verify kernel]. */
 int eccb200_profile_enable(eccb200_ctx *ctx, int on);
 int eccb200_profile_read(eccb200_ctx *ctx, float *ms, int cap);

@@ -61,8 +61,11 @@ struct eccb200_ctx {
 	uint64_t launches = 0;
 	/* optional per-kernel timing of the device-pointer API (bench.py's roofline leg) */
 	bool profiling = false;
-	cudaEvent_t ev[3] = { nullptr, nullptr, nullptr };
-	int ev_count = 0; /* kernels timed by the last device-pointer call */
+	static const int kProfCalls = 64;
+	cudaEvent_t ev[kProfCalls][3];  /* per timed call: before kernel 0, between, after kernel 1 */
+	int ev_kernels[kProfCalls];     /* kernels timed by that call (1 or 2) */
+	int ev_calls = 0;               /* timed device-pointer calls since the last eccb200_profile_read */
+	bool ev_ready = false;
 };
 
 template <class Fn> static int dispatch(int curve_id, Fn &&fn)
@@ -152,7 +155,7 @@ extern "C" int eccb200_ctx_create(eccb200_ctx **out, int curve_id, int device, i
 		if (w <= 16) {
 			/* direct build: every entry is a scalar multiplication d * 2^(w*i) * G (K2's window_mul) */
 			if (ensure_work(ctx, (uint32_t)entries)) return -1;
-			LaunchSmul<C>::table_points((uint32_t)entries, w, ctx->jac, 0);
+			LaunchVar<C>::table_points((uint32_t)entries, w, ctx->jac, 0);
 			LaunchMisc<C>::to_table(affine_grid(ctx, (uint32_t)entries), (uint32_t)entries, ctx->jac, ctx->prefix,
 						ctx->table, 0);
 			ctx->launches += 2;
@@ -163,11 +166,11 @@ extern "C" int eccb200_ctx_create(eccb200_ctx **out, int curve_id, int device, i
 			uint32_t *half = nullptr;
 			CUDA_OK(cudaMalloc(&half, (size_t)half_entries * 2 * C::N * sizeof(uint32_t)));
 			if (ensure_work(ctx, std::max(half_entries, per_win))) return -1;
-			LaunchSmul<C>::table_points(half_entries, h, ctx->jac, 0);
+			LaunchVar<C>::table_points(half_entries, h, ctx->jac, 0);
 			LaunchMisc<C>::to_table(affine_grid(ctx, half_entries), half_entries, ctx->jac, ctx->prefix, half, 0);
 			ctx->launches += 2;
 			for (int i = 0; i < ctx->nwin; i++) {
-				LaunchSmul<C>::table_merge(per_win, (uint64_t)i << w, w, nwin_half, half, ctx->jac, 0);
+				LaunchFixed<C>::table_merge(per_win, (uint64_t)i << w, w, nwin_half, half, ctx->jac, 0);
 				LaunchMisc<C>::to_table(affine_grid(ctx, per_win), per_win, ctx->jac, ctx->prefix,
 							ctx->table + ((size_t)i << w) * 2 * C::N, 0);
 				ctx->launches += 2;
@@ -208,8 +211,9 @@ extern "C" void eccb200_ctx_destroy(eccb200_ctx *ctx)
 		if (ctx->stage_prefix[s]) cudaFree(ctx->stage_prefix[s]);
 		if (ctx->stage_aff[s]) cudaFree(ctx->stage_aff[s]);
 	}
-	for (int i = 0; i < 3; i++)
-		if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+	if (ctx->ev_ready)
+		for (int c = 0; c < eccb200_ctx::kProfCalls; c++)
+			for (int i = 0; i < 3; i++) cudaEventDestroy(ctx->ev[c][i]);
 	if (ctx->table) cudaFree(ctx->table);
 	if (ctx->jac) cudaFree(ctx->jac);
 	if (ctx->prefix) cudaFree(ctx->prefix);
@@ -221,21 +225,34 @@ extern "C" int eccb200_profile_enable(eccb200_ctx *ctx, int on)
 {
 	if (!ctx) return fail("null ctx");
 	CUDA_OK(cudaSetDevice(ctx->device));
-	if (on && !ctx->ev[0])
-		for (int i = 0; i < 3; i++) CUDA_OK(cudaEventCreate(&ctx->ev[i]));
+	if (on && !ctx->ev_ready) {
+		for (int c = 0; c < eccb200_ctx::kProfCalls; c++)
+			for (int i = 0; i < 3; i++) CUDA_OK(cudaEventCreate(&ctx->ev[c][i]));
+		ctx->ev_ready = true;
+	}
 	ctx->profiling = on != 0;
-	ctx->ev_count = 0;
+	ctx->ev_calls = 0;
 	return 0;
 }
 
+/* Sums, per kernel position, the device time of every timed device-pointer call since the previous read. */
 extern "C" int eccb200_profile_read(eccb200_ctx *ctx, float *ms, int cap)
 {
 	if (!ctx || !ms) return fail("null argument");
-	if (!ctx->profiling || ctx->ev_count == 0) return 0;
-	CUDA_OK(cudaEventSynchronize(ctx->ev[ctx->ev_count]));
-	int k = 0;
-	for (; k < ctx->ev_count && k < cap; k++) CUDA_OK(cudaEventElapsedTime(&ms[k], ctx->ev[k], ctx->ev[k + 1]));
-	return k;
+	if (!ctx->profiling || ctx->ev_calls == 0) return 0;
+	int kmax = 0;
+	for (int k = 0; k < cap && k < 2; k++) ms[k] = 0.f;
+	for (int c = 0; c < ctx->ev_calls; c++) {
+		CUDA_OK(cudaEventSynchronize(ctx->ev[c][ctx->ev_kernels[c]]));
+		for (int k = 0; k < ctx->ev_kernels[c] && k < cap; k++) {
+			float t = 0.f;
+			CUDA_OK(cudaEventElapsedTime(&t, ctx->ev[c][k], ctx->ev[c][k + 1]));
+			ms[k] += t;
+		}
+		if (ctx->ev_kernels[c] > kmax) kmax = ctx->ev_kernels[c];
+	}
+	ctx->ev_calls = 0;
+	return kmax < cap ? kmax : cap;
 }
 
 extern "C" int eccb200_comb_window(const eccb200_ctx *ctx) { return ctx ? ctx->w : -1; }
@@ -249,17 +266,18 @@ static int smul_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_scalars, cons
 	if (n == 0) return 0;
 	return dispatch(ctx->curve_id, [&](auto c) {
 		typedef decltype(c) C;
-		const bool prof = ctx->profiling && jac == ctx->jac;
-		if (prof) cudaEventRecord(ctx->ev[0], st);
+		const bool prof = ctx->profiling && jac == ctx->jac && ctx->ev_calls < eccb200_ctx::kProfCalls;
+		cudaEvent_t *pe = prof ? ctx->ev[ctx->ev_calls] : nullptr;
+		if (prof) cudaEventRecord(pe[0], st);
 		if (d_points)
-			LaunchSmul<C>::var(n, d_scalars, d_points, jac, d_status, st);
+			LaunchVar<C>::var(n, d_scalars, d_points, jac, d_status, st);
 		else
-			LaunchSmul<C>::fixed(n, d_scalars, ctx->table, ctx->w, jac, d_status, st);
-		if (prof) cudaEventRecord(ctx->ev[1], st);
+			LaunchFixed<C>::fixed(n, d_scalars, ctx->table, ctx->w, jac, d_status, st);
+		if (prof) cudaEventRecord(pe[1], st);
 		LaunchMisc<C>::to_affine(affine_grid(ctx, n), n, jac, prefix, d_out, d_status, st);
 		if (prof) {
-			cudaEventRecord(ctx->ev[2], st);
-			ctx->ev_count = 2;
+			cudaEventRecord(pe[2], st);
+			ctx->ev_kernels[ctx->ev_calls++] = 2;
 		}
 		ctx->launches += 2;
 		CUDA_OK(cudaGetLastError());
@@ -283,12 +301,14 @@ static int verify_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_sigs, const
 	return dispatch(ctx->curve_id, [&](auto c) {
 		typedef decltype(c) C;
 		const bool prof = ctx->profiling && d_verdict != (int8_t *)ctx->d_out[0] &&
-				  d_verdict != (int8_t *)ctx->d_out[1] && d_verdict != (int8_t *)ctx->d_out[2];
-		if (prof) cudaEventRecord(ctx->ev[0], st);
+				  d_verdict != (int8_t *)ctx->d_out[1] && d_verdict != (int8_t *)ctx->d_out[2] &&
+				  ctx->ev_calls < eccb200_ctx::kProfCalls;
+		cudaEvent_t *pe = prof ? ctx->ev[ctx->ev_calls] : nullptr;
+		if (prof) cudaEventRecord(pe[0], st);
 		LaunchVerify<C>::verify(n, d_sigs, d_pubkeys, d_digests, hlen, ctx->table, ctx->w, d_verdict, st);
 		if (prof) {
-			cudaEventRecord(ctx->ev[1], st);
-			ctx->ev_count = 1;
+			cudaEventRecord(pe[1], st);
+			ctx->ev_kernels[ctx->ev_calls++] = 1;
 		}
 		ctx->launches += 1;
 		CUDA_OK(cudaGetLastError());
@@ -375,6 +395,34 @@ static int run_pipeline(eccb200_ctx *ctx, uint32_t n, std::vector<HostCol> &in, 
 	}
 	if (ensure_stages(ctx, (size_t)kChunk * in_item, (size_t)kChunk * out_item)) return -1;
 	uint32_t nchunks = (n + kChunk - 1) / kChunk;
+	bool all_pinned = true;
+	for (auto &c : in) all_pinned = all_pinned && c.pinned;
+	for (auto &c : out) all_pinned = all_pinned && c.pinned;
+	if (all_pinned) {
+		/* No host-side staging: enqueue every chunk without a single host synchronisation.  Stage buffers are
+		 * reused by chunk c + kStages on the SAME stream, so stream order alone keeps them safe. */
+		for (uint32_t c = 0; c < nchunks; c++) {
+			int s = (int)(c % kStages);
+			uint32_t lo = c * kChunk, cnt = std::min(kChunk, n - lo);
+			size_t off = 0;
+			for (auto &col : in) {
+				size_t bytes = (size_t)cnt * col.item;
+				CUDA_OK(cudaMemcpyAsync(ctx->d_in[s] + off, col.host + (size_t)lo * col.item, bytes,
+							cudaMemcpyHostToDevice, ctx->streams[s]));
+				off += bytes;
+			}
+			if (launch(s, cnt)) return -1;
+			off = 0;
+			for (auto &col : out) {
+				size_t bytes = (size_t)cnt * col.item;
+				CUDA_OK(cudaMemcpyAsync(col.host + (size_t)lo * col.item, ctx->d_out[s] + off, bytes,
+							cudaMemcpyDeviceToHost, ctx->streams[s]));
+				off += bytes;
+			}
+		}
+		for (int s = 0; s < kStages; s++) CUDA_OK(cudaStreamSynchronize(ctx->streams[s]));
+		return 0;
+	}
 	std::vector<uint32_t> pending_lo(kStages, 0), pending_cnt(kStages, 0);
 	for (uint32_t c = 0; c < nchunks + kStages; c++) {
 		int s = (int)(c % kStages);
@@ -461,7 +509,7 @@ static int sign_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_priv, const u
 	if (n == 0) return 0;
 	return dispatch(ctx->curve_id, [&](auto c) {
 		typedef decltype(c) C;
-		LaunchSmul<C>::fixed(n, d_nonce, ctx->table, ctx->w, jac, d_status, st);       /* k*G          */
+		LaunchFixed<C>::fixed(n, d_nonce, ctx->table, ctx->w, jac, d_status, st);       /* k*G          */
 		LaunchMisc<C>::to_affine(affine_grid(ctx, n), n, jac, prefix, aff, d_status, st); /* affine (x, y) */
 		LaunchMisc<C>::sign_finish(affine_grid(ctx, n), n, d_priv, d_nonce, d_dig, hlen, aff, prefix, d_sigs,
 					   d_status, st);                                        /* r, s          */
@@ -507,7 +555,7 @@ static int ecdh_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_priv, const u
 	if (n == 0) return 0;
 	return dispatch(ctx->curve_id, [&](auto c) {
 		typedef decltype(c) C;
-		LaunchSmul<C>::var(n, d_priv, d_peers, jac, d_status, st);
+		LaunchVar<C>::var(n, d_priv, d_peers, jac, d_status, st);
 		LaunchMisc<C>::to_x_only(affine_grid(ctx, n), n, jac, prefix, d_shared, d_status, st);
 		ctx->launches += 2;
 		CUDA_OK(cudaGetLastError());

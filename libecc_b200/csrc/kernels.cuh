@@ -639,14 +639,20 @@ namespace eccb200 {
 static const int kThreads = 128;
 static inline uint32_t grid_for(uint32_t n) { return (n + kThreads - 1) / kThreads; }
 
-template <class C> struct LaunchSmul {
+/* K1 group: compiled with the multiplier INLINED (ECC_INLINE_MUL): its loop body is one mixed addition and runs
+ * 5-9 % faster that way; K2 / K3 groups call the out-of-line multiplier, which keeps their much larger loop bodies
+ * inside the instruction cache (+18 % on k_smul_var).  Measured in round 1, see DESIGN.md §4. */
+template <class C> struct LaunchFixed {
 	static void fixed(uint32_t n, const uint8_t *scalars, const uint32_t *table, int w, uint32_t *jac,
 			  int8_t *status, cudaStream_t st);
+	static void table_merge(uint32_t count, uint64_t first_entry, int w, int nwin_half, const uint32_t *half_table,
+				uint32_t *jac, cudaStream_t st);
+};
+
+template <class C> struct LaunchVar {
 	static void var(uint32_t n, const uint8_t *scalars, const uint8_t *points, uint32_t *jac, int8_t *status,
 			cudaStream_t st);
 	static void table_points(uint32_t entries, int w, uint32_t *jac, cudaStream_t st);
-	static void table_merge(uint32_t count, uint64_t first_entry, int w, int nwin_half, const uint32_t *half_table,
-				uint32_t *jac, cudaStream_t st);
 };
 
 template <class C> struct LaunchMisc {
@@ -673,28 +679,31 @@ template <class C> struct LaunchVerify {
 		       cudaStream_t st);
 };
 
-#if defined(ECC_TU_SMUL)
+#if defined(ECC_TU_FIXED)
 template <class C>
-void LaunchSmul<C>::fixed(uint32_t n, const uint8_t *scalars, const uint32_t *table, int w, uint32_t *jac,
-			  int8_t *status, cudaStream_t st)
+void LaunchFixed<C>::fixed(uint32_t n, const uint8_t *scalars, const uint32_t *table, int w, uint32_t *jac,
+			   int8_t *status, cudaStream_t st)
 {
 	k_smul_fixed<C><<<grid_for(n), kThreads, 0, st>>>(n, scalars, table, w, jac, status);
 }
 template <class C>
-void LaunchSmul<C>::var(uint32_t n, const uint8_t *scalars, const uint8_t *points, uint32_t *jac, int8_t *status,
-			cudaStream_t st)
+void LaunchFixed<C>::table_merge(uint32_t count, uint64_t first_entry, int w, int nwin_half,
+				 const uint32_t *half_table, uint32_t *jac, cudaStream_t st)
+{
+	k_table_merge<C><<<grid_for(count), kThreads, 0, st>>>(count, first_entry, w, nwin_half, half_table, jac);
+}
+#endif
+
+#if defined(ECC_TU_VAR)
+template <class C>
+void LaunchVar<C>::var(uint32_t n, const uint8_t *scalars, const uint8_t *points, uint32_t *jac, int8_t *status,
+		       cudaStream_t st)
 {
 	k_smul_var<C><<<grid_for(n), kThreads, 0, st>>>(n, scalars, points, jac, status);
 }
-template <class C> void LaunchSmul<C>::table_points(uint32_t entries, int w, uint32_t *jac, cudaStream_t st)
+template <class C> void LaunchVar<C>::table_points(uint32_t entries, int w, uint32_t *jac, cudaStream_t st)
 {
 	k_table_points<C><<<grid_for(entries), kThreads, 0, st>>>(entries, w, jac);
-}
-template <class C>
-void LaunchSmul<C>::table_merge(uint32_t count, uint64_t first_entry, int w, int nwin_half,
-				const uint32_t *half_table, uint32_t *jac, cudaStream_t st)
-{
-	k_table_merge<C><<<grid_for(count), kThreads, 0, st>>>(count, first_entry, w, nwin_half, half_table, jac);
 }
 #endif
 

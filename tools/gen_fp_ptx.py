@@ -470,7 +470,9 @@ def fields():
 
 def main():
     out = ["/* GENERATED by tools/gen_fp_ptx.py — do not edit.  Inline-PTX field arithmetic (device only). */",
-           "#pragma once", "", "namespace eccb200 {", "",
+           "#pragma once", "",
+           "#if defined(ECC_INLINE_MUL)", "#define ECC_MUL_LINKAGE __forceinline__", "#else",
+           "#define ECC_MUL_LINKAGE __noinline__", "#endif", "", "namespace eccb200 {", "",
            "template <class F> struct FieldPtx;", ""]
     for tag, n, mod in fields():
         mul, sqr, add, sub = gen_mul(n, mod), gen_sqr(n, mod), gen_add(n, mod), gen_sub(n, mod)
@@ -481,12 +483,17 @@ def main():
         out.append(f"template <> struct FieldPtx<{tag}> {{")
         out.append(f"\tstatic constexpr int N = {n};")
         out.append(f"\ttypedef Fe<{n}> E;")
-        out.append("\tstatic __device__ __forceinline__ void mul(E &r, const E &a, const E &b)\n\t{")
+        out.append("\t/* Out-of-line, operands and result BY VALUE (they stay in registers; ptxas allocates across the call):")
+        out.append("\t * one copy of the ~200-instruction product per kernel instead of one per use keeps the hot loops of")
+        out.append("\t * the scalar-multiplication kernels inside the instruction cache (profiles/: no_instruction stalls). */")
+        out.append("\tstatic __device__ ECC_MUL_LINKAGE E mul_fn(E a, E b)\n\t{\n\t\tE r;")
         out.append(render_asm(mul, n))
-        out.append("\t}")
-        out.append("\tstatic __device__ __forceinline__ void sqr(E &r, const E &a)\n\t{")
+        out.append("\t\treturn r;\n\t}")
+        out.append("\tstatic __device__ ECC_MUL_LINKAGE E sqr_fn(E a)\n\t{\n\t\tE r;")
         out.append(render_asm(sqr, n, two_inputs=False))
-        out.append("\t}")
+        out.append("\t\treturn r;\n\t}")
+        out.append("\tstatic __device__ __forceinline__ void mul(E &r, const E &a, const E &b) { r = mul_fn(a, b); }")
+        out.append("\tstatic __device__ __forceinline__ void sqr(E &r, const E &a) { r = sqr_fn(a); }")
         out.append("\tstatic __device__ __forceinline__ void add(E &r, const E &a, const E &b)\n\t{")
         out.append(render_asm(add, n))
         out.append("\t}")
