@@ -119,14 +119,24 @@ __global__ void __launch_bounds__(128) k_smul_fixed(uint32_t n, const uint8_t *_
 
 /* ------------------------------------------------------------------------------------------ K2: variable base */
 
+/* Minimum resident CTAs per SM for K2 / K3 (register caps 80 / 96).  With the out-of-line multiplier the extra
+ * warps hide its fixed-latency dependency chains better than the few spills cost: round-1 sweep on a B200,
+ * (1,1) -> (4,3) -> (5,4) -> (6,5): k_smul_var 20.6 -> 21.05 -> 21.14 -> 21.18 M/s, k_ecdsa_verify<FRP256V1> 15.4 -> 16.6 -> 17.0 -> 17.3 M/s. */
 #ifndef ECC_MINB_VAR
-#define ECC_MINB_VAR 1
+#define ECC_MINB_VAR 6
 #endif
 #ifndef ECC_MINB_VERIFY
-#define ECC_MINB_VERIFY 1
+#define ECC_MINB_VERIFY 5
+#endif
+/* 12-word fields (P-384) need 1.5x the registers per element: keep their caps at 168 / 128 registers */
+#ifndef ECC_MINB_VAR_WIDE
+#define ECC_MINB_VAR_WIDE 3
+#endif
+#ifndef ECC_MINB_VERIFY_WIDE
+#define ECC_MINB_VERIFY_WIDE 4
 #endif
 template <class C>
-__global__ void __launch_bounds__(128, ECC_MINB_VAR) k_smul_var(uint32_t n, const uint8_t *__restrict__ scalars,
+__global__ void __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VAR : ECC_MINB_VAR_WIDE)) k_smul_var(uint32_t n, const uint8_t *__restrict__ scalars,
 						  const uint8_t *__restrict__ points, uint32_t *__restrict__ jac,
 						  int8_t *__restrict__ status)
 {
@@ -380,7 +390,7 @@ __global__ void __launch_bounds__(128) k_prj_load(uint32_t n, const uint8_t *__r
  * digests: hlen bytes each; e = leftmost min(8*hlen, bitlen(q)) bits (:760-775), reduced mod q (:777).
  */
 template <class C>
-__global__ void __launch_bounds__(128, ECC_MINB_VERIFY) k_ecdsa_verify(uint32_t n, const uint8_t *__restrict__ sigs,
+__global__ void __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VERIFY : ECC_MINB_VERIFY_WIDE)) k_ecdsa_verify(uint32_t n, const uint8_t *__restrict__ sigs,
 						      const uint8_t *__restrict__ pubkeys,
 						      const uint8_t *__restrict__ digests, uint32_t hlen,
 						      const uint32_t *__restrict__ table, int w,
