@@ -31,7 +31,7 @@ static int fail(const std::string &m)
 
 extern "C" const char *eccb200_last_error(void) { return g_err.c_str(); }
 
-static const int kStages = 4; /* pipeline depth of the host-pointer API */
+static const int kStages = 3; /* pipeline depth of the host-pointer API */
 
 struct eccb200_ctx {
 	int curve_id = 0;
@@ -41,8 +41,7 @@ struct eccb200_ctx {
 	int w = 0;           /* comb window */
 	int nwin = 0;
 	int sm_count = 0;
-	uint32_t chunk = 0; /* items per pipeline chunk: two full waves of K1 (2 * SMs * 4 CTAs * 128 threads), so a
-			     * chunk neither leaves a partial wave nor makes the pipeline coarse */
+	uint32_t chunk = 0; /* items per pipeline chunk: four full waves of K1 (4 * SMs * 4 CTAs * 128 threads) */
 	uint32_t *table = nullptr;
 	/* work buffers (grown on demand) */
 	uint32_t cap = 0;
@@ -145,7 +144,7 @@ extern "C" int eccb200_ctx_create(eccb200_ctx **out, int curve_id, int device, i
 	ctx->device = device;
 	ctx->w = w;
 	ctx->sm_count = prop.multiProcessorCount;
-	ctx->chunk = 2u * (uint32_t)prop.multiProcessorCount * 4u * 128u;
+	ctx->chunk = 4u * (uint32_t)prop.multiProcessorCount * 4u * 128u;
 	int rc = dispatch(curve_id, [&](auto c) {
 		typedef decltype(c) C;
 		ctx->N = C::N;
@@ -467,11 +466,32 @@ static int run_pipeline(eccb200_ctx *ctx, uint32_t n, std::vector<HostCol> &in, 
 	return 0;
 }
 
+/* Page-locked buffers are visible to the device through unified addressing: with ECCB200_ZEROCOPY=1 the kernels read
+ * their operands from, and write their results to, the caller's host memory directly, so the PCIe traffic overlaps
+ * the arithmetic warp by warp and no staging copy or copy-engine transfer is issued at all. */
+static bool zero_copy_enabled()
+{
+	static int v = -1;
+	if (v < 0) {
+		const char *e = getenv("ECCB200_ZEROCOPY");
+		v = (e && atoi(e) != 0) ? 1 : 0;
+	}
+	return v == 1;
+}
+
 extern "C" int eccb200_prj_pt_mul_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *scalars, const uint8_t *points,
 					uint8_t *out, int8_t *status)
 {
 	if (!ctx || (n && (!scalars || !out || !status))) return fail("null argument");
 	if (n == 0) return 0;
+	if (zero_copy_enabled() && is_pinned(scalars) && is_pinned(out) && is_pinned(status) &&
+	    (!points || is_pinned(points))) {
+		CUDA_OK(cudaSetDevice(ctx->device));
+		if (ensure_work(ctx, n)) return -1;
+		if (smul_dev(ctx, n, scalars, points, out, status, ctx->jac, ctx->prefix, ctx->streams[0])) return -1;
+		CUDA_OK(cudaStreamSynchronize(ctx->streams[0]));
+		return 0;
+	}
 	const size_t sl = ctx->qlen, pl = 2 * (size_t)ctx->plen;
 	std::vector<HostCol> in = { { (uint8_t *)scalars, sl, false } };
 	if (points) in.push_back({ (uint8_t *)points, pl, false });
