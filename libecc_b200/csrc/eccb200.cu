@@ -103,7 +103,12 @@ extern "C" const char *eccb200_curve_name(int curve_id)
 static uint32_t affine_grid(const eccb200_ctx *ctx, uint32_t n)
 {
 	uint32_t want = grid_for(n);
-	uint32_t cap = (uint32_t)ctx->sm_count * 4u; /* 4 CTAs of 128 threads per SM */
+	static int per_sm = 0; /* CTAs of 128 threads per SM; ECCB200_AFFINE_CTAS overrides (tuning knob) */
+	if (!per_sm) {
+		const char *e = getenv("ECCB200_AFFINE_CTAS");
+		per_sm = (e && atoi(e) > 0) ? atoi(e) : 4;
+	}
+	uint32_t cap = (uint32_t)ctx->sm_count * (uint32_t)per_sm;
 	return std::max(1u, std::min(want, cap));
 }
 

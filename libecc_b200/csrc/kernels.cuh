@@ -239,9 +239,10 @@ __global__ void __launch_bounds__(128) k_table_merge(uint32_t count, uint64_t fi
 /* ------------------------------------------------------------------------------------------ K4: normalisation */
 
 /*
- * Jacobian -> affine for a whole batch with ONE field inversion per thread (Montgomery's simultaneous inversion):
- * thread t owns items t, t+T, t+2T, ... (T = total threads, so every pass over the batch is coalesced), keeps the
- * running product of their Z in registers, stores the prefix products, inverts once, and walks back.
+ * Jacobian -> affine for a whole batch with ONE field inversion per CTA (Montgomery's simultaneous inversion, two
+ * levels): thread t owns items t, t+T, t+2T, ... (T = total threads, so every pass over the batch is coalesced), keeps
+ * the running product of their Z in registers and stores the prefix products; the CTA's 128 thread products are then
+ * combined through shared memory, one warp inverts, and each thread walks back over its items.
  * Replaces n calls of prj_pt_unique (curves/prj_pt.c:241) -> fp_inv (fp/fp_mul.c:51, ~1.5*bitlen(p) products each).
  * MODE 0: Jacobian in, writes big-endian affine bytes + status (0 -> stays 0, infinity -> 1, -1 untouched).
  * MODE 1: Jacobian in, writes Montgomery-form words (comb table entry format), infinity as all-zero.
@@ -260,24 +261,93 @@ __global__ void __launch_bounds__(128) k_to_affine(uint32_t n, const uint32_t *_
 	constexpr bool TABLE = (MODE == 1);
 	const uint32_t T = gridDim.x * blockDim.x;
 	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-	if (tid >= n) return;
+	const bool active = tid < n; /* idle threads still take part in the block-wide inversion below */
 	Fe<N> acc;
 	F::set_one(acc);
 	uint32_t last = tid;
-	for (uint32_t e = tid; e < n; e += T) {
-		Fe<N> z;
-		load_words<N>(z, jac + (size_t)e * (3 * N) + 2 * N);
-		store_words<N>(prefix + (size_t)e * N, acc);
-		if (!F::is_zero(z)) {
-			Fe<N> t;
-			F::mul(t, acc, z);
-			acc = t;
+	if (active) {
+		for (uint32_t e = tid; e < n; e += T) {
+			Fe<N> z;
+			load_words<N>(z, jac + (size_t)e * (3 * N) + 2 * N);
+			store_words<N>(prefix + (size_t)e * N, acc);
+			if (!F::is_zero(z)) {
+				Fe<N> t;
+				F::mul(t, acc, z);
+				acc = t;
+			}
+			last = e;
+			if (n - e <= T) break; /* avoid uint32 overflow of e += T */
 		}
-		last = e;
-		if (n - e <= T) break; /* avoid uint32 overflow of e += T */
 	}
+	/*
+	 * Block-wide simultaneous inversion: the 128 per-thread products are combined with two shared-memory scans
+	 * (inclusive prefix P, inclusive suffix S, 7 doubling steps each), ONE warp inverts the block product, and every
+	 * thread recovers the inverse of its own product as inv_total * P[t-1] * S[t+1].  Only one warp per CTA issues
+	 * the ~330-product Fermat chain instead of all four.
+	 */
 	Fe<N> inv;
-	F::inv(inv, acc);
+	{
+		__shared__ uint32_t sP[2][128 * N];   /* double-buffered prefix scan */
+		__shared__ uint32_t sS[2][128 * N];   /* double-buffered suffix scan */
+		__shared__ uint32_t sInv[N];
+		const int t = threadIdx.x;
+		auto st_sh = [&](uint32_t *base, int idx, const Fe<N> &v) {
+#pragma unroll
+			for (int j = 0; j < N; j++) base[idx * N + j] = v.w[j];
+		};
+		auto ld_sh = [&](Fe<N> &v, const uint32_t *base, int idx) {
+#pragma unroll
+			for (int j = 0; j < N; j++) v.w[j] = base[idx * N + j];
+		};
+		Fe<N> pv = acc, sv = acc;
+		st_sh(sP[0], t, pv);
+		st_sh(sS[0], t, sv);
+		__syncthreads();
+		int cur = 0;
+#pragma unroll 1
+		for (int d = 1; d < 128; d <<= 1) {
+			Fe<N> o, r;
+			if (t >= d) {
+				ld_sh(o, sP[cur], t - d);
+				F::mul(r, pv, o);
+				pv = r;
+			}
+			if (t + d < 128) {
+				ld_sh(o, sS[cur], t + d);
+				F::mul(r, sv, o);
+				sv = r;
+			}
+			st_sh(sP[cur ^ 1], t, pv);
+			st_sh(sS[cur ^ 1], t, sv);
+			__syncthreads();
+			cur ^= 1;
+		}
+		/* pv = prod_{u <= t} acc_u, sv = prod_{u >= t} acc_u; block product = P[127] */
+		if (t < 32) {
+			Fe<N> tot, ti;
+			ld_sh(tot, sP[cur], 127);
+			F::inv(ti, tot);
+			if (t == 0) {
+#pragma unroll
+				for (int j = 0; j < N; j++) sInv[j] = ti.w[j];
+			}
+		}
+		__syncthreads();
+#pragma unroll
+		for (int j = 0; j < N; j++) inv.w[j] = sInv[j];
+		Fe<N> o, r;
+		if (t > 0) {
+			ld_sh(o, sP[cur], t - 1);
+			F::mul(r, inv, o);
+			inv = r;
+		}
+		if (t < 127) {
+			ld_sh(o, sS[cur], t + 1);
+			F::mul(r, inv, o);
+			inv = r;
+		}
+	}
+	if (!active) return;
 	for (uint32_t e = last;; e -= T) {
 		Fe<N> z, pre, X, Y;
 		const uint32_t *b = jac + (size_t)e * (3 * N);
