@@ -437,18 +437,14 @@ ECC_HD void ecdsa_uv(Fe<C::N> &u, Fe<C::N> &v, const Fe<C::N> &r, const Fe<C::N>
  *     candidates c in {r, r+q} that are < p (:803-810);
  *   - uG through the comb table (K1), vY through the signed window (K2) instead of two ladders (:788,793).
  */
+/* Steps 7-10 of __ecdsa_verify_finalize (sig/ecdsa_common.c:796-810) given u and v: W' = uG + vY, reject infinity,
+ * accept iff x(W') mod q == r.  Returns 0 valid, 2 infinity, 3 mismatch. */
 template <class C>
-ECC_HD int ecdsa_verify_core(const Fe<C::N> &r, const Fe<C::N> &s, const Fe<C::N> &e, const Aff<C> &Y,
+ECC_HD int ecdsa_verify_tail(const Fe<C::N> &r, const Fe<C::N> &u, const Fe<C::N> &v, const Aff<C> &Y,
 			     const uint32_t *__restrict__ table, int w)
 {
 	typedef Field<typename C::Fp> F;
-	typedef Field<typename C::Fq> Fq;
 	constexpr int N = C::N;
-	if (Fq::is_zero(r) || Fq::is_zero(s) || Fq::geq_mod(r) || Fq::geq_mod(s)) return 1;
-
-	Fe<N> u, v;
-	ecdsa_uv<C>(u, v, r, s, e);
-
 	Jac<C> uG, W;
 	comb_mul<C>(uG, u, table, w);
 	window_mul<C>(W, v, Y, &uG); /* W' = vY + uG (:796) */
@@ -478,6 +474,25 @@ ECC_HD int ecdsa_verify_core(const Fe<C::N> &r, const Fe<C::N> &s, const Fe<C::N
 		}
 	}
 	return match ? 0 : 3;
+}
+
+/* r, s in [1, q-1]?  (__ecdsa_verify_init, sig/ecdsa_common.c:653-658) */
+template <class C> ECC_HD bool ecdsa_rs_in_range(const Fe<C::N> &r, const Fe<C::N> &s)
+{
+	typedef Field<typename C::Fq> Fq;
+	return !(Fq::is_zero(r) || Fq::is_zero(s) || Fq::geq_mod(r) || Fq::geq_mod(s));
+}
+
+/* Whole verification of one signature with a per-item inversion of s (host build of the tests and reference for the
+ * kernel, which replaces the inversion by a CTA-wide simultaneous one). */
+template <class C>
+ECC_HD int ecdsa_verify_core(const Fe<C::N> &r, const Fe<C::N> &s, const Fe<C::N> &e, const Aff<C> &Y,
+			     const uint32_t *__restrict__ table, int w)
+{
+	if (!ecdsa_rs_in_range<C>(r, s)) return 1;
+	Fe<C::N> u, v;
+	ecdsa_uv<C>(u, v, r, s, e);
+	return ecdsa_verify_tail<C>(r, u, v, Y, table, w);
 }
 
 } // namespace eccb200

@@ -99,6 +99,80 @@ template <class C> __device__ __forceinline__ bool load_affine_checked(Aff<C> &P
 	return ok;
 }
 
+/* ------------------------------------------------------------------------------------------ CTA-wide inversion */
+
+/*
+ * Simultaneous inversion across the 128 threads of a CTA: every thread passes a non-zero Montgomery-form element
+ * `acc` and gets acc^-1 back.  Two shared-memory scans (inclusive prefix P and suffix S, 7 doubling steps), ONE warp
+ * runs the ~330-product Fermat chain on the CTA product, and thread t computes inv_total * P[t-1] * S[t+1].
+ * Must be called by all 128 threads of the CTA (it synchronises).  Cost per thread: 16 products + 1/4 inversion.
+ */
+template <class FT> __device__ __forceinline__ void cta_inverse_128(Fe<FT::N> &inv, const Fe<FT::N> &acc)
+{
+	typedef Field<FT> F;
+	constexpr int N = FT::N;
+	__shared__ uint32_t sP[2][128 * N]; /* double-buffered prefix scan */
+	__shared__ uint32_t sS[2][128 * N]; /* double-buffered suffix scan */
+	__shared__ uint32_t sInv[N];
+	const int t = threadIdx.x;
+	auto st_sh = [&](uint32_t *base, int idx, const Fe<N> &v) {
+#pragma unroll
+		for (int j = 0; j < N; j++) base[idx * N + j] = v.w[j];
+	};
+	auto ld_sh = [&](Fe<N> &v, const uint32_t *base, int idx) {
+#pragma unroll
+		for (int j = 0; j < N; j++) v.w[j] = base[idx * N + j];
+	};
+	Fe<N> pv = acc, sv = acc;
+	st_sh(sP[0], t, pv);
+	st_sh(sS[0], t, sv);
+	__syncthreads();
+	int cur = 0;
+#pragma unroll 1
+	for (int d = 1; d < 128; d <<= 1) {
+		Fe<N> o, r;
+		if (t >= d) {
+			ld_sh(o, sP[cur], t - d);
+			F::mul(r, pv, o);
+			pv = r;
+		}
+		if (t + d < 128) {
+			ld_sh(o, sS[cur], t + d);
+			F::mul(r, sv, o);
+			sv = r;
+		}
+		st_sh(sP[cur ^ 1], t, pv);
+		st_sh(sS[cur ^ 1], t, sv);
+		__syncthreads();
+		cur ^= 1;
+	}
+	/* pv = prod_{u <= t} acc_u, sv = prod_{u >= t} acc_u; CTA product = P[127] */
+	if (t < 32) {
+		Fe<N> tot, ti;
+		ld_sh(tot, sP[cur], 127);
+		F::inv(ti, tot);
+		if (t == 0) {
+#pragma unroll
+			for (int j = 0; j < N; j++) sInv[j] = ti.w[j];
+		}
+	}
+	__syncthreads();
+#pragma unroll
+	for (int j = 0; j < N; j++) inv.w[j] = sInv[j];
+	Fe<N> o, r;
+	if (t > 0) {
+		ld_sh(o, sP[cur], t - 1);
+		F::mul(r, inv, o);
+		inv = r;
+	}
+	if (t < 127) {
+		ld_sh(o, sS[cur], t + 1);
+		F::mul(r, inv, o);
+		inv = r;
+	}
+	__syncthreads(); /* the buffers may be reused by a second call */
+}
+
 /* ------------------------------------------------------------------------------------------ K1: fixed base */
 
 template <class C>
@@ -279,74 +353,8 @@ __global__ void __launch_bounds__(128) k_to_affine(uint32_t n, const uint32_t *_
 			if (n - e <= T) break; /* avoid uint32 overflow of e += T */
 		}
 	}
-	/*
-	 * Block-wide simultaneous inversion: the 128 per-thread products are combined with two shared-memory scans
-	 * (inclusive prefix P, inclusive suffix S, 7 doubling steps each), ONE warp inverts the block product, and every
-	 * thread recovers the inverse of its own product as inv_total * P[t-1] * S[t+1].  Only one warp per CTA issues
-	 * the ~330-product Fermat chain instead of all four.
-	 */
 	Fe<N> inv;
-	{
-		__shared__ uint32_t sP[2][128 * N];   /* double-buffered prefix scan */
-		__shared__ uint32_t sS[2][128 * N];   /* double-buffered suffix scan */
-		__shared__ uint32_t sInv[N];
-		const int t = threadIdx.x;
-		auto st_sh = [&](uint32_t *base, int idx, const Fe<N> &v) {
-#pragma unroll
-			for (int j = 0; j < N; j++) base[idx * N + j] = v.w[j];
-		};
-		auto ld_sh = [&](Fe<N> &v, const uint32_t *base, int idx) {
-#pragma unroll
-			for (int j = 0; j < N; j++) v.w[j] = base[idx * N + j];
-		};
-		Fe<N> pv = acc, sv = acc;
-		st_sh(sP[0], t, pv);
-		st_sh(sS[0], t, sv);
-		__syncthreads();
-		int cur = 0;
-#pragma unroll 1
-		for (int d = 1; d < 128; d <<= 1) {
-			Fe<N> o, r;
-			if (t >= d) {
-				ld_sh(o, sP[cur], t - d);
-				F::mul(r, pv, o);
-				pv = r;
-			}
-			if (t + d < 128) {
-				ld_sh(o, sS[cur], t + d);
-				F::mul(r, sv, o);
-				sv = r;
-			}
-			st_sh(sP[cur ^ 1], t, pv);
-			st_sh(sS[cur ^ 1], t, sv);
-			__syncthreads();
-			cur ^= 1;
-		}
-		/* pv = prod_{u <= t} acc_u, sv = prod_{u >= t} acc_u; block product = P[127] */
-		if (t < 32) {
-			Fe<N> tot, ti;
-			ld_sh(tot, sP[cur], 127);
-			F::inv(ti, tot);
-			if (t == 0) {
-#pragma unroll
-				for (int j = 0; j < N; j++) sInv[j] = ti.w[j];
-			}
-		}
-		__syncthreads();
-#pragma unroll
-		for (int j = 0; j < N; j++) inv.w[j] = sInv[j];
-		Fe<N> o, r;
-		if (t > 0) {
-			ld_sh(o, sP[cur], t - 1);
-			F::mul(r, inv, o);
-			inv = r;
-		}
-		if (t < 127) {
-			ld_sh(o, sS[cur], t + 1);
-			F::mul(r, inv, o);
-			inv = r;
-		}
-	}
+	cta_inverse_128<typename C::Fp>(inv, acc); /* one Fermat chain per CTA instead of one per thread */
 	if (!active) return;
 	for (uint32_t e = last;; e -= T) {
 		Fe<N> z, pre, X, Y;
@@ -466,17 +474,35 @@ __global__ void __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VERIFY : ECC_MINB_V
 						      const uint32_t *__restrict__ table, int w,
 						      int8_t *__restrict__ verdict)
 {
+	typedef Field<typename C::Fq> Fq;
 	constexpr int N = C::N;
-	uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= n) return;
+	const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool active = idx < n;
+	const uint32_t i0 = active ? idx : 0; /* idle threads of the last CTA still join the CTA-wide inversion */
 
 	Fe<N> r, s, e;
-	load_be16<N>(r, sigs + (size_t)idx * (8 * N));
-	load_be16<N>(s, sigs + (size_t)idx * (8 * N) + 4 * N);
+	load_be16<N>(r, sigs + (size_t)i0 * (8 * N));
+	load_be16<N>(s, sigs + (size_t)i0 * (8 * N) + 4 * N);
+	const bool rs_ok = ecdsa_rs_in_range<C>(r, s);
+	/* s^-1 mod q for the whole CTA at once (sig/ecdsa_common.c:781 does one nn_modinv per signature) */
+	Fe<N> sm, wm;
+	Fq::set_one(sm);
+	if (rs_ok) Fq::to_mont(sm, s);
+	cta_inverse_128<typename C::Fq>(wm, sm);
+	if (!active) return;
 	Aff<C> Y;
 	bool key_ok = load_affine_checked<C>(Y, pubkeys + (size_t)idx * (8 * N));
 	digest_to_scalar<C>(e, digests + (size_t)idx * hlen, hlen);
-	int code = key_ok ? ecdsa_verify_core<C>(r, s, e, Y, table, w) : 4;
+	int code = 4;
+	if (key_ok) {
+		code = 1;
+		if (rs_ok) {
+			Fe<N> u, v;
+			Fq::mul(u, e, wm); /* u = e * s^-1 mod q  (:786) */
+			Fq::mul(v, r, wm); /* v = r * s^-1 mod q  (:791) */
+			code = ecdsa_verify_tail<C>(r, u, v, Y, table, w);
+		}
+	}
 #if defined(ECC_VERDICT_DEBUG)
 	verdict[idx] = (int8_t)(-code);
 #else
@@ -489,7 +515,7 @@ __global__ void __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VERIFY : ECC_MINB_V
 /*
  * Second half of a batched ECDSA signature (__ecdsa_sign_finalize steps 6-11, sig/ecdsa_common.c:479-560), after K1
  * computed k*G and K4 normalised it:  r = x(kG) mod q,  s = k^-1 (e + r*d) mod q.
- * k^-1 mod q uses the same simultaneous inversion as K4 (one Fermat inversion mod q per thread; the reference does
+ * k^-1 mod q uses the same two-level simultaneous inversion as K4 (one Fermat chain mod q per CTA; the reference does
  * one nn_modinv_fermat per signature, :537).  status: 0 ok; 2 = the reference's "restart with a new nonce" cases
  * (r == 0 :487, e == r*d :513, s == 0 :545); -1 = d or k outside [1, q-1].
  */
@@ -505,25 +531,28 @@ __global__ void __launch_bounds__(128) k_ecdsa_sign_finish(uint32_t n, const uin
 	constexpr int N = C::N;
 	const uint32_t T = gridDim.x * blockDim.x;
 	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-	if (tid >= n) return;
+	const bool active = tid < n;
 	Fe<N> acc;
 	Fq::set_one(acc);
 	uint32_t last = tid;
-	for (uint32_t e = tid; e < n; e += T) {
-		Fe<N> kk, km;
-		load_be16<N>(kk, nonces + (size_t)e * (4 * N));
-		store_words<N>(prefix + (size_t)e * N, acc);
-		if (!Fq::is_zero(kk) && !Fq::geq_mod(kk)) {
-			Fe<N> t;
-			Fq::to_mont(km, kk);
-			Fq::mul(t, acc, km);
-			acc = t;
+	if (active) {
+		for (uint32_t e = tid; e < n; e += T) {
+			Fe<N> kk, km;
+			load_be16<N>(kk, nonces + (size_t)e * (4 * N));
+			store_words<N>(prefix + (size_t)e * N, acc);
+			if (!Fq::is_zero(kk) && !Fq::geq_mod(kk)) {
+				Fe<N> t;
+				Fq::to_mont(km, kk);
+				Fq::mul(t, acc, km);
+				acc = t;
+			}
+			last = e;
+			if (n - e <= T) break;
 		}
-		last = e;
-		if (n - e <= T) break;
 	}
 	Fe<N> inv;
-	Fq::inv(inv, acc);
+	cta_inverse_128<typename C::Fq>(inv, acc);
+	if (!active) return;
 	for (uint32_t e = last;; e -= T) {
 		Fe<N> kk, d, x, r, ev, s, zero;
 		Fq::set_zero(zero);

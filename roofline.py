@@ -20,7 +20,8 @@ def work_per_item(workload: str, comb_window: int):
     nib = QBITS[curve] // 4
     m_fixed = 11 * (nwin - 1)                                   # mixed add 8M+3S per window; first window is a copy
     m_var = 7 * 11 + 8 + nib * 4 * 8 + nib * (15.0 / 16) * 16   # table (7 madd, one of them a dbl) + 4 dbl/digit + adds
-    fermat_q = (QBITS[curve] // 4) * 5 + 14                     # 4 sqr + 1 mul per nibble + table
+    fermat = (QBITS[curve] // 4) * 5 + 14                       # 4 sqr + 1 mul per nibble + table
+    fermat_q = 16 + fermat / 4.0                                # CTA-wide inversion: 2 scans + 1 chain per 4 warps
     if kind == "fixed":
         m, kernel = m_fixed, "k_smul_fixed"
         m_ref = M_REF[curve]
