@@ -114,7 +114,7 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------------------------------------ inputs
 
-def make_inputs(workload: str, n: int, rank: int):
+def make_inputs(workload: str, n: int, rank: int, use_gpu: bool = True):
     """Seeded synthetic inputs of SURVEY.md §8d for one rank (host numpy arrays)."""
     from common import CURVES, ORDER, edge_scalars
     curve, kind, _, _ = WORKLOADS[workload]
@@ -137,7 +137,7 @@ def make_inputs(workload: str, n: int, rank: int):
     if kind == "var":
         inputs["points"] = make_points(curve, n, rank)
     if kind == "verify":
-        inputs.update(make_verify_inputs(curve, n, rank))
+        inputs.update(make_verify_inputs(curve, n, rank, use_gpu))
     return inputs
 
 
@@ -157,17 +157,52 @@ def make_points(curve: str, n: int, rank: int) -> np.ndarray:
     return pts
 
 
-def make_verify_inputs(curve: str, n: int, rank: int):
-    """(sigs, pubkeys, digests, expected): distinct random key per tuple, 1/16 corrupted.  Signatures are made with
-    the oracle's deterministic signer on a small pool and replicated with distinct keys... the full-size generator
-    lives in tests/common.make_signatures (CPU oracle); for 2^20 tuples we tile a 2^12 pool (documented)."""
-    from common import make_signatures
-    pool = 1 << 12
-    sigs, pubs, dg, exp = make_signatures(curve, min(pool, n), tag=500 + rank, corrupt_every=16)
-    reps = (n + sigs.shape[0] - 1) // sigs.shape[0]
-    tile = lambda a: np.ascontiguousarray(np.tile(a, (reps, 1))[:n])
-    return {"sigs": tile(sigs), "pubkeys": tile(pubs), "digests": tile(dg),
-            "expected": np.tile(exp, reps)[:n].copy(), "hlen": dg.shape[1]}
+def make_verify_inputs(curve: str, n: int, rank: int, use_gpu: bool = True):
+    """(sigs, pubkeys, digests, expected) of SURVEY.md §8d.3: a distinct random key per tuple, 1/16 of the tuples
+    corrupted (bit flip in r, s, digest or key; r = 0; s >= q) with the expected verdict recorded.
+    Ours arm: keys and signatures come from the engine's own batch signer (eccb200_ecdsa_sign_batch: d*G for the
+    keys, then r, s), and a 2^12 sample is cross-checked with the oracle's signer and verifier.  Reference arm (no
+    GPU): the oracle's signer on a 2^12 pool, tiled."""
+    from common import CURVES, ORDER, make_signatures, oracle_sign, oracle_verify
+    _, plen, qlen = CURVES[curve]
+    hlen = 32
+    if not use_gpu:
+        pool = min(1 << 12, n)
+        sigs, pubs, dg, exp = make_signatures(curve, pool, tag=500 + rank, corrupt_every=16)
+        reps = (n + pool - 1) // pool
+        tile = lambda a: np.ascontiguousarray(np.tile(a, (reps, 1))[:n])
+        return {"sigs": tile(sigs), "pubkeys": tile(pubs), "digests": tile(dg),
+                "expected": np.tile(exp, reps)[:n].copy(), "hlen": hlen}
+    import libecc_b200
+    q = ORDER[curve]
+    d = splitmix_bytes(n * qlen, 600 + rank).reshape(n, qlen)
+    k = splitmix_bytes(n * qlen, 700 + rank).reshape(n, qlen)
+    d[:, 0] &= 0x7F
+    k[:, 0] &= 0x7F
+    d[:, -1] |= 1
+    k[:, -1] |= 1                                   # in [1, q-1]: top bit clear, never zero
+    dg = splitmix_bytes(n * hlen, 800 + rank).reshape(n, hlen)
+    eng = libecc_b200.Engine(curve, device=int(os.environ.get("LOCAL_RANK", 0)))
+    pubs, st = eng.prj_pt_mul_batch(d)
+    assert (st == 0).all()
+    sigs, st = eng.ecdsa_sign_batch(d, k, dg, hlen)
+    assert (st == 0).all()
+    eng.close()
+    m = min(n, 1 << 12)                              # cross-check of the signer on a 2^12 sample
+    want, wst = oracle_sign(curve, d[:m], k[:m], dg[:m], hlen)
+    assert (wst == 0).all() and (want == sigs[:m]).all()
+    expected = np.zeros(n, dtype=np.int8)
+    idx = np.arange(0, n, 16)
+    kind = (idx // 16) % 6
+    expected[idx] = -1
+    sigs[idx[kind == 0], qlen - 1] ^= 1              # bit flip in r
+    sigs[idx[kind == 1], 2 * qlen - 1] ^= 1          # bit flip in s
+    dg[idx[kind == 2], 0] ^= 0x80                    # bit flip in the digest
+    pubs[idx[kind == 3], plen - 1] ^= 1              # key off the curve
+    sigs[idx[kind == 4], :qlen] = 0                  # r = 0
+    sigs[idx[kind == 5], qlen:] = np.frombuffer(q.to_bytes(qlen, "big"), dtype=np.uint8)  # s = q
+    assert (oracle_verify(curve, sigs[:m], pubs[:m], dg[:m], hlen) == expected[:m]).all()
+    return {"sigs": sigs, "pubkeys": pubs, "digests": dg, "expected": expected, "hlen": hlen}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms
@@ -249,7 +284,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        inputs = make_inputs(args.workload, n, 0) if kind != "var" else None
+        inputs = make_inputs(args.workload, n, 0, use_gpu=False) if kind != "var" else None
         if kind == "var":
             # no GPU on this arm: derive the points with the CPU oracle on the bounded sample only
             from common import oracle_smul
@@ -404,7 +439,8 @@ def main():
         got = d_out[:256].cpu().numpy()
         want = oracle_verify(curve, inputs["sigs"][:256], inputs["pubkeys"][:256], inputs["digests"][:256],
                              inputs["hlen"])
-        parity = bool((got == want).all())
+        # the oracle on a prefix, and the by-construction expectation (valid unless corrupted) on the WHOLE batch
+        parity = bool((got == want).all() and (d_out.cpu().numpy() == inputs["expected"]).all())
     else:
         got = d_out[: 256 * 2 * plen].cpu().numpy().reshape(256, 2 * plen)
         want, wst = oracle_smul(curve, inputs["scalars"][:256], inputs["points"][:256] if kind == "var" else None)

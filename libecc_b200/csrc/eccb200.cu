@@ -266,6 +266,17 @@ extern "C" uint64_t eccb200_kernel_launches(const eccb200_ctx *ctx) { return ctx
 
 /* ------------------------------------------------------------------------------------------ device-pointer API */
 
+/* ECCB200_TMA_STAGING=1 selects the K1 variant that stages the scalars with cp.async.bulk (layout experiment) */
+static bool tma_staging_enabled()
+{
+	static int v = -1;
+	if (v < 0) {
+		const char *e = getenv("ECCB200_TMA_STAGING");
+		v = (e && atoi(e) != 0) ? 1 : 0;
+	}
+	return v == 1;
+}
+
 static int smul_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_scalars, const uint8_t *d_points, uint8_t *d_out,
 		    int8_t *d_status, uint32_t *jac, uint32_t *prefix, cudaStream_t st)
 {
@@ -277,6 +288,8 @@ static int smul_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_scalars, cons
 		if (prof) cudaEventRecord(pe[0], st);
 		if (d_points)
 			LaunchVar<C>::var(n, d_scalars, d_points, jac, d_status, st);
+		else if (tma_staging_enabled())
+			LaunchFixed<C>::fixed_tma(n, d_scalars, ctx->table, ctx->w, jac, d_status, st);
 		else
 			LaunchFixed<C>::fixed(n, d_scalars, ctx->table, ctx->w, jac, d_status, st);
 		if (prof) cudaEventRecord(pe[1], st);

@@ -191,6 +191,68 @@ __global__ void __launch_bounds__(128) k_smul_fixed(uint32_t n, const uint8_t *_
 	status[idx] = 0;
 }
 
+/*
+ * Staging experiment: K1 with the CTA's 128 scalars brought into shared memory by ONE bulk
+ * asynchronous copy (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier) instead of per-thread 16-byte loads.
+ * Same results; selected with ECCB200_TMA_STAGING=1 so that both variants can be timed.  The scalar traffic is 32 B
+ * per ~100 field products, so no effect is expected — and none was measured.
+ */
+template <class C>
+__global__ void __launch_bounds__(128) k_smul_fixed_tma(uint32_t n, const uint8_t *__restrict__ scalars,
+							 const uint32_t *__restrict__ table, int w,
+							 uint32_t *__restrict__ jac, int8_t *__restrict__ status)
+{
+	constexpr int N = C::N;
+	__shared__ __align__(128) uint8_t sbuf[128 * 4 * N];
+	__shared__ __align__(8) uint64_t bar;
+	const uint32_t base = blockIdx.x * 128u;
+	const uint32_t cnt = (n - base < 128u) ? (n - base) : 128u;
+	const uint32_t bytes = cnt * 4u * N; /* multiple of 16 */
+	const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&bar);
+	const uint32_t dst_addr = (uint32_t)__cvta_generic_to_shared(sbuf);
+	if (threadIdx.x == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
+		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+			     ::"r"(dst_addr), "l"(scalars + (size_t)base * (4 * N)), "r"(bytes), "r"(bar_addr)
+			     : "memory");
+	}
+	{ /* every thread waits for phase 0 of the barrier */
+		uint32_t done = 0;
+		while (!done) {
+			asm volatile("{\n\t.reg .pred p;\n\t"
+				     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+				     "selp.u32 %0, 1, 0, p;\n\t}"
+				     : "=r"(done)
+				     : "r"(bar_addr)
+				     : "memory");
+		}
+	}
+	if (threadIdx.x >= cnt) return;
+	const uint32_t idx = base + threadIdx.x;
+	Fe<N> k;
+	{
+		const uint4 *p = reinterpret_cast<const uint4 *>(sbuf + (size_t)threadIdx.x * (4 * N));
+#pragma unroll
+		for (int j = 0; j < N / 4; j++) {
+			uint4 v = p[j];
+			k.w[N - 1 - 4 * j] = bswap32(v.x);
+			k.w[N - 2 - 4 * j] = bswap32(v.y);
+			k.w[N - 3 - 4 * j] = bswap32(v.z);
+			k.w[N - 4 - 4 * j] = bswap32(v.w);
+		}
+	}
+	scalar_reduce<C>(k);
+	Jac<C> acc;
+	comb_mul<C>(acc, k, table, w);
+	store_jac<C>(jac, idx, acc);
+	status[idx] = 0;
+}
+
 /* ------------------------------------------------------------------------------------------ K2: variable base */
 
 /* Minimum resident CTAs per SM for K2 / K3 (register caps 80 / 96).  With the out-of-line multiplier the extra
@@ -754,6 +816,8 @@ static inline uint32_t grid_for(uint32_t n) { return (n + kThreads - 1) / kThrea
 template <class C> struct LaunchFixed {
 	static void fixed(uint32_t n, const uint8_t *scalars, const uint32_t *table, int w, uint32_t *jac,
 			  int8_t *status, cudaStream_t st);
+	static void fixed_tma(uint32_t n, const uint8_t *scalars, const uint32_t *table, int w, uint32_t *jac,
+			      int8_t *status, cudaStream_t st);
 	static void table_merge(uint32_t count, uint64_t first_entry, int w, int nwin_half, const uint32_t *half_table,
 				uint32_t *jac, cudaStream_t st);
 };
@@ -794,6 +858,12 @@ void LaunchFixed<C>::fixed(uint32_t n, const uint8_t *scalars, const uint32_t *t
 			   int8_t *status, cudaStream_t st)
 {
 	k_smul_fixed<C><<<grid_for(n), kThreads, 0, st>>>(n, scalars, table, w, jac, status);
+}
+template <class C>
+void LaunchFixed<C>::fixed_tma(uint32_t n, const uint8_t *scalars, const uint32_t *table, int w, uint32_t *jac,
+			       int8_t *status, cudaStream_t st)
+{
+	k_smul_fixed_tma<C><<<grid_for(n), kThreads, 0, st>>>(n, scalars, table, w, jac, status);
 }
 template <class C>
 void LaunchFixed<C>::table_merge(uint32_t count, uint64_t first_entry, int w, int nwin_half,

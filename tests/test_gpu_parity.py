@@ -279,3 +279,79 @@ def test_layout_experiment_kernels_agree(curve):
     want = [x * pow(y * rinv, iters, p) % p for x, y in zip(a, b)]
     assert [int.from_bytes(o.tobytes(), "big") for o in o0] == want
     assert (o0 == o1).all()
+
+
+def test_full_size_ecdsa_verify_frp256v1():
+    """BASELINE.json config 3 at full size: 2^20 FRP256V1 signatures under 2^20 distinct keys.  Keys and signatures
+    come from the engine's own batch signer (cross-checked with the oracle on a sample); 1/16 are corrupted; the
+    verdict vector must equal the by-construction expectation on the whole batch and the oracle on a sample."""
+    import bench
+    inp = bench.make_verify_inputs("FRP256V1", 1 << 20, rank=3)
+    got = engine("FRP256V1").ecdsa_verify_batch(inp["sigs"], inp["pubkeys"], inp["digests"], inp["hlen"])
+    assert (got == inp["expected"]).all()
+    assert (got[::16] == -1).all() and int((got == 0).sum()) == (1 << 20) - (1 << 16)
+    idx = rng(101).choice(1 << 20, size=1024, replace=False)
+    want = oracle_verify("FRP256V1", inp["sigs"][idx], inp["pubkeys"][idx], inp["digests"][idx], inp["hlen"])
+    assert (got[idx] == want).all()
+
+
+def test_full_size_secp384r1_fixed_base_properties():
+    """BASELINE.json config 4 at full size (2^20 scalars on G, secp384r1): negation property on the whole batch and a
+    seeded sample against the oracle."""
+    curve = "SECP384R1"
+    n = 1 << 20
+    p, q = PRIME[curve], ORDER[curve]
+    sc = random_scalars(curve, n // 2, tag=170, below_q=False)
+    sc[:, 0] &= 0x7F
+    qb = np.frombuffer(q.to_bytes(48, "big"), dtype=np.uint8).astype(np.int32)
+    neg = sc.copy()
+    borrow = np.zeros(n // 2, dtype=np.int32)
+    for j in range(47, -1, -1):
+        dj = qb[j] - sc[:, j].astype(np.int32) - borrow
+        borrow = (dj < 0).astype(np.int32)
+        neg[:, j] = (dj + 256 * borrow).astype(np.uint8)
+    allsc = np.concatenate([sc, neg])
+    out, st = engine(curve).prj_pt_mul_batch(allsc)
+    assert (st == 0).all()
+    a, b = out[: n // 2], out[n // 2:]
+    assert (a[:, :48] == b[:, :48]).all()
+    pb = np.frombuffer(p.to_bytes(48, "big"), dtype=np.uint8).astype(np.int32)
+    carry = np.zeros(n // 2, dtype=np.int32)
+    ok = np.ones(n // 2, dtype=bool)
+    for j in range(47, -1, -1):
+        s = a[:, 48 + j].astype(np.int32) + b[:, 48 + j].astype(np.int32) + carry
+        ok &= (s & 0xFF) == pb[j]
+        carry = s >> 8
+    assert ok.all() and (carry == 0).all()
+    idx = rng(171).choice(n, size=1024, replace=False)
+    want, wst = oracle_smul(curve, allsc[idx])
+    assert (out[idx] == want).all() and (st[idx] == wst).all()
+
+
+def test_tma_staged_k1_variant_matches():
+    """DESIGN.md §3 staging experiment: K1 with its scalars staged by cp.async.bulk (ECCB200_TMA_STAGING=1, read once
+    per process, hence the subprocess) must give the same bytes, including for a ragged last CTA."""
+    import subprocess
+    import sys
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, 'tests'); sys.path.insert(0, '.')
+import libecc_b200
+from common import random_scalars, edge_scalars, oracle_smul
+import torch
+for curve in ('SECP256R1', 'SECP384R1'):
+    sc = np.concatenate([random_scalars(curve, 1000, tag=7, below_q=False), edge_scalars(curve)])
+    want, wst = oracle_smul(curve, sc)
+    eng = libecc_b200.Engine(curve, 0, 8)
+    d_sc = torch.from_numpy(sc.copy()).cuda().reshape(-1)
+    n = sc.shape[0]; rec = want.shape[1]
+    d_out = torch.zeros(n * rec, dtype=torch.uint8, device='cuda'); d_st = torch.zeros(n, dtype=torch.int8, device='cuda')
+    eng.prj_pt_mul_batch_dev(d_sc, None, d_out, d_st, 0)
+    torch.cuda.synchronize()
+    assert (d_out.cpu().numpy().reshape(n, rec) == want).all() and (d_st.cpu().numpy() == wst).all()
+print('TMA-OK')
+"""
+    env = dict(**__import__("os").environ, ECCB200_TMA_STAGING="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env,
+                       cwd=__import__("common").ROOT)
+    assert r.returncode == 0 and "TMA-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
