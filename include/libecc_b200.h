@@ -123,6 +123,7 @@ int eccb200_ecccdh_derive_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t 
 /* Page-locked host memory for the host-pointer entry points (wrappers of cudaHostAlloc / cudaFreeHost so that a C
  * caller need not link the CUDA runtime).  NULL on failure. */
 void *eccb200_host_alloc(size_t bytes);
+void *eccb200_host_alloc_input(size_t bytes); /* write-combined: for buffers the host only writes (batch inputs) */
 void eccb200_host_free(void *p);
 
 /* Field-level entry point used by the arithmetic unit tests (pattern: src/arithmetic_tests FP_MUL_MONTY):

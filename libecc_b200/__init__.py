@@ -24,7 +24,7 @@ ABI_SYMBOLS = [
     "eccb200_ecdsa_verify_batch_dev", "eccb200_fp_mul_monty_batch", "eccb200_comb_window",
     "eccb200_kernel_launches", "eccb200_last_error", "eccb200_ecdsa_uv_batch",
     "eccb200_profile_enable", "eccb200_profile_read", "eccb200_imad_peak", "eccb200_prj_pt_unique_batch",
-    "eccb200_host_alloc", "eccb200_host_free", "eccb200_ecdsa_sign_batch", "eccb200_ecdsa_sign_batch_dev",
+    "eccb200_host_alloc", "eccb200_host_alloc_input", "eccb200_host_free", "eccb200_ecdsa_sign_batch", "eccb200_ecdsa_sign_batch_dev",
     "eccb200_ecccdh_derive_batch", "eccb200_ecccdh_derive_batch_dev", "eccb200_fp_mul_chain_bench",
 ]
 
@@ -68,6 +68,8 @@ def load_library() -> ctypes.CDLL:
                                                ctypes.POINTER(ctypes.c_float)]
     lib.eccb200_host_alloc.argtypes = [ctypes.c_size_t]
     lib.eccb200_host_alloc.restype = ctypes.c_void_p
+    lib.eccb200_host_alloc_input.argtypes = [ctypes.c_size_t]
+    lib.eccb200_host_alloc_input.restype = ctypes.c_void_p
     lib.eccb200_host_free.argtypes = [ctypes.c_void_p]
     lib.eccb200_host_free.restype = None
     lib.eccb200_comb_window.argtypes = [ctypes.c_void_p]
@@ -94,12 +96,13 @@ def _as_u8(a, nbytes: Optional[int] = None) -> np.ndarray:
     return arr
 
 
-def pinned_empty(shape, dtype=np.uint8) -> np.ndarray:
-    """numpy array backed by page-locked memory from eccb200_host_alloc (freed with the array)."""
+def pinned_empty(shape, dtype=np.uint8, write_combined: bool = False) -> np.ndarray:
+    """numpy array backed by page-locked memory from eccb200_host_alloc (freed with the array);
+    write_combined=True uses eccb200_host_alloc_input (for input buffers the host only writes)."""
     lib = load_library()
     shape = (shape,) if isinstance(shape, int) else tuple(shape)
     nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
-    p = lib.eccb200_host_alloc(max(nbytes, 1))
+    p = (lib.eccb200_host_alloc_input if write_combined else lib.eccb200_host_alloc)(max(nbytes, 1))
     if not p:
         raise EccB200Error("eccb200_host_alloc failed")
     buf = (ctypes.c_uint8 * max(nbytes, 1)).from_address(p)

@@ -175,11 +175,6 @@ void fp_set_word(eccb200_fp *dst, const eccb200_fp *tmpl, uint64_t v)
 	dst->fp_val.val[0] = v;
 }
 
-struct Item {
-	bool valid;      /* structs initialised and on a supported curve */
-	bool inf;        /* input is the point at infinity */
-};
-
 /* core: out[i] = m[i]*in[i]; returns 0 iff all ok */
 int mul_batch(eccb200_prj_pt *out, const eccb200_nn *m, const eccb200_prj_pt *in, uint32_t n, int *ret)
 {

@@ -10,7 +10,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <mutex>
 #include <string>
 #include <vector>
 
@@ -638,6 +637,19 @@ extern "C" void *eccb200_host_alloc(size_t bytes)
 	if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
 		cudaGetLastError();
 		g_err = "cudaHostAlloc failed";
+		return nullptr;
+	}
+	return p;
+}
+
+/* Write-combined page-locked memory: for INPUT buffers the host only writes (reads of it by the CPU are slow);
+ * host->device DMA out of write-combined memory skips the CPU cache snoops. */
+extern "C" void *eccb200_host_alloc_input(size_t bytes)
+{
+	void *p = nullptr;
+	if (cudaHostAlloc(&p, bytes, cudaHostAllocWriteCombined) != cudaSuccess) {
+		cudaGetLastError();
+		g_err = "cudaHostAlloc(write-combined) failed";
 		return nullptr;
 	}
 	return p;

@@ -1,5 +1,6 @@
 /*
- * kernels.cuh — the sm_100a kernels of the engine (SURVEY.md §2 "new kernel" table: K1..K5).
+ * kernels.cuh — the sm_100a kernels of the engine (SURVEY.md §2 "new kernel" table: K1..K5), the kernels of the
+ * "next" rows built so far (ECDSA sign, ECC-CDH), and the measurement / experiment kernels DESIGN.md cites.
  *
  * Layout in HBM (all produced / consumed by these kernels):
  *   wire buffers   : libecc big-endian byte strings, array-of-structures (scalars [n][qlen], affine points
@@ -293,7 +294,8 @@ __global__ void __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VAR : ECC_MINB_VAR_
 	status[idx] = ok ? 0 : -1;
 }
 
-/* Comb-table build: entry e = (i << w) + d  ->  (d << (w*i)) * G, through the same window_mul as K2. */
+/* Comb-table build (w <= 16, and the half-width base table of wider ones): entry e = (i << w) + d  ->
+ * (d << (w*i)) * G, through the same window_mul as K2. */
 template <class C>
 __global__ void __launch_bounds__(128) k_table_points(uint32_t n_entries, int w, uint32_t *__restrict__ jac)
 {

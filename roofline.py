@@ -7,8 +7,10 @@ import math
 
 # one Montgomery CIOS product of n 64-bit limbs = 2n^2+n wide multiply-accumulates, each = 4 32x32->64 IMADs
 IMAD32_PER_MUL = {"SECP256R1": (2 * 4 * 4 + 4) * 4, "FRP256V1": (2 * 4 * 4 + 4) * 4, "SECP384R1": (2 * 6 * 6 + 6) * 4}
-# IMAD.WIDE instructions the generated multiplier really issues (tools/gen_fp_ptx.py; P-256's 0/1 words are free)
-IMAD_EXECUTED_PER_MUL = {"SECP256R1": 96, "FRP256V1": 136, "SECP384R1": 276}
+# IMAD.WIDE instructions the generated code really issues per product, averaged over a mixed addition (8 mul + 3 sqr;
+# tools/gen_fp_ptx.py: P-256 mul 96 / sqr 68, generic 256-bit 136 / 108, P-384 276 / 210 incl. the m_i products)
+IMAD_EXECUTED_PER_MUL = {"SECP256R1": (8 * 96 + 3 * 68) / 11, "FRP256V1": (8 * 136 + 3 * 108) / 11,
+                         "SECP384R1": (8 * 276 + 3 * 210) / 11}
 M_REF = {"SECP256R1": 8724, "FRP256V1": 8724, "SECP384R1": 13076}   # reference ladder (probe)
 QBITS = {"SECP256R1": 256, "FRP256V1": 256, "SECP384R1": 384}
 
