@@ -258,6 +258,27 @@ def cpu_baseline(workload: str, inputs, budget_s: float = 12.0):
             "sample": f"first {cnt} items of the step's batch, {t:.1f} s on {threads} threads"}, cnt, outs
 
 
+def ncu_dram_traffic(workload: str, batch_log2: int, comb_window: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
+    `ncu --set full` capture of this exact configuration (profiles/); None when no capture matches."""
+    if not (workload == "secp256r1_fixed_base" and batch_log2 == 20 and comb_window == 22):
+        return None
+    path = os.path.join(ROOT, "profiles", "r01_ncu_smul_fixed_w22.csv")
+    try:
+        tot = 0.0
+        for line in open(path):
+            parts = line.strip().split(",")
+            if parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[parts[1]]
+                tot += float(parts[2]) * scale
+        return {"bytes_per_launch": tot, "algorithmic_bytes_per_launch": (1 << batch_log2) * (32 + 96 + 1 + 12 * 64),
+                "source": "profiles/r01_ncu_smul_fixed_w22.csv; algorithmic = scalar 32 B + Jacobian result 96 B + "
+                          "status 1 B + 12 random 64 B table entries per item (3.2 GiB table, mostly L2 misses, "
+                          "fetched in 128 B lines); 13 % of the measured HBM bandwidth - not the bound"}
+    except OSError:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------ main
 
 def main():
@@ -506,7 +527,8 @@ def main():
     work = work_per_item(args.workload, eng.comb_window)
     achieved = n * work["imad32_per_item"] / (k0 / 1000.0) / 1e12
     roofline = {"bound": "int-mad", "kernel": work["kernel"], "achieved": achieved, "peak": peak["timad32_per_s"],
-                "unit": "T IMAD32/s", "frac": achieved / peak["timad32_per_s"], "traffic": None,
+                "unit": "T IMAD32/s", "frac": achieved / peak["timad32_per_s"],
+                "traffic": ncu_dram_traffic(args.workload, args.batch_log2, eng.comb_window),
                 "kernel_ms": k0, "kernel_share_of_step": k0 / (sum(step_ms) / len(step_ms)),
                 "M_impl": work["M_impl"], "imad32_per_field_mul": work["imad32_per_mul"],
                 "frac_executed_imad_wide": n * work["imad_executed_per_item"] / (k0 / 1000.0) / 1e12
