@@ -140,6 +140,13 @@ extern "C" int eccb200_ctx_create(eccb200_ctx **out, int curve_id, int device, i
 	CUDA_OK(cudaGetDeviceProperties(&prop, device));
 	if (prop.major != 10) return fail("libecc_b200 is built for sm_100a (B200) only");
 	if (const char *ss = getenv("ECCB200_STACK")) cudaDeviceSetLimit(cudaLimitStackSize, (size_t)atoi(ss));
+	/* tuning knob: L2 fetch granularity for the random 64-96 B comb-table gathers (32, 64 or 128; measured: no
+	 * effect on the kernel time, which is integer-pipe bound — left at the device default unless requested) */
+	if (const char *lf = getenv("ECCB200_L2_FETCH")) {
+		size_t g = (size_t)atoi(lf);
+		if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g);
+		cudaGetLastError();
+	}
 	int w = comb_window ? comb_window : 22; /* default: 22-bit windows (12 adds per 256-bit scalar, 3.2 GB table) */
 	if (w < 4 || w > 24 || (w > 16 && (w & 1))) return fail("comb_window must be in [4,16] or even in [18,24]");
 
