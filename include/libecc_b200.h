@@ -120,6 +120,21 @@ int eccb200_ecccdh_derive_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *pri
 int eccb200_ecccdh_derive_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_privkeys,
 				    const uint8_t *d_peer_pubkeys, uint8_t *d_shared, int8_t *d_status, void *stream);
 
+/*
+ * Hashing of short messages on the device (SHA-256 / SHA-384 / SHA-512; hash_type = the reference's hash_alg_type
+ * value: 2, 3, 4 — src/lib_ecc_types.h:82-).  Replaces hfunc_scattered of the matching hash_mapping
+ * (src/hash/hash_algs.h:232-241; sha256_scattered src/hash/sha256.c:201) for a batch: message i is
+ * msgs[offsets[i] .. offsets[i+1]), offsets has n+1 entries, digests is [n][digest_size].
+ */
+int eccb200_hash_batch(eccb200_ctx *ctx, int hash_type, uint32_t n, const uint8_t *msgs, const uint64_t *offsets,
+		       uint8_t *digests);
+
+/* ECDSA verification of raw messages: eccb200_hash_batch + eccb200_ecdsa_verify_batch fused on the device, i.e. the
+ * whole of ec_verify(…, ECDSA, hash_type, NULL, 0) (src/sig/sig_algs.c:655) per item. */
+int eccb200_ecdsa_verify_msgs_batch(eccb200_ctx *ctx, int hash_type, uint32_t n, const uint8_t *sigs,
+				    const uint8_t *pubkeys, const uint8_t *msgs, const uint64_t *offsets,
+				    int8_t *verdict);
+
 /* Page-locked host memory for the host-pointer entry points (wrappers of cudaHostAlloc / cudaFreeHost so that a C
  * caller need not link the CUDA runtime).  NULL on failure. */
 void *eccb200_host_alloc(size_t bytes);

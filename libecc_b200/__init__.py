@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "eccb200_kernel_launches", "eccb200_last_error", "eccb200_ecdsa_uv_batch",
     "eccb200_profile_enable", "eccb200_profile_read", "eccb200_imad_peak", "eccb200_prj_pt_unique_batch",
     "eccb200_host_alloc", "eccb200_host_alloc_input", "eccb200_host_free", "eccb200_ecdsa_sign_batch", "eccb200_ecdsa_sign_batch_dev",
-    "eccb200_ecccdh_derive_batch", "eccb200_ecccdh_derive_batch_dev", "eccb200_fp_mul_chain_bench",
+    "eccb200_ecccdh_derive_batch", "eccb200_ecccdh_derive_batch_dev", "eccb200_fp_mul_chain_bench", "eccb200_hash_batch", "eccb200_ecdsa_verify_msgs_batch",
 ]
 
 _lib = None
@@ -66,6 +66,8 @@ def load_library() -> ctypes.CDLL:
     lib.eccb200_ecccdh_derive_batch_dev.argtypes = [ctypes.c_void_p, u32, u8p, u8p, u8p, i8p, ctypes.c_void_p]
     lib.eccb200_fp_mul_chain_bench.argtypes = [ctypes.c_void_p, ctypes.c_int, u32, u8p, u8p, u8p, ctypes.c_int,
                                                ctypes.POINTER(ctypes.c_float)]
+    lib.eccb200_hash_batch.argtypes = [ctypes.c_void_p, ctypes.c_int, u32, u8p, u8p, u8p]
+    lib.eccb200_ecdsa_verify_msgs_batch.argtypes = [ctypes.c_void_p, ctypes.c_int, u32, u8p, u8p, u8p, u8p, i8p]
     lib.eccb200_host_alloc.argtypes = [ctypes.c_size_t]
     lib.eccb200_host_alloc.restype = ctypes.c_void_p
     lib.eccb200_host_alloc_input.argtypes = [ctypes.c_size_t]
@@ -218,6 +220,34 @@ class Engine:
                                                          shared.ctypes.data, status.ctypes.data),
                     "eccb200_ecccdh_derive_batch")
         return shared, status
+
+    HASH_IDS = {"SHA256": 2, "SHA384": 3, "SHA512": 4}   # libecc hash_alg_type
+    HASH_LEN = {"SHA256": 32, "SHA384": 48, "SHA512": 64}
+
+    @staticmethod
+    def _pack_msgs(msgs):
+        off = np.zeros(len(msgs) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(m) for m in msgs])
+        blob = np.frombuffer(b"".join(bytes(m) for m in msgs) or b"\0", dtype=np.uint8).copy()
+        return blob, off
+
+    def hash_batch(self, hash_name: str, msgs) -> np.ndarray:
+        blob, off = self._pack_msgs(msgs)
+        out = np.zeros((len(msgs), self.HASH_LEN[hash_name]), dtype=np.uint8)
+        self._check(self.lib.eccb200_hash_batch(self._h, self.HASH_IDS[hash_name], len(msgs), blob.ctypes.data,
+                                                off.ctypes.data, out.ctypes.data), "eccb200_hash_batch")
+        return out
+
+    def ecdsa_verify_msgs_batch(self, hash_name: str, sigs, pubkeys, msgs) -> np.ndarray:
+        n = len(msgs)
+        sg = _as_u8(sigs, n * 2 * self.qlen)
+        pk = _as_u8(pubkeys, n * 2 * self.plen)
+        blob, off = self._pack_msgs(msgs)
+        verdict = np.zeros(n, dtype=np.int8)
+        self._check(self.lib.eccb200_ecdsa_verify_msgs_batch(self._h, self.HASH_IDS[hash_name], n, sg.ctypes.data,
+                                                             pk.ctypes.data, blob.ctypes.data, off.ctypes.data,
+                                                             verdict.ctypes.data), "eccb200_ecdsa_verify_msgs_batch")
+        return verdict
 
     def prj_pt_unique_batch(self, prj_points) -> Tuple[np.ndarray, np.ndarray]:
         pp = _as_u8(prj_points)

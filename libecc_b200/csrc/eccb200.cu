@@ -4,6 +4,7 @@
  */
 #include "../../include/libecc_b200.h"
 #include "kernels.cuh"
+#include "sha2.cuh"
 
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -635,6 +636,73 @@ extern "C" int eccb200_ecccdh_derive_batch(eccb200_ctx *ctx, uint32_t n, const u
 				(int8_t *)(ctx->d_out[s] + (size_t)cnt * pl), ctx->stage_jac[s], ctx->stage_prefix[s],
 				ctx->streams[s]);
 	});
+}
+
+/* ------------------------------------------------------------------------------------------ hashing on device (§8f.3) */
+
+static int hash_dev(eccb200_ctx *ctx, int hash_type, uint32_t n, const uint8_t *d_msgs, const uint64_t *d_off,
+		    uint8_t *d_digests, cudaStream_t st)
+{
+	if (n == 0) return 0;
+	if (!sha2_digest_size(hash_type)) return fail("unsupported hash (SHA256 = 2, SHA384 = 3, SHA512 = 4)");
+	k_sha2_batch<<<grid_for(n), kThreads, 0, st>>>(n, hash_type, d_msgs, d_off, d_digests);
+	ctx->launches += 1;
+	CUDA_OK(cudaGetLastError());
+	return 0;
+}
+
+extern "C" int eccb200_hash_batch(eccb200_ctx *ctx, int hash_type, uint32_t n, const uint8_t *msgs,
+				  const uint64_t *offsets, uint8_t *digests)
+{
+	if (!ctx || (n && (!offsets || !digests))) return fail("null argument");
+	const int ds = sha2_digest_size(hash_type);
+	if (!ds) return fail("unsupported hash (SHA256 = 2, SHA384 = 3, SHA512 = 4)");
+	if (n == 0) return 0;
+	CUDA_OK(cudaSetDevice(ctx->device));
+	const uint64_t total = offsets[n];
+	if (total && !msgs) return fail("null argument");
+	uint8_t *d = nullptr;
+	const size_t off_b = ((size_t)total + 15) & ~(size_t)15, offs_bytes = (size_t)(n + 1) * sizeof(uint64_t);
+	CUDA_OK(cudaMalloc(&d, off_b + offs_bytes + (size_t)n * ds + 16));
+	int rc = 0;
+	if ((total && cudaMemcpy(d, msgs, total, cudaMemcpyHostToDevice) != cudaSuccess) ||
+	    cudaMemcpy(d + off_b, offsets, offs_bytes, cudaMemcpyHostToDevice) != cudaSuccess)
+		rc = fail("H2D copy failed");
+	if (!rc) rc = hash_dev(ctx, hash_type, n, d, (const uint64_t *)(d + off_b), d + off_b + offs_bytes, 0);
+	if (!rc && cudaMemcpy(digests, d + off_b + offs_bytes, (size_t)n * ds, cudaMemcpyDeviceToHost) != cudaSuccess)
+		rc = fail("D2H copy failed");
+	cudaFree(d);
+	return rc;
+}
+
+/* ECDSA verification of raw messages: SHA-2 on the device, then K3.  One launch pair for the whole batch. */
+extern "C" int eccb200_ecdsa_verify_msgs_batch(eccb200_ctx *ctx, int hash_type, uint32_t n, const uint8_t *sigs,
+					       const uint8_t *pubkeys, const uint8_t *msgs, const uint64_t *offsets,
+					       int8_t *verdict)
+{
+	if (!ctx || (n && (!sigs || !pubkeys || !offsets || !verdict))) return fail("null argument");
+	const int ds = sha2_digest_size(hash_type);
+	if (!ds) return fail("unsupported hash (SHA256 = 2, SHA384 = 3, SHA512 = 4)");
+	if (n == 0) return 0;
+	CUDA_OK(cudaSetDevice(ctx->device));
+	const uint64_t total = offsets[n];
+	if (total && !msgs) return fail("null argument");
+	const size_t sg = (size_t)n * 2 * ctx->qlen, pk = (size_t)n * 2 * ctx->plen, dg = (((size_t)n * ds) + 15) & ~(size_t)15;
+	const size_t mb = ((size_t)total + 15) & ~(size_t)15, ob = (size_t)(n + 1) * sizeof(uint64_t);
+	uint8_t *d = nullptr;
+	CUDA_OK(cudaMalloc(&d, sg + pk + dg + mb + ob + n + 16));
+	uint8_t *d_sig = d, *d_pk = d + sg, *d_dg = d + sg + pk, *d_msg = d_dg + dg, *d_off = d_msg + mb, *d_v = d_off + ob;
+	int rc = 0;
+	if (cudaMemcpy(d_sig, sigs, sg, cudaMemcpyHostToDevice) != cudaSuccess ||
+	    cudaMemcpy(d_pk, pubkeys, pk, cudaMemcpyHostToDevice) != cudaSuccess ||
+	    (total && cudaMemcpy(d_msg, msgs, total, cudaMemcpyHostToDevice) != cudaSuccess) ||
+	    cudaMemcpy(d_off, offsets, ob, cudaMemcpyHostToDevice) != cudaSuccess)
+		rc = fail("H2D copy failed");
+	if (!rc) rc = hash_dev(ctx, hash_type, n, d_msg, (const uint64_t *)d_off, d_dg, 0);
+	if (!rc) rc = verify_dev(ctx, n, d_sig, d_pk, d_dg, (uint32_t)ds, (int8_t *)d_v, 0);
+	if (!rc && cudaMemcpy(verdict, d_v, n, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail("D2H copy failed");
+	cudaFree(d);
+	return rc;
 }
 
 /* Page-locked host memory for callers that do not link CUDA themselves (cudaHostAlloc / cudaFreeHost). */

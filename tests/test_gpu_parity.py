@@ -355,3 +355,53 @@ print('TMA-OK')
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env,
                        cwd=__import__("common").ROOT)
     assert r.returncode == 0 and "TMA-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_device_sha2_matches_hashlib_and_reference():
+    """Row (f).3: SHA-256/384/512 on the device against hashlib and the reference's own src/hash (ref_hash)."""
+    import ctypes
+    import hashlib
+    from common import ref_lib
+    g = rng(111)
+    lens = list(range(0, 150)) + [183, 184, 185, 239, 240, 247, 248, 255, 256, 257, 1000, 4097]
+    msgs = [g.bytes(n) for n in lens]
+    eng = engine("SECP256R1", 8)
+    ref = ref_lib()
+    for name, fn in (("SHA256", hashlib.sha256), ("SHA384", hashlib.sha384), ("SHA512", hashlib.sha512)):
+        out = eng.hash_batch(name, msgs)
+        assert [o.tobytes() for o in out] == [fn(m).digest() for m in msgs], name
+        if ref is not None:
+            for m in msgs[::17]:
+                buf = ctypes.create_string_buffer(64); ol = ctypes.c_uint32()
+                assert ref.ref_hash(name.encode(), m, len(m), buf, ctypes.byref(ol)) == 0
+                assert buf.raw[: ol.value] == fn(m).digest()
+
+
+def test_ecdsa_verify_msgs_batch():
+    """ec_verify on raw messages (hash on the device, then K3): the reference's KATs that use SHA-2, and a seeded
+    batch signed by the oracle over hashlib digests with a few corrupted messages."""
+    import hashlib
+    from common import oracle_sign
+    fn = {"SHA256": hashlib.sha256, "SHA384": hashlib.sha384, "SHA512": hashlib.sha512}
+    for v in golden("ecdsa_kat.json"):
+        if v["hash"] not in fn:
+            continue
+        msg = bytes.fromhex(v["msg"])
+        got = engine(v["curve"]).ecdsa_verify_msgs_batch(v["hash"], hx(v["sig"]), hx(v["pub"]), [msg])
+        assert got[0] == 0, v["name"]
+        assert engine(v["curve"]).ecdsa_verify_msgs_batch(v["hash"], hx(v["sig"]), hx(v["pub"]), [msg + b"x"])[0] == -1
+    for curve, hname in (("FRP256V1", "SHA256"), ("SECP384R1", "SHA384"), ("SECP256R1", "SHA512")):
+        n = 600
+        g = rng(112)
+        msgs = [g.bytes(int(g.integers(0, 200))) for _ in range(n)]
+        dg = np.stack([np.frombuffer(fn[hname](m).digest(), dtype=np.uint8) for m in msgs])
+        d = random_scalars(curve, n, tag=113); k = random_scalars(curve, n, tag=114)
+        sigs, st = oracle_sign(curve, d, k, dg, dg.shape[1])
+        assert (st == 0).all()
+        pubs, _ = oracle_smul(curve, d)
+        bad = list(range(0, n, 10))
+        for i in bad:
+            msgs[i] = msgs[i] + b"!"
+        got = engine(curve).ecdsa_verify_msgs_batch(hname, sigs, pubs, msgs)
+        want = np.zeros(n, dtype=np.int8); want[bad] = -1
+        assert (got == want).all()
