@@ -29,6 +29,10 @@ extern "C" {
 #define ECCB200_FRP256V1 1
 #define ECCB200_SECP256R1 4
 #define ECCB200_SECP384R1 5
+/* additional short-Weierstrass curves served by the same kernels (generic-a / a = 0 doubling, generic reduction) */
+#define ECCB200_BRAINPOOLP256R1 8
+#define ECCB200_BRAINPOOLP384R1 12
+#define ECCB200_SECP256K1 19
 
 /* Per-item status codes written by the batch calls. */
 #define ECCB200_OK 0        /* finite result / valid signature                                          */

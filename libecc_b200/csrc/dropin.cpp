@@ -26,6 +26,7 @@ constexpr uint64_t kFpMagic = 0x14e96c8ab28221efULL;     /* fp/fp.c:127 */
 constexpr uint64_t kNnMagic = 0xb4cf5d56e2023316ULL ^ (uint64_t)(ECCB200_NN_MAX_WORD_LEN + 64); /* nn/nn.c:28 */
 constexpr uint64_t kPubKeyMagic = 0x31327f37741ffb76ULL; /* sig/ec_key.h:118 */
 constexpr int kMaxWords = ECCB200_NN_MAX_WORD_LEN;
+constexpr int kNumCurves = 6;
 
 struct CurveInfo {
 	int id;
@@ -50,8 +51,9 @@ template <class C> CurveInfo make_info()
 
 const CurveInfo *curves()
 {
-	static const CurveInfo tab[3] = { make_info<Curve_SECP256R1>(), make_info<Curve_FRP256V1>(),
-					  make_info<Curve_SECP384R1>() };
+	static const CurveInfo tab[kNumCurves] = { make_info<Curve_SECP256R1>(),       make_info<Curve_FRP256V1>(),
+						    make_info<Curve_SECP384R1>(),       make_info<Curve_BRAINPOOLP256R1>(),
+						    make_info<Curve_BRAINPOOLP384R1>(), make_info<Curve_SECP256K1>() };
 	return tab;
 }
 
@@ -73,7 +75,7 @@ const CurveInfo *identify(const eccb200_prj_pt *pt)
 {
 	const eccb200_fp_ctx *ctx = pt->X.ctx;
 	if (!nn_ok(&ctx->p) || !nn_ok(&pt->crv->order)) return nullptr;
-	for (int c = 0; c < 3; c++) {
+	for (int c = 0; c < kNumCurves; c++) {
 		const CurveInfo *ci = &curves()[c];
 		if (words_eq(&ctx->p, ci->p, ci->n64) && words_eq(&pt->crv->order, ci->q, ci->n64)) return ci;
 	}
@@ -82,7 +84,7 @@ const CurveInfo *identify(const eccb200_prj_pt *pt)
 
 std::mutex g_mu;
 unsigned long long g_calls = 0; /* scalar multiplications served (eccb200_dropin_call_count) */
-eccb200_ctx *g_ctx[8] = { nullptr };
+eccb200_ctx *g_ctx[32] = { nullptr }; /* indexed by the reference's ec_curve_type (< 32 here) */
 int g_device = -1;
 
 eccb200_ctx *engine_for(int curve_id)

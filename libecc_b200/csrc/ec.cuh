@@ -15,8 +15,9 @@
  *     window, no doublings (K1);
  *   - variable base (k*P): signed 4-bit fixed window, 8-entry Jacobian table per thread (K2).
  *
- * All three target curves have a = p - 3 (curves/known/ec_params_secp256r1.h:78-83, ..._frp256v1.h:84-89,
- * ..._secp384r1.h); tools/gen_curve_constants.py asserts it.
+ * The three curves of BASELINE.json have a = p - 3 (curves/known/ec_params_secp256r1.h:78-83, ..._frp256v1.h:84-89,
+ * ..._secp384r1.h) and use the a = -3 doubling; the additional curves (Brainpool P256r1 / P384r1: generic a,
+ * secp256k1: a = 0) select their doubling through Curve::A_KIND (tools/gen_curve_constants.py).
  */
 #pragma once
 #include "fp.cuh"
@@ -53,15 +54,28 @@ template <class C> struct EC {
 		F::set_one(p.Z);
 	}
 
-	/* y^2 == x^3 - 3x + b (all Montgomery form); affine form of prj_pt_is_on_curve (curves/prj_pt.c:144-190) */
+	static ECC_HD void load_a(E &r)
+	{
+#pragma unroll
+		for (int i = 0; i < N; i++) r.w[i] = C::A_MONT(i);
+	}
+
+	/* y^2 == x^3 + a x + b (all Montgomery form); affine form of prj_pt_is_on_curve (curves/prj_pt.c:144-190) */
 	static ECC_HD bool on_curve(const A &a)
 	{
 		E t, u, b;
 		F::sqr(t, a.x);
 		F::mul(u, t, a.x);      /* x^3 */
-		F::add(t, a.x, a.x);
-		F::add(t, t, a.x);      /* 3x */
-		F::sub(u, u, t);
+		if (C::A_KIND == 0) {
+			F::add(t, a.x, a.x);
+			F::add(t, t, a.x);  /* 3x */
+			F::sub(u, u, t);
+		} else if (C::A_KIND == 2) {
+			E am;
+			load_a(am);
+			F::mul(t, am, a.x);
+			F::add(u, u, t);
+		}
 #pragma unroll
 		for (int i = 0; i < N; i++) b.w[i] = C::B_MONT(i);
 		F::add(u, u, b);
@@ -73,9 +87,68 @@ template <class C> struct EC {
 	 * path from being inlined into every hot loop. */
 	static ECC_NOINLINE void dbl_slow(J &r, const J &p) { dbl(r, p); }
 
-	/* Jacobian doubling for a = -3 (dbl-2001-b): 3M + 5S.  inf -> inf (Z3 = 0).  r may alias p. */
+	/* Jacobian doubling, r may alias p, inf -> inf (Z3 = 0).  Three formulas selected at compile time by the curve:
+	 * a = -3 (dbl-2001-b, 3M + 5S: the three curves of BASELINE.json), a = 0 (dbl-2009-l, 2M + 5S: secp256k1) and
+	 * generic a (dbl-2007-bl, 2M + 8S: Brainpool). */
 	static ECC_HD void dbl(J &r, const J &p)
 	{
+		if (C::A_KIND == 1) {
+			E a_, b_, c_, d_, e_, f_, t;
+			F::sqr(a_, p.X);
+			F::sqr(b_, p.Y);
+			F::sqr(c_, b_);
+			F::add(t, p.X, b_);
+			F::sqr(d_, t);
+			F::sub(d_, d_, a_);
+			F::sub(d_, d_, c_);
+			F::add(d_, d_, d_);      /* D = 2((X+B)^2 - A - C) */
+			F::add(e_, a_, a_);
+			F::add(e_, e_, a_);      /* E = 3A */
+			F::sqr(f_, e_);
+			F::mul(t, p.Y, p.Z);
+			F::add(r.Z, t, t);       /* Z3 = 2YZ */
+			F::sub(f_, f_, d_);
+			F::sub(r.X, f_, d_);     /* X3 = F - 2D */
+			F::sub(t, d_, r.X);
+			F::mul(f_, e_, t);
+			F::add(c_, c_, c_);
+			F::add(c_, c_, c_);
+			F::add(c_, c_, c_);      /* 8C */
+			F::sub(r.Y, f_, c_);
+			return;
+		}
+		if (C::A_KIND == 2) {
+			E xx, yy, yyyy, zz, s_, m_, t, am;
+			F::sqr(xx, p.X);
+			F::sqr(yy, p.Y);
+			F::sqr(yyyy, yy);
+			F::sqr(zz, p.Z);
+			F::add(t, p.X, yy);
+			F::sqr(s_, t);
+			F::sub(s_, s_, xx);
+			F::sub(s_, s_, yyyy);
+			F::add(s_, s_, s_);      /* S = 2((X+YY)^2 - XX - YYYY) */
+			F::add(t, p.Y, p.Z);
+			F::sqr(r.Z, t);
+			F::sub(r.Z, r.Z, yy);
+			F::sub(r.Z, r.Z, zz);    /* Z3 = (Y+Z)^2 - YY - ZZ */
+			F::sqr(t, zz);
+			load_a(am);
+			F::mul(m_, am, t);       /* a ZZ^2 */
+			F::add(t, xx, xx);
+			F::add(t, t, xx);
+			F::add(m_, m_, t);       /* M = 3XX + a ZZ^2 */
+			F::sqr(t, m_);
+			F::sub(t, t, s_);
+			F::sub(r.X, t, s_);      /* X3 = M^2 - 2S */
+			F::sub(t, s_, r.X);
+			F::mul(s_, m_, t);
+			F::add(yyyy, yyyy, yyyy);
+			F::add(yyyy, yyyy, yyyy);
+			F::add(yyyy, yyyy, yyyy); /* 8 YYYY */
+			F::sub(r.Y, s_, yyyy);
+			return;
+		}
 		E delta, gamma, beta, alpha, t0, t1;
 		F::sqr(delta, p.Z);
 		F::sqr(gamma, p.Y);

@@ -74,6 +74,9 @@ template <class Fn> static int dispatch(int curve_id, Fn &&fn)
 	case ECCB200_SECP256R1: return fn(Curve_SECP256R1());
 	case ECCB200_FRP256V1: return fn(Curve_FRP256V1());
 	case ECCB200_SECP384R1: return fn(Curve_SECP384R1());
+	case ECCB200_BRAINPOOLP256R1: return fn(Curve_BRAINPOOLP256R1());
+	case ECCB200_BRAINPOOLP384R1: return fn(Curve_BRAINPOOLP384R1());
+	case ECCB200_SECP256K1: return fn(Curve_SECP256K1());
 	default: return fail("unknown curve id");
 	}
 }

@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(128) k_to_affine(uint32_t n, const uint32_t *_
 }
 
 /* Loads homogeneous projective wire points (X||Y||Z big-endian, prj_pt_export_to_buf curves/prj_pt.c:562), checks
- * them like prj_pt_import_from_buf (:462-500: coordinates < p, Y^2 Z == X^3 - 3 X Z^2 + b Z^3) and writes
+ * them like prj_pt_import_from_buf (:462-500: coordinates < p, Y^2 Z == X^3 + a X Z^2 + b Z^3) and writes
  * Montgomery-form words for k_to_affine<MODE 2>.  status: 0 ok, -1 rejected (then Z is written as 0). */
 template <class C>
 __global__ void __launch_bounds__(128) k_prj_load(uint32_t n, const uint8_t *__restrict__ prj,
@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(128) k_prj_load(uint32_t n, const uint8_t *__r
 	F::to_mont(P.X, x);
 	F::to_mont(P.Y, y);
 	F::to_mont(P.Z, z);
-	{ /* Y^2 Z == X^3 - 3 X Z^2 + b Z^3 */
+	{ /* Y^2 Z == X^3 + a X Z^2 + b Z^3 */
 		Fe<N> l, r, t, z2, bm;
 		F::sqr(t, P.Y);
 		F::mul(l, t, P.Z);
@@ -505,9 +505,16 @@ __global__ void __launch_bounds__(128) k_prj_load(uint32_t n, const uint8_t *__r
 		F::mul(r, t, P.X);
 		F::sqr(z2, P.Z);
 		F::mul(t, P.X, z2);
-		F::sub(r, r, t);
-		F::sub(r, r, t);
-		F::sub(r, r, t);
+		if (C::A_KIND == 0) {
+			F::sub(r, r, t);
+			F::sub(r, r, t);
+			F::sub(r, r, t);
+		} else if (C::A_KIND == 2) {
+			Fe<N> am, at;
+			EC<C>::load_a(am);
+			F::mul(at, am, t);
+			F::add(r, r, at);
+		}
 #pragma unroll
 		for (int i = 0; i < N; i++) bm.w[i] = C::B_MONT(i);
 		F::mul(t, z2, P.Z);

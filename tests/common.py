@@ -20,15 +20,24 @@ HOSTSIM_SO = os.path.join(ROOT, "tests", "hostsim", "_build", "libecc_hostsim.so
 SEED = 0x6C69626563632D31  # "libecc-1" 
 
 CURVES = {"SECP256R1": (4, 32, 32), "FRP256V1": (1, 32, 32), "SECP384R1": (5, 48, 48)}  # id, plen, qlen
+# additional curves: same kernels, generic-a / a = 0 doubling
+EXTRA_CURVES = {"BRAINPOOLP256R1": (8, 32, 32), "BRAINPOOLP384R1": (12, 48, 48), "SECP256K1": (19, 32, 32)}
+ALL_CURVES = dict(CURVES, **EXTRA_CURVES)
 ORDER = {
     "SECP256R1": 0xffffffff00000000ffffffffffffffffbce6faada7179e84f3b9cac2fc632551,
     "FRP256V1": 0xf1fd178c0b3ad58f10126de8ce42435b53dc67e140d2bf941ffdd459c6d655e1,
     "SECP384R1": 0xffffffffffffffffffffffffffffffffffffffffffffffffc7634d81f4372ddf581a0db248b0a77aecec196accc52973,
+    "BRAINPOOLP256R1": 0xa9fb57dba1eea9bc3e660a909d838d718c397aa3b561a6f7901e0e82974856a7,
+    "BRAINPOOLP384R1": 0x8cb91e82a3386d280f5d6f7e50e641df152f7109ed5456b31f166e6cac0425a7cf3ab6af6b7fc3103b883202e9046565,
+    "SECP256K1": 0xfffffffffffffffffffffffffffffffebaaedce6af48a03bbfd25e8cd0364141,
 }
 PRIME = {
     "SECP256R1": 0xffffffff00000001000000000000000000000000ffffffffffffffffffffffff,
     "FRP256V1": 0xf1fd178c0b3ad58f10126de8ce42435b3961adbcabc8ca6de8fcf353d86e9c03,
     "SECP384R1": 0xfffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffeffffffff0000000000000000ffffffff,
+    "BRAINPOOLP256R1": 0xa9fb57dba1eea9bc3e660a909d838d726e3bf623d52620282013481d1f6e5377,
+    "BRAINPOOLP384R1": 0x8cb91e82a3386d280f5d6f7e50e641df152f7109ed5456b412b1da197fb71123acd3a729901d1a71874700133107ec53,
+    "SECP256K1": 0xfffffffffffffffffffffffffffffffffffffffffffffffffffffffefffffc2f,
 }
 HASHLEN = {"SHA224": 28, "SHA256": 32, "SHA384": 48, "SHA512": 64, "SHA3_224": 28, "SHA3_256": 32,
            "SHA3_384": 48, "SHA3_512": 64}
@@ -92,7 +101,7 @@ def rng(tag: int = 0) -> np.random.Generator:
 
 def random_scalars(curve: str, n: int, tag: int = 0, below_q: bool = True) -> np.ndarray:
     """n big-endian qlen-byte scalars, uniform in [1, q-1] (rejection sampling) or raw bytes."""
-    _, _, qlen = CURVES[curve]
+    _, _, qlen = ALL_CURVES[curve]
     g = rng(tag)
     raw = g.integers(0, 256, size=(n, qlen), dtype=np.uint8)
     if below_q:
@@ -108,7 +117,7 @@ def random_scalars(curve: str, n: int, tag: int = 0, below_q: bool = True) -> np
 
 def edge_scalars(curve: str) -> np.ndarray:
     """The adversarial scalars of SURVEY.md §8a's edge table."""
-    _, _, qlen = CURVES[curve]
+    _, _, qlen = ALL_CURVES[curve]
     q = ORDER[curve]
     vals = [0, 1, 2, 3, q - 2, q - 1, q, q + 1, (1 << (8 * qlen)) - 1, 1 << (8 * qlen - 1), 0x10, 0x100, 1 << 16,
             (1 << 16) - 1, 1 << 64, q >> 1, (q >> 1) + 1]
@@ -123,7 +132,7 @@ def _buf(a):
 
 def oracle_smul(curve: str, scalars: np.ndarray, points=None, nthreads: int = 8, lib=None):
     """(out[n,2plen], status[n]) from the oracle port (or the compiled reference with lib=ref_lib())."""
-    _, plen, qlen = CURVES[curve]
+    _, plen, qlen = ALL_CURVES[curve]
     sc = np.ascontiguousarray(scalars, dtype=np.uint8).reshape(-1, qlen)
     n = sc.shape[0]
     out = np.zeros((n, 2 * plen), dtype=np.uint8)
@@ -139,7 +148,7 @@ def oracle_smul(curve: str, scalars: np.ndarray, points=None, nthreads: int = 8,
 
 
 def oracle_verify(curve: str, sigs, pubkeys, digests, hlen: int, nthreads: int = 8) -> np.ndarray:
-    _, plen, qlen = CURVES[curve]
+    _, plen, qlen = ALL_CURVES[curve]
     sg = np.ascontiguousarray(sigs, dtype=np.uint8).reshape(-1, 2 * qlen)
     n = sg.shape[0]
     pk = np.ascontiguousarray(pubkeys, dtype=np.uint8).reshape(n, 2 * plen)
@@ -152,7 +161,7 @@ def oracle_verify(curve: str, sigs, pubkeys, digests, hlen: int, nthreads: int =
 
 
 def oracle_sign(curve: str, privkeys, nonces, digests, hlen: int, nthreads: int = 8):
-    _, plen, qlen = CURVES[curve]
+    _, plen, qlen = ALL_CURVES[curve]
     d = np.ascontiguousarray(privkeys, dtype=np.uint8).reshape(-1, qlen)
     n = d.shape[0]
     k = np.ascontiguousarray(nonces, dtype=np.uint8).reshape(n, qlen)
@@ -174,7 +183,7 @@ def make_signatures(curve: str, n: int, tag: int = 0, hlen: int = 32, corrupt_ev
     produced with the oracle's deterministic signer; every `corrupt_every`-th tuple is corrupted in a way that
     rotates over {flip bit in r, in s, in digest, in key, r = 0, s >= q}.  Returns (sigs, pubs, digests, expected)
     where expected comes from the oracle's verifier."""
-    _, plen, qlen = CURVES[curve]
+    _, plen, qlen = ALL_CURVES[curve]
     d = random_scalars(curve, n, tag=1000 + tag)
     k = random_scalars(curve, n, tag=2000 + tag)
     dg = rng(3000 + tag).integers(0, 256, size=(n, hlen), dtype=np.uint8)

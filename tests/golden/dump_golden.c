@@ -34,7 +34,8 @@ static const char *curve_name(const ec_str_params *sp)
 static int wanted_curve(const ec_str_params *sp)
 {
 	const char *n = curve_name(sp);
-	return !strcmp(n, "SECP256R1") || !strcmp(n, "SECP384R1") || !strcmp(n, "FRP256V1");
+	return !strcmp(n, "SECP256R1") || !strcmp(n, "SECP384R1") || !strcmp(n, "FRP256V1") ||
+	       !strcmp(n, "BRAINPOOLP256R1") || !strcmp(n, "BRAINPOOLP384R1") || !strcmp(n, "SECP256K1");
 }
 
 static const char *hash_name(hash_alg_type t)

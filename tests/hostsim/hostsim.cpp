@@ -25,6 +25,9 @@ template <class Fn> static int dispatch(int curve_id, Fn &&fn)
 	case 4: return fn(Curve_SECP256R1());
 	case 1: return fn(Curve_FRP256V1());
 	case 5: return fn(Curve_SECP384R1());
+	case 8: return fn(Curve_BRAINPOOLP256R1());
+	case 12: return fn(Curve_BRAINPOOLP384R1());
+	case 19: return fn(Curve_SECP256K1());
 	default: return -1;
 	}
 }

@@ -6,7 +6,7 @@ import re
 
 import pytest
 
-from common import CURVES, ORDER, PRIME, ROOT, ref_lib
+from common import ALL_CURVES, CURVES, ORDER, PRIME, ROOT, ref_lib
 
 
 def parse_inc():
@@ -26,7 +26,7 @@ def parse_inc():
     return out
 
 
-@pytest.mark.parametrize("curve", list(CURVES))
+@pytest.mark.parametrize("curve", list(ALL_CURVES))
 def test_generated_constants(curve):
     inc = parse_inc()
     p, q = PRIME[curve], ORDER[curve]
@@ -41,7 +41,8 @@ def test_generated_constants(curve):
     gx, gy = c["GX"], c["GY"]
     assert c["GX_MONT"] == gx * R % p and c["GY_MONT"] == gy * R % p
     b = c["B_MONT"] * pow(R, -1, p) % p
-    assert (gy * gy - (gx ** 3 - 3 * gx + b)) % p == 0
+    a = c["A_MONT"] * pow(R, -1, p) % p
+    assert (gy * gy - (gx ** 3 + a * gx + b)) % p == 0
     ref = ref_lib()
     if ref is None:
         pytest.skip("compiled reference not available")
@@ -49,5 +50,5 @@ def test_generated_constants(curve):
     bufs = [ctypes.create_string_buffer(66) for _ in range(6)]
     assert ref.ref_curve_info(curve.encode(), ctypes.byref(plen), ctypes.byref(qlen), *bufs) == 0
     rp, rq, ra, rb, rgx, rgy = [int.from_bytes(x.raw[: plen.value], "big") for x in bufs]
-    assert (rp, rq, rgx, rgy, rb) == (p, q, gx, gy, b) and ra == p - 3
-    assert (plen.value, qlen.value) == CURVES[curve][1:]
+    assert (rp, rq, rgx, rgy, rb, ra) == (p, q, gx, gy, b, a)
+    assert (plen.value, qlen.value) == ALL_CURVES[curve][1:]

@@ -3,7 +3,7 @@ vectors and the oracle.  Bit-exact (integer/byte work): affine bytes, infinity f
 import numpy as np
 import pytest
 
-from common import (CURVES, HASHLEN, ORDER, PRIME, edge_scalars, golden, hx, make_signatures, oracle_smul,
+from common import (ALL_CURVES, CURVES, HASHLEN, ORDER, PRIME, edge_scalars, golden, hx, make_signatures, oracle_smul,
                     oracle_verify, random_scalars, rng)
 
 pytestmark = pytest.mark.gpu
@@ -23,11 +23,11 @@ def be(vals, nbytes):
     return np.frombuffer(b"".join(int(v).to_bytes(nbytes, "big") for v in vals), dtype=np.uint8).copy()
 
 
-@pytest.mark.parametrize("curve", list(CURVES))
+@pytest.mark.parametrize("curve", list(ALL_CURVES))
 def test_fp_mul_monty_against_integers(curve):
     """fp_mul_monty unit test in the pattern of src/arithmetic_tests (NN_MUL_REDC1 / FP_MUL_MONTY)."""
     eng = engine(curve, 8)
-    _, plen, _ = CURVES[curve]
+    _, plen, _ = ALL_CURVES[curve]
     g = rng(31)
     for which, mod in ((0, PRIME[curve]), (1, ORDER[curve])):
         a = [int.from_bytes(g.bytes(plen + 8), "big") % mod for _ in range(4096)] + [0, 1, mod - 1, mod - 1]
@@ -41,7 +41,7 @@ def test_fp_mul_monty_against_integers(curve):
 @pytest.mark.parametrize("curve", ["SECP256R1", "SECP384R1"])
 def test_ecccdh_kat(curve):
     """NIST ECC-CDH vectors (reference: src/tests/ecccdh_test_vectors.h:1501-2999)."""
-    _, plen, _ = CURVES[curve]
+    _, plen, _ = ALL_CURVES[curve]
     vecs = [v for v in golden("ecccdh_kat.json") if v["curve"] == curve]
     d = np.stack([hx(v["priv"]) for v in vecs]); peers = np.stack([hx(v["peer_pub"]) for v in vecs])
     for w in (8, 0):
@@ -51,7 +51,7 @@ def test_ecccdh_kat(curve):
     assert (st == 0).all() and [o[:plen].tobytes().hex() for o in out] == [v["shared"] for v in vecs]
 
 
-@pytest.mark.parametrize("curve", list(CURVES))
+@pytest.mark.parametrize("curve", list(ALL_CURVES))
 @pytest.mark.parametrize("w", [5, 8, 13, 0])
 def test_fixed_base_vs_oracle(curve, w):
     sc = np.concatenate([random_scalars(curve, 1024 if w else 4096, tag=41 + w, below_q=False), edge_scalars(curve)])
@@ -73,9 +73,9 @@ def test_fixed_base_wide_window_tables(curve, w):
     _engines.pop((curve, w)).close()   # give the table memory back
 
 
-@pytest.mark.parametrize("curve", list(CURVES))
+@pytest.mark.parametrize("curve", list(ALL_CURVES))
 def test_variable_base_vs_oracle(curve):
-    _, plen, qlen = CURVES[curve]
+    _, plen, qlen = ALL_CURVES[curve]
     base_sc = random_scalars(curve, 2048, tag=51)
     pts, st0 = oracle_smul(curve, base_sc)
     sc = random_scalars(curve, 2048, tag=52, below_q=False)
@@ -91,9 +91,12 @@ def test_variable_base_vs_oracle(curve):
     assert (out == want).all()
 
 
-@pytest.mark.parametrize("curve", ["SECP256R1", "SECP384R1"])
+WYCHE_CURVES = ["SECP256R1", "SECP384R1", "BRAINPOOLP256R1", "BRAINPOOLP384R1", "SECP256K1"]
+
+
+@pytest.mark.parametrize("curve", WYCHE_CURVES)
 def test_wycheproof_ecdh(curve):
-    _, plen, qlen = CURVES[curve]
+    _, plen, qlen = ALL_CURVES[curve]
     vecs = [v for v in golden("wycheproof_ecdh.json.gz") if v["curve"] == curve and len(v["priv"]) <= 2 * qlen]
     d = np.stack([hx(v["priv"].rjust(2 * qlen, "0")) for v in vecs]); q = np.stack([hx(v["peer_pub"]) for v in vecs])
     out, st = engine(curve).prj_pt_mul_batch(d, q)
@@ -109,13 +112,13 @@ def test_ecdsa_kat():
         assert engine(v["curve"]).ecdsa_verify_batch(hx(v["sig"]), hx(v["pub"]), bad, HASHLEN[v["hash"]])[0] == -1
 
 
-@pytest.mark.parametrize("curve", ["SECP256R1", "SECP384R1"])
+@pytest.mark.parametrize("curve", WYCHE_CURVES)
 def test_wycheproof_ecdsa_all(curve):
     """Every Wycheproof ECDSA vector the reference ships for the curve: verdict == the reference's own ec_verify."""
-    _, plen, qlen = CURVES[curve]
+    _, plen, qlen = ALL_CURVES[curve]
     vecs = [v for v in golden("wycheproof_ecdsa.json.gz")
             if v["curve"] == curve and len(v["sig"]) == 4 * qlen and len(v["pub"]) == 4 * plen]
-    assert len(vecs) > 1500
+    assert len(vecs) > 400
     for h in sorted({v["hash"] for v in vecs}):
         vs = [v for v in vecs if v["hash"] == h]
         sig = np.stack([hx(v["sig"]) for v in vs]); pub = np.stack([hx(v["pub"]) for v in vs])
@@ -127,7 +130,8 @@ def test_wycheproof_ecdsa_all(curve):
 
 @pytest.mark.parametrize("curve,hlen,w", [("FRP256V1", 32, 0), ("SECP256R1", 32, 0), ("SECP384R1", 48, 0),
                                           ("SECP256R1", 64, 13), ("SECP384R1", 20, 8), ("FRP256V1", 32, 16),
-                                          ("SECP256R1", 32, 18)])
+                                          ("SECP256R1", 32, 18), ("BRAINPOOLP256R1", 32, 0),
+                                          ("BRAINPOOLP384R1", 48, 13), ("SECP256K1", 32, 0)])
 def test_ecdsa_synthetic_with_corruptions(curve, hlen, w):
     """Includes comb windows that straddle 32-bit words (13, 18, default 22) and ones that do not (8, 16)."""
     sigs, pubs, dg, expected = make_signatures(curve, 512, tag=hlen, hlen=hlen, corrupt_every=8)
@@ -192,11 +196,11 @@ def test_full_size_batch_properties_and_sample():
     assert (out[idx] == want).all() and (st[idx] == wst).all()
 
 
-@pytest.mark.parametrize("curve", list(CURVES))
+@pytest.mark.parametrize("curve", list(ALL_CURVES))
 def test_ecdsa_scalar_preparation_mod_q(curve):
     """u = e*s^-1, v = r*s^-1 mod q on the device (nn_modinv / nn_mod_mul on the order, ecdsa_common.c:781-791)
     against Python integers, including digests longer and shorter than the order."""
-    _, plen, qlen = CURVES[curve]
+    _, plen, qlen = ALL_CURVES[curve]
     q = ORDER[curve]
     g = rng(81)
     for hlen in (20, qlen, 64):
@@ -225,8 +229,9 @@ def test_ecdsa_sign_batch_kat_and_oracle():
             continue
         sig, st = engine(v["curve"]).ecdsa_sign_batch(hx(v["priv"]), hx(v["nonce"]), hx(v["digest"]), HASHLEN[v["hash"]])
         assert st[0] == 0 and sig[0].tobytes().hex() == v["sig"], v["name"]
-    for curve, hlen in (("SECP256R1", 32), ("FRP256V1", 32), ("SECP384R1", 48), ("SECP256R1", 64)):
-        _, plen, qlen = CURVES[curve]
+    for curve, hlen in (("SECP256R1", 32), ("FRP256V1", 32), ("SECP384R1", 48), ("SECP256R1", 64),
+                        ("BRAINPOOLP256R1", 32), ("BRAINPOOLP384R1", 48), ("SECP256K1", 32)):
+        _, plen, qlen = ALL_CURVES[curve]
         q = ORDER[curve]
         n = 3000
         d = random_scalars(curve, n, tag=91); k = random_scalars(curve, n, tag=92)
@@ -243,14 +248,15 @@ def test_ecdsa_sign_batch_kat_and_oracle():
         assert (engine(curve).ecdsa_verify_batch(sig[4:], pubs, dg[4:], hlen) == 0).all()
 
 
-@pytest.mark.parametrize("curve", ["SECP256R1", "SECP384R1"])
+@pytest.mark.parametrize("curve", WYCHE_CURVES)
 def test_ecccdh_derive_batch(curve):
     """Row (f).2: batched ecccdh_derive_secret — NIST KATs and every uncompressed Wycheproof ECDH vector."""
-    _, plen, qlen = CURVES[curve]
+    _, plen, qlen = ALL_CURVES[curve]
     vecs = [v for v in golden("ecccdh_kat.json") if v["curve"] == curve]
-    sh, st = engine(curve).ecccdh_derive_batch(np.stack([hx(v["priv"]) for v in vecs]),
-                                               np.stack([hx(v["peer_pub"]) for v in vecs]))
-    assert (st == 0).all() and [s.tobytes().hex() for s in sh] == [v["shared"] for v in vecs]
+    if vecs:  # the NIST ECC-CDH KATs exist for the NIST curves only
+        sh, st = engine(curve).ecccdh_derive_batch(np.stack([hx(v["priv"]) for v in vecs]),
+                                                   np.stack([hx(v["peer_pub"]) for v in vecs]))
+        assert (st == 0).all() and [s.tobytes().hex() for s in sh] == [v["shared"] for v in vecs]
     vecs = [v for v in golden("wycheproof_ecdh.json.gz") if v["curve"] == curve and len(v["priv"]) <= 2 * qlen]
     sh, st = engine(curve).ecccdh_derive_batch(np.stack([hx(v["priv"].rjust(2 * qlen, "0")) for v in vecs]),
                                                np.stack([hx(v["peer_pub"]) for v in vecs]))
@@ -264,7 +270,7 @@ def test_ecccdh_derive_batch(curve):
 @pytest.mark.parametrize("curve", ["SECP256R1", "FRP256V1"])
 def test_layout_experiment_kernels_agree(curve):
     """the lane-striped (__shfl_sync) multiplier computes the same products as the production one."""
-    _, plen, _ = CURVES[curve]
+    _, plen, _ = ALL_CURVES[curve]
     p = PRIME[curve]
     g = rng(97)
     n = 4096

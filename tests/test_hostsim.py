@@ -4,7 +4,7 @@ the C ABI); it keeps kernel-algorithm bugs from costing GPU minutes and yields M
 import numpy as np
 import pytest
 
-from common import (CURVES, HASHLEN, ORDER, PRIME, edge_scalars, golden, hostsim_lib, hx, make_signatures,
+from common import (ALL_CURVES, CURVES, HASHLEN, ORDER, PRIME, edge_scalars, golden, hostsim_lib, hx, make_signatures,
                     oracle_smul, oracle_verify, random_scalars, rng, _buf)
 
 
@@ -22,11 +22,11 @@ def rand_mod(g, mod, n):
     return [int.from_bytes(g.bytes(nb + 8), "big") % mod for _ in range(n)]
 
 
-@pytest.mark.parametrize("curve", list(CURVES))
+@pytest.mark.parametrize("curve", list(ALL_CURVES))
 def test_field_ops_against_integers(curve):
     """Pattern of the reference's src/arithmetic_tests (FP_MUL_MONTY / FP_ADD / FP_SUB / FP_INV vs big ints)."""
     lib = hostsim_lib()
-    cid, plen, _ = CURVES[curve]
+    cid, plen, _ = ALL_CURVES[curve]
     g = rng(11)
     for which, mod in ((0, PRIME[curve]), (1, ORDER[curve])):
         n = 200
@@ -48,10 +48,10 @@ def test_field_ops_against_integers(curve):
     assert from_be(out, plen) == [pow(x, p - 2, p) for x in a]
 
 
-@pytest.mark.parametrize("curve", list(CURVES))
+@pytest.mark.parametrize("curve", list(ALL_CURVES))
 def test_group_law_including_exceptional_cases(curve):
     lib = hostsim_lib()
-    cid, plen, qlen = CURVES[curve]
+    cid, plen, qlen = ALL_CURVES[curve]
     q = ORDER[curve]
     ks = [1, 2, 3, 5, q - 1, q - 2, 7]
     pts, st = oracle_smul(curve, be(ks, qlen).reshape(-1, qlen))
@@ -76,11 +76,11 @@ def test_group_law_including_exceptional_cases(curve):
     o, s = op(2, zero, zero); assert s == 1                                          # dbl(inf) = inf
 
 
-@pytest.mark.parametrize("curve", list(CURVES))
+@pytest.mark.parametrize("curve", list(ALL_CURVES))
 @pytest.mark.parametrize("w", [4, 6])
 def test_scalar_mult_matches_oracle(curve, w):
     lib = hostsim_lib()
-    cid, plen, qlen = CURVES[curve]
+    cid, plen, qlen = ALL_CURVES[curve]
     sc = np.concatenate([random_scalars(curve, 16, tag=21, below_q=False), edge_scalars(curve)])
     n = sc.shape[0]
     want, wst = oracle_smul(curve, sc)
@@ -101,7 +101,7 @@ def test_scalar_mult_matches_oracle(curve, w):
 @pytest.mark.parametrize("curve", ["SECP256R1", "SECP384R1"])
 def test_ecccdh_kat(curve):
     lib = hostsim_lib()
-    cid, plen, qlen = CURVES[curve]
+    cid, plen, qlen = ALL_CURVES[curve]
     vecs = [v for v in golden("ecccdh_kat.json") if v["curve"] == curve]
     d = np.stack([hx(v["priv"]) for v in vecs]); peers = np.stack([hx(v["peer_pub"]) for v in vecs])
     n = len(vecs)
@@ -115,13 +115,13 @@ def test_ecccdh_kat(curve):
 def test_ecdsa_verify_core_kat_and_wycheproof_sample():
     lib = hostsim_lib()
     for v in golden("ecdsa_kat.json"):
-        cid, plen, qlen = CURVES[v["curve"]]
+        cid, plen, qlen = ALL_CURVES[v["curve"]]
         out = np.zeros(1, dtype=np.int8)
         lib.hostsim_ecdsa_verify_batch(cid, 4, 1, _buf(hx(v["sig"])), _buf(hx(v["pub"])), _buf(hx(v["digest"])),
                                        HASHLEN[v["hash"]], _buf(out))
         assert out[0] == 0, v["name"]
-    for curve in ("SECP256R1", "SECP384R1"):
-        cid, plen, qlen = CURVES[curve]
+    for curve in ("SECP256R1", "SECP384R1", "BRAINPOOLP256R1", "SECP256K1"):
+        cid, plen, qlen = ALL_CURVES[curve]
         vecs = [v for v in golden("wycheproof_ecdsa.json.gz")
                 if v["curve"] == curve and len(v["sig"]) == 4 * qlen and len(v["pub"]) == 4 * plen]
         vecs = vecs[::4]  # a quarter on the CPU; the GPU tests run all of them
@@ -139,7 +139,7 @@ def test_ecdsa_verify_frp256v1_synthetic():
     """FRP256V1 has q > p: exercises the 'candidate r >= p' branch; corrupted tuples must be rejected."""
     lib = hostsim_lib()
     curve = "FRP256V1"
-    cid, plen, qlen = CURVES[curve]
+    cid, plen, qlen = ALL_CURVES[curve]
     sigs, pubs, dg, expected = make_signatures(curve, 48, tag=5, corrupt_every=4)
     got = np.zeros(48, dtype=np.int8)
     lib.hostsim_ecdsa_verify_batch(cid, 4, 48, _buf(sigs), _buf(pubs), _buf(dg), 32, _buf(got))
@@ -150,7 +150,7 @@ def test_ecdsa_verify_frp256v1_synthetic():
 def test_multiplication_counts():
     """M_impl: field multiplications of the implemented algorithms, counted in this host build."""
     lib = hostsim_lib()
-    cid, plen, qlen = CURVES["SECP256R1"]
+    cid, plen, qlen = ALL_CURVES["SECP256R1"]
     sc = random_scalars("SECP256R1", 1, tag=9)
     out = np.zeros(64, dtype=np.uint8); st = np.zeros(1, dtype=np.int8)
     lib.hostsim_prj_pt_mul_batch(cid, 8, 1, _buf(sc), None, _buf(out), _buf(st))

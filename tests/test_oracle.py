@@ -6,7 +6,7 @@ import ctypes
 import numpy as np
 import pytest
 
-from common import (CURVES, HASHLEN, ORDER, edge_scalars, golden, hx, oracle_lib, oracle_sign, oracle_smul,
+from common import (ALL_CURVES, CURVES, HASHLEN, ORDER, edge_scalars, golden, hx, oracle_lib, oracle_sign, oracle_smul,
                     oracle_verify, random_scalars, ref_lib, _buf)
 
 
@@ -14,7 +14,7 @@ from common import (CURVES, HASHLEN, ORDER, edge_scalars, golden, hx, oracle_lib
 def test_ecccdh_kat_fixed_and_variable_base(curve):
     vecs = [v for v in golden("ecccdh_kat.json") if v["curve"] == curve]
     assert len(vecs) == 25
-    _, plen, qlen = CURVES[curve]
+    _, plen, qlen = ALL_CURVES[curve]
     d = np.stack([hx(v["priv"]) for v in vecs])
     out, st = oracle_smul(curve, d)
     assert (st == 0).all()
@@ -29,7 +29,7 @@ def test_ecccdh_kat_fixed_and_variable_base(curve):
 
 def test_ecdsa_kat_verify_and_sign():
     vecs = golden("ecdsa_kat.json")
-    assert {v["curve"] for v in vecs} == {"SECP256R1", "SECP384R1", "FRP256V1"}
+    assert {v["curve"] for v in vecs} >= {"SECP256R1", "SECP384R1", "FRP256V1", "BRAINPOOLP256R1"}
     for v in vecs:
         curve, hlen = v["curve"], HASHLEN[v["hash"]]
         assert v["ref_verdict"] == 0
@@ -43,11 +43,14 @@ def test_ecdsa_kat_verify_and_sign():
             assert st[0] == 0 and sig[0].tobytes().hex() == v["sig"], v["name"]
 
 
-@pytest.mark.parametrize("curve", ["SECP256R1", "SECP384R1"])
+WYCHE_CURVES = ["SECP256R1", "SECP384R1", "BRAINPOOLP256R1", "BRAINPOOLP384R1", "SECP256K1"]
+
+
+@pytest.mark.parametrize("curve", WYCHE_CURVES)
 def test_wycheproof_ecdsa_matches_reference_verdicts(curve):
-    _, plen, qlen = CURVES[curve]
+    _, plen, qlen = ALL_CURVES[curve]
     vecs = [v for v in golden("wycheproof_ecdsa.json.gz") if v["curve"] == curve]
-    assert len(vecs) > 1500
+    assert len(vecs) > 400
     by_h = {}
     for v in vecs:
         by_h.setdefault(v["hash"], []).append(v)
@@ -72,14 +75,14 @@ def test_wycheproof_ecdsa_matches_reference_verdicts(curve):
             if v["expected"] == -1:
                 assert g == -1
         checked += len(ok_len)
-    assert checked > 1500
+    assert checked > 400
 
 
-@pytest.mark.parametrize("curve", ["SECP256R1", "SECP384R1"])
+@pytest.mark.parametrize("curve", WYCHE_CURVES)
 def test_wycheproof_ecdh_points(curve):
-    _, plen, qlen = CURVES[curve]
+    _, plen, qlen = ALL_CURVES[curve]
     vecs = [v for v in golden("wycheproof_ecdh.json.gz") if v["curve"] == curve and len(v["priv"]) <= 2 * qlen]
-    assert len(vecs) > 400
+    assert len(vecs) > 200
     d = np.stack([hx(v["priv"].rjust(2 * qlen, "0")) for v in vecs])
     q = np.stack([hx(v["peer_pub"]) for v in vecs])
     out, st = oracle_smul(curve, d, q)
@@ -90,12 +93,12 @@ def test_wycheproof_ecdh_points(curve):
             assert o[:plen].tobytes().hex() == v["shared"].rjust(2 * plen, "0")
 
 
-@pytest.mark.parametrize("curve", list(CURVES))
+@pytest.mark.parametrize("curve", list(ALL_CURVES))
 def test_oracle_vs_compiled_reference_random_and_edges(curve):
     ref = ref_lib()
     if ref is None:
         pytest.skip("oracle/_ref/libecc_ref.so not built (needs /root/reference)")
-    _, plen, qlen = CURVES[curve]
+    _, plen, qlen = ALL_CURVES[curve]
     sc = np.concatenate([random_scalars(curve, 24, tag=7, below_q=False), edge_scalars(curve)])
     o1, s1 = oracle_smul(curve, sc)
     o2, s2 = oracle_smul(curve, sc, lib=ref)

@@ -34,6 +34,28 @@ CURVES = {
         0xffffffffffffffffffffffffffffffffffffffffffffffffc7634d81f4372ddf581a0db248b0a77aecec196accc52973,
         0xaa87ca22be8b05378eb1c71ef320ad746e1d3b628ba79b9859f741e082542a385502f25dbf55296c3a545e3872760ab7,
         0x3617de4a96262c6f5d9e98bf9292dc29f8f41dbd289a147ce9da3113b5f0b8c00a60b1ce1d7e819d7a431d7c90ea0e5f),
+    # generic-a (Brainpool) and a = 0 (secp256k1) curves: the "other short-Weierstrass curves" row
+    "BRAINPOOLP256R1": (8,
+        0xa9fb57dba1eea9bc3e660a909d838d726e3bf623d52620282013481d1f6e5377,
+        0x7d5a0975fc2c3057eef67530417affe7fb8055c126dc5c6ce94a4b44f330b5d9,
+        0x26dc5c6ce94a4b44f330b5d9bbd77cbf958416295cf7e1ce6bccdc18ff8c07b6,
+        0xa9fb57dba1eea9bc3e660a909d838d718c397aa3b561a6f7901e0e82974856a7,
+        0x8bd2aeb9cb7e57cb2c4b482ffc81b7afb9de27e1e3bd23c23a4453bd9ace3262,
+        0x547ef835c3dac4fd97f8461a14611dc9c27745132ded8e545c1d54c72f046997),
+    "BRAINPOOLP384R1": (12,
+        0x8cb91e82a3386d280f5d6f7e50e641df152f7109ed5456b412b1da197fb71123acd3a729901d1a71874700133107ec53,
+        0x7bc382c63d8c150c3c72080ace05afa0c2bea28e4fb22787139165efba91f90f8aa5814a503ad4eb04a8c7dd22ce2826,
+        0x04a8c7dd22ce28268b39b55416f0447c2fb77de107dcd2a62e880ea53eeb62d57cb4390295dbc9943ab78696fa504c11,
+        0x8cb91e82a3386d280f5d6f7e50e641df152f7109ed5456b31f166e6cac0425a7cf3ab6af6b7fc3103b883202e9046565,
+        0x1d1c64f068cf45ffa2a63a81b7c13f6b8847a3e77ef14fe3db7fcafe0cbd10e8e826e03436d646aaef87b2e247d4af1e,
+        0x8abe1d7520f9c2a45cb1eb8e95cfd55262b70b29feec5864e19c054ff99129280e4646217791811142820341263c5315),
+    "SECP256K1": (19,
+        0xfffffffffffffffffffffffffffffffffffffffffffffffffffffffefffffc2f,
+        0x0,
+        0x7,
+        0xfffffffffffffffffffffffffffffffebaaedce6af48a03bbfd25e8cd0364141,
+        0x79be667ef9dcbbac55a06295ce870b07029bfcdb2dce28d959f2815b16f81798,
+        0x483ada7726a3c4655da4fbfc0e1108a8fd17b448a68554199c47d08ffb10d4b8),
 }
 
 
@@ -62,7 +84,7 @@ def main():
     for name, (cid, p, a, b, q, gx, gy) in CURVES.items():
         n = (p.bit_length() + 31) // 32
         assert (q.bit_length() + 31) // 32 == n
-        assert a == p - 3, "device formulas assume a = -3"
+        a_kind = 0 if a == p - 3 else (1 if a == 0 else 2)   # selects the doubling formula in ec.cuh
         assert (gy * gy - (gx ** 3 + a * gx + b)) % p == 0
         R = 1 << (32 * n)
         lines += field_block("Fp_%s" % name, p, n)
@@ -75,6 +97,8 @@ def main():
         lines.append("    static constexpr int PLEN = %d;  /* bytes of p */" % ((p.bit_length() + 7) // 8))
         lines.append("    static constexpr int QLEN = %d;  /* bytes of q */" % ((q.bit_length() + 7) // 8))
         lines.append("    static constexpr int QBITS = %d;" % q.bit_length())
+        lines.append("    static constexpr int A_KIND = %d;  /* 0: a = -3, 1: a = 0, 2: generic a */" % a_kind)
+        lines.append("    ECC_CONST_ARRAY(A_MONT, %d, %s);   /* a*R mod p */" % (n, words(a * R % p, n)))
         lines.append("    static const char *name() { return \"%s\"; }" % name)
         lines.append("    ECC_CONST_ARRAY(B_MONT, %d, %s);   /* b*R mod p */" % (n, words(b * R % p, n)))
         lines.append("    ECC_CONST_ARRAY(GX_MONT, %d, %s);  /* Gx*R mod p */" % (n, words(gx * R % p, n)))
