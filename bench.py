@@ -45,6 +45,9 @@ WORKLOADS = {
     "secp256r1_variable_base": ("SECP256R1", "var", "secp256r1 variable-base prj_pt_mul/sec", "prj_pt_mul/s"),
     "frp256v1_ecdsa_verify": ("FRP256V1", "verify", "frp256v1 ECDSA ec_verify/sec", "ec_verify/s"),
     "secp256r1_ecdsa_verify": ("SECP256R1", "verify", "secp256r1 ECDSA ec_verify/sec", "ec_verify/s"),
+    "brainpoolp256r1_fixed_base": ("BRAINPOOLP256R1", "fixed", "brainpoolp256r1 prj_pt_mul/sec", "prj_pt_mul/s"),
+    "brainpoolp256r1_ecdsa_verify": ("BRAINPOOLP256R1", "verify", "brainpoolp256r1 ECDSA ec_verify/sec", "ec_verify/s"),
+    "secp256k1_fixed_base": ("SECP256K1", "fixed", "secp256k1 prj_pt_mul/sec", "prj_pt_mul/s"),
 }
 SEED = 0x6C69626563632D31
 
@@ -116,7 +119,7 @@ class ClockSampler(threading.Thread):
 
 def make_inputs(workload: str, n: int, rank: int, use_gpu: bool = True):
     """Seeded synthetic inputs of SURVEY.md §8d for one rank (host numpy arrays)."""
-    from common import CURVES, ORDER, edge_scalars
+    from common import ALL_CURVES as CURVES, ORDER, edge_scalars
     curve, kind, _, _ = WORKLOADS[workload]
     _, plen, qlen = CURVES[curve]
     q = ORDER[curve]
@@ -163,7 +166,7 @@ def make_verify_inputs(curve: str, n: int, rank: int, use_gpu: bool = True):
     Ours arm: keys and signatures come from the engine's own batch signer (eccb200_ecdsa_sign_batch: d*G for the
     keys, then r, s), and a 2^12 sample is cross-checked with the oracle's signer and verifier.  Reference arm (no
     GPU): the oracle's signer on a 2^12 pool, tiled."""
-    from common import CURVES, ORDER, make_signatures, oracle_sign, oracle_verify
+    from common import ALL_CURVES as CURVES, ORDER, make_signatures, oracle_sign, oracle_verify
     _, plen, qlen = CURVES[curve]
     hlen = 32
     if not use_gpu:
@@ -215,7 +218,7 @@ def ref_lib():
 def cpu_run(workload: str, inputs, lo: int, cnt: int, threads: int):
     """Runs items [lo, lo+cnt) of the workload on the reference (or the oracle port) with `threads` host threads.
     Returns (seconds, kind, outputs)."""
-    from common import CURVES, oracle_lib
+    from common import ALL_CURVES as CURVES, oracle_lib
     curve, kind, _, _ = WORKLOADS[workload]
     _, plen, qlen = CURVES[curve]
     ref = ref_lib()
@@ -338,7 +341,7 @@ def main():
     import torch
     import torch.distributed as dist
     import libecc_b200
-    from common import CURVES
+    from common import ALL_CURVES as CURVES
     from libecc_b200.sharding import gather_results
 
     torch.cuda.set_device(local_rank)

@@ -6,13 +6,17 @@ import ctypes
 import math
 
 # one Montgomery CIOS product of n 64-bit limbs = 2n^2+n wide multiply-accumulates, each = 4 32x32->64 IMADs
-IMAD32_PER_MUL = {"SECP256R1": (2 * 4 * 4 + 4) * 4, "FRP256V1": (2 * 4 * 4 + 4) * 4, "SECP384R1": (2 * 6 * 6 + 6) * 4}
+IMAD32_PER_MUL = {"SECP256R1": (2 * 4 * 4 + 4) * 4, "FRP256V1": (2 * 4 * 4 + 4) * 4, "SECP384R1": (2 * 6 * 6 + 6) * 4,
+                  "BRAINPOOLP256R1": 144, "SECP256K1": 144, "BRAINPOOLP384R1": 312}
 # IMAD.WIDE instructions the generated code really issues per product, averaged over a mixed addition (8 mul + 3 sqr;
 # tools/gen_fp_ptx.py: P-256 mul 96 / sqr 68, generic 256-bit 136 / 108, P-384 276 / 210 incl. the m_i products)
 IMAD_EXECUTED_PER_MUL = {"SECP256R1": (8 * 96 + 3 * 68) / 11, "FRP256V1": (8 * 136 + 3 * 108) / 11,
-                         "SECP384R1": (8 * 276 + 3 * 210) / 11}
-M_REF = {"SECP256R1": 8724, "FRP256V1": 8724, "SECP384R1": 13076}   # reference ladder (probe)
-QBITS = {"SECP256R1": 256, "FRP256V1": 256, "SECP384R1": 384}
+                         "SECP384R1": (8 * 276 + 3 * 210) / 11, "BRAINPOOLP256R1": (8 * 136 + 3 * 108) / 11,
+                         "SECP256K1": (8 * 136 + 3 * 108) / 11, "BRAINPOOLP384R1": (8 * 300 + 3 * 234) / 11}
+M_REF = {"SECP256R1": 8724, "FRP256V1": 8724, "SECP384R1": 13076,   # reference ladder (probe)
+         "BRAINPOOLP256R1": 8724, "SECP256K1": 8724, "BRAINPOOLP384R1": 13076}
+QBITS = {"SECP256R1": 256, "FRP256V1": 256, "SECP384R1": 384, "BRAINPOOLP256R1": 256, "SECP256K1": 256,
+         "BRAINPOOLP384R1": 384}
 
 
 def work_per_item(workload: str, comb_window: int):

@@ -83,8 +83,8 @@ static int run_direct(const char *dropin_path)
 		printf("FAIL missing drop-in symbols\n");
 		return 1;
 	}
-	const char *names[3] = { "SECP256R1", "FRP256V1", "SECP384R1" };
-	for (int c = 0; c < 3; c++) {
+	const char *names[5] = { "SECP256R1", "FRP256V1", "SECP384R1", "BRAINPOOLP256R1", "SECP256K1" };
+	for (int c = 0; c < 5; c++) {
 		ec_params params;
 		CHECK(!load_params(&params, names[c]), "import_params %s", names[c]);
 		u8 qlen = (u8)BYTECEIL(params.ec_gen_order_bitlen);
@@ -210,8 +210,8 @@ static int run_preload(void)
 		return 1;
 	}
 	unsigned long long c0 = calls();
-	const char *names[3] = { "SECP256R1", "FRP256V1", "SECP384R1" };
-	for (int c = 0; c < 3; c++) {
+	const char *names[5] = { "SECP256R1", "FRP256V1", "SECP384R1", "BRAINPOOLP256R1", "SECP256K1" };
+	for (int c = 0; c < 5; c++) {
 		ec_params params;
 		CHECK(!load_params(&params, names[c]), "import_params");
 		u8 qlen = (u8)BYTECEIL(params.ec_gen_order_bitlen);
@@ -237,7 +237,7 @@ static int run_preload(void)
 	}
 	unsigned long long used = calls() - c0;
 	printf("preload: %llu prj_pt_mul calls served by the GPU drop-in\n", used);
-	CHECK(used >= 3 * (6 * 4 + 4), "too few interposed calls (%llu): the reference did not go through the drop-in", used);
+	CHECK(used >= 5 * (6 * 4 + 4), "too few interposed calls (%llu): the reference did not go through the drop-in", used);
 	return failures != 0;
 }
 
