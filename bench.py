@@ -48,6 +48,9 @@ WORKLOADS = {
     "brainpoolp256r1_fixed_base": ("BRAINPOOLP256R1", "fixed", "brainpoolp256r1 prj_pt_mul/sec", "prj_pt_mul/s"),
     "brainpoolp256r1_ecdsa_verify": ("BRAINPOOLP256R1", "verify", "brainpoolp256r1 ECDSA ec_verify/sec", "ec_verify/s"),
     "secp256k1_fixed_base": ("SECP256K1", "fixed", "secp256k1 prj_pt_mul/sec", "prj_pt_mul/s"),
+    "secp521r1_fixed_base": ("SECP521R1", "fixed", "secp521r1 prj_pt_mul/sec", "prj_pt_mul/s"),
+    "secp521r1_variable_base": ("SECP521R1", "var", "secp521r1 prj_pt_mul/sec (variable base)", "prj_pt_mul/s"),
+    "secp521r1_ecdsa_verify": ("SECP521R1", "verify", "secp521r1 ECDSA ec_verify/sec", "ec_verify/s"),
 }
 SEED = 0x6C69626563632D31
 
@@ -124,6 +127,7 @@ def make_inputs(workload: str, n: int, rank: int, use_gpu: bool = True):
     _, plen, qlen = CURVES[curve]
     q = ORDER[curve]
     raw = splitmix_bytes(n * qlen, 100 + rank).reshape(n, qlen)
+    raw[:, 0] &= (1 << (q.bit_length() - 8 * (qlen - 1))) - 1   # bitlen(q) need not be a multiple of 8 (P-521)
     # uniform in [1, q-1]: clear the top bit pattern that could exceed q cheaply (rejection on the few rows >= q)
     vals_hi = raw[:, 0].astype(np.int64)
     qb = np.frombuffer(q.to_bytes(qlen, "big"), dtype=np.uint8)
@@ -132,6 +136,7 @@ def make_inputs(workload: str, n: int, rank: int, use_gpu: bool = True):
     for i in suspicious:
         while not (0 < int.from_bytes(raw[i].tobytes(), "big") < q):
             raw[i] = g.integers(0, 256, size=qlen, dtype=np.uint8)
+            raw[i, 0] &= (1 << (q.bit_length() - 8 * (qlen - 1))) - 1
     # ~0.1 % adversarial slots: k in {0, 1, 2, q-1, q, q+1, 2^(8 qlen)-1, ...}
     es = edge_scalars(curve)
     slots = np.arange(0, n, 1024)[: max(1, n // 1024)]
@@ -148,9 +153,10 @@ def make_points(curve: str, n: int, rank: int) -> np.ndarray:
     """n distinct valid affine points: produced by the engine's own fixed-base path from seeded scalars and
     spot-checked against the oracle (the reference would need minutes for 2^20 points)."""
     import libecc_b200
-    from common import oracle_smul, random_scalars
-    sc = splitmix_bytes(n * 32 if curve != "SECP384R1" else n * 48, 300 + rank).reshape(n, -1)
-    sc[:, 0] &= 0x7F
+    from common import ALL_CURVES, ORDER, oracle_smul
+    qlen = ALL_CURVES[curve][2]
+    sc = splitmix_bytes(n * qlen, 300 + rank).reshape(n, qlen)
+    sc[:, 0] &= ((1 << (ORDER[curve].bit_length() - 8 * (qlen - 1))) - 1) >> 1   # < q without rejection
     eng = libecc_b200.Engine(curve, device=int(os.environ.get("LOCAL_RANK", 0)))
     pts, st = eng.prj_pt_mul_batch(sc)
     assert (st == 0).all()
@@ -180,8 +186,9 @@ def make_verify_inputs(curve: str, n: int, rank: int, use_gpu: bool = True):
     q = ORDER[curve]
     d = splitmix_bytes(n * qlen, 600 + rank).reshape(n, qlen)
     k = splitmix_bytes(n * qlen, 700 + rank).reshape(n, qlen)
-    d[:, 0] &= 0x7F
-    k[:, 0] &= 0x7F
+    safe = ((1 << (q.bit_length() - 8 * (qlen - 1))) - 1) >> 1   # 0x7F for byte-aligned orders, 0 for P-521
+    d[:, 0] &= safe
+    k[:, 0] &= safe
     d[:, -1] |= 1
     k[:, -1] |= 1                                   # in [1, q-1]: top bit clear, never zero
     dg = splitmix_bytes(n * hlen, 800 + rank).reshape(n, hlen)

@@ -33,6 +33,7 @@ extern "C" {
 #define ECCB200_BRAINPOOLP256R1 8
 #define ECCB200_BRAINPOOLP384R1 12
 #define ECCB200_SECP256K1 19
+#define ECCB200_SECP521R1 6
 
 /* Per-item status codes written by the batch calls. */
 #define ECCB200_OK 0        /* finite result / valid signature                                          */

@@ -26,12 +26,13 @@ constexpr uint64_t kFpMagic = 0x14e96c8ab28221efULL;     /* fp/fp.c:127 */
 constexpr uint64_t kNnMagic = 0xb4cf5d56e2023316ULL ^ (uint64_t)(ECCB200_NN_MAX_WORD_LEN + 64); /* nn/nn.c:28 */
 constexpr uint64_t kPubKeyMagic = 0x31327f37741ffb76ULL; /* sig/ec_key.h:118 */
 constexpr int kMaxWords = ECCB200_NN_MAX_WORD_LEN;
-constexpr int kNumCurves = 6;
+constexpr int kNumCurves = 7;
 
 struct CurveInfo {
 	int id;
 	int n64;              /* 64-bit limbs of p / q */
-	uint64_t p[6], q[6], gx[6], gy[6];
+	int plen, qlen;       /* wire bytes of a field element / of a scalar (BYTECEIL of the bit lengths) */
+	uint64_t p[9], q[9], gx[9], gy[9];
 };
 
 template <class C> CurveInfo make_info()
@@ -40,6 +41,8 @@ template <class C> CurveInfo make_info()
 	memset(&ci, 0, sizeof(ci));
 	ci.id = C::ID;
 	ci.n64 = C::N / 2;
+	ci.plen = C::PLEN;
+	ci.qlen = C::QLEN;
 	for (int i = 0; i < C::N / 2; i++) {
 		ci.p[i] = ((uint64_t)C::Fp::P(2 * i + 1) << 32) | C::Fp::P(2 * i);
 		ci.q[i] = ((uint64_t)C::Fq::P(2 * i + 1) << 32) | C::Fq::P(2 * i);
@@ -53,7 +56,8 @@ const CurveInfo *curves()
 {
 	static const CurveInfo tab[kNumCurves] = { make_info<Curve_SECP256R1>(),       make_info<Curve_FRP256V1>(),
 						    make_info<Curve_SECP384R1>(),       make_info<Curve_BRAINPOOLP256R1>(),
-						    make_info<Curve_BRAINPOOLP384R1>(), make_info<Curve_SECP256K1>() };
+						    make_info<Curve_BRAINPOOLP384R1>(), make_info<Curve_SECP256K1>(),
+						    make_info<Curve_SECP521R1>() };
 	return tab;
 }
 
@@ -101,11 +105,17 @@ eccb200_ctx *engine_for(int curve_id)
 	return g_ctx[curve_id];
 }
 
+/* little-endian 64-bit words -> len big-endian bytes (nn_export_to_buf, nn/nn.c:511) */
+void words_to_be(uint8_t *out, int len, const uint64_t *w)
+{
+	for (int j = 0; j < len; j++) out[len - 1 - j] = (uint8_t)(w[j / 8] >> (8 * (j % 8)));
+}
+
 /* m mod q -> big-endian qlen bytes.  Plain binary long division on 64-bit words (nn_mod, nn/nn_div.c:1005). */
 void scalar_mod_to_be(uint8_t *out, const eccb200_nn *m, const CurveInfo *ci)
 {
 	const int n = ci->n64;
-	uint64_t r[7] = { 0 };
+	uint64_t r[10] = { 0 };
 	int top = m->wlen > kMaxWords ? kMaxWords : m->wlen;
 	for (int wi = top - 1; wi >= 0; wi--) {
 		for (int b = 63; b >= 0; b--) {
@@ -137,14 +147,15 @@ void scalar_mod_to_be(uint8_t *out, const eccb200_nn *m, const CurveInfo *ci)
 			}
 		}
 	}
-	for (int i = 0; i < n; i++)
-		for (int b = 0; b < 8; b++) out[8 * (n - 1 - i) + b] = (uint8_t)(r[i] >> (8 * (7 - b)));
+	words_to_be(out, ci->qlen, r);
 }
 
-void fp_to_be(uint8_t *out, const eccb200_fp *a, int n64)
+void fp_to_be(uint8_t *out, const eccb200_fp *a, int len) { words_to_be(out, len, a->fp_val.val); }
+
+void gen_to_be(uint8_t *pp, const CurveInfo *ci)
 {
-	for (int i = 0; i < n64; i++)
-		for (int b = 0; b < 8; b++) out[8 * (n64 - 1 - i) + b] = (uint8_t)(a->fp_val.val[i] >> (8 * (7 - b)));
+	words_to_be(pp, ci->plen, ci->gx);
+	words_to_be(pp + ci->plen, ci->plen, ci->gy);
 }
 
 bool fp_is_small(const eccb200_fp *a, uint64_t v)
@@ -155,16 +166,12 @@ bool fp_is_small(const eccb200_fp *a, uint64_t v)
 	return true;
 }
 
-void fp_set_be(eccb200_fp *dst, const eccb200_fp *tmpl, const uint8_t *be, int n64)
+void fp_set_be(eccb200_fp *dst, const eccb200_fp *tmpl, const uint8_t *be, int len)
 {
 	*dst = *tmpl; /* ctx pointer, magics */
 	memset(dst->fp_val.val, 0, sizeof(dst->fp_val.val));
 	if (be) {
-		for (int i = 0; i < n64; i++) {
-			uint64_t w = 0;
-			for (int b = 0; b < 8; b++) w = (w << 8) | be[8 * (n64 - 1 - i) + b];
-			dst->fp_val.val[i] = w;
-		}
+		for (int j = 0; j < len; j++) dst->fp_val.val[j / 8] |= (uint64_t)be[len - 1 - j] << (8 * (j % 8));
 	}
 	dst->fp_val.magic = kNnMagic;
 	dst->fp_val.wlen = tmpl->ctx->p.wlen; /* elements carry the word length of p (fp_init, fp/fp.c:139) */
@@ -200,9 +207,9 @@ int mul_batch(eccb200_prj_pt *out, const eccb200_nn *m, const eccb200_prj_pt *in
 	}
 	eccb200_ctx *eng = engine_for(ci->id);
 	if (!eng) return -1;
-	const int n64 = ci->n64;
-	const size_t plen = 8 * (size_t)n64;
-	std::vector<uint8_t> scalars(n * plen), points(n * 2 * plen), outb(n * 2 * plen);
+	const size_t plen = (size_t)ci->plen, qlen = (size_t)ci->qlen;
+	const int pl = ci->plen;
+	std::vector<uint8_t> scalars(n * qlen), points(n * 2 * plen), outb(n * 2 * plen);
 	std::vector<int8_t> status(n);
 	/* 1. inputs with Z != 1 are normalised on the device first (batched prj_pt_unique) */
 	std::vector<uint32_t> prj_idx;
@@ -217,9 +224,9 @@ int mul_batch(eccb200_prj_pt *out, const eccb200_nn *m, const eccb200_prj_pt *in
 		std::vector<int8_t> st(prj_idx.size());
 		for (size_t k = 0; k < prj_idx.size(); k++) {
 			const eccb200_prj_pt *p = &in[prj_idx[k]];
-			fp_to_be(&pb[k * 3 * plen], &p->X, n64);
-			fp_to_be(&pb[k * 3 * plen + plen], &p->Y, n64);
-			fp_to_be(&pb[k * 3 * plen + 2 * plen], &p->Z, n64);
+			fp_to_be(&pb[k * 3 * plen], &p->X, pl);
+			fp_to_be(&pb[k * 3 * plen + plen], &p->Y, pl);
+			fp_to_be(&pb[k * 3 * plen + 2 * plen], &p->Z, pl);
 		}
 		if (eccb200_prj_pt_unique_batch(eng, (uint32_t)prj_idx.size(), pb.data(), ab.data(), st.data())) return -1;
 		for (size_t k = 0; k < prj_idx.size(); k++) {
@@ -231,42 +238,27 @@ int mul_batch(eccb200_prj_pt *out, const eccb200_nn *m, const eccb200_prj_pt *in
 	}
 	for (uint32_t i = 0; i < n; i++) {
 		if (rc[i]) {
-			memset(&scalars[i * plen], 0, plen);
+			memset(&scalars[i * qlen], 0, qlen);
 			continue;
 		}
-		scalar_mod_to_be(&scalars[i * plen], &m[i], ci);
+		scalar_mod_to_be(&scalars[i * qlen], &m[i], ci);
 		if (fp_is_small(&in[i].Z, 1)) {
-			fp_to_be(&points[i * 2 * plen], &in[i].X, n64);
-			fp_to_be(&points[i * 2 * plen + plen], &in[i].Y, n64);
+			fp_to_be(&points[i * 2 * plen], &in[i].X, pl);
+			fp_to_be(&points[i * 2 * plen + plen], &in[i].Y, pl);
 		}
 		if (is_inf[i]) { /* any valid point works as a placeholder; the result is forced to infinity below */
-			uint8_t *pp = &points[i * 2 * plen];
-			for (int k = 0; k < n64; k++)
-				for (int b = 0; b < 8; b++) {
-					pp[8 * (n64 - 1 - k) + b] = (uint8_t)(ci->gx[k] >> (8 * (7 - b)));
-					pp[plen + 8 * (n64 - 1 - k) + b] = (uint8_t)(ci->gy[k] >> (8 * (7 - b)));
-				}
-			memset(&scalars[i * plen], 0, plen);
+			gen_to_be(&points[i * 2 * plen], ci);
+			memset(&scalars[i * qlen], 0, qlen);
 		}
 		/* fixed-base fast path only when every base is the generator */
-		const uint8_t *pp = &points[i * 2 * plen];
-		for (int k = 0; k < n64 && all_gen; k++)
-			for (int b = 0; b < 8; b++)
-				if (pp[8 * (n64 - 1 - k) + b] != (uint8_t)(ci->gx[k] >> (8 * (7 - b))) ||
-				    pp[plen + 8 * (n64 - 1 - k) + b] != (uint8_t)(ci->gy[k] >> (8 * (7 - b)))) {
-					all_gen = false;
-					break;
-				}
+		if (all_gen) {
+			uint8_t gb[2 * 72];
+			gen_to_be(gb, ci);
+			if (memcmp(gb, &points[i * 2 * plen], 2 * plen)) all_gen = false;
+		}
 	}
 	for (uint32_t i = 0; i < n; i++)
-		if (rc[i]) { /* keep the batch launchable: give rejected slots the generator */
-			uint8_t *pp = &points[i * 2 * plen];
-			for (int k = 0; k < n64; k++)
-				for (int b = 0; b < 8; b++) {
-					pp[8 * (n64 - 1 - k) + b] = (uint8_t)(ci->gx[k] >> (8 * (7 - b)));
-					pp[plen + 8 * (n64 - 1 - k) + b] = (uint8_t)(ci->gy[k] >> (8 * (7 - b)));
-				}
-		}
+		if (rc[i]) gen_to_be(&points[i * 2 * plen], ci); /* keep the batch launchable: rejected slots get G */
 	if (eccb200_prj_pt_mul_batch(eng, n, scalars.data(), all_gen ? nullptr : points.data(), outb.data(),
 				     status.data()))
 		return -1;
@@ -283,8 +275,8 @@ int mul_batch(eccb200_prj_pt *out, const eccb200_nn *m, const eccb200_prj_pt *in
 			fp_set_word(&o->Y, &src.Y, 1);
 			fp_set_word(&o->Z, &src.Z, 0);
 		} else {
-			fp_set_be(&o->X, &src.X, &outb[i * 2 * plen], n64);
-			fp_set_be(&o->Y, &src.Y, &outb[i * 2 * plen + plen], n64);
+			fp_set_be(&o->X, &src.X, &outb[i * 2 * plen], pl);
+			fp_set_be(&o->Y, &src.Y, &outb[i * 2 * plen + plen], pl);
 			fp_set_word(&o->Z, &src.Z, 1);
 		}
 		o->crv = src.crv;
@@ -398,8 +390,8 @@ extern "C" int eccb200_dropin_ecdsa_verify_batch(const uint8_t **s, const uint8_
 	if (!ci) return -1;
 	eccb200_ctx *eng = engine_for(ci->id);
 	if (!eng) return -1;
-	const int n64 = ci->n64;
-	const size_t plen = 8 * (size_t)n64, qlen = plen;
+	const int pl = ci->plen;
+	const size_t plen = (size_t)ci->plen, qlen = (size_t)ci->qlen;
 	std::vector<uint8_t> sigs(num * 2 * qlen, 0), pubs(num * 2 * plen, 0), dig(num * (size_t)hlen, 0);
 	/* public keys whose y is not already (x, y, 1) go through the batched prj_pt_unique */
 	std::vector<uint32_t> prj_idx;
@@ -418,8 +410,8 @@ extern "C" int eccb200_dropin_ecdsa_verify_batch(const uint8_t **s, const uint8_
 		}
 		const eccb200_prj_pt *y = &pub_keys[i]->y;
 		if (fp_is_small(&y->Z, 1)) {
-			fp_to_be(&pubs[i * 2 * plen], &y->X, n64);
-			fp_to_be(&pubs[i * 2 * plen + plen], &y->Y, n64);
+			fp_to_be(&pubs[i * 2 * plen], &y->X, pl);
+			fp_to_be(&pubs[i * 2 * plen + plen], &y->Y, pl);
 		} else {
 			prj_idx.push_back(i);
 		}
@@ -429,9 +421,9 @@ extern "C" int eccb200_dropin_ecdsa_verify_batch(const uint8_t **s, const uint8_
 		std::vector<int8_t> st(prj_idx.size());
 		for (size_t k = 0; k < prj_idx.size(); k++) {
 			const eccb200_prj_pt *p = &pub_keys[prj_idx[k]]->y;
-			fp_to_be(&pb[k * 3 * plen], &p->X, n64);
-			fp_to_be(&pb[k * 3 * plen + plen], &p->Y, n64);
-			fp_to_be(&pb[k * 3 * plen + 2 * plen], &p->Z, n64);
+			fp_to_be(&pb[k * 3 * plen], &p->X, pl);
+			fp_to_be(&pb[k * 3 * plen + plen], &p->Y, pl);
+			fp_to_be(&pb[k * 3 * plen + 2 * plen], &p->Z, pl);
 		}
 		if (eccb200_prj_pt_unique_batch(eng, (uint32_t)prj_idx.size(), pb.data(), ab.data(), st.data())) return -1;
 		for (size_t k = 0; k < prj_idx.size(); k++) {

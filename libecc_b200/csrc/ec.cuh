@@ -284,38 +284,47 @@ template <class C> struct EC {
 
 /* ---------------------------------------------------------------------------------------------- wire format */
 
-/* big-endian bytes (libecc wire format, nn_init_from_buf nn/nn.c:479) -> N little-endian 32-bit words */
-template <int N> ECC_HD void load_be(Fe<N> &r, const uint8_t *buf)
+/* len big-endian bytes (libecc wire format, nn_init_from_buf nn/nn.c:479) -> N little-endian 32-bit words; portable
+ * byte-wise form for the host build of the tests (the kernels use load_wire / store_wire of kernels.cuh) */
+template <int N> ECC_HD void load_be(Fe<N> &r, const uint8_t *buf, int len = 4 * N)
 {
-#pragma unroll
-	for (int i = 0; i < N; i++) {
-		const uint8_t *b = buf + 4 * (N - 1 - i);
-		r.w[i] = ((uint32_t)b[0] << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | (uint32_t)b[3];
-	}
+	for (int i = 0; i < N; i++) r.w[i] = 0;
+	for (int j = 0; j < len && j < 4 * N; j++) r.w[j >> 2] |= (uint32_t)buf[len - 1 - j] << (8 * (j & 3));
 }
 
 /* nn_export_to_buf (nn/nn.c:511) */
-template <int N> ECC_HD void store_be(uint8_t *buf, const Fe<N> &a)
+template <int N> ECC_HD void store_be(uint8_t *buf, const Fe<N> &a, int len = 4 * N)
 {
-#pragma unroll
-	for (int i = 0; i < N; i++) {
-		uint8_t *b = buf + 4 * (N - 1 - i);
-		uint32_t v = a.w[i];
-		b[0] = (uint8_t)(v >> 24);
-		b[1] = (uint8_t)(v >> 16);
-		b[2] = (uint8_t)(v >> 8);
-		b[3] = (uint8_t)v;
-	}
+	for (int j = 0; j < len; j++) buf[len - 1 - j] = (j < 4 * N) ? (uint8_t)(a.w[j >> 2] >> (8 * (j & 3))) : 0;
 }
 
 /* ---------------------------------------------------------------------------------------------- scalars */
 
-/* Reduce a raw N-word scalar modulo q (all target curves have 2^(32N) < 2q, but loop to be general: the
- * reference's ladder yields (k mod q)*P for any k, curves/prj_pt.c:1591-1619). */
+/* Reduce a raw wire scalar (QLEN bytes, so < 2^(8*QLEN)) modulo q: the reference's ladder yields (k mod q)*P for any
+ * k (curves/prj_pt.c:1591-1619).  Shifted conditional subtractions of q << sh, sh = 8*QLEN - bitlen(q) .. 0: a single
+ * step for the 256/384-bit curves (2^(8*QLEN) < 2q), eight for the 521-bit one (66-byte scalars, q < 2^521). */
 template <class C> ECC_HD void scalar_reduce(Fe<C::N> &k)
 {
 	typedef Field<typename C::Fq> Fq;
-	for (int it = 0; it < 4; it++) Fq::cond_sub_mod(k, k);
+	constexpr int N = C::N;
+	constexpr int SH = 8 * C::QLEN - C::QBITS;
+	static_assert(SH >= 0 && SH < 32 && C::QBITS + SH <= 32 * N, "scalar_reduce: q << SH must fit N words");
+#pragma unroll
+	for (int sh = SH; sh > 0; sh--) {
+		uint32_t d[N];
+		uint64_t bw = 0;
+#pragma unroll
+		for (int i = 0; i < N; i++) {
+			uint32_t lo = (i > 0) ? C::Fq::P(i - 1) : 0u;
+			uint32_t qs = (C::Fq::P(i) << sh) | (lo >> (32 - sh)); /* word i of q << sh */
+			uint64_t t = (uint64_t)k.w[i] - qs - bw;
+			d[i] = (uint32_t)t;
+			bw = (t >> 32) & 1;
+		}
+#pragma unroll
+		for (int i = 0; i < N; i++) k.w[i] = bw ? k.w[i] : d[i];
+	}
+	for (int it = 0; it < 2; it++) Fq::cond_sub_mod(k, k);
 }
 
 /* 64-bit funnel shifts on word pairs (static register indices only: the scalar walks through the window loop by
@@ -356,22 +365,38 @@ template <class C> ECC_HD void load_table_entry(Aff<C> &t, const uint32_t *__res
 	constexpr int N = C::N;
 	const uint32_t *base = table + e * (2 * N);
 #if defined(__CUDA_ARCH__)
-	const uint4 *src = reinterpret_cast<const uint4 *>(base);
+	if (N % 4 == 0) {
+		const uint4 *src = reinterpret_cast<const uint4 *>(base);
 #pragma unroll
-	for (int j = 0; j < N / 4; j++) {
-		uint4 v = __ldg(src + j);
-		t.x.w[4 * j] = v.x;
-		t.x.w[4 * j + 1] = v.y;
-		t.x.w[4 * j + 2] = v.z;
-		t.x.w[4 * j + 3] = v.w;
-	}
+		for (int j = 0; j < N / 4; j++) {
+			uint4 v = __ldg(src + j);
+			t.x.w[4 * j] = v.x;
+			t.x.w[4 * j + 1] = v.y;
+			t.x.w[4 * j + 2] = v.z;
+			t.x.w[4 * j + 3] = v.w;
+		}
 #pragma unroll
-	for (int j = 0; j < N / 4; j++) {
-		uint4 v = __ldg(src + N / 4 + j);
-		t.y.w[4 * j] = v.x;
-		t.y.w[4 * j + 1] = v.y;
-		t.y.w[4 * j + 2] = v.z;
-		t.y.w[4 * j + 3] = v.w;
+		for (int j = 0; j < N / 4; j++) {
+			uint4 v = __ldg(src + N / 4 + j);
+			t.y.w[4 * j] = v.x;
+			t.y.w[4 * j + 1] = v.y;
+			t.y.w[4 * j + 2] = v.z;
+			t.y.w[4 * j + 3] = v.w;
+		}
+	} else { /* N even: 8-byte loads */
+		const uint2 *src = reinterpret_cast<const uint2 *>(base);
+#pragma unroll
+		for (int j = 0; j < N / 2; j++) {
+			uint2 v = __ldg(src + j);
+			t.x.w[2 * j] = v.x;
+			t.x.w[2 * j + 1] = v.y;
+		}
+#pragma unroll
+		for (int j = 0; j < N / 2; j++) {
+			uint2 v = __ldg(src + N / 2 + j);
+			t.y.w[2 * j] = v.x;
+			t.y.w[2 * j + 1] = v.y;
+		}
 	}
 #else
 	for (int j = 0; j < N; j++) {
@@ -421,19 +446,35 @@ ECC_HD void window_mul(Jac<C> &acc, const Fe<C::N> &k, const Aff<C> &P, const Ja
 #pragma unroll 1
 	for (int j = 1; j < 8; j++) G::add_mixed(tbl[j], tbl[j - 1], P); /* j == 1 takes the P == Q (doubling) branch */
 
-	/* K' = k + 0x8888...8 with carry-out */
+	/* K' = k + 0x88..8 over the ND = ceil(bitlen(q)/4) nibbles a reduced scalar occupies; the carry lands in
+	 * nibble ND (0 or 1).  K' is then moved to the top of the N words so that nibbles leave from the MSB end. */
+	constexpr int ND = (C::QBITS + 3) / 4;
+	constexpr int PAD = 32 * N - 4 * ND; /* unused high bits: 0 for 256/384-bit, 52 for the 521-bit curve */
 	uint32_t kk[N];
 	uint64_t c = 0;
 #pragma unroll
 	for (int i = 0; i < N; i++) {
-		uint64_t s = (uint64_t)k.w[i] + 0x88888888u + c;
+		const int nib = ND - 8 * i; /* nibbles of this word below ND */
+		const uint32_t eights = nib >= 8 ? 0x88888888u : (nib <= 0 ? 0u : (0x88888888u >> (4 * (8 - nib))));
+		uint64_t s = (uint64_t)k.w[i] + eights + c;
 		kk[i] = (uint32_t)s;
 		c = s >> 32;
 	}
+	if (PAD > 0) {
+		constexpr int WS = PAD / 32, BS = PAD % 32;
+		constexpr int TW = (4 * ND) / 32 < N ? (4 * ND) / 32 : 0; /* (index clamp only for the dead PAD == 0 case) */
+		c = (kk[TW] >> ((4 * ND) % 32)) & 1u; /* top digit */
+#pragma unroll
+		for (int j = N - 1; j >= 0; j--) {
+			uint32_t hi = (j - WS >= 0) ? kk[j - WS] : 0u;
+			uint32_t lo = (j - WS - 1 >= 0) ? kk[j - WS - 1] : 0u;
+			kk[j] = BS ? funnel_l(lo, hi, BS) : hi;
+		}
+	}
 	G::set_inf(acc);
-	if (c) acc = tbl[0]; /* top digit (weight 16^(8N)) is 0 or 1 */
+	if (c) acc = tbl[0]; /* top digit (weight 16^ND) is 0 or 1 */
 #pragma unroll 1
-	for (int di = 8 * N - 1; di >= -1; di--) {
+	for (int di = ND - 1; di >= -1; di--) {
 		Jac<C> e, t;
 		bool have;
 		if (di >= 0) {

@@ -77,6 +77,7 @@ template <class Fn> static int dispatch(int curve_id, Fn &&fn)
 	case ECCB200_BRAINPOOLP256R1: return fn(Curve_BRAINPOOLP256R1());
 	case ECCB200_BRAINPOOLP384R1: return fn(Curve_BRAINPOOLP384R1());
 	case ECCB200_SECP256K1: return fn(Curve_SECP256K1());
+	case ECCB200_SECP521R1: return fn(Curve_SECP521R1());
 	default: return fail("unknown curve id");
 	}
 }
@@ -151,7 +152,10 @@ extern "C" int eccb200_ctx_create(eccb200_ctx **out, int curve_id, int device, i
 		if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g);
 		cudaGetLastError();
 	}
-	int w = comb_window ? comb_window : 22; /* default: 22-bit windows (12 adds per 256-bit scalar, 3.2 GB table) */
+	/* default: 22-bit windows (12 adds per 256-bit scalar, 3.2 GB table); 20-bit for the 521-bit curve (27 adds, 4 GB) */
+	uint32_t plen_probe = 0, qlen_probe = 0;
+	if (eccb200_curve_sizes(curve_id, &plen_probe, &qlen_probe)) return -1;
+	int w = comb_window ? comb_window : (plen_probe > 48 ? 20 : 22);
 	if (w < 4 || w > 24 || (w > 16 && (w & 1))) return fail("comb_window must be in [4,16] or even in [18,24]");
 
 	eccb200_ctx *ctx = new eccb200_ctx();

@@ -21,59 +21,108 @@ namespace eccb200 {
 
 __device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
 
-/* N words from a 16-byte-aligned big-endian field (4N bytes) */
-template <int N> __device__ __forceinline__ void load_be16(Fe<N> &r, const uint8_t *buf)
+/* A wire field is LEN big-endian bytes holding an N-word value (LEN <= 4N).  LEN == 4N with N a multiple of 4 (the
+ * 256- and 384-bit curves) is read with 16-byte vector loads — item strides are then multiples of 16 bytes; any
+ * other length (66 bytes for the 521-bit curve) has no alignment to rely on and is read byte by byte. */
+template <int N, int LEN> __device__ __forceinline__ void load_wire(Fe<N> &r, const uint8_t *buf)
 {
-	const uint4 *p = reinterpret_cast<const uint4 *>(buf);
+	if (LEN == 4 * N && N % 4 == 0) {
+		const uint4 *p = reinterpret_cast<const uint4 *>(buf);
 #pragma unroll
-	for (int j = 0; j < N / 4; j++) {
-		uint4 v = __ldg(p + j);
-		/* bytes [16j, 16j+16) hold words N-1-4j .. N-4-4j (most significant first) */
-		r.w[N - 1 - 4 * j] = bswap32(v.x);
-		r.w[N - 2 - 4 * j] = bswap32(v.y);
-		r.w[N - 3 - 4 * j] = bswap32(v.z);
-		r.w[N - 4 - 4 * j] = bswap32(v.w);
+		for (int j = 0; j < N / 4; j++) {
+			uint4 v = __ldg(p + j);
+			/* bytes [16j, 16j+16) hold words N-1-4j .. N-4-4j (most significant first) */
+			r.w[N - 1 - 4 * j] = bswap32(v.x);
+			r.w[N - 2 - 4 * j] = bswap32(v.y);
+			r.w[N - 3 - 4 * j] = bswap32(v.z);
+			r.w[N - 4 - 4 * j] = bswap32(v.w);
+		}
+	} else {
+#pragma unroll
+		for (int i = 0; i < N; i++) {
+			uint32_t v = 0;
+#pragma unroll
+			for (int b = 0; b < 4; b++) {
+				const int pos = LEN - 1 - (4 * i + b); /* byte of significance 4i+b */
+				if (pos >= 0) v |= (uint32_t)__ldg(buf + pos) << (8 * b);
+			}
+			r.w[i] = v;
+		}
 	}
 }
 
-template <int N> __device__ __forceinline__ void store_be16(uint8_t *buf, const Fe<N> &a)
+template <int N, int LEN> __device__ __forceinline__ void store_wire(uint8_t *buf, const Fe<N> &a)
 {
-	uint4 *p = reinterpret_cast<uint4 *>(buf);
+	if (LEN == 4 * N && N % 4 == 0) {
+		uint4 *p = reinterpret_cast<uint4 *>(buf);
 #pragma unroll
-	for (int j = 0; j < N / 4; j++) {
-		uint4 v;
-		v.x = bswap32(a.w[N - 1 - 4 * j]);
-		v.y = bswap32(a.w[N - 2 - 4 * j]);
-		v.z = bswap32(a.w[N - 3 - 4 * j]);
-		v.w = bswap32(a.w[N - 4 - 4 * j]);
-		p[j] = v;
+		for (int j = 0; j < N / 4; j++) {
+			uint4 v;
+			v.x = bswap32(a.w[N - 1 - 4 * j]);
+			v.y = bswap32(a.w[N - 2 - 4 * j]);
+			v.z = bswap32(a.w[N - 3 - 4 * j]);
+			v.w = bswap32(a.w[N - 4 - 4 * j]);
+			p[j] = v;
+		}
+	} else {
+#pragma unroll
+		for (int i = 0; i < N; i++) {
+#pragma unroll
+			for (int b = 0; b < 4; b++) {
+				const int pos = LEN - 1 - (4 * i + b);
+				if (pos >= 0) buf[pos] = (uint8_t)(a.w[i] >> (8 * b));
+			}
+		}
 	}
 }
 
+/* word buffers written by these kernels (Jacobian, prefix, table): 16-byte accesses when N is a multiple of 4,
+ * 8-byte ones otherwise (N is always even: two words per reference limb) */
 template <int N> __device__ __forceinline__ void load_words(Fe<N> &r, const uint32_t *src)
 {
-	const uint4 *p = reinterpret_cast<const uint4 *>(src);
+	if (N % 4 == 0) {
+		const uint4 *p = reinterpret_cast<const uint4 *>(src);
 #pragma unroll
-	for (int j = 0; j < N / 4; j++) {
-		uint4 v = p[j];
-		r.w[4 * j] = v.x;
-		r.w[4 * j + 1] = v.y;
-		r.w[4 * j + 2] = v.z;
-		r.w[4 * j + 3] = v.w;
+		for (int j = 0; j < N / 4; j++) {
+			uint4 v = p[j];
+			r.w[4 * j] = v.x;
+			r.w[4 * j + 1] = v.y;
+			r.w[4 * j + 2] = v.z;
+			r.w[4 * j + 3] = v.w;
+		}
+	} else {
+		const uint2 *p = reinterpret_cast<const uint2 *>(src);
+#pragma unroll
+		for (int j = 0; j < N / 2; j++) {
+			uint2 v = p[j];
+			r.w[2 * j] = v.x;
+			r.w[2 * j + 1] = v.y;
+		}
 	}
 }
 
 template <int N> __device__ __forceinline__ void store_words(uint32_t *dst, const Fe<N> &a)
 {
-	uint4 *p = reinterpret_cast<uint4 *>(dst);
+	if (N % 4 == 0) {
+		uint4 *p = reinterpret_cast<uint4 *>(dst);
 #pragma unroll
-	for (int j = 0; j < N / 4; j++) {
-		uint4 v;
-		v.x = a.w[4 * j];
-		v.y = a.w[4 * j + 1];
-		v.z = a.w[4 * j + 2];
-		v.w = a.w[4 * j + 3];
-		p[j] = v;
+		for (int j = 0; j < N / 4; j++) {
+			uint4 v;
+			v.x = a.w[4 * j];
+			v.y = a.w[4 * j + 1];
+			v.z = a.w[4 * j + 2];
+			v.w = a.w[4 * j + 3];
+			p[j] = v;
+		}
+	} else {
+		uint2 *p = reinterpret_cast<uint2 *>(dst);
+#pragma unroll
+		for (int j = 0; j < N / 2; j++) {
+			uint2 v;
+			v.x = a.w[2 * j];
+			v.y = a.w[2 * j + 1];
+			p[j] = v;
+		}
 	}
 }
 
@@ -91,8 +140,8 @@ template <class C> __device__ __forceinline__ bool load_affine_checked(Aff<C> &P
 {
 	typedef Field<typename C::Fp> F;
 	Fe<C::N> x, y;
-	load_be16<C::N>(x, buf);
-	load_be16<C::N>(y, buf + 4 * C::N);
+	load_wire<C::N, C::PLEN>(x, buf);
+	load_wire<C::N, C::PLEN>(y, buf + C::PLEN);
 	bool ok = !F::geq_mod(x) && !F::geq_mod(y);
 	F::to_mont(P.x, x);
 	F::to_mont(P.y, y);
@@ -184,7 +233,7 @@ __global__ void __launch_bounds__(128) k_smul_fixed(uint32_t n, const uint8_t *_
 	uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= n) return;
 	Fe<C::N> k;
-	load_be16<C::N>(k, scalars + (size_t)idx * (4 * C::N));
+	load_wire<C::N, C::QLEN>(k, scalars + (size_t)idx * C::QLEN);
 	scalar_reduce<C>(k);
 	Jac<C> acc;
 	comb_mul<C>(acc, k, table, w);
@@ -265,7 +314,8 @@ __global__ void __launch_bounds__(128) k_smul_fixed_tma(uint32_t n, const uint8_
 #ifndef ECC_MINB_VERIFY
 #define ECC_MINB_VERIFY 5
 #endif
-/* 12-word fields (P-384) need 1.5x the registers per element: keep their caps at 168 / 128 registers */
+/* 12-word fields (P-384) need 1.5x the registers per element: keep their caps at 168 / 128 registers;
+ * 18-word fields (P-521) get the full 255 (2 CTAs per SM) */
 #ifndef ECC_MINB_VAR_WIDE
 #define ECC_MINB_VAR_WIDE 3
 #endif
@@ -273,17 +323,17 @@ __global__ void __launch_bounds__(128) k_smul_fixed_tma(uint32_t n, const uint8_
 #define ECC_MINB_VERIFY_WIDE 4
 #endif
 template <class C>
-__global__ void __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VAR : ECC_MINB_VAR_WIDE)) k_smul_var(uint32_t n, const uint8_t *__restrict__ scalars,
+__global__ void __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VAR : (C::N <= 12 ? ECC_MINB_VAR_WIDE : 2))) k_smul_var(uint32_t n, const uint8_t *__restrict__ scalars,
 						  const uint8_t *__restrict__ points, uint32_t *__restrict__ jac,
 						  int8_t *__restrict__ status)
 {
 	uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= n) return;
 	Fe<C::N> k;
-	load_be16<C::N>(k, scalars + (size_t)idx * (4 * C::N));
+	load_wire<C::N, C::QLEN>(k, scalars + (size_t)idx * C::QLEN);
 	scalar_reduce<C>(k);
 	Aff<C> P;
-	bool ok = load_affine_checked<C>(P, points + (size_t)idx * (8 * C::N));
+	bool ok = load_affine_checked<C>(P, points + (size_t)idx * (2 * C::PLEN));
 	Jac<C> acc;
 	if (ok) {
 		window_mul<C>(acc, k, P);
@@ -396,6 +446,7 @@ __global__ void __launch_bounds__(128) k_to_affine(uint32_t n, const uint32_t *_
 {
 	typedef Field<typename C::Fp> F;
 	constexpr int N = C::N;
+	constexpr int PL = C::PLEN;
 	constexpr bool TABLE = (MODE == 1);
 	const uint32_t T = gridDim.x * blockDim.x;
 	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -450,12 +501,12 @@ __global__ void __launch_bounds__(128) k_to_affine(uint32_t n, const uint32_t *_
 				store_words<N>(table_out + (size_t)e * (2 * N) + N, Y);
 			} else if (MODE == 3) {
 				F::from_mont(t, X);
-				store_be16<N>(out + (size_t)e * (4 * N), t);
+				store_wire<N, PL>(out + (size_t)e * PL, t);
 			} else {
 				F::from_mont(t, X);
-				store_be16<N>(out + (size_t)e * (8 * N), t);
+				store_wire<N, PL>(out + (size_t)e * (2 * PL), t);
 				F::from_mont(t, Y);
-				store_be16<N>(out + (size_t)e * (8 * N) + 4 * N, t);
+				store_wire<N, PL>(out + (size_t)e * (2 * PL) + PL, t);
 			}
 		} else {
 			Fe<N> zero;
@@ -464,11 +515,11 @@ __global__ void __launch_bounds__(128) k_to_affine(uint32_t n, const uint32_t *_
 				store_words<N>(table_out + (size_t)e * (2 * N), zero);
 				store_words<N>(table_out + (size_t)e * (2 * N) + N, zero);
 			} else if (MODE == 3) {
-				store_be16<N>(out + (size_t)e * (4 * N), zero);
+				store_wire<N, PL>(out + (size_t)e * PL, zero);
 				status[e] = -1;
 			} else {
-				store_be16<N>(out + (size_t)e * (8 * N), zero);
-				store_be16<N>(out + (size_t)e * (8 * N) + 4 * N, zero);
+				store_wire<N, PL>(out + (size_t)e * (2 * PL), zero);
+				store_wire<N, PL>(out + (size_t)e * (2 * PL) + PL, zero);
 				if (!err) status[e] = 1;
 			}
 		}
@@ -488,10 +539,10 @@ __global__ void __launch_bounds__(128) k_prj_load(uint32_t n, const uint8_t *__r
 	uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= n) return;
 	Fe<N> x, y, z;
-	const uint8_t *b = prj + (size_t)idx * (12 * N);
-	load_be16<N>(x, b);
-	load_be16<N>(y, b + 4 * N);
-	load_be16<N>(z, b + 8 * N);
+	const uint8_t *b = prj + (size_t)idx * (3 * C::PLEN);
+	load_wire<N, C::PLEN>(x, b);
+	load_wire<N, C::PLEN>(y, b + C::PLEN);
+	load_wire<N, C::PLEN>(z, b + 2 * C::PLEN);
 	bool ok = !F::geq_mod(x) && !F::geq_mod(y) && !F::geq_mod(z);
 	Jac<C> P;
 	F::to_mont(P.X, x);
@@ -539,7 +590,7 @@ __global__ void __launch_bounds__(128) k_prj_load(uint32_t n, const uint8_t *__r
  * digests: hlen bytes each; e = leftmost min(8*hlen, bitlen(q)) bits (:760-775), reduced mod q (:777).
  */
 template <class C>
-__global__ void __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VERIFY : ECC_MINB_VERIFY_WIDE)) k_ecdsa_verify(uint32_t n, const uint8_t *__restrict__ sigs,
+__global__ void __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VERIFY : (C::N <= 12 ? ECC_MINB_VERIFY_WIDE : 2))) k_ecdsa_verify(uint32_t n, const uint8_t *__restrict__ sigs,
 						      const uint8_t *__restrict__ pubkeys,
 						      const uint8_t *__restrict__ digests, uint32_t hlen,
 						      const uint32_t *__restrict__ table, int w,
@@ -552,8 +603,8 @@ __global__ void __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VERIFY : ECC_MINB_V
 	const uint32_t i0 = active ? idx : 0; /* idle threads of the last CTA still join the CTA-wide inversion */
 
 	Fe<N> r, s, e;
-	load_be16<N>(r, sigs + (size_t)i0 * (8 * N));
-	load_be16<N>(s, sigs + (size_t)i0 * (8 * N) + 4 * N);
+	load_wire<N, C::QLEN>(r, sigs + (size_t)i0 * (2 * C::QLEN));
+	load_wire<N, C::QLEN>(s, sigs + (size_t)i0 * (2 * C::QLEN) + C::QLEN);
 	const bool rs_ok = ecdsa_rs_in_range<C>(r, s);
 	/* s^-1 mod q for the whole CTA at once (sig/ecdsa_common.c:781 does one nn_modinv per signature) */
 	Fe<N> sm, wm;
@@ -562,7 +613,7 @@ __global__ void __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VERIFY : ECC_MINB_V
 	cta_inverse_128<typename C::Fq>(wm, sm);
 	if (!active) return;
 	Aff<C> Y;
-	bool key_ok = load_affine_checked<C>(Y, pubkeys + (size_t)idx * (8 * N));
+	bool key_ok = load_affine_checked<C>(Y, pubkeys + (size_t)idx * (2 * C::PLEN));
 	digest_to_scalar<C>(e, digests + (size_t)idx * hlen, hlen);
 	int code = 4;
 	if (key_ok) {
@@ -609,7 +660,7 @@ __global__ void __launch_bounds__(128) k_ecdsa_sign_finish(uint32_t n, const uin
 	if (active) {
 		for (uint32_t e = tid; e < n; e += T) {
 			Fe<N> kk, km;
-			load_be16<N>(kk, nonces + (size_t)e * (4 * N));
+			load_wire<N, C::QLEN>(kk, nonces + (size_t)e * C::QLEN);
 			store_words<N>(prefix + (size_t)e * N, acc);
 			if (!Fq::is_zero(kk) && !Fq::geq_mod(kk)) {
 				Fe<N> t;
@@ -627,8 +678,8 @@ __global__ void __launch_bounds__(128) k_ecdsa_sign_finish(uint32_t n, const uin
 	for (uint32_t e = last;; e -= T) {
 		Fe<N> kk, d, x, r, ev, s, zero;
 		Fq::set_zero(zero);
-		load_be16<N>(kk, nonces + (size_t)e * (4 * N));
-		load_be16<N>(d, privkeys + (size_t)e * (4 * N));
+		load_wire<N, C::QLEN>(kk, nonces + (size_t)e * C::QLEN);
+		load_wire<N, C::QLEN>(d, privkeys + (size_t)e * C::QLEN);
 		bool k_ok = !Fq::is_zero(kk) && !Fq::geq_mod(kk);
 		bool d_ok = !Fq::is_zero(d) && !Fq::geq_mod(d);
 		int st = 0;
@@ -641,7 +692,7 @@ __global__ void __launch_bounds__(128) k_ecdsa_sign_finish(uint32_t n, const uin
 			Fq::mul(kinv, inv, pre);  /* k^-1 in Montgomery form */
 			Fq::mul(t, inv, km);
 			inv = t;
-			load_be16<N>(x, kG_aff + (size_t)e * (8 * N));
+			load_wire<N, C::PLEN>(x, kG_aff + (size_t)e * (2 * C::PLEN));
 			r = x;
 			scalar_reduce<C>(r);                        /* r = W_x mod q          (:483) */
 			digest_to_scalar<C>(ev, digests + (size_t)e * hlen, hlen);
@@ -659,8 +710,8 @@ __global__ void __launch_bounds__(128) k_ecdsa_sign_finish(uint32_t n, const uin
 			r = zero;
 			s = zero;
 		}
-		store_be16<N>(sigs + (size_t)e * (8 * N), r);
-		store_be16<N>(sigs + (size_t)e * (8 * N) + 4 * N, s);
+		store_wire<N, C::QLEN>(sigs + (size_t)e * (2 * C::QLEN), r);
+		store_wire<N, C::QLEN>(sigs + (size_t)e * (2 * C::QLEN) + C::QLEN, s);
 		status[e] = (int8_t)st;
 		if (e < T) break;
 	}
@@ -678,12 +729,12 @@ __global__ void __launch_bounds__(128) k_ecdsa_uv(uint32_t n, const uint8_t *__r
 	uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= n) return;
 	Fe<N> r, s, e, u, v;
-	load_be16<N>(r, sigs + (size_t)idx * (8 * N));
-	load_be16<N>(s, sigs + (size_t)idx * (8 * N) + 4 * N);
+	load_wire<N, C::QLEN>(r, sigs + (size_t)idx * (2 * C::QLEN));
+	load_wire<N, C::QLEN>(s, sigs + (size_t)idx * (2 * C::QLEN) + C::QLEN);
 	digest_to_scalar<C>(e, digests + (size_t)idx * hlen, hlen);
 	ecdsa_uv<C>(u, v, r, s, e);
-	store_be16<N>(out + (size_t)idx * (8 * N), u);
-	store_be16<N>(out + (size_t)idx * (8 * N) + 4 * N, v);
+	store_wire<N, C::QLEN>(out + (size_t)idx * (2 * C::QLEN), u);
+	store_wire<N, C::QLEN>(out + (size_t)idx * (2 * C::QLEN) + C::QLEN, v);
 }
 
 template <class FT>
@@ -694,10 +745,10 @@ __global__ void k_fp_mul_monty(uint32_t n, const uint8_t *__restrict__ a, const 
 	uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= n) return;
 	Fe<N> x, y, z;
-	load_be16<N>(x, a + (size_t)idx * (4 * N));
-	load_be16<N>(y, b + (size_t)idx * (4 * N));
+	load_wire<N, FT::BYTES>(x, a + (size_t)idx * FT::BYTES);
+	load_wire<N, FT::BYTES>(y, b + (size_t)idx * FT::BYTES);
 	Field<FT>::mul(z, x, y);
-	store_be16<N>(out + (size_t)idx * (4 * N), z);
+	store_wire<N, FT::BYTES>(out + (size_t)idx * FT::BYTES, z);
 }
 
 /*
@@ -717,11 +768,11 @@ __global__ void __launch_bounds__(128) k_fp_mul_chain(uint32_t n, const uint8_t 
 	uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= n) return;
 	Fe<N> x, y;
-	load_be16<N>(x, a + (size_t)idx * (4 * N));
-	load_be16<N>(y, b + (size_t)idx * (4 * N));
+	load_wire<N, FT::BYTES>(x, a + (size_t)idx * FT::BYTES);
+	load_wire<N, FT::BYTES>(y, b + (size_t)idx * FT::BYTES);
 #pragma unroll 1
 	for (int i = 0; i < iters; i++) Field<FT>::mul(x, x, y);
-	store_be16<N>(out + (size_t)idx * (4 * N), x);
+	store_wire<N, FT::BYTES>(out + (size_t)idx * FT::BYTES, x);
 }
 
 template <class FT>
@@ -872,7 +923,10 @@ template <class C>
 void LaunchFixed<C>::fixed_tma(uint32_t n, const uint8_t *scalars, const uint32_t *table, int w, uint32_t *jac,
 			       int8_t *status, cudaStream_t st)
 {
-	k_smul_fixed_tma<C><<<grid_for(n), kThreads, 0, st>>>(n, scalars, table, w, jac, status);
+	if constexpr (C::QLEN == 4 * C::N && C::N % 4 == 0) /* the bulk copy needs 16-byte multiples */
+		k_smul_fixed_tma<C><<<grid_for(n), kThreads, 0, st>>>(n, scalars, table, w, jac, status);
+	else
+		k_smul_fixed<C><<<grid_for(n), kThreads, 0, st>>>(n, scalars, table, w, jac, status);
 }
 template <class C>
 void LaunchFixed<C>::table_merge(uint32_t count, uint64_t first_entry, int w, int nwin_half,

@@ -22,7 +22,7 @@
 typedef uint64_t u64;
 typedef unsigned __int128 u128;
 
-#define MAXL 6   /* limbs of a field element / order (4 for 256-bit, 6 for 384-bit) */
+#define MAXL 9   /* limbs of a field element / order (4 for 256-bit, 6 for 384-bit, 9 for 521-bit) */
 #define BIGL 24  /* capacity for scalars (reference: nn up to 27 words, nn_config.h:154) */
 
 static __thread u64 g_mul_count;
@@ -313,6 +313,14 @@ static const struct {
 	  "0000000000000000000000000000000000000000000000000000000000000007",
 	  "79be667ef9dcbbac55a06295ce870b07029bfcdb2dce28d959f2815b16f81798",
 	  "483ada7726a3c4655da4fbfc0e1108a8fd17b448a68554199c47d08ffb10d4b8" },
+	/* 521-bit: 66-byte strings, 9 limbs (curves/known/ec_params_secp521r1.h) */
+	{ "SECP521R1",
+	  "01ffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffff",
+	  "01fffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffa51868783bf2f966b7fcc0148f709a5d03bb5c9b8899c47aebb6fb71e91386409",
+	  "01fffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffc",
+	  "0051953eb9618e1c9a1f929a21a0b68540eea2da725b99b315f3b8b489918ef109e156193951ec7e937b1652c0bd3bb1bf073573df883d2c34f1ef451fd46b503f00",
+	  "00c6858e06b70404e9cd9e3ecb662395b4429c648139053fb521f828af606b4d3dbaa14b5e77efe75928fe1dc127a2ffa8de3348b3c1856a429bf97e7e31c2e5bd66",
+	  "011839296a789a3bc0045c8a5fb42c7d1bd998f54449579b446817afbd17273e662c97ee72995ef42640c550b9013fad0761353c7086a272c24088be94769fd16650" },
 };
 
 static void hex_to_limbs(u64 *out, int n, const char *hex)
@@ -334,7 +342,7 @@ static int curve_load(curve_t *c, const char *name)
 		u64 p[MAXL], q[MAXL], b3[MAXL];
 		size_t hl = strlen(CURVE_HEX[k].p);
 		c->name = CURVE_HEX[k].name;
-		c->n = (int)(hl / 16);
+		c->n = (int)((hl + 15) / 16);
 		c->plen = (uint32_t)(hl / 2);
 		c->qlen = (uint32_t)(strlen(CURVE_HEX[k].q) / 2);
 		hex_to_limbs(p, c->n, CURVE_HEX[k].p);

@@ -7,23 +7,25 @@ import math
 
 # one Montgomery CIOS product of n 64-bit limbs = 2n^2+n wide multiply-accumulates, each = 4 32x32->64 IMADs
 IMAD32_PER_MUL = {"SECP256R1": (2 * 4 * 4 + 4) * 4, "FRP256V1": (2 * 4 * 4 + 4) * 4, "SECP384R1": (2 * 6 * 6 + 6) * 4,
-                  "BRAINPOOLP256R1": 144, "SECP256K1": 144, "BRAINPOOLP384R1": 312}
+                  "BRAINPOOLP256R1": 144, "SECP256K1": 144, "BRAINPOOLP384R1": 312, "SECP521R1": (2 * 9 * 9 + 9) * 4}
 # IMAD.WIDE instructions the generated code really issues per product, averaged over a mixed addition (8 mul + 3 sqr;
 # tools/gen_fp_ptx.py: P-256 mul 96 / sqr 68, generic 256-bit 136 / 108, P-384 276 / 210 incl. the m_i products)
 IMAD_EXECUTED_PER_MUL = {"SECP256R1": (8 * 96 + 3 * 68) / 11, "FRP256V1": (8 * 136 + 3 * 108) / 11,
                          "SECP384R1": (8 * 276 + 3 * 210) / 11, "BRAINPOOLP256R1": (8 * 136 + 3 * 108) / 11,
-                         "SECP256K1": (8 * 136 + 3 * 108) / 11, "BRAINPOOLP384R1": (8 * 300 + 3 * 234) / 11}
+                         "SECP256K1": (8 * 136 + 3 * 108) / 11, "BRAINPOOLP384R1": (8 * 300 + 3 * 234) / 11,
+                         "SECP521R1": (8 * 630 + 3 * 477) / 11}
 M_REF = {"SECP256R1": 8724, "FRP256V1": 8724, "SECP384R1": 13076,   # reference ladder (probe)
-         "BRAINPOOLP256R1": 8724, "SECP256K1": 8724, "BRAINPOOLP384R1": 13076}
+         "BRAINPOOLP256R1": 8724, "SECP256K1": 8724, "BRAINPOOLP384R1": 13076,
+         "SECP521R1": (2 * 521 + 1) * 17 + 3}
 QBITS = {"SECP256R1": 256, "FRP256V1": 256, "SECP384R1": 384, "BRAINPOOLP256R1": 256, "SECP256K1": 256,
-         "BRAINPOOLP384R1": 384}
+         "BRAINPOOLP384R1": 384, "SECP521R1": 521}
 
 
 def work_per_item(workload: str, comb_window: int):
     from bench import WORKLOADS
     curve, kind, _, _ = WORKLOADS[workload]
     nwin = math.ceil(QBITS[curve] / comb_window)
-    nib = QBITS[curve] // 4
+    nib = (QBITS[curve] + 3) // 4
     m_fixed = 11 * (nwin - 1)                                   # mixed add 8M+3S per window; first window is a copy
     m_var = 7 * 11 + 8 + nib * 4 * 8 + nib * (15.0 / 16) * 16   # table (7 madd, one of them a dbl) + 4 dbl/digit + adds
     fermat = (QBITS[curve] // 4) * 5 + 14                       # 4 sqr + 1 mul per nibble + table
@@ -36,7 +38,7 @@ def work_per_item(workload: str, comb_window: int):
         m_ref = M_REF[curve]
     else:
         m, kernel = m_fixed + 11 + m_var + 16 + fermat_q + 12, "k_ecdsa_verify"
-        m_ref = 2 * M_REF[curve] + 17 + 513 + 2
+        m_ref = 2 * M_REF[curve] + 17 + (2 * QBITS[curve] + 1) + 2
     return {"M_impl": m, "kernel": kernel, "imad32_per_mul": IMAD32_PER_MUL[curve],
             "imad32_per_item": m * IMAD32_PER_MUL[curve], "imad32_ref_per_item": m_ref * IMAD32_PER_MUL[curve],
             "imad_executed_per_item": m * IMAD_EXECUTED_PER_MUL[curve]}

@@ -21,7 +21,8 @@ SEED = 0x6C69626563632D31  # "libecc-1" 
 
 CURVES = {"SECP256R1": (4, 32, 32), "FRP256V1": (1, 32, 32), "SECP384R1": (5, 48, 48)}  # id, plen, qlen
 # additional curves: same kernels, generic-a / a = 0 doubling
-EXTRA_CURVES = {"BRAINPOOLP256R1": (8, 32, 32), "BRAINPOOLP384R1": (12, 48, 48), "SECP256K1": (19, 32, 32)}
+EXTRA_CURVES = {"BRAINPOOLP256R1": (8, 32, 32), "BRAINPOOLP384R1": (12, 48, 48), "SECP256K1": (19, 32, 32),
+                "SECP521R1": (6, 66, 66)}  # 521-bit: byte lengths not a multiple of the word size
 ALL_CURVES = dict(CURVES, **EXTRA_CURVES)
 ORDER = {
     "SECP256R1": 0xffffffff00000000ffffffffffffffffbce6faada7179e84f3b9cac2fc632551,
@@ -30,6 +31,7 @@ ORDER = {
     "BRAINPOOLP256R1": 0xa9fb57dba1eea9bc3e660a909d838d718c397aa3b561a6f7901e0e82974856a7,
     "BRAINPOOLP384R1": 0x8cb91e82a3386d280f5d6f7e50e641df152f7109ed5456b31f166e6cac0425a7cf3ab6af6b7fc3103b883202e9046565,
     "SECP256K1": 0xfffffffffffffffffffffffffffffffebaaedce6af48a03bbfd25e8cd0364141,
+    "SECP521R1": 0x01fffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffa51868783bf2f966b7fcc0148f709a5d03bb5c9b8899c47aebb6fb71e91386409,
 }
 PRIME = {
     "SECP256R1": 0xffffffff00000001000000000000000000000000ffffffffffffffffffffffff,
@@ -38,6 +40,7 @@ PRIME = {
     "BRAINPOOLP256R1": 0xa9fb57dba1eea9bc3e660a909d838d726e3bf623d52620282013481d1f6e5377,
     "BRAINPOOLP384R1": 0x8cb91e82a3386d280f5d6f7e50e641df152f7109ed5456b412b1da197fb71123acd3a729901d1a71874700133107ec53,
     "SECP256K1": 0xfffffffffffffffffffffffffffffffffffffffffffffffffffffffefffffc2f,
+    "SECP521R1": (1 << 521) - 1,
 }
 HASHLEN = {"SHA224": 28, "SHA256": 32, "SHA384": 48, "SHA512": 64, "SHA3_224": 28, "SHA3_256": 32,
            "SHA3_384": 48, "SHA3_512": 64}
@@ -106,12 +109,15 @@ def random_scalars(curve: str, n: int, tag: int = 0, below_q: bool = True) -> np
     raw = g.integers(0, 256, size=(n, qlen), dtype=np.uint8)
     if below_q:
         q = ORDER[curve]
+        top = (1 << (q.bit_length() - 8 * (qlen - 1))) - 1   # bitlen(q) is not a multiple of 8 for P-521
+        raw[:, 0] &= top
         for i in range(n):
             while True:
                 v = int.from_bytes(raw[i].tobytes(), "big")
                 if 0 < v < q:
                     break
                 raw[i] = g.integers(0, 256, size=qlen, dtype=np.uint8)
+                raw[i, 0] &= top
     return raw
 
 
@@ -176,6 +182,13 @@ def oracle_sign(curve: str, privkeys, nonces, digests, hlen: int, nthreads: int 
 
 def hx(s: str) -> np.ndarray:
     return np.frombuffer(bytes.fromhex(s), dtype=np.uint8)
+
+
+def hx_fit(s: str, nbytes: int) -> np.ndarray:
+    """Big-endian integer string resized to nbytes (the reference's vectors zero-pad some P-521 keys to 68 bytes;
+    nn_init_from_buf, nn/nn.c:479, accepts any length)."""
+    v = int(s, 16) if s else 0
+    return np.frombuffer(v.to_bytes(nbytes, "big"), dtype=np.uint8)
 
 
 def make_signatures(curve: str, n: int, tag: int = 0, hlen: int = 32, corrupt_every: int = 0):

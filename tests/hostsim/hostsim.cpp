@@ -28,6 +28,7 @@ template <class Fn> static int dispatch(int curve_id, Fn &&fn)
 	case 8: return fn(Curve_BRAINPOOLP256R1());
 	case 12: return fn(Curve_BRAINPOOLP384R1());
 	case 19: return fn(Curve_SECP256K1());
+	case 6: return fn(Curve_SECP521R1());
 	default: return -1;
 	}
 }
@@ -37,7 +38,7 @@ template <class C> static int jac_to_wire(const Jac<C> &p, uint8_t *out)
 {
 	typedef Field<typename C::Fp> F;
 	constexpr int N = C::N;
-	memset(out, 0, 8 * N);
+	memset(out, 0, 2 * C::PLEN);
 	if (F::is_zero(p.Z)) return 1;
 	Fe<N> zi, zi2, zi3, x, y, t;
 	F::inv(zi, p.Z);
@@ -47,8 +48,8 @@ template <class C> static int jac_to_wire(const Jac<C> &p, uint8_t *out)
 	F::from_mont(x, t);
 	F::mul(t, p.Y, zi3);
 	F::from_mont(y, t);
-	store_be<N>(out, x);
-	store_be<N>(out + 4 * N, y);
+	store_be<N>(out, x, C::PLEN);
+	store_be<N>(out + C::PLEN, y, C::PLEN);
 	return 0;
 }
 
@@ -56,8 +57,8 @@ template <class C> static bool load_point(Aff<C> &P, const uint8_t *buf)
 {
 	typedef Field<typename C::Fp> F;
 	Fe<C::N> x, y;
-	load_be<C::N>(x, buf);
-	load_be<C::N>(y, buf + 4 * C::N);
+	load_be<C::N>(x, buf, C::PLEN);
+	load_be<C::N>(y, buf + C::PLEN, C::PLEN);
 	bool ok = !F::geq_mod(x) && !F::geq_mod(y);
 	F::to_mont(P.x, x);
 	F::to_mont(P.y, y);
@@ -121,11 +122,12 @@ int hostsim_fp_mul(int curve_id, int which, uint32_t n, const uint8_t *a, const 
 		constexpr int N = C::N;
 		for (uint32_t i = 0; i < n; i++) {
 			Fe<N> x, y, z;
-			load_be<N>(x, a + (size_t)i * 4 * N);
-			load_be<N>(y, b + (size_t)i * 4 * N);
+			const int len = which == 0 ? C::PLEN : C::QLEN;
+			load_be<N>(x, a + (size_t)i * len, len);
+			load_be<N>(y, b + (size_t)i * len, len);
 			if (which == 0) Field<typename C::Fp>::mul(z, x, y);
 			else Field<typename C::Fq>::mul(z, x, y);
-			store_be<N>(out + (size_t)i * 4 * N, z);
+			store_be<N>(out + (size_t)i * len, z, len);
 		}
 		return 0;
 	});
@@ -140,8 +142,8 @@ int hostsim_fp_op(int curve_id, int op, uint32_t n, const uint8_t *a, const uint
 		constexpr int N = C::N;
 		for (uint32_t i = 0; i < n; i++) {
 			Fe<N> x, y, z;
-			load_be<N>(x, a + (size_t)i * 4 * N);
-			load_be<N>(y, b + (size_t)i * 4 * N);
+			load_be<N>(x, a + (size_t)i * C::PLEN, C::PLEN);
+			load_be<N>(y, b + (size_t)i * C::PLEN, C::PLEN);
 			if (op == 0) F::add(z, x, y);
 			else if (op == 1) F::sub(z, x, y);
 			else {
@@ -150,7 +152,7 @@ int hostsim_fp_op(int curve_id, int op, uint32_t n, const uint8_t *a, const uint
 				F::inv(zi, xm);
 				F::from_mont(z, zi);
 			}
-			store_be<N>(out + (size_t)i * 4 * N, z);
+			store_be<N>(out + (size_t)i * C::PLEN, z, C::PLEN);
 		}
 		return 0;
 	});
@@ -165,14 +167,14 @@ int hostsim_prj_pt_mul_batch(int curve_id, int w, uint32_t n, const uint8_t *sca
 		constexpr int N = C::N;
 		for (uint32_t i = 0; i < n; i++) {
 			Fe<N> k;
-			load_be<N>(k, scalars + (size_t)i * 4 * N);
+			load_be<N>(k, scalars + (size_t)i * C::QLEN, C::QLEN);
 			scalar_reduce<C>(k);
 			Jac<C> acc;
-			uint8_t *o = out + (size_t)i * 8 * N;
+			uint8_t *o = out + (size_t)i * 2 * C::PLEN;
 			if (points) {
 				Aff<C> P;
-				if (!load_point<C>(P, points + (size_t)i * 8 * N)) {
-					memset(o, 0, 8 * N);
+				if (!load_point<C>(P, points + (size_t)i * 2 * C::PLEN)) {
+					memset(o, 0, 2 * C::PLEN);
 					status[i] = -1;
 					continue;
 				}
@@ -198,10 +200,10 @@ int hostsim_ecdsa_verify_batch(int curve_id, int w, uint32_t n, const uint8_t *s
 		const std::vector<uint32_t> &tab = table_for<C>(w);
 		for (uint32_t i = 0; i < n; i++) {
 			Fe<N> r, s, e;
-			load_be<N>(r, sigs + (size_t)i * 8 * N);
-			load_be<N>(s, sigs + (size_t)i * 8 * N + 4 * N);
+			load_be<N>(r, sigs + (size_t)i * 2 * C::QLEN, C::QLEN);
+			load_be<N>(s, sigs + (size_t)i * 2 * C::QLEN + C::QLEN, C::QLEN);
 			Aff<C> Y;
-			bool ok = load_point<C>(Y, pubkeys + (size_t)i * 8 * N);
+			bool ok = load_point<C>(Y, pubkeys + (size_t)i * 2 * C::PLEN);
 			digest_to_scalar<C>(e, digests + (size_t)i * hlen, hlen);
 			g_fe_mul_count = 0;
 			ok = ok && (ecdsa_verify_core<C>(r, s, e, Y, tab.data(), w) == 0);
@@ -226,7 +228,7 @@ int hostsim_point_op(int curve_id, int which, const uint8_t *p1, const uint8_t *
 		};
 		Jac<C> A, B, R;
 		Aff<C> a, b;
-		bool a_inf = is_zero_buf(p1, 8 * N), b_inf = is_zero_buf(p2, 8 * N);
+		bool a_inf = is_zero_buf(p1, 2 * C::PLEN), b_inf = is_zero_buf(p2, 2 * C::PLEN);
 		if (a_inf) G::set_inf(A);
 		else {
 			if (!load_point<C>(a, p1)) return -1;

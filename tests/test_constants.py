@@ -30,7 +30,7 @@ def parse_inc():
 def test_generated_constants(curve):
     inc = parse_inc()
     p, q = PRIME[curve], ORDER[curve]
-    n = (p.bit_length() + 31) // 32
+    n = 2 * ((p.bit_length() + 63) // 64)  # two device words per reference limb
     R = 1 << (32 * n)
     for tag, mod in (("Fp_" + curve, p), ("Fq_" + curve, q)):
         f = inc[tag]

@@ -4,7 +4,7 @@ the C ABI); it keeps kernel-algorithm bugs from costing GPU minutes and yields M
 import numpy as np
 import pytest
 
-from common import (ALL_CURVES, CURVES, HASHLEN, ORDER, PRIME, edge_scalars, golden, hostsim_lib, hx, make_signatures,
+from common import (hx_fit, ALL_CURVES, CURVES, HASHLEN, ORDER, PRIME, edge_scalars, golden, hostsim_lib, hx, make_signatures,
                     oracle_smul, oracle_verify, random_scalars, rng, _buf)
 
 
@@ -28,13 +28,14 @@ def test_field_ops_against_integers(curve):
     lib = hostsim_lib()
     cid, plen, _ = ALL_CURVES[curve]
     g = rng(11)
+    rbits = 64 * ((PRIME[curve].bit_length() + 63) // 64)  # the reference's R = 2^(64 * wlen)
     for which, mod in ((0, PRIME[curve]), (1, ORDER[curve])):
         n = 200
         a = rand_mod(g, mod, n) + [0, 1, mod - 1, mod - 1, 0]
         b = rand_mod(g, mod, n) + [0, mod - 1, mod - 1, 1, mod - 1]
         out = np.zeros(len(a) * plen, dtype=np.uint8)
         assert lib.hostsim_fp_mul(cid, which, len(a), _buf(be(a, plen)), _buf(be(b, plen)), _buf(out)) == 0
-        rinv = pow(1 << (8 * plen), -1, mod)
+        rinv = pow(1 << rbits, -1, mod)
         assert from_be(out, plen) == [x * y * rinv % mod for x, y in zip(a, b)]
     p = PRIME[curve]
     a = rand_mod(g, p, 100) + [0, p - 1, 1]
@@ -98,12 +99,12 @@ def test_scalar_mult_matches_oracle(curve, w):
         assert (st2 == wst2).all() and (out2 == want2).all() and wst2[3] == -1
 
 
-@pytest.mark.parametrize("curve", ["SECP256R1", "SECP384R1"])
+@pytest.mark.parametrize("curve", ["SECP256R1", "SECP384R1", "SECP521R1"])
 def test_ecccdh_kat(curve):
     lib = hostsim_lib()
     cid, plen, qlen = ALL_CURVES[curve]
     vecs = [v for v in golden("ecccdh_kat.json") if v["curve"] == curve]
-    d = np.stack([hx(v["priv"]) for v in vecs]); peers = np.stack([hx(v["peer_pub"]) for v in vecs])
+    d = np.stack([hx_fit(v["priv"], ALL_CURVES[v["curve"]][2]) for v in vecs]); peers = np.stack([hx(v["peer_pub"]) for v in vecs])
     n = len(vecs)
     out = np.zeros((n, 2 * plen), dtype=np.uint8); st = np.zeros(n, dtype=np.int8)
     lib.hostsim_prj_pt_mul_batch(cid, 5, n, _buf(d), None, _buf(out), _buf(st))
@@ -120,7 +121,7 @@ def test_ecdsa_verify_core_kat_and_wycheproof_sample():
         lib.hostsim_ecdsa_verify_batch(cid, 4, 1, _buf(hx(v["sig"])), _buf(hx(v["pub"])), _buf(hx(v["digest"])),
                                        HASHLEN[v["hash"]], _buf(out))
         assert out[0] == 0, v["name"]
-    for curve in ("SECP256R1", "SECP384R1", "BRAINPOOLP256R1", "SECP256K1"):
+    for curve in ("SECP256R1", "SECP384R1", "BRAINPOOLP256R1", "SECP256K1", "SECP521R1"):
         cid, plen, qlen = ALL_CURVES[curve]
         vecs = [v for v in golden("wycheproof_ecdsa.json.gz")
                 if v["curve"] == curve and len(v["sig"]) == 4 * qlen and len(v["pub"]) == 4 * plen]

@@ -56,7 +56,20 @@ CURVES = {
         0xfffffffffffffffffffffffffffffffebaaedce6af48a03bbfd25e8cd0364141,
         0x79be667ef9dcbbac55a06295ce870b07029bfcdb2dce28d959f2815b16f81798,
         0x483ada7726a3c4655da4fbfc0e1108a8fd17b448a68554199c47d08ffb10d4b8),
+    # 521-bit instantiation: 9 reference limbs = 18 device words, byte lengths (66) not a multiple of 4
+    "SECP521R1": (6,
+        (1 << 521) - 1,
+        (1 << 521) - 4,
+        0x0051953eb9618e1c9a1f929a21a0b68540eea2da725b99b315f3b8b489918ef109e156193951ec7e937b1652c0bd3bb1bf073573df883d2c34f1ef451fd46b503f00,
+        0x01fffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffa51868783bf2f966b7fcc0148f709a5d03bb5c9b8899c47aebb6fb71e91386409,
+        0x00c6858e06b70404e9cd9e3ecb662395b4429c648139053fb521f828af606b4d3dbaa14b5e77efe75928fe1dc127a2ffa8de3348b3c1856a429bf97e7e31c2e5bd66,
+        0x011839296a789a3bc0045c8a5fb42c7d1bd998f54449579b446817afbd17273e662c97ee72995ef42640c550b9013fad0761353c7086a272c24088be94769fd16650),
 }
+
+
+def nwords(p):
+    """Device words per element: two per 64-bit limb of the reference (nn wlen), so that R = 2^(32N) is the reference's."""
+    return 2 * ((p.bit_length() + 63) // 64)
 
 
 def words(x, n):
@@ -70,6 +83,7 @@ def field_block(tag, mod, n):
     out.append("struct %s {" % tag)
     out.append("    static constexpr int N = %d;" % n)
     out.append("    static constexpr int BITS = %d;" % mod.bit_length())
+    out.append("    static constexpr int BYTES = %d;  /* wire length (big-endian) */" % ((mod.bit_length() + 7) // 8))
     out.append("    static constexpr uint32_t M0 = 0x%08xu;  /* -mod^-1 mod 2^32 */" % m0)
     out.append("    ECC_CONST_ARRAY(P, %d, %s);      /* modulus */" % (n, words(mod, n)))
     out.append("    ECC_CONST_ARRAY(ONE, %d, %s);    /* R mod m */" % (n, words(R % mod, n)))
@@ -82,8 +96,8 @@ def field_block(tag, mod, n):
 def main():
     lines = ["/* GENERATED by tools/gen_curve_constants.py — do not edit. 32-bit little-endian words. */", ""]
     for name, (cid, p, a, b, q, gx, gy) in CURVES.items():
-        n = (p.bit_length() + 31) // 32
-        assert (q.bit_length() + 31) // 32 == n
+        n = nwords(p)
+        assert nwords(q) == n
         a_kind = 0 if a == p - 3 else (1 if a == 0 else 2)   # selects the doubling formula in ec.cuh
         assert (gy * gy - (gx ** 3 + a * gx + b)) % p == 0
         R = 1 << (32 * n)

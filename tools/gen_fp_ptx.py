@@ -27,7 +27,7 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from gen_curve_constants import CURVES  # noqa: E402
+from gen_curve_constants import CURVES, nwords  # noqa: E402
 
 MASK = 0xFFFFFFFF
 
@@ -463,7 +463,7 @@ def render_asm(prog: Prog, n: int, two_inputs=True, indent="\t\t"):
 
 def fields():
     for name, (cid, p, a, b, q, gx, gy) in CURVES.items():
-        n = (p.bit_length() + 31) // 32
+        n = nwords(p)
         yield f"Fp_{name}", n, p
         yield f"Fq_{name}", n, q
 
