@@ -83,8 +83,8 @@ static int run_direct(const char *dropin_path)
 		printf("FAIL missing drop-in symbols\n");
 		return 1;
 	}
-	const char *names[5] = { "SECP256R1", "FRP256V1", "SECP384R1", "BRAINPOOLP256R1", "SECP256K1" };
-	for (int c = 0; c < 5; c++) {
+	const char *names[6] = { "SECP256R1", "FRP256V1", "SECP384R1", "BRAINPOOLP256R1", "SECP256K1", "SECP521R1" };
+	for (int c = 0; c < 6; c++) {
 		ec_params params;
 		CHECK(!load_params(&params, names[c]), "import_params %s", names[c]);
 		u8 qlen = (u8)BYTECEIL(params.ec_gen_order_bitlen);
@@ -94,7 +94,7 @@ static int run_direct(const char *dropin_path)
 		CHECK(!prj_pt_add(&base2, &tmp, &params.ec_gen), "add"); /* 3G with Z != 1 */
 		u16 lens[5] = { qlen, 1, (u16)(qlen + 8), 72, (u16)(2 * qlen) };
 		for (int t = 0; t < 10; t++) {
-			u8 kb[96];
+			u8 kb[160];
 			u16 kl = lens[t % 5];
 			for (u16 i = 0; i < kl; i++) kb[i] = rnd8();
 			nn k;
@@ -146,7 +146,7 @@ static int run_direct(const char *dropin_path)
 			static nn ks[NB];
 			int rets[NB];
 			for (int i = 0; i < NB; i++) {
-				u8 kb[64];
+				u8 kb[96];
 				for (int j = 0; j < qlen; j++) kb[j] = rnd8();
 				CHECK(!nn_init_from_buf(&ks[i], kb, qlen), "nn");
 				CHECK(!prj_pt_copy(&in[i], (i % 3) ? &base2 : &params.ec_gen), "copy");
@@ -168,7 +168,7 @@ static int run_direct(const char *dropin_path)
 			const ec_pub_key *pk[NS];
 			u8 sl[NS];
 			u32 ml[NS];
-			hash_alg_type ht = (c == 2) ? SHA384 : SHA256;
+			hash_alg_type ht = (c == 2) ? SHA384 : ((c == 5) ? SHA512 : SHA256);
 			for (int i = 0; i < NS; i++) {
 				CHECK(!ec_key_pair_gen(&kp[i], &params, ECDSA), "keygen");
 				ml[i] = (u32)(1 + (rnd8() % 39));
@@ -210,12 +210,12 @@ static int run_preload(void)
 		return 1;
 	}
 	unsigned long long c0 = calls();
-	const char *names[5] = { "SECP256R1", "FRP256V1", "SECP384R1", "BRAINPOOLP256R1", "SECP256K1" };
-	for (int c = 0; c < 5; c++) {
+	const char *names[6] = { "SECP256R1", "FRP256V1", "SECP384R1", "BRAINPOOLP256R1", "SECP256K1", "SECP521R1" };
+	for (int c = 0; c < 6; c++) {
 		ec_params params;
 		CHECK(!load_params(&params, names[c]), "import_params");
 		u8 qlen = (u8)BYTECEIL(params.ec_gen_order_bitlen);
-		hash_alg_type ht = (c == 2) ? SHA384 : SHA256;
+		hash_alg_type ht = (c == 2) ? SHA384 : ((c == 5) ? SHA512 : SHA256);
 		for (int t = 0; t < 6; t++) {
 			ec_key_pair kp;
 			u8 sig[2 * 66], msg[32];
@@ -237,7 +237,7 @@ static int run_preload(void)
 	}
 	unsigned long long used = calls() - c0;
 	printf("preload: %llu prj_pt_mul calls served by the GPU drop-in\n", used);
-	CHECK(used >= 5 * (6 * 4 + 4), "too few interposed calls (%llu): the reference did not go through the drop-in", used);
+	CHECK(used >= 6 * (6 * 4 + 4), "too few interposed calls (%llu): the reference did not go through the drop-in", used);
 	return failures != 0;
 }
 

@@ -206,7 +206,8 @@ def test_ecdsa_scalar_preparation_mod_q(curve):
     for hlen in (20, qlen, 64):
         n = 500
         sig = g.integers(0, 256, size=(n, 2 * qlen), dtype=np.uint8)
-        sig[:, 0] &= 0x7F; sig[:, qlen] &= 0x7F          # r, s < q
+        top = ((1 << (q.bit_length() - 8 * (qlen - 1))) - 1) >> 1
+        sig[:, 0] &= top; sig[:, qlen] &= top            # r, s < q
         sig[0, qlen:] = 0; sig[0, -1] = 1                # s = 1
         sig[1, qlen:] = np.frombuffer((q - 1).to_bytes(qlen, "big"), dtype=np.uint8)
         dg = g.integers(0, 256, size=(n, hlen), dtype=np.uint8)
@@ -214,7 +215,8 @@ def test_ecdsa_scalar_preparation_mod_q(curve):
         uv = engine(curve, 8).ecdsa_uv_batch(sig, dg, hlen)
         for i in range(n):
             r = int.from_bytes(sig[i, :qlen].tobytes(), "big"); s = int.from_bytes(sig[i, qlen:].tobytes(), "big")
-            e = int.from_bytes(dg[i, :min(hlen, qlen)].tobytes(), "big") % q
+            take = min(hlen, qlen)                       # leftmost min(8*hlen, bitlen(q)) bits (ecdsa_common.c:760-775)
+            e = (int.from_bytes(dg[i, :take].tobytes(), "big") >> max(0, 8 * take - q.bit_length())) % q
             w = pow(s, -1, q)
             assert int.from_bytes(uv[i, :qlen].tobytes(), "big") == e * w % q
             assert int.from_bytes(uv[i, qlen:].tobytes(), "big") == r * w % q
