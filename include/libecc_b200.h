@@ -140,6 +140,47 @@ int eccb200_ecdsa_verify_msgs_batch(eccb200_ctx *ctx, int hash_type, uint32_t n,
 				    const uint8_t *pubkeys, const uint8_t *msgs, const uint64_t *offsets,
 				    int8_t *verdict);
 
+/*
+ * The reference's structured key / signature records, batched.  `alg` is the reference's
+ * ec_alg_type (ECDSA = 1, DECDSA = 14; src/lib_ecc_types.h:22-), `hash_type` its hash_alg_type; the third header byte
+ * is the context's curve id.
+ *   structured public key   [0][alg][curve] X || Y || Z   3 + 3*plen bytes  (src/sig/ec_key.c:451-497)
+ *   structured private key  [1][alg][curve] x             3 + priv_len bytes, priv_len >= qlen
+ *                                                          (src/sig/ec_key.c:358-408; EC_PRIV_KEY_EXPORT_SIZE
+ *                                                          src/sig/ec_key.h:75-83 is 64 or 66 in the default build)
+ *   structured signature    [alg][hash][curve] r || s     3 + 2*qlen bytes  (src/sig/sig_algs.c:742-790)
+ */
+#define ECCB200_ALG_ECDSA 1
+#define ECCB200_ALG_DECDSA 14
+
+/* ec_structured_pub_key_import_from_buf (src/sig/ec_key.c:410-449) -> affine keys [n][2*plen] for the verify entry
+ * points.  status: 0 ok, 1 the key is the point at infinity (the reference accepts that import), -1 rejected (header,
+ * coordinate >= p, not on the curve: prj_pt_import_from_buf src/curves/prj_pt.c:462-500). */
+int eccb200_structured_pub_key_import_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *records, int alg,
+					    uint8_t *pubkeys, int8_t *status);
+
+/* ec_structured_pub_key_export_to_buf (src/sig/ec_key.c:451-497) of affine keys; Z is written as 1. */
+int eccb200_structured_pub_key_export_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *pubkeys, int alg,
+					    uint8_t *records);
+
+/* ec_structured_key_pair_import_from_priv_key_buf (src/sig/ec_key.c:499-545: header check, x < q
+ * src/sig/ecdsa_common.c:188, Y = x*G :193) followed by the structured export of the public half.
+ * status: 0 ok, 1 x = 0 (Y at infinity), -1 rejected. */
+int eccb200_structured_key_pair_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *priv_records, uint32_t priv_len,
+				      int alg, uint8_t *pub_records, int8_t *status);
+
+/* ec_structured_sig_import_from_buf (src/sig/sig_algs.c:702-740) + ec_structured_pub_key_import_from_buf +
+ * ec_verify on pre-hashed messages, per item; verdict 0 / -1 like eccb200_ecdsa_verify_batch. */
+int eccb200_ecdsa_verify_structured_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *sig_records,
+					  const uint8_t *pub_records, int alg, int hash_type, const uint8_t *digests,
+					  uint32_t hlen, int8_t *verdict);
+
+/* eccb200_ecdsa_sign_batch on structured private keys, producing structured signatures
+ * (ec_structured_sig_export_to_buf src/sig/sig_algs.c:742-790). */
+int eccb200_ecdsa_sign_structured_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *priv_records, uint32_t priv_len,
+					int alg, int hash_type, const uint8_t *nonces, const uint8_t *digests,
+					uint32_t hlen, uint8_t *sig_records, int8_t *status);
+
 /* Page-locked host memory for the host-pointer entry points (wrappers of cudaHostAlloc / cudaFreeHost so that a C
  * caller need not link the CUDA runtime).  NULL on failure. */
 void *eccb200_host_alloc(size_t bytes);

@@ -27,6 +27,8 @@ ABI_SYMBOLS = [
     "eccb200_profile_enable", "eccb200_profile_read", "eccb200_imad_peak", "eccb200_prj_pt_unique_batch",
     "eccb200_host_alloc", "eccb200_host_alloc_input", "eccb200_host_free", "eccb200_ecdsa_sign_batch", "eccb200_ecdsa_sign_batch_dev",
     "eccb200_ecccdh_derive_batch", "eccb200_ecccdh_derive_batch_dev", "eccb200_fp_mul_chain_bench", "eccb200_hash_batch", "eccb200_ecdsa_verify_msgs_batch",
+    "eccb200_structured_pub_key_import_batch", "eccb200_structured_pub_key_export_batch",
+    "eccb200_structured_key_pair_batch", "eccb200_ecdsa_verify_structured_batch", "eccb200_ecdsa_sign_structured_batch",
 ]
 
 _lib = None
@@ -69,6 +71,13 @@ def load_library() -> ctypes.CDLL:
                                                ctypes.POINTER(ctypes.c_float)]
     lib.eccb200_hash_batch.argtypes = [ctypes.c_void_p, ctypes.c_int, u32, u8p, u8p, u8p]
     lib.eccb200_ecdsa_verify_msgs_batch.argtypes = [ctypes.c_void_p, ctypes.c_int, u32, u8p, u8p, u8p, u8p, i8p]
+    lib.eccb200_structured_pub_key_import_batch.argtypes = [ctypes.c_void_p, u32, u8p, ctypes.c_int, u8p, i8p]
+    lib.eccb200_structured_pub_key_export_batch.argtypes = [ctypes.c_void_p, u32, u8p, ctypes.c_int, u8p]
+    lib.eccb200_structured_key_pair_batch.argtypes = [ctypes.c_void_p, u32, u8p, u32, ctypes.c_int, u8p, i8p]
+    lib.eccb200_ecdsa_verify_structured_batch.argtypes = [ctypes.c_void_p, u32, u8p, u8p, ctypes.c_int, ctypes.c_int,
+                                                          u8p, u32, i8p]
+    lib.eccb200_ecdsa_sign_structured_batch.argtypes = [ctypes.c_void_p, u32, u8p, u32, ctypes.c_int, ctypes.c_int,
+                                                        u8p, u8p, u32, u8p, i8p]
     lib.eccb200_host_alloc.argtypes = [ctypes.c_size_t]
     lib.eccb200_host_alloc.restype = ctypes.c_void_p
     lib.eccb200_host_alloc_input.argtypes = [ctypes.c_size_t]
@@ -222,7 +231,9 @@ class Engine:
                     "eccb200_ecccdh_derive_batch")
         return shared, status
 
-    HASH_IDS = {"SHA256": 2, "SHA384": 3, "SHA512": 4}   # libecc hash_alg_type
+    HASH_IDS = {"SHA256": 2, "SHA384": 3, "SHA512": 4}   # libecc hash_alg_type values hashed on the device
+    REF_HASH_IDS = {"SHA224": 1, "SHA256": 2, "SHA384": 3, "SHA512": 4, "SHA3_224": 5, "SHA3_256": 6, "SHA3_384": 7,
+                    "SHA3_512": 8}                        # header byte of structured signatures (lib_ecc_types.h:82-)
     HASH_LEN = {"SHA256": 32, "SHA384": 48, "SHA512": 64}
 
     @staticmethod
@@ -249,6 +260,63 @@ class Engine:
                                                              pk.ctypes.data, blob.ctypes.data, off.ctypes.data,
                                                              verdict.ctypes.data), "eccb200_ecdsa_verify_msgs_batch")
         return verdict
+
+    # ---- the reference's structured key / signature records (include/libecc_b200.h)
+    def structured_pub_key_import_batch(self, records, alg: int = 1) -> Tuple[np.ndarray, np.ndarray]:
+        rec = _as_u8(records)
+        n = rec.size // (3 + 3 * self.plen)
+        out = np.zeros((n, 2 * self.plen), dtype=np.uint8)
+        status = np.zeros(n, dtype=np.int8)
+        self._check(self.lib.eccb200_structured_pub_key_import_batch(self._h, n, rec.ctypes.data, alg, out.ctypes.data,
+                                                                     status.ctypes.data),
+                    "eccb200_structured_pub_key_import_batch")
+        return out, status
+
+    def structured_pub_key_export_batch(self, pubkeys, alg: int = 1) -> np.ndarray:
+        pk = _as_u8(pubkeys)
+        n = pk.size // (2 * self.plen)
+        out = np.zeros((n, 3 + 3 * self.plen), dtype=np.uint8)
+        self._check(self.lib.eccb200_structured_pub_key_export_batch(self._h, n, pk.ctypes.data, alg, out.ctypes.data),
+                    "eccb200_structured_pub_key_export_batch")
+        return out
+
+    def structured_key_pair_batch(self, priv_records, priv_len: int, alg: int = 1) -> Tuple[np.ndarray, np.ndarray]:
+        rec = _as_u8(priv_records)
+        n = rec.size // (3 + priv_len)
+        out = np.zeros((n, 3 + 3 * self.plen), dtype=np.uint8)
+        status = np.zeros(n, dtype=np.int8)
+        self._check(self.lib.eccb200_structured_key_pair_batch(self._h, n, rec.ctypes.data, priv_len, alg,
+                                                               out.ctypes.data, status.ctypes.data),
+                    "eccb200_structured_key_pair_batch")
+        return out, status
+
+    def ecdsa_verify_structured_batch(self, sig_records, pub_records, hash_name: str, digests, hlen: int,
+                                      alg: int = 1) -> np.ndarray:
+        sr = _as_u8(sig_records)
+        n = sr.size // (3 + 2 * self.qlen)
+        pr = _as_u8(pub_records, n * (3 + 3 * self.plen))
+        dg = _as_u8(digests, n * hlen)
+        verdict = np.zeros(n, dtype=np.int8)
+        self._check(self.lib.eccb200_ecdsa_verify_structured_batch(self._h, n, sr.ctypes.data, pr.ctypes.data, alg,
+                                                                   self.REF_HASH_IDS[hash_name], dg.ctypes.data, hlen,
+                                                                   verdict.ctypes.data),
+                    "eccb200_ecdsa_verify_structured_batch")
+        return verdict
+
+    def ecdsa_sign_structured_batch(self, priv_records, priv_len: int, nonces, hash_name: str, digests, hlen: int,
+                                    alg: int = 1) -> Tuple[np.ndarray, np.ndarray]:
+        rec = _as_u8(priv_records)
+        n = rec.size // (3 + priv_len)
+        k = _as_u8(nonces, n * self.qlen)
+        dg = _as_u8(digests, n * hlen)
+        out = np.zeros((n, 3 + 2 * self.qlen), dtype=np.uint8)
+        status = np.zeros(n, dtype=np.int8)
+        self._check(self.lib.eccb200_ecdsa_sign_structured_batch(self._h, n, rec.ctypes.data, priv_len, alg,
+                                                                 self.REF_HASH_IDS[hash_name], k.ctypes.data,
+                                                                 dg.ctypes.data, hlen, out.ctypes.data,
+                                                                 status.ctypes.data),
+                    "eccb200_ecdsa_sign_structured_batch")
+        return out, status
 
     def prj_pt_unique_batch(self, prj_points) -> Tuple[np.ndarray, np.ndarray]:
         pp = _as_u8(prj_points)

@@ -555,13 +555,15 @@ ECC_HD void ecdsa_uv(Fe<C::N> &u, Fe<C::N> &v, const Fe<C::N> &r, const Fe<C::N>
  * accept iff x(W') mod q == r.  Returns 0 valid, 2 infinity, 3 mismatch. */
 template <class C>
 ECC_HD int ecdsa_verify_tail(const Fe<C::N> &r, const Fe<C::N> &u, const Fe<C::N> &v, const Aff<C> &Y,
-			     const uint32_t *__restrict__ table, int w)
+			     const uint32_t *__restrict__ table, int w, bool y_inf = false)
 {
 	typedef Field<typename C::Fp> F;
 	constexpr int N = C::N;
 	Jac<C> uG, W;
 	comb_mul<C>(uG, u, table, w);
-	window_mul<C>(W, v, Y, &uG); /* W' = vY + uG (:796) */
+	if (!y_inf) window_mul<C>(W, v, Y, &uG); /* W' = vY + uG (:796) */
+	else W = uG; /* a public key imported as the point at infinity (possible through the projective key formats,
+	                sig/ec_key.c:139): v*Y = infinity, exactly what the reference's complete formulas compute */
 	if (EC<C>::is_inf(W)) return 2; /* (:799-800) */
 
 	Fe<N> z2, c, t;

@@ -5,6 +5,7 @@
 #include "../../include/libecc_b200.h"
 #include "kernels.cuh"
 #include "sha2.cuh"
+#include "wire.cuh"
 
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -710,6 +711,223 @@ extern "C" int eccb200_ecdsa_verify_msgs_batch(eccb200_ctx *ctx, int hash_type, 
 	if (!rc && cudaMemcpy(verdict, d_v, n, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail("D2H copy failed");
 	cudaFree(d);
 	return rc;
+}
+
+/* ------------------------------------------------------------------------------------------ structured wire formats (§8f.2) */
+
+static inline uint32_t grid_bytes(uint64_t total) { return (uint32_t)((total + 255) / 256); }
+static inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+/* device scratch of the structured-record entry points: one allocation, carved into 16-byte aligned pieces */
+struct DevArena {
+	uint8_t *base = nullptr;
+	size_t used = 0, cap = 0;
+	std::vector<size_t> want;
+	size_t reserve(size_t bytes)
+	{
+		want.push_back(align16(bytes));
+		return want.size() - 1;
+	}
+	int commit()
+	{
+		for (size_t b : want) cap += b;
+		return cudaMalloc(&base, cap ? cap : 16) == cudaSuccess ? 0 : -1;
+	}
+	uint8_t *get(size_t idx)
+	{
+		size_t off = 0;
+		for (size_t i = 0; i < idx; i++) off += want[i];
+		return base + off;
+	}
+	~DevArena()
+	{
+		if (base) cudaFree(base);
+	}
+};
+
+/* records (device) -> validated affine keys + state (0 ok, 1 infinity, -1 rejected); d_prj: [n][3*plen] scratch */
+static int structured_pub_import_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_rec, int alg, uint8_t *d_prj,
+				     uint8_t *d_aff, int8_t *d_state, cudaStream_t st)
+{
+	const uint32_t pl = ctx->plen, stride = 3 + 3 * pl;
+	k_struct_unpack<<<grid_bytes((uint64_t)n * 3 * pl), 256, 0, st>>>(n, d_rec, stride, 3 * pl, d_prj, 3 * pl);
+	int rc = dispatch(ctx->curve_id, [&](auto c) {
+		typedef decltype(c) C;
+		LaunchMisc<C>::prj_unique(affine_grid(ctx, n), n, d_prj, ctx->jac, ctx->prefix, d_aff, d_state, st);
+		return 0;
+	});
+	if (rc) return rc;
+	k_struct_check<<<grid_for(n), kThreads, 0, st>>>(n, d_rec, stride, 0 /* EC_PUBKEY */, (uint8_t)alg,
+							 (uint8_t)ctx->curve_id, 0, d_state);
+	ctx->launches += 4;
+	CUDA_OK(cudaGetLastError());
+	return 0;
+}
+
+/* ec_structured_pub_key_import_from_buf (sig/ec_key.c:410-449) for n records of 3 + 3*plen bytes: header check,
+ * coordinates < p, point on the curve, normalisation to affine.  status: 0 ok, 1 the key is the point at infinity
+ * (the reference imports it), -1 rejected.  Rejected / infinity slots of `pubkeys` are zero. */
+extern "C" int eccb200_structured_pub_key_import_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *records, int alg,
+							 uint8_t *pubkeys, int8_t *status)
+{
+	if (!ctx || (n && (!records || !pubkeys || !status))) return fail("null argument");
+	if (n == 0) return 0;
+	CUDA_OK(cudaSetDevice(ctx->device));
+	if (ensure_work(ctx, n)) return -1;
+	const size_t pl = ctx->plen, rec_b = (size_t)n * (3 + 3 * pl);
+	DevArena a;
+	const size_t i_rec = a.reserve(rec_b), i_prj = a.reserve((size_t)n * 3 * pl), i_aff = a.reserve((size_t)n * 2 * pl),
+		     i_st = a.reserve(n);
+	if (a.commit()) return fail("cudaMalloc failed");
+	CUDA_OK(cudaMemcpy(a.get(i_rec), records, rec_b, cudaMemcpyHostToDevice));
+	if (structured_pub_import_dev(ctx, n, a.get(i_rec), alg, a.get(i_prj), a.get(i_aff), (int8_t *)a.get(i_st), 0))
+		return -1;
+	CUDA_OK(cudaMemcpy(pubkeys, a.get(i_aff), (size_t)n * 2 * pl, cudaMemcpyDeviceToHost));
+	CUDA_OK(cudaMemcpy(status, a.get(i_st), n, cudaMemcpyDeviceToHost));
+	for (uint32_t i = 0; i < n; i++)
+		if (status[i] < 0) memset(pubkeys + (size_t)i * 2 * pl, 0, 2 * pl);
+	return 0;
+}
+
+/* ec_structured_pub_key_export_to_buf (sig/ec_key.c:451-497) for n affine keys: records of 3 + 3*plen bytes with
+ * Z = 1 (a representation the reference's import accepts; its own export carries whatever Z the key holds). */
+extern "C" int eccb200_structured_pub_key_export_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *pubkeys, int alg,
+							 uint8_t *records)
+{
+	if (!ctx || (n && (!pubkeys || !records))) return fail("null argument");
+	if (n == 0) return 0;
+	CUDA_OK(cudaSetDevice(ctx->device));
+	const size_t pl = ctx->plen, rec_b = (size_t)n * (3 + 3 * pl);
+	DevArena a;
+	const size_t i_aff = a.reserve((size_t)n * 2 * pl), i_st = a.reserve(n), i_rec = a.reserve(rec_b);
+	if (a.commit()) return fail("cudaMalloc failed");
+	CUDA_OK(cudaMemcpy(a.get(i_aff), pubkeys, (size_t)n * 2 * pl, cudaMemcpyHostToDevice));
+	CUDA_OK(cudaMemset(a.get(i_st), 0, n));
+	k_struct_pack_pub<<<grid_bytes(rec_b), 256>>>(n, a.get(i_aff), (uint32_t)pl, (const int8_t *)a.get(i_st), 0,
+						     (uint8_t)alg, (uint8_t)ctx->curve_id, a.get(i_rec));
+	ctx->launches += 1;
+	CUDA_OK(cudaGetLastError());
+	CUDA_OK(cudaMemcpy(records, a.get(i_rec), rec_b, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+/* ec_structured_key_pair_import_from_priv_key_buf (sig/ec_key.c:499-545) + ec_structured_pub_key_export_to_buf for
+ * n private-key records of 3 + priv_len bytes: header check, x < q (sig/ecdsa_common.c:188), Y = x*G on the
+ * fixed-base path (K1 + K4), structured public-key records out.  status: 0 ok, 1 x = 0 (Y at infinity), -1 rejected. */
+extern "C" int eccb200_structured_key_pair_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *priv_records,
+						   uint32_t priv_len, int alg, uint8_t *pub_records, int8_t *status)
+{
+	if (!ctx || (n && (!priv_records || !pub_records || !status))) return fail("null argument");
+	if (priv_len < ctx->qlen || priv_len > 252) return fail("priv_len must be in [qlen, 252]");
+	if (n == 0) return 0;
+	CUDA_OK(cudaSetDevice(ctx->device));
+	if (ensure_work(ctx, n)) return -1;
+	const size_t pl = ctx->plen, ql = ctx->qlen, in_b = (size_t)n * (3 + priv_len), out_b = (size_t)n * (3 + 3 * pl);
+	DevArena a;
+	const size_t i_in = a.reserve(in_b), i_sc = a.reserve((size_t)n * ql), i_aff = a.reserve((size_t)n * 2 * pl),
+		     i_st = a.reserve(n), i_out = a.reserve(out_b);
+	if (a.commit()) return fail("cudaMalloc failed");
+	CUDA_OK(cudaMemcpy(a.get(i_in), priv_records, in_b, cudaMemcpyHostToDevice));
+	int8_t *d_st = (int8_t *)a.get(i_st);
+	k_struct_unpack<<<grid_bytes((uint64_t)n * ql), 256>>>(n, a.get(i_in), 3 + priv_len, priv_len, a.get(i_sc),
+							      (uint32_t)ql);
+	if (smul_dev(ctx, n, a.get(i_sc), nullptr, a.get(i_aff), d_st, ctx->jac, ctx->prefix, 0)) return -1;
+	int rc = dispatch(ctx->curve_id, [&](auto c) {
+		typedef decltype(c) C;
+		LaunchMisc<C>::scalar_below_order(n, a.get(i_sc), d_st, 0);
+		return 0;
+	});
+	if (rc) return rc;
+	k_struct_check<<<grid_for(n), kThreads>>>(n, a.get(i_in), 3 + priv_len, 1 /* EC_PRIVKEY */, (uint8_t)alg,
+						  (uint8_t)ctx->curve_id, priv_len - (uint32_t)ql, d_st);
+	k_struct_pack_pub<<<grid_bytes(out_b), 256>>>(n, a.get(i_aff), (uint32_t)pl, d_st, 0, (uint8_t)alg,
+						     (uint8_t)ctx->curve_id, a.get(i_out));
+	ctx->launches += 4;
+	CUDA_OK(cudaGetLastError());
+	CUDA_OK(cudaMemcpy(pub_records, a.get(i_out), out_b, cudaMemcpyDeviceToHost));
+	CUDA_OK(cudaMemcpy(status, d_st, n, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+/* ECDSA verification on the reference's record formats: structured signatures (3 + 2*qlen bytes,
+ * ec_structured_sig_import_from_buf sig/sig_algs.c:702) and structured public keys (3 + 3*plen bytes), digests as in
+ * eccb200_ecdsa_verify_batch.  A record whose header does not name (alg, hash_type, this curve) / (EC_PUBKEY, alg, this
+ * curve) fails like the reference's callers fail it (tests/ec_utils.c verify path); a key imported as the point at
+ * infinity is verified the way the reference's complete formulas do (W' = u*G). */
+extern "C" int eccb200_ecdsa_verify_structured_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *sig_records,
+						       const uint8_t *pub_records, int alg, int hash_type,
+						       const uint8_t *digests, uint32_t hlen, int8_t *verdict)
+{
+	if (!ctx || (n && (!sig_records || !pub_records || !digests || !verdict))) return fail("null argument");
+	if (hlen == 0 || hlen > 128) return fail("bad digest length");
+	if (n == 0) return 0;
+	CUDA_OK(cudaSetDevice(ctx->device));
+	if (ensure_work(ctx, n)) return -1;
+	const size_t pl = ctx->plen, ql = ctx->qlen, sr_b = (size_t)n * (3 + 2 * ql), pr_b = (size_t)n * (3 + 3 * pl);
+	DevArena a;
+	const size_t i_sr = a.reserve(sr_b), i_pr = a.reserve(pr_b), i_dg = a.reserve((size_t)n * hlen),
+		     i_sig = a.reserve((size_t)n * 2 * ql), i_prj = a.reserve((size_t)n * 3 * pl),
+		     i_aff = a.reserve((size_t)n * 2 * pl), i_st = a.reserve(n), i_v = a.reserve(n);
+	if (a.commit()) return fail("cudaMalloc failed");
+	CUDA_OK(cudaMemcpy(a.get(i_sr), sig_records, sr_b, cudaMemcpyHostToDevice));
+	CUDA_OK(cudaMemcpy(a.get(i_pr), pub_records, pr_b, cudaMemcpyHostToDevice));
+	CUDA_OK(cudaMemcpy(a.get(i_dg), digests, (size_t)n * hlen, cudaMemcpyHostToDevice));
+	int8_t *d_st = (int8_t *)a.get(i_st);
+	if (structured_pub_import_dev(ctx, n, a.get(i_pr), alg, a.get(i_prj), a.get(i_aff), d_st, 0)) return -1;
+	k_struct_unpack<<<grid_bytes((uint64_t)n * 2 * ql), 256>>>(n, a.get(i_sr), (uint32_t)(3 + 2 * ql),
+								  (uint32_t)(2 * ql), a.get(i_sig), (uint32_t)(2 * ql));
+	k_struct_check<<<grid_for(n), kThreads>>>(n, a.get(i_sr), (uint32_t)(3 + 2 * ql), (uint8_t)alg, (uint8_t)hash_type,
+						  (uint8_t)ctx->curve_id, 0, d_st);
+	int rc = dispatch(ctx->curve_id, [&](auto c) {
+		typedef decltype(c) C;
+		LaunchVerify<C>::verify(n, a.get(i_sig), a.get(i_aff), a.get(i_dg), hlen, ctx->table, ctx->w,
+					(int8_t *)a.get(i_v), 0, d_st);
+		return 0;
+	});
+	if (rc) return rc;
+	ctx->launches += 3;
+	CUDA_OK(cudaGetLastError());
+	CUDA_OK(cudaMemcpy(verdict, a.get(i_v), n, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+/* ECDSA signing on the record formats: structured private keys in, structured signatures (3 + 2*qlen bytes) out;
+ * nonces and digests as in eccb200_ecdsa_sign_batch.  status as there (0 / 2 retry / -1), -1 also for a bad record. */
+extern "C" int eccb200_ecdsa_sign_structured_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *priv_records,
+						     uint32_t priv_len, int alg, int hash_type, const uint8_t *nonces,
+						     const uint8_t *digests, uint32_t hlen, uint8_t *sig_records,
+						     int8_t *status)
+{
+	if (!ctx || (n && (!priv_records || !nonces || !digests || !sig_records || !status))) return fail("null argument");
+	if (priv_len < ctx->qlen || priv_len > 252) return fail("priv_len must be in [qlen, 252]");
+	if (hlen == 0 || hlen > 128) return fail("bad digest length");
+	if (n == 0) return 0;
+	CUDA_OK(cudaSetDevice(ctx->device));
+	if (ensure_work(ctx, n)) return -1;
+	const size_t ql = ctx->qlen, in_b = (size_t)n * (3 + priv_len), out_b = (size_t)n * (3 + 2 * ql);
+	DevArena a;
+	const size_t i_in = a.reserve(in_b), i_d = a.reserve((size_t)n * ql), i_k = a.reserve((size_t)n * ql),
+		     i_dg = a.reserve((size_t)n * hlen), i_sig = a.reserve((size_t)n * 2 * ql), i_st = a.reserve(n),
+		     i_out = a.reserve(out_b);
+	if (a.commit()) return fail("cudaMalloc failed");
+	CUDA_OK(cudaMemcpy(a.get(i_in), priv_records, in_b, cudaMemcpyHostToDevice));
+	CUDA_OK(cudaMemcpy(a.get(i_k), nonces, (size_t)n * ql, cudaMemcpyHostToDevice));
+	CUDA_OK(cudaMemcpy(a.get(i_dg), digests, (size_t)n * hlen, cudaMemcpyHostToDevice));
+	int8_t *d_st = (int8_t *)a.get(i_st);
+	k_struct_unpack<<<grid_bytes((uint64_t)n * ql), 256>>>(n, a.get(i_in), 3 + priv_len, priv_len, a.get(i_d),
+							      (uint32_t)ql);
+	if (sign_dev(ctx, n, a.get(i_d), a.get(i_k), a.get(i_dg), hlen, a.get(i_sig), d_st, ctx->jac, ctx->prefix, ctx->aff,
+		     0))
+		return -1;
+	k_struct_check<<<grid_for(n), kThreads>>>(n, a.get(i_in), 3 + priv_len, 1 /* EC_PRIVKEY */, (uint8_t)alg,
+						  (uint8_t)ctx->curve_id, priv_len - (uint32_t)ql, d_st);
+	k_struct_pack<<<grid_bytes(out_b), 256>>>(n, a.get(i_sig), (uint32_t)(2 * ql), d_st, (uint8_t)alg,
+						 (uint8_t)hash_type, (uint8_t)ctx->curve_id, a.get(i_out));
+	ctx->launches += 3;
+	CUDA_OK(cudaGetLastError());
+	CUDA_OK(cudaMemcpy(sig_records, a.get(i_out), out_b, cudaMemcpyDeviceToHost));
+	CUDA_OK(cudaMemcpy(status, d_st, n, cudaMemcpyDeviceToHost));
+	return 0;
 }
 
 /* Page-locked host memory for callers that do not link CUDA themselves (cudaHostAlloc / cudaFreeHost). */

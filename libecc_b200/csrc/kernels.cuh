@@ -594,8 +594,11 @@ __global__ void __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VERIFY : (C::N <= 1
 						      const uint8_t *__restrict__ pubkeys,
 						      const uint8_t *__restrict__ digests, uint32_t hlen,
 						      const uint32_t *__restrict__ table, int w,
-						      int8_t *__restrict__ verdict)
+						      int8_t *__restrict__ verdict,
+						      const int8_t *__restrict__ key_state)
 {
+	/* key_state (optional, from the structured-key import): 0 = pubkeys[i] is a validated affine point, 1 = the key
+	 * is the point at infinity (pubkeys[i] ignored), -1 = the key or signature record was rejected */
 	typedef Field<typename C::Fq> Fq;
 	constexpr int N = C::N;
 	const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -613,7 +616,9 @@ __global__ void __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VERIFY : (C::N <= 1
 	cta_inverse_128<typename C::Fq>(wm, sm);
 	if (!active) return;
 	Aff<C> Y;
+	const int ks = key_state ? (int)key_state[idx] : 0;
 	bool key_ok = load_affine_checked<C>(Y, pubkeys + (size_t)idx * (2 * C::PLEN));
+	key_ok = (key_ok && ks == 0) || ks == 1;
 	digest_to_scalar<C>(e, digests + (size_t)idx * hlen, hlen);
 	int code = 4;
 	if (key_ok) {
@@ -622,7 +627,7 @@ __global__ void __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VERIFY : (C::N <= 1
 			Fe<N> u, v;
 			Fq::mul(u, e, wm); /* u = e * s^-1 mod q  (:786) */
 			Fq::mul(v, r, wm); /* v = r * s^-1 mod q  (:791) */
-			code = ecdsa_verify_tail<C>(r, u, v, Y, table, w);
+			code = ecdsa_verify_tail<C>(r, u, v, Y, table, w, ks == 1);
 		}
 	}
 #if defined(ECC_VERDICT_DEBUG)
@@ -715,6 +720,19 @@ __global__ void __launch_bounds__(128) k_ecdsa_sign_finish(uint32_t n, const uin
 		status[e] = (int8_t)st;
 		if (e < T) break;
 	}
+}
+
+/* Private-key sanity check of __ecdsa_init_pub_key (sig/ecdsa_common.c:188): x < q, else the key is rejected (-1).
+ * Run before K1, which would silently reduce x mod q.  state[i] is only ever lowered to -1. */
+template <class C>
+__global__ void __launch_bounds__(128) k_scalar_below_order(uint32_t n, const uint8_t *__restrict__ scalars,
+							     int8_t *__restrict__ state)
+{
+	uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= n) return;
+	Fe<C::N> k;
+	load_wire<C::N, C::QLEN>(k, scalars + (size_t)idx * C::QLEN);
+	if (Field<typename C::Fq>::geq_mod(k)) state[idx] = -1;
 }
 
 /* ------------------------------------------------------------------------------------------ unit-test kernels */
@@ -901,13 +919,15 @@ template <class C> struct LaunchMisc {
 				const uint8_t *digests, uint32_t hlen, const uint8_t *kG_aff, uint32_t *prefix,
 				uint8_t *sigs, int8_t *status, cudaStream_t st);
 	static void fp_mul(int which, uint32_t n, const uint8_t *a, const uint8_t *b, uint8_t *out, cudaStream_t st);
+	static void scalar_below_order(uint32_t n, const uint8_t *scalars, int8_t *state, cudaStream_t st);
 	static void fp_mul_chain(int striped, uint32_t n, const uint8_t *a, const uint8_t *b, uint8_t *out, int iters,
 				 cudaStream_t st);
 };
 
 template <class C> struct LaunchVerify {
 	static void verify(uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys, const uint8_t *digests,
-			   uint32_t hlen, const uint32_t *table, int w, int8_t *verdict, cudaStream_t st);
+			   uint32_t hlen, const uint32_t *table, int w, int8_t *verdict, cudaStream_t st,
+			   const int8_t *key_state = nullptr);
 	static void uv(uint32_t n, const uint8_t *sigs, const uint8_t *digests, uint32_t hlen, uint8_t *out,
 		       cudaStream_t st);
 };
@@ -984,6 +1004,11 @@ void LaunchMisc<C>::to_table(uint32_t blocks, uint32_t n, const uint32_t *jac, u
 	k_to_affine<C, 1><<<blocks, kThreads, 0, st>>>(n, jac, prefix, nullptr, nullptr, table);
 }
 template <class C>
+void LaunchMisc<C>::scalar_below_order(uint32_t n, const uint8_t *scalars, int8_t *state, cudaStream_t st)
+{
+	k_scalar_below_order<C><<<grid_for(n), kThreads, 0, st>>>(n, scalars, state);
+}
+template <class C>
 void LaunchMisc<C>::fp_mul(int which, uint32_t n, const uint8_t *a, const uint8_t *b, uint8_t *out, cudaStream_t st)
 {
 	if (which == 0)
@@ -1017,9 +1042,11 @@ void LaunchMisc<C>::fp_mul_chain(int striped, uint32_t n, const uint8_t *a, cons
 #if defined(ECC_TU_VERIFY)
 template <class C>
 void LaunchVerify<C>::verify(uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys, const uint8_t *digests,
-			     uint32_t hlen, const uint32_t *table, int w, int8_t *verdict, cudaStream_t st)
+			     uint32_t hlen, const uint32_t *table, int w, int8_t *verdict, cudaStream_t st,
+			     const int8_t *key_state)
 {
-	k_ecdsa_verify<C><<<grid_for(n), kThreads, 0, st>>>(n, sigs, pubkeys, digests, hlen, table, w, verdict);
+	k_ecdsa_verify<C><<<grid_for(n), kThreads, 0, st>>>(n, sigs, pubkeys, digests, hlen, table, w, verdict,
+							     key_state);
 }
 template <class C>
 void LaunchVerify<C>::uv(uint32_t n, const uint8_t *sigs, const uint8_t *digests, uint32_t hlen, uint8_t *out,

@@ -267,6 +267,66 @@ int ref_ecdsa_sign_batch(const char *curve, const char *hash, uint32_t n, const 
 	return run_sig_jobs(sign_worker, &p, n, nthreads);
 }
 
+/* ---------------------------------------------------------------- structured key / signature records (sig/ec_key.c) */
+
+/* ec_key_pair_import_from_priv_key_buf + the two structured exports.  Returns the import's code; lengths out. */
+int ref_structured_keygen(const char *curve, const uint8_t *priv, uint32_t priv_len, uint8_t *priv_rec,
+			  uint32_t *priv_rec_len, uint8_t *pub_rec, uint32_t *pub_rec_len)
+{
+	ref_curve c;
+	ec_key_pair kp;
+	if (ref_load_curve(&c, curve)) return -2;
+	if (ec_key_pair_import_from_priv_key_buf(&kp, &c.params, priv, (u8)priv_len, ECDSA)) return -1;
+	*priv_rec_len = EC_STRUCTURED_PRIV_KEY_EXPORT_SIZE(&kp.priv_key);
+	*pub_rec_len = EC_STRUCTURED_PUB_KEY_EXPORT_SIZE(&kp.pub_key);
+	if (ec_structured_priv_key_export_to_buf(&kp.priv_key, priv_rec, (u8)*priv_rec_len)) return -3;
+	if (ec_structured_pub_key_export_to_buf(&kp.pub_key, pub_rec, (u8)*pub_rec_len)) return -3;
+	return 0;
+}
+
+/* ec_structured_pub_key_import_from_buf; on success the affine point (or is_inf = 1) */
+int ref_structured_pub_import(const char *curve, const uint8_t *rec, uint32_t len, uint8_t *aff, int *is_inf)
+{
+	ref_curve c;
+	ec_pub_key pk;
+	int z = 0;
+	if (ref_load_curve(&c, curve)) return -2;
+	*is_inf = 0;
+	memset(aff, 0, 2 * c.plen);
+	if (ec_structured_pub_key_import_from_buf(&pk, &c.params, rec, (u8)len, ECDSA)) return -1;
+	if (prj_pt_iszero(&pk.y, &z)) return -3;
+	if (z) {
+		*is_inf = 1;
+		return 0;
+	}
+	if (prj_pt_export_to_aff_buf(&pk.y, aff, 2 * c.plen)) return -3;
+	return 0;
+}
+
+/* What the reference's verify front end does with structured inputs (tests/ec_utils.c, verify_bin_file): import the
+ * key record, import the signature record and require its (alg, hash, curve) to match, then ec_verify. */
+int ref_structured_verify(const char *curve, const char *hash, const uint8_t *sig_rec, uint32_t sig_rec_len,
+			  const uint8_t *pub_rec, uint32_t pub_rec_len, const uint8_t *msg, uint32_t mlen)
+{
+	ref_curve c;
+	ec_pub_key pk;
+	const hash_mapping *hm = NULL;
+	u8 sig[EC_MAX_SIGLEN], name[MAX_CURVE_NAME_LEN];
+	ec_alg_type st;
+	hash_alg_type ht;
+	u32 siglen;
+	int same = 0;
+	if (ref_load_curve(&c, curve)) return -2;
+	if (get_hash_by_name(hash, &hm) || !hm) return -2;
+	if (ec_structured_pub_key_import_from_buf(&pk, &c.params, pub_rec, (u8)pub_rec_len, ECDSA)) return -1;
+	if (sig_rec_len < 3 || sig_rec_len - 3 > EC_MAX_SIGLEN) return -1;
+	siglen = sig_rec_len - 3;
+	if (ec_structured_sig_import_from_buf(sig, siglen, sig_rec, sig_rec_len, &st, &ht, name)) return -1;
+	if (st != ECDSA || ht != hm->type) return -1;
+	if (are_str_equal((const char *)name, (const char *)c.params.curve_name, &same) || !same) return -1;
+	return ec_verify(sig, (u8)siglen, &pk, msg, mlen, ECDSA, hm->type, NULL, 0) ? -1 : 0;
+}
+
 /* sizeof/offsetof facts about the reference's structs (used to pin include/libecc_b200_dropin.h's mirror). */
 int ref_abi_facts(uint64_t *out, uint32_t nmax)
 {
