@@ -34,6 +34,10 @@ extern "C" {
 #define ECCB200_BRAINPOOLP384R1 12
 #define ECCB200_SECP256K1 19
 #define ECCB200_SECP521R1 6
+#define ECCB200_SM2P256V1 17
+#define ECCB200_BRAINPOOLP512R1 9
+#define ECCB200_SECP224R1 3
+#define ECCB200_SECP192R1 2
 
 /* Per-item status codes written by the batch calls. */
 #define ECCB200_OK 0        /* finite result / valid signature                                          */

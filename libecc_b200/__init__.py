@@ -16,7 +16,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ECCB200_LIB", os.path.join(_HERE, "libecc_b200.so"))
 
 CURVE_IDS = {"FRP256V1": 1, "SECP256R1": 4, "SECP384R1": 5,   # libecc ec_curve_type (src/lib_ecc_types.h:147-)
-             "BRAINPOOLP256R1": 8, "BRAINPOOLP384R1": 12, "SECP256K1": 19, "SECP521R1": 6}
+             "BRAINPOOLP256R1": 8, "BRAINPOOLP384R1": 12, "SECP256K1": 19, "SECP521R1": 6,
+             "SM2P256V1": 17, "BRAINPOOLP512R1": 9, "SECP224R1": 3, "SECP192R1": 2}
 
 # Every symbol include/libecc_b200.h and include/libecc_b200_dropin.h declare (tests check they are exported).
 ABI_SYMBOLS = [

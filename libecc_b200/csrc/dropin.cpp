@@ -26,7 +26,7 @@ constexpr uint64_t kFpMagic = 0x14e96c8ab28221efULL;     /* fp/fp.c:127 */
 constexpr uint64_t kNnMagic = 0xb4cf5d56e2023316ULL ^ (uint64_t)(ECCB200_NN_MAX_WORD_LEN + 64); /* nn/nn.c:28 */
 constexpr uint64_t kPubKeyMagic = 0x31327f37741ffb76ULL; /* sig/ec_key.h:118 */
 constexpr int kMaxWords = ECCB200_NN_MAX_WORD_LEN;
-constexpr int kNumCurves = 7;
+constexpr int kNumCurves = 11;
 
 struct CurveInfo {
 	int id;
@@ -57,7 +57,11 @@ const CurveInfo *curves()
 	static const CurveInfo tab[kNumCurves] = { make_info<Curve_SECP256R1>(),       make_info<Curve_FRP256V1>(),
 						    make_info<Curve_SECP384R1>(),       make_info<Curve_BRAINPOOLP256R1>(),
 						    make_info<Curve_BRAINPOOLP384R1>(), make_info<Curve_SECP256K1>(),
-						    make_info<Curve_SECP521R1>() };
+						    make_info<Curve_SECP521R1>(),
+						    make_info<Curve_SM2P256V1>(),
+						    make_info<Curve_BRAINPOOLP512R1>(),
+						    make_info<Curve_SECP224R1>(),
+						    make_info<Curve_SECP192R1>() };
 	return tab;
 }
 

@@ -79,6 +79,10 @@ template <class Fn> static int dispatch(int curve_id, Fn &&fn)
 	case ECCB200_BRAINPOOLP384R1: return fn(Curve_BRAINPOOLP384R1());
 	case ECCB200_SECP256K1: return fn(Curve_SECP256K1());
 	case ECCB200_SECP521R1: return fn(Curve_SECP521R1());
+	case ECCB200_SM2P256V1: return fn(Curve_SM2P256V1());
+	case ECCB200_BRAINPOOLP512R1: return fn(Curve_BRAINPOOLP512R1());
+	case ECCB200_SECP224R1: return fn(Curve_SECP224R1());
+	case ECCB200_SECP192R1: return fn(Curve_SECP192R1());
 	default: return fail("unknown curve id");
 	}
 }

@@ -1,0 +1,6 @@
+/* translation unit: LaunchMisc kernels for BRAINPOOLP512R1 (split so that the kernel groups compile in parallel) */
+#define ECC_TU_MISC
+#include "kernels.cuh"
+namespace eccb200 {
+template struct LaunchMisc<Curve_BRAINPOOLP512R1>;
+}

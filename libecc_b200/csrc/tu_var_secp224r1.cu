@@ -1,0 +1,6 @@
+/* translation unit: LaunchVar kernels (K2 + direct table build) for SECP224R1; out-of-line multiplier */
+#define ECC_TU_VAR
+#include "kernels.cuh"
+namespace eccb200 {
+template struct LaunchVar<Curve_SECP224R1>;
+}

@@ -22,7 +22,9 @@ SEED = 0x6C69626563632D31  # "libecc-1" 
 CURVES = {"SECP256R1": (4, 32, 32), "FRP256V1": (1, 32, 32), "SECP384R1": (5, 48, 48)}  # id, plen, qlen
 # additional curves: same kernels, generic-a / a = 0 doubling
 EXTRA_CURVES = {"BRAINPOOLP256R1": (8, 32, 32), "BRAINPOOLP384R1": (12, 48, 48), "SECP256K1": (19, 32, 32),
-                "SECP521R1": (6, 66, 66)}  # 521-bit: byte lengths not a multiple of the word size
+                "SECP521R1": (6, 66, 66),
+                "SM2P256V1": (17, 32, 32), "BRAINPOOLP512R1": (9, 64, 64), "SECP224R1": (3, 28, 28),
+                "SECP192R1": (2, 24, 24)}  # 521-bit: byte lengths not a multiple of the word size
 ALL_CURVES = dict(CURVES, **EXTRA_CURVES)
 ORDER = {
     "SECP256R1": 0xffffffff00000000ffffffffffffffffbce6faada7179e84f3b9cac2fc632551,
@@ -32,6 +34,10 @@ ORDER = {
     "BRAINPOOLP384R1": 0x8cb91e82a3386d280f5d6f7e50e641df152f7109ed5456b31f166e6cac0425a7cf3ab6af6b7fc3103b883202e9046565,
     "SECP256K1": 0xfffffffffffffffffffffffffffffffebaaedce6af48a03bbfd25e8cd0364141,
     "SECP521R1": 0x01fffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffa51868783bf2f966b7fcc0148f709a5d03bb5c9b8899c47aebb6fb71e91386409,
+    "SM2P256V1": 0xfffffffeffffffffffffffffffffffff7203df6b21c6052b53bbf40939d54123,
+    "BRAINPOOLP512R1": 0xaadd9db8dbe9c48b3fd4e6ae33c9fc07cb308db3b3c9d20ed6639cca70330870553e5c414ca92619418661197fac10471db1d381085ddaddb58796829ca90069,
+    "SECP224R1": 0xffffffffffffffffffffffffffff16a2e0b8f03e13dd29455c5c2a3d,
+    "SECP192R1": 0xffffffffffffffffffffffff99def836146bc9b1b4d22831,
 }
 PRIME = {
     "SECP256R1": 0xffffffff00000001000000000000000000000000ffffffffffffffffffffffff,
@@ -41,6 +47,10 @@ PRIME = {
     "BRAINPOOLP384R1": 0x8cb91e82a3386d280f5d6f7e50e641df152f7109ed5456b412b1da197fb71123acd3a729901d1a71874700133107ec53,
     "SECP256K1": 0xfffffffffffffffffffffffffffffffffffffffffffffffffffffffefffffc2f,
     "SECP521R1": (1 << 521) - 1,
+    "SM2P256V1": 0xfffffffeffffffffffffffffffffffffffffffff00000000ffffffffffffffff,
+    "BRAINPOOLP512R1": 0xaadd9db8dbe9c48b3fd4e6ae33c9fc07cb308db3b3c9d20ed6639cca703308717d4d9b009bc66842aecda12ae6a380e62881ff2f2d82c68528aa6056583a48f3,
+    "SECP224R1": 0xffffffffffffffffffffffffffffffff000000000000000000000001,
+    "SECP192R1": 0xfffffffffffffffffffffffffffffffeffffffffffffffff,
 }
 HASHLEN = {"SHA224": 28, "SHA256": 32, "SHA384": 48, "SHA512": 64, "SHA3_224": 28, "SHA3_256": 32,
            "SHA3_384": 48, "SHA3_512": 64}

@@ -83,8 +83,9 @@ static int run_direct(const char *dropin_path)
 		printf("FAIL missing drop-in symbols\n");
 		return 1;
 	}
-	const char *names[6] = { "SECP256R1", "FRP256V1", "SECP384R1", "BRAINPOOLP256R1", "SECP256K1", "SECP521R1" };
-	for (int c = 0; c < 6; c++) {
+	const char *names[8] = { "SECP256R1", "FRP256V1", "SECP384R1", "BRAINPOOLP256R1", "SECP256K1", "SECP521R1",
+				 "SECP224R1", "BRAINPOOLP512R1" };
+	for (int c = 0; c < 8; c++) {
 		ec_params params;
 		CHECK(!load_params(&params, names[c]), "import_params %s", names[c]);
 		u8 qlen = (u8)BYTECEIL(params.ec_gen_order_bitlen);
@@ -168,7 +169,7 @@ static int run_direct(const char *dropin_path)
 			const ec_pub_key *pk[NS];
 			u8 sl[NS];
 			u32 ml[NS];
-			hash_alg_type ht = (c == 2) ? SHA384 : ((c == 5) ? SHA512 : SHA256);
+			hash_alg_type ht = (c == 2) ? SHA384 : ((c == 5 || c == 7) ? SHA512 : SHA256);
 			for (int i = 0; i < NS; i++) {
 				CHECK(!ec_key_pair_gen(&kp[i], &params, ECDSA), "keygen");
 				ml[i] = (u32)(1 + (rnd8() % 39));
@@ -210,12 +211,13 @@ static int run_preload(void)
 		return 1;
 	}
 	unsigned long long c0 = calls();
-	const char *names[6] = { "SECP256R1", "FRP256V1", "SECP384R1", "BRAINPOOLP256R1", "SECP256K1", "SECP521R1" };
-	for (int c = 0; c < 6; c++) {
+	const char *names[8] = { "SECP256R1", "FRP256V1", "SECP384R1", "BRAINPOOLP256R1", "SECP256K1", "SECP521R1",
+				 "SECP224R1", "BRAINPOOLP512R1" };
+	for (int c = 0; c < 8; c++) {
 		ec_params params;
 		CHECK(!load_params(&params, names[c]), "import_params");
 		u8 qlen = (u8)BYTECEIL(params.ec_gen_order_bitlen);
-		hash_alg_type ht = (c == 2) ? SHA384 : ((c == 5) ? SHA512 : SHA256);
+		hash_alg_type ht = (c == 2) ? SHA384 : ((c == 5 || c == 7) ? SHA512 : SHA256);
 		for (int t = 0; t < 6; t++) {
 			ec_key_pair kp;
 			u8 sig[2 * 66], msg[32];
@@ -237,7 +239,7 @@ static int run_preload(void)
 	}
 	unsigned long long used = calls() - c0;
 	printf("preload: %llu prj_pt_mul calls served by the GPU drop-in\n", used);
-	CHECK(used >= 6 * (6 * 4 + 4), "too few interposed calls (%llu): the reference did not go through the drop-in", used);
+	CHECK(used >= 8 * (6 * 4 + 4), "too few interposed calls (%llu): the reference did not go through the drop-in", used);
 	return failures != 0;
 }
 

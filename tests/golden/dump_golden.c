@@ -36,7 +36,8 @@ static int wanted_curve(const ec_str_params *sp)
 	const char *n = curve_name(sp);
 	return !strcmp(n, "SECP256R1") || !strcmp(n, "SECP384R1") || !strcmp(n, "FRP256V1") ||
 	       !strcmp(n, "BRAINPOOLP256R1") || !strcmp(n, "BRAINPOOLP384R1") || !strcmp(n, "SECP256K1") ||
-	       !strcmp(n, "SECP521R1");
+	       !strcmp(n, "SECP521R1") || !strcmp(n, "SM2P256V1") || !strcmp(n, "BRAINPOOLP512R1") ||
+	       !strcmp(n, "SECP224R1") || !strcmp(n, "SECP192R1");
 }
 
 static const char *hash_name(hash_alg_type t)

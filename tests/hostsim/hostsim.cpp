@@ -29,6 +29,10 @@ template <class Fn> static int dispatch(int curve_id, Fn &&fn)
 	case 12: return fn(Curve_BRAINPOOLP384R1());
 	case 19: return fn(Curve_SECP256K1());
 	case 6: return fn(Curve_SECP521R1());
+	case 17: return fn(Curve_SM2P256V1());
+	case 9: return fn(Curve_BRAINPOOLP512R1());
+	case 3: return fn(Curve_SECP224R1());
+	case 2: return fn(Curve_SECP192R1());
 	default: return -1;
 	}
 }

@@ -38,7 +38,7 @@ def test_fp_mul_monty_against_integers(curve):
         assert got == [x * y * rinv % mod for x, y in zip(a, b)]
 
 
-@pytest.mark.parametrize("curve", ["SECP256R1", "SECP384R1", "SECP521R1"])
+@pytest.mark.parametrize("curve", ["SECP256R1", "SECP384R1", "SECP521R1", "SECP224R1", "SECP192R1"])
 def test_ecccdh_kat(curve):
     """NIST ECC-CDH vectors (reference: src/tests/ecccdh_test_vectors.h:1501-2999)."""
     _, plen, _ = ALL_CURVES[curve]
@@ -91,7 +91,8 @@ def test_variable_base_vs_oracle(curve):
     assert (out == want).all()
 
 
-WYCHE_CURVES = ["SECP256R1", "SECP384R1", "BRAINPOOLP256R1", "BRAINPOOLP384R1", "SECP256K1", "SECP521R1"]
+WYCHE_CURVES = ["SECP256R1", "SECP384R1", "BRAINPOOLP256R1", "BRAINPOOLP384R1", "SECP256K1", "SECP521R1", "BRAINPOOLP512R1",
+                "SECP224R1"]
 
 
 @pytest.mark.parametrize("curve", WYCHE_CURVES)

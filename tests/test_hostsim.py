@@ -99,7 +99,7 @@ def test_scalar_mult_matches_oracle(curve, w):
         assert (st2 == wst2).all() and (out2 == want2).all() and wst2[3] == -1
 
 
-@pytest.mark.parametrize("curve", ["SECP256R1", "SECP384R1", "SECP521R1"])
+@pytest.mark.parametrize("curve", ["SECP256R1", "SECP384R1", "SECP521R1", "SECP224R1", "SECP192R1"])
 def test_ecccdh_kat(curve):
     lib = hostsim_lib()
     cid, plen, qlen = ALL_CURVES[curve]
@@ -121,7 +121,7 @@ def test_ecdsa_verify_core_kat_and_wycheproof_sample():
         lib.hostsim_ecdsa_verify_batch(cid, 4, 1, _buf(hx(v["sig"])), _buf(hx(v["pub"])), _buf(hx(v["digest"])),
                                        HASHLEN[v["hash"]], _buf(out))
         assert out[0] == 0, v["name"]
-    for curve in ("SECP256R1", "SECP384R1", "BRAINPOOLP256R1", "SECP256K1", "SECP521R1"):
+    for curve in ("SECP256R1", "SECP384R1", "BRAINPOOLP256R1", "SECP256K1", "SECP521R1", "SECP224R1", "BRAINPOOLP512R1"):
         cid, plen, qlen = ALL_CURVES[curve]
         vecs = [v for v in golden("wycheproof_ecdsa.json.gz")
                 if v["curve"] == curve and len(v["sig"]) == 4 * qlen and len(v["pub"]) == 4 * plen]

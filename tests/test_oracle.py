@@ -10,7 +10,7 @@ from common import (hx_fit, ALL_CURVES, CURVES, HASHLEN, ORDER, edge_scalars, go
                     oracle_verify, random_scalars, ref_lib, _buf)
 
 
-@pytest.mark.parametrize("curve", ["SECP256R1", "SECP384R1", "SECP521R1"])
+@pytest.mark.parametrize("curve", ["SECP256R1", "SECP384R1", "SECP521R1", "SECP224R1", "SECP192R1"])
 def test_ecccdh_kat_fixed_and_variable_base(curve):
     vecs = [v for v in golden("ecccdh_kat.json") if v["curve"] == curve]
     assert len(vecs) == 25
@@ -43,7 +43,8 @@ def test_ecdsa_kat_verify_and_sign():
             assert st[0] == 0 and sig[0].tobytes().hex() == v["sig"], v["name"]
 
 
-WYCHE_CURVES = ["SECP256R1", "SECP384R1", "BRAINPOOLP256R1", "BRAINPOOLP384R1", "SECP256K1", "SECP521R1"]
+WYCHE_CURVES = ["SECP256R1", "SECP384R1", "BRAINPOOLP256R1", "BRAINPOOLP384R1", "SECP256K1", "SECP521R1", "BRAINPOOLP512R1",
+                "SECP224R1"]
 
 
 @pytest.mark.parametrize("curve", WYCHE_CURVES)

@@ -64,6 +64,36 @@ CURVES = {
         0x01fffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffa51868783bf2f966b7fcc0148f709a5d03bb5c9b8899c47aebb6fb71e91386409,
         0x00c6858e06b70404e9cd9e3ecb662395b4429c648139053fb521f828af606b4d3dbaa14b5e77efe75928fe1dc127a2ffa8de3348b3c1856a429bf97e7e31c2e5bd66,
         0x011839296a789a3bc0045c8a5fb42c7d1bd998f54449579b446817afbd17273e662c97ee72995ef42640c550b9013fad0761353c7086a272c24088be94769fd16650),
+    # more of the reference's short-Weierstrass parameter sets (src/curves/known/): SM2, the largest Brainpool prime
+    # (16 words), and the two small NIST primes (224 bits: 28-byte fields in 8 words; 192 bits: 6 words)
+    "SM2P256V1": (17,
+        0xfffffffeffffffffffffffffffffffffffffffff00000000ffffffffffffffff,
+        0xfffffffeffffffffffffffffffffffffffffffff00000000fffffffffffffffc,
+        0x28e9fa9e9d9f5e344d5a9e4bcf6509a7f39789f515ab8f92ddbcbd414d940e93,
+        0xfffffffeffffffffffffffffffffffff7203df6b21c6052b53bbf40939d54123,
+        0x32c4ae2c1f1981195f9904466a39c9948fe30bbff2660be1715a4589334c74c7,
+        0xbc3736a2f4f6779c59bdcee36b692153d0a9877cc62a474002df32e52139f0a0),
+    "BRAINPOOLP512R1": (9,
+        0xaadd9db8dbe9c48b3fd4e6ae33c9fc07cb308db3b3c9d20ed6639cca703308717d4d9b009bc66842aecda12ae6a380e62881ff2f2d82c68528aa6056583a48f3,
+        0x7830a3318b603b89e2327145ac234cc594cbdd8d3df91610a83441caea9863bc2ded5d5aa8253aa10a2ef1c98b9ac8b57f1117a72bf2c7b9e7c1ac4d77fc94ca,
+        0x3df91610a83441caea9863bc2ded5d5aa8253aa10a2ef1c98b9ac8b57f1117a72bf2c7b9e7c1ac4d77fc94cadc083e67984050b75ebae5dd2809bd638016f723,
+        0xaadd9db8dbe9c48b3fd4e6ae33c9fc07cb308db3b3c9d20ed6639cca70330870553e5c414ca92619418661197fac10471db1d381085ddaddb58796829ca90069,
+        0x81aee4bdd82ed9645a21322e9c4c6a9385ed9f70b5d916c1b43b62eef4d0098eff3b1f78e2d0d48d50d1687b93b97d5f7c6d5047406a5e688b352209bcb9f822,
+        0x7dde385d566332ecc0eabfa9cf7822fdf209f70024a57b1aa000c55b881f8111b2dcde494a5f485e5bca4bd88a2763aed1ca2b2fa8f0540678cd1e0f3ad80892),
+    "SECP224R1": (3,
+        0xffffffffffffffffffffffffffffffff000000000000000000000001,
+        0xfffffffffffffffffffffffffffffffefffffffffffffffffffffffe,
+        0xb4050a850c04b3abf54132565044b0b7d7bfd8ba270b39432355ffb4,
+        0xffffffffffffffffffffffffffff16a2e0b8f03e13dd29455c5c2a3d,
+        0xb70e0cbd6bb4bf7f321390b94a03c1d356c21122343280d6115c1d21,
+        0xbd376388b5f723fb4c22dfe6cd4375a05a07476444d5819985007e34),
+    "SECP192R1": (2,
+        0xfffffffffffffffffffffffffffffffeffffffffffffffff,
+        0xfffffffffffffffffffffffffffffffefffffffffffffffc,
+        0x64210519e59c80e70fa7e9ab72243049feb8deecc146b9b1,
+        0xffffffffffffffffffffffff99def836146bc9b1b4d22831,
+        0x188da80eb03090f67cbf20eb43a18800f4ff0afd82ff1012,
+        0x07192b95ffc8da78631011ed6b24cdd573f977a11e794811),
 }
 
 
