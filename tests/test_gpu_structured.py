@@ -61,7 +61,7 @@ def test_structured_records_against_reference(curve):
     cid, plen, qlen = ALL_CURVES[curve]
     q, p = ORDER[curve], PRIME[curve]
     eng = engine(curve)
-    hname = {32: "SHA256", 48: "SHA384", 66: "SHA512"}[qlen]
+    hname = "SHA256" if qlen <= 32 else ("SHA384" if qlen <= 48 else "SHA512")
     hlen = HASH[hname]().digest_size
     n = 40
     privs = [int.from_bytes(r.tobytes(), "big") for r in random_scalars(curve, n, tag=901)] + [1, q - 1]
