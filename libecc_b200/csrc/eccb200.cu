@@ -51,6 +51,12 @@ struct eccb200_ctx {
 	uint8_t *aff = nullptr;  /* [cap][2*plen] scratch (k*G of the signing path) */
 	/* host-pointer pipeline */
 	cudaStream_t streams[kStages] = {};
+	cudaEvent_t kdone[kStages] = {}; /* the next chunk's kernels may start: recorded after the chunk's LAST kernel, or
+	                                  * by the launcher after its throughput-bound kernel (kdone_set) so that the short
+	                                  * latency-bound normalisation overlaps the next chunk's scalar multiplications */
+	bool kdone_set = false;
+	cudaStream_t hi[kStages] = {};    /* highest-priority streams for the short normalisation kernels of the pipeline */
+	cudaEvent_t ndone[kStages] = {};  /* normalisation of the stage's chunk finished */
 	uint8_t *h_in[kStages] = {};   /* pinned */
 	uint8_t *h_out[kStages] = {};  /* pinned */
 	uint8_t *d_in[kStages] = {};
@@ -168,7 +174,11 @@ extern "C" int eccb200_ctx_create(eccb200_ctx **out, int curve_id, int device, i
 	ctx->device = device;
 	ctx->w = w;
 	ctx->sm_count = prop.multiProcessorCount;
-	ctx->chunk = 4u * (uint32_t)prop.multiProcessorCount * 4u * 128u;
+	{ /* pipeline chunk = full K1 waves (SMs x 4 CTAs x 128 items); ECCB200_CHUNK_WAVES overrides (tuning knob) */
+		const char *cw = getenv("ECCB200_CHUNK_WAVES");
+		uint32_t waves = (cw && atoi(cw) > 0 && atoi(cw) <= 64) ? (uint32_t)atoi(cw) : 4u;
+		ctx->chunk = waves * (uint32_t)prop.multiProcessorCount * 4u * 128u;
+	}
 	int rc = dispatch(curve_id, [&](auto c) {
 		typedef decltype(c) C;
 		ctx->N = C::N;
@@ -212,7 +222,12 @@ extern "C" int eccb200_ctx_create(eccb200_ctx **out, int curve_id, int device, i
 		return -1;
 	}
 	for (int s = 0; s < kStages; s++) {
-		if (cudaStreamCreateWithFlags(&ctx->streams[s], cudaStreamNonBlocking) != cudaSuccess) {
+		int least = 0, greatest = 0;
+		cudaDeviceGetStreamPriorityRange(&least, &greatest);
+		if (cudaStreamCreateWithPriority(&ctx->streams[s], cudaStreamNonBlocking, least) != cudaSuccess ||
+		    cudaStreamCreateWithPriority(&ctx->hi[s], cudaStreamNonBlocking, greatest) != cudaSuccess ||
+		    cudaEventCreateWithFlags(&ctx->kdone[s], cudaEventDisableTiming) != cudaSuccess ||
+		    cudaEventCreateWithFlags(&ctx->ndone[s], cudaEventDisableTiming) != cudaSuccess) {
 			eccb200_ctx_destroy(ctx);
 			return fail("cudaStreamCreate failed");
 		}
@@ -228,6 +243,9 @@ extern "C" void eccb200_ctx_destroy(eccb200_ctx *ctx)
 	cudaDeviceSynchronize();
 	for (int s = 0; s < kStages; s++) {
 		if (ctx->streams[s]) cudaStreamDestroy(ctx->streams[s]);
+		if (ctx->kdone[s]) cudaEventDestroy(ctx->kdone[s]);
+		if (ctx->hi[s]) cudaStreamDestroy(ctx->hi[s]);
+		if (ctx->ndone[s]) cudaEventDestroy(ctx->ndone[s]);
 		if (ctx->h_in[s]) cudaFreeHost(ctx->h_in[s]);
 		if (ctx->h_out[s]) cudaFreeHost(ctx->h_out[s]);
 		if (ctx->d_in[s]) cudaFree(ctx->d_in[s]);
@@ -297,8 +315,12 @@ static bool tma_staging_enabled()
 }
 
 static int smul_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_scalars, const uint8_t *d_points, uint8_t *d_out,
-		    int8_t *d_status, uint32_t *jac, uint32_t *prefix, cudaStream_t st)
+		    int8_t *d_status, uint32_t *jac, uint32_t *prefix, cudaStream_t st, cudaEvent_t after_smul = nullptr,
+		    cudaStream_t st_norm = nullptr, cudaEvent_t after_norm = nullptr)
 {
+	/* Pipeline form (after_smul / st_norm / after_norm given): the normalisation runs on a highest-priority stream
+	 * behind the scalar multiplication, so the NEXT chunk's scalar multiplication (which only waits for after_smul)
+	 * overlaps its latency-bound inversion without delaying it; `st` resumes (for the D2H) after after_norm. */
 	if (n == 0) return 0;
 	return dispatch(ctx->curve_id, [&](auto c) {
 		typedef decltype(c) C;
@@ -312,7 +334,15 @@ static int smul_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_scalars, cons
 		else
 			LaunchFixed<C>::fixed(n, d_scalars, ctx->table, ctx->w, jac, d_status, st);
 		if (prof) cudaEventRecord(pe[1], st);
-		LaunchMisc<C>::to_affine(affine_grid(ctx, n), n, jac, prefix, d_out, d_status, st);
+		if (after_smul) cudaEventRecord(after_smul, st);
+		if (st_norm && after_smul && after_norm) {
+			cudaStreamWaitEvent(st_norm, after_smul, 0);
+			LaunchMisc<C>::to_affine(affine_grid(ctx, n), n, jac, prefix, d_out, d_status, st_norm);
+			cudaEventRecord(after_norm, st_norm);
+			cudaStreamWaitEvent(st, after_norm, 0);
+		} else {
+			LaunchMisc<C>::to_affine(affine_grid(ctx, n), n, jac, prefix, d_out, d_status, st);
+		}
 		if (prof) {
 			cudaEventRecord(pe[2], st);
 			ctx->ev_kernels[ctx->ev_calls++] = 2;
@@ -439,18 +469,34 @@ static int run_pipeline(eccb200_ctx *ctx, uint32_t n, std::vector<HostCol> &in, 
 	for (auto &c : out) all_pinned = all_pinned && c.pinned;
 	if (all_pinned) {
 		/* No host-side staging: enqueue every chunk without a single host synchronisation.  Stage buffers are
-		 * reused by chunk c + kStages on the SAME stream, so stream order alone keeps them safe. */
+		 * reused by chunk c + kStages on the SAME stream, so stream order alone keeps them safe.
+		 * ECCB200_PIPE_TRACE=1 records an event after each phase of each chunk and prints the timeline
+		 * (diagnostic for DESIGN.md §7; the events cost a few microseconds per chunk). */
+		static const bool trace = getenv("ECCB200_PIPE_TRACE") && atoi(getenv("ECCB200_PIPE_TRACE")) != 0;
+		std::vector<cudaEvent_t> ev;
+		if (trace) {
+			ev.resize((size_t)nchunks * 4);
+			for (auto &e : ev) CUDA_OK(cudaEventCreate(&e));
+		}
 		for (uint32_t c = 0; c < nchunks; c++) {
 			int s = (int)(c % kStages);
 			uint32_t lo = c * kChunk, cnt = std::min(kChunk, n - lo);
 			size_t off = 0;
+			if (trace) cudaEventRecord(ev[4 * c + 0], ctx->streams[s]);
 			for (auto &col : in) {
 				size_t bytes = (size_t)cnt * col.item;
 				CUDA_OK(cudaMemcpyAsync(ctx->d_in[s] + off, col.host + (size_t)lo * col.item, bytes,
 							cudaMemcpyHostToDevice, ctx->streams[s]));
 				off += bytes;
 			}
+			if (trace) cudaEventRecord(ev[4 * c + 1], ctx->streams[s]);
+			/* kernels run in chunk order: without this the block scheduler interleaves the CTAs of the chunks
+			 * queued on the other streams, every chunk finishes late and no D2H overlaps the arithmetic */
+			if (c > 0) CUDA_OK(cudaStreamWaitEvent(ctx->streams[s], ctx->kdone[(c - 1) % kStages], 0));
+			ctx->kdone_set = false;
 			if (launch(s, cnt)) return -1;
+			if (!ctx->kdone_set) CUDA_OK(cudaEventRecord(ctx->kdone[s], ctx->streams[s]));
+			if (trace) cudaEventRecord(ev[4 * c + 2], ctx->streams[s]);
 			off = 0;
 			for (auto &col : out) {
 				size_t bytes = (size_t)cnt * col.item;
@@ -458,8 +504,20 @@ static int run_pipeline(eccb200_ctx *ctx, uint32_t n, std::vector<HostCol> &in, 
 							cudaMemcpyDeviceToHost, ctx->streams[s]));
 				off += bytes;
 			}
+			if (trace) cudaEventRecord(ev[4 * c + 3], ctx->streams[s]);
 		}
 		for (int s = 0; s < kStages; s++) CUDA_OK(cudaStreamSynchronize(ctx->streams[s]));
+		if (trace) {
+			fprintf(stderr, "[eccb200 pipe] n=%u chunk=%u: per chunk, ms since the first copy was enqueued: "
+					"h2d_start h2d_end kernels_end d2h_end\n", n, kChunk);
+			for (uint32_t c = 0; c < nchunks; c++) {
+				float t[4];
+				for (int k = 0; k < 4; k++) cudaEventElapsedTime(&t[k], ev[0], ev[4 * c + k]);
+				fprintf(stderr, "[eccb200 pipe]   chunk %u (stream %u): %.3f %.3f %.3f %.3f\n", c, c % kStages, t[0], t[1],
+					t[2], t[3]);
+			}
+			for (auto &e : ev) cudaEventDestroy(e);
+		}
 		return 0;
 	}
 	std::vector<uint32_t> pending_lo(kStages, 0), pending_cnt(kStages, 0);
@@ -489,7 +547,10 @@ static int run_pipeline(eccb200_ctx *ctx, uint32_t n, std::vector<HostCol> &in, 
 			CUDA_OK(cudaMemcpyAsync(ctx->d_in[s] + off, src, bytes, cudaMemcpyHostToDevice, ctx->streams[s]));
 			off += bytes;
 		}
+		if (c > 0) CUDA_OK(cudaStreamWaitEvent(ctx->streams[s], ctx->kdone[(c - 1) % kStages], 0));
+		ctx->kdone_set = false;
 		if (launch(s, cnt)) return -1;
+		if (!ctx->kdone_set) CUDA_OK(cudaEventRecord(ctx->kdone[s], ctx->streams[s]));
 		off = 0;
 		for (auto &col : out) {
 			size_t bytes = (size_t)cnt * col.item;
@@ -538,7 +599,9 @@ extern "C" int eccb200_prj_pt_mul_batch(eccb200_ctx *ctx, uint32_t n, const uint
 		const uint8_t *d_pt = points ? ctx->d_in[s] + (size_t)cnt * sl : nullptr;
 		uint8_t *d_o = ctx->d_out[s];
 		int8_t *d_st = (int8_t *)(ctx->d_out[s] + (size_t)cnt * pl);
-		return smul_dev(ctx, cnt, d_sc, d_pt, d_o, d_st, ctx->stage_jac[s], ctx->stage_prefix[s], ctx->streams[s]);
+		ctx->kdone_set = true;
+		return smul_dev(ctx, cnt, d_sc, d_pt, d_o, d_st, ctx->stage_jac[s], ctx->stage_prefix[s], ctx->streams[s],
+				ctx->kdone[s], ctx->hi[s], ctx->ndone[s]);
 	});
 }
 
