@@ -428,23 +428,71 @@ template <class C> ECC_HD void comb_mul(Jac<C> &acc, const Fe<C::N> &k, const ui
 	}
 }
 
+/* One field inversion for the calling thread alone: the inverter of the host build of the tests and of the one-off
+ * table construction.  K2 / K3 pass an inverter that shares ONE Fermat chain among the 128 threads of the CTA
+ * (cta_inverse_128, kernels.cuh); an inverter of that kind must be called by every thread of the CTA. */
+template <class C> struct ThreadInverter {
+	ECC_HD void operator()(Fe<C::N> &r, const Fe<C::N> &a) const { Field<typename C::Fp>::inv(r, a); }
+};
+
 /*
  * Variable base: acc = k*P (+ addend), P affine and on the curve, k < q.  Signed 4-bit fixed window:
  * K' = k + 0x88..8 (one 8 per nibble); digit_i = nibble_i(K') - 8 in [-8, 7], plus a top digit = the carry out.
- * Table tbl[j] = (j+1)*P, j = 0..7 (Jacobian, per-thread local memory).  The optional addend (uG of an ECDSA
- * verification, sig/ecdsa_common.c:796) is added by one extra trip through the same loop body, so the kernel
- * holds a single inlined copy of the general addition.
+ * Table tbl[j] = (j+1)*P, j = 0..7, built with 7 mixed additions and then made AFFINE with one inversion
+ * (Montgomery's trick over the seven Z's, and the addend's): every window addition is a mixed one (8M + 3S instead of
+ * 12M + 4S), for ~50 products of conversion plus the thread's share of the inverter.  None of the multiples is the
+ * point at infinity (the group order is a prime > 8).  The optional addend (uG of an ECDSA verification,
+ * sig/ecdsa_common.c:796) is converted by the same inversion and added by one extra trip through the loop body, so the
+ * kernel holds a single inlined copy of the addition.
  */
-template <class C>
-ECC_HD void window_mul(Jac<C> &acc, const Fe<C::N> &k, const Aff<C> &P, const Jac<C> *addend = nullptr)
+template <class C, class Inv>
+ECC_HD void window_mul(Jac<C> &acc, const Fe<C::N> &k, const Aff<C> &P, const Jac<C> *addend, const Inv &invert)
 {
 	typedef EC<C> G;
 	typedef Field<typename C::Fp> F;
 	constexpr int N = C::N;
-	Jac<C> tbl[8];
+	Jac<C> tbl[8]; /* after the conversion only X, Y are meaningful (affine) */
 	G::from_affine(tbl[0], P);
 #pragma unroll 1
 	for (int j = 1; j < 8; j++) G::add_mixed(tbl[j], tbl[j - 1], P); /* j == 1 takes the P == Q (doubling) branch */
+
+	/* simultaneous inversion of Z(2P) .. Z(8P) and of the addend's Z */
+	const bool have_add = addend != nullptr && !G::is_inf(*addend);
+	Aff<C> add_aff;
+	{
+		Fe<N> pre[7]; /* pre[j] = Z(2P) * ... * Z((j+2)P) */
+		pre[0] = tbl[1].Z;
+#pragma unroll 1
+		for (int j = 2; j < 8; j++) F::mul(pre[j - 1], pre[j - 2], tbl[j].Z);
+		Fe<N> tot = pre[6], inv, zi, zi2, zi3, t;
+		if (have_add) F::mul(tot, pre[6], addend->Z);
+		invert(inv, tot);
+		if (have_add) {
+			F::mul(zi, inv, pre[6]);
+			F::mul(t, inv, addend->Z);
+			inv = t;
+			F::sqr(zi2, zi);
+			F::mul(zi3, zi2, zi);
+			F::mul(add_aff.x, addend->X, zi2);
+			F::mul(add_aff.y, addend->Y, zi3);
+		}
+#pragma unroll 1
+		for (int j = 7; j >= 1; j--) {
+			if (j > 1) {
+				F::mul(zi, inv, pre[j - 2]);
+				F::mul(t, inv, tbl[j].Z);
+				inv = t;
+			} else {
+				zi = inv;
+			}
+			F::sqr(zi2, zi);
+			F::mul(zi3, zi2, zi);
+			F::mul(t, tbl[j].X, zi2);
+			tbl[j].X = t;
+			F::mul(t, tbl[j].Y, zi3);
+			tbl[j].Y = t;
+		}
+	}
 
 	/* K' = k + 0x88..8 over the ND = ceil(bitlen(q)/4) nibbles a reduced scalar occupies; the carry lands in
 	 * nibble ND (0 or 1).  K' is then moved to the top of the N words so that nibbles leave from the MSB end. */
@@ -472,10 +520,11 @@ ECC_HD void window_mul(Jac<C> &acc, const Fe<C::N> &k, const Aff<C> &P, const Ja
 		}
 	}
 	G::set_inf(acc);
-	if (c) acc = tbl[0]; /* top digit (weight 16^ND) is 0 or 1 */
+	if (c) G::from_affine(acc, P); /* top digit (weight 16^ND) is 0 or 1 */
 #pragma unroll 1
 	for (int di = ND - 1; di >= -1; di--) {
-		Jac<C> e, t;
+		Aff<C> e;
+		Jac<C> t;
 		bool have;
 		if (di >= 0) {
 #pragma unroll 1
@@ -486,17 +535,25 @@ ECC_HD void window_mul(Jac<C> &acc, const Fe<C::N> &k, const Aff<C> &P, const Ja
 			kk[0] <<= 4;
 			int ad = d < 0 ? -d : d;
 			have = d != 0;
-			e = tbl[(ad - 1) & 7];
-			if (d < 0) F::neg(e.Y, e.Y);
+			const Jac<C> &te = tbl[(ad - 1) & 7];
+			e.x = te.X;
+			e.y = te.Y;
+			if (d < 0) F::neg(e.y, e.y);
 		} else {
-			have = addend != nullptr;
-			if (have) e = *addend;
+			have = have_add;
+			if (have) e = add_aff;
 		}
 		if (have) {
-			G::add_full(t, acc, e);
+			G::add_mixed(t, acc, e);
 			acc = t;
 		}
 	}
+}
+
+template <class C>
+ECC_HD void window_mul(Jac<C> &acc, const Fe<C::N> &k, const Aff<C> &P, const Jac<C> *addend = nullptr)
+{
+	window_mul<C>(acc, k, P, addend, ThreadInverter<C>());
 }
 
 /* ---------------------------------------------------------------------------------------------- ECDSA */
@@ -553,17 +610,28 @@ ECC_HD void ecdsa_uv(Fe<C::N> &u, Fe<C::N> &v, const Fe<C::N> &r, const Fe<C::N>
  */
 /* Steps 7-10 of __ecdsa_verify_finalize (sig/ecdsa_common.c:796-810) given u and v: W' = uG + vY, reject infinity,
  * accept iff x(W') mod q == r.  Returns 0 valid, 2 infinity, 3 mismatch. */
-template <class C>
-ECC_HD int ecdsa_verify_tail(const Fe<C::N> &r, const Fe<C::N> &u, const Fe<C::N> &v, const Aff<C> &Y,
-			     const uint32_t *__restrict__ table, int w, bool y_inf = false)
+template <class C, class Inv>
+ECC_HD int ecdsa_verify_tail(const Fe<C::N> &r, const Fe<C::N> &u, const Fe<C::N> &v_in, const Aff<C> &Y_in,
+			     const uint32_t *__restrict__ table, int w, bool y_inf, const Inv &invert)
 {
 	typedef Field<typename C::Fp> F;
 	constexpr int N = C::N;
 	Jac<C> uG, W;
 	comb_mul<C>(uG, u, table, w);
-	if (!y_inf) window_mul<C>(W, v, Y, &uG); /* W' = vY + uG (:796) */
-	else W = uG; /* a public key imported as the point at infinity (possible through the projective key formats,
-	                sig/ec_key.c:139): v*Y = infinity, exactly what the reference's complete formulas compute */
+	/* A public key imported as the point at infinity (possible through the projective key formats,
+	 * sig/ec_key.c:139): v*Y = infinity, exactly what the reference's complete formulas compute, so W' = uG.  The
+	 * thread still walks the same code (v = 0 on a dummy base) because the inverter may be a CTA-wide one. */
+	Fe<N> v = v_in;
+	Aff<C> Y = Y_in;
+	if (y_inf) {
+#pragma unroll
+		for (int i = 0; i < N; i++) {
+			v.w[i] = 0;
+			Y.x.w[i] = C::GX_MONT(i);
+			Y.y.w[i] = C::GY_MONT(i);
+		}
+	}
+	window_mul<C>(W, v, Y, &uG, invert); /* W' = vY + uG (:796) */
 	if (EC<C>::is_inf(W)) return 2; /* (:799-800) */
 
 	Fe<N> z2, c, t;
@@ -590,6 +658,13 @@ ECC_HD int ecdsa_verify_tail(const Fe<C::N> &r, const Fe<C::N> &u, const Fe<C::N
 		}
 	}
 	return match ? 0 : 3;
+}
+
+template <class C>
+ECC_HD int ecdsa_verify_tail(const Fe<C::N> &r, const Fe<C::N> &u, const Fe<C::N> &v, const Aff<C> &Y,
+			     const uint32_t *__restrict__ table, int w, bool y_inf = false)
+{
+	return ecdsa_verify_tail<C>(r, u, v, Y, table, w, y_inf, ThreadInverter<C>());
 }
 
 /* r, s in [1, q-1]?  (__ecdsa_verify_init, sig/ecdsa_common.c:653-658) */

@@ -157,13 +157,17 @@ template <class C> __device__ __forceinline__ bool load_affine_checked(Aff<C> &P
  * runs the ~330-product Fermat chain on the CTA product, and thread t computes inv_total * P[t-1] * S[t+1].
  * Must be called by all 128 threads of the CTA (it synchronises).  Cost per thread: 16 products + 1/4 inversion.
  */
-template <class FT> __device__ __forceinline__ void cta_inverse_128(Fe<FT::N> &inv, const Fe<FT::N> &acc)
+#define ECC_CTA_INV_WORDS(N) ((4 * 128 + 1) * (N)) /* shared words one CTA-wide inversion needs */
+template <class FT>
+__device__ __forceinline__ void cta_inverse_128(Fe<FT::N> &inv, const Fe<FT::N> &acc, uint32_t *__restrict__ sh)
 {
 	typedef Field<FT> F;
 	constexpr int N = FT::N;
-	__shared__ uint32_t sP[2][128 * N]; /* double-buffered prefix scan */
-	__shared__ uint32_t sS[2][128 * N]; /* double-buffered suffix scan */
-	__shared__ uint32_t sInv[N];
+	/* sh: ECC_CTA_INV_WORDS(N) words of shared memory, owned by the kernel so that calls for different fields (mod q
+	 * and mod p in K3) reuse the same 16-37 KB */
+	uint32_t *sP[2] = { sh, sh + 128 * N };                 /* double-buffered prefix scan */
+	uint32_t *sS[2] = { sh + 2 * 128 * N, sh + 3 * 128 * N }; /* double-buffered suffix scan */
+	uint32_t *sInv = sh + 4 * 128 * N;
 	const int t = threadIdx.x;
 	auto st_sh = [&](uint32_t *base, int idx, const Fe<N> &v) {
 #pragma unroll
@@ -327,19 +331,30 @@ __global__ void __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VAR : (C::N <= 12 ?
 						  const uint8_t *__restrict__ points, uint32_t *__restrict__ jac,
 						  int8_t *__restrict__ status)
 {
-	uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= n) return;
+	/* every thread of the CTA walks the whole kernel (the table inversion is CTA-wide); threads past n and threads
+	 * whose point was rejected work on the generator and discard the result */
+	const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool active = idx < n;
+	const uint32_t i0 = active ? idx : 0;
+	__shared__ uint32_t sh_inv[ECC_CTA_INV_WORDS(C::N)];
 	Fe<C::N> k;
-	load_wire<C::N, C::QLEN>(k, scalars + (size_t)idx * C::QLEN);
+	load_wire<C::N, C::QLEN>(k, scalars + (size_t)i0 * C::QLEN);
 	scalar_reduce<C>(k);
 	Aff<C> P;
-	bool ok = load_affine_checked<C>(P, points + (size_t)idx * (2 * C::PLEN));
-	Jac<C> acc;
-	if (ok) {
-		window_mul<C>(acc, k, P);
-	} else {
-		EC<C>::set_inf(acc);
+	bool ok = load_affine_checked<C>(P, points + (size_t)i0 * (2 * C::PLEN));
+	if (!ok) {
+#pragma unroll
+		for (int j = 0; j < C::N; j++) {
+			P.x.w[j] = C::GX_MONT(j);
+			P.y.w[j] = C::GY_MONT(j);
+		}
 	}
+	Jac<C> acc;
+	window_mul<C>(acc, k, P, nullptr, [&](Fe<C::N> &r, const Fe<C::N> &a) {
+		cta_inverse_128<typename C::Fp>(r, a, sh_inv);
+	});
+	if (!active) return;
+	if (!ok) EC<C>::set_inf(acc);
 	store_jac<C>(jac, idx, acc);
 	status[idx] = ok ? 0 : -1;
 }
@@ -469,7 +484,8 @@ __global__ void __launch_bounds__(128) k_to_affine(uint32_t n, const uint32_t *_
 		}
 	}
 	Fe<N> inv;
-	cta_inverse_128<typename C::Fp>(inv, acc); /* one Fermat chain per CTA instead of one per thread */
+	__shared__ uint32_t sh_inv[ECC_CTA_INV_WORDS(N)];
+	cta_inverse_128<typename C::Fp>(inv, acc, sh_inv); /* one Fermat chain per CTA instead of one per thread */
 	if (!active) return;
 	for (uint32_t e = last;; e -= T) {
 		Fe<N> z, pre, X, Y;
@@ -610,26 +626,39 @@ __global__ void __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VERIFY : (C::N <= 1
 	load_wire<N, C::QLEN>(s, sigs + (size_t)i0 * (2 * C::QLEN) + C::QLEN);
 	const bool rs_ok = ecdsa_rs_in_range<C>(r, s);
 	/* s^-1 mod q for the whole CTA at once (sig/ecdsa_common.c:781 does one nn_modinv per signature) */
+	__shared__ uint32_t sh_inv[ECC_CTA_INV_WORDS(N)];
 	Fe<N> sm, wm;
 	Fq::set_one(sm);
 	if (rs_ok) Fq::to_mont(sm, s);
-	cta_inverse_128<typename C::Fq>(wm, sm);
-	if (!active) return;
+	cta_inverse_128<typename C::Fq>(wm, sm, sh_inv);
 	Aff<C> Y;
-	const int ks = key_state ? (int)key_state[idx] : 0;
-	bool key_ok = load_affine_checked<C>(Y, pubkeys + (size_t)idx * (2 * C::PLEN));
+	const int ks = key_state ? (int)key_state[i0] : 0;
+	bool key_ok = load_affine_checked<C>(Y, pubkeys + (size_t)i0 * (2 * C::PLEN));
 	key_ok = (key_ok && ks == 0) || ks == 1;
-	digest_to_scalar<C>(e, digests + (size_t)idx * hlen, hlen);
-	int code = 4;
-	if (key_ok) {
-		code = 1;
-		if (rs_ok) {
-			Fe<N> u, v;
-			Fq::mul(u, e, wm); /* u = e * s^-1 mod q  (:786) */
-			Fq::mul(v, r, wm); /* v = r * s^-1 mod q  (:791) */
-			code = ecdsa_verify_tail<C>(r, u, v, Y, table, w, ks == 1);
+	digest_to_scalar<C>(e, digests + (size_t)i0 * hlen, hlen);
+	/* Every thread of the CTA runs the tail (its window table is normalised by a CTA-wide inversion); a rejected
+	 * item runs it on u = v = 0 and the generator — the cheapest walk — and its result is ignored. */
+	const bool run = key_ok && rs_ok;
+	Fe<N> u, v;
+	Fq::mul(u, e, wm); /* u = e * s^-1 mod q  (:786) */
+	Fq::mul(v, r, wm); /* v = r * s^-1 mod q  (:791) */
+	if (!run) {
+		Fq::set_zero(u);
+		Fq::set_zero(v);
+	}
+	if (!run || ks == 1) {
+#pragma unroll
+		for (int j = 0; j < N; j++) {
+			Y.x.w[j] = C::GX_MONT(j);
+			Y.y.w[j] = C::GY_MONT(j);
 		}
 	}
+	int code = ecdsa_verify_tail<C>(r, u, v, Y, table, w, ks == 1, [&](Fe<N> &o, const Fe<N> &a) {
+		cta_inverse_128<typename C::Fp>(o, a, sh_inv);
+	});
+	if (!active) return;
+	if (!key_ok) code = 4;
+	else if (!rs_ok) code = 1;
 #if defined(ECC_VERDICT_DEBUG)
 	verdict[idx] = (int8_t)(-code);
 #else
@@ -678,7 +707,8 @@ __global__ void __launch_bounds__(128) k_ecdsa_sign_finish(uint32_t n, const uin
 		}
 	}
 	Fe<N> inv;
-	cta_inverse_128<typename C::Fq>(inv, acc);
+	__shared__ uint32_t sh_inv[ECC_CTA_INV_WORDS(N)];
+	cta_inverse_128<typename C::Fq>(inv, acc, sh_inv);
 	if (!active) return;
 	for (uint32_t e = last;; e -= T) {
 		Fe<N> kk, d, x, r, ev, s, zero;

@@ -27,9 +27,13 @@ def work_per_item(workload: str, comb_window: int):
     nwin = math.ceil(QBITS[curve] / comb_window)
     nib = (QBITS[curve] + 3) // 4
     m_fixed = 11 * (nwin - 1)                                   # mixed add 8M+3S per window; first window is a copy
-    m_var = 7 * 11 + 8 + nib * 4 * 8 + nib * (15.0 / 16) * 16   # table (7 madd, one of them a dbl) + 4 dbl/digit + adds
-    fermat = (QBITS[curve] // 4) * 5 + 14                       # 4 sqr + 1 mul per nibble + table
-    fermat_q = 16 + fermat / 4.0                                # CTA-wide inversion: 2 scans + 1 chain per 4 warps
+    fermat = nib * 5 + 14                                       # 4 sqr + 1 mul per nibble of the exponent + table
+    cta_inv = 16 + fermat / 4.0                                 # CTA-wide inversion per thread: 2 scans (14) + 2, and
+    #                                                             one Fermat chain run by one of the CTA's four warps
+    # variable base: 8-entry table (6 mixed adds + 1 doubling + the abandoned add that detects it), made affine with
+    # one shared inversion (6 prefix + 12 back-substitution + 7 x 4 conversion products), 4 doublings per digit
+    # (8 products each) and a mixed addition for 15 of 16 digits
+    m_var = (6 * 11 + 8 + 5) + (6 + 12 + 28) + cta_inv + nib * 4 * 8 + nib * (15.0 / 16) * 11
     if kind == "fixed":
         m, kernel = m_fixed, "k_smul_fixed"
         m_ref = M_REF[curve]
@@ -37,7 +41,9 @@ def work_per_item(workload: str, comb_window: int):
         m, kernel = m_var, "k_smul_var"
         m_ref = M_REF[curve]
     else:
-        m, kernel = m_fixed + 11 + m_var + 16 + fermat_q + 12, "k_ecdsa_verify"
+        # comb for uG, window for vY with uG folded into the table inversion (+7) and added last (+11), the mod-q
+        # inversion, u / v / key validation / final comparison (~12)
+        m, kernel = m_fixed + m_var + 7 + 11 + cta_inv + 12, "k_ecdsa_verify"
         m_ref = 2 * M_REF[curve] + 17 + (2 * QBITS[curve] + 1) + 2
     return {"M_impl": m, "kernel": kernel, "imad32_per_mul": IMAD32_PER_MUL[curve],
             "imad32_per_item": m * IMAD32_PER_MUL[curve], "imad32_ref_per_item": m_ref * IMAD32_PER_MUL[curve],
