@@ -29,18 +29,25 @@ def result(n, r):
 @pytest.mark.parametrize("tag,n,mod", list(gen_fp_ptx.fields()))
 def test_generated_streams(tag, n, mod):
     rnd = random.Random(hash(tag) & 0xFFFF)
-    mul, add, sub = gen_fp_ptx.gen_mul(n, mod), gen_fp_ptx.gen_add(n, mod), gen_fp_ptx.gen_sub(n, mod)
-    sqr = gen_fp_ptx.gen_sqr(n, mod)
+    add, sub = gen_fp_ptx.gen_add(n, mod), gen_fp_ptx.gen_sub(n, mod)
+    # every multiplier variant the header carries (generic, and the add-form reduction of 0xffffffff modulus words for
+    # the inlined / out-of-line multipliers), plus the all-words form whatever the configured shares are
+    progs = [(gen_fp_ptx.gen_mul(n, mod), gen_fp_ptx.gen_sqr(n, mod))]
+    progs += [(m, s) for _, m, s in gen_fp_ptx.variants(n, mod)]
+    full = frozenset(gen_fp_ptx.solinas_words(mod, n, n))
+    progs.append((gen_fp_ptx.gen_mul(n, mod, full), gen_fp_ptx.gen_sqr(n, mod, full)))
+    mul, sqr = progs[0]
     rinv = pow(1 << (32 * n), -1, mod)
     special = [0, 1, 2, mod - 1, mod - 2, (1 << (32 * n - 1)) % mod, (mod >> 1), (1 << 32) - 1, ((1 << 32) - 1) << 32,
                mod - (1 << 32), int("ffffffff" * n, 16) % mod, int("ffffffff" * n, 16) - mod if int("ffffffff" * n, 16) - mod < mod else 5]
     pairs = [(x, y) for x in special for y in special]
     pairs += [(rnd.randrange(mod), rnd.randrange(mod)) for _ in range(600)]
     for a, b in pairs:
-        assert result(n, mul.run(env(n, a, b))) == a * b * rinv % mod
+        for pm, ps in progs:
+            assert result(n, pm.run(env(n, a, b))) == a * b * rinv % mod
+            assert result(n, ps.run(env(n, a, b))) == a * a * rinv % mod
         assert result(n, add.run(env(n, a, b))) == (a + b) % mod
         assert result(n, sub.run(env(n, a, b))) == (a - b) % mod
-        assert result(n, sqr.run(env(n, a, b))) == a * a * rinv % mod
     wide, total = mul.count()
     m0_is_one = (-pow(mod, -1, 1 << 32)) % (1 << 32) == 1
     assert wide <= 2 * n * n and total <= 2 * (2 * n * n) + 8 * n + (0 if m0_is_one else n) + 8

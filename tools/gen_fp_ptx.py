@@ -87,6 +87,10 @@ class Prog:
                 r[dst] = t & MASK
                 if ".cc" in op:
                     cc = 1 if t < 0 else 0
+            elif op == "sub.u32":          # wrapping, leaves the carry flag alone
+                r[dst] = (v[0] - v[1]) & MASK
+            elif op == "min.u32":
+                r[dst] = min(v[0], v[1])
             elif op == "and.b32":
                 r[dst] = v[0] & v[1]
             elif op == "mov.u32":
@@ -109,8 +113,24 @@ def words(x, n):
     return [(x >> (32 * i)) & MASK for i in range(n)]
 
 
-def gen_mul(n, mod):
-    """Instruction stream computing r = a*b*2^(-32n) mod `mod` (a, b < mod). Registers a0.., b0.. in, r0.. out."""
+def emit_solinas_operands(g, m):
+    """For modulus words equal to 0xffffffff:  m * 0xffffffff = (m - [m != 0]) * 2^32 + (-m mod 2^32), so the pair of
+    a reduction chain takes two plain additions (ALU pipe) instead of one IMAD.WIDE (the busier fmaheavy pipe).
+    The three instructions leave the carry flag alone (a fold carry may be pending)."""
+    g.emit("sub.u32", "negm", 0, m)
+    g.emit("sub.u32", "mt", m, 1)
+    g.emit("min.u32", "mm1", "mt", m)
+
+
+def solinas_words(mod, n, limit):
+    """Indices of the 0xffffffff words of `mod` handled in add form: at most `limit` of them, lowest first."""
+    idx = [j for j, w in enumerate(words(mod, n)) if w == MASK]
+    return set(idx[:limit])
+
+
+def gen_mul(n, mod, repl=frozenset()):
+    """Instruction stream computing r = a*b*2^(-32n) mod `mod` (a, b < mod). Registers a0.., b0.. in, r0.. out.
+    repl: word indices of the modulus (value 0xffffffff) reduced in add form (emit_solinas_operands)."""
     P = words(mod, n)
     m0 = (-pow(mod, -1, 1 << 32)) % (1 << 32)
     g = Prog()
@@ -162,6 +182,8 @@ def gen_mul(n, mod):
         else:
             m = "m"
             g.emit("mul.lo.u32", m, X(i), m0)
+        if repl:
+            emit_solinas_operands(g, m)
         # ---- reduction chain A: even j, file X.  The low word at position i becomes 0 and dies.
         started = False
         for j in range(0, n, 2):
@@ -177,6 +199,9 @@ def gen_mul(n, mod):
             if pj == 1:
                 g.emit("addc.cc.u32" if started else "add.cc.u32", dst_lo, addend(lo), m)
                 g.emit("addc.cc.u32", hi, addend(hi), 0)
+            elif pj == MASK and j in repl:
+                g.emit("addc.cc.u32" if started else "add.cc.u32", dst_lo, addend(lo), "negm")
+                g.emit("addc.cc.u32", hi, addend(hi), "mm1")
             else:
                 g.emit("madc.lo.cc.u32" if started else "mad.lo.cc.u32", dst_lo, m, pj, addend(lo))
                 g.emit("madc.hi.cc.u32", hi, m, pj, addend(hi))
@@ -201,6 +226,9 @@ def gen_mul(n, mod):
             if pj == 1:
                 g.emit("addc.cc.u32" if started else "add.cc.u32", lo, addend(lo), m)
                 g.emit("addc.cc.u32", hi, addend(hi), 0)
+            elif pj == MASK and j in repl:
+                g.emit("addc.cc.u32" if started else "add.cc.u32", lo, addend(lo), "negm")
+                g.emit("addc.cc.u32", hi, addend(hi), "mm1")
             else:
                 g.emit("madc.lo.cc.u32" if started else "mad.lo.cc.u32", lo, m, pj, addend(lo))
                 g.emit("madc.hi.cc.u32", hi, m, pj, addend(hi))
@@ -235,7 +263,7 @@ def gen_mul(n, mod):
     return g
 
 
-def gen_sqr(n, mod):
+def gen_sqr(n, mod, repl=frozenset()):
     """r = a*a*2^(-32n) mod `mod`.  The product phase uses the symmetry of squaring: the n(n-1)/2 cross products
     a_i*a_j (i < j) are accumulated once, doubled by a one-bit shift, and the n squares a_i^2 are added — n(n+1)/2
     wide multiplies instead of n^2.  The double-width product then sits in file E (even-aligned pairs); the n
@@ -332,6 +360,8 @@ def gen_sqr(n, mod):
         else:
             m = "m"
             g.emit("mul.lo.u32", m, X(i), m0)
+        if repl:
+            emit_solinas_operands(g, m)
         # chain B first when there is a fold carry pending (i > 0); chain A afterwards (it starts its own chain)
         def chain(F, js, carry_in, f_is_e, top_pos):
             started = carry_in
@@ -349,6 +379,9 @@ def gen_sqr(n, mod):
                 if pj == 1:
                     g.emit("addc.cc.u32" if started else "add.cc.u32", dst_lo, addend(lo), m)
                     g.emit("addc.cc.u32", hi, addend(hi), 0)
+                elif pj == MASK and j in repl:
+                    g.emit("addc.cc.u32" if started else "add.cc.u32", dst_lo, addend(lo), "negm")
+                    g.emit("addc.cc.u32", hi, addend(hi), "mm1")
                 else:
                     g.emit("madc.lo.cc.u32" if started else "mad.lo.cc.u32", dst_lo, m, pj, addend(lo))
                     g.emit("madc.hi.cc.u32", hi, m, pj, addend(hi))
@@ -468,6 +501,30 @@ def fields():
         yield f"Fq_{name}", n, q
 
 
+# Share of a modulus' 0xffffffff words reduced in add form, per multiplier variant (the inlined multiplier of the
+# fixed-base kernels / the out-of-line one of K2 and K3).  MEASURED SLOWER on B200 and therefore OFF by default:
+# with shares (0.5, 1.0) secp256r1 fixed base fell from 478 to 449 M/s, ECDSA verify from 20.2 to 18.5 M/s, secp384r1
+# from 149 to 144 M/s, secp521r1 from 37.6 to 35.5 M/s; with (1.0, 1.0) further (436 / 18.5 / 136 / 32.1).  One
+# IMAD.WIDE (fmaheavy pipe, issue rate 1/4) is replaced by two IADD3.X on the ALU pipe (issue rate 1/2 each), which
+# is cycle-neutral at best, plus three ALU instructions per row, and the dependent carry chains get longer.
+# Kept as a generator option (and covered by tests/test_ptx_emulation.py): ECC_SOLINAS_INLINE / ECC_SOLINAS_CALL.
+SOLINAS_SHARE = {"inline": float(os.environ.get("ECC_SOLINAS_INLINE", "0")),
+                 "call": float(os.environ.get("ECC_SOLINAS_CALL", "0"))}
+
+
+def variant_repl(mod, n, variant):
+    cnt = sum(1 for w in words(mod, n) if w == MASK)
+    return frozenset(solinas_words(mod, n, int(cnt * SOLINAS_SHARE[variant] + 1e-9)))
+
+
+def variants(n, mod):
+    """[(variant name, mul program, sqr program)]; one entry when both variants are the same program."""
+    ri, rc = variant_repl(mod, n, "inline"), variant_repl(mod, n, "call")
+    if ri == rc:
+        return [("both", gen_mul(n, mod, ri), gen_sqr(n, mod, ri))]
+    return [("inline", gen_mul(n, mod, ri), gen_sqr(n, mod, ri)), ("call", gen_mul(n, mod, rc), gen_sqr(n, mod, rc))]
+
+
 def main():
     out = ["/* GENERATED by tools/gen_fp_ptx.py — do not edit.  Inline-PTX field arithmetic (device only). */",
            "#pragma once", "",
@@ -475,23 +532,29 @@ def main():
            "#define ECC_MUL_LINKAGE __noinline__", "#endif", "", "namespace eccb200 {", "",
            "template <class F> struct FieldPtx;", ""]
     for tag, n, mod in fields():
-        mul, sqr, add, sub = gen_mul(n, mod), gen_sqr(n, mod), gen_add(n, mod), gen_sub(n, mod)
-        wide, total = mul.count()
-        swide, stotal = sqr.count()
-        out.append(f"/* {tag}: mul = {wide} wide multiply-accumulates, {total} PTX instructions; "
-                   f"sqr = {swide} wide, {stotal} PTX instructions */")
+        add, sub = gen_add(n, mod), gen_sub(n, mod)
+        vs = variants(n, mod)
         out.append(f"template <> struct FieldPtx<{tag}> {{")
         out.append(f"\tstatic constexpr int N = {n};")
         out.append(f"\ttypedef Fe<{n}> E;")
         out.append("\t/* Out-of-line, operands and result BY VALUE (they stay in registers; ptxas allocates across the call):")
         out.append("\t * one copy of the ~200-instruction product per kernel instead of one per use keeps the hot loops of")
         out.append("\t * the scalar-multiplication kernels inside the instruction cache (profiles/: no_instruction stalls). */")
-        out.append("\tstatic __device__ ECC_MUL_LINKAGE E mul_fn(E a, E b)\n\t{\n\t\tE r;")
-        out.append(render_asm(mul, n))
-        out.append("\t\treturn r;\n\t}")
-        out.append("\tstatic __device__ ECC_MUL_LINKAGE E sqr_fn(E a)\n\t{\n\t\tE r;")
-        out.append(render_asm(sqr, n, two_inputs=False))
-        out.append("\t\treturn r;\n\t}")
+        for vi, (vname, mul, sqr) in enumerate(vs):
+            if len(vs) > 1:
+                out.append("#if defined(ECC_INLINE_MUL)" if vi == 0 else "#else")
+            wide, total = mul.count()
+            swide, stotal = sqr.count()
+            out.append(f"\t/* {tag} [{vname}]: mul = {wide} wide multiply-accumulates, {total} PTX instructions; "
+                       f"sqr = {swide} wide, {stotal} PTX instructions */")
+            out.append("\tstatic __device__ ECC_MUL_LINKAGE E mul_fn(E a, E b)\n\t{\n\t\tE r;")
+            out.append(render_asm(mul, n))
+            out.append("\t\treturn r;\n\t}")
+            out.append("\tstatic __device__ ECC_MUL_LINKAGE E sqr_fn(E a)\n\t{\n\t\tE r;")
+            out.append(render_asm(sqr, n, two_inputs=False))
+            out.append("\t\treturn r;\n\t}")
+        if len(vs) > 1:
+            out.append("#endif")
         out.append("\tstatic __device__ __forceinline__ void mul(E &r, const E &a, const E &b) { r = mul_fn(a, b); }")
         out.append("\tstatic __device__ __forceinline__ void sqr(E &r, const E &a) { r = sqr_fn(a); }")
         out.append("\tstatic __device__ __forceinline__ void add(E &r, const E &a, const E &b)\n\t{")
