@@ -145,6 +145,18 @@ int eccb200_ecdsa_verify_msgs_batch(eccb200_ctx *ctx, int hash_type, uint32_t n,
 				    int8_t *verdict);
 
 /*
+ * ECFSDSA verification (the Schnorr-type scheme for which the reference ships a verify_batch,
+ * src/sig/ecfsdsa.c:711-1074), per item like ec_verify(…, ECFSDSA, …) (src/sig/ecfsdsa.c:416-610):
+ * sigs [n][2*plen + qlen] = r || s with r = W_x || W_y, digests[i] = H(r_i || m_i) (hlen <= 8N bytes, the whole digest
+ * is reduced mod q), pubkeys as for ECDSA.  verdict 0 / -1.  The same comb + signed-window kernel as ECDSA, without
+ * the inversion mod q.
+ */
+int eccb200_ecfsdsa_verify_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys,
+				 const uint8_t *digests, uint32_t hlen, int8_t *verdict);
+int eccb200_ecfsdsa_verify_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_sigs, const uint8_t *d_pubkeys,
+				     const uint8_t *d_digests, uint32_t hlen, int8_t *d_verdict, void *stream);
+
+/*
  * The reference's structured key / signature records, batched.  `alg` is the reference's
  * ec_alg_type (ECDSA = 1, DECDSA = 14; src/lib_ecc_types.h:22-), `hash_type` its hash_alg_type; the third header byte
  * is the context's curve id.

@@ -30,6 +30,7 @@ ABI_SYMBOLS = [
     "eccb200_ecccdh_derive_batch", "eccb200_ecccdh_derive_batch_dev", "eccb200_fp_mul_chain_bench", "eccb200_hash_batch", "eccb200_ecdsa_verify_msgs_batch",
     "eccb200_structured_pub_key_import_batch", "eccb200_structured_pub_key_export_batch",
     "eccb200_structured_key_pair_batch", "eccb200_ecdsa_verify_structured_batch", "eccb200_ecdsa_sign_structured_batch",
+    "eccb200_ecfsdsa_verify_batch", "eccb200_ecfsdsa_verify_batch_dev",
 ]
 
 _lib = None
@@ -79,6 +80,8 @@ def load_library() -> ctypes.CDLL:
                                                           u8p, u32, i8p]
     lib.eccb200_ecdsa_sign_structured_batch.argtypes = [ctypes.c_void_p, u32, u8p, u32, ctypes.c_int, ctypes.c_int,
                                                         u8p, u8p, u32, u8p, i8p]
+    lib.eccb200_ecfsdsa_verify_batch.argtypes = [ctypes.c_void_p, u32, u8p, u8p, u8p, u32, i8p]
+    lib.eccb200_ecfsdsa_verify_batch_dev.argtypes = [ctypes.c_void_p, u32, u8p, u8p, u8p, u32, i8p, ctypes.c_void_p]
     lib.eccb200_host_alloc.argtypes = [ctypes.c_size_t]
     lib.eccb200_host_alloc.restype = ctypes.c_void_p
     lib.eccb200_host_alloc_input.argtypes = [ctypes.c_size_t]
@@ -260,6 +263,17 @@ class Engine:
         self._check(self.lib.eccb200_ecdsa_verify_msgs_batch(self._h, self.HASH_IDS[hash_name], n, sg.ctypes.data,
                                                              pk.ctypes.data, blob.ctypes.data, off.ctypes.data,
                                                              verdict.ctypes.data), "eccb200_ecdsa_verify_msgs_batch")
+        return verdict
+
+    def ecfsdsa_verify_batch(self, sigs, pubkeys, digests, hlen: int) -> np.ndarray:
+        """digests[i] = H(r_i || m_i); sigs [n][2*plen + qlen]."""
+        sg = _as_u8(sigs)
+        n = sg.size // (2 * self.plen + self.qlen)
+        pk = _as_u8(pubkeys, n * 2 * self.plen)
+        dg = _as_u8(digests, n * hlen)
+        verdict = np.zeros(n, dtype=np.int8)
+        self._check(self.lib.eccb200_ecfsdsa_verify_batch(self._h, n, sg.ctypes.data, pk.ctypes.data, dg.ctypes.data,
+                                                          hlen, verdict.ctypes.data), "eccb200_ecfsdsa_verify_batch")
         return verdict
 
     # ---- the reference's structured key / signature records (include/libecc_b200.h)

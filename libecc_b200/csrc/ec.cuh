@@ -667,6 +667,62 @@ ECC_HD int ecdsa_verify_tail(const Fe<C::N> &r, const Fe<C::N> &u, const Fe<C::N
 	return ecdsa_verify_tail<C>(r, u, v, Y, table, w, y_inf, ThreadInverter<C>());
 }
 
+/* ------------------------------------------------------------------------------------------ ECFSDSA (§8f.4) */
+
+/*
+ * h = OS2I(digest) mod q with the WHOLE digest (sig/ecfsdsa.c:590-592: nn_init_from_buf + nn_mod — no truncation to
+ * bitlen(q), unlike ECDSA), hlen <= 8N bytes.  The low 4N bytes are reduced by a round trip through the Montgomery
+ * domain (x -> xR -> x mod q, valid for any x < R); the bytes above them are a second N-word integer `hi`, and
+ * hi * 2^(32N) mod q = hi * R mod q is exactly to_mont(hi).
+ */
+template <class C> ECC_HD void digest_full_mod_q(Fe<C::N> &e, const uint8_t *h, uint32_t hlen)
+{
+	typedef Field<typename C::Fq> Fq;
+	constexpr int N = C::N;
+	Fe<N> lo, hi, t;
+#pragma unroll
+	for (int i = 0; i < N; i++) lo.w[i] = hi.w[i] = 0;
+	for (uint32_t i = 0; i < hlen; i++) {
+		uint32_t pos = hlen - 1 - i; /* byte significance */
+		uint32_t v = (uint32_t)h[i] << (8 * (pos & 3));
+		int wi = (int)(pos >> 2);
+#pragma unroll
+		for (int j = 0; j < N; j++) {
+			lo.w[j] |= (j == wi) ? v : 0u;
+			hi.w[j] |= (j + N == wi) ? v : 0u;
+		}
+	}
+	Fq::to_mont(t, lo);
+	Fq::from_mont(e, t);
+	if (hlen > 4u * N) {
+		Fq::to_mont(t, hi);
+		Fq::add(e, e, t);
+	}
+}
+
+/* Steps 5-7 of _ecfsdsa_verify_finalize (sig/ecfsdsa.c:597-610): W' = sG + eY with e = -h mod q, reject infinity
+ * (prj_pt_unique fails on it), accept iff W' == r.  R is the signature's point (validated, Montgomery form); the
+ * comparison is done projectively (X == r_x Z^2, Y == r_y Z^3) instead of normalising W'.  0 valid, 2 infinity,
+ * 3 mismatch. */
+template <class C, class Inv>
+ECC_HD int ecfsdsa_verify_tail(const Aff<C> &R, const Fe<C::N> &s, const Fe<C::N> &e_neg, const Aff<C> &Y,
+			       const uint32_t *__restrict__ table, int w, const Inv &invert)
+{
+	typedef Field<typename C::Fp> F;
+	Jac<C> sG, W;
+	comb_mul<C>(sG, s, table, w);
+	window_mul<C>(W, e_neg, Y, &sG, invert);
+	if (EC<C>::is_inf(W)) return 2;
+	Fe<C::N> z2, z3, t;
+	F::sqr(z2, W.Z);
+	F::mul(z3, z2, W.Z);
+	F::mul(t, R.x, z2);
+	bool ok = F::eq(t, W.X);
+	F::mul(t, R.y, z3);
+	ok = ok && F::eq(t, W.Y);
+	return ok ? 0 : 3;
+}
+
 /* r, s in [1, q-1]?  (__ecdsa_verify_init, sig/ecdsa_common.c:653-658) */
 template <class C> ECC_HD bool ecdsa_rs_in_range(const Fe<C::N> &r, const Fe<C::N> &s)
 {

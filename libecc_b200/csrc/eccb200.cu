@@ -394,6 +394,29 @@ extern "C" int eccb200_ecdsa_verify_batch_dev(eccb200_ctx *ctx, uint32_t n, cons
 	return verify_dev(ctx, n, d_sigs, d_pubkeys, d_digests, hlen, d_verdict, (cudaStream_t)stream);
 }
 
+static int ecfsdsa_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_sigs, const uint8_t *d_pubkeys,
+		       const uint8_t *d_digests, uint32_t hlen, int8_t *d_verdict, cudaStream_t st)
+{
+	if (n == 0) return 0;
+	return dispatch(ctx->curve_id, [&](auto c) {
+		typedef decltype(c) C;
+		LaunchVerify<C>::ecfsdsa(n, d_sigs, d_pubkeys, d_digests, hlen, ctx->table, ctx->w, d_verdict, st);
+		ctx->launches += 1;
+		CUDA_OK(cudaGetLastError());
+		return 0;
+	});
+}
+
+extern "C" int eccb200_ecfsdsa_verify_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_sigs,
+						  const uint8_t *d_pubkeys, const uint8_t *d_digests, uint32_t hlen,
+						  int8_t *d_verdict, void *stream)
+{
+	if (!ctx || (n && (!d_sigs || !d_pubkeys || !d_digests || !d_verdict))) return fail("null argument");
+	if (hlen == 0 || hlen > 8u * (uint32_t)ctx->N) return fail("bad digest length (1 .. 8N bytes)");
+	CUDA_OK(cudaSetDevice(ctx->device));
+	return ecfsdsa_dev(ctx, n, d_sigs, d_pubkeys, d_digests, hlen, d_verdict, (cudaStream_t)stream);
+}
+
 /* ------------------------------------------------------------------------------------------ host-pointer API */
 
 static int ensure_stages(eccb200_ctx *ctx, size_t in_bytes, size_t out_bytes)
@@ -626,6 +649,24 @@ extern "C" int eccb200_ecdsa_verify_batch(eccb200_ctx *ctx, uint32_t n, const ui
 		const uint8_t *d = ctx->d_in[s];
 		return verify_dev(ctx, cnt, d, d + (size_t)cnt * sg, d + (size_t)cnt * (sg + pk), hlen,
 				  (int8_t *)ctx->d_out[s], ctx->streams[s]);
+	});
+}
+
+extern "C" int eccb200_ecfsdsa_verify_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys,
+					    const uint8_t *digests, uint32_t hlen, int8_t *verdict)
+{
+	if (!ctx || (n && (!sigs || !pubkeys || !digests || !verdict))) return fail("null argument");
+	if (hlen == 0 || hlen > 8u * (uint32_t)ctx->N) return fail("bad digest length (1 .. 8N bytes)");
+	if (n == 0) return 0;
+	const size_t pk = 2 * (size_t)ctx->plen, sg = pk + (size_t)ctx->qlen;
+	/* column order keeps the 16-byte-multiple items first (256/384-bit curves): keys, signatures, digests */
+	std::vector<HostCol> in = { { (uint8_t *)pubkeys, pk, false }, { (uint8_t *)sigs, sg, false },
+				    { (uint8_t *)digests, hlen, false } };
+	std::vector<HostCol> outc = { { (uint8_t *)verdict, 1, false } };
+	return run_pipeline(ctx, n, in, outc, [&](int s, uint32_t cnt) {
+		const uint8_t *d = ctx->d_in[s];
+		return ecfsdsa_dev(ctx, cnt, d + (size_t)cnt * pk, d, d + (size_t)cnt * (pk + sg), hlen,
+				   (int8_t *)ctx->d_out[s], ctx->streams[s]);
 	});
 }
 

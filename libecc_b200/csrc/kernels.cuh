@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(128) k_prj_load(uint32_t n, const uint8_t *__r
  *   - uG via the comb table (K1), vY via the signed window (K2) instead of two ladders (:788,793).
  * digests: hlen bytes each; e = leftmost min(8*hlen, bitlen(q)) bits (:760-775), reduced mod q (:777).
  */
-template <class C>
+template <class C, int SCHEME = 0>
 __global__ void __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VERIFY : (C::N <= 12 ? ECC_MINB_VERIFY_WIDE : 2))) k_ecdsa_verify(uint32_t n, const uint8_t *__restrict__ sigs,
 						      const uint8_t *__restrict__ pubkeys,
 						      const uint8_t *__restrict__ digests, uint32_t hlen,
@@ -620,6 +620,39 @@ __global__ void __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VERIFY : (C::N <= 1
 	const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
 	const bool active = idx < n;
 	const uint32_t i0 = active ? idx : 0; /* idle threads of the last CTA still join the CTA-wide inversion */
+
+	if (SCHEME == 1) {
+		/* ECFSDSA (sig/ecfsdsa.c:416-610): signature r || s with r = W_x || W_y a curve point and s in
+		 * ]0, q[; digests[i] = H(r || m); W' = sG + (-h mod q) Y must equal r.  Same double-scalar core as ECDSA — comb
+		 * for the generator, signed window for the key — without the mod-q inversion. */
+		__shared__ uint32_t sh_inv1[ECC_CTA_INV_WORDS(N)];
+		const uint8_t *sg = sigs + (size_t)i0 * (2 * C::PLEN + C::QLEN);
+		Aff<C> Rp, Y;
+		Fe<N> s, h;
+		const bool r_ok = load_affine_checked<C>(Rp, sg);                 /* (:453-460) */
+		load_wire<N, C::QLEN>(s, sg + 2 * C::PLEN);
+		const bool s_ok = !Fq::is_zero(s) && !Fq::geq_mod(s);            /* (:465-470) */
+		const bool key_ok = load_affine_checked<C>(Y, pubkeys + (size_t)i0 * (2 * C::PLEN));
+		digest_full_mod_q<C>(h, digests + (size_t)i0 * hlen, hlen);      /* (:590-592) */
+		Fq::neg(h, h);                                                    /* e = -h mod q (:594) */
+		const bool run = r_ok && s_ok && key_ok;
+		if (!run) {
+			Fq::set_zero(s);
+			Fq::set_zero(h);
+#pragma unroll
+			for (int j = 0; j < N; j++) {
+				Y.x.w[j] = C::GX_MONT(j);
+				Y.y.w[j] = C::GY_MONT(j);
+			}
+		}
+		int code = ecfsdsa_verify_tail<C>(Rp, s, h, Y, table, w, [&](Fe<N> &o, const Fe<N> &a) {
+			cta_inverse_128<typename C::Fp>(o, a, sh_inv1);
+		});
+		if (!active) return;
+		if (!run) code = 1;
+		verdict[idx] = code ? -1 : 0;
+		return;
+	}
 
 	Fe<N> r, s, e;
 	load_wire<N, C::QLEN>(r, sigs + (size_t)i0 * (2 * C::QLEN));
@@ -958,6 +991,8 @@ template <class C> struct LaunchVerify {
 	static void verify(uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys, const uint8_t *digests,
 			   uint32_t hlen, const uint32_t *table, int w, int8_t *verdict, cudaStream_t st,
 			   const int8_t *key_state = nullptr);
+	static void ecfsdsa(uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys, const uint8_t *digests,
+			    uint32_t hlen, const uint32_t *table, int w, int8_t *verdict, cudaStream_t st);
 	static void uv(uint32_t n, const uint8_t *sigs, const uint8_t *digests, uint32_t hlen, uint8_t *out,
 		       cudaStream_t st);
 };
@@ -1077,6 +1112,12 @@ void LaunchVerify<C>::verify(uint32_t n, const uint8_t *sigs, const uint8_t *pub
 {
 	k_ecdsa_verify<C><<<grid_for(n), kThreads, 0, st>>>(n, sigs, pubkeys, digests, hlen, table, w, verdict,
 							     key_state);
+}
+template <class C>
+void LaunchVerify<C>::ecfsdsa(uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys, const uint8_t *digests,
+			      uint32_t hlen, const uint32_t *table, int w, int8_t *verdict, cudaStream_t st)
+{
+	k_ecdsa_verify<C, 1><<<grid_for(n), kThreads, 0, st>>>(n, sigs, pubkeys, digests, hlen, table, w, verdict, nullptr);
 }
 template <class C>
 void LaunchVerify<C>::uv(uint32_t n, const uint8_t *sigs, const uint8_t *digests, uint32_t hlen, uint8_t *out,

@@ -679,6 +679,75 @@ static int ecdsa_verify_one(const uint8_t *sig, const uint8_t *pub, const uint8_
 	return nn_cmp_n(rp, r, n) == 0 ? 0 : -1; /* (:809-810) */
 }
 
+/* x mod q for a wide x (nlimbs limbs): plain binary long division, the result of nn_mod (nn/nn_div.c:1005) */
+static void wide_mod_q(u64 *out, const u64 *x, int nlimbs, const curve_t *c)
+{
+	u64 r[MAXL + 1];
+	int n = c->n;
+	memset(r, 0, sizeof(r));
+	for (int bit = 64 * nlimbs - 1; bit >= 0; bit--) {
+		u64 carry = (x[bit / 64] >> (bit % 64)) & 1;
+		for (int i = 0; i <= n; i++) {
+			u64 nc = r[i] >> 63;
+			r[i] = (r[i] << 1) | carry;
+			carry = nc;
+		}
+		if (r[n] || nn_cmp_n(r, c->fq.p, n) >= 0) {
+			u64 bw = nn_sub_n(r, r, c->fq.p, n);
+			r[n] -= bw;
+		}
+	}
+	memcpy(out, r, sizeof(u64) * (size_t)n);
+}
+
+/* _ecfsdsa_verify_init checks (sig/ecfsdsa.c:447-470) + _ecfsdsa_verify_finalize (:536-610) on h = H(r || m):
+ * signature = r || s with r = W_x || W_y (2*plen bytes) and s (qlen bytes). */
+static int ecfsdsa_verify_one(const uint8_t *sig, const uint8_t *pub, const uint8_t *h, uint32_t hlen,
+			      const curve_t *c)
+{
+	u64 s[MAXL], e[MAXL], big[16];
+	pt_t Y, G, R, sG, eY, W, Wa;
+	uint8_t rprime[2 * 8 * MAXL];
+	int n = c->n;
+	/* 1. r must be a point of the curve (coordinates < p, :453-460) */
+	if (pt_import_aff(&R, sig, c)) return -1;
+	/* 2. s in ]0, q[ (:465-470) */
+	nn_from_be(s, n, sig + 2 * c->plen, c->qlen);
+	if (nn_iszero_n(s, n) || nn_cmp_n(s, c->fq.p, n) >= 0) return -1;
+	if (pt_import_aff(&Y, pub, c)) return -1;
+	/* 4. e = -(OS2I(h) mod q) mod q, the WHOLE digest (:590-594) */
+	memset(big, 0, sizeof(big));
+	nn_from_be(big, 16, h, hlen > 128 ? 128 : hlen);
+	wide_mod_q(e, big, 16, c);
+	if (!nn_iszero_n(e, n)) nn_sub_n(e, c->fq.p, e, n);
+	/* 5. W' = sG + eY (:597-600) */
+	memcpy(G.X, c->gx, sizeof(G.X));
+	memcpy(G.Y, c->gy, sizeof(G.Y));
+	memset(G.Z, 0, sizeof(G.Z));
+	G.Z[0] = 1;
+	if (pt_mul(&sG, s, n, &G, c)) return -1;
+	if (pt_mul(&eY, e, n, &Y, c)) return -1;
+	if (pt_add_cf(&W, &sG, &eY, c)) return -1;
+	if (pt_iszero(&W, c)) return -1;       /* prj_pt_unique fails on the point at infinity (curves/prj_pt.c:246) */
+	if (pt_unique(&Wa, &W, c)) return -1;
+	/* 6.-7. r' = FE2OS(W'_x) || FE2OS(W'_y) must equal r (:603-610) */
+	nn_to_be(rprime, c->plen, Wa.X, n);
+	nn_to_be(rprime + c->plen, c->plen, Wa.Y, n);
+	return memcmp(rprime, sig, 2 * c->plen) == 0 ? 0 : -1;
+}
+
+static void *fs_verify_worker(void *arg)
+{
+	job_t *j = (job_t *)arg;
+	const curve_t *c = j->c;
+	for (uint32_t i = j->lo; i < j->hi; i++) {
+		j->status[i] = (int8_t)ecfsdsa_verify_one(j->sigs + (size_t)i * (2 * c->plen + c->qlen),
+							  j->pubkeys + (size_t)i * 2 * c->plen,
+							  j->digests + (size_t)i * j->hlen, j->hlen, c);
+	}
+	return NULL;
+}
+
 static void *verify_worker(void *arg)
 {
 	job_t *j = (job_t *)arg;
@@ -789,6 +858,24 @@ int ora_ecdsa_verify_digest_batch(const char *curve, uint32_t n, const uint8_t *
 	p.hlen = hlen;
 	p.status = verdict;
 	run_jobs(verify_worker, &p, n, nthreads);
+	return 0;
+}
+
+/* ECFSDSA verification on h = H(r || m) (sig/ecfsdsa.c); sigs are [n][2*plen + qlen] */
+int ora_ecfsdsa_verify_digest_batch(const char *curve, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys,
+				  const uint8_t *digests, uint32_t hlen, int8_t *verdict, int nthreads)
+{
+	curve_t c;
+	job_t p;
+	if (curve_load(&c, curve)) return -1;
+	memset(&p, 0, sizeof(p));
+	p.c = &c;
+	p.sigs = sigs;
+	p.pubkeys = pubkeys;
+	p.digests = digests;
+	p.hlen = hlen;
+	p.status = verdict;
+	run_jobs(fs_verify_worker, &p, n, nthreads);
 	return 0;
 }
 

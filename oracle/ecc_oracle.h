@@ -26,6 +26,10 @@ int ora_prj_pt_mul_batch(const char *curve, uint32_t n, const uint8_t *scalars, 
 int ora_ecdsa_verify_digest_batch(const char *curve, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys,
 				  const uint8_t *digests, uint32_t hlen, int8_t *verdict, int nthreads);
 
+/* ECFSDSA verification (sig/ecfsdsa.c) on digests[i] = H(r_i || m_i); sigs are [n][2*plen + qlen] (r = W_x || W_y, s). */
+int ora_ecfsdsa_verify_digest_batch(const char *curve, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys,
+				    const uint8_t *digests, uint32_t hlen, int8_t *verdict, int nthreads);
+
 /* ECDSA signing on pre-hashed messages with caller-supplied nonces (deterministic; RFC-vector friendly).
  * status 0 ok, -1 error (k, d out of range, r == 0 or s == 0). */
 int ora_ecdsa_sign_digest_batch(const char *curve, uint32_t n, const uint8_t *privkeys, const uint8_t *nonces,

@@ -165,6 +165,8 @@ typedef struct {
 	uint8_t *sigs_out;
 	uint8_t *pubkeys_out;
 	int8_t *verdict;
+	ec_alg_type alg;   /* ECDSA or ECFSDSA */
+	uint32_t siglen;   /* 2*qlen (ECDSA) or 2*plen + qlen (ECFSDSA, sig/ecfsdsa.h) */
 } sig_job;
 
 static void *verify_worker(void *arg)
@@ -175,10 +177,10 @@ static void *verify_worker(void *arg)
 		ec_pub_key pk;
 		j->verdict[i] = -1;
 		if (ec_pub_key_import_from_aff_buf(&pk, &c->params, j->pubkeys + (size_t)i * 2 * c->plen,
-						   (u8)(2 * c->plen), ECDSA))
+						   (u8)(2 * c->plen), j->alg))
 			continue;
-		if (ec_verify(j->sigs + (size_t)i * 2 * c->qlen, (u8)(2 * c->qlen), &pk, j->msgs + j->off[i],
-			      (u32)(j->off[i + 1] - j->off[i]), ECDSA, j->ht, NULL, 0))
+		if (ec_verify(j->sigs + (size_t)i * j->siglen, (u8)j->siglen, &pk, j->msgs + j->off[i],
+			      (u32)(j->off[i + 1] - j->off[i]), j->alg, j->ht, NULL, 0))
 			continue;
 		j->verdict[i] = 0;
 	}
@@ -193,13 +195,13 @@ static void *sign_worker(void *arg)
 		ec_key_pair kp;
 		j->verdict[i] = -1;
 		if (ec_key_pair_import_from_priv_key_buf(&kp, &c->params, j->privkeys + (size_t)i * c->qlen,
-							 (u8)c->qlen, ECDSA))
+							 (u8)c->qlen, j->alg))
 			continue;
 		if (ec_pub_key_export_to_aff_buf(&kp.pub_key, j->pubkeys_out + (size_t)i * 2 * c->plen,
 						 (u8)(2 * c->plen)))
 			continue;
-		if (ec_sign(j->sigs_out + (size_t)i * 2 * c->qlen, (u8)(2 * c->qlen), &kp, j->msgs + j->off[i],
-			    (u32)(j->off[i + 1] - j->off[i]), ECDSA, j->ht, NULL, 0))
+		if (ec_sign(j->sigs_out + (size_t)i * j->siglen, (u8)j->siglen, &kp, j->msgs + j->off[i],
+			    (u32)(j->off[i + 1] - j->off[i]), j->alg, j->ht, NULL, 0))
 			continue;
 		j->verdict[i] = 0;
 	}
@@ -242,6 +244,8 @@ int ref_ecdsa_verify_batch(const char *curve, const char *hash, uint32_t n, cons
 	p.msgs = msgs;
 	p.off = off;
 	p.verdict = verdict;
+	p.alg = ECDSA;
+	p.siglen = 2 * c.qlen;
 	return run_sig_jobs(verify_worker, &p, n, nthreads);
 }
 
@@ -264,7 +268,94 @@ int ref_ecdsa_sign_batch(const char *curve, const char *hash, uint32_t n, const 
 	p.sigs_out = sigs_out;
 	p.pubkeys_out = pubkeys_out;
 	p.verdict = status;
+	p.alg = ECDSA;
+	p.siglen = 2 * c.qlen;
 	return run_sig_jobs(sign_worker, &p, n, nthreads);
+}
+
+/* The same two for ECFSDSA (sig/ecfsdsa.c): signatures are r || s with r = W_x || W_y (2*plen bytes) and s (qlen). */
+int ref_ecfsdsa_verify_batch(const char *curve, const char *hash, uint32_t n, const uint8_t *sigs,
+			     const uint8_t *pubkeys, const uint8_t *msgs, const uint64_t *off, int8_t *verdict,
+			     int nthreads)
+{
+	ref_curve c;
+	sig_job p;
+	u8 dlen;
+	memset(&p, 0, sizeof(p));
+	if (ref_load_curve(&c, curve)) return -1;
+	if (ref_hash_type(hash, &p.ht, &dlen)) return -1;
+	p.c = &c;
+	p.sigs = sigs;
+	p.pubkeys = pubkeys;
+	p.msgs = msgs;
+	p.off = off;
+	p.verdict = verdict;
+	p.alg = ECFSDSA;
+	p.siglen = 2 * c.plen + c.qlen;
+	return run_sig_jobs(verify_worker, &p, n, nthreads);
+}
+
+int ref_ecfsdsa_sign_batch(const char *curve, const char *hash, uint32_t n, const uint8_t *privkeys,
+			   const uint8_t *msgs, const uint64_t *off, uint8_t *sigs_out, uint8_t *pubkeys_out,
+			   int8_t *status, int nthreads)
+{
+	ref_curve c;
+	sig_job p;
+	u8 dlen;
+	memset(&p, 0, sizeof(p));
+	if (ref_load_curve(&c, curve)) return -1;
+	if (ref_hash_type(hash, &p.ht, &dlen)) return -1;
+	p.c = &c;
+	p.privkeys = privkeys;
+	p.msgs = msgs;
+	p.off = off;
+	p.sigs_out = sigs_out;
+	p.pubkeys_out = pubkeys_out;
+	p.verdict = status;
+	p.alg = ECFSDSA;
+	p.siglen = 2 * c.plen + c.qlen;
+	return run_sig_jobs(sign_worker, &p, n, nthreads);
+}
+
+/* The reference's own batch entry point, ec_verify_batch(…, ECFSDSA, …) (sig/sig_algs.c:675 -> sig/ecfsdsa.c:1057):
+ * one 0 / -1 answer for the whole batch.  use_scratch = 0: no scratch pad, the reference verifies the signatures one
+ * after the other (sig/ecfsdsa.c:711); use_scratch = 1: its Bos-Coster multi-scalar multiplication (:842). */
+int ref_ecfsdsa_verify_batch_all(const char *curve, const char *hash, uint32_t n, const uint8_t *sigs,
+				 const uint8_t *pubkeys, const uint8_t *msgs, const uint64_t *off, int use_scratch)
+{
+	ref_curve c;
+	hash_alg_type ht;
+	u8 dlen;
+	int ret = -1;
+	if (ref_load_curve(&c, curve) || ref_hash_type(hash, &ht, &dlen) || n == 0) return -2;
+	const uint32_t siglen = 2 * c.plen + c.qlen;
+	ec_pub_key *pks = (ec_pub_key *)calloc(n, sizeof(ec_pub_key));
+	const ec_pub_key **pkp = (const ec_pub_key **)calloc(n, sizeof(void *));
+	const u8 **sp = (const u8 **)calloc(n, sizeof(void *)), **mp = (const u8 **)calloc(n, sizeof(void *));
+	u8 *sl = (u8 *)calloc(n, 1);
+	u32 *ml = (u32 *)calloc(n, sizeof(u32));
+	u32 scratch_len = 0;
+	verify_batch_scratch_pad *scratch = NULL;
+	for (uint32_t i = 0; i < n; i++) {
+		if (ec_pub_key_import_from_aff_buf(&pks[i], &c.params, pubkeys + (size_t)i * 2 * c.plen, (u8)(2 * c.plen),
+						   ECFSDSA))
+			goto out;
+		pkp[i] = &pks[i];
+		sp[i] = sigs + (size_t)i * siglen;
+		sl[i] = (u8)siglen;
+		mp[i] = msgs + off[i];
+		ml[i] = (u32)(off[i + 1] - off[i]);
+	}
+	/* with a scratch pad the reference runs its Bos-Coster batch algorithm; it wants (2n + 1) entries
+	 * (sig/ecfsdsa.c:898) */
+	if (use_scratch) {
+		scratch_len = (u32)((2 * (size_t)n + 1) * sizeof(verify_batch_scratch_pad));
+		scratch = (verify_batch_scratch_pad *)calloc(1, scratch_len);
+	}
+	ret = ec_verify_batch(sp, sl, pkp, mp, ml, n, ECFSDSA, ht, NULL, NULL, scratch, &scratch_len) ? -1 : 0;
+out:
+	free(pks); free(pkp); free(sp); free(mp); free(sl); free(ml); free(scratch);
+	return ret;
 }
 
 /* ---------------------------------------------------------------- structured key / signature records (sig/ec_key.c) */

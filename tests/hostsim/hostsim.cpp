@@ -217,6 +217,32 @@ int hostsim_ecdsa_verify_batch(int curve_id, int w, uint32_t n, const uint8_t *s
 	});
 }
 
+/* ECFSDSA verification with the kernel's building blocks (digest_full_mod_q, ecfsdsa_verify_tail) */
+int hostsim_ecfsdsa_verify_batch(int curve_id, int w, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys,
+				 const uint8_t *digests, uint32_t hlen, int8_t *verdict)
+{
+	return dispatch(curve_id, [&](auto c) {
+		typedef decltype(c) C;
+		typedef Field<typename C::Fq> Fq;
+		constexpr int N = C::N;
+		const std::vector<uint32_t> &tab = table_for<C>(w);
+		for (uint32_t i = 0; i < n; i++) {
+			const uint8_t *sg = sigs + (size_t)i * (2 * C::PLEN + C::QLEN);
+			Aff<C> R, Y;
+			Fe<N> s, h;
+			bool ok = load_point<C>(R, sg);
+			load_be<N>(s, sg + 2 * C::PLEN, C::QLEN);
+			ok = ok && !Fq::is_zero(s) && !Fq::geq_mod(s);
+			ok = ok && load_point<C>(Y, pubkeys + (size_t)i * 2 * C::PLEN);
+			digest_full_mod_q<C>(h, digests + (size_t)i * hlen, hlen);
+			Fq::neg(h, h);
+			ok = ok && (ecfsdsa_verify_tail<C>(R, s, h, Y, tab.data(), w, ThreadInverter<C>()) == 0);
+			verdict[i] = ok ? 0 : -1;
+		}
+		return 0;
+	});
+}
+
 /* group-law unit test: out = P1 + P2 on affine wire points through add_full / add_mixed (which = 0 / 1),
  * or 2*P1 through dbl (which = 2); infinity operands are encoded as all-zero wire points */
 int hostsim_point_op(int curve_id, int which, const uint8_t *p1, const uint8_t *p2, uint8_t *out, int8_t *status)
