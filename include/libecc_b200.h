@@ -147,8 +147,8 @@ int eccb200_ecdsa_verify_msgs_batch(eccb200_ctx *ctx, int hash_type, uint32_t n,
 /*
  * ECFSDSA verification (the Schnorr-type scheme for which the reference ships a verify_batch,
  * src/sig/ecfsdsa.c:711-1074), per item like ec_verify(…, ECFSDSA, …) (src/sig/ecfsdsa.c:416-610):
- * sigs [n][2*plen + qlen] = r || s with r = W_x || W_y, digests[i] = H(r_i || m_i) (hlen <= 8N bytes, the whole digest
- * is reduced mod q), pubkeys as for ECDSA.  verdict 0 / -1.  The same comb + signed-window kernel as ECDSA, without
+ * sigs [n][2*plen + qlen] = r || s with r = W_x || W_y, digests[i] = H(r_i || m_i) (the whole digest is
+ * reduced mod q, whatever its length), pubkeys as for ECDSA.  verdict 0 / -1.  The same comb + signed-window kernel as ECDSA, without
  * the inversion mod q.
  */
 int eccb200_ecfsdsa_verify_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys,

@@ -671,32 +671,35 @@ ECC_HD int ecdsa_verify_tail(const Fe<C::N> &r, const Fe<C::N> &u, const Fe<C::N
 
 /*
  * h = OS2I(digest) mod q with the WHOLE digest (sig/ecfsdsa.c:590-592: nn_init_from_buf + nn_mod — no truncation to
- * bitlen(q), unlike ECDSA), hlen <= 8N bytes.  The low 4N bytes are reduced by a round trip through the Montgomery
- * domain (x -> xR -> x mod q, valid for any x < R); the bytes above them are a second N-word integer `hi`, and
- * hi * 2^(32N) mod q = hi * R mod q is exactly to_mont(hi).
+ * bitlen(q), unlike ECDSA), any hlen.  Horner over chunks of 4N bytes, most significant first:
+ * h <- h * 2^(32N) + chunk (mod q).  A chunk (any integer < R) is reduced by a round trip through the Montgomery
+ * domain (x -> xR -> x mod q), and h * 2^(32N) mod q = h * R mod q is exactly to_mont(h).
  */
 template <class C> ECC_HD void digest_full_mod_q(Fe<C::N> &e, const uint8_t *h, uint32_t hlen)
 {
 	typedef Field<typename C::Fq> Fq;
 	constexpr int N = C::N;
-	Fe<N> lo, hi, t;
+	const uint32_t nchunks = (hlen + 4u * N - 1u) / (4u * N);
 #pragma unroll
-	for (int i = 0; i < N; i++) lo.w[i] = hi.w[i] = 0;
-	for (uint32_t i = 0; i < hlen; i++) {
-		uint32_t pos = hlen - 1 - i; /* byte significance */
-		uint32_t v = (uint32_t)h[i] << (8 * (pos & 3));
-		int wi = (int)(pos >> 2);
+	for (int i = 0; i < N; i++) e.w[i] = 0;
+	for (uint32_t c = nchunks; c-- > 0;) {
+		Fe<N> ch, t;
 #pragma unroll
-		for (int j = 0; j < N; j++) {
-			lo.w[j] |= (j == wi) ? v : 0u;
-			hi.w[j] |= (j + N == wi) ? v : 0u;
+		for (int i = 0; i < N; i++) ch.w[i] = 0;
+		const uint32_t lo = c * 4u * N, hi = (lo + 4u * N < hlen) ? lo + 4u * N : hlen; /* byte significances */
+		for (uint32_t pos = lo; pos < hi; pos++) {
+			uint32_t v = (uint32_t)h[hlen - 1 - pos] << (8 * (pos & 3));
+			int wi = (int)((pos - lo) >> 2);
+#pragma unroll
+			for (int j = 0; j < N; j++) ch.w[j] |= (j == wi) ? v : 0u;
 		}
-	}
-	Fq::to_mont(t, lo);
-	Fq::from_mont(e, t);
-	if (hlen > 4u * N) {
-		Fq::to_mont(t, hi);
-		Fq::add(e, e, t);
+		if (c + 1 < nchunks) {
+			Fq::to_mont(t, e);
+			e = t;
+		}
+		Fq::to_mont(t, ch);
+		Fq::from_mont(ch, t);
+		Fq::add(e, e, ch);
 	}
 }
 

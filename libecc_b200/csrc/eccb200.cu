@@ -412,7 +412,7 @@ extern "C" int eccb200_ecfsdsa_verify_batch_dev(eccb200_ctx *ctx, uint32_t n, co
 						  int8_t *d_verdict, void *stream)
 {
 	if (!ctx || (n && (!d_sigs || !d_pubkeys || !d_digests || !d_verdict))) return fail("null argument");
-	if (hlen == 0 || hlen > 8u * (uint32_t)ctx->N) return fail("bad digest length (1 .. 8N bytes)");
+	if (hlen == 0 || hlen > 128) return fail("bad digest length");
 	CUDA_OK(cudaSetDevice(ctx->device));
 	return ecfsdsa_dev(ctx, n, d_sigs, d_pubkeys, d_digests, hlen, d_verdict, (cudaStream_t)stream);
 }
@@ -656,7 +656,7 @@ extern "C" int eccb200_ecfsdsa_verify_batch(eccb200_ctx *ctx, uint32_t n, const 
 					    const uint8_t *digests, uint32_t hlen, int8_t *verdict)
 {
 	if (!ctx || (n && (!sigs || !pubkeys || !digests || !verdict))) return fail("null argument");
-	if (hlen == 0 || hlen > 8u * (uint32_t)ctx->N) return fail("bad digest length (1 .. 8N bytes)");
+	if (hlen == 0 || hlen > 128) return fail("bad digest length");
 	if (n == 0) return 0;
 	const size_t pk = 2 * (size_t)ctx->plen, sg = pk + (size_t)ctx->qlen;
 	/* column order keeps the 16-byte-multiple items first (256/384-bit curves): keys, signatures, digests */

@@ -91,7 +91,8 @@ def test_oracle_against_reference_kats():
 
 
 @pytest.mark.parametrize("curve,hash_name", [("FRP256V1", "SHA256"), ("SECP256R1", "SHA512"), ("SECP384R1", "SHA384"),
-                                             ("SECP521R1", "SHA512"), ("SECP224R1", "SHA256"), ("SECP256K1", "SHA256")])
+                                             ("SECP521R1", "SHA512"), ("SECP224R1", "SHA256"), ("SECP256K1", "SHA256"),
+                                             ("SECP192R1", "SHA512")])
 def test_oracle_and_host_algorithm_against_reference(curve, hash_name):
     """Digests longer than the order (SHA-512 on P-256, SHA-256 on P-224) exercise the full-digest reduction."""
     if ref_lib() is None:
