@@ -529,7 +529,10 @@ def main():
     out = ["/* GENERATED by tools/gen_fp_ptx.py — do not edit.  Inline-PTX field arithmetic (device only). */",
            "#pragma once", "",
            "#if defined(ECC_INLINE_MUL)", "#define ECC_MUL_LINKAGE __forceinline__", "#else",
-           "#define ECC_MUL_LINKAGE __noinline__", "#endif", "", "namespace eccb200 {", "",
+           "#define ECC_MUL_LINKAGE __noinline__", "#endif",
+           "/* the squaring can be kept out of line on its own (instruction-cache experiments on K1, DESIGN.md §4) */",
+           "#if defined(ECC_INLINE_MUL) && !defined(ECC_NOINLINE_SQR)", "#define ECC_SQR_LINKAGE __forceinline__", "#else",
+           "#define ECC_SQR_LINKAGE __noinline__", "#endif", "", "namespace eccb200 {", "",
            "template <class F> struct FieldPtx;", ""]
     for tag, n, mod in fields():
         add, sub = gen_add(n, mod), gen_sub(n, mod)
@@ -550,7 +553,7 @@ def main():
             out.append("\tstatic __device__ ECC_MUL_LINKAGE E mul_fn(E a, E b)\n\t{\n\t\tE r;")
             out.append(render_asm(mul, n))
             out.append("\t\treturn r;\n\t}")
-            out.append("\tstatic __device__ ECC_MUL_LINKAGE E sqr_fn(E a)\n\t{\n\t\tE r;")
+            out.append("\tstatic __device__ ECC_SQR_LINKAGE E sqr_fn(E a)\n\t{\n\t\tE r;")
             out.append(render_asm(sqr, n, two_inputs=False))
             out.append("\t\treturn r;\n\t}")
         if len(vs) > 1:
