@@ -82,6 +82,8 @@ def test_group_law_including_exceptional_cases(curve):
 def test_scalar_mult_matches_oracle(curve, w):
     lib = hostsim_lib()
     cid, plen, qlen = ALL_CURVES[curve]
+    if w == 6 and plen >= 64:
+        pytest.skip("second comb width only for the smaller fields (the CPU table build dominates the suite)")
     sc = np.concatenate([random_scalars(curve, 16, tag=21, below_q=False), edge_scalars(curve)])
     n = sc.shape[0]
     want, wst = oracle_smul(curve, sc)
