@@ -273,7 +273,7 @@ def ncu_dram_traffic(workload: str, batch_log2: int, comb_window: int):
     `ncu --set full` capture of this exact configuration (profiles/); None when no capture matches."""
     if not (workload == "secp256r1_fixed_base" and batch_log2 == 20 and comb_window == 22):
         return None
-    path = os.path.join(ROOT, "profiles", "r01_ncu_smul_fixed_w22.csv")
+    path = os.path.join(ROOT, "profiles", "r01_ncu_smul_fixed_final2.csv")
     try:
         tot = 0.0
         for line in open(path):
@@ -282,7 +282,7 @@ def ncu_dram_traffic(workload: str, batch_log2: int, comb_window: int):
                 scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[parts[1]]
                 tot += float(parts[2]) * scale
         return {"bytes_per_launch": tot, "algorithmic_bytes_per_launch": (1 << batch_log2) * (32 + 96 + 1 + 12 * 64),
-                "source": "profiles/r01_ncu_smul_fixed_w22.csv; algorithmic = scalar 32 B + Jacobian result 96 B + "
+                "source": "profiles/r01_ncu_smul_fixed_final2.csv; algorithmic = scalar 32 B + Jacobian result 96 B + "
                           "status 1 B + 12 random 64 B table entries per item (3.2 GiB table, mostly L2 misses, "
                           "fetched in 128 B lines); 13 % of the measured HBM bandwidth - not the bound"}
     except OSError:
