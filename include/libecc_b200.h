@@ -130,8 +130,8 @@ int eccb200_ecccdh_derive_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t 
 				    const uint8_t *d_peer_pubkeys, uint8_t *d_shared, int8_t *d_status, void *stream);
 
 /*
- * Hashing of short messages on the device (SHA-256 / SHA-384 / SHA-512; hash_type = the reference's hash_alg_type
- * value: 2, 3, 4 — src/lib_ecc_types.h:82-).  Replaces hfunc_scattered of the matching hash_mapping
+ * Hashing of short messages on the device (SHA-256 / SHA-384 / SHA-512 and SHA3-224 / 256 / 384 / 512; hash_type =
+ * the reference's hash_alg_type value: 2, 3, 4 and 5 .. 8 — src/lib_ecc_types.h:82-).  Replaces hfunc_scattered of the matching hash_mapping
  * (src/hash/hash_algs.h:232-241; sha256_scattered src/hash/sha256.c:201) for a batch: message i is
  * msgs[offsets[i] .. offsets[i+1]), offsets has n+1 entries, digests is [n][digest_size].
  */

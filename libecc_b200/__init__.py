@@ -235,10 +235,11 @@ class Engine:
                     "eccb200_ecccdh_derive_batch")
         return shared, status
 
-    HASH_IDS = {"SHA256": 2, "SHA384": 3, "SHA512": 4}   # libecc hash_alg_type values hashed on the device
+    HASH_IDS = {"SHA256": 2, "SHA384": 3, "SHA512": 4, "SHA3_224": 5, "SHA3_256": 6, "SHA3_384": 7,
+                "SHA3_512": 8}                            # libecc hash_alg_type values hashed on the device
     REF_HASH_IDS = {"SHA224": 1, "SHA256": 2, "SHA384": 3, "SHA512": 4, "SHA3_224": 5, "SHA3_256": 6, "SHA3_384": 7,
                     "SHA3_512": 8}                        # header byte of structured signatures (lib_ecc_types.h:82-)
-    HASH_LEN = {"SHA256": 32, "SHA384": 48, "SHA512": 64}
+    HASH_LEN = {"SHA256": 32, "SHA384": 48, "SHA512": 64, "SHA3_224": 28, "SHA3_256": 32, "SHA3_384": 48, "SHA3_512": 64}
 
     @staticmethod
     def _pack_msgs(msgs):

@@ -775,7 +775,7 @@ static int hash_dev(eccb200_ctx *ctx, int hash_type, uint32_t n, const uint8_t *
 		    uint8_t *d_digests, cudaStream_t st)
 {
 	if (n == 0) return 0;
-	if (!sha2_digest_size(hash_type)) return fail("unsupported hash (SHA256 = 2, SHA384 = 3, SHA512 = 4)");
+	if (!sha2_digest_size(hash_type)) return fail("unsupported hash (SHA256 = 2, SHA384 = 3, SHA512 = 4, SHA3_224..512 = 5..8)");
 	k_sha2_batch<<<grid_for(n), kThreads, 0, st>>>(n, hash_type, d_msgs, d_off, d_digests);
 	ctx->launches += 1;
 	CUDA_OK(cudaGetLastError());
@@ -787,7 +787,7 @@ extern "C" int eccb200_hash_batch(eccb200_ctx *ctx, int hash_type, uint32_t n, c
 {
 	if (!ctx || (n && (!offsets || !digests))) return fail("null argument");
 	const int ds = sha2_digest_size(hash_type);
-	if (!ds) return fail("unsupported hash (SHA256 = 2, SHA384 = 3, SHA512 = 4)");
+	if (!ds) return fail("unsupported hash (SHA256 = 2, SHA384 = 3, SHA512 = 4, SHA3_224..512 = 5..8)");
 	if (n == 0) return 0;
 	CUDA_OK(cudaSetDevice(ctx->device));
 	const uint64_t total = offsets[n];
@@ -813,7 +813,7 @@ extern "C" int eccb200_ecdsa_verify_msgs_batch(eccb200_ctx *ctx, int hash_type, 
 {
 	if (!ctx || (n && (!sigs || !pubkeys || !offsets || !verdict))) return fail("null argument");
 	const int ds = sha2_digest_size(hash_type);
-	if (!ds) return fail("unsupported hash (SHA256 = 2, SHA384 = 3, SHA512 = 4)");
+	if (!ds) return fail("unsupported hash (SHA256 = 2, SHA384 = 3, SHA512 = 4, SHA3_224..512 = 5..8)");
 	if (n == 0) return 0;
 	CUDA_OK(cudaSetDevice(ctx->device));
 	const uint64_t total = offsets[n];

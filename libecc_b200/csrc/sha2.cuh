@@ -8,6 +8,7 @@
  */
 #pragma once
 #include <stdint.h>
+#include "sha3.cuh"
 
 namespace eccb200 {
 
@@ -120,10 +121,12 @@ __device__ inline void sha512_family_device(const uint8_t *__restrict__ m, uint6
 	for (int i = 0; i < out_bytes; i++) digest[i] = (uint8_t)(h[i >> 3] >> (8 * (7 - (i & 7))));
 }
 
-/* hash_alg_type values of the reference (lib_ecc_types.h:82-): SHA256 = 2, SHA384 = 3, SHA512 = 4 */
+/* hash_alg_type values of the reference (lib_ecc_types.h:82-): SHA256 = 2, SHA384 = 3, SHA512 = 4, SHA3_224 = 5,
+ * SHA3_256 = 6, SHA3_384 = 7, SHA3_512 = 8 (sha3.cuh) */
 __host__ __device__ inline int sha2_digest_size(int hash_type)
 {
-	return hash_type == 2 ? 32 : hash_type == 3 ? 48 : hash_type == 4 ? 64 : 0;
+	return hash_type == 2 ? 32 : hash_type == 3 ? 48 : hash_type == 4 ? 64 : hash_type == 5 ? 28 : hash_type == 6 ? 32 :
+	       hash_type == 7 ? 48 : hash_type == 8 ? 64 : 0;
 }
 
 /* messages are concatenated in `msgs`; message i is msgs[off[i] .. off[i+1]); digests are [n][digest_size] */
@@ -138,7 +141,8 @@ __global__ void __launch_bounds__(128) k_sha2_batch(uint32_t n, int hash_type, c
 	uint8_t *out = digests + (size_t)idx * ds;
 	if (hash_type == 2) sha256_device(m, len, out);
 	else if (hash_type == 3) sha512_family_device(m, len, out, kSha384H, 48);
-	else sha512_family_device(m, len, out, kSha512H, 64);
+	else if (hash_type == 4) sha512_family_device(m, len, out, kSha512H, 64);
+	else sha3_device(m, len, out, ds);
 }
 
 } // namespace eccb200

@@ -11,6 +11,7 @@
  */
 #define ECC_COUNT_MULS
 #include "../../libecc_b200/csrc/ec.cuh"
+#include "../../libecc_b200/csrc/sha3.cuh"
 #include <cstring>
 #include <vector>
 
@@ -288,5 +289,8 @@ int hostsim_point_op(int curve_id, int which, const uint8_t *p1, const uint8_t *
 }
 
 unsigned long long hostsim_last_mul_count(void) { return g_fe_mul_count; }
+
+/* SHA-3 as compiled for the device (sha3.cuh is plain C++) */
+void hostsim_sha3(int digest_bytes, const uint8_t *m, uint64_t len, uint8_t *out) { sha3_device(m, len, out, digest_bytes); }
 
 } /* extern "C" */

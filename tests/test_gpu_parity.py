@@ -391,7 +391,8 @@ def test_ecdsa_verify_msgs_batch():
     batch signed by the oracle over hashlib digests with a few corrupted messages."""
     import hashlib
     from common import oracle_sign
-    fn = {"SHA256": hashlib.sha256, "SHA384": hashlib.sha384, "SHA512": hashlib.sha512}
+    fn = {"SHA256": hashlib.sha256, "SHA384": hashlib.sha384, "SHA512": hashlib.sha512, "SHA3_224": hashlib.sha3_224,
+          "SHA3_256": hashlib.sha3_256, "SHA3_384": hashlib.sha3_384, "SHA3_512": hashlib.sha3_512}
     for v in golden("ecdsa_kat.json"):
         if v["hash"] not in fn:
             continue
