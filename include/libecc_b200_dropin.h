@@ -119,7 +119,15 @@ int eccb200_dropin_ecdsa_verify_batch(const uint8_t **s, const uint8_t *s_len, c
 				      int hash_type, const uint8_t **adata, const uint16_t *adata_len,
 				      void *scratch_pad_area, uint32_t *scratch_pad_area_len);
 
-/* Per-signature verdicts of the last eccb200_dropin_ecdsa_verify_batch call on this thread (0 / -1), for callers
+/* The same for ECFSDSA (sig_type = ECFSDSA = 5): a replacement for the reference's own ecfsdsa_verify_batch
+ * (src/sig/ecfsdsa.c:1057) in the ECFSDSA entry of ec_sig_maps[]; signatures are W_x || W_y || s and the digest is
+ * H(W_x || W_y || m), computed with the reference's src/hash. */
+int eccb200_dropin_ecfsdsa_verify_batch(const uint8_t **s, const uint8_t *s_len, const eccb200_ec_pub_key **pub_keys,
+					const uint8_t **m, const uint32_t *m_len, uint32_t num, int sig_type,
+					int hash_type, const uint8_t **adata, const uint16_t *adata_len,
+					void *scratch_pad_area, uint32_t *scratch_pad_area_len);
+
+/* Per-signature verdicts of the last eccb200_dropin_*_verify_batch call on this thread (0 / -1), for callers
  * that want to know WHICH signature failed; returns the number of verdicts copied. */
 uint32_t eccb200_dropin_last_verdicts(int8_t *verdicts, uint32_t cap);
 

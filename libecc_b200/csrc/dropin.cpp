@@ -354,19 +354,16 @@ extern "C" uint32_t eccb200_dropin_last_verdicts(int8_t *verdicts, uint32_t cap)
 	return k;
 }
 
-extern "C" int eccb200_dropin_ecdsa_verify_batch(const uint8_t **s, const uint8_t *s_len,
-						 const eccb200_ec_pub_key **pub_keys, const uint8_t **m,
-						 const uint32_t *m_len, uint32_t num, int sig_type, int hash_type,
-						 const uint8_t **adata, const uint16_t *adata_len,
-						 void *scratch_pad_area, uint32_t *scratch_pad_area_len)
+/* fs = false: ECDSA / DECDSA (signature r || s, digest H(m));  fs = true: ECFSDSA (signature W_x || W_y || s, digest
+ * H(W_x || W_y || m), sig/ecfsdsa.c:482,529) */
+static int verify_batch_common(bool fs, const uint8_t **s, const uint8_t *s_len, const eccb200_ec_pub_key **pub_keys,
+			       const uint8_t **m, const uint32_t *m_len, uint32_t num, int sig_type, int hash_type,
+			       const uint8_t **adata)
 {
-	(void)scratch_pad_area;
-	(void)scratch_pad_area_len;
-	(void)adata_len;
 	t_verdicts.assign(num, -1);
 	if (num == 0) return -1; /* the reference's implementations reject an empty batch (sig/ecfsdsa.c:740) */
 	if (!s || !s_len || !pub_keys || !m || !m_len) return -1;
-	if (sig_type != 1 /* ECDSA */ && sig_type != 14 /* DECDSA */) return -1;
+	if (fs ? (sig_type != 5 /* ECFSDSA */) : (sig_type != 1 /* ECDSA */ && sig_type != 14 /* DECDSA */)) return -1;
 	if (adata) /* ECDSA takes no ancillary data: every entry must be NULL (sig/ecdsa.c:76-83) */
 		for (uint32_t i = 0; i < num; i++)
 			if (adata[i]) return -1;
@@ -396,18 +393,19 @@ extern "C" int eccb200_dropin_ecdsa_verify_batch(const uint8_t **s, const uint8_
 	if (!eng) return -1;
 	const int pl = ci->plen;
 	const size_t plen = (size_t)ci->plen, qlen = (size_t)ci->qlen;
-	std::vector<uint8_t> sigs(num * 2 * qlen, 0), pubs(num * 2 * plen, 0), dig(num * (size_t)hlen, 0);
+	const size_t siglen = fs ? 2 * plen + qlen : 2 * qlen;
+	std::vector<uint8_t> sigs(num * siglen, 0), pubs(num * 2 * plen, 0), dig(num * (size_t)hlen, 0);
 	/* public keys whose y is not already (x, y, 1) go through the batched prj_pt_unique */
 	std::vector<uint32_t> prj_idx;
 	for (uint32_t i = 0; i < num; i++) {
 		if (!ok[i]) continue;
-		if (s_len[i] != 2 * qlen) { /* siglen check, sig/ecdsa_common.c:645 */
+		if (s_len[i] != siglen) { /* siglen check, sig/ecdsa_common.c:645, sig/ecfsdsa.c:447 */
 			ok[i] = 0;
 			continue;
 		}
-		memcpy(&sigs[i * 2 * qlen], s[i], 2 * qlen);
-		const unsigned char *inputs[2] = { m[i], nullptr };
-		uint32_t ilens[1] = { m_len[i] };
+		memcpy(&sigs[i * siglen], s[i], siglen);
+		const unsigned char *inputs[3] = { fs ? s[i] : m[i], fs ? m[i] : nullptr, nullptr };
+		uint32_t ilens[2] = { fs ? (uint32_t)(2 * plen) : m_len[i], fs ? m_len[i] : 0 };
 		if (hm->hfunc_scattered(inputs, ilens, &dig[i * (size_t)hlen])) {
 			ok[i] = 0;
 			continue;
@@ -437,7 +435,9 @@ extern "C" int eccb200_dropin_ecdsa_verify_batch(const uint8_t **s, const uint8_
 		}
 	}
 	std::vector<int8_t> verdict(num, -1);
-	if (eccb200_ecdsa_verify_batch(eng, num, sigs.data(), pubs.data(), dig.data(), hlen, verdict.data())) return -1;
+	if (fs ? eccb200_ecfsdsa_verify_batch(eng, num, sigs.data(), pubs.data(), dig.data(), hlen, verdict.data())
+	       : eccb200_ecdsa_verify_batch(eng, num, sigs.data(), pubs.data(), dig.data(), hlen, verdict.data()))
+		return -1;
 	int all = 0;
 	for (uint32_t i = 0; i < num; i++) {
 		if (!ok[i]) verdict[i] = -1;
@@ -445,4 +445,29 @@ extern "C" int eccb200_dropin_ecdsa_verify_batch(const uint8_t **s, const uint8_
 	}
 	t_verdicts.assign(verdict.begin(), verdict.end());
 	return all;
+}
+
+extern "C" int eccb200_dropin_ecdsa_verify_batch(const uint8_t **s, const uint8_t *s_len,
+						 const eccb200_ec_pub_key **pub_keys, const uint8_t **m,
+						 const uint32_t *m_len, uint32_t num, int sig_type, int hash_type,
+						 const uint8_t **adata, const uint16_t *adata_len,
+						 void *scratch_pad_area, uint32_t *scratch_pad_area_len)
+{
+	(void)scratch_pad_area;
+	(void)scratch_pad_area_len;
+	(void)adata_len;
+	return verify_batch_common(false, s, s_len, pub_keys, m, m_len, num, sig_type, hash_type, adata);
+}
+
+/* ECFSDSA: a replacement for the reference's own ecfsdsa_verify_batch (sig/ecfsdsa.c:1057) in the same slot */
+extern "C" int eccb200_dropin_ecfsdsa_verify_batch(const uint8_t **s, const uint8_t *s_len,
+						   const eccb200_ec_pub_key **pub_keys, const uint8_t **m,
+						   const uint32_t *m_len, uint32_t num, int sig_type, int hash_type,
+						   const uint8_t **adata, const uint16_t *adata_len,
+						   void *scratch_pad_area, uint32_t *scratch_pad_area_len)
+{
+	(void)scratch_pad_area;
+	(void)scratch_pad_area_len;
+	(void)adata_len;
+	return verify_batch_common(true, s, s_len, pub_keys, m, m_len, num, sig_type, hash_type, adata);
 }

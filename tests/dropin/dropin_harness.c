@@ -78,8 +78,9 @@ static int run_direct(const char *dropin_path)
 	mul_fn gpu_mul_blind = (mul_fn)dlsym(h, "prj_pt_mul_blind");
 	mul_batch_fn gpu_batch = (mul_batch_fn)dlsym(h, "eccb200_dropin_prj_pt_mul_batch");
 	vbatch_fn gpu_vbatch = (vbatch_fn)dlsym(h, "eccb200_dropin_ecdsa_verify_batch");
+	vbatch_fn gpu_fsbatch = (vbatch_fn)dlsym(h, "eccb200_dropin_ecfsdsa_verify_batch");
 	verdicts_fn gpu_verdicts = (verdicts_fn)dlsym(h, "eccb200_dropin_last_verdicts");
-	if (!gpu_mul || !gpu_mul_blind || !gpu_batch || !gpu_vbatch || !gpu_verdicts) {
+	if (!gpu_mul || !gpu_mul_blind || !gpu_batch || !gpu_vbatch || !gpu_fsbatch || !gpu_verdicts) {
 		printf("FAIL missing drop-in symbols\n");
 		return 1;
 	}
@@ -196,6 +197,41 @@ static int run_direct(const char *dropin_path)
 			/* the generic entry point still reports ECDSA batch as unsupported in the unmodified reference */
 			CHECK(ec_verify_batch(sp, sl, pk, mp, ml, NS, ECDSA, ht, NULL, NULL, NULL, NULL) == -1,
 			      "reference ec_verify_batch(ECDSA) unexpectedly supported");
+		}
+		/* ---- ECFSDSA in the same slot: against the reference's ec_verify, item by item */
+		{
+			enum { NF = 24 };
+			static ec_key_pair kp[NF];
+			static u8 sigs[NF][3 * 66], msgs[NF][40];
+			const u8 *sp[NF], *mp[NF];
+			const ec_pub_key *pk[NF];
+			u8 sl[NF], plen = (u8)BYTECEIL(params.ec_fp.p_bitlen);
+			u32 ml[NF];
+			hash_alg_type ht = (c == 2) ? SHA384 : ((c == 5 || c == 7) ? SHA512 : SHA256);
+			for (int i = 0; i < NF; i++) {
+				CHECK(!ec_key_pair_gen(&kp[i], &params, ECFSDSA), "ecfsdsa keygen");
+				ml[i] = (u32)(1 + (rnd8() % 39));
+				for (u32 j = 0; j < ml[i]; j++) msgs[i][j] = rnd8();
+				sl[i] = (u8)(2 * plen + qlen);
+				CHECK(!ec_sign(sigs[i], sl[i], &kp[i], msgs[i], ml[i], ECFSDSA, ht, NULL, 0), "ec_sign ECFSDSA");
+				sp[i] = sigs[i];
+				mp[i] = msgs[i];
+				pk[i] = &kp[i].pub_key;
+			}
+			int r = gpu_fsbatch(sp, sl, pk, mp, ml, NF, ECFSDSA, ht, NULL, NULL, NULL, NULL);
+			CHECK(r == 0, "%s ecfsdsa verify_batch: valid batch rejected", names[c]);
+			sigs[3][2 * plen + 1] ^= 0x10; /* s */
+			sigs[7][0] ^= 1;               /* r off the curve */
+			msgs[11][0] ^= 1;
+			r = gpu_fsbatch(sp, sl, pk, mp, ml, NF, ECFSDSA, ht, NULL, NULL, NULL, NULL);
+			CHECK(r == -1, "%s ecfsdsa verify_batch: corrupted batch accepted", names[c]);
+			signed char v[NF];
+			CHECK(gpu_verdicts(v, NF) == NF, "verdict count");
+			for (int i = 0; i < NF; i++) {
+				int want = ec_verify(sigs[i], sl[i], pk[i], msgs[i], ml[i], ECFSDSA, ht, NULL, 0) ? -1 : 0;
+				CHECK(v[i] == want, "%s ecfsdsa verdict[%d] = %d, reference ec_verify says %d", names[c], i, v[i], want);
+			}
+			CHECK(v[3] == -1 && v[7] == -1 && v[11] == -1, "corrupted ECFSDSA items not flagged");
 		}
 		printf("direct %s done, failures so far %d\n", names[c], failures);
 	}

@@ -27,7 +27,8 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/libecc_b200.h but not exported"
     drop = ctypes.CDLL(os.path.join(os.path.dirname(libecc_b200.LIB_PATH), "libecc_b200_dropin.so"))
     decl2 = declared_symbols("libecc_b200_dropin.h")
-    assert {"prj_pt_mul", "prj_pt_mul_blind", "eccb200_dropin_ecdsa_verify_batch"} <= decl2
+    assert {"prj_pt_mul", "prj_pt_mul_blind", "eccb200_dropin_ecdsa_verify_batch",
+            "eccb200_dropin_ecfsdsa_verify_batch"} <= decl2
     for name in sorted(decl2):
         assert hasattr(drop, name), f"{name} declared in include/libecc_b200_dropin.h but not exported"
     assert set(os.listdir(os.path.join(ROOT, "include"))) == {"libecc_b200.h", "libecc_b200_dropin.h"}
