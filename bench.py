@@ -326,7 +326,9 @@ def main():
         threads = nproc()
         probe = min(n, 8 * threads)
         t, k, _ = cpu_run(args.workload, inputs, 0, probe, threads)
-        per_step = int(min(n, max(probe, (probe / t) * 10.0)))   # ~10 s of CPU work per step
+        # bounded sample: ~10 s of CPU work per step, less when many steps are asked for (whole run <= ~2-3 min)
+        step_s = max(1.0, min(10.0, 120.0 / max(1, args.steps)))
+        per_step = int(min(n, max(probe, (probe / t) * step_s)))
         for _ in range(min(args.warmup, 1)):
             cpu_run(args.workload, inputs, 0, min(per_step, 4 * probe), threads)
         times = []
