@@ -15,6 +15,17 @@
 #pragma once
 #include "ec.cuh"
 
+/* cluster-wide inversion experiment, see cta_inverse_128 */
+#ifndef ECC_CLUSTER_INV
+#define ECC_CLUSTER_INV 1
+#endif
+#if ECC_CLUSTER_INV > 1
+#include <cooperative_groups.h>
+#define ECC_CLUSTER_ATTR __cluster_dims__(ECC_CLUSTER_INV, 1, 1)
+#else
+#define ECC_CLUSTER_ATTR
+#endif
+
 namespace eccb200 {
 
 /* ------------------------------------------------------------------------------------------ device wire helpers */
@@ -157,8 +168,14 @@ template <class C> __device__ __forceinline__ bool load_affine_checked(Aff<C> &P
  * runs the ~330-product Fermat chain on the CTA product, and thread t computes inv_total * P[t-1] * S[t+1].
  * Must be called by all 128 threads of the CTA (it synchronises).  Cost per thread: 16 products + 1/4 inversion.
  */
-#define ECC_CTA_INV_WORDS(N) ((4 * 128 + 1) * (N)) /* shared words one CTA-wide inversion needs */
-template <class FT>
+/*
+ * Experimental (off by default, -DECC_CLUSTER_INV=2|4|8): K2 / K3 run as thread-block clusters and ONE Fermat chain
+ * serves the whole cluster — the CTA totals are exchanged through distributed shared memory, rank 0 inverts their
+ * product and hands every CTA the inverse of its own total.  The chain's share per thread drops from 330/4 to
+ * 330/(4*CL) product-equivalents (roofline.py: cta_inv).  Not part of the validated default build.
+ */
+#define ECC_CTA_INV_WORDS(N) ((4 * 128 + 2 + 8) * (N)) /* shared words one CTA-wide inversion needs */
+template <class FT, int CL = 1>
 __device__ __forceinline__ void cta_inverse_128(Fe<FT::N> &inv, const Fe<FT::N> &acc, uint32_t *__restrict__ sh)
 {
 	typedef Field<FT> F;
@@ -201,18 +218,75 @@ __device__ __forceinline__ void cta_inverse_128(Fe<FT::N> &inv, const Fe<FT::N> 
 		cur ^= 1;
 	}
 	/* pv = prod_{u <= t} acc_u, sv = prod_{u >= t} acc_u; CTA product = P[127] */
-	if (t < 32) {
-		Fe<N> tot, ti;
-		ld_sh(tot, sP[cur], 127);
-		F::inv(ti, tot);
+#if ECC_CLUSTER_INV > 1
+	if (CL > 1) {
+		namespace cg = cooperative_groups;
+		cg::cluster_group cluster = cg::this_cluster();
+		const unsigned rank = cluster.block_rank();
+		uint32_t *sTot = sh + (4 * 128 + 1) * N;  /* this CTA's total, read by rank 0 */
+		uint32_t *sInvs = sh + (4 * 128 + 2) * N; /* rank 0: inverse of every CTA's total, [CL][N] */
 		if (t == 0) {
+			Fe<N> tot;
+			ld_sh(tot, sP[cur], 127);
 #pragma unroll
-			for (int j = 0; j < N; j++) sInv[j] = ti.w[j];
+			for (int j = 0; j < N; j++) sTot[j] = tot.w[j];
 		}
-	}
-	__syncthreads();
+		cluster.sync();
+		if (rank == 0 && t < 32) {
+			Fe<N> T[CL], pre[CL], suf[CL], ti, r;
 #pragma unroll
-	for (int j = 0; j < N; j++) inv.w[j] = sInv[j];
+			for (int c = 0; c < CL; c++) {
+				const uint32_t *rt = cluster.map_shared_rank(sTot, c);
+#pragma unroll
+				for (int j = 0; j < N; j++) T[c].w[j] = rt[j];
+			}
+			pre[0] = T[0];
+#pragma unroll
+			for (int c = 1; c < CL; c++) F::mul(pre[c], pre[c - 1], T[c]);
+			suf[CL - 1] = T[CL - 1];
+#pragma unroll
+			for (int c = CL - 2; c >= 0; c--) F::mul(suf[c], suf[c + 1], T[c]);
+			F::inv(ti, pre[CL - 1]);
+#pragma unroll
+			for (int c = 0; c < CL; c++) {
+				Fe<N> v = ti;
+				if (c > 0) {
+					F::mul(r, v, pre[c - 1]);
+					v = r;
+				}
+				if (c < CL - 1) {
+					F::mul(r, v, suf[c + 1]);
+					v = r;
+				}
+				if (t == 0) {
+#pragma unroll
+					for (int j = 0; j < N; j++) sInvs[c * N + j] = v.w[j];
+				}
+			}
+		}
+		cluster.sync();
+		{
+			const uint32_t *r0 = cluster.map_shared_rank(sInvs, 0);
+#pragma unroll
+			for (int j = 0; j < N; j++) inv.w[j] = r0[rank * N + j];
+		}
+		cluster.sync(); /* rank 0's shared memory has been read by everyone */
+	} else
+#endif
+	{
+		if (t < 32) {
+			Fe<N> tot, ti;
+			ld_sh(tot, sP[cur], 127);
+			F::inv(ti, tot);
+			if (t == 0) {
+#pragma unroll
+				for (int j = 0; j < N; j++) sInv[j] = ti.w[j];
+			}
+		}
+		__syncthreads();
+#pragma unroll
+		for (int j = 0; j < N; j++) inv.w[j] = sInv[j];
+	}
 	Fe<N> o, r;
 	if (t > 0) {
 		ld_sh(o, sP[cur], t - 1);
@@ -328,7 +402,7 @@ __global__ void __launch_bounds__(128) k_smul_fixed_tma(uint32_t n, const uint8_
 #define ECC_MINB_VERIFY_WIDE 4
 #endif
 template <class C>
-__global__ void __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VAR : (C::N <= 12 ? ECC_MINB_VAR_WIDE : 2))) k_smul_var(uint32_t n, const uint8_t *__restrict__ scalars,
+__global__ void ECC_CLUSTER_ATTR __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VAR : (C::N <= 12 ? ECC_MINB_VAR_WIDE : 2))) k_smul_var(uint32_t n, const uint8_t *__restrict__ scalars,
 						  const uint8_t *__restrict__ points, uint32_t *__restrict__ jac,
 						  int8_t *__restrict__ status)
 {
@@ -352,7 +426,7 @@ __global__ void __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VAR : (C::N <= 12 ?
 	}
 	Jac<C> acc;
 	window_mul<C>(acc, k, P, nullptr, [&](Fe<C::N> &r, const Fe<C::N> &a) {
-		cta_inverse_128<typename C::Fp>(r, a, sh_inv);
+		cta_inverse_128<typename C::Fp, ECC_CLUSTER_INV>(r, a, sh_inv);
 	});
 	if (!active) return;
 	if (!ok) EC<C>::set_inf(acc);
@@ -607,7 +681,7 @@ __global__ void __launch_bounds__(128) k_prj_load(uint32_t n, const uint8_t *__r
  * digests: hlen bytes each; e = leftmost min(8*hlen, bitlen(q)) bits (:760-775), reduced mod q (:777).
  */
 template <class C, int SCHEME = 0>
-__global__ void __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VERIFY : (C::N <= 12 ? ECC_MINB_VERIFY_WIDE : 2))) k_ecdsa_verify(uint32_t n, const uint8_t *__restrict__ sigs,
+__global__ void ECC_CLUSTER_ATTR __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VERIFY : (C::N <= 12 ? ECC_MINB_VERIFY_WIDE : 2))) k_ecdsa_verify(uint32_t n, const uint8_t *__restrict__ sigs,
 						      const uint8_t *__restrict__ pubkeys,
 						      const uint8_t *__restrict__ digests, uint32_t hlen,
 						      const uint32_t *__restrict__ table, int w,
@@ -647,7 +721,7 @@ __global__ void __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VERIFY : (C::N <= 1
 			}
 		}
 		int code = ecfsdsa_verify_tail<C>(Rp, s, h, Y, table, w, [&](Fe<N> &o, const Fe<N> &a) {
-			cta_inverse_128<typename C::Fp>(o, a, sh_inv1);
+			cta_inverse_128<typename C::Fp, ECC_CLUSTER_INV>(o, a, sh_inv1);
 		});
 		if (!active) return;
 		if (!run) code = 1;
@@ -664,7 +738,7 @@ __global__ void __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VERIFY : (C::N <= 1
 	Fe<N> sm, wm;
 	Fq::set_one(sm);
 	if (rs_ok) Fq::to_mont(sm, s);
-	cta_inverse_128<typename C::Fq>(wm, sm, sh_inv);
+	cta_inverse_128<typename C::Fq, ECC_CLUSTER_INV>(wm, sm, sh_inv);
 	Aff<C> Y;
 	const int ks = key_state ? (int)key_state[i0] : 0;
 	bool key_ok = load_affine_checked<C>(Y, pubkeys + (size_t)i0 * (2 * C::PLEN));
@@ -688,7 +762,7 @@ __global__ void __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VERIFY : (C::N <= 1
 		}
 	}
 	int code = ecdsa_verify_tail<C>(r, u, v, Y, table, w, ks == 1, [&](Fe<N> &o, const Fe<N> &a) {
-		cta_inverse_128<typename C::Fp>(o, a, sh_inv);
+		cta_inverse_128<typename C::Fp, ECC_CLUSTER_INV>(o, a, sh_inv);
 	});
 	if (!active) return;
 	if (!key_ok) code = 4;
@@ -951,6 +1025,11 @@ namespace eccb200 {
 
 static const int kThreads = 128;
 static inline uint32_t grid_for(uint32_t n) { return (n + kThreads - 1) / kThreads; }
+/* grids of the cluster kernels are whole clusters (idle CTAs take part in the inversion and write nothing) */
+static inline uint32_t grid_clustered(uint32_t n)
+{
+	return (grid_for(n) + ECC_CLUSTER_INV - 1) / ECC_CLUSTER_INV * ECC_CLUSTER_INV;
+}
 
 /* K1 group: compiled with the multiplier INLINED (ECC_INLINE_MUL): its loop body is one mixed addition and runs
  * 5-9 % faster that way; K2 / K3 groups call the out-of-line multiplier, which keeps their much larger loop bodies
@@ -1027,7 +1106,7 @@ template <class C>
 void LaunchVar<C>::var(uint32_t n, const uint8_t *scalars, const uint8_t *points, uint32_t *jac, int8_t *status,
 		       cudaStream_t st)
 {
-	k_smul_var<C><<<grid_for(n), kThreads, 0, st>>>(n, scalars, points, jac, status);
+	k_smul_var<C><<<grid_clustered(n), kThreads, 0, st>>>(n, scalars, points, jac, status);
 }
 template <class C> void LaunchVar<C>::table_points(uint32_t entries, int w, uint32_t *jac, cudaStream_t st)
 {
@@ -1111,14 +1190,14 @@ void LaunchVerify<C>::verify(uint32_t n, const uint8_t *sigs, const uint8_t *pub
 			     uint32_t hlen, const uint32_t *table, int w, int8_t *verdict, cudaStream_t st,
 			     const int8_t *key_state)
 {
-	k_ecdsa_verify<C><<<grid_for(n), kThreads, 0, st>>>(n, sigs, pubkeys, digests, hlen, table, w, verdict,
+	k_ecdsa_verify<C><<<grid_clustered(n), kThreads, 0, st>>>(n, sigs, pubkeys, digests, hlen, table, w, verdict,
 							     key_state);
 }
 template <class C>
 void LaunchVerify<C>::ecfsdsa(uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys, const uint8_t *digests,
 			      uint32_t hlen, const uint32_t *table, int w, int8_t *verdict, cudaStream_t st)
 {
-	k_ecdsa_verify<C, 1><<<grid_for(n), kThreads, 0, st>>>(n, sigs, pubkeys, digests, hlen, table, w, verdict, nullptr);
+	k_ecdsa_verify<C, 1><<<grid_clustered(n), kThreads, 0, st>>>(n, sigs, pubkeys, digests, hlen, table, w, verdict, nullptr);
 }
 template <class C>
 void LaunchVerify<C>::uv(uint32_t n, const uint8_t *sigs, const uint8_t *digests, uint32_t hlen, uint8_t *out,
