@@ -12,7 +12,7 @@
  *   - bare u64[n] instead of the 27-word nn container with magic/wlen (nn.h:67-71);
  *   - WORD_MUL (words.h:98-127) is one unsigned __int128 product;
  *   - s^-1 mod q by Fermat instead of the binary xgcd of nn_modinv.c:220 (same unique inverse, q prime);
- *   - Montgomery constants (mpinv, R, R^2) are derived here instead of read from curves/known/*.h.
+ *   - Montgomery constants (mpinv, R, R^2) are derived here instead of read from the curves/known headers.
  */
 #include "ecc_oracle.h"
 #include <pthread.h>

@@ -5,7 +5,7 @@
  * are the only permitted callers.  The product (libecc_b200/) never links, loads or calls this.
  *
  * Parity status: PINNED — tests/test_oracle.py checks this port against (i) the golden vectors extracted from
- * the reference's own test headers (tests/golden/*.json: NIST ECC-CDH, RFC 4754/6979 ECDSA, Wycheproof) and
+ * the reference's own test headers (the tests/golden JSON files: NIST ECC-CDH, RFC 4754/6979 ECDSA, Wycheproof) and
  * (ii) the unmodified reference compiled here (oracle/_ref/libecc_ref.so) on seeded random inputs.
  */
 #ifndef ECC_ORACLE_H
