@@ -4,13 +4,17 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
 A "step" is one pass of the hot path over one batch of synthetic input.  Default workload (N = 1) is BASELINE.json
-configs[1]: 2^20 random scalars on the fixed base G of secp256r1 per GPU.  Other workloads (parity-test configs, also
-usable for extra measurements): secp384r1_fixed_base, secp256r1_variable_base, frp256v1_ecdsa_verify.
+configs[1]: 2^20 random scalars on the fixed base G of secp256r1 per GPU.  The other configs of BASELINE.json
+(frp256v1_ecdsa_verify = config 3, secp384r1_fixed_base = config 4, the variable-base form, config 5's 2^24 over 8
+GPUs) are measured by the same code on short runs and reported in the `extra` block of the same JSON line.
 
-Ours arm, per step and per rank (one process per GPU; torchrun for N > 1):
-  value  : inputs resident in HBM, eccb200_*_batch_dev on torch's current stream, for N > 1 followed by the NCCL
-           all-gather of the results (the path's only exchange step); CUDA events, max over ranks.
-  e2e    : the host-pointer C-ABI call (eccb200_prj_pt_mul_batch / eccb200_ecdsa_verify_batch) on host buffers:
+Ours arm, per step and per rank (one process per GPU; torchrun for N > 1) — the SAME timing protocol at every N:
+  value  : inputs resident in HBM, eccb200_*_batch_dev on torch's current stream; per-step CUDA events with the L2
+           flush between steps outside them; sum over the K steps, max over ranks.  For N > 1 the step includes the
+           result gather: the normalisation kernel of every rank stores its results straight into rank 0's gathered
+           buffer over NVLink (peer-mapped memory) and rank 0's step ends only when every rank's results have landed
+           (--gather peer-root, default; peer-all = every rank receives everything; nccl = one all_gather per step).
+  e2e    : the host-pointer C-ABI call (eccb200_prj_pt_mul_batch / eccb200_ecdsa_verify_msgs_batch) on host buffers:
            host->device copy of the step's inputs and device->host copy of its results inside the timed region.
   roofline: the dominant kernel's own duration (CUDA events recorded by the library around that kernel on the
            launching stream) against the measured integer multiply-add peak (imad_peak micro-benchmark, run here).
@@ -24,6 +28,7 @@ from __future__ import annotations
 
 import argparse
 import ctypes
+import hashlib
 import json
 import os
 import statistics
@@ -53,6 +58,11 @@ WORKLOADS = {
     "secp521r1_ecdsa_verify": ("SECP521R1", "verify", "secp521r1 ECDSA ec_verify/sec", "ec_verify/s"),
 }
 SEED = 0x6C69626563632D31
+MSG_LEN = 32          # the ECDSA workloads verify MESSAGES (ec_verify hashes them): 32 random bytes each, SHA-256
+VERIFY_HASH = "SHA256"
+# comb window of the fixed-base table when --comb-window is not given: the widest table that pays on a B200
+# (measured sweep in DESIGN.md §4); other curves keep the library default
+DEFAULT_COMB = {"SECP256R1": int(os.environ.get("BENCH_COMB_WINDOW", "0"))}
 
 
 def splitmix_bytes(n_bytes: int, tag: int) -> np.ndarray:
@@ -65,6 +75,29 @@ def nproc() -> int:
         return len(os.sched_getaffinity(0))
     except Exception:
         return os.cpu_count() or 1
+
+
+def host_info() -> dict:
+    """What the CPU numbers were measured on (the same 'cores' figure meant 5x different rates on two boxes)."""
+    info = {"affinity_cpus": nproc(), "os_cpus": os.cpu_count()}
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                info["model"] = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    try:
+        info["loadavg"] = [float(x) for x in open("/proc/loadavg").read().split()[:3]]
+    except (OSError, ValueError):
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            info["cgroup_cpu_limit"] = open(path).read().strip()
+            break
+        except OSError:
+            continue
+    return info
 
 
 class ClockSampler(threading.Thread):
@@ -120,28 +153,34 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------------------------------------ inputs
 
-def make_inputs(workload: str, n: int, rank: int, use_gpu: bool = True):
-    """Seeded synthetic inputs of SURVEY.md §8d for one rank (host numpy arrays)."""
+def make_scalars(curve: str, n: int, tag: int) -> np.ndarray:
+    """Seeded scalars of SURVEY.md §8d: uniform in [1, q-1] plus ~0.1 % edge scalars (0, 1, q-1, q, q+1, 2^l-1, ...)."""
     from common import ALL_CURVES as CURVES, ORDER, edge_scalars
-    curve, kind, _, _ = WORKLOADS[workload]
     _, plen, qlen = CURVES[curve]
     q = ORDER[curve]
-    raw = splitmix_bytes(n * qlen, 100 + rank).reshape(n, qlen)
+    raw = splitmix_bytes(n * qlen, tag).reshape(n, qlen)
     raw[:, 0] &= (1 << (q.bit_length() - 8 * (qlen - 1))) - 1   # bitlen(q) need not be a multiple of 8 (P-521)
-    # uniform in [1, q-1]: clear the top bit pattern that could exceed q cheaply (rejection on the few rows >= q)
     vals_hi = raw[:, 0].astype(np.int64)
     qb = np.frombuffer(q.to_bytes(qlen, "big"), dtype=np.uint8)
-    suspicious = np.nonzero(vals_hi >= int(qb[0]))[0]
-    g = np.random.default_rng(7 + rank)
+    suspicious = np.nonzero(vals_hi >= int(qb[0]))[0]           # rejection on the few rows that could be >= q
+    g = np.random.default_rng(7 + tag)
     for i in suspicious:
         while not (0 < int.from_bytes(raw[i].tobytes(), "big") < q):
             raw[i] = g.integers(0, 256, size=qlen, dtype=np.uint8)
             raw[i, 0] &= (1 << (q.bit_length() - 8 * (qlen - 1))) - 1
-    # ~0.1 % adversarial slots: k in {0, 1, 2, q-1, q, q+1, 2^(8 qlen)-1, ...}
     es = edge_scalars(curve)
     slots = np.arange(0, n, 1024)[: max(1, n // 1024)]
     raw[slots] = es[np.arange(len(slots)) % es.shape[0]]
-    inputs = {"scalars": np.ascontiguousarray(raw)}
+    return np.ascontiguousarray(raw)
+
+
+def make_inputs(workload: str, n: int, rank: int, use_gpu: bool = True):
+    """Seeded synthetic inputs for one rank (host numpy arrays).  Fixed / variable base: TWO scalar sets, used by
+    alternate steps so that consecutive steps do not gather the same table entries."""
+    curve, kind, _, _ = WORKLOADS[workload]
+    inputs = {"scalars": make_scalars(curve, n, 100 + rank)}
+    if kind in ("fixed", "var"):
+        inputs["scalars_b"] = make_scalars(curve, n, 4100 + rank)
     if kind == "var":
         inputs["points"] = make_points(curve, n, rank)
     if kind == "verify":
@@ -157,7 +196,7 @@ def make_points(curve: str, n: int, rank: int) -> np.ndarray:
     qlen = ALL_CURVES[curve][2]
     sc = splitmix_bytes(n * qlen, 300 + rank).reshape(n, qlen)
     sc[:, 0] &= ((1 << (ORDER[curve].bit_length() - 8 * (qlen - 1))) - 1) >> 1   # < q without rejection
-    eng = libecc_b200.Engine(curve, device=int(os.environ.get("LOCAL_RANK", 0)))
+    eng = libecc_b200.Engine(curve, device=int(os.environ.get("LOCAL_RANK", 0)), comb_window=16)
     pts, st = eng.prj_pt_mul_batch(sc)
     assert (st == 0).all()
     want, _ = oracle_smul(curve, sc[:64])
@@ -166,24 +205,50 @@ def make_points(curve: str, n: int, rank: int) -> np.ndarray:
     return pts
 
 
+def sha256_rows(msgs: np.ndarray) -> np.ndarray:
+    return np.frombuffer(b"".join(hashlib.sha256(m.tobytes()).digest() for m in msgs), dtype=np.uint8) \
+        .reshape(len(msgs), 32).copy()
+
+
 def make_verify_inputs(curve: str, n: int, rank: int, use_gpu: bool = True):
-    """(sigs, pubkeys, digests, expected) of SURVEY.md §8d.3: a distinct random key per tuple, 1/16 of the tuples
-    corrupted (bit flip in r, s, digest or key; r = 0; s >= q) with the expected verdict recorded.
-    Ours arm: keys and signatures come from the engine's own batch signer (eccb200_ecdsa_sign_batch: d*G for the
-    keys, then r, s), and a 2^12 sample is cross-checked with the oracle's signer and verifier.  Reference arm (no
-    GPU): the oracle's signer on a 2^12 pool, tiled."""
-    from common import ALL_CURVES as CURVES, ORDER, make_signatures, oracle_sign, oracle_verify
+    """(sigs, pubkeys, msgs, digests, expected) of SURVEY.md §8d.3: a distinct random key and a distinct random 32-byte
+    message per tuple, 1/16 of the tuples corrupted (bit flip in r, s, message or key; r = 0; s = q) with the expected
+    verdict recorded.  Ours arm: digests, keys and signatures come from the engine's own batch entry points (device
+    SHA-256, d*G, then r, s); a 2^12 sample is cross-checked with hashlib and the oracle's signer and verifier.
+    Reference arm (no GPU): hashlib + the oracle's signer on a 2^12 pool, tiled."""
+    from common import ALL_CURVES as CURVES, ORDER, oracle_sign, oracle_smul, oracle_verify, random_scalars
     _, plen, qlen = CURVES[curve]
     hlen = 32
+    q = ORDER[curve]
+    qbytes = np.frombuffer(q.to_bytes(qlen, "big"), dtype=np.uint8)
+
+    def corrupt(sigs, pubs, msgs, count):
+        expected = np.zeros(count, dtype=np.int8)
+        idx = np.arange(0, count, 16)
+        kind = (idx // 16) % 6
+        expected[idx] = -1
+        sigs[idx[kind == 0], qlen - 1] ^= 1              # bit flip in r
+        sigs[idx[kind == 1], 2 * qlen - 1] ^= 1          # bit flip in s
+        msgs[idx[kind == 2], 0] ^= 0x80                  # bit flip in the message
+        pubs[idx[kind == 3], plen - 1] ^= 1              # key off the curve
+        sigs[idx[kind == 4], :qlen] = 0                  # r = 0
+        sigs[idx[kind == 5], qlen:] = qbytes             # s = q
+        return expected
+
     if not use_gpu:
         pool = min(1 << 12, n)
-        sigs, pubs, dg, exp = make_signatures(curve, pool, tag=500 + rank, corrupt_every=16)
+        msgs = splitmix_bytes(pool * MSG_LEN, 800 + rank).reshape(pool, MSG_LEN)
+        d = random_scalars(curve, pool, tag=1500 + rank)
+        k = random_scalars(curve, pool, tag=2500 + rank)
+        pubs, st = oracle_smul(curve, d)
+        sigs, st = oracle_sign(curve, d, k, sha256_rows(msgs), hlen)
+        expected = corrupt(sigs, pubs, msgs, pool)
+        assert (oracle_verify(curve, sigs, pubs, sha256_rows(msgs), hlen) == expected).all()
         reps = (n + pool - 1) // pool
         tile = lambda a: np.ascontiguousarray(np.tile(a, (reps, 1))[:n])
-        return {"sigs": tile(sigs), "pubkeys": tile(pubs), "digests": tile(dg),
-                "expected": np.tile(exp, reps)[:n].copy(), "hlen": hlen}
+        return {"sigs": tile(sigs), "pubkeys": tile(pubs), "msgs": tile(msgs), "expected": np.tile(expected, reps)[:n].copy(),
+                "hlen": hlen}
     import libecc_b200
-    q = ORDER[curve]
     d = splitmix_bytes(n * qlen, 600 + rank).reshape(n, qlen)
     k = splitmix_bytes(n * qlen, 700 + rank).reshape(n, qlen)
     safe = ((1 << (q.bit_length() - 8 * (qlen - 1))) - 1) >> 1   # 0x7F for byte-aligned orders, 0 for P-521
@@ -191,28 +256,22 @@ def make_verify_inputs(curve: str, n: int, rank: int, use_gpu: bool = True):
     k[:, 0] &= safe
     d[:, -1] |= 1
     k[:, -1] |= 1                                   # in [1, q-1]: top bit clear, never zero
-    dg = splitmix_bytes(n * hlen, 800 + rank).reshape(n, hlen)
-    eng = libecc_b200.Engine(curve, device=int(os.environ.get("LOCAL_RANK", 0)))
+    msgs = splitmix_bytes(n * MSG_LEN, 800 + rank).reshape(n, MSG_LEN)
+    off = np.arange(n + 1, dtype=np.uint64) * MSG_LEN
+    eng = libecc_b200.Engine(curve, device=int(os.environ.get("LOCAL_RANK", 0)), comb_window=16)
+    dg = eng.hash_batch_raw(VERIFY_HASH, msgs, off)
     pubs, st = eng.prj_pt_mul_batch(d)
     assert (st == 0).all()
     sigs, st = eng.ecdsa_sign_batch(d, k, dg, hlen)
     assert (st == 0).all()
     eng.close()
-    m = min(n, 1 << 12)                              # cross-check of the signer on a 2^12 sample
+    m = min(n, 1 << 12)                              # cross-check of the hashing and of the signer on a 2^12 sample
+    assert (dg[:m] == sha256_rows(msgs[:m])).all()
     want, wst = oracle_sign(curve, d[:m], k[:m], dg[:m], hlen)
     assert (wst == 0).all() and (want == sigs[:m]).all()
-    expected = np.zeros(n, dtype=np.int8)
-    idx = np.arange(0, n, 16)
-    kind = (idx // 16) % 6
-    expected[idx] = -1
-    sigs[idx[kind == 0], qlen - 1] ^= 1              # bit flip in r
-    sigs[idx[kind == 1], 2 * qlen - 1] ^= 1          # bit flip in s
-    dg[idx[kind == 2], 0] ^= 0x80                    # bit flip in the digest
-    pubs[idx[kind == 3], plen - 1] ^= 1              # key off the curve
-    sigs[idx[kind == 4], :qlen] = 0                  # r = 0
-    sigs[idx[kind == 5], qlen:] = np.frombuffer(q.to_bytes(qlen, "big"), dtype=np.uint8)  # s = q
-    assert (oracle_verify(curve, sigs[:m], pubs[:m], dg[:m], hlen) == expected[:m]).all()
-    return {"sigs": sigs, "pubkeys": pubs, "digests": dg, "expected": expected, "hlen": hlen}
+    expected = corrupt(sigs, pubs, msgs, n)
+    assert (oracle_verify(curve, sigs[:m], pubs[:m], sha256_rows(msgs[:m]), hlen) == expected[:m]).all()
+    return {"sigs": sigs, "pubkeys": pubs, "msgs": msgs, "expected": expected, "hlen": hlen}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms
@@ -247,10 +306,17 @@ def cpu_run(workload: str, inputs, lo: int, cnt: int, threads: int):
         return time.perf_counter() - t0, k, (out, st)
     sg = np.ascontiguousarray(inputs["sigs"][lo:lo + cnt])
     pk = np.ascontiguousarray(inputs["pubkeys"][lo:lo + cnt])
-    dg = np.ascontiguousarray(inputs["digests"][lo:lo + cnt])
+    ms = np.ascontiguousarray(inputs["msgs"][lo:lo + cnt])
     v = np.zeros(cnt, dtype=np.int8)
+    if ref is not None:
+        # the reference's own ec_verify on the MESSAGES: key import, SHA-256, verification (src/sig/sig_algs.c:655)
+        off = np.arange(cnt + 1, dtype=np.uint64) * MSG_LEN
+        t0 = time.perf_counter()
+        ref.ref_ecdsa_verify_batch(curve.encode(), VERIFY_HASH.encode(), cnt, ptr(sg), ptr(pk), ptr(ms), ptr(off), ptr(v),
+                                   threads)
+        return time.perf_counter() - t0, "reference", (v,)
     t0 = time.perf_counter()
-    # pre-hashed inputs: the oracle port takes digests directly (the reference's ec_verify hashes a message itself)
+    dg = sha256_rows(ms)                  # the port takes digests: hashing timed with it
     oracle_lib().ora_ecdsa_verify_digest_batch(curve.encode(), cnt, ptr(sg), ptr(pk), ptr(dg), inputs["hlen"], ptr(v),
                                                threads)
     return time.perf_counter() - t0, "port", (v,)
@@ -265,31 +331,370 @@ def cpu_baseline(workload: str, inputs, budget_s: float = 12.0):
     cnt = int(min(n, max(probe, rate * budget_s)))
     t, kind, outs = cpu_run(workload, inputs, 0, cnt, threads)
     return {"value": cnt / t, "unit": WORKLOADS[workload][3], "cores": threads, "kind": kind,
-            "sample": f"first {cnt} items of the step's batch, {t:.1f} s on {threads} threads"}, cnt, outs
+            "sample": f"first {cnt} items of the step's batch, {t:.1f} s on {threads} threads",
+            "host": host_info()}, cnt, outs
 
 
 def ncu_dram_traffic(workload: str, batch_log2: int, comb_window: int):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
     `ncu --set full` capture of this exact configuration (profiles/); None when no capture matches."""
-    if not (workload == "secp256r1_fixed_base" and batch_log2 == 20 and comb_window == 22):
-        return None
-    path = os.path.join(ROOT, "profiles", "r01_ncu_smul_fixed_final2.csv")
+    table = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
-        tot = 0.0
-        for line in open(path):
-            parts = line.strip().split(",")
-            if parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[parts[1]]
-                tot += float(parts[2]) * scale
-        return {"bytes_per_launch": tot, "algorithmic_bytes_per_launch": (1 << batch_log2) * (32 + 96 + 1 + 12 * 64),
-                "source": "profiles/r01_ncu_smul_fixed_final2.csv; algorithmic = scalar 32 B + Jacobian result 96 B + "
-                          "status 1 B + 12 random 64 B table entries per item (3.2 GiB table, mostly L2 misses, "
-                          "fetched in 128 B lines); 13 % of the measured HBM bandwidth - not the bound"}
-    except OSError:
+        entries = json.load(open(table))
+    except (OSError, ValueError):
         return None
+    for e in entries:
+        if e["workload"] == workload and e["batch_log2"] == batch_log2 and e["comb_window"] == comb_window:
+            return e
+    return None
 
 
-# ------------------------------------------------------------------------------------------------ main
+def run_reference(args, rank: int):
+    """--impl reference: the reference's own CPU path, bounded sample per step, rank 0 only."""
+    if rank != 0:
+        return
+    curve, kind, metric, unit = WORKLOADS[args.workload]
+    n = 1 << args.batch_log2
+    config = workload_config(args.workload, args.batch_log2, 1)
+    if kind == "var":
+        # no GPU on this arm: derive the points with the CPU oracle on the bounded sample only
+        from common import oracle_smul
+        inputs = {"scalars": make_scalars(curve, n, 100)}
+        m = min(n, 1 << 12)
+        pts, _ = oracle_smul(curve, splitmix_bytes(m * 32, 300).reshape(m, 32) & 0x7F)
+        inputs["points"] = np.tile(pts, ((n + m - 1) // m, 1))[:n]
+    else:
+        inputs = make_inputs(args.workload, n, 0, use_gpu=False)
+    threads = nproc()
+    probe = min(n, 8 * threads)
+    t, k, _ = cpu_run(args.workload, inputs, 0, probe, threads)
+    # bounded sample: ~10 s of CPU work per step, less when many steps are asked for (whole run <= ~2-3 min)
+    step_s = max(1.0, min(10.0, 120.0 / max(1, args.steps)))
+    per_step = int(min(n, max(probe, (probe / t) * step_s)))
+    for _ in range(min(args.warmup, 1)):
+        cpu_run(args.workload, inputs, 0, min(per_step, 4 * probe), threads)
+    times = []
+    for s in range(args.steps):
+        lo = (s * per_step) % max(1, n - per_step + 1)
+        t, k, _ = cpu_run(args.workload, inputs, lo, per_step, threads)
+        times.append(t)
+    val = per_step * len(times) / sum(times)
+    line = {"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * sum(times) / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": val, "unit": unit, "cores": threads, "kind": k,
+                             "sample": f"{per_step} items per step (bounded sample of the 2^{args.batch_log2} batch)",
+                             "host": host_info()},
+            "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(workload: str, batch_log2: int, world: int) -> dict:
+    curve = WORKLOADS[workload][0]
+    n = 1 << batch_log2
+    return {"workload": f"{workload}: 2^{batch_log2} items per GPU per step, seeded synthetic "
+                        f"(uniform scalars in [1,q-1] + 0.1% edge scalars)",
+            "curve": curve, "batch_per_gpu": n, "global_batch": n * world}
+
+
+# ------------------------------------------------------------------------------------------------ ours
+
+class Ours:
+    """One workload on this rank's GPU: device-resident leg (`value`), host-pointer leg (`e2e`), parity checks."""
+
+    def __init__(self, workload: str, batch_log2: int, comb_window: int, rank: int, world: int, local_rank: int,
+                 gather: str):
+        import torch
+        import libecc_b200
+        from common import ALL_CURVES as CURVES
+        self.torch = torch
+        self.workload, self.batch_log2 = workload, batch_log2
+        self.curve, self.kind, self.metric, self.unit = WORKLOADS[workload]
+        self.n = 1 << batch_log2
+        self.rank, self.world, self.local_rank = rank, world, local_rank
+        self.gather = gather if (world > 1 and self.kind != "verify") else ("nccl" if world > 1 else "none")
+        _, self.plen, self.qlen = CURVES[self.curve]
+        self.dev = torch.device("cuda", local_rank)
+        self.inputs = make_inputs(workload, self.n, rank)
+        if not comb_window:
+            comb_window = DEFAULT_COMB.get(self.curve, 0)
+        self.eng = libecc_b200.Engine(self.curve, device=local_rank, comb_window=comb_window)
+        n, plen = self.n, self.plen
+        skip = ("expected",)
+        self.d = {k: torch.from_numpy(v).to(self.dev) for k, v in self.inputs.items()
+                  if isinstance(v, np.ndarray) and k not in skip}
+        if self.kind == "verify":
+            self.d["offsets"] = (torch.arange(n + 1, dtype=torch.int64, device=self.dev) * MSG_LEN)
+            self.d["digests"] = torch.empty(n * 32, dtype=torch.uint8, device=self.dev)
+            self.d_out = torch.empty(n, dtype=torch.int8, device=self.dev)
+            self.d_status = None
+            self.out_item = 1
+            self.in_item = 2 * self.qlen + 2 * plen + MSG_LEN + 8
+        else:
+            self.d_out = torch.empty(n * 2 * plen, dtype=torch.uint8, device=self.dev)
+            self.d_status = torch.empty(n, dtype=torch.int8, device=self.dev)
+            self.out_item = 2 * plen + 1
+            self.in_item = self.qlen + (2 * plen if self.kind == "var" else 0)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
+        self.pg = None
+        self.step_no = 0
+        self.last_buf = 0
+        if self.gather.startswith("peer"):
+            from libecc_b200.sharding import PeerGather
+            self.pg = PeerGather(self.eng, rank, world, n, mode="root" if self.gather == "peer-root" else "all")
+        elif self.gather == "nccl":
+            out_rec = 1 if self.kind == "verify" else 2 * plen
+            self.res_bytes = n * out_rec + (0 if self.kind == "verify" else n)
+            self.res = torch.empty(self.res_bytes, dtype=torch.uint8, device=self.dev)
+            self.gathered = torch.empty(world * self.res_bytes, dtype=torch.uint8, device=self.dev)
+
+    # one step of the device-resident leg on torch's current stream
+    def step_dev(self):
+        torch, eng, d, n = self.torch, self.eng, self.d, self.n
+        stream = torch.cuda.current_stream().cuda_stream
+        sc = d["scalars_b"] if (self.step_no & 1 and "scalars_b" in d) else d.get("scalars")
+        self.step_no += 1
+        if self.kind == "verify":
+            out = self.res[:n].view(torch.int8) if self.gather == "nccl" else self.d_out
+            eng.ecdsa_verify_msgs_batch_dev(VERIFY_HASH, d["sigs"].view(-1), d["pubkeys"].view(-1), d["msgs"].view(-1),
+                                            d["offsets"], d["digests"], out, stream)
+        elif self.pg is not None:
+            pts = d["points"].data_ptr() if self.kind == "var" else None
+            self.last_buf = self.pg.step(sc.data_ptr(), pts, self.d_out.data_ptr(), self.d_status.data_ptr(), stream)
+        else:
+            if self.gather == "nccl":
+                out, st = self.res[: n * 2 * self.plen], self.res[n * 2 * self.plen:].view(torch.int8)
+            else:
+                out, st = self.d_out, self.d_status
+            eng.prj_pt_mul_batch_dev(sc.view(-1), d["points"].view(-1) if self.kind == "var" else None, out, st, stream)
+        if self.gather == "nccl":     # the path's exchange step as a collective: same stream, inside the step's events
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self.gathered, self.res)
+
+    def sync_all(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def measure_device(self, steps: int, warmup: int) -> dict:
+        torch, eng = self.torch, self.eng
+        eng.profile_enable(True)
+        for _ in range(warmup):
+            self.step_dev()
+            self.flush.zero_()
+        self.sync_all()
+        eng.profile_read()                      # discard the warm-up calls' timings
+        launches0 = eng.kernel_launches
+        sampler = ClockSampler(self.local_rank)
+        sampler.start()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        kernel_ms = []
+        for s in range(steps):
+            self.flush.zero_()                  # L2 flush between timed iterations, outside the step's events
+            evs[s][0].record()
+            self.step_dev()
+            evs[s][1].record()
+            kernel_ms.append(eng.profile_read())   # waits for the step's kernels (host-side), at every N alike
+        self.sync_all()
+        clocks = sampler.stop()
+        step_ms = [a.elapsed_time(b) for a, b in evs]          # per-step events: the flush is outside them, at every N
+        total = torch.tensor([sum(step_ms)], dtype=torch.float64, device=self.dev)
+        k1 = torch.tensor([sum(k[0] for k in kernel_ms if k) / steps], dtype=torch.float64, device=self.dev)
+        k1_all = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(total, op=dist.ReduceOp.MAX)
+            k1_list = [torch.zeros_like(k1) for _ in range(self.world)]
+            dist.all_gather(k1_list, k1)
+            k1_all = [float(x.item()) for x in k1_list]
+        total_ms = float(total.item())
+        return {"total_ms": total_ms, "ms_per_step": total_ms / steps, "step_ms_this_rank": step_ms,
+                "value": self.n * self.world * steps / (total_ms / 1000.0), "kernel_ms": float(k1.item()),
+                "kernel_ms_per_rank": k1_all, "launches": int(eng.kernel_launches - launches0), "clocks": clocks,
+                "steps": steps}
+
+    def local_results(self):
+        """Host copies of this rank's results of the LAST step (out, status) / (verdict,)."""
+        torch, n = self.torch, self.n
+        if self.gather == "nccl":
+            if self.kind == "verify":
+                return (self.res[:n].view(torch.int8).cpu().numpy(),)
+            return (self.res[: n * 2 * self.plen].cpu().numpy().reshape(n, 2 * self.plen),
+                    self.res[n * 2 * self.plen:].view(torch.int8).cpu().numpy())
+        if self.kind == "verify":
+            return (self.d_out.cpu().numpy(),)
+        return self.d_out.cpu().numpy().reshape(n, 2 * self.plen), self.d_status.cpu().numpy()
+
+    def ensure_last_step_used_set_a(self):
+        """The CPU baseline runs on scalar set A: make the last (untimed, if needed) step use it too."""
+        if self.kind != "verify" and self.last_scalars() is not self.inputs["scalars"]:
+            self.step_dev()
+            self.torch.cuda.synchronize()
+
+    def close_gather(self):
+        if self.pg is not None:
+            self.pg.close()
+            self.pg = None
+
+    def last_scalars(self):
+        return self.inputs["scalars_b"] if ((self.step_no - 1) & 1 and "scalars_b" in self.inputs) \
+            else self.inputs["scalars"]
+
+    def parity(self) -> bool:
+        """Oracle spot-check of what was just timed (first 256 items of this rank); whole-batch expectation for the
+        verification workloads."""
+        from common import oracle_smul, oracle_verify
+        res = self.local_results()
+        if self.kind == "verify":
+            i = self.inputs
+            want = oracle_verify(self.curve, i["sigs"][:256], i["pubkeys"][:256], sha256_rows(i["msgs"][:256]), i["hlen"])
+            return bool((res[0][:256] == want).all() and (res[0] == i["expected"]).all())
+        sc = self.last_scalars()
+        want, wst = oracle_smul(self.curve, sc[:256], self.inputs["points"][:256] if self.kind == "var" else None)
+        return bool((res[0][:256] == want).all() and (res[1][:256] == wst).all())
+
+    def gather_checks(self) -> dict:
+        """N > 1, rank 0: the gathered buffer must hold the other ranks' real results — checked against the oracle on
+        inputs regenerated from the LAST rank's seed, and (peer gather) byte for byte against a NCCL all_gather of every
+        rank's local results."""
+        import torch.distributed as dist
+        from common import oracle_smul
+        torch, n, world = self.torch, self.n, self.world
+        out = {}
+        if self.kind != "fixed":
+            return out
+        slot = n * 2 * self.plen + n
+        mine = torch.cat([self.d_out if self.gather != "nccl" else self.res[: n * 2 * self.plen],
+                          (self.d_status if self.gather != "nccl" else self.res[n * 2 * self.plen:].view(torch.int8))
+                          .view(torch.uint8)])
+        via_nccl = torch.empty(world * slot, dtype=torch.uint8, device=self.dev)
+        dist.all_gather_into_tensor(via_nccl, mine)            # outside every timed region
+        torch.cuda.synchronize()
+        if self.rank != 0:
+            return out
+        if self.pg is not None:
+            got = np.concatenate([self.eng.copy_to_host(self.pg.buffer_ptr(self.last_buf, r), slot) for r in range(world)])
+            out["gather_matches_nccl"] = bool((got == via_nccl.cpu().numpy()).all())
+        else:
+            got = self.gathered.cpu().numpy()
+        other = world - 1
+        tag = (4100 if ((self.step_no - 1) & 1) else 100) + other
+        osc = make_scalars(self.curve, n, tag)[:128]
+        want_o, _ = oracle_smul(self.curve, osc)
+        got_o = got.reshape(world, -1)[other][: 128 * 2 * self.plen].reshape(128, 2 * self.plen)
+        out["gather_parity_other_rank"] = bool((got_o == want_o).all())
+        return out
+
+    def measure_e2e(self, steps: int, n_items: int = None) -> dict:
+        """The host-pointer C-ABI call on page-locked host buffers: H2D + kernels + D2H inside the timed region."""
+        import libecc_b200
+        torch, eng, inputs = self.torch, self.eng, self.inputs
+        n = n_items or self.n
+        reps = (n + self.n - 1) // self.n
+        wc = os.environ.get("BENCH_WC_INPUTS", "0") == "1"
+
+        def pinned_from(a):
+            full = np.tile(a, (reps, 1))[:n] if reps > 1 else a
+            h = libecc_b200.pinned_empty(full.shape, full.dtype, write_combined=wc)
+            h[...] = full
+            return h
+        if self.kind == "verify":
+            hp = {k: pinned_from(inputs[k]) for k in ("sigs", "pubkeys", "msgs")}
+            off = libecc_b200.pinned_empty(n + 1, np.uint64)
+            off[...] = np.arange(n + 1, dtype=np.uint64) * MSG_LEN
+            h_verdict = libecc_b200.pinned_empty(n, np.int8)
+            call = lambda: eng.ecdsa_verify_msgs_batch_raw(VERIFY_HASH, hp["sigs"], hp["pubkeys"], hp["msgs"], off,
+                                                           verdict=h_verdict)
+        else:
+            hp = {"scalars": pinned_from(inputs["scalars"])}
+            if self.kind == "var":
+                hp["points"] = pinned_from(inputs["points"])
+            h_out = libecc_b200.pinned_empty((n, 2 * self.plen), np.uint8)
+            h_status = libecc_b200.pinned_empty(n, np.int8)
+            call = lambda: eng.prj_pt_mul_batch(hp["scalars"], hp.get("points"), out=h_out, status=h_status)
+        call()
+        self.sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            res = call()
+        e1.record()
+        self.sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        val = n * self.world * steps / (float(ms.item()) / 1000.0)
+        # the host-pointer results must equal the device leg's (which the oracle checks) on the first self.n items
+        if self.kind == "verify":
+            same = bool((np.asarray(res)[: self.n] == inputs["expected"]).all())
+        else:
+            from common import oracle_smul
+            want, wst = oracle_smul(self.curve, inputs["scalars"][:256], inputs["points"][:256] if self.kind == "var" else None)
+            same = bool((res[0][:256] == want).all() and (res[1][:256] == wst).all())
+            if reps > 1:                                  # tiled inputs: every tile must repeat the first one
+                same = same and bool((res[0][self.n: 2 * self.n] == res[0][: self.n]).all())
+        return {"value": val, "unit": self.unit, "h2d_bytes_per_step": n * self.in_item,
+                "d2h_bytes_per_step": n * self.out_item, "steps": steps, "items_per_gpu": n,
+                "host_buffers": "page-locked (eccb200_host_alloc)", "parity": same}
+
+    def roofline(self, kernel_ms: float, step_ms: float) -> dict:
+        from roofline import imad_peak_measured, work_per_item
+        n = self.n
+        peak = imad_peak_measured(self.local_rank)
+        work = work_per_item(self.workload, self.eng.comb_window)
+        achieved = n * work["imad32_per_item"] / (kernel_ms / 1000.0) / 1e12
+        executed = n * work["imad_executed_per_item"] / (kernel_ms / 1000.0) / 1e12
+        return {"bound": "int-mad", "kernel": work["kernel"], "achieved": achieved, "peak": peak["timad32_per_s"],
+                "unit": "T IMAD32/s", "frac": achieved / peak["timad32_per_s"],
+                "frac_executed_imad_wide": executed / peak["timad32_per_s"],
+                "frac_note": "frac charges the generic CIOS cost (SURVEY.md 8d: 4(2n^2+n) IMAD32 per product) to every "
+                             "product and so can exceed 1; frac_executed_imad_wide counts the IMAD.WIDE instructions "
+                             "the kernel really issues and is the figure to compare with ncu's fmaheavy pipe utilisation",
+                "traffic": ncu_dram_traffic(self.workload, self.batch_log2, self.eng.comb_window),
+                "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / step_ms,
+                "M_impl": work["M_impl"], "imad32_per_field_mul": work["imad32_per_mul"],
+                "ref_normalised_frac": n * work["imad32_ref_per_item"] / (kernel_ms / 1000.0) / 1e12 / peak["timad32_per_s"],
+                "peak_source": peak["how"],
+                "hbm_algorithmic_GBps": n * (self.in_item + self.out_item) / (kernel_ms / 1000.0) / 1e9}
+
+    def close(self):
+        if self.pg is not None:
+            self.pg.close()
+            self.pg = None
+        self.eng.close()
+
+
+def run_extra(name: str, batch_log2: int, steps: int, warmup: int, local_rank: int, with_cpu: bool) -> dict:
+    """Short measurement of another BASELINE.json config with the same code as the headline (N = 1)."""
+    t0 = time.perf_counter()
+    o = Ours(name, batch_log2, 0, 0, 1, local_rank, "none")
+    m = o.measure_device(steps, warmup)
+    parity = o.parity()
+    rl = o.roofline(m["kernel_ms"], m["ms_per_step"])
+    e2e = o.measure_e2e(max(2, min(steps, 3)))
+    res = {"metric": o.metric, "unit": o.unit, "value": m["value"], "ms_per_step": m["ms_per_step"], "steps": steps,
+           "warmup": warmup, "batch": 1 << batch_log2, "comb_window": o.eng.comb_window, "kernel": rl["kernel"],
+           "kernel_ms": m["kernel_ms"], "roofline_frac": rl["frac"], "frac_executed_imad_wide": rl["frac_executed_imad_wide"],
+           "M_impl": rl["M_impl"], "parity_spot_check": parity, "e2e": {k: e2e[k] for k in
+                                                                       ("value", "h2d_bytes_per_step", "d2h_bytes_per_step",
+                                                                        "steps", "parity")},
+           "clocks": m["clocks"]}
+    if with_cpu:
+        cb, cnt, outs = cpu_baseline(name, o.inputs, budget_s=4.0)
+        res["cpu_baseline"] = {k: cb[k] for k in ("value", "cores", "kind", "sample")}
+        o.ensure_last_step_used_set_a()
+        got = o.local_results()
+        if o.kind == "verify":
+            res["parity_on_cpu_prefix"] = bool((got[0][:cnt] == outs[0]).all())
+        else:
+            res["parity_on_cpu_prefix"] = bool((got[0][:cnt] == outs[0]).all() and (got[1][:cnt] == outs[1]).all())
+    o.close()
+    res["wall_s"] = round(time.perf_counter() - t0, 1)
+    return res
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -300,282 +705,156 @@ def main():
     ap.add_argument("--workload", default="secp256r1_fixed_base", choices=sorted(WORKLOADS))
     ap.add_argument("--batch-log2", type=int, default=20, help="items per GPU per step (2^k)")
     ap.add_argument("--comb-window", type=int, default=0)
+    ap.add_argument("--gather", default="peer-root", choices=["peer-root", "peer-all", "nccl"],
+                    help="N > 1: how the per-step results are gathered")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other BASELINE.json configs")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
-    curve, kind, metric, unit = WORKLOADS[args.workload]
-    n = 1 << args.batch_log2
-    config = {"workload": f"{args.workload}: 2^{args.batch_log2} items per GPU per step, seeded synthetic "
-                          f"(uniform scalars in [1,q-1] + 0.1% edge scalars)",
-              "curve": curve, "batch_per_gpu": n, "global_batch": n * world}
-
     if args.impl == "reference":
-        if rank != 0:
-            return
-        inputs = make_inputs(args.workload, n, 0, use_gpu=False) if kind != "var" else None
-        if kind == "var":
-            # no GPU on this arm: derive the points with the CPU oracle on the bounded sample only
-            from common import oracle_smul
-            inputs = {"scalars": make_inputs("secp256r1_fixed_base", n, 0)["scalars"]}
-            m = min(n, 1 << 12)
-            pts, _ = oracle_smul(curve, splitmix_bytes(m * 32, 300).reshape(m, 32) & 0x7F)
-            inputs["points"] = np.tile(pts, ((n + m - 1) // m, 1))[:n]
-        threads = nproc()
-        probe = min(n, 8 * threads)
-        t, k, _ = cpu_run(args.workload, inputs, 0, probe, threads)
-        # bounded sample: ~10 s of CPU work per step, less when many steps are asked for (whole run <= ~2-3 min)
-        step_s = max(1.0, min(10.0, 120.0 / max(1, args.steps)))
-        per_step = int(min(n, max(probe, (probe / t) * step_s)))
-        for _ in range(min(args.warmup, 1)):
-            cpu_run(args.workload, inputs, 0, min(per_step, 4 * probe), threads)
-        times = []
-        for s in range(args.steps):
-            lo = (s * per_step) % max(1, n - per_step + 1)
-            t, k, _ = cpu_run(args.workload, inputs, lo, per_step, threads)
-            times.append(t)
-        val = per_step * len(times) / sum(times)
-        line = {"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * sum(times) / len(times),
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-                "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": val, "unit": unit, "cores": threads, "kind": k,
-                                 "sample": f"{per_step} items per step (bounded sample of the 2^{args.batch_log2} batch)"},
-                "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        run_reference(args, rank)
         return
 
     import torch
     import torch.distributed as dist
-    import libecc_b200
-    from common import ALL_CURVES as CURVES
-    from libecc_b200.sharding import gather_results
 
     torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    _, plen, qlen = CURVES[curve]
-    inputs = make_inputs(args.workload, n, rank)
-    eng = libecc_b200.Engine(curve, device=local_rank, comb_window=args.comb_window)
-    stream = torch.cuda.current_stream().cuda_stream
-
-    # device-resident copies
-    d = {k: torch.from_numpy(v).to(dev) for k, v in inputs.items() if isinstance(v, np.ndarray) and k != "expected"}
-    if kind == "verify":
-        d_out = torch.empty(n, dtype=torch.int8, device=dev)
-        out_item = 1
-    else:
-        d_out = torch.empty(n * 2 * plen, dtype=torch.uint8, device=dev)
-        d_status = torch.empty(n, dtype=torch.int8, device=dev)
-        out_item = 2 * plen + 1
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    # N > 1: the results of step s are all-gathered (NCCL, one collective per step: the affine points and the status
-    # bytes share one buffer) on a side stream while step s+1 computes into the other of two result buffers.
-    out_rec = 1 if kind == "verify" else 2 * plen
-    res_bytes = n * out_rec + (0 if kind == "verify" else n)
-    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
-    if world > 1:
-        res = [torch.empty(res_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
-        gathered = [torch.empty(world * res_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
-        gather_done = [None, None]
-
-    def compute(buf_out, buf_status):
-        if kind == "verify":
-            eng.ecdsa_verify_batch_dev(d["sigs"].view(-1), d["pubkeys"].view(-1), d["digests"].view(-1),
-                                       inputs["hlen"], buf_out, stream)
-        else:
-            eng.prj_pt_mul_batch_dev(d["scalars"].view(-1), d["points"].view(-1) if kind == "var" else None,
-                                     buf_out, buf_status, stream)
-
-    step_no = [0]
-
-    def step_dev():
-        if world == 1:
-            compute(d_out, None if kind == "verify" else d_status)
-            return
-        b_ = step_no[0] & 1
-        step_no[0] += 1
-        if gather_done[b_] is not None:           # the gather that last read this buffer must be finished
-            torch.cuda.current_stream().wait_event(gather_done[b_])
-        r = res[b_]
-        compute(r[: n * out_rec].view(torch.int8) if kind == "verify" else r[: n * out_rec],
-                None if kind == "verify" else r[n * out_rec:].view(torch.int8))
-        ready = torch.cuda.Event()
-        ready.record()
-        comm_stream.wait_event(ready)
-        with torch.cuda.stream(comm_stream):      # the path's only exchange step
-            dist.all_gather_into_tensor(gathered[b_], r)
-            ev = torch.cuda.Event()
-            ev.record()
-        gather_done[b_] = ev
-
-    def join_comm():
-        if world > 1:
-            torch.cuda.current_stream().wait_stream(comm_stream)
-
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    eng.profile_enable(True)
-    for _ in range(args.warmup):
-        step_dev()
-        flush.zero_()
-    join_comm()
-    sync_all()
-    eng.profile_read()                      # discard the warm-up calls' timings
-    launches0 = eng.kernel_launches
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
-    t_begin.record()
-    for s in range(args.steps):
-        flush.zero_()                      # L2 flush between timed iterations
-        evs[s][0].record()
-        step_dev()
-        evs[s][1].record()
-        if world == 1:
-            kernel_ms.append(eng.profile_read())
-    join_comm()
-    t_end.record()
-    sync_all()
-    clocks = sampler.stop()
-    if world == 1:
-        step_ms = [a.elapsed_time(b) for a, b in evs]          # per-step events: the flush is outside them
-    else:
-        # steps overlap their gathers with the next step, so only the whole loop (flushes included) is meaningful
-        step_ms = [t_begin.elapsed_time(t_end) / args.steps] * args.steps
-        kernel_ms = [[x / args.steps for x in eng.profile_read()]]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
-    launches = eng.kernel_launches - launches0
-    value = n * world * args.steps / (total_ms / 1000.0)
-
-    # parity spot-check of what was just timed (first 256 items of this rank) against the oracle
-    from common import oracle_smul, oracle_verify
-    if world > 1:
-        last = res[(args.steps - 1) & 1]
-        if kind == "verify":
-            d_out = last[:n].view(torch.int8)
-        else:
-            d_out, d_status = last[: n * out_rec], last[n * out_rec:].view(torch.int8)
-    if kind == "verify":
-        got = d_out[:256].cpu().numpy()
-        want = oracle_verify(curve, inputs["sigs"][:256], inputs["pubkeys"][:256], inputs["digests"][:256],
-                             inputs["hlen"])
-        # the oracle on a prefix, and the by-construction expectation (valid unless corrupted) on the WHOLE batch
-        parity = bool((got == want).all() and (d_out.cpu().numpy() == inputs["expected"]).all())
-    else:
-        got = d_out[: 256 * 2 * plen].cpu().numpy().reshape(256, 2 * plen)
-        want, wst = oracle_smul(curve, inputs["scalars"][:256], inputs["points"][:256] if kind == "var" else None)
-        parity = bool((got == want).all() and (d_status[:256].cpu().numpy() == wst).all())
-
-    # N > 1: the gathered buffer on rank 0 must hold the other ranks' real results: regenerate the LAST rank's inputs
-    # from their seed and check its first items (slice 0) against the oracle
-    gather_parity = None
-    if world > 1 and rank == 0 and kind == "fixed":
-        other = world - 1
-        osc = make_inputs(args.workload, n, other)["scalars"][:128]
-        want_o, wst_o = oracle_smul(curve, osc)
-        got_o = gathered[(args.steps - 1) & 1].view(world, res_bytes)[other][: 128 * out_rec].cpu().numpy() \
-            .reshape(128, out_rec)
-        gather_parity = bool((got_o == want_o).all())
-
-    # ---- e2e: the host-pointer C-ABI call on host buffers (H2D + kernels + D2H inside the timed region)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    default_workload = args.workload == "secp256r1_fixed_base" and args.batch_log2 == 20
+    o = Ours(args.workload, args.batch_log2, args.comb_window, rank, world, local_rank, args.gather)
+    n = o.n
+    m = o.measure_device(args.steps, args.warmup)
+    parity = o.parity()
+    gchk = o.gather_checks() if world > 1 else {}
     e2e_steps = max(3, min(args.steps, 10))
-    # host buffers of the e2e leg are page-locked (eccb200_host_alloc), as a caller that cares about throughput would do
-    hp = {}
-    for k_, v_ in inputs.items():
-        if isinstance(v_, np.ndarray) and k_ != "expected":
-            hp[k_] = libecc_b200.pinned_empty(v_.shape, v_.dtype,
-                                              write_combined=os.environ.get("BENCH_WC_INPUTS", "0") == "1")
-            hp[k_][...] = v_
-    if kind == "verify":
-        h_verdict = libecc_b200.pinned_empty(n, np.int8)
-    else:
-        h_out = libecc_b200.pinned_empty((n, 2 * plen), np.uint8)
-        h_status = libecc_b200.pinned_empty(n, np.int8)
+    e2e = o.measure_e2e(e2e_steps)
 
-    def step_host():
-        if kind == "verify":
-            return eng.ecdsa_verify_batch(hp["sigs"], hp["pubkeys"], hp["digests"], inputs["hlen"], verdict=h_verdict)
-        return eng.prj_pt_mul_batch(hp["scalars"], hp.get("points"), out=h_out, status=h_status)
-    step_host()
-    sync_all()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(e2e_steps):
-        res = step_host()
-    e1.record()
-    sync_all()
-    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    extra = {}
+    if world > 1 and default_workload and not args.no_extra and o.kind == "fixed":
+        # config 5 as written (2^24 scalars over 8 GPUs = 2^21 per GPU) with the same gather, same protocol
+        per_gpu_log2 = 24 - max(0, (world - 1).bit_length())
+        if 20 < per_gpu_log2 <= 22:
+            o5 = Ours(args.workload, per_gpu_log2, o.eng.comb_window, rank, world, local_rank, args.gather)
+            m5 = o5.measure_device(5, 2)
+            ok5 = o5.parity()
+            g5 = o5.gather_checks()
+            o5.close_gather()
+            extra["config5_2^24_total"] = dict({"value": m5["value"], "ms_per_step": m5["ms_per_step"], "steps": 5,
+                                                "batch_per_gpu": 1 << per_gpu_log2, "global_batch": world << per_gpu_log2,
+                                                "kernel_ms_per_rank": m5["kernel_ms_per_rank"], "parity_spot_check": ok5}, **g5)
+            o5.close()
+
     if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_val = n * world * e2e_steps / (float(e2e_ms.item()) / 1000.0)
-    if kind == "verify":
-        e2e_parity = bool((np.asarray(res) == d_out.cpu().numpy()).all())
-    else:
-        e2e_parity = bool((res[0] == d_out.cpu().numpy().reshape(n, 2 * plen)).all())
-    in_item = {"fixed": qlen, "var": qlen + 2 * plen, "verify": 2 * qlen + 2 * plen + inputs.get("hlen", 0)}[kind]
-
+        o.close_gather()            # collective: every rank unmaps its peers' regions before anybody frees its own
     if rank != 0:
+        o.close()
         if world > 1:
+            dist.barrier()          # rank 0 may still be running its single-process multi-device leg
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (integer multiply-add bound)
-    from roofline import imad_peak_measured, work_per_item
-    k0 = statistics.mean(k[0] for k in kernel_ms if k)
-    peak = imad_peak_measured(local_rank)
-    work = work_per_item(args.workload, eng.comb_window)
-    achieved = n * work["imad32_per_item"] / (k0 / 1000.0) / 1e12
-    roofline = {"bound": "int-mad", "kernel": work["kernel"], "achieved": achieved, "peak": peak["timad32_per_s"],
-                "unit": "T IMAD32/s", "frac": achieved / peak["timad32_per_s"],
-                "traffic": ncu_dram_traffic(args.workload, args.batch_log2, eng.comb_window),
-                "kernel_ms": k0, "kernel_share_of_step": k0 / (sum(step_ms) / len(step_ms)),
-                "M_impl": work["M_impl"], "imad32_per_field_mul": work["imad32_per_mul"],
-                "frac_executed_imad_wide": n * work["imad_executed_per_item"] / (k0 / 1000.0) / 1e12
-                / peak["timad32_per_s"],
-                "ref_normalised_frac": n * work["imad32_ref_per_item"] / (k0 / 1000.0) / 1e12 / peak["timad32_per_s"],
-                "peak_source": peak["how"],
-                "hbm_algorithmic_GBps": n * (in_item + out_item) / (k0 / 1000.0) / 1e9}
-
-    line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+    roofline = o.roofline(m["kernel_ms"], m["ms_per_step"])
+    gather_desc = {"none": "none",
+                   "peer-root": "fused into the normalisation kernel: every rank's K4 stores its results straight into rank "
+                                "0's gathered buffer over NVLink (CUDA-IPC peer memory) and signals arrival; rank 0's step "
+                                "ends when all ranks' results have landed; double-buffered with acknowledgements; no "
+                                "collective kernel",
+                   "peer-all": "as peer-root, but every rank receives every rank's results (all-gather semantics)",
+                   "nccl": "one nccl all_gather per step on the compute stream, inside the step's events"}[o.gather]
+    line = {"metric": o.metric, "value": m["value"], "unit": o.unit, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": dict(config, l2="256 MiB buffer rewritten between timed iterations",
-                           comb_window=eng.comb_window, result_gather=("one nccl all_gather per step on a side stream, overlapped with the "
-                                          "next step's kernels (double-buffered results); timed over the whole "
-                                          "loop, L2 flushes included" if world > 1 else "none")),
-            "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": {"value": e2e_val, "unit": unit, "h2d_bytes_per_step": n * in_item,
-                    "d2h_bytes_per_step": n * out_item, "steps": e2e_steps,
-                    "host_buffers": "page-locked (eccb200_host_alloc)", "same_results_as_device_leg": e2e_parity},
+            "config": dict(workload_config(args.workload, args.batch_log2, world),
+                           l2="256 MiB buffer rewritten between timed iterations (outside the per-step events, at every N)",
+                           comb_window=o.eng.comb_window, result_gather=gather_desc,
+                           timing="sum of per-step CUDA-event intervals on the compute stream, max over ranks"),
+            "clocks": m["clocks"], "gpu_launches": m["launches"],
+            "e2e": dict(e2e, same_results_as_device_leg=e2e["parity"]),
             "roofline": roofline, "parity_spot_check": parity}
-    if gather_parity is not None:
-        line["gather_parity_other_rank"] = gather_parity
+    line.update(gchk)
+    if m["kernel_ms_per_rank"]:
+        line["kernel_ms_per_rank"] = m["kernel_ms_per_rank"]
     if world == 1 and not args.no_cpu_baseline:
-        cb, cnt, outs = cpu_baseline(args.workload, inputs)
+        cb, cnt, outs = cpu_baseline(args.workload, o.inputs)
         line["cpu_baseline"] = cb
-        # the timed GPU results must equal the reference on the CPU-timed prefix
-        if kind != "verify":
-            gpu_out = d_out[: cnt * 2 * plen].cpu().numpy().reshape(cnt, 2 * plen)
-            line["parity_on_cpu_prefix"] = bool((gpu_out == outs[0]).all() and
-                                                (d_status[:cnt].cpu().numpy() == outs[1]).all())
+        got = o.local_results()
+        # the timed GPU results must equal the reference on the CPU-timed prefix (same scalar set as the last step)
+        if o.kind == "verify":
+            line["parity_on_cpu_prefix"] = bool((got[0][:cnt] == outs[0]).all())
         else:
-            line["parity_on_cpu_prefix"] = bool((d_out[:cnt].cpu().numpy() == outs[0]).all())
+            o.ensure_last_step_used_set_a()
+            got = o.local_results()
+            line["parity_on_cpu_prefix"] = bool((got[0][:cnt] == outs[0]).all() and (got[1][:cnt] == outs[1]).all())
+
+    if default_workload and not args.no_extra:
+        if world == 1:
+            # end-to-end at larger batches (fill / drain amortised): same call, inputs tiled
+            for lg in (22, 24):
+                try:
+                    r = o.measure_e2e(3, n_items=1 << lg)
+                    extra[f"e2e_2^{lg}"] = {k: r[k] for k in ("value", "items_per_gpu", "steps", "parity")}
+                except Exception as exc:       # noqa: BLE001 — an extra must not take the headline down
+                    extra[f"e2e_2^{lg}"] = {"error": str(exc)[:200]}
+            o.close()
+            for name, lg, st, wu in (("frp256v1_ecdsa_verify", 20, 3, 1), ("secp384r1_fixed_base", 20, 5, 2),
+                                     ("secp256r1_variable_base", 20, 3, 1)):
+                try:
+                    extra[name] = run_extra(name, lg, st, wu, local_rank, with_cpu=not args.no_cpu_baseline)
+                except Exception as exc:       # noqa: BLE001
+                    extra[name] = {"error": str(exc)[:300]}
+        else:
+            o.close()
+            # the in-process multi-device C ABI (eccb200_multi_*): ONE host call shards 2^24 scalars over all GPUs of
+            # the box, each GPU DMAs its shard's results straight into the caller's pinned output
+            try:
+                extra["multi_device_c_abi"] = run_multi_abi(args.workload, world, 24)
+            except Exception as exc:           # noqa: BLE001
+                extra["multi_device_c_abi"] = {"error": str(exc)[:300]}
+    else:
+        o.close()
+    if extra:
+        line["extra"] = extra
     print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def run_multi_abi(workload: str, n_dev: int, total_log2: int) -> dict:
+    import libecc_b200
+    from common import ALL_CURVES as CURVES, oracle_smul
+    curve, kind, metric, unit = WORKLOADS[workload]
+    _, plen, qlen = CURVES[curve]
+    n = 1 << total_log2
+    base = make_scalars(curve, 1 << 20, 9100)
+    reps = n >> 20
+    h_sc = libecc_b200.pinned_empty((n, qlen), np.uint8)
+    h_sc[...] = np.tile(base, (reps, 1))
+    h_out = libecc_b200.pinned_empty((n, 2 * plen), np.uint8)
+    h_st = libecc_b200.pinned_empty(n, np.int8)
+    me = libecc_b200.MultiEngine(curve, devices=list(range(n_dev)), comb_window=DEFAULT_COMB.get(curve, 0))
+    me.prj_pt_mul_batch(h_sc, None, out=h_out, status=h_st)          # warm-up (stage buffers, first-touch)
+    times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        me.prj_pt_mul_batch(h_sc, None, out=h_out, status=h_st)
+        times.append(time.perf_counter() - t0)
+    want, wst = oracle_smul(curve, base[:128])
+    ok = True
+    for g in range(n_dev):                                            # first items of every device's shard
+        lo = n * g // n_dev
+        w, ws = oracle_smul(curve, h_sc[lo:lo + 64])
+        ok = ok and bool((h_out[lo:lo + 64] == w).all() and (h_st[lo:lo + 64] == ws).all())
+    me.close()
+    best = min(times)
+    return {"call": "eccb200_multi_prj_pt_mul_batch", "devices": n_dev, "items": n, "e2e_value": n / best, "unit": unit,
+            "seconds_best_of_3": best, "seconds_all": times, "h2d_bytes": n * qlen, "d2h_bytes": n * (2 * plen + 1),
+            "timing": "host wall clock around the blocking call (one process, one host thread per GPU)",
+            "parity_first_items_of_every_shard": ok}
 
 
 if __name__ == "__main__":

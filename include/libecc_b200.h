@@ -51,7 +51,8 @@ typedef struct eccb200_ctx eccb200_ctx;
  * Create an engine context for one curve on one device: uploads the curve constants and builds the fixed-base
  * comb table T[i][d] = d * 2^(w*i) * G on the GPU.  Replaces import_params (src/curves/ec_params.c:24) as the
  * place where per-curve state is derived.  comb_window: bits per fixed-base window: 4..16, or an even value in
- * 18..24 (table of ceil(qbits/w) * 2^w * 2*plen bytes, built from a half-width table); 0 = default.
+ * 18..26 (table of ceil(qbits/w) * 2^w * 2*plen bytes, built from a half-width table: 3.2 GiB at 22 bits and
+ * 40 GiB at 26 bits for a 256-bit curve); 0 = default.
  */
 int eccb200_ctx_create(eccb200_ctx **ctx, int curve_id, int device, int comb_window);
 void eccb200_ctx_destroy(eccb200_ctx *ctx);
@@ -76,9 +77,64 @@ const char *eccb200_curve_name(int curve_id);
 int eccb200_prj_pt_mul_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *scalars, const uint8_t *points,
 			     uint8_t *out, int8_t *status);
 
-/* Same, on device-resident buffers, enqueued on `stream` (a cudaStream_t; NULL = default stream); asynchronous. */
+/*
+ * Same, on device-resident buffers, enqueued on `stream` (a cudaStream_t; NULL = default stream); asynchronous.
+ * Rules for every *_dev entry point:
+ *  - a context is used by one host thread at a time; its *_dev calls may name different streams, but they share one
+ *    set of scratch buffers, so the library chains them on the device (each call's kernels wait for the previous
+ *    call's) — use one context per stream to overlap calls;
+ *  - on the 256-, 384- and 512-bit curves the scalar / point / signature / key / output buffers must be 16-byte
+ *    aligned (the kernels use 16-byte vector accesses); a misaligned pointer is refused with -1, never dereferenced.
+ */
 int eccb200_prj_pt_mul_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_scalars, const uint8_t *d_points,
 				 uint8_t *d_out, int8_t *d_status, void *stream);
+
+/*
+ * Multi-GPU, one process per GPU (SURVEY.md §8e "final result gather"): the normalisation kernel of a batch stores
+ * every result not only into d_out / d_status but also straight into up to 8 destination buffers on PEER GPUs —
+ * buffers allocated with eccb200_ipc_alloc in the peer's process and mapped here with eccb200_ipc_open — so the
+ * gather travels over NVLink as ordinary stores of the kernel that produces the bytes, and no collective kernel
+ * competes with the arithmetic for the SMs.  dst_out[j] / dst_status[j] point at THIS rank's slot of destination j
+ * (same [n][2*plen] / [n] layout as d_out / d_status).  When the last thread block has stored its results the kernel
+ * publishes flag_value to *dst_flag[j] (system-scope release); the destination waits for it with eccb200_flag_wait.
+ * Flow control: if wait_count > 0 the normalisation kernel (not the scalar multiplication before it) first waits
+ * until d_wait_flags[i] >= wait_value for all i < wait_count — the destinations' "buffer released" acknowledgements
+ * (eccb200_flag_signal), flags in this GPU's memory.
+ * n must be > 0.  Flags are 32-bit counters compared modulo 2^32.
+ */
+int eccb200_prj_pt_mul_batch_dev_gather(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_scalars,
+					const uint8_t *d_points, uint8_t *d_out, int8_t *d_status, int n_dst,
+					uint8_t *const *dst_out, int8_t *const *dst_status, uint32_t *const *dst_flag,
+					uint32_t flag_value, const uint32_t *d_wait_flags, int wait_count,
+					uint32_t wait_value, void *stream);
+/* Device memory that other processes on the box can map: cudaMalloc + cudaIpcGetMemHandle (zero-filled).  The
+ * 64-byte handle is passed to the peers by any means (bench.py: torch.distributed); they map it with
+ * eccb200_ipc_open (peer access over NVLink is enabled on first use) and unmap it with eccb200_ipc_close. */
+int eccb200_ipc_alloc(eccb200_ctx *ctx, size_t bytes, void **d_ptr, uint8_t handle[64]);
+int eccb200_ipc_open(eccb200_ctx *ctx, const uint8_t handle[64], void **d_ptr);
+int eccb200_ipc_close(eccb200_ctx *ctx, void *d_ptr);
+int eccb200_ipc_free(eccb200_ctx *ctx, void *d_ptr);
+/* Stream-ordered flag operations of the gather: wait until d_flags[i] >= value for all i < count (flags in this
+ * GPU's memory); publish value to count (<= 8) flags, typically peer-mapped, after everything enqueued before. */
+int eccb200_flag_wait(eccb200_ctx *ctx, const uint32_t *d_flags, int count, uint32_t value, void *stream);
+int eccb200_flag_signal(eccb200_ctx *ctx, uint32_t *const *d_flags, int count, uint32_t value, void *stream);
+
+/*
+ * Multi-GPU, ONE process (SURVEY.md §8b "multi-GPU fan-out is internal"): a context set over several devices
+ * (devices == NULL or n_devices <= 0: every visible device); the batch calls below shard [0, n) into contiguous
+ * ranges, one per device, run each shard through that device's host-pointer pipeline on its own host thread, and
+ * every device DMAs its results straight into the caller's arrays — there is no gather step.  Same argument
+ * meaning, status codes and error behaviour as the single-device calls; n is 64-bit.
+ */
+typedef struct eccb200_multi eccb200_multi;
+int eccb200_multi_create(eccb200_multi **m, int curve_id, const int *devices, int n_devices, int comb_window);
+void eccb200_multi_destroy(eccb200_multi *m);
+int eccb200_multi_device_count(const eccb200_multi *m);
+eccb200_ctx *eccb200_multi_ctx(eccb200_multi *m, int index); /* the per-device context (owned by m) */
+int eccb200_multi_prj_pt_mul_batch(eccb200_multi *m, uint64_t n, const uint8_t *scalars, const uint8_t *points,
+				   uint8_t *out, int8_t *status);
+int eccb200_multi_ecdsa_verify_batch(eccb200_multi *m, uint64_t n, const uint8_t *sigs, const uint8_t *pubkeys,
+				     const uint8_t *digests, uint32_t hlen, int8_t *verdict);
 
 /*
  * Batched prj_pt_unique + prj_pt_export_to_aff_buf (src/curves/prj_pt.c:241, :600) on the reference's homogeneous
@@ -143,6 +199,14 @@ int eccb200_hash_batch(eccb200_ctx *ctx, int hash_type, uint32_t n, const uint8_
 int eccb200_ecdsa_verify_msgs_batch(eccb200_ctx *ctx, int hash_type, uint32_t n, const uint8_t *sigs,
 				    const uint8_t *pubkeys, const uint8_t *msgs, const uint64_t *offsets,
 				    int8_t *verdict);
+
+/* Same on device-resident buffers (d_offsets: n + 1 entries starting at 0, non-decreasing; d_digests: [n][digest_size]
+ * scratch), hash kernel + verification kernel enqueued on `stream`; asynchronous. */
+int eccb200_ecdsa_verify_msgs_batch_dev(eccb200_ctx *ctx, int hash_type, uint32_t n, const uint8_t *d_sigs,
+					const uint8_t *d_pubkeys, const uint8_t *d_msgs, const uint64_t *d_offsets,
+					uint8_t *d_digests, int8_t *d_verdict, void *stream);
+/* cudaMemcpy device -> host (for callers that do not link the CUDA runtime). */
+int eccb200_copy_to_host(eccb200_ctx *ctx, void *host_dst, const void *d_src, size_t bytes);
 
 /*
  * ECFSDSA verification (the Schnorr-type scheme for which the reference ships a verify_batch,

@@ -31,6 +31,11 @@ ABI_SYMBOLS = [
     "eccb200_structured_pub_key_import_batch", "eccb200_structured_pub_key_export_batch",
     "eccb200_structured_key_pair_batch", "eccb200_ecdsa_verify_structured_batch", "eccb200_ecdsa_sign_structured_batch",
     "eccb200_ecfsdsa_verify_batch", "eccb200_ecfsdsa_verify_batch_dev",
+    "eccb200_prj_pt_mul_batch_dev_gather", "eccb200_ipc_alloc", "eccb200_ipc_open", "eccb200_ipc_close",
+    "eccb200_ipc_free", "eccb200_flag_wait", "eccb200_flag_signal",
+    "eccb200_multi_create", "eccb200_multi_destroy", "eccb200_multi_device_count", "eccb200_multi_ctx",
+    "eccb200_multi_prj_pt_mul_batch", "eccb200_multi_ecdsa_verify_batch",
+    "eccb200_ecdsa_verify_msgs_batch_dev", "eccb200_copy_to_host",
 ]
 
 _lib = None
@@ -82,6 +87,25 @@ def load_library() -> ctypes.CDLL:
                                                         u8p, u8p, u32, u8p, i8p]
     lib.eccb200_ecfsdsa_verify_batch.argtypes = [ctypes.c_void_p, u32, u8p, u8p, u8p, u32, i8p]
     lib.eccb200_ecfsdsa_verify_batch_dev.argtypes = [ctypes.c_void_p, u32, u8p, u8p, u8p, u32, i8p, ctypes.c_void_p]
+    vp, u64 = ctypes.c_void_p, ctypes.c_uint64
+    lib.eccb200_prj_pt_mul_batch_dev_gather.argtypes = [vp, u32, u8p, u8p, u8p, i8p, ctypes.c_int, vp, vp, vp, u32,
+                                                        vp, ctypes.c_int, u32, vp]
+    lib.eccb200_ipc_alloc.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(vp), vp]
+    lib.eccb200_ipc_open.argtypes = [vp, vp, ctypes.POINTER(vp)]
+    lib.eccb200_ipc_close.argtypes = [vp, vp]
+    lib.eccb200_ipc_free.argtypes = [vp, vp]
+    lib.eccb200_flag_wait.argtypes = [vp, vp, ctypes.c_int, u32, vp]
+    lib.eccb200_flag_signal.argtypes = [vp, vp, ctypes.c_int, u32, vp]
+    lib.eccb200_multi_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int, vp, ctypes.c_int, ctypes.c_int]
+    lib.eccb200_multi_destroy.argtypes = [vp]
+    lib.eccb200_multi_destroy.restype = None
+    lib.eccb200_multi_device_count.argtypes = [vp]
+    lib.eccb200_multi_ctx.argtypes = [vp, ctypes.c_int]
+    lib.eccb200_multi_ctx.restype = vp
+    lib.eccb200_multi_prj_pt_mul_batch.argtypes = [vp, u64, u8p, u8p, u8p, i8p]
+    lib.eccb200_multi_ecdsa_verify_batch.argtypes = [vp, u64, u8p, u8p, u8p, u32, i8p]
+    lib.eccb200_ecdsa_verify_msgs_batch_dev.argtypes = [vp, ctypes.c_int, u32, u8p, u8p, u8p, vp, u8p, i8p, vp]
+    lib.eccb200_copy_to_host.argtypes = [vp, vp, vp, ctypes.c_size_t]
     lib.eccb200_host_alloc.argtypes = [ctypes.c_size_t]
     lib.eccb200_host_alloc.restype = ctypes.c_void_p
     lib.eccb200_host_alloc_input.argtypes = [ctypes.c_size_t]
@@ -255,6 +279,43 @@ class Engine:
                                                 off.ctypes.data, out.ctypes.data), "eccb200_hash_batch")
         return out
 
+    def hash_batch_raw(self, hash_name: str, blob, offsets) -> np.ndarray:
+        """Messages already packed: blob uint8, offsets uint64[n + 1]."""
+        blob = _as_u8(blob)
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = off.size - 1
+        out = np.zeros((n, self.HASH_LEN[hash_name]), dtype=np.uint8)
+        self._check(self.lib.eccb200_hash_batch(self._h, self.HASH_IDS[hash_name], n, blob.ctypes.data,
+                                                off.ctypes.data, out.ctypes.data), "eccb200_hash_batch")
+        return out
+
+    def ecdsa_verify_msgs_batch_raw(self, hash_name: str, sigs, pubkeys, blob, offsets, verdict=None) -> np.ndarray:
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = off.size - 1
+        sg = _as_u8(sigs, n * 2 * self.qlen)
+        pk = _as_u8(pubkeys, n * 2 * self.plen)
+        blob = _as_u8(blob)
+        if verdict is None:
+            verdict = np.zeros(n, dtype=np.int8)
+        self._check(self.lib.eccb200_ecdsa_verify_msgs_batch(self._h, self.HASH_IDS[hash_name], n, sg.ctypes.data,
+                                                             pk.ctypes.data, blob.ctypes.data, off.ctypes.data,
+                                                             verdict.ctypes.data), "eccb200_ecdsa_verify_msgs_batch")
+        return verdict
+
+    def ecdsa_verify_msgs_batch_dev(self, hash_name: str, d_sigs, d_pubkeys, d_msgs, d_offsets, d_digests, d_verdict,
+                                    stream_handle: int = 0):
+        n = d_sigs.numel() // (2 * self.qlen)
+        self._check(self.lib.eccb200_ecdsa_verify_msgs_batch_dev(
+            self._h, self.HASH_IDS[hash_name], n, d_sigs.data_ptr(), d_pubkeys.data_ptr(), d_msgs.data_ptr(),
+            d_offsets.data_ptr(), d_digests.data_ptr(), d_verdict.data_ptr(), ctypes.c_void_p(stream_handle)),
+            "eccb200_ecdsa_verify_msgs_batch_dev")
+
+    def copy_to_host(self, d_ptr: int, nbytes: int) -> np.ndarray:
+        out = np.empty(nbytes, dtype=np.uint8)
+        self._check(self.lib.eccb200_copy_to_host(self._h, out.ctypes.data, ctypes.c_void_p(d_ptr), nbytes),
+                    "eccb200_copy_to_host")
+        return out
+
     def ecdsa_verify_msgs_batch(self, hash_name: str, sigs, pubkeys, msgs) -> np.ndarray:
         n = len(msgs)
         sg = _as_u8(sigs, n * 2 * self.qlen)
@@ -379,8 +440,102 @@ class Engine:
             self._h, n, d_scalars.data_ptr(), d_points.data_ptr() if d_points is not None else None,
             d_out.data_ptr(), d_status.data_ptr(), ctypes.c_void_p(stream_handle)), "eccb200_prj_pt_mul_batch_dev")
 
+    def prj_pt_mul_batch_dev_gather(self, n: int, p_scalars: int, p_points, p_out: int, p_status: int, dst_out, dst_status,
+                                    dst_flag, flag_value: int, p_wait_flags, wait_count: int, wait_value: int,
+                                    stream_handle: int = 0):
+        """Raw-pointer form (ints): see eccb200_prj_pt_mul_batch_dev_gather in include/libecc_b200.h."""
+        k = len(dst_out)
+        arr = lambda xs: (ctypes.c_void_p * max(k, 1))(*[ctypes.c_void_p(x) for x in xs])
+        a_out, a_st, a_fl = arr(dst_out), arr(dst_status), arr(dst_flag)
+        self._check(self.lib.eccb200_prj_pt_mul_batch_dev_gather(
+            self._h, n, p_scalars, p_points, p_out, p_status, k, a_out, a_st, a_fl, flag_value & 0xFFFFFFFF,
+            p_wait_flags, wait_count, wait_value & 0xFFFFFFFF, ctypes.c_void_p(stream_handle)),
+            "eccb200_prj_pt_mul_batch_dev_gather")
+
+    def ipc_alloc(self, nbytes: int):
+        p = ctypes.c_void_p()
+        h = (ctypes.c_uint8 * 64)()
+        self._check(self.lib.eccb200_ipc_alloc(self._h, nbytes, ctypes.byref(p), h), "eccb200_ipc_alloc")
+        return int(p.value), bytes(h)
+
+    def ipc_open(self, handle: bytes) -> int:
+        p = ctypes.c_void_p()
+        h = (ctypes.c_uint8 * 64)(*handle)
+        self._check(self.lib.eccb200_ipc_open(self._h, h, ctypes.byref(p)), "eccb200_ipc_open")
+        return int(p.value)
+
+    def ipc_close(self, ptr: int):
+        self._check(self.lib.eccb200_ipc_close(self._h, ctypes.c_void_p(ptr)), "eccb200_ipc_close")
+
+    def ipc_free(self, ptr: int):
+        self._check(self.lib.eccb200_ipc_free(self._h, ctypes.c_void_p(ptr)), "eccb200_ipc_free")
+
+    def flag_wait(self, p_flags: int, count: int, value: int, stream_handle: int = 0):
+        self._check(self.lib.eccb200_flag_wait(self._h, ctypes.c_void_p(p_flags), count, value & 0xFFFFFFFF,
+                                               ctypes.c_void_p(stream_handle)), "eccb200_flag_wait")
+
+    def flag_signal(self, flag_ptrs, value: int, stream_handle: int = 0):
+        a = (ctypes.c_void_p * len(flag_ptrs))(*[ctypes.c_void_p(x) for x in flag_ptrs])
+        self._check(self.lib.eccb200_flag_signal(self._h, a, len(flag_ptrs), value & 0xFFFFFFFF,
+                                                 ctypes.c_void_p(stream_handle)), "eccb200_flag_signal")
+
     def ecdsa_verify_batch_dev(self, d_sigs, d_pubkeys, d_digests, hlen: int, d_verdict, stream_handle: int = 0):
         n = d_sigs.numel() // (2 * self.qlen)
         self._check(self.lib.eccb200_ecdsa_verify_batch_dev(
             self._h, n, d_sigs.data_ptr(), d_pubkeys.data_ptr(), d_digests.data_ptr(), hlen,
             d_verdict.data_ptr(), ctypes.c_void_p(stream_handle)), "eccb200_ecdsa_verify_batch_dev")
+
+
+class MultiEngine:
+    """One curve on several GPUs of ONE process (eccb200_multi): host-pointer batches are sharded internally."""
+
+    def __init__(self, curve: str, devices=None, comb_window: int = 0):
+        self.lib = load_library()
+        self.curve = curve
+        self.plen, self.qlen = curve_sizes(curve)
+        h = ctypes.c_void_p()
+        arr = (ctypes.c_int * len(devices))(*devices) if devices else None
+        if self.lib.eccb200_multi_create(ctypes.byref(h), CURVE_IDS[curve], arr, len(devices) if devices else 0,
+                                         comb_window):
+            raise EccB200Error("eccb200_multi_create: " + self.lib.eccb200_last_error().decode())
+        self._h = h
+
+    @property
+    def device_count(self) -> int:
+        return self.lib.eccb200_multi_device_count(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.eccb200_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def prj_pt_mul_batch(self, scalars, points=None, out=None, status=None):
+        sc = _as_u8(scalars)
+        n = sc.size // self.qlen
+        pt = _as_u8(points, n * 2 * self.plen) if points is not None else None
+        if out is None:
+            out = np.zeros((n, 2 * self.plen), dtype=np.uint8)
+        if status is None:
+            status = np.zeros(n, dtype=np.int8)
+        if self.lib.eccb200_multi_prj_pt_mul_batch(self._h, n, sc.ctypes.data, pt.ctypes.data if pt is not None else None,
+                                                   out.ctypes.data, status.ctypes.data):
+            raise EccB200Error("eccb200_multi_prj_pt_mul_batch: " + self.lib.eccb200_last_error().decode())
+        return out, status
+
+    def ecdsa_verify_batch(self, sigs, pubkeys, digests, hlen: int, verdict=None):
+        sg = _as_u8(sigs)
+        n = sg.size // (2 * self.qlen)
+        pk = _as_u8(pubkeys, n * 2 * self.plen)
+        dg = _as_u8(digests, n * hlen)
+        if verdict is None:
+            verdict = np.zeros(n, dtype=np.int8)
+        if self.lib.eccb200_multi_ecdsa_verify_batch(self._h, n, sg.ctypes.data, pk.ctypes.data, dg.ctypes.data, hlen,
+                                                     verdict.ctypes.data):
+            raise EccB200Error("eccb200_multi_ecdsa_verify_batch: " + self.lib.eccb200_last_error().decode())
+        return verdict

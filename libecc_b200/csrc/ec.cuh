@@ -280,6 +280,83 @@ template <class C> struct EC {
 		r.Z = p.Z;
 		F::neg(r.Y, p.Y);
 	}
+
+	/*
+	 * Extended Jacobian ("XYZZ") accumulator of the fixed-base comb: x = X/ZZ, y = Y/ZZZ with ZZ^3 == ZZZ^2;
+	 * ZZ == 0 <=> point at infinity.  Mixed addition madd-2008-s: 8M + 2S (one squaring less than the Jacobian
+	 * mixed addition, because Z^2 and Z^3 are carried instead of recomputed).  Exceptional cases as in add_mixed.
+	 */
+	struct XZ {
+		E X, Y, ZZ, ZZZ;
+	};
+	static ECC_HD void xz_set_inf(XZ &p)
+	{
+		F::set_one(p.X);
+		F::set_one(p.Y);
+		F::set_zero(p.ZZ);
+		F::set_zero(p.ZZZ);
+	}
+	static ECC_HD void xz_from_affine(XZ &p, const A &a)
+	{
+		p.X = a.x;
+		p.Y = a.y;
+		F::set_one(p.ZZ);
+		F::set_one(p.ZZZ);
+	}
+	/* rarely taken P == Q branch of xz_add_mixed: 2Q through the Jacobian doubling, then ZZ = Z^2, ZZZ = Z^3 */
+	static ECC_NOINLINE void xz_dbl_affine_slow(XZ &r, const A &q)
+	{
+		J qq, d;
+		from_affine(qq, q);
+		dbl(d, qq);
+		r.X = d.X;
+		r.Y = d.Y;
+		F::sqr(r.ZZ, d.Z);
+		F::mul(r.ZZZ, r.ZZ, d.Z);
+	}
+	static ECC_HD void xz_add_mixed(XZ &r, const XZ &p, const A &q)
+	{
+		E u2, s2, pp_, rr, ppp, qv, t;
+		if (F::is_zero(p.ZZ)) { /* first non-zero window of the comb */
+			xz_from_affine(r, q);
+			return;
+		}
+		F::mul(u2, q.x, p.ZZ);
+		F::mul(s2, q.y, p.ZZZ);
+		F::sub(pp_, u2, p.X); /* P */
+		F::sub(rr, s2, p.Y);  /* R */
+		if (F::is_zero(pp_)) {
+			if (F::is_zero(rr)) xz_dbl_affine_slow(r, q);
+			else xz_set_inf(r);
+			return;
+		}
+		E x3, y3;
+		F::sqr(t, pp_);        /* PP */
+		F::mul(ppp, pp_, t);   /* PPP */
+		F::mul(qv, p.X, t);    /* Q = X1 * PP */
+		E zz3;
+		F::mul(zz3, p.ZZ, t);  /* ZZ3 = ZZ1 * PP */
+		F::sqr(x3, rr);
+		F::sub(x3, x3, ppp);
+		F::sub(x3, x3, qv);
+		F::sub(x3, x3, qv);    /* X3 = R^2 - PPP - 2Q */
+		F::sub(t, qv, x3);
+		F::mul(y3, rr, t);
+		F::mul(t, p.Y, ppp);
+		F::sub(y3, y3, t);     /* Y3 = R (Q - X3) - Y1 PPP */
+		F::mul(t, p.ZZZ, ppp); /* ZZZ3 = ZZZ1 * PPP */
+		r.ZZZ = t;
+		r.ZZ = zz3;
+		r.X = x3;
+		r.Y = y3;
+	}
+	/* XYZZ -> Jacobian with Z' = ZZ: x = X ZZ / ZZ^2, y = Y ZZZ / ZZ^3 (ZZ^3 == ZZZ^2).  2M. */
+	static ECC_HD void xz_to_jac(J &r, const XZ &p)
+	{
+		F::mul(r.X, p.X, p.ZZ);
+		F::mul(r.Y, p.Y, p.ZZZ);
+		r.Z = p.ZZ;
+	}
 };
 
 /* ---------------------------------------------------------------------------------------------- wire format */
@@ -356,7 +433,7 @@ template <int N> ECC_HD void shift_right(Fe<N> &k, int w)
 
 /*
  * Fixed-base comb: acc = sum_i T[i][digit_i(k)],  T[i][d] = d * 2^(w*i) * G  (affine, Montgomery form, entry
- * (i << w) + d; d == 0 unused), 4 <= w <= 24.  One mixed addition per non-zero window, no doublings.  k must be < q.
+ * (i << w) + d; d == 0 unused), 4 <= w <= 26.  One mixed addition per non-zero window, no doublings.  k must be < q.
  * For k < q the accumulator before window i is (k mod 2^(w*i))*G with 0 <= k mod 2^(w*i) < 2^(w*i) <= d*2^(w*i) < q,
  * so the add never meets P = +-Q; add_mixed resolves those cases anyway.
  */
@@ -406,11 +483,12 @@ template <class C> ECC_HD void load_table_entry(Aff<C> &t, const uint32_t *__res
 #endif
 }
 
-template <class C> ECC_HD void comb_mul(Jac<C> &acc, const Fe<C::N> &k, const uint32_t *__restrict__ table, int w)
+template <class C> ECC_HD void comb_mul(Jac<C> &out, const Fe<C::N> &k, const uint32_t *__restrict__ table, int w)
 {
 	typedef EC<C> G;
 	constexpr int N = C::N;
-	G::set_inf(acc);
+	typename G::XZ acc; /* extended Jacobian accumulator: 8M + 2S per window (xz_add_mixed) */
+	G::xz_set_inf(acc);
 	const int nwin = (C::QBITS + w - 1) / w;
 	const uint32_t mask = (1u << w) - 1u;
 	Fe<N> kk = k; /* consumed w bits at a time from the least significant end */
@@ -421,11 +499,12 @@ template <class C> ECC_HD void comb_mul(Jac<C> &acc, const Fe<C::N> &k, const ui
 		if (d != 0) {
 			Aff<C> t;
 			load_table_entry<C>(t, table, ((size_t)i << w) + d);
-			Jac<C> r;
-			G::add_mixed(r, acc, t);
+			typename G::XZ r;
+			G::xz_add_mixed(r, acc, t);
 			acc = r;
 		}
 	}
+	G::xz_to_jac(out, acc); /* (X ZZ, Y ZZZ, ZZ): the Jacobian form K4 / the verification tail expect */
 }
 
 /* One field inversion for the calling thread alone: the inverter of the host build of the tests and of the one-off

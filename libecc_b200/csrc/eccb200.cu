@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace eccb200;
@@ -66,6 +67,12 @@ struct eccb200_ctx {
 	uint32_t *stage_prefix[kStages] = {};
 	uint8_t *stage_aff[kStages] = {};
 	uint64_t launches = 0;
+	/* The device-pointer entry points share ONE scratch set (jac / prefix / aff).  Calls may come in on different
+	 * streams: every call first makes its stream wait for scratch_done (recorded behind the previous call's last
+	 * kernel), so calls are serialised on the device in the order they were issued — never racing on the scratch. */
+	cudaEvent_t scratch_done = nullptr;
+	bool scratch_used = false;
+	unsigned int *gather_counter = nullptr; /* CTA counter of the fused K4 gather (kernels.cuh GatherDst) */
 	/* optional per-kernel timing of the device-pointer API (bench.py's roofline leg) */
 	bool profiling = false;
 	static const int kProfCalls = 64;
@@ -130,6 +137,7 @@ static uint32_t affine_grid(const eccb200_ctx *ctx, uint32_t n)
 static int ensure_work(eccb200_ctx *ctx, uint32_t n)
 {
 	if (n <= ctx->cap) return 0;
+	CUDA_OK(cudaDeviceSynchronize()); /* earlier calls may still be using the scratch that is about to be replaced */
 	if (ctx->jac) cudaFree(ctx->jac);
 	if (ctx->prefix) cudaFree(ctx->prefix);
 	if (ctx->aff) cudaFree(ctx->aff);
@@ -167,7 +175,7 @@ extern "C" int eccb200_ctx_create(eccb200_ctx **out, int curve_id, int device, i
 	uint32_t plen_probe = 0, qlen_probe = 0;
 	if (eccb200_curve_sizes(curve_id, &plen_probe, &qlen_probe)) return -1;
 	int w = comb_window ? comb_window : (plen_probe > 48 ? 20 : 22);
-	if (w < 4 || w > 24 || (w > 16 && (w & 1))) return fail("comb_window must be in [4,16] or even in [18,24]");
+	if (w < 4 || w > 26 || (w > 16 && (w & 1))) return fail("comb_window must be in [4,16] or even in [18,26]");
 
 	eccb200_ctx *ctx = new eccb200_ctx();
 	ctx->curve_id = curve_id;
@@ -198,17 +206,22 @@ extern "C" int eccb200_ctx_create(eccb200_ctx **out, int curve_id, int device, i
 			/* wide table from a half-width one: one addition per entry (k_table_merge), window by window */
 			const int h = w / 2, nwin_half = (C::QBITS + h - 1) / h;
 			const uint32_t half_entries = (uint32_t)nwin_half << h, per_win = 1u << w;
+			/* merged in slices of at most 2^22 entries so that the scratch stays small next to a table of tens of GB */
+			const uint32_t slice = std::min(per_win, 1u << 22);
 			uint32_t *half = nullptr;
 			CUDA_OK(cudaMalloc(&half, (size_t)half_entries * 2 * C::N * sizeof(uint32_t)));
-			if (ensure_work(ctx, std::max(half_entries, per_win))) return -1;
+			if (ensure_work(ctx, std::max(half_entries, slice))) return -1;
 			LaunchVar<C>::table_points(half_entries, h, ctx->jac, 0);
 			LaunchMisc<C>::to_table(affine_grid(ctx, half_entries), half_entries, ctx->jac, ctx->prefix, half, 0);
 			ctx->launches += 2;
 			for (int i = 0; i < ctx->nwin; i++) {
-				LaunchFixed<C>::table_merge(per_win, (uint64_t)i << w, w, nwin_half, half, ctx->jac, 0);
-				LaunchMisc<C>::to_table(affine_grid(ctx, per_win), per_win, ctx->jac, ctx->prefix,
-							ctx->table + ((size_t)i << w) * 2 * C::N, 0);
-				ctx->launches += 2;
+				for (uint32_t off = 0; off < per_win; off += slice) {
+					const uint64_t first = ((uint64_t)i << w) + off;
+					LaunchFixed<C>::table_merge(slice, first, w, nwin_half, half, ctx->jac, 0);
+					LaunchMisc<C>::to_table(affine_grid(ctx, slice), slice, ctx->jac, ctx->prefix,
+								ctx->table + (size_t)first * 2 * C::N, 0);
+					ctx->launches += 2;
+				}
 			}
 			CUDA_OK(cudaDeviceSynchronize());
 			cudaFree(half);
@@ -220,6 +233,12 @@ extern "C" int eccb200_ctx_create(eccb200_ctx **out, int curve_id, int device, i
 	if (rc) {
 		eccb200_ctx_destroy(ctx);
 		return -1;
+	}
+	if (cudaEventCreateWithFlags(&ctx->scratch_done, cudaEventDisableTiming) != cudaSuccess ||
+	    cudaMalloc(&ctx->gather_counter, sizeof(unsigned int)) != cudaSuccess ||
+	    cudaMemset(ctx->gather_counter, 0, sizeof(unsigned int)) != cudaSuccess) {
+		eccb200_ctx_destroy(ctx);
+		return fail("context event / counter allocation failed");
 	}
 	for (int s = 0; s < kStages; s++) {
 		int least = 0, greatest = 0;
@@ -257,6 +276,8 @@ extern "C" void eccb200_ctx_destroy(eccb200_ctx *ctx)
 	if (ctx->ev_ready)
 		for (int c = 0; c < eccb200_ctx::kProfCalls; c++)
 			for (int i = 0; i < 3; i++) cudaEventDestroy(ctx->ev[c][i]);
+	if (ctx->scratch_done) cudaEventDestroy(ctx->scratch_done);
+	if (ctx->gather_counter) cudaFree(ctx->gather_counter);
 	if (ctx->table) cudaFree(ctx->table);
 	if (ctx->jac) cudaFree(ctx->jac);
 	if (ctx->prefix) cudaFree(ctx->prefix);
@@ -314,9 +335,49 @@ static bool tma_staging_enabled()
 	return v == 1;
 }
 
+/* see eccb200_ctx::scratch_done */
+static void scratch_enter(eccb200_ctx *ctx, cudaStream_t st)
+{
+	if (ctx->scratch_used) cudaStreamWaitEvent(st, ctx->scratch_done, 0);
+}
+static void scratch_leave(eccb200_ctx *ctx, cudaStream_t st)
+{
+	cudaEventRecord(ctx->scratch_done, st);
+	ctx->scratch_used = true;
+}
+
+/* The 256-, 384- and 512-bit curves read and write their wire fields with 16-byte vector accesses (load_wire /
+ * store_wire): caller-supplied device (or zero-copy host) buffers must be 16-byte aligned there. */
+static bool misaligned16(const eccb200_ctx *ctx, std::initializer_list<const void *> ptrs)
+{
+	if (ctx->plen % 16) return false; /* byte-granular loaders */
+	for (const void *p : ptrs)
+		if (p && ((uintptr_t)p & 15)) return true;
+	return false;
+}
+static const char *kAlignMsg = "buffer not 16-byte aligned (required for the 256/384/512-bit curves' vector accesses)";
+
+/* waits until flags[i] >= value for i < count (flags in this GPU's memory, written by peers; wrap-safe compare) */
+__global__ void k_flag_wait(const uint32_t *flags, int count, uint32_t value)
+{
+	for (int i = threadIdx.x; i < count; i += blockDim.x)
+		while ((int32_t)(ld_acquire_sys(flags + i) - value) < 0) __nanosleep(200);
+}
+
+struct FlagList {
+	uint32_t *p[ECC_MAX_GATHER_DST];
+};
+/* publishes value to up to ECC_MAX_GATHER_DST (peer-mapped) flags; everything earlier in the stream is visible first */
+__global__ void k_flag_signal(FlagList fl, int count, uint32_t value)
+{
+	__threadfence_system();
+	if ((int)threadIdx.x < count) st_release_sys(fl.p[threadIdx.x], value);
+}
+
 static int smul_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_scalars, const uint8_t *d_points, uint8_t *d_out,
 		    int8_t *d_status, uint32_t *jac, uint32_t *prefix, cudaStream_t st, cudaEvent_t after_smul = nullptr,
-		    cudaStream_t st_norm = nullptr, cudaEvent_t after_norm = nullptr)
+		    cudaStream_t st_norm = nullptr, cudaEvent_t after_norm = nullptr, const GatherDst *gd = nullptr,
+		    const uint32_t *d_wait_flags = nullptr, int wait_count = 0, uint32_t wait_value = 0)
 {
 	/* Pipeline form (after_smul / st_norm / after_norm given): the normalisation runs on a highest-priority stream
 	 * behind the scalar multiplication, so the NEXT chunk's scalar multiplication (which only waits for after_smul)
@@ -324,7 +385,9 @@ static int smul_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_scalars, cons
 	if (n == 0) return 0;
 	return dispatch(ctx->curve_id, [&](auto c) {
 		typedef decltype(c) C;
-		const bool prof = ctx->profiling && jac == ctx->jac && ctx->ev_calls < eccb200_ctx::kProfCalls;
+		const bool own_scratch = jac == ctx->jac;
+		if (own_scratch) scratch_enter(ctx, st);
+		const bool prof = ctx->profiling && own_scratch && ctx->ev_calls < eccb200_ctx::kProfCalls;
 		cudaEvent_t *pe = prof ? ctx->ev[ctx->ev_calls] : nullptr;
 		if (prof) cudaEventRecord(pe[0], st);
 		if (d_points)
@@ -341,12 +404,19 @@ static int smul_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_scalars, cons
 			cudaEventRecord(after_norm, st_norm);
 			cudaStreamWaitEvent(st, after_norm, 0);
 		} else {
-			LaunchMisc<C>::to_affine(affine_grid(ctx, n), n, jac, prefix, d_out, d_status, st);
+			/* multi-GPU gather: the destination's consumer must have released the buffer (ack flag) before K4 stores
+			 * into it; K1 above does not wait */
+			if (d_wait_flags && wait_count > 0) {
+				k_flag_wait<<<1, 32, 0, st>>>(d_wait_flags, wait_count, wait_value);
+				ctx->launches += 1;
+			}
+			LaunchMisc<C>::to_affine(affine_grid(ctx, n), n, jac, prefix, d_out, d_status, st, gd);
 		}
 		if (prof) {
 			cudaEventRecord(pe[2], st);
 			ctx->ev_kernels[ctx->ev_calls++] = 2;
 		}
+		if (own_scratch) scratch_leave(ctx, st);
 		ctx->launches += 2;
 		CUDA_OK(cudaGetLastError());
 		return 0;
@@ -357,9 +427,111 @@ extern "C" int eccb200_prj_pt_mul_batch_dev(eccb200_ctx *ctx, uint32_t n, const 
 					    const uint8_t *d_points, uint8_t *d_out, int8_t *d_status, void *stream)
 {
 	if (!ctx || (n && (!d_scalars || !d_out || !d_status))) return fail("null argument");
+	if (misaligned16(ctx, { d_scalars, d_points, d_out })) return fail(kAlignMsg);
 	CUDA_OK(cudaSetDevice(ctx->device));
 	if (ensure_work(ctx, n)) return -1;
 	return smul_dev(ctx, n, d_scalars, d_points, d_out, d_status, ctx->jac, ctx->prefix, (cudaStream_t)stream);
+}
+
+/* ------------------------------------------------------------------------------------------ multi-GPU result gather */
+
+extern "C" int eccb200_ipc_alloc(eccb200_ctx *ctx, size_t bytes, void **d_ptr, uint8_t handle[64])
+{
+	if (!ctx || !d_ptr || !handle || bytes == 0) return fail("bad argument");
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+	CUDA_OK(cudaSetDevice(ctx->device));
+	void *p = nullptr;
+	CUDA_OK(cudaMalloc(&p, bytes));
+	if (cudaMemset(p, 0, bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+		cudaFree(p);
+		return fail("cudaMemset of the IPC allocation failed");
+	}
+	cudaIpcMemHandle_t h;
+	cudaError_t e = cudaIpcGetMemHandle(&h, p);
+	if (e != cudaSuccess) {
+		cudaFree(p);
+		return fail(std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+	}
+	memcpy(handle, &h, 64);
+	*d_ptr = p;
+	return 0;
+}
+
+extern "C" int eccb200_ipc_open(eccb200_ctx *ctx, const uint8_t handle[64], void **d_ptr)
+{
+	if (!ctx || !d_ptr || !handle) return fail("bad argument");
+	CUDA_OK(cudaSetDevice(ctx->device));
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle, 64);
+	CUDA_OK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+	return 0;
+}
+
+extern "C" int eccb200_ipc_close(eccb200_ctx *ctx, void *d_ptr)
+{
+	if (!ctx || !d_ptr) return fail("bad argument");
+	CUDA_OK(cudaSetDevice(ctx->device));
+	CUDA_OK(cudaIpcCloseMemHandle(d_ptr));
+	return 0;
+}
+
+extern "C" int eccb200_ipc_free(eccb200_ctx *ctx, void *d_ptr)
+{
+	if (!ctx || !d_ptr) return fail("bad argument");
+	CUDA_OK(cudaSetDevice(ctx->device));
+	CUDA_OK(cudaFree(d_ptr));
+	return 0;
+}
+
+extern "C" int eccb200_prj_pt_mul_batch_dev_gather(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_scalars,
+						   const uint8_t *d_points, uint8_t *d_out, int8_t *d_status, int n_dst,
+						   uint8_t *const *dst_out, int8_t *const *dst_status,
+						   uint32_t *const *dst_flag, uint32_t flag_value,
+						   const uint32_t *d_wait_flags, int wait_count, uint32_t wait_value,
+						   void *stream)
+{
+	if (!ctx || (n && (!d_scalars || !d_out || !d_status))) return fail("null argument");
+	if (n_dst < 0 || n_dst > ECC_MAX_GATHER_DST || (n_dst && (!dst_out || !dst_status || !dst_flag)))
+		return fail("bad destination list");
+	if (n == 0) return fail("empty batch: the gather signals arrival from the normalisation kernel");
+	if (misaligned16(ctx, { d_scalars, d_points, d_out })) return fail(kAlignMsg);
+	GatherDst gd;
+	gd.n = n_dst;
+	for (int j = 0; j < n_dst; j++) {
+		if (!dst_out[j] || !dst_status[j] || !dst_flag[j]) return fail("null destination");
+		if (misaligned16(ctx, { dst_out[j] })) return fail(kAlignMsg);
+		gd.out[j] = dst_out[j];
+		gd.status[j] = dst_status[j];
+		gd.flag[j] = dst_flag[j];
+	}
+	gd.flag_value = flag_value;
+	gd.counter = ctx->gather_counter;
+	CUDA_OK(cudaSetDevice(ctx->device));
+	if (ensure_work(ctx, n)) return -1;
+	return smul_dev(ctx, n, d_scalars, d_points, d_out, d_status, ctx->jac, ctx->prefix, (cudaStream_t)stream, nullptr,
+			nullptr, nullptr, n_dst ? &gd : nullptr, d_wait_flags, wait_count, wait_value);
+}
+
+extern "C" int eccb200_flag_wait(eccb200_ctx *ctx, const uint32_t *d_flags, int count, uint32_t value, void *stream)
+{
+	if (!ctx || !d_flags || count <= 0 || count > 1024) return fail("bad argument");
+	CUDA_OK(cudaSetDevice(ctx->device));
+	k_flag_wait<<<1, 32, 0, (cudaStream_t)stream>>>(d_flags, count, value);
+	ctx->launches += 1;
+	CUDA_OK(cudaGetLastError());
+	return 0;
+}
+
+extern "C" int eccb200_flag_signal(eccb200_ctx *ctx, uint32_t *const *d_flags, int count, uint32_t value, void *stream)
+{
+	if (!ctx || !d_flags || count <= 0 || count > ECC_MAX_GATHER_DST) return fail("bad argument");
+	CUDA_OK(cudaSetDevice(ctx->device));
+	FlagList fl;
+	for (int i = 0; i < count; i++) fl.p[i] = d_flags[i];
+	k_flag_signal<<<1, 32, 0, (cudaStream_t)stream>>>(fl, count, value);
+	ctx->launches += 1;
+	CUDA_OK(cudaGetLastError());
+	return 0;
 }
 
 static int verify_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_sigs, const uint8_t *d_pubkeys,
@@ -390,6 +562,7 @@ extern "C" int eccb200_ecdsa_verify_batch_dev(eccb200_ctx *ctx, uint32_t n, cons
 {
 	if (!ctx || (n && (!d_sigs || !d_pubkeys || !d_digests || !d_verdict))) return fail("null argument");
 	if (hlen == 0 || hlen > 128) return fail("bad digest length");
+	if (misaligned16(ctx, { d_sigs, d_pubkeys })) return fail(kAlignMsg);
 	CUDA_OK(cudaSetDevice(ctx->device));
 	return verify_dev(ctx, n, d_sigs, d_pubkeys, d_digests, hlen, d_verdict, (cudaStream_t)stream);
 }
@@ -413,6 +586,7 @@ extern "C" int eccb200_ecfsdsa_verify_batch_dev(eccb200_ctx *ctx, uint32_t n, co
 {
 	if (!ctx || (n && (!d_sigs || !d_pubkeys || !d_digests || !d_verdict))) return fail("null argument");
 	if (hlen == 0 || hlen > 128) return fail("bad digest length");
+	if (misaligned16(ctx, { d_sigs, d_pubkeys })) return fail(kAlignMsg);
 	CUDA_OK(cudaSetDevice(ctx->device));
 	return ecfsdsa_dev(ctx, n, d_sigs, d_pubkeys, d_digests, hlen, d_verdict, (cudaStream_t)stream);
 }
@@ -423,6 +597,10 @@ static int ensure_stages(eccb200_ctx *ctx, size_t in_bytes, size_t out_bytes)
 {
 	if (in_bytes <= ctx->stage_in_bytes && out_bytes <= ctx->stage_out_bytes && ctx->stage_jac[0]) return 0;
 	size_t ib = std::max(in_bytes, ctx->stage_in_bytes), ob = std::max(out_bytes, ctx->stage_out_bytes);
+	/* nothing may still be using the buffers that are about to be replaced; and until the reallocation has fully
+	 * succeeded the recorded sizes are zero, so that a later, smaller call cannot pass the size check on null pointers */
+	CUDA_OK(cudaDeviceSynchronize());
+	ctx->stage_in_bytes = ctx->stage_out_bytes = 0;
 	for (int s = 0; s < kStages; s++) {
 		if (ctx->h_in[s]) cudaFreeHost(ctx->h_in[s]);
 		if (ctx->h_out[s]) cudaFreeHost(ctx->h_out[s]);
@@ -471,8 +649,31 @@ static bool is_pinned(const void *p)
  * staging buffers (one extra memcpy each way).
  */
 template <class Launch>
+static int run_pipeline_body(eccb200_ctx *ctx, uint32_t n, std::vector<HostCol> &in, std::vector<HostCol> &out,
+			     Launch launch, bool ordered);
+
+template <class Launch>
 static int run_pipeline(eccb200_ctx *ctx, uint32_t n, std::vector<HostCol> &in, std::vector<HostCol> &out,
 			Launch launch, bool ordered = false)
+{
+	const int rc = run_pipeline_body(ctx, n, in, out, launch, ordered);
+	if (rc) {
+		/* a failed enqueue leaves copies into the caller's buffers and kernels on the stage buffers in flight: drain
+		 * every stream before the caller may free its memory or the next call reshapes the stages */
+		const std::string keep = g_err;
+		for (int s = 0; s < kStages; s++) {
+			if (ctx->streams[s]) cudaStreamSynchronize(ctx->streams[s]);
+			if (ctx->hi[s]) cudaStreamSynchronize(ctx->hi[s]);
+		}
+		cudaGetLastError();
+		g_err = keep;
+	}
+	return rc;
+}
+
+template <class Launch>
+static int run_pipeline_body(eccb200_ctx *ctx, uint32_t n, std::vector<HostCol> &in, std::vector<HostCol> &out,
+			     Launch launch, bool ordered)
 {
 	/* ordered: the chunks' kernels run in chunk order (event chain).  Right for the short fixed-base kernels, whose
 	 * D2H must overlap the next chunk's arithmetic; wrong for the long K2 / K3 launches, where letting the next chunk's
@@ -619,6 +820,7 @@ extern "C" int eccb200_prj_pt_mul_batch(eccb200_ctx *ctx, uint32_t n, const uint
 	if (n == 0) return 0;
 	if (zero_copy_enabled() && is_pinned(scalars) && is_pinned(out) && is_pinned(status) &&
 	    (!points || is_pinned(points))) {
+		if (misaligned16(ctx, { scalars, points, out })) return fail(kAlignMsg);
 		CUDA_OK(cudaSetDevice(ctx->device));
 		if (ensure_work(ctx, n)) return -1;
 		if (smul_dev(ctx, n, scalars, points, out, status, ctx->jac, ctx->prefix, ctx->streams[0])) return -1;
@@ -688,10 +890,12 @@ static int sign_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_priv, const u
 	if (n == 0) return 0;
 	return dispatch(ctx->curve_id, [&](auto c) {
 		typedef decltype(c) C;
+		if (jac == ctx->jac) scratch_enter(ctx, st);
 		LaunchFixed<C>::fixed(n, d_nonce, ctx->table, ctx->w, jac, d_status, st);       /* k*G          */
 		LaunchMisc<C>::to_affine(affine_grid(ctx, n), n, jac, prefix, aff, d_status, st); /* affine (x, y) */
 		LaunchMisc<C>::sign_finish(affine_grid(ctx, n), n, d_priv, d_nonce, d_dig, hlen, aff, prefix, d_sigs,
 					   d_status, st);                                        /* r, s          */
+		if (jac == ctx->jac) scratch_leave(ctx, st);
 		ctx->launches += 3;
 		CUDA_OK(cudaGetLastError());
 		return 0;
@@ -704,6 +908,7 @@ extern "C" int eccb200_ecdsa_sign_batch_dev(eccb200_ctx *ctx, uint32_t n, const 
 {
 	if (!ctx || (n && (!d_privkeys || !d_nonces || !d_digests || !d_sigs || !d_status))) return fail("null argument");
 	if (hlen == 0 || hlen > 128) return fail("bad digest length");
+	if (misaligned16(ctx, { d_privkeys, d_nonces, d_sigs })) return fail(kAlignMsg);
 	CUDA_OK(cudaSetDevice(ctx->device));
 	if (ensure_work(ctx, n)) return -1;
 	return sign_dev(ctx, n, d_privkeys, d_nonces, d_digests, hlen, d_sigs, d_status, ctx->jac, ctx->prefix, ctx->aff,
@@ -734,8 +939,10 @@ static int ecdh_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_priv, const u
 	if (n == 0) return 0;
 	return dispatch(ctx->curve_id, [&](auto c) {
 		typedef decltype(c) C;
+		if (jac == ctx->jac) scratch_enter(ctx, st);
 		LaunchVar<C>::var(n, d_priv, d_peers, jac, d_status, st);
 		LaunchMisc<C>::to_x_only(affine_grid(ctx, n), n, jac, prefix, d_shared, d_status, st);
+		if (jac == ctx->jac) scratch_leave(ctx, st);
 		ctx->launches += 2;
 		CUDA_OK(cudaGetLastError());
 		return 0;
@@ -747,6 +954,7 @@ extern "C" int eccb200_ecccdh_derive_batch_dev(eccb200_ctx *ctx, uint32_t n, con
 					       void *stream)
 {
 	if (!ctx || (n && (!d_privkeys || !d_peer_pubkeys || !d_shared || !d_status))) return fail("null argument");
+	if (misaligned16(ctx, { d_privkeys, d_peer_pubkeys, d_shared })) return fail(kAlignMsg);
 	CUDA_OK(cudaSetDevice(ctx->device));
 	if (ensure_work(ctx, n)) return -1;
 	return ecdh_dev(ctx, n, d_privkeys, d_peer_pubkeys, d_shared, d_status, ctx->jac, ctx->prefix,
@@ -782,6 +990,15 @@ static int hash_dev(eccb200_ctx *ctx, int hash_type, uint32_t n, const uint8_t *
 	return 0;
 }
 
+/* offsets[0] == 0 and non-decreasing: message i is msgs[offsets[i], offsets[i+1]) inside the offsets[n] bytes copied */
+static bool offsets_ok(const uint64_t *offsets, uint32_t n)
+{
+	if (offsets[0] != 0) return false;
+	for (uint32_t i = 0; i < n; i++)
+		if (offsets[i + 1] < offsets[i]) return false;
+	return true;
+}
+
 extern "C" int eccb200_hash_batch(eccb200_ctx *ctx, int hash_type, uint32_t n, const uint8_t *msgs,
 				  const uint64_t *offsets, uint8_t *digests)
 {
@@ -789,6 +1006,7 @@ extern "C" int eccb200_hash_batch(eccb200_ctx *ctx, int hash_type, uint32_t n, c
 	const int ds = sha2_digest_size(hash_type);
 	if (!ds) return fail("unsupported hash (SHA256 = 2, SHA384 = 3, SHA512 = 4, SHA3_224..512 = 5..8)");
 	if (n == 0) return 0;
+	if (!offsets_ok(offsets, n)) return fail("offsets must start at 0 and be non-decreasing");
 	CUDA_OK(cudaSetDevice(ctx->device));
 	const uint64_t total = offsets[n];
 	if (total && !msgs) return fail("null argument");
@@ -815,6 +1033,7 @@ extern "C" int eccb200_ecdsa_verify_msgs_batch(eccb200_ctx *ctx, int hash_type, 
 	const int ds = sha2_digest_size(hash_type);
 	if (!ds) return fail("unsupported hash (SHA256 = 2, SHA384 = 3, SHA512 = 4, SHA3_224..512 = 5..8)");
 	if (n == 0) return 0;
+	if (!offsets_ok(offsets, n)) return fail("offsets must start at 0 and be non-decreasing");
 	CUDA_OK(cudaSetDevice(ctx->device));
 	const uint64_t total = offsets[n];
 	if (total && !msgs) return fail("null argument");
@@ -834,6 +1053,32 @@ extern "C" int eccb200_ecdsa_verify_msgs_batch(eccb200_ctx *ctx, int hash_type, 
 	if (!rc && cudaMemcpy(verdict, d_v, n, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail("D2H copy failed");
 	cudaFree(d);
 	return rc;
+}
+
+/* Device-resident form: messages, offsets (n + 1 entries, offsets[0] == 0, non-decreasing — NOT re-checked here) and a
+ * [n][digest_size] scratch for the digests all live on the device; hash kernel + K3 on `stream`, asynchronous. */
+extern "C" int eccb200_ecdsa_verify_msgs_batch_dev(eccb200_ctx *ctx, int hash_type, uint32_t n, const uint8_t *d_sigs,
+						   const uint8_t *d_pubkeys, const uint8_t *d_msgs,
+						   const uint64_t *d_offsets, uint8_t *d_digests, int8_t *d_verdict,
+						   void *stream)
+{
+	if (!ctx || (n && (!d_sigs || !d_pubkeys || !d_offsets || !d_digests || !d_verdict))) return fail("null argument");
+	const int ds = sha2_digest_size(hash_type);
+	if (!ds) return fail("unsupported hash (SHA256 = 2, SHA384 = 3, SHA512 = 4, SHA3_224..512 = 5..8)");
+	if (misaligned16(ctx, { d_sigs, d_pubkeys })) return fail(kAlignMsg);
+	if (n == 0) return 0;
+	CUDA_OK(cudaSetDevice(ctx->device));
+	if (hash_dev(ctx, hash_type, n, d_msgs, d_offsets, d_digests, (cudaStream_t)stream)) return -1;
+	return verify_dev(ctx, n, d_sigs, d_pubkeys, d_digests, (uint32_t)ds, d_verdict, (cudaStream_t)stream);
+}
+
+/* cudaMemcpy device -> host for callers that do not link the CUDA runtime (bench.py reads peer-written buffers). */
+extern "C" int eccb200_copy_to_host(eccb200_ctx *ctx, void *host_dst, const void *d_src, size_t bytes)
+{
+	if (!ctx || !host_dst || !d_src) return fail("null argument");
+	CUDA_OK(cudaSetDevice(ctx->device));
+	CUDA_OK(cudaMemcpy(host_dst, d_src, bytes, cudaMemcpyDeviceToHost));
+	return 0;
 }
 
 /* ------------------------------------------------------------------------------------------ structured wire formats (§8f.2) */
@@ -876,7 +1121,9 @@ static int structured_pub_import_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t
 	k_struct_unpack<<<grid_bytes((uint64_t)n * 3 * pl), 256, 0, st>>>(n, d_rec, stride, 3 * pl, d_prj, 3 * pl);
 	int rc = dispatch(ctx->curve_id, [&](auto c) {
 		typedef decltype(c) C;
+		scratch_enter(ctx, st);
 		LaunchMisc<C>::prj_unique(affine_grid(ctx, n), n, d_prj, ctx->jac, ctx->prefix, d_aff, d_state, st);
+		scratch_leave(ctx, st);
 		return 0;
 	});
 	if (rc) return rc;
@@ -1057,7 +1304,7 @@ extern "C" int eccb200_ecdsa_sign_structured_batch(eccb200_ctx *ctx, uint32_t n,
 extern "C" void *eccb200_host_alloc(size_t bytes)
 {
 	void *p = nullptr;
-	if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+	if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
 		cudaGetLastError();
 		g_err = "cudaHostAlloc failed";
 		return nullptr;
@@ -1070,7 +1317,7 @@ extern "C" void *eccb200_host_alloc(size_t bytes)
 extern "C" void *eccb200_host_alloc_input(size_t bytes)
 {
 	void *p = nullptr;
-	if (cudaHostAlloc(&p, bytes, cudaHostAllocWriteCombined) != cudaSuccess) {
+	if (cudaHostAlloc(&p, bytes, cudaHostAllocWriteCombined | cudaHostAllocPortable) != cudaSuccess) {
 		cudaGetLastError();
 		g_err = "cudaHostAlloc(write-combined) failed";
 		return nullptr;
@@ -1099,8 +1346,10 @@ extern "C" int eccb200_prj_pt_unique_batch(eccb200_ctx *ctx, uint32_t n, const u
 	if (!rc)
 		rc = dispatch(ctx->curve_id, [&](auto c) {
 			typedef decltype(c) C;
+			scratch_enter(ctx, 0);
 			LaunchMisc<C>::prj_unique(affine_grid(ctx, n), n, d, ctx->jac, ctx->prefix, d + in_b,
 						  (int8_t *)(d + in_b + out_b), 0);
+			scratch_leave(ctx, 0);
 			ctx->launches += 2;
 			CUDA_OK(cudaGetLastError());
 			CUDA_OK(cudaMemcpy(out, d + in_b, out_b, cudaMemcpyDeviceToHost));
@@ -1273,4 +1522,110 @@ extern "C" int eccb200_imad_peak(int device, double *imad32_per_s, double *imad_
 	*imad32_per_s = best;
 	*imad_per_clk_per_sm = clk_khz ? best / ((double)clk_khz * 1e3) / prop.multiProcessorCount : 0;
 	return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ multi-device (one process) */
+/*
+ * SURVEY.md §8(b) "multi-GPU fan-out is internal", §8(e): a C host hands ONE batch to the library and the library
+ * shards it.  Items are independent, so device g takes the contiguous range [g*n/G, (g+1)*n/G) and runs the ordinary
+ * host-pointer pipeline of its own context on it (own streams, own comb table, own PCIe link), one host thread per
+ * device; every device DMAs its results straight into the caller's output arrays at the shard's offset, so there is
+ * no gather step at all.  Page-locked buffers must be visible to every device (eccb200_host_alloc allocates them
+ * portable).
+ */
+struct eccb200_multi {
+	std::vector<eccb200_ctx *> ctx;
+};
+
+extern "C" void eccb200_multi_destroy(eccb200_multi *m)
+{
+	if (!m) return;
+	for (auto *c : m->ctx) eccb200_ctx_destroy(c);
+	delete m;
+}
+
+extern "C" int eccb200_multi_create(eccb200_multi **out, int curve_id, const int *devices, int n_devices,
+				    int comb_window)
+{
+	if (!out) return fail("null argument");
+	*out = nullptr;
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+		return fail("no CUDA device: libecc_b200 has no CPU fallback");
+	std::vector<int> devs;
+	if (devices && n_devices > 0) devs.assign(devices, devices + n_devices);
+	else
+		for (int d = 0; d < ndev; d++) devs.push_back(d);
+	if (devs.size() > 64) return fail("too many devices");
+	eccb200_multi *m = new eccb200_multi();
+	m->ctx.assign(devs.size(), nullptr);
+	std::vector<int> rc(devs.size(), 0);
+	std::vector<std::string> msg(devs.size());
+	std::vector<std::thread> th;
+	for (size_t g = 0; g < devs.size(); g++) /* the comb tables are built concurrently, one host thread per device */
+		th.emplace_back([&, g] {
+			rc[g] = eccb200_ctx_create(&m->ctx[g], curve_id, devs[g], comb_window);
+			if (rc[g]) msg[g] = eccb200_last_error();
+		});
+	for (auto &t : th) t.join();
+	for (size_t g = 0; g < devs.size(); g++)
+		if (rc[g]) {
+			std::string e = "device " + std::to_string(devs[g]) + ": " + msg[g];
+			eccb200_multi_destroy(m);
+			return fail(e);
+		}
+	*out = m;
+	return 0;
+}
+
+extern "C" int eccb200_multi_device_count(const eccb200_multi *m) { return m ? (int)m->ctx.size() : -1; }
+extern "C" eccb200_ctx *eccb200_multi_ctx(eccb200_multi *m, int index)
+{
+	return (m && index >= 0 && index < (int)m->ctx.size()) ? m->ctx[index] : nullptr;
+}
+
+template <class Fn> static int multi_run(eccb200_multi *m, uint64_t n, Fn &&fn)
+{
+	if (!m) return fail("null argument");
+	const size_t G = m->ctx.size();
+	if (n / G >= 0xffffffffull) return fail("shard too large (2^32 - 1 items per device)");
+	std::vector<int> rc(G, 0);
+	std::vector<std::string> msg(G);
+	std::vector<std::thread> th;
+	for (size_t g = 0; g < G; g++) {
+		const uint64_t lo = n * g / G, hi = n * (g + 1) / G;
+		if (hi == lo) continue;
+		th.emplace_back([&, g, lo, hi] {
+			rc[g] = fn(m->ctx[g], lo, (uint32_t)(hi - lo));
+			if (rc[g]) msg[g] = eccb200_last_error();
+		});
+	}
+	for (auto &t : th) t.join();
+	for (size_t g = 0; g < G; g++)
+		if (rc[g]) return fail("device shard " + std::to_string(g) + ": " + msg[g]);
+	return 0;
+}
+
+extern "C" int eccb200_multi_prj_pt_mul_batch(eccb200_multi *m, uint64_t n, const uint8_t *scalars,
+					      const uint8_t *points, uint8_t *out, int8_t *status)
+{
+	if (!m || (n && (!scalars || !out || !status))) return fail("null argument");
+	const size_t ql = m->ctx[0]->qlen, pl = 2 * (size_t)m->ctx[0]->plen;
+	return multi_run(m, n, [&](eccb200_ctx *c, uint64_t lo, uint32_t cnt) {
+		return eccb200_prj_pt_mul_batch(c, cnt, scalars + lo * ql, points ? points + lo * pl : nullptr,
+						out + lo * pl, status + lo);
+	});
+}
+
+extern "C" int eccb200_multi_ecdsa_verify_batch(eccb200_multi *m, uint64_t n, const uint8_t *sigs,
+						const uint8_t *pubkeys, const uint8_t *digests, uint32_t hlen,
+						int8_t *verdict)
+{
+	if (!m || (n && (!sigs || !pubkeys || !digests || !verdict))) return fail("null argument");
+	if (hlen == 0 || hlen > 128) return fail("bad digest length");
+	const size_t sg = 2 * (size_t)m->ctx[0]->qlen, pk = 2 * (size_t)m->ctx[0]->plen;
+	return multi_run(m, n, [&](eccb200_ctx *c, uint64_t lo, uint32_t cnt) {
+		return eccb200_ecdsa_verify_batch(c, cnt, sigs + lo * sg, pubkeys + lo * pk, digests + lo * (size_t)hlen, hlen,
+						  verdict + lo);
+	});
 }

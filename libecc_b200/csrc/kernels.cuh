@@ -529,10 +529,39 @@ __global__ void __launch_bounds__(128) k_table_merge(uint32_t count, uint64_t fi
  * MODE 3: Jacobian in, writes only the big-endian x coordinate ([n][plen]); infinity is an error (-1): the shared
  *         secret of ecccdh_derive_secret (ecdh/ecccdh.c:209-224).
  */
+/*
+ * Result gather fused into K4 (multi-GPU, one process per GPU): besides its own `out` / `status` the
+ * kernel stores every item's affine bytes and status byte straight into up to ECC_MAX_GATHER_DST other buffers — the
+ * gathered result buffers of peer GPUs, mapped through CUDA IPC, so the stores travel over NVLink while the kernel
+ * computes — and the LAST CTA to finish publishes `flag_value` to each destination's arrival flag with a
+ * system-scope release store.  No separate collective kernel runs, so nothing competes with K1 for the SMs.
+ */
+#define ECC_MAX_GATHER_DST 8
+struct GatherDst {
+	int n = 0;                              /* remote destinations (0: plain K4) */
+	uint8_t *out[ECC_MAX_GATHER_DST];       /* slot base of this rank's shard in destination j: [n_items][2*plen] */
+	int8_t *status[ECC_MAX_GATHER_DST];     /* [n_items] */
+	uint32_t *flag[ECC_MAX_GATHER_DST];     /* arrival flag of this rank at destination j */
+	uint32_t flag_value = 0;
+	unsigned int *counter = nullptr;        /* local: CTAs finished (reset by the last one) */
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v)
+{
+	asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
+{
+	uint32_t v;
+	asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+
 template <class C, int MODE>
 __global__ void __launch_bounds__(128) k_to_affine(uint32_t n, const uint32_t *__restrict__ jac,
 						   uint32_t *__restrict__ prefix, uint8_t *__restrict__ out,
-						   int8_t *__restrict__ status, uint32_t *__restrict__ table_out)
+						   int8_t *__restrict__ status, uint32_t *__restrict__ table_out,
+						   const GatherDst gd)
 {
 	typedef Field<typename C::Fp> F;
 	constexpr int N = C::N;
@@ -561,7 +590,7 @@ __global__ void __launch_bounds__(128) k_to_affine(uint32_t n, const uint32_t *_
 	Fe<N> inv;
 	__shared__ uint32_t sh_inv[ECC_CTA_INV_WORDS(N)];
 	cta_inverse_128<typename C::Fp>(inv, acc, sh_inv); /* one Fermat chain per CTA instead of one per thread */
-	if (!active) return;
+	if (active)
 	for (uint32_t e = last;; e -= T) {
 		Fe<N> z, pre, X, Y;
 		const uint32_t *b = jac + (size_t)e * (3 * N);
@@ -595,9 +624,17 @@ __global__ void __launch_bounds__(128) k_to_affine(uint32_t n, const uint32_t *_
 				store_wire<N, PL>(out + (size_t)e * PL, t);
 			} else {
 				F::from_mont(t, X);
+				F::from_mont(zi, Y);
 				store_wire<N, PL>(out + (size_t)e * (2 * PL), t);
-				F::from_mont(t, Y);
-				store_wire<N, PL>(out + (size_t)e * (2 * PL) + PL, t);
+				store_wire<N, PL>(out + (size_t)e * (2 * PL) + PL, zi);
+				if (MODE == 0) {
+					const int8_t st = err ? (int8_t)-1 : (int8_t)0;
+					for (int j = 0; j < gd.n; j++) {
+						store_wire<N, PL>(gd.out[j] + (size_t)e * (2 * PL), t);
+						store_wire<N, PL>(gd.out[j] + (size_t)e * (2 * PL) + PL, zi);
+						gd.status[j][e] = st;
+					}
+				}
 			}
 		} else {
 			Fe<N> zero;
@@ -612,9 +649,29 @@ __global__ void __launch_bounds__(128) k_to_affine(uint32_t n, const uint32_t *_
 				store_wire<N, PL>(out + (size_t)e * (2 * PL), zero);
 				store_wire<N, PL>(out + (size_t)e * (2 * PL) + PL, zero);
 				if (!err) status[e] = 1;
+				if (MODE == 0) {
+					for (int j = 0; j < gd.n; j++) {
+						store_wire<N, PL>(gd.out[j] + (size_t)e * (2 * PL), zero);
+						store_wire<N, PL>(gd.out[j] + (size_t)e * (2 * PL) + PL, zero);
+						gd.status[j][e] = err ? (int8_t)-1 : (int8_t)1;
+					}
+				}
 			}
 		}
 		if (e < T || e - T < tid) break;
+	}
+	if (MODE == 0 && gd.n > 0) {
+		/* every thread's remote stores are ordered before the counter increment; the last CTA publishes the flags */
+		__threadfence_system();
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			const unsigned int done = atomicAdd(gd.counter, 1u);
+			if (done == gridDim.x - 1) {
+				*gd.counter = 0;
+				__threadfence_system();
+				for (int j = 0; j < gd.n; j++) st_release_sys(gd.flag[j], gd.flag_value);
+			}
+		}
 	}
 }
 
@@ -1051,7 +1108,7 @@ template <class C> struct LaunchVar {
 
 template <class C> struct LaunchMisc {
 	static void to_affine(uint32_t blocks, uint32_t n, const uint32_t *jac, uint32_t *prefix, uint8_t *out,
-			      int8_t *status, cudaStream_t st);
+			      int8_t *status, cudaStream_t st, const GatherDst *gd = nullptr);
 	static void to_table(uint32_t blocks, uint32_t n, const uint32_t *jac, uint32_t *prefix, uint32_t *table,
 			     cudaStream_t st);
 	static void prj_unique(uint32_t blocks, uint32_t n, const uint8_t *prj, uint32_t *jac, uint32_t *prefix,
@@ -1117,15 +1174,15 @@ template <class C> void LaunchVar<C>::table_points(uint32_t entries, int w, uint
 #if defined(ECC_TU_MISC)
 template <class C>
 void LaunchMisc<C>::to_affine(uint32_t blocks, uint32_t n, const uint32_t *jac, uint32_t *prefix, uint8_t *out,
-			      int8_t *status, cudaStream_t st)
+			      int8_t *status, cudaStream_t st, const GatherDst *gd)
 {
-	k_to_affine<C, 0><<<blocks, kThreads, 0, st>>>(n, jac, prefix, out, status, nullptr);
+	k_to_affine<C, 0><<<blocks, kThreads, 0, st>>>(n, jac, prefix, out, status, nullptr, gd ? *gd : GatherDst());
 }
 template <class C>
 void LaunchMisc<C>::to_x_only(uint32_t blocks, uint32_t n, const uint32_t *jac, uint32_t *prefix, uint8_t *out,
 			      int8_t *status, cudaStream_t st)
 {
-	k_to_affine<C, 3><<<blocks, kThreads, 0, st>>>(n, jac, prefix, out, status, nullptr);
+	k_to_affine<C, 3><<<blocks, kThreads, 0, st>>>(n, jac, prefix, out, status, nullptr, GatherDst());
 }
 template <class C>
 void LaunchMisc<C>::sign_finish(uint32_t blocks, uint32_t n, const uint8_t *privkeys, const uint8_t *nonces,
@@ -1140,13 +1197,13 @@ void LaunchMisc<C>::prj_unique(uint32_t blocks, uint32_t n, const uint8_t *prj, 
 			       uint8_t *out, int8_t *status, cudaStream_t st)
 {
 	k_prj_load<C><<<grid_for(n), kThreads, 0, st>>>(n, prj, jac, status);
-	k_to_affine<C, 2><<<blocks, kThreads, 0, st>>>(n, jac, prefix, out, status, nullptr);
+	k_to_affine<C, 2><<<blocks, kThreads, 0, st>>>(n, jac, prefix, out, status, nullptr, GatherDst());
 }
 template <class C>
 void LaunchMisc<C>::to_table(uint32_t blocks, uint32_t n, const uint32_t *jac, uint32_t *prefix, uint32_t *table,
 			     cudaStream_t st)
 {
-	k_to_affine<C, 1><<<blocks, kThreads, 0, st>>>(n, jac, prefix, nullptr, nullptr, table);
+	k_to_affine<C, 1><<<blocks, kThreads, 0, st>>>(n, jac, prefix, nullptr, nullptr, table, GatherDst());
 }
 template <class C>
 void LaunchMisc<C>::scalar_below_order(uint32_t n, const uint8_t *scalars, int8_t *state, cudaStream_t st)

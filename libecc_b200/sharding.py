@@ -1,5 +1,6 @@
 """Multi-GPU plumbing: the batch is embarrassingly parallel, so each rank takes a contiguous shard
-and the only exchange is one all-gather of the fixed-size results (NCCL over NVLink on GPUs; gloo in the CPU tests).
+and the only exchange is the gather of the fixed-size results: either a NCCL all-gather (gather_results; gloo in the
+CPU tests) or, on the hot path, stores of the normalisation kernel into peer-mapped buffers (PeerGather).
 No arithmetic here."""
 from __future__ import annotations
 
@@ -32,3 +33,110 @@ def gather_results(local: torch.Tensor, n_total: int, item: int, group=None) -> 
     buf = torch.empty(world * mx, dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(buf, padded, group=group)
     return torch.cat([buf[r * mx: r * mx + counts[r] * item] for r in range(world)])
+
+
+# ------------------------------------------------------------------------------------------------ peer-memory gather
+#
+# The result gather of the multi-GPU path without a collective kernel: every rank owns one
+# IPC-exported region; the normalisation kernel (K4) of a source rank stores its results straight into its slot of
+# each destination's region over NVLink and publishes an arrival counter; destinations acknowledge consumption so
+# that a slot is never overwritten early.  This module only computes the layout and moves 64-byte handles around
+# (torch.distributed); the stores, flags and waits are in libecc_b200.so (eccb200_prj_pt_mul_batch_dev_gather,
+# eccb200_flag_wait, eccb200_flag_signal).
+
+FLAG_BYTES = 4096          # [0, 2048): arrive[src] u32 counters; [2048, 4096): ack[dst] u32 counters
+ACK_OFFSET = 2048
+
+
+def gather_layout(world: int, n_items: int, plen: int, nbuf: int = 2) -> dict:
+    """Byte layout of one rank's region: flags, then nbuf buffers of `world` slots; a slot holds one source rank's
+    [n_items][2*plen] affine points followed by its [n_items] status bytes, padded to 256 bytes."""
+    assert 1 <= world <= 512 and nbuf >= 1
+    out_bytes = n_items * 2 * plen
+    slot = (out_bytes + n_items + 255) // 256 * 256
+    return {"flags": 0, "ack": ACK_OFFSET, "data": FLAG_BYTES, "slot_bytes": slot, "status_offset": out_bytes,
+            "buf_bytes": world * slot, "total": FLAG_BYTES + nbuf * world * slot, "nbuf": nbuf, "world": world}
+
+
+def slot_offset(layout: dict, buf: int, src: int) -> int:
+    return layout["data"] + buf * layout["buf_bytes"] + src * layout["slot_bytes"]
+
+
+def gather_destinations(world: int, mode: str):
+    """Ranks that receive every rank's results: 'root' -> [0] (the final result gather of SURVEY.md §8e),
+    'all' -> every rank (all-gather semantics)."""
+    if mode == "root":
+        return [0]
+    if mode == "all":
+        return list(range(world))
+    raise ValueError(mode)
+
+
+class PeerGather:
+    """Per-rank state of the peer-memory gather for fixed-size batches of `n_items` results."""
+
+    def __init__(self, eng, rank: int, world: int, n_items: int, mode: str = "root", nbuf: int = 2, group=None):
+        self.group = group
+        self.eng, self.rank, self.world, self.n, self.nbuf = eng, rank, world, n_items, nbuf
+        self.layout = gather_layout(world, n_items, eng.plen, nbuf)
+        self.dests = gather_destinations(world, mode)
+        if len(self.dests) > 8:
+            raise ValueError("at most 8 destinations")
+        self.base, handle = eng.ipc_alloc(self.layout["total"])
+        handles = [None] * world
+        dist.all_gather_object(handles, handle, group=group)
+        self.peer = {}                       # rank -> mapped base pointer of that rank's region
+        for r in set(self.dests) | {self.rank}:
+            self.peer[r] = self.base if r == rank else eng.ipc_open(handles[r])
+        if rank in self.dests:               # a destination acknowledges into every source's region
+            for r in range(world):
+                if r not in self.peer:
+                    self.peer[r] = eng.ipc_open(handles[r])
+        self.step_no = 0
+        dist.barrier(group=group)            # every mapping exists before anybody stores
+
+    def step(self, p_scalars: int, p_points, p_out: int, p_status: int, stream: int):
+        """One batch: K1, (wait for the buffer's release), K4 with the fused gather; on a destination rank also the
+        wait for every source's arrival and the release acknowledgement.  Returns the buffer index used."""
+        c = self.step_no + 1
+        b = self.step_no % self.nbuf
+        L = self.layout
+        dst_out = [self.peer[d] + slot_offset(L, b, self.rank) for d in self.dests]
+        dst_st = [p + L["status_offset"] for p in dst_out]
+        dst_flag = [self.peer[d] + L["flags"] + 4 * self.rank for d in self.dests]
+        need_ack = c - self.nbuf                     # the step that last used this buffer must have been consumed
+        if need_ack >= 1:
+            wait_ptr, wait_cnt = self._ack_wait_ptr()
+        else:
+            wait_ptr, wait_cnt = None, 0
+        self.eng.prj_pt_mul_batch_dev_gather(self.n, p_scalars, p_points, p_out, p_status, dst_out, dst_st, dst_flag, c,
+                                             wait_ptr, wait_cnt, max(need_ack, 0), stream)
+        if self.rank in self.dests:
+            self.eng.flag_wait(self.base + L["flags"], self.world, c, stream)        # all sources' step c has landed
+            # ... a consumer of buffer b would run here ...
+            acks = [self.peer[r] + L["ack"] + 4 * self.rank for r in range(self.world)]
+            for i in range(0, len(acks), 8):
+                self.eng.flag_signal(acks[i:i + 8], c, stream)
+        self.step_no += 1
+        return b
+
+    def _ack_wait_ptr(self):
+        d = sorted(self.dests)
+        if d == list(range(d[0], d[0] + len(d))):   # contiguous ack counters: one wait kernel covers them
+            return self.base + self.layout["ack"] + 4 * d[0], len(d)
+        raise ValueError("destination ranks must be contiguous")
+
+    def buffer_ptr(self, buf: int, src: int) -> int:
+        """Address of source `src`'s slot of buffer `buf` in THIS rank's region (meaningful on destinations)."""
+        return self.base + slot_offset(self.layout, buf, src)
+
+    def close(self, group=None):
+        """Collective: every rank unmaps the peers' regions, then (after a barrier) frees its own."""
+        for r, p in self.peer.items():
+            if r != self.rank:
+                self.eng.ipc_close(p)
+        self.peer = {}
+        dist.barrier(group=group)
+        if self.base:
+            self.eng.ipc_free(self.base)
+            self.base = 0

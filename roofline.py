@@ -8,12 +8,14 @@ import math
 # one Montgomery CIOS product of n 64-bit limbs = 2n^2+n wide multiply-accumulates, each = 4 32x32->64 IMADs
 IMAD32_PER_MUL = {"SECP256R1": (2 * 4 * 4 + 4) * 4, "FRP256V1": (2 * 4 * 4 + 4) * 4, "SECP384R1": (2 * 6 * 6 + 6) * 4,
                   "BRAINPOOLP256R1": 144, "SECP256K1": 144, "BRAINPOOLP384R1": 312, "SECP521R1": (2 * 9 * 9 + 9) * 4}
-# IMAD.WIDE instructions the generated code really issues per product, averaged over a mixed addition (8 mul + 3 sqr;
-# tools/gen_fp_ptx.py: P-256 mul 96 / sqr 68, generic 256-bit 136 / 108, P-384 276 / 210 incl. the m_i products)
-IMAD_EXECUTED_PER_MUL = {"SECP256R1": (8 * 96 + 3 * 68) / 11, "FRP256V1": (8 * 136 + 3 * 108) / 11,
-                         "SECP384R1": (8 * 276 + 3 * 210) / 11, "BRAINPOOLP256R1": (8 * 136 + 3 * 108) / 11,
-                         "SECP256K1": (8 * 136 + 3 * 108) / 11, "BRAINPOOLP384R1": (8 * 300 + 3 * 234) / 11,
-                         "SECP521R1": (8 * 630 + 3 * 477) / 11}
+# IMAD.WIDE instructions the generated code really issues per product (tools/gen_fp_ptx.py: P-256 mul 96 / sqr 68,
+# generic 256-bit 136 / 108, P-384 276 / 210 incl. the m_i products)
+IMAD_MUL_SQR = {"SECP256R1": (96, 68), "FRP256V1": (136, 108), "SECP384R1": (276, 210), "BRAINPOOLP256R1": (136, 108),
+                "SECP256K1": (136, 108), "BRAINPOOLP384R1": (300, 234), "SECP521R1": (630, 477)}
+# averaged over a Jacobian mixed addition (8 mul + 3 sqr): the variable-base / verification kernels
+IMAD_EXECUTED_PER_MUL = {c: (8 * m + 3 * q) / 11 for c, (m, q) in IMAD_MUL_SQR.items()}
+# averaged over the comb's extended-Jacobian mixed addition (8 mul + 2 sqr): the fixed-base kernel
+IMAD_EXECUTED_PER_MUL_FIXED = {c: (8 * m + 2 * q) / 10 for c, (m, q) in IMAD_MUL_SQR.items()}
 M_REF = {"SECP256R1": 8724, "FRP256V1": 8724, "SECP384R1": 13076,   # reference ladder (probe)
          "BRAINPOOLP256R1": 8724, "SECP256K1": 8724, "BRAINPOOLP384R1": 13076,
          "SECP521R1": (2 * 521 + 1) * 17 + 3}
@@ -26,7 +28,8 @@ def work_per_item(workload: str, comb_window: int):
     curve, kind, _, _ = WORKLOADS[workload]
     nwin = math.ceil(QBITS[curve] / comb_window)
     nib = (QBITS[curve] + 3) // 4
-    m_fixed = 11 * (nwin - 1)                                   # mixed add 8M+3S per window; first window is a copy
+    m_fixed = 10 * (nwin - 1) + 2                               # extended-Jacobian mixed add 8M+2S per window (the
+    #                                                             first window is a copy) + 2M back to Jacobian
     fermat = nib * 5 + 14                                       # 4 sqr + 1 mul per nibble of the exponent + table
     cta_inv = 16 + fermat / 4.0                                 # CTA-wide inversion per thread: 2 scans (14) + 2, and
     #                                                             one Fermat chain run by one of the CTA's four warps
@@ -45,9 +48,10 @@ def work_per_item(workload: str, comb_window: int):
         # inversion, u / v / key validation / final comparison (~12)
         m, kernel = m_fixed + m_var + 7 + 11 + cta_inv + 12, "k_ecdsa_verify"
         m_ref = 2 * M_REF[curve] + 17 + (2 * QBITS[curve] + 1) + 2
+    per_mul = (IMAD_EXECUTED_PER_MUL_FIXED if kind == "fixed" else IMAD_EXECUTED_PER_MUL)[curve]
     return {"M_impl": m, "kernel": kernel, "imad32_per_mul": IMAD32_PER_MUL[curve],
             "imad32_per_item": m * IMAD32_PER_MUL[curve], "imad32_ref_per_item": m_ref * IMAD32_PER_MUL[curve],
-            "imad_executed_per_item": m * IMAD_EXECUTED_PER_MUL[curve]}
+            "imad_executed_per_item": m * per_mul}
 
 
 def imad_peak_measured(device: int = 0):

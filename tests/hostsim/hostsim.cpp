@@ -244,7 +244,7 @@ int hostsim_ecfsdsa_verify_batch(int curve_id, int w, uint32_t n, const uint8_t 
 	});
 }
 
-/* group-law unit test: out = P1 + P2 on affine wire points through add_full / add_mixed (which = 0 / 1),
+/* group-law unit test: out = P1 + P2 on affine wire points through add_full / add_mixed / xz_add_mixed (which = 0 / 1 / 3),
  * or 2*P1 through dbl (which = 2); infinity operands are encoded as all-zero wire points */
 int hostsim_point_op(int curve_id, int which, const uint8_t *p1, const uint8_t *p2, uint8_t *out, int8_t *status)
 {
@@ -282,6 +282,16 @@ int hostsim_point_op(int curve_id, int which, const uint8_t *p1, const uint8_t *
 		else if (which == 1) {
 			if (b_inf) return -1;
 			G::add_mixed(R, A, b);
+		} else if (which == 3) { /* extended Jacobian accumulator of the comb: (X, Y, ZZ, ZZZ) + affine */
+			if (b_inf) return -1;
+			typedef Field<typename C::Fp> F;
+			typename G::XZ P, S;
+			P.X = A.X;
+			P.Y = A.Y;
+			F::sqr(P.ZZ, A.Z);
+			F::mul(P.ZZZ, P.ZZ, A.Z);
+			G::xz_add_mixed(S, P, b);
+			G::xz_to_jac(R, S);
 		} else G::dbl(R, A);
 		*status = (int8_t)jac_to_wire<C>(R, out);
 		return 0;
