@@ -62,7 +62,10 @@ MSG_LEN = 32          # the ECDSA workloads verify MESSAGES (ec_verify hashes th
 VERIFY_HASH = "SHA256"
 # comb window of the fixed-base table when --comb-window is not given: the widest table that pays on a B200
 # (measured sweep in DESIGN.md §4); other curves keep the library default
-DEFAULT_COMB = {"SECP256R1": int(os.environ.get("BENCH_COMB_WINDOW", "0"))}
+# round 2, one B200, 2^20 scalars: secp256r1 w = 22 / 24 / 26 -> 513 / 555 / 604 M/s (tables 3.2 / 11.8 / 40 GiB of the
+# 180 GB HBM); secp384r1 keeps to 24 bits (24 GiB; 26 bits would be 90 GiB)
+DEFAULT_COMB = {"SECP256R1": int(os.environ.get("BENCH_COMB_WINDOW", "26")),
+                "SECP384R1": int(os.environ.get("BENCH_COMB_WINDOW_384", "24"))}
 
 
 def splitmix_bytes(n_bytes: int, tag: int) -> np.ndarray:
@@ -270,8 +273,10 @@ def make_verify_inputs(curve: str, n: int, rank: int, use_gpu: bool = True):
     want, wst = oracle_sign(curve, d[:m], k[:m], dg[:m], hlen)
     assert (wst == 0).all() and (want == sigs[:m]).all()
     expected = corrupt(sigs, pubs, msgs, n)
+    changed = np.arange(0, n, 16)[(np.arange(0, n, 16) // 16) % 6 == 2]      # rows whose message was corrupted
+    dg[changed] = sha256_rows(msgs[changed])
     assert (oracle_verify(curve, sigs[:m], pubs[:m], sha256_rows(msgs[:m]), hlen) == expected[:m]).all()
-    return {"sigs": sigs, "pubkeys": pubs, "msgs": msgs, "expected": expected, "hlen": hlen}
+    return {"sigs": sigs, "pubkeys": pubs, "msgs": msgs, "digests_host": dg, "expected": expected, "hlen": hlen}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms
@@ -421,7 +426,7 @@ class Ours:
             comb_window = DEFAULT_COMB.get(self.curve, 0)
         self.eng = libecc_b200.Engine(self.curve, device=local_rank, comb_window=comb_window)
         n, plen = self.n, self.plen
-        skip = ("expected",)
+        skip = ("expected", "digests_host")
         self.d = {k: torch.from_numpy(v).to(self.dev) for k, v in self.inputs.items()
                   if isinstance(v, np.ndarray) and k not in skip}
         if self.kind == "verify":

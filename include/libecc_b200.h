@@ -157,6 +157,13 @@ int eccb200_ecdsa_verify_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *sigs
 			       const uint8_t *digests, uint32_t hlen, int8_t *verdict);
 int eccb200_ecdsa_verify_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_sigs, const uint8_t *d_pubkeys,
 				   const uint8_t *d_digests, uint32_t hlen, int8_t *d_verdict, void *stream);
+/* The same with a per-key state column: 0 = affine key in pubkeys[i]; 1 = the key is the point at infinity
+ * (pubkeys[i] ignored) — the reference's ec_verify accepts such an ec_pub_key and computes W' = u*G
+ * (src/curves/prj_pt.c:1767-1775 gives v*infinity = infinity); -1 = rejected key.  For callers that hold
+ * reference structs (the drop-in layer). */
+int eccb200_ecdsa_verify_keystate_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys,
+					const int8_t *key_state, const uint8_t *digests, uint32_t hlen,
+					int8_t *verdict);
 
 /*
  * Batched ECDSA signing on pre-hashed messages with caller-supplied nonces: replaces, per signature,

@@ -3,10 +3,13 @@
  * implemented on the GPU engine (libecc_b200.h).  Built as libecc_b200/libecc_b200_dropin.so.
  *
  * What a libecc maintainer gets (see INTEGRATION.md for the exact link lines):
- *   - `prj_pt_mul` / `prj_pt_mul_blind` with the reference's exact signatures (src/curves/prj_pt.h:61-62).  Linked
- *     (or LD_PRELOADed) ahead of a shared libsign/libec, they interpose the reference's definitions, so every
- *     caller — ECDSA sign/verify (src/sig/ecdsa_common.c:479,788,793), ECC-CDH (src/ecdh/ecccdh.c:80,209), all
- *     other schemes of src/sig — runs its scalar multiplications on the B200 without being recompiled.
+ *   - `prj_pt_mul` with the reference's exact signature (src/curves/prj_pt.h:61).  Linked (or LD_PRELOADed) ahead of
+ *     a shared libsign/libec, it interposes the reference's definition, so every caller — ECDSA sign/verify
+ *     (src/sig/ecdsa_common.c:479,788,793), ECC-CDH (src/ecdh/ecccdh.c:80,209), all other schemes of src/sig — runs
+ *     its scalar multiplications on the B200 without being recompiled.
+ *   - `ec_verify` with the reference's exact signature (src/sig/sig_algs.h:85-88): ECDSA / DECDSA / ECFSDSA
+ *     verifications become ONE kernel launch each; every other scheme is forwarded to the reference's own ec_verify.
+ *   - `prj_pt_mul_blind` (src/curves/prj_pt.h:62) is exported but NOT taken over by default: see its comment below.
  *   - `eccb200_dropin_prj_pt_mul_batch`: the same on arrays of reference structs (one launch for the batch).
  *   - `eccb200_dropin_ecdsa_verify_batch`: a function with the signature of the reference's per-scheme
  *     `verify_batch` slot (src/sig/sig_algs_internal.h:78-81), to put in ec_sig_maps[] where the reference has
@@ -92,13 +95,42 @@ typedef struct {
  * Drop-in replacements with the reference's exact prototypes (src/curves/prj_pt.h:61-62):
  *     int prj_pt_mul(prj_pt_t out, nn_src_t m, prj_pt_src_t in);
  *     int prj_pt_mul_blind(prj_pt_t out, nn_src_t m, prj_pt_src_t in);
+ * (prj_pt_mul_blind: see the security note below.)
  * Semantics kept (SURVEY.md §8a edge table): 0 / -1; `in` must be initialised and on its curve (else -1); any
  * scalar m (up to 27 words) gives (m mod order)*in; out may alias in; out is a valid initialised struct, canonical
  * (x, y, 1) for finite results and (0, 1, 0) for the point at infinity.  Supported curves: those of libecc_b200.h
  * (identified by p and the order); any other curve returns -1.
  */
 int prj_pt_mul(eccb200_prj_pt *out, const eccb200_nn *m, const eccb200_prj_pt *in);
+
+/*
+ * SECURITY NOTE — prj_pt_mul_blind.  The reference calls prj_pt_mul_blind where the scalar is SECRET (the ECDSA nonce
+ * under USE_SIG_BLINDING, src/sig/ecdsa_common.c:476): it blinds the scalar and runs its constant-time ladder
+ * (src/curves/prj_pt.c:1782-1822).  The GPU engine is a throughput path: table indices and branches depend on the
+ * scalar, nothing is blinded.  Therefore this symbol does NOT silently route secret scalars to the GPU: by default it
+ * forwards to the NEXT prj_pt_mul_blind in the process (the reference's own, when this library is preloaded or linked
+ * ahead of a shared libec) and returns -1 if there is none.  Setting ECCB200_BLIND_ON_GPU=1 in the environment, or
+ * calling eccb200_dropin_allow_nonct_blind(1), opts in to serving it on the GPU (same point, no side-channel
+ * protection).  The same caveat holds for the explicit batch signing / ECDH entry points of libecc_b200.h, which a
+ * caller only reaches by choosing them.
+ */
 int prj_pt_mul_blind(eccb200_prj_pt *out, const eccb200_nn *m, const eccb200_prj_pt *in);
+void eccb200_dropin_allow_nonct_blind(int on);
+
+/*
+ * ec_verify with the reference's prototype (src/sig/sig_algs.h:85-88; sig_type / hash_type are the reference's
+ * ec_alg_type / hash_alg_type values):
+ *     int ec_verify(const u8 *sig, u8 siglen, const ec_pub_key *pub_key, const u8 *m, u32 mlen,
+ *                   ec_alg_type sig_type, hash_alg_type hash_type, const u8 *adata, u16 adata_len);
+ * ECDSA (1), DECDSA (14) and ECFSDSA (5) without ancillary data on a supported curve: the message is hashed on the
+ * host with the reference's src/hash and the whole verification (steps 3-10 of __ecdsa_verify_finalize,
+ * src/sig/ecdsa_common.c:760-810) is ONE launch of the verification kernel; 0 = valid, -1 = invalid.  Anything else is
+ * forwarded unchanged to the next ec_verify in the process (the reference's own); -1 if there is none.
+ */
+int ec_verify(const uint8_t *sig, uint8_t siglen, const eccb200_ec_pub_key *pub_key, const uint8_t *m, uint32_t mlen,
+	      int sig_type, int hash_type, const uint8_t *adata, uint16_t adata_len);
+int eccb200_dropin_ec_verify(const uint8_t *sig, uint8_t siglen, const eccb200_ec_pub_key *pub_key, const uint8_t *m,
+			     uint32_t mlen, int sig_type, int hash_type, const uint8_t *adata, uint16_t adata_len);
 
 /* The same under non-clashing names (for callers that link the reference statically and choose per call). */
 int eccb200_dropin_prj_pt_mul(eccb200_prj_pt *out, const eccb200_nn *m, const eccb200_prj_pt *in);
@@ -135,8 +167,20 @@ uint32_t eccb200_dropin_last_verdicts(int8_t *verdicts, uint32_t cap);
  * interposed prj_pt_mul, not the CPU one, was reached). */
 unsigned long long eccb200_dropin_call_count(void);
 
+/* Signatures verified on the GPU by this layer (ec_verify shim and verify_batch adapters). */
+unsigned long long eccb200_dropin_verify_count(void);
+
 /* Device the drop-in layer uses (default 0; also settable with the ECCB200_DEVICE environment variable). */
 int eccb200_dropin_set_device(int device);
+
+/*
+ * Memory policy.  Engine contexts are created lazily, per curve: up to four SMALL ones (16-bit fixed-base comb,
+ * 64 MiB for a 256-bit curve; concurrent callers do not block each other) for single calls and small batches, and
+ * one BIG one (the engine's default 22-bit comb, 3.2 GiB for a 256-bit curve; ECCB200_COMB_WINDOW overrides) only
+ * when a batch of at least 2^15 items arrives.  eccb200_dropin_release() destroys every context and frees the
+ * page-locked staging buffers; the next call re-creates what it needs.
+ */
+void eccb200_dropin_release(void);
 
 #ifdef __cplusplus
 }

@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "eccb200_ipc_free", "eccb200_flag_wait", "eccb200_flag_signal",
     "eccb200_multi_create", "eccb200_multi_destroy", "eccb200_multi_device_count", "eccb200_multi_ctx",
     "eccb200_multi_prj_pt_mul_batch", "eccb200_multi_ecdsa_verify_batch",
-    "eccb200_ecdsa_verify_msgs_batch_dev", "eccb200_copy_to_host",
+    "eccb200_ecdsa_verify_msgs_batch_dev", "eccb200_copy_to_host", "eccb200_ecdsa_verify_keystate_batch",
 ]
 
 _lib = None
@@ -106,6 +106,7 @@ def load_library() -> ctypes.CDLL:
     lib.eccb200_multi_ecdsa_verify_batch.argtypes = [vp, u64, u8p, u8p, u8p, u32, i8p]
     lib.eccb200_ecdsa_verify_msgs_batch_dev.argtypes = [vp, ctypes.c_int, u32, u8p, u8p, u8p, vp, u8p, i8p, vp]
     lib.eccb200_copy_to_host.argtypes = [vp, vp, vp, ctypes.c_size_t]
+    lib.eccb200_ecdsa_verify_keystate_batch.argtypes = [vp, u32, u8p, u8p, i8p, u8p, u32, i8p]
     lib.eccb200_host_alloc.argtypes = [ctypes.c_size_t]
     lib.eccb200_host_alloc.restype = ctypes.c_void_p
     lib.eccb200_host_alloc_input.argtypes = [ctypes.c_size_t]

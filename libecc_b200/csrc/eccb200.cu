@@ -535,7 +535,8 @@ extern "C" int eccb200_flag_signal(eccb200_ctx *ctx, uint32_t *const *d_flags, i
 }
 
 static int verify_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_sigs, const uint8_t *d_pubkeys,
-		      const uint8_t *d_digests, uint32_t hlen, int8_t *d_verdict, cudaStream_t st)
+		      const uint8_t *d_digests, uint32_t hlen, int8_t *d_verdict, cudaStream_t st,
+		      const int8_t *d_key_state = nullptr)
 {
 	if (n == 0) return 0;
 	return dispatch(ctx->curve_id, [&](auto c) {
@@ -545,7 +546,7 @@ static int verify_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_sigs, const
 		const bool prof = ctx->profiling && !staged && ctx->ev_calls < eccb200_ctx::kProfCalls;
 		cudaEvent_t *pe = prof ? ctx->ev[ctx->ev_calls] : nullptr;
 		if (prof) cudaEventRecord(pe[0], st);
-		LaunchVerify<C>::verify(n, d_sigs, d_pubkeys, d_digests, hlen, ctx->table, ctx->w, d_verdict, st);
+		LaunchVerify<C>::verify(n, d_sigs, d_pubkeys, d_digests, hlen, ctx->table, ctx->w, d_verdict, st, d_key_state);
 		if (prof) {
 			cudaEventRecord(pe[1], st);
 			ctx->ev_kernels[ctx->ev_calls++] = 1;
@@ -860,6 +861,27 @@ extern "C" int eccb200_ecdsa_verify_batch(eccb200_ctx *ctx, uint32_t n, const ui
 		const uint8_t *d = ctx->d_in[s];
 		return verify_dev(ctx, cnt, d, d + (size_t)cnt * sg, d + (size_t)cnt * (sg + pk), hlen,
 				  (int8_t *)ctx->d_out[s], ctx->streams[s]);
+	});
+}
+
+/* With a per-key state column (0 = affine key in pubkeys[i], 1 = the key is the point at infinity, -1 = rejected): the
+ * reference's ec_verify accepts an ec_pub_key whose y is the point at infinity and then computes W' = u*G
+ * (prj_pt_mul on infinity gives infinity, curves/prj_pt.c:1767-1775); callers holding reference structs need it. */
+extern "C" int eccb200_ecdsa_verify_keystate_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *sigs,
+						   const uint8_t *pubkeys, const int8_t *key_state,
+						   const uint8_t *digests, uint32_t hlen, int8_t *verdict)
+{
+	if (!ctx || (n && (!sigs || !pubkeys || !key_state || !digests || !verdict))) return fail("null argument");
+	if (hlen == 0 || hlen > 128) return fail("bad digest length");
+	if (n == 0) return 0;
+	const size_t sg = 2 * (size_t)ctx->qlen, pk = 2 * (size_t)ctx->plen;
+	std::vector<HostCol> in = { { (uint8_t *)sigs, sg, false }, { (uint8_t *)pubkeys, pk, false },
+				    { (uint8_t *)key_state, 1, false }, { (uint8_t *)digests, hlen, false } };
+	std::vector<HostCol> outc = { { (uint8_t *)verdict, 1, false } };
+	return run_pipeline(ctx, n, in, outc, [&](int s, uint32_t cnt) {
+		const uint8_t *d = ctx->d_in[s];
+		return verify_dev(ctx, cnt, d, d + (size_t)cnt * sg, d + (size_t)cnt * (sg + pk + 1), hlen,
+				  (int8_t *)ctx->d_out[s], ctx->streams[s], (const int8_t *)(d + (size_t)cnt * (sg + pk)));
 	});
 }
 

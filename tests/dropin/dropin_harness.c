@@ -27,6 +27,10 @@ typedef int (*vbatch_fn)(const u8 **, const u8 *, const ec_pub_key **, const u8 
 			 hash_alg_type, const u8 **, const u16 *, verify_batch_scratch_pad *, u32 *);
 typedef u32 (*verdicts_fn)(signed char *, u32);
 typedef unsigned long long (*count_fn)(void);
+typedef void (*allow_fn)(int);
+typedef int (*everify_fn)(const u8 *, u8, const ec_pub_key *, const u8 *, u32, ec_alg_type, hash_alg_type, const u8 *, u16);
+#include <pthread.h>
+#include <time.h>
 
 static int failures = 0;
 #define CHECK(cond, ...)                                      \
@@ -80,7 +84,12 @@ static int run_direct(const char *dropin_path)
 	vbatch_fn gpu_vbatch = (vbatch_fn)dlsym(h, "eccb200_dropin_ecdsa_verify_batch");
 	vbatch_fn gpu_fsbatch = (vbatch_fn)dlsym(h, "eccb200_dropin_ecfsdsa_verify_batch");
 	verdicts_fn gpu_verdicts = (verdicts_fn)dlsym(h, "eccb200_dropin_last_verdicts");
-	if (!gpu_mul || !gpu_mul_blind || !gpu_batch || !gpu_vbatch || !gpu_fsbatch || !gpu_verdicts) {
+	count_fn gpu_calls = (count_fn)dlsym(h, "eccb200_dropin_call_count");
+	count_fn gpu_vcount = (count_fn)dlsym(h, "eccb200_dropin_verify_count");
+	allow_fn gpu_allow_blind = (allow_fn)dlsym(h, "eccb200_dropin_allow_nonct_blind");
+	everify_fn gpu_everify = (everify_fn)dlsym(h, "eccb200_dropin_ec_verify");
+	if (!gpu_mul || !gpu_mul_blind || !gpu_batch || !gpu_vbatch || !gpu_fsbatch || !gpu_verdicts || !gpu_calls ||
+	    !gpu_vcount || !gpu_allow_blind || !gpu_everify) {
 		printf("FAIL missing drop-in symbols\n");
 		return 1;
 	}
@@ -106,8 +115,17 @@ static int run_direct(const char *dropin_path)
 			int r1 = prj_pt_mul(&o_ref, &k, b);
 			int r2 = gpu_mul(&o_gpu, &k, b);
 			compare("prj_pt_mul", names[c], r1, &o_ref, r2, &o_gpu);
+			/* prj_pt_mul_blind: by default NOT served by the GPU (secret scalars) but forwarded to the reference's
+			 * own; after the explicit opt-in it runs on the GPU.  Same point either way. */
+			unsigned long long before = gpu_calls();
 			r2 = gpu_mul_blind(&o_gpu, &k, b);
-			compare("prj_pt_mul_blind", names[c], r1, &o_ref, r2, &o_gpu);
+			compare("prj_pt_mul_blind (forwarded)", names[c], r1, &o_ref, r2, &o_gpu);
+			CHECK(gpu_calls() == before, "%s: prj_pt_mul_blind reached the GPU without the opt-in", names[c]);
+			gpu_allow_blind(1);
+			r2 = gpu_mul_blind(&o_gpu, &k, b);
+			compare("prj_pt_mul_blind (opt-in, GPU)", names[c], r1, &o_ref, r2, &o_gpu);
+			CHECK(gpu_calls() == before + 1, "%s: opted-in prj_pt_mul_blind did not reach the GPU", names[c]);
+			gpu_allow_blind(0);
 			/* out == in */
 			prj_pt alias;
 			CHECK(!prj_pt_copy(&alias, b), "copy");
@@ -194,6 +212,38 @@ static int run_direct(const char *dropin_path)
 				CHECK(v[i] == want, "%s verify_batch verdict[%d] = %d, reference ec_verify says %d", names[c], i, v[i], want);
 			}
 			CHECK(v[5] == -1 && v[9] == -1, "corrupted items not flagged");
+			/* ---- ec_verify shim: one kernel launch per ECDSA signature, verdicts equal the reference's; other
+			 * schemes are forwarded to the reference's ec_verify (no GPU verification counted) */
+			for (int i = 0; i < 12; i++) {
+				unsigned long long v0 = gpu_vcount();
+				int want = ec_verify(sigs[i], sl[i], pk[i], msgs[i], ml[i], ECDSA, ht, NULL, 0);
+				int got = gpu_everify(sigs[i], sl[i], pk[i], msgs[i], ml[i], ECDSA, ht, NULL, 0);
+				CHECK(got == want, "%s ec_verify shim item %d: %d vs reference %d", names[c], i, got, want);
+				CHECK(gpu_vcount() == v0 + 1, "%s ec_verify shim did not run on the GPU", names[c]);
+			}
+			CHECK(gpu_everify(sigs[0], (u8)(sl[0] - 1), pk[0], msgs[0], ml[0], ECDSA, ht, NULL, 0) == -1, "short signature accepted");
+			{
+				ec_key_pair kq;
+				u8 sg[3 * 66];
+				u8 sgl = 0;
+				unsigned long long v0 = gpu_vcount();
+				CHECK(!ec_key_pair_gen(&kq, &params, ECSDSA), "ecsdsa keygen");
+				CHECK(!ec_get_sig_len(&params, ECSDSA, ht, &sgl), "siglen");
+				CHECK(!ec_sign(sg, sgl, &kq, msgs[0], ml[0], ECSDSA, ht, NULL, 0), "ecsdsa sign");
+				CHECK(gpu_everify(sg, sgl, &kq.pub_key, msgs[0], ml[0], ECSDSA, ht, NULL, 0) == 0, "forwarded ECSDSA verify failed");
+				sg[2] ^= 1;
+				CHECK(gpu_everify(sg, sgl, &kq.pub_key, msgs[0], ml[0], ECSDSA, ht, NULL, 0) == -1, "forwarded ECSDSA forgery accepted");
+				CHECK(gpu_vcount() == v0, "ECSDSA must be forwarded, not counted as a GPU verification");
+			}
+			/* ---- a public key that IS the point at infinity: the reference's ec_verify accepts the struct and goes on
+			 * with W' = u*G; shim and batch adapter must give the reference's verdict, whatever it is */
+			{
+				ec_pub_key kinf = kp[0].pub_key;
+				CHECK(!prj_pt_zero(&kinf.y), "zero key");
+				int want = ec_verify(sigs[0], sl[0], &kinf, msgs[0], ml[0], ECDSA, ht, NULL, 0);
+				int got = gpu_everify(sigs[0], sl[0], &kinf, msgs[0], ml[0], ECDSA, ht, NULL, 0);
+				CHECK(got == want, "%s key at infinity: shim %d vs reference %d", names[c], got, want);
+			}
 			/* the generic entry point still reports ECDSA batch as unsupported in the unmodified reference */
 			CHECK(ec_verify_batch(sp, sl, pk, mp, ml, NS, ECDSA, ht, NULL, NULL, NULL, NULL) == -1,
 			      "reference ec_verify_batch(ECDSA) unexpectedly supported");
@@ -238,6 +288,123 @@ static int run_direct(const char *dropin_path)
 	return failures != 0;
 }
 
+/* threads mode: the reference's functions are re-entrant; several host threads call the drop-in at once */
+typedef struct {
+	mul_fn mul;
+	const ec_params *params;
+	int id, bad;
+} thr_arg;
+
+static void *thr_main(void *p)
+{
+	thr_arg *a = (thr_arg *)p;
+	unsigned long long st = 0x1234567ULL * (unsigned long long)(a->id + 1);
+	for (int t = 0; t < 40; t++) {
+		u8 kb[66];
+		u8 ql = (u8)BYTECEIL(a->params->ec_gen_order_bitlen);
+		for (int j = 0; j < ql; j++) {
+			st = st * 6364136223846793005ULL + 1442695040888963407ULL;
+			kb[j] = (u8)(st >> 56);
+		}
+		nn k;
+		prj_pt o_ref, o_gpu;
+		int cmp = 1;
+		if (nn_init_from_buf(&k, kb, ql) || prj_pt_mul(&o_ref, &k, &a->params->ec_gen) || a->mul(&o_gpu, &k, &a->params->ec_gen) ||
+		    prj_pt_cmp(&o_ref, &o_gpu, &cmp) || cmp)
+			a->bad++;
+	}
+	return NULL;
+}
+
+static int run_threads(const char *dropin_path)
+{
+	void *h = dlopen(dropin_path, RTLD_NOW | RTLD_LOCAL);
+	if (!h) return 1;
+	mul_fn gpu_mul = (mul_fn)dlsym(h, "prj_pt_mul");
+	ec_params p1, p2;
+	CHECK(!load_params(&p1, "SECP256R1") && !load_params(&p2, "BRAINPOOLP256R1"), "params");
+	enum { NT = 8 };
+	pthread_t th[NT];
+	thr_arg args[NT];
+	for (int i = 0; i < NT; i++) {
+		args[i].mul = gpu_mul;
+		args[i].params = (i & 1) ? &p2 : &p1;
+		args[i].id = i;
+		args[i].bad = 0;
+		pthread_create(&th[i], NULL, thr_main, &args[i]);
+	}
+	for (int i = 0; i < NT; i++) {
+		pthread_join(th[i], NULL);
+		CHECK(args[i].bad == 0, "thread %d: %d wrong results", i, args[i].bad);
+	}
+	printf("threads: %d threads x 40 concurrent prj_pt_mul calls on two curves agree with the reference\n", NT);
+	return failures != 0;
+}
+
+/* bench mode: throughput of the reference-facing batch adapter on REAL ec_pub_key structs (one struct per item) */
+static double now_s(void)
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+static int run_bench(const char *dropin_path, const char *curve, u32 n)
+{
+	void *h = dlopen(dropin_path, RTLD_NOW | RTLD_LOCAL);
+	if (!h) return 1;
+	vbatch_fn gpu_vbatch = (vbatch_fn)dlsym(h, "eccb200_dropin_ecdsa_verify_batch");
+	verdicts_fn gpu_verdicts = (verdicts_fn)dlsym(h, "eccb200_dropin_last_verdicts");
+	ec_params params;
+	CHECK(!load_params(&params, curve), "params");
+	const u8 qlen = (u8)BYTECEIL(params.ec_gen_order_bitlen);
+	enum { POOL = 2048, ML = 32 };
+	static ec_key_pair kp[POOL];
+	static u8 psig[POOL][2 * 66], pmsg[POOL][ML];
+	for (int i = 0; i < POOL; i++) { /* signatures made by the reference */
+		CHECK(!ec_key_pair_gen(&kp[i], &params, ECDSA), "keygen");
+		for (int j = 0; j < ML; j++) pmsg[i][j] = rnd8();
+		CHECK(!ec_sign(psig[i], (u8)(2 * qlen), &kp[i], pmsg[i], ML, ECDSA, SHA256, NULL, 0), "sign");
+	}
+	/* n independent items: every item owns its ec_pub_key struct, signature and message bytes (tiled from the pool) */
+	ec_pub_key *keys = (ec_pub_key *)malloc((size_t)n * sizeof(ec_pub_key));
+	u8 *sigs = (u8 *)malloc((size_t)n * 2 * qlen), *msgs = (u8 *)malloc((size_t)n * ML);
+	const u8 **sp = malloc((size_t)n * sizeof(*sp)), **mp = malloc((size_t)n * sizeof(*mp));
+	const ec_pub_key **pk = malloc((size_t)n * sizeof(*pk));
+	u8 *sl = malloc(n);
+	u32 *ml = malloc((size_t)n * sizeof(u32));
+	signed char *v = malloc(n);
+	if (!keys || !sigs || !msgs || !sp || !mp || !pk || !sl || !ml || !v) return 1;
+	for (u32 i = 0; i < n; i++) {
+		keys[i] = kp[i % POOL].pub_key;
+		memcpy(sigs + (size_t)i * 2 * qlen, psig[i % POOL], 2 * qlen);
+		memcpy(msgs + (size_t)i * ML, pmsg[i % POOL], ML);
+		if (i % 64 == 13) sigs[(size_t)i * 2 * qlen + 7] ^= 2; /* 1/64 invalid */
+		sp[i] = sigs + (size_t)i * 2 * qlen;
+		mp[i] = msgs + (size_t)i * ML;
+		pk[i] = &keys[i];
+		sl[i] = (u8)(2 * qlen);
+		ml[i] = ML;
+	}
+	double best = 1e9;
+	for (int rep = 0; rep < 4; rep++) {
+		double t0 = now_s();
+		int r = gpu_vbatch(sp, sl, pk, mp, ml, n, ECDSA, SHA256, NULL, NULL, NULL, NULL);
+		double t = now_s() - t0;
+		CHECK(r == -1, "the batch contains invalid signatures");
+		if (rep > 0 && t < best) best = t; /* first call builds the comb table and the staging buffers */
+		printf("bench rep %d: %.4f s\n", rep, t);
+	}
+	CHECK(gpu_verdicts(v, n) == n, "verdicts");
+	u32 bad = 0;
+	for (u32 i = 0; i < n; i++) bad += (v[i] != ((i % 64 == 13) ? -1 : 0));
+	CHECK(bad == 0, "%u verdicts wrong", bad);
+	printf("DROPIN_BENCH {\"call\": \"eccb200_dropin_ecdsa_verify_batch\", \"curve\": \"%s\", \"items\": %u, "
+	       "\"seconds_best\": %.5f, \"verify_per_s\": %.1f, \"struct_bytes_per_key\": %u, \"wrong_verdicts\": %u}\n",
+	       curve, n, best, (double)n / best, (unsigned)sizeof(ec_pub_key), bad);
+	return failures != 0;
+}
+
 /* preload mode: the reference's own high-level code, with prj_pt_mul interposed by the GPU drop-in */
 static int run_preload(void)
 {
@@ -274,8 +441,13 @@ static int run_preload(void)
 		CHECK(!memcmp(sa, sb, plen), "%s: ECC-CDH secrets differ", names[c]);
 	}
 	unsigned long long used = calls() - c0;
-	printf("preload: %llu prj_pt_mul calls served by the GPU drop-in\n", used);
-	CHECK(used >= 8 * (6 * 4 + 4), "too few interposed calls (%llu): the reference did not go through the drop-in", used);
+	count_fn vcount = (count_fn)dlsym(RTLD_DEFAULT, "eccb200_dropin_verify_count");
+	unsigned long long verified = vcount ? vcount() : 0;
+	printf("preload: %llu prj_pt_mul calls and %llu ec_verify calls served by the GPU drop-in\n", used, verified);
+	/* per curve: 6 x (keygen + sign) + 2 + 2 ECC-CDH multiplications through prj_pt_mul; the 12 ec_verify calls are
+	 * whole-kernel verifications of the interposed ec_verify */
+	CHECK(used >= 8 * (6 * 2 + 4), "too few interposed calls (%llu): the reference did not go through the drop-in", used);
+	CHECK(verified >= 8 * 12, "ec_verify was not served by the drop-in (%llu)", verified);
 	return failures != 0;
 }
 
@@ -284,8 +456,10 @@ int main(int argc, char **argv)
 	int rc;
 	if (argc >= 2 && !strcmp(argv[1], "preload")) rc = run_preload();
 	else if (argc >= 3 && !strcmp(argv[1], "direct")) rc = run_direct(argv[2]);
+	else if (argc >= 3 && !strcmp(argv[1], "threads")) rc = run_threads(argv[2]);
+	else if (argc >= 5 && !strcmp(argv[1], "bench")) rc = run_bench(argv[2], argv[3], (u32)strtoul(argv[4], NULL, 10));
 	else {
-		printf("usage: %s direct <path to libecc_b200_dropin.so> | preload\n", argv[0]);
+		printf("usage: %s direct <dropin.so> | threads <dropin.so> | bench <dropin.so> <curve> <items> | preload\n", argv[0]);
 		return 2;
 	}
 	printf(rc ? "HARNESS FAILED (%d failures)\n" : "HARNESS OK (%d failures)\n", failures);

@@ -296,12 +296,17 @@ def test_full_size_ecdsa_verify_frp256v1():
     verdict vector must equal the by-construction expectation on the whole batch and the oracle on a sample."""
     import bench
     inp = bench.make_verify_inputs("FRP256V1", 1 << 20, rank=3)
-    got = engine("FRP256V1").ecdsa_verify_batch(inp["sigs"], inp["pubkeys"], inp["digests"], inp["hlen"])
+    n = 1 << 20
+    got = engine("FRP256V1").ecdsa_verify_batch(inp["sigs"], inp["pubkeys"], inp["digests_host"], inp["hlen"])
     assert (got == inp["expected"]).all()
-    assert (got[::16] == -1).all() and int((got == 0).sum()) == (1 << 20) - (1 << 16)
-    idx = rng(101).choice(1 << 20, size=1024, replace=False)
-    want = oracle_verify("FRP256V1", inp["sigs"][idx], inp["pubkeys"][idx], inp["digests"][idx], inp["hlen"])
+    assert (got[::16] == -1).all() and int((got == 0).sum()) == n - (1 << 16)
+    idx = rng(101).choice(n, size=1024, replace=False)
+    want = oracle_verify("FRP256V1", inp["sigs"][idx], inp["pubkeys"][idx], bench.sha256_rows(inp["msgs"][idx]), inp["hlen"])
     assert (got[idx] == want).all()
+    # the same batch as MESSAGES (what ec_verify takes): SHA-256 on the device, then the verification kernel
+    off = np.arange(n + 1, dtype=np.uint64) * bench.MSG_LEN
+    got_m = engine("FRP256V1").ecdsa_verify_msgs_batch_raw("SHA256", inp["sigs"], inp["pubkeys"], inp["msgs"], off)
+    assert (got_m == inp["expected"]).all()
 
 
 def test_full_size_secp384r1_fixed_base_properties():
