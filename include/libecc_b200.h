@@ -161,6 +161,11 @@ int eccb200_ecdsa_verify_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *
  * (pubkeys[i] ignored) — the reference's ec_verify accepts such an ec_pub_key and computes W' = u*G
  * (src/curves/prj_pt.c:1767-1775 gives v*infinity = infinity); -1 = rejected key.  For callers that hold
  * reference structs (the drop-in layer). */
+/* The same with the public keys in the reference's homogeneous projective form X || Y || Z (3*plen bytes each: what an
+ * ec_pub_key's y holds, Z != 1 in general): key import (prj_pt_import_from_buf's checks, src/curves/prj_pt.c:462-500)
+ * and the batched prj_pt_unique run on the device in front of the verification kernel, chunk by chunk. */
+int eccb200_ecdsa_verify_prj_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *sigs, const uint8_t *prj_pubkeys,
+				   const uint8_t *digests, uint32_t hlen, int8_t *verdict);
 int eccb200_ecdsa_verify_keystate_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys,
 					const int8_t *key_state, const uint8_t *digests, uint32_t hlen,
 					int8_t *verdict);
@@ -278,6 +283,11 @@ void eccb200_host_free(void *p);
  * out[i] = a[i]*b[i]*R^-1 mod p (which = 0) or mod q (which = 1), R = 2^(8*plen); inputs must be < modulus. */
 int eccb200_fp_mul_monty_batch(eccb200_ctx *ctx, int which, uint32_t n, const uint8_t *a, const uint8_t *b,
 			       uint8_t *out);
+
+/* The same pattern for FP_ADD / FP_SUB / FP_SQR_MONTY (src/fp/fp_montgomery.c:26,35,53): op 0 = a + b, 1 = a - b,
+ * 2 = a*a*R^-1 (b ignored), mod p (which = 0) or mod q (1). */
+int eccb200_fp_addsub_batch(eccb200_ctx *ctx, int which, int op, uint32_t n, const uint8_t *a, const uint8_t *b,
+			    uint8_t *out);
 
 /* Mod-q scalar preparation of ECDSA verification alone (nn_modinv / nn_mod_mul on the order q,
  * src/sig/ecdsa_common.c:777-791): out[i] = u || v, u = e*s^-1 mod q, v = r*s^-1 mod q, 2*qlen bytes big-endian.

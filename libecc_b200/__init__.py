@@ -36,6 +36,7 @@ ABI_SYMBOLS = [
     "eccb200_multi_create", "eccb200_multi_destroy", "eccb200_multi_device_count", "eccb200_multi_ctx",
     "eccb200_multi_prj_pt_mul_batch", "eccb200_multi_ecdsa_verify_batch",
     "eccb200_ecdsa_verify_msgs_batch_dev", "eccb200_copy_to_host", "eccb200_ecdsa_verify_keystate_batch",
+    "eccb200_fp_addsub_batch", "eccb200_ecdsa_verify_prj_batch",
 ]
 
 _lib = None
@@ -106,6 +107,8 @@ def load_library() -> ctypes.CDLL:
     lib.eccb200_multi_ecdsa_verify_batch.argtypes = [vp, u64, u8p, u8p, u8p, u32, i8p]
     lib.eccb200_ecdsa_verify_msgs_batch_dev.argtypes = [vp, ctypes.c_int, u32, u8p, u8p, u8p, vp, u8p, i8p, vp]
     lib.eccb200_copy_to_host.argtypes = [vp, vp, vp, ctypes.c_size_t]
+    lib.eccb200_fp_addsub_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, u32, u8p, u8p, u8p]
+    lib.eccb200_ecdsa_verify_prj_batch.argtypes = [vp, u32, u8p, u8p, u8p, u32, i8p]
     lib.eccb200_ecdsa_verify_keystate_batch.argtypes = [vp, u32, u8p, u8p, i8p, u8p, u32, i8p]
     lib.eccb200_host_alloc.argtypes = [ctypes.c_size_t]
     lib.eccb200_host_alloc.restype = ctypes.c_void_p
@@ -236,6 +239,17 @@ class Engine:
         self._check(self.lib.eccb200_ecdsa_verify_batch(
             self._h, n, sg.ctypes.data, pk.ctypes.data, dg.ctypes.data, hlen, verdict.ctypes.data),
             "eccb200_ecdsa_verify_batch")
+        return verdict
+
+    def ecdsa_verify_prj_batch(self, sigs, prj_pubkeys, digests, hlen: int) -> np.ndarray:
+        """Public keys as X || Y || Z (homogeneous projective, 3*plen bytes each)."""
+        sg = _as_u8(sigs)
+        n = sg.size // (2 * self.qlen)
+        pk = _as_u8(prj_pubkeys, n * 3 * self.plen)
+        dg = _as_u8(digests, n * hlen)
+        verdict = np.zeros(n, dtype=np.int8)
+        self._check(self.lib.eccb200_ecdsa_verify_prj_batch(self._h, n, sg.ctypes.data, pk.ctypes.data, dg.ctypes.data,
+                                                            hlen, verdict.ctypes.data), "eccb200_ecdsa_verify_prj_batch")
         return verdict
 
     def ecdsa_sign_batch(self, privkeys, nonces, digests, hlen: int) -> Tuple[np.ndarray, np.ndarray]:
@@ -432,6 +446,16 @@ class Engine:
         out = np.zeros((n, self.plen), dtype=np.uint8)
         self._check(self.lib.eccb200_fp_mul_monty_batch(self._h, which, n, x.ctypes.data, y.ctypes.data,
                                                         out.ctypes.data), "eccb200_fp_mul_monty_batch")
+        return out
+
+    def fp_addsub_batch(self, a, b, op: int, which: int = 0) -> np.ndarray:
+        """op 0 = a + b, 1 = a - b, 2 = a * a * R^-1 (mod p for which = 0, mod q for 1)."""
+        x = _as_u8(a)
+        n = x.size // self.plen
+        y = _as_u8(b, n * self.plen)
+        out = np.zeros((n, self.plen), dtype=np.uint8)
+        self._check(self.lib.eccb200_fp_addsub_batch(self._h, which, op, n, x.ctypes.data, y.ctypes.data,
+                                                     out.ctypes.data), "eccb200_fp_addsub_batch")
         return out
 
     # ---- device-buffer API (torch uint8/int8 CUDA tensors; asynchronous on torch's current stream) ---------

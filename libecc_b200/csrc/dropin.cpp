@@ -457,6 +457,26 @@ extern "C" int prj_pt_mul(eccb200_prj_pt *out, const eccb200_nn *m, const eccb20
  */
 typedef int (*mul_sig)(eccb200_prj_pt *, const eccb200_nn *, const eccb200_prj_pt *);
 
+/* Is `fn` defined by THIS shared object?  (Comparing with &our_function is not enough: a reference to an exported
+ * function of a -fPIC library is itself bound through the global lookup scope, i.e. possibly to the reference's.) */
+static void self_anchor() {}
+static bool defined_here(void *fn)
+{
+	Dl_info a, b;
+	if (!fn || !dladdr(fn, &a) || !dladdr((void *)&self_anchor, &b)) return false;
+	return a.dli_fbase == b.dli_fbase;
+}
+
+/* the next definition of `name` after this library: RTLD_NEXT when preloaded / linked ahead, else (library opened
+ * privately with dlopen) whatever the global scope holds, as long as it is not our own */
+static void *next_definition(const char *name)
+{
+	void *f = dlsym(RTLD_NEXT, name);
+	if (f && !defined_here(f)) return f;
+	f = dlsym(RTLD_DEFAULT, name);
+	return (f && !defined_here(f)) ? f : nullptr;
+}
+
 extern "C" int prj_pt_mul_blind(eccb200_prj_pt *out, const eccb200_nn *m, const eccb200_prj_pt *in);
 
 static bool blind_on_gpu()
@@ -475,14 +495,7 @@ extern "C" void eccb200_dropin_allow_nonct_blind(int on) { g_blind_on_gpu.store(
 extern "C" int prj_pt_mul_blind(eccb200_prj_pt *out, const eccb200_nn *m, const eccb200_prj_pt *in)
 {
 	if (blind_on_gpu()) return mul_batch(out, m, in, 1, nullptr);
-	static mul_sig next = [] {
-		mul_sig f = (mul_sig)dlsym(RTLD_NEXT, "prj_pt_mul_blind");
-		if (!f) { /* dlopen'ed privately: look in the global scope, but never at ourselves */
-			mul_sig g = (mul_sig)dlsym(RTLD_DEFAULT, "prj_pt_mul_blind");
-			if (g && g != (mul_sig)&prj_pt_mul_blind) f = g;
-		}
-		return f;
-	}();
+	static mul_sig next = (mul_sig)next_definition("prj_pt_mul_blind");
 	return next ? next(out, m, in) : -1;
 }
 
@@ -539,12 +552,13 @@ static int verify_batch_common(bool fs, const uint8_t **s, const uint8_t *s_len,
 	const size_t plen = (size_t)ci->plen, qlen = (size_t)ci->qlen;
 	const size_t siglen = fs ? 2 * plen + qlen : 2 * qlen;
 	/* page-locked staging owned by the slot: the engine's pipeline DMAs straight out of / into it */
-	uint8_t *sigs = engine.slot->st[0].get(num * siglen), *pubs = engine.slot->st[1].get(num * 2 * plen),
+	/* ECDSA: the keys travel in the reference's projective form (X || Y || Z) and are normalised on the device in front
+	 * of the verification kernel; ECFSDSA keeps affine keys (Z != 1 ones go through eccb200_prj_pt_unique_batch) */
+	const size_t keylen = fs ? 2 * plen : 3 * plen;
+	uint8_t *sigs = engine.slot->st[0].get(num * siglen), *pubs = engine.slot->st[1].get(num * keylen),
 		*dig = engine.slot->st[2].get(num * (size_t)hlen);
 	int8_t *verdict = (int8_t *)engine.slot->st[3].get(num);
-	int8_t *kstate = (int8_t *)engine.slot->st[4].get(num);
-	if (!sigs || !pubs || !dig || !verdict || !kstate) return -1;
-	memset(kstate, 0, num);
+	if (!sigs || !pubs || !dig || !verdict) return -1;
 	std::vector<uint8_t> ok(num, 0);
 	std::atomic<int> mixed{ 0 };
 	std::vector<std::vector<uint32_t>> prj_parts(64);
@@ -553,7 +567,7 @@ static int verify_batch_common(bool fs, const uint8_t **s, const uint8_t *s_len,
 		std::vector<uint32_t> &prj = prj_parts[t];
 		for (uint32_t i = lo; i < hi; i++) {
 			memset(&sigs[i * siglen], 0, siglen);
-			memset(&pubs[i * 2 * plen], 0, 2 * plen);
+			memset(&pubs[i * keylen], 0, keylen);
 			memset(&dig[i * (size_t)hlen], 0, hlen);
 			const eccb200_ec_pub_key *pk = pub_keys[i];
 			if (!pk || pk->magic != kPubKeyMagic || pk->key_type != sig_type || !pt_ok(&pk->y)) continue;
@@ -570,7 +584,11 @@ static int verify_batch_common(bool fs, const uint8_t **s, const uint8_t *s_len,
 			uint32_t ilens[2] = { fs ? (uint32_t)(2 * plen) : m_len[i], fs ? m_len[i] : 0 };
 			if (hm->hfunc_scattered(inputs, ilens, &dig[i * (size_t)hlen])) continue;
 			const eccb200_prj_pt *y = &pk->y;
-			if (fp_is_small(&y->Z, 1)) {
+			if (!fs) {
+				fp_to_be(&pubs[i * keylen], &y->X, pl);
+				fp_to_be(&pubs[i * keylen + plen], &y->Y, pl);
+				fp_to_be(&pubs[i * keylen + 2 * plen], &y->Z, pl);
+			} else if (fp_is_small(&y->Z, 1)) {
 				fp_to_be(&pubs[i * 2 * plen], &y->X, pl);
 				fp_to_be(&pubs[i * 2 * plen + plen], &y->Y, pl);
 			} else {
@@ -595,14 +613,14 @@ static int verify_batch_common(bool fs, const uint8_t **s, const uint8_t *s_len,
 		for (size_t k = 0; k < prj_idx.size(); k++) {
 			uint32_t i = prj_idx[k];
 			if (st[k] == 0) memcpy(&pubs[i * 2 * plen], &ab[k * 2 * plen], 2 * plen);
-			else if (st[k] == 1 && !fs) kstate[i] = 1; /* key at infinity: ECDSA's ec_verify goes on with W' = u*G */
 			else ok[i] = 0; /* off the curve.  ECFSDSA with a key at infinity is rejected too — a documented divergence:
-					 * the reference would accept it iff s*G == r */
+					 * the reference would accept it iff s*G == r.  (ECDSA keys are normalised on the
+					 * device, where a key at infinity continues with W' = u*G like the reference's ec_verify.) */
 		}
 	}
 	memset(verdict, 0xff, num);
 	if (fs ? eccb200_ecfsdsa_verify_batch(eng, num, sigs, pubs, dig, hlen, verdict)
-	       : eccb200_ecdsa_verify_keystate_batch(eng, num, sigs, pubs, kstate, dig, hlen, verdict))
+	       : eccb200_ecdsa_verify_prj_batch(eng, num, sigs, pubs, dig, hlen, verdict))
 		return -1;
 	g_verifies += num;
 	int all = 0;
@@ -654,14 +672,7 @@ extern "C" int ec_verify(const uint8_t *sig, uint8_t siglen, const eccb200_ec_pu
 
 static ec_verify_sig next_ec_verify()
 {
-	static ec_verify_sig next = [] {
-		ec_verify_sig f = (ec_verify_sig)dlsym(RTLD_NEXT, "ec_verify");
-		if (!f) {
-			ec_verify_sig g = (ec_verify_sig)dlsym(RTLD_DEFAULT, "ec_verify");
-			if (g && g != (ec_verify_sig)&ec_verify) f = g;
-		}
-		return f;
-	}();
+	static ec_verify_sig next = (ec_verify_sig)next_definition("ec_verify");
 	return next;
 }
 

@@ -66,6 +66,7 @@ struct eccb200_ctx {
 	uint32_t *stage_jac[kStages] = {};
 	uint32_t *stage_prefix[kStages] = {};
 	uint8_t *stage_aff[kStages] = {};
+	uint8_t *stage_state[kStages] = {}; /* [chunk] per-key states of the projective-key verification */
 	uint64_t launches = 0;
 	/* The device-pointer entry points share ONE scratch set (jac / prefix / aff).  Calls may come in on different
 	 * streams: every call first makes its stream wait for scratch_done (recorded behind the previous call's last
@@ -272,6 +273,7 @@ extern "C" void eccb200_ctx_destroy(eccb200_ctx *ctx)
 		if (ctx->stage_jac[s]) cudaFree(ctx->stage_jac[s]);
 		if (ctx->stage_prefix[s]) cudaFree(ctx->stage_prefix[s]);
 		if (ctx->stage_aff[s]) cudaFree(ctx->stage_aff[s]);
+		if (ctx->stage_state[s]) cudaFree(ctx->stage_state[s]);
 	}
 	if (ctx->ev_ready)
 		for (int c = 0; c < eccb200_ctx::kProfCalls; c++)
@@ -616,6 +618,7 @@ static int ensure_stages(eccb200_ctx *ctx, size_t in_bytes, size_t out_bytes)
 			CUDA_OK(cudaMalloc(&ctx->stage_jac[s], (size_t)ctx->chunk * 3 * ctx->N * sizeof(uint32_t)));
 			CUDA_OK(cudaMalloc(&ctx->stage_prefix[s], (size_t)ctx->chunk * ctx->N * sizeof(uint32_t)));
 			CUDA_OK(cudaMalloc(&ctx->stage_aff[s], (size_t)ctx->chunk * 2 * ctx->plen));
+			CUDA_OK(cudaMalloc(&ctx->stage_state[s], (size_t)ctx->chunk));
 		}
 	}
 	ctx->stage_in_bytes = ib;
@@ -882,6 +885,41 @@ extern "C" int eccb200_ecdsa_verify_keystate_batch(eccb200_ctx *ctx, uint32_t n,
 		const uint8_t *d = ctx->d_in[s];
 		return verify_dev(ctx, cnt, d, d + (size_t)cnt * sg, d + (size_t)cnt * (sg + pk + 1), hlen,
 				  (int8_t *)ctx->d_out[s], ctx->streams[s], (const int8_t *)(d + (size_t)cnt * (sg + pk)));
+	});
+}
+
+/*
+ * ECDSA verification with the public keys in the reference's HOMOGENEOUS PROJECTIVE form (X || Y || Z, what an
+ * ec_pub_key holds: the output of a prj_pt_mul, Z != 1 in general).  Per pipeline chunk: key import + batched
+ * prj_pt_unique on the device (k_prj_load + K4 mode 2, one inversion per CTA) feeding the verification kernel its
+ * affine keys and key states — the keys never go back to the host.
+ */
+extern "C" int eccb200_ecdsa_verify_prj_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *sigs,
+					      const uint8_t *prj_pubkeys, const uint8_t *digests, uint32_t hlen,
+					      int8_t *verdict)
+{
+	if (!ctx || (n && (!sigs || !prj_pubkeys || !digests || !verdict))) return fail("null argument");
+	if (hlen == 0 || hlen > 128) return fail("bad digest length");
+	if (n == 0) return 0;
+	const size_t sg = 2 * (size_t)ctx->qlen, pk = 3 * (size_t)ctx->plen;
+	std::vector<HostCol> in = { { (uint8_t *)sigs, sg, false }, { (uint8_t *)prj_pubkeys, pk, false },
+				    { (uint8_t *)digests, hlen, false } };
+	std::vector<HostCol> outc = { { (uint8_t *)verdict, 1, false } };
+	return run_pipeline(ctx, n, in, outc, [&](int s, uint32_t cnt) {
+		const uint8_t *d = ctx->d_in[s];
+		cudaStream_t st = ctx->streams[s];
+		/* the stage's affine scratch receives the normalised keys, its state scratch the key states (0 / 1 / -1) */
+		int8_t *state = (int8_t *)ctx->stage_state[s];
+		int rc = dispatch(ctx->curve_id, [&](auto c) {
+			typedef decltype(c) C;
+			LaunchMisc<C>::prj_unique(affine_grid(ctx, cnt), cnt, d + (size_t)cnt * sg, ctx->stage_jac[s],
+						  ctx->stage_prefix[s], ctx->stage_aff[s], state, st);
+			ctx->launches += 2;
+			return 0;
+		});
+		if (rc) return rc;
+		return verify_dev(ctx, cnt, d, ctx->stage_aff[s], d + (size_t)cnt * (sg + pk), hlen, (int8_t *)ctx->d_out[s], st,
+				  state);
 	});
 }
 
@@ -1407,6 +1445,34 @@ extern "C" int eccb200_fp_mul_monty_batch(eccb200_ctx *ctx, int which, uint32_t 
 			return 0;
 		});
 	} while (0);
+	cudaFree(d);
+	return rc;
+}
+
+/* fp_add_monty / fp_sub_monty / fp_sqr_monty unit entry point (op 0 / 1 / 2), mod p (which = 0) or mod q (1) */
+extern "C" int eccb200_fp_addsub_batch(eccb200_ctx *ctx, int which, int op, uint32_t n, const uint8_t *a,
+				       const uint8_t *b, uint8_t *out)
+{
+	if (!ctx || (n && (!a || !b || !out))) return fail("null argument");
+	if (op < 0 || op > 2) return fail("op must be 0 (add), 1 (sub) or 2 (sqr)");
+	if (n == 0) return 0;
+	CUDA_OK(cudaSetDevice(ctx->device));
+	size_t bytes = (size_t)n * ctx->plen;
+	uint8_t *d = nullptr;
+	CUDA_OK(cudaMalloc(&d, 3 * bytes));
+	int rc = 0;
+	if (cudaMemcpy(d, a, bytes, cudaMemcpyHostToDevice) != cudaSuccess ||
+	    cudaMemcpy(d + bytes, b, bytes, cudaMemcpyHostToDevice) != cudaSuccess)
+		rc = fail("H2D copy failed");
+	if (!rc)
+		rc = dispatch(ctx->curve_id, [&](auto c) {
+			typedef decltype(c) C;
+			LaunchMisc<C>::fp_addsub(which, op, n, d, d + bytes, d + 2 * bytes, 0);
+			ctx->launches += 1;
+			CUDA_OK(cudaGetLastError());
+			CUDA_OK(cudaMemcpy(out, d + 2 * bytes, bytes, cudaMemcpyDeviceToHost));
+			return 0;
+		});
 	cudaFree(d);
 	return rc;
 }

@@ -964,6 +964,24 @@ __global__ void k_fp_mul_monty(uint32_t n, const uint8_t *__restrict__ a, const 
 	store_wire<N, FT::BYTES>(out + (size_t)idx * FT::BYTES, z);
 }
 
+/* fp_add_monty / fp_sub_monty / fp_sqr_monty (fp/fp_montgomery.c:26,35,53) as direct unit kernels of the PTX back
+ * end: op 0 = a + b, 1 = a - b, 2 = a * a * R^-1 (b unused); operands < modulus. */
+template <class FT>
+__global__ void k_fp_addsub(uint32_t n, int op, const uint8_t *__restrict__ a, const uint8_t *__restrict__ b,
+			    uint8_t *__restrict__ out)
+{
+	constexpr int N = FT::N;
+	uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= n) return;
+	Fe<N> x, y, z;
+	load_wire<N, FT::BYTES>(x, a + (size_t)idx * FT::BYTES);
+	load_wire<N, FT::BYTES>(y, b + (size_t)idx * FT::BYTES);
+	if (op == 0) Field<FT>::add(z, x, y);
+	else if (op == 1) Field<FT>::sub(z, x, y);
+	else Field<FT>::sqr(z, x);
+	store_wire<N, FT::BYTES>(out + (size_t)idx * FT::BYTES, z);
+}
+
 /*
  * Layout experiment: the SAME Montgomery product with the N = 8 words of an element striped across
  * 8 lanes (4 elements per warp) and every cross-word carry / broadcast done with __shfl_sync, as the north star
@@ -1119,6 +1137,8 @@ template <class C> struct LaunchMisc {
 				const uint8_t *digests, uint32_t hlen, const uint8_t *kG_aff, uint32_t *prefix,
 				uint8_t *sigs, int8_t *status, cudaStream_t st);
 	static void fp_mul(int which, uint32_t n, const uint8_t *a, const uint8_t *b, uint8_t *out, cudaStream_t st);
+	static void fp_addsub(int which, int op, uint32_t n, const uint8_t *a, const uint8_t *b, uint8_t *out,
+			      cudaStream_t st);
 	static void scalar_below_order(uint32_t n, const uint8_t *scalars, int8_t *state, cudaStream_t st);
 	static void fp_mul_chain(int striped, uint32_t n, const uint8_t *a, const uint8_t *b, uint8_t *out, int iters,
 				 cudaStream_t st);
@@ -1217,6 +1237,18 @@ void LaunchMisc<C>::fp_mul(int which, uint32_t n, const uint8_t *a, const uint8_
 		k_fp_mul_monty<typename C::Fp><<<grid_for(n), kThreads, 0, st>>>(n, a, b, out);
 	else
 		k_fp_mul_monty<typename C::Fq><<<grid_for(n), kThreads, 0, st>>>(n, a, b, out);
+}
+#endif
+
+#if defined(ECC_TU_MISC)
+template <class C>
+void LaunchMisc<C>::fp_addsub(int which, int op, uint32_t n, const uint8_t *a, const uint8_t *b, uint8_t *out,
+			      cudaStream_t st)
+{
+	if (which == 0)
+		k_fp_addsub<typename C::Fp><<<grid_for(n), kThreads, 0, st>>>(n, op, a, b, out);
+	else
+		k_fp_addsub<typename C::Fq><<<grid_for(n), kThreads, 0, st>>>(n, op, a, b, out);
 }
 #endif
 

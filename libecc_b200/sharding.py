@@ -93,6 +93,7 @@ class PeerGather:
                 if r not in self.peer:
                     self.peer[r] = eng.ipc_open(handles[r])
         self.step_no = 0
+        self._dst = {}
         dist.barrier(group=group)            # every mapping exists before anybody stores
 
     def step(self, p_scalars: int, p_points, p_out: int, p_status: int, stream: int):
@@ -101,9 +102,11 @@ class PeerGather:
         c = self.step_no + 1
         b = self.step_no % self.nbuf
         L = self.layout
-        dst_out = [self.peer[d] + slot_offset(L, b, self.rank) for d in self.dests]
-        dst_st = [p + L["status_offset"] for p in dst_out]
-        dst_flag = [self.peer[d] + L["flags"] + 4 * self.rank for d in self.dests]
+        if b not in self._dst:       # pointer lists per buffer, computed once
+            out = [self.peer[d] + slot_offset(L, b, self.rank) for d in self.dests]
+            self._dst[b] = (out, [p + L["status_offset"] for p in out],
+                            [self.peer[d] + L["flags"] + 4 * self.rank for d in self.dests])
+        dst_out, dst_st, dst_flag = self._dst[b]
         need_ack = c - self.nbuf                     # the step that last used this buffer must have been consumed
         if need_ack >= 1:
             wait_ptr, wait_cnt = self._ack_wait_ptr()

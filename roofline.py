@@ -30,9 +30,10 @@ def work_per_item(workload: str, comb_window: int):
     nib = (QBITS[curve] + 3) // 4
     m_fixed = 10 * (nwin - 1) + 2                               # extended-Jacobian mixed add 8M+2S per window (the
     #                                                             first window is a copy) + 2M back to Jacobian
-    fermat = nib * 5 + 14                                       # 4 sqr + 1 mul per nibble of the exponent + table
-    cta_inv = 16 + fermat / 4.0                                 # CTA-wide inversion per thread: 2 scans (14) + 2, and
-    #                                                             one Fermat chain run by one of the CTA's four warps
+    cta_inv = 16 + 2 / 4.0                                      # CTA-wide inversion per thread: 2 scans (14) + 2; the
+    #                                                             inversion itself (safegcd division steps, run by one
+    #                                                             of the CTA's four warps) costs two field products and
+    #                                                             ~750 division steps of 32-bit ALU work, not charged
     # variable base: 8-entry table (6 mixed adds + 1 doubling + the abandoned add that detects it), made affine with
     # one shared inversion (6 prefix + 12 back-substitution + 7 x 4 conversion products), 4 doublings per digit
     # (8 products each) and a mixed addition for 15 of 16 digits

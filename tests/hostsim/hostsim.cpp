@@ -163,6 +163,32 @@ int hostsim_fp_op(int curve_id, int op, uint32_t n, const uint8_t *a, const uint
 	});
 }
 
+/* out = a^-1 mod p (which = 0) or mod q (1), plain integers in and out, through Field::inv (safegcd, fermat = 0) or
+ * Field::inv_fermat (1) */
+int hostsim_fp_inv(int curve_id, int which, int fermat, uint32_t n, const uint8_t *a, uint8_t *out)
+{
+	return dispatch(curve_id, [&](auto c) {
+		typedef decltype(c) C;
+		constexpr int N = C::N;
+		auto run = [&](auto ftag) {
+			typedef decltype(ftag) FT;
+			typedef Field<FT> F;
+			for (uint32_t i = 0; i < n; i++) {
+				Fe<N> x, xm, zi, z;
+				load_be<N>(x, a + (size_t)i * FT::BYTES, FT::BYTES);
+				F::to_mont(xm, x);
+				if (fermat) F::inv_fermat(zi, xm);
+				else F::inv(zi, xm);
+				F::from_mont(z, zi);
+				store_be<N>(out + (size_t)i * FT::BYTES, z, FT::BYTES);
+			}
+		};
+		if (which == 0) run(typename C::Fp());
+		else run(typename C::Fq());
+		return 0;
+	});
+}
+
 /* same contract as eccb200_prj_pt_mul_batch; w = comb window used for the fixed-base path */
 int hostsim_prj_pt_mul_batch(int curve_id, int w, uint32_t n, const uint8_t *scalars, const uint8_t *points,
 			     uint8_t *out, int8_t *status)

@@ -36,6 +36,11 @@ def test_fp_mul_monty_against_integers(curve):
         rinv = pow(1 << (64 * ((PRIME[curve].bit_length() + 63) // 64)), -1, mod)  # the reference's R
         got = [int.from_bytes(o.tobytes(), "big") for o in out]
         assert got == [x * y * rinv % mod for x, y in zip(a, b)]
+        # FP_ADD / FP_SUB / FP_SQR_MONTY through their own unit kernel (the PTX add / sub / dedicated squaring)
+        ints = lambda arr: [int.from_bytes(o.tobytes(), "big") for o in arr]
+        assert ints(eng.fp_addsub_batch(be(a, plen), be(b, plen), 0, which)) == [(x + y) % mod for x, y in zip(a, b)]
+        assert ints(eng.fp_addsub_batch(be(a, plen), be(b, plen), 1, which)) == [(x - y) % mod for x, y in zip(a, b)]
+        assert ints(eng.fp_addsub_batch(be(a, plen), be(b, plen), 2, which)) == [x * x * rinv % mod for x in a]
 
 
 @pytest.mark.parametrize("curve", ["SECP256R1", "SECP384R1", "SECP521R1", "SECP224R1", "SECP192R1"])
