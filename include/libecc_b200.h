@@ -233,6 +233,19 @@ int eccb200_ecfsdsa_verify_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t
 				     const uint8_t *d_digests, uint32_t hlen, int8_t *d_verdict, void *stream);
 
 /*
+ * BIP0340 (Schnorr over x-only keys) verification, per item like ec_verify(…, BIP0340, …)
+ * (src/sig/bip0340.c:383-577): sigs [n][plen + qlen] = r || s with r a field element < p and s < q; pubkeys affine
+ * x || y as for ECDSA (the kernel lifts the key to its even-y representative, :540-545); digests[i] = the tagged hash
+ * H(H("BIP0340/challenge") || H("BIP0340/challenge") || r_i || x(Y_i) || m_i) computed by the host with src/hash (the
+ * whole digest is reduced mod q).  The same comb + signed-window kernel as ECDSA (SCHEME = 2), plus one shared
+ * inversion for the affine W' (the scheme tests the parity of y(W')).  verdict 0 / -1.
+ */
+int eccb200_bip0340_verify_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys,
+				 const uint8_t *digests, uint32_t hlen, int8_t *verdict);
+int eccb200_bip0340_verify_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_sigs, const uint8_t *d_pubkeys,
+				     const uint8_t *d_digests, uint32_t hlen, int8_t *d_verdict, void *stream);
+
+/*
  * The reference's structured key / signature records, batched.  `alg` is the reference's
  * ec_alg_type (ECDSA = 1, DECDSA = 14; src/lib_ecc_types.h:22-), `hash_type` its hash_alg_type; the third header byte
  * is the context's curve id.

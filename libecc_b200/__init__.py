@@ -36,7 +36,8 @@ ABI_SYMBOLS = [
     "eccb200_multi_create", "eccb200_multi_destroy", "eccb200_multi_device_count", "eccb200_multi_ctx",
     "eccb200_multi_prj_pt_mul_batch", "eccb200_multi_ecdsa_verify_batch",
     "eccb200_ecdsa_verify_msgs_batch_dev", "eccb200_copy_to_host", "eccb200_ecdsa_verify_keystate_batch",
-    "eccb200_fp_addsub_batch", "eccb200_ecdsa_verify_prj_batch",
+    "eccb200_fp_addsub_batch", "eccb200_ecdsa_verify_prj_batch", "eccb200_bip0340_verify_batch",
+    "eccb200_bip0340_verify_batch_dev",
 ]
 
 _lib = None
@@ -109,6 +110,8 @@ def load_library() -> ctypes.CDLL:
     lib.eccb200_copy_to_host.argtypes = [vp, vp, vp, ctypes.c_size_t]
     lib.eccb200_fp_addsub_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, u32, u8p, u8p, u8p]
     lib.eccb200_ecdsa_verify_prj_batch.argtypes = [vp, u32, u8p, u8p, u8p, u32, i8p]
+    lib.eccb200_bip0340_verify_batch.argtypes = [vp, u32, u8p, u8p, u8p, u32, i8p]
+    lib.eccb200_bip0340_verify_batch_dev.argtypes = [vp, u32, u8p, u8p, u8p, u32, i8p, vp]
     lib.eccb200_ecdsa_verify_keystate_batch.argtypes = [vp, u32, u8p, u8p, i8p, u8p, u32, i8p]
     lib.eccb200_host_alloc.argtypes = [ctypes.c_size_t]
     lib.eccb200_host_alloc.restype = ctypes.c_void_p
@@ -351,6 +354,17 @@ class Engine:
         verdict = np.zeros(n, dtype=np.int8)
         self._check(self.lib.eccb200_ecfsdsa_verify_batch(self._h, n, sg.ctypes.data, pk.ctypes.data, dg.ctypes.data,
                                                           hlen, verdict.ctypes.data), "eccb200_ecfsdsa_verify_batch")
+        return verdict
+
+    def bip0340_verify_batch(self, sigs, pubkeys, digests, hlen: int) -> np.ndarray:
+        """sigs [n][plen + qlen] = r || s; digests[i] = tagged hash of r_i || x(Y_i) || m_i."""
+        sg = _as_u8(sigs)
+        n = sg.size // (self.plen + self.qlen)
+        pk = _as_u8(pubkeys, n * 2 * self.plen)
+        dg = _as_u8(digests, n * hlen)
+        verdict = np.zeros(n, dtype=np.int8)
+        self._check(self.lib.eccb200_bip0340_verify_batch(self._h, n, sg.ctypes.data, pk.ctypes.data, dg.ctypes.data,
+                                                          hlen, verdict.ctypes.data), "eccb200_bip0340_verify_batch")
         return verdict
 
     # ---- the reference's structured key / signature records (include/libecc_b200.h)

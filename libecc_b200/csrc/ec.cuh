@@ -805,6 +805,40 @@ ECC_HD int ecfsdsa_verify_tail(const Aff<C> &R, const Fe<C::N> &s, const Fe<C::N
 	return ok ? 0 : 3;
 }
 
+/* ------------------------------------------------------------------------------------------ BIP0340 (§8f.4) */
+
+/*
+ * _bip0340_verify_finalize (sig/bip0340.c:497-577) after the init checks: W' = sG + (-e)Y' with Y' the public key
+ * lifted to an even y (:540-545; the caller passes Y already lifted, Montgomery form), reject infinity (:555-556),
+ * reject an odd y(W') (:559-560), accept iff x(W') == r (:563-564).  Unlike ECDSA / ECFSDSA the comparison needs the
+ * affine representative (the parity of y), so W' is normalised with one more inversion — `invert`, a CTA-wide one in
+ * the kernel, which every thread must call: rejected items walk the same code on dummy values.
+ * r: plain integer < p.  0 valid, 2 infinity, 3 mismatch / odd y.
+ */
+template <class C, class Inv>
+ECC_HD int bip0340_verify_tail(const Fe<C::N> &r, const Fe<C::N> &s, const Fe<C::N> &e_neg, const Aff<C> &Y,
+			       const uint32_t *__restrict__ table, int w, const Inv &invert)
+{
+	typedef Field<typename C::Fp> F;
+	Jac<C> sG, W;
+	comb_mul<C>(sG, s, table, w);                   /* s may be 0: the comb then returns infinity (:537) */
+	window_mul<C>(W, e_neg, Y, &sG, invert);
+	const bool inf = EC<C>::is_inf(W);
+	Fe<C::N> z, zi, zi2, zi3, x, y, t;
+	z = W.Z;
+	if (inf) F::set_one(z);
+	invert(zi, z);
+	F::sqr(zi2, zi);
+	F::mul(zi3, zi2, zi);
+	F::mul(t, W.X, zi2);
+	F::from_mont(x, t);
+	F::mul(t, W.Y, zi3);
+	F::from_mont(y, t);
+	if (inf) return 2;
+	if (y.w[0] & 1u) return 3;
+	return F::eq(x, r) ? 0 : 3;
+}
+
 /* r, s in [1, q-1]?  (__ecdsa_verify_init, sig/ecdsa_common.c:653-658) */
 template <class C> ECC_HD bool ecdsa_rs_in_range(const Fe<C::N> &r, const Fe<C::N> &s)
 {

@@ -594,6 +594,30 @@ extern "C" int eccb200_ecfsdsa_verify_batch_dev(eccb200_ctx *ctx, uint32_t n, co
 	return ecfsdsa_dev(ctx, n, d_sigs, d_pubkeys, d_digests, hlen, d_verdict, (cudaStream_t)stream);
 }
 
+static int bip0340_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_sigs, const uint8_t *d_pubkeys,
+		       const uint8_t *d_digests, uint32_t hlen, int8_t *d_verdict, cudaStream_t st)
+{
+	if (n == 0) return 0;
+	return dispatch(ctx->curve_id, [&](auto c) {
+		typedef decltype(c) C;
+		LaunchVerify<C>::bip0340(n, d_sigs, d_pubkeys, d_digests, hlen, ctx->table, ctx->w, d_verdict, st);
+		ctx->launches += 1;
+		CUDA_OK(cudaGetLastError());
+		return 0;
+	});
+}
+
+extern "C" int eccb200_bip0340_verify_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_sigs,
+						  const uint8_t *d_pubkeys, const uint8_t *d_digests, uint32_t hlen,
+						  int8_t *d_verdict, void *stream)
+{
+	if (!ctx || (n && (!d_sigs || !d_pubkeys || !d_digests || !d_verdict))) return fail("null argument");
+	if (hlen == 0 || hlen > 128) return fail("bad digest length");
+	if (misaligned16(ctx, { d_sigs, d_pubkeys })) return fail(kAlignMsg);
+	CUDA_OK(cudaSetDevice(ctx->device));
+	return bip0340_dev(ctx, n, d_sigs, d_pubkeys, d_digests, hlen, d_verdict, (cudaStream_t)stream);
+}
+
 /* ------------------------------------------------------------------------------------------ host-pointer API */
 
 static int ensure_stages(eccb200_ctx *ctx, size_t in_bytes, size_t out_bytes)
@@ -937,6 +961,23 @@ extern "C" int eccb200_ecfsdsa_verify_batch(eccb200_ctx *ctx, uint32_t n, const 
 	return run_pipeline(ctx, n, in, outc, [&](int s, uint32_t cnt) {
 		const uint8_t *d = ctx->d_in[s];
 		return ecfsdsa_dev(ctx, cnt, d + (size_t)cnt * pk, d, d + (size_t)cnt * (pk + sg), hlen,
+				   (int8_t *)ctx->d_out[s], ctx->streams[s]);
+	});
+}
+
+extern "C" int eccb200_bip0340_verify_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys,
+					    const uint8_t *digests, uint32_t hlen, int8_t *verdict)
+{
+	if (!ctx || (n && (!sigs || !pubkeys || !digests || !verdict))) return fail("null argument");
+	if (hlen == 0 || hlen > 128) return fail("bad digest length");
+	if (n == 0) return 0;
+	const size_t pk = 2 * (size_t)ctx->plen, sg = (size_t)ctx->plen + (size_t)ctx->qlen;
+	std::vector<HostCol> in = { { (uint8_t *)pubkeys, pk, false }, { (uint8_t *)sigs, sg, false },
+				    { (uint8_t *)digests, hlen, false } };
+	std::vector<HostCol> outc = { { (uint8_t *)verdict, 1, false } };
+	return run_pipeline(ctx, n, in, outc, [&](int s, uint32_t cnt) {
+		const uint8_t *d = ctx->d_in[s];
+		return bip0340_dev(ctx, cnt, d + (size_t)cnt * pk, d, d + (size_t)cnt * (pk + sg), hlen,
 				   (int8_t *)ctx->d_out[s], ctx->streams[s]);
 	});
 }

@@ -786,6 +786,44 @@ __global__ void ECC_CLUSTER_ATTR __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VE
 		return;
 	}
 
+	if (SCHEME == 2) {
+		/* BIP0340 (sig/bip0340.c:383-577): signature r || s with r a field element (the x coordinate
+		 * of the nonce point) and s < q; digests[i] = the tagged hash H(H(tag) || H(tag) || r || Y_x || m) computed by the
+		 * host; W' = sG - eY' with the key lifted to an even y; accept iff W' is finite, y(W') even and x(W') == r. */
+		typedef Field<typename C::Fp> F;
+		__shared__ uint32_t sh_inv2[ECC_CTA_INV_WORDS(N)];
+		const uint8_t *sg = sigs + (size_t)i0 * (C::PLEN + C::QLEN);
+		const uint8_t *pkb = pubkeys + (size_t)i0 * (2 * C::PLEN);
+		Fe<N> r, s, h, yraw;
+		Aff<C> Y;
+		load_wire<N, C::PLEN>(r, sg);
+		load_wire<N, C::QLEN>(s, sg + C::PLEN);
+		const bool r_ok = !F::geq_mod(r);                                 /* fp_import_from_buf (:431) */
+		const bool s_ok = !Fq::geq_mod(s);                                /* s < q (:433-434); s = 0 is not excluded */
+		load_wire<N, C::PLEN>(yraw, pkb + C::PLEN);
+		const bool key_ok = load_affine_checked<C>(Y, pkb);
+		if (yraw.w[0] & 1u) F::neg(Y.y, Y.y);                             /* lift to the even y (:540-545) */
+		digest_full_mod_q<C>(h, digests + (size_t)i0 * hlen, hlen);      /* e = OS2I(hash) mod q (:530-531) */
+		Fq::neg(h, h);                                                    /* -e mod q (:538) */
+		const bool run = r_ok && s_ok && key_ok;
+		if (!run) {
+			Fq::set_zero(s);
+			Fq::set_zero(h);
+#pragma unroll
+			for (int j = 0; j < N; j++) {
+				Y.x.w[j] = C::GX_MONT(j);
+				Y.y.w[j] = C::GY_MONT(j);
+			}
+		}
+		int code = bip0340_verify_tail<C>(r, s, h, Y, table, w, [&](Fe<N> &o, const Fe<N> &a) {
+			cta_inverse_128<typename C::Fp, ECC_CLUSTER_INV>(o, a, sh_inv2);
+		});
+		if (!active) return;
+		if (!run) code = 1;
+		verdict[idx] = code ? -1 : 0;
+		return;
+	}
+
 	Fe<N> r, s, e;
 	load_wire<N, C::QLEN>(r, sigs + (size_t)i0 * (2 * C::QLEN));
 	load_wire<N, C::QLEN>(s, sigs + (size_t)i0 * (2 * C::QLEN) + C::QLEN);
@@ -1150,6 +1188,8 @@ template <class C> struct LaunchVerify {
 			   const int8_t *key_state = nullptr);
 	static void ecfsdsa(uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys, const uint8_t *digests,
 			    uint32_t hlen, const uint32_t *table, int w, int8_t *verdict, cudaStream_t st);
+	static void bip0340(uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys, const uint8_t *digests,
+			    uint32_t hlen, const uint32_t *table, int w, int8_t *verdict, cudaStream_t st);
 	static void uv(uint32_t n, const uint8_t *sigs, const uint8_t *digests, uint32_t hlen, uint8_t *out,
 		       cudaStream_t st);
 };
@@ -1287,6 +1327,12 @@ void LaunchVerify<C>::ecfsdsa(uint32_t n, const uint8_t *sigs, const uint8_t *pu
 			      uint32_t hlen, const uint32_t *table, int w, int8_t *verdict, cudaStream_t st)
 {
 	k_ecdsa_verify<C, 1><<<grid_clustered(n), kThreads, 0, st>>>(n, sigs, pubkeys, digests, hlen, table, w, verdict, nullptr);
+}
+template <class C>
+void LaunchVerify<C>::bip0340(uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys, const uint8_t *digests,
+			      uint32_t hlen, const uint32_t *table, int w, int8_t *verdict, cudaStream_t st)
+{
+	k_ecdsa_verify<C, 2><<<grid_clustered(n), kThreads, 0, st>>>(n, sigs, pubkeys, digests, hlen, table, w, verdict, nullptr);
 }
 template <class C>
 void LaunchVerify<C>::uv(uint32_t n, const uint8_t *sigs, const uint8_t *digests, uint32_t hlen, uint8_t *out,

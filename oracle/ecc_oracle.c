@@ -736,6 +736,53 @@ static int ecfsdsa_verify_one(const uint8_t *sig, const uint8_t *pub, const uint
 	return memcmp(rprime, sig, 2 * c->plen) == 0 ? 0 : -1;
 }
 
+/* _bip0340_verify_init checks (sig/bip0340.c:383-465) + _bip0340_verify_finalize (:497-577) on
+ * h = H(H(tag) || H(tag) || r || x(Y) || m), the tagged challenge hash computed by the caller: 0 valid, -1 invalid */
+static int bip0340_verify_one(const uint8_t *sig, const uint8_t *pub, const uint8_t *h, uint32_t hlen,
+			      const curve_t *c)
+{
+	u64 r[MAXL], s[MAXL], e[MAXL], big[16];
+	pt_t Y, G, sG, eY, W, Wa;
+	int n = c->n;
+	/* r is imported as a field element: it must be < p (fp_import_from_buf, :431) */
+	nn_from_be(r, n, sig, c->plen);
+	if (nn_cmp_n(r, c->fp.p, n) >= 0) return -1;
+	/* s < q (:433-434); zero is not excluded */
+	nn_from_be(s, n, sig + c->plen, c->qlen);
+	if (nn_cmp_n(s, c->fq.p, n) >= 0) return -1;
+	if (pt_import_aff(&Y, pub, c)) return -1;
+	/* e = OS2I(h) mod q with the whole digest (:530-531), then -e mod q (:538) */
+	memset(big, 0, sizeof(big));
+	nn_from_be(big, 16, h, hlen > 128 ? 128 : hlen);
+	wide_mod_q(e, big, 16, c);
+	if (!nn_iszero_n(e, n)) nn_sub_n(e, c->fq.p, e, n);
+	/* lift the key to its even-y representative (:540-545) */
+	if (Y.Y[0] & 1) nn_sub_n(Y.Y, c->fp.p, Y.Y, n);
+	memcpy(G.X, c->gx, sizeof(G.X));
+	memcpy(G.Y, c->gy, sizeof(G.Y));
+	memset(G.Z, 0, sizeof(G.Z));
+	G.Z[0] = 1;
+	if (pt_mul(&sG, s, n, &G, c)) return -1;
+	if (pt_mul(&eY, e, n, &Y, c)) return -1;
+	if (pt_add_cf(&W, &sG, &eY, c)) return -1;
+	if (pt_iszero(&W, c)) return -1;          /* prj_pt_unique fails on infinity (:552), iszero check (:555-556) */
+	if (pt_unique(&Wa, &W, c)) return -1;
+	if (Wa.Y[0] & 1) return -1;               /* odd y (:559-560) */
+	return nn_cmp_n(Wa.X, r, n) == 0 ? 0 : -1; /* x(W') == r (:563-564) */
+}
+
+static void *bip_verify_worker(void *arg)
+{
+	job_t *j = (job_t *)arg;
+	const curve_t *c = j->c;
+	for (uint32_t i = j->lo; i < j->hi; i++) {
+		j->status[i] = (int8_t)bip0340_verify_one(j->sigs + (size_t)i * (c->plen + c->qlen),
+							  j->pubkeys + (size_t)i * 2 * c->plen,
+							  j->digests + (size_t)i * j->hlen, j->hlen, c);
+	}
+	return NULL;
+}
+
 static void *fs_verify_worker(void *arg)
 {
 	job_t *j = (job_t *)arg;
@@ -876,6 +923,24 @@ int ora_ecfsdsa_verify_digest_batch(const char *curve, uint32_t n, const uint8_t
 	p.hlen = hlen;
 	p.status = verdict;
 	run_jobs(fs_verify_worker, &p, n, nthreads);
+	return 0;
+}
+
+/* BIP0340 verification on the tagged challenge hash (sig/bip0340.c); sigs are [n][plen + qlen] (r, s) */
+int ora_bip0340_verify_digest_batch(const char *curve, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys,
+				    const uint8_t *digests, uint32_t hlen, int8_t *verdict, int nthreads)
+{
+	curve_t c;
+	job_t p;
+	if (curve_load(&c, curve)) return -1;
+	memset(&p, 0, sizeof(p));
+	p.c = &c;
+	p.sigs = sigs;
+	p.pubkeys = pubkeys;
+	p.digests = digests;
+	p.hlen = hlen;
+	p.status = verdict;
+	run_jobs(bip_verify_worker, &p, n, nthreads);
 	return 0;
 }
 

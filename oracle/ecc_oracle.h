@@ -30,6 +30,11 @@ int ora_ecdsa_verify_digest_batch(const char *curve, uint32_t n, const uint8_t *
 int ora_ecfsdsa_verify_digest_batch(const char *curve, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys,
 				    const uint8_t *digests, uint32_t hlen, int8_t *verdict, int nthreads);
 
+/* BIP0340 verification (sig/bip0340.c:383-577) on digests[i] = H(H(tag) || H(tag) || r_i || x(Y_i) || m_i) with
+ * tag = "BIP0340/challenge"; sigs are [n][plen + qlen] (r = x coordinate, s). */
+int ora_bip0340_verify_digest_batch(const char *curve, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys,
+				    const uint8_t *digests, uint32_t hlen, int8_t *verdict, int nthreads);
+
 /* ECDSA signing on pre-hashed messages with caller-supplied nonces (deterministic; RFC-vector friendly).
  * status 0 ok, -1 error (k, d out of range, r == 0 or s == 0). */
 int ora_ecdsa_sign_digest_batch(const char *curve, uint32_t n, const uint8_t *privkeys, const uint8_t *nonces,

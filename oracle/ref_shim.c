@@ -317,6 +317,51 @@ int ref_ecfsdsa_sign_batch(const char *curve, const char *hash, uint32_t n, cons
 	return run_sig_jobs(sign_worker, &p, n, nthreads);
 }
 
+/* The same two for BIP0340 (sig/bip0340.c): signatures are r || s with r = x(kG) (plen bytes) and s (qlen).  The
+ * reference's signer draws its auxiliary randomness from /dev/urandom and negates the key / nonce as BIP0340 says. */
+int ref_bip0340_verify_batch(const char *curve, const char *hash, uint32_t n, const uint8_t *sigs,
+			     const uint8_t *pubkeys, const uint8_t *msgs, const uint64_t *off, int8_t *verdict,
+			     int nthreads)
+{
+	ref_curve c;
+	sig_job p;
+	u8 dlen;
+	memset(&p, 0, sizeof(p));
+	if (ref_load_curve(&c, curve)) return -1;
+	if (ref_hash_type(hash, &p.ht, &dlen)) return -1;
+	p.c = &c;
+	p.sigs = sigs;
+	p.pubkeys = pubkeys;
+	p.msgs = msgs;
+	p.off = off;
+	p.verdict = verdict;
+	p.alg = BIP0340;
+	p.siglen = c.plen + c.qlen;
+	return run_sig_jobs(verify_worker, &p, n, nthreads);
+}
+
+int ref_bip0340_sign_batch(const char *curve, const char *hash, uint32_t n, const uint8_t *privkeys,
+			   const uint8_t *msgs, const uint64_t *off, uint8_t *sigs_out, uint8_t *pubkeys_out,
+			   int8_t *status, int nthreads)
+{
+	ref_curve c;
+	sig_job p;
+	u8 dlen;
+	memset(&p, 0, sizeof(p));
+	if (ref_load_curve(&c, curve)) return -1;
+	if (ref_hash_type(hash, &p.ht, &dlen)) return -1;
+	p.c = &c;
+	p.privkeys = privkeys;
+	p.msgs = msgs;
+	p.off = off;
+	p.sigs_out = sigs_out;
+	p.pubkeys_out = pubkeys_out;
+	p.verdict = status;
+	p.alg = BIP0340;
+	p.siglen = c.plen + c.qlen;
+	return run_sig_jobs(sign_worker, &p, n, nthreads);
+}
+
 /* The reference's own batch entry point, ec_verify_batch(…, ECFSDSA, …) (sig/sig_algs.c:675 -> sig/ecfsdsa.c:1057):
  * one 0 / -1 answer for the whole batch.  use_scratch = 0: no scratch pad, the reference verifies the signatures one
  * after the other (sig/ecfsdsa.c:711); use_scratch = 1: its Bos-Coster multi-scalar multiplication (:842). */

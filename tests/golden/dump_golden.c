@@ -179,6 +179,55 @@ int main(int argc, char **argv)
 	fprintf(f, "\n]\n");
 	fclose(f);
 
+	/* ---------------------------------------------------------------- BIP0340 KATs (sig/bip0340.c) */
+	snprintf(path, sizeof(path), "%s/bip0340_kat.json", dir);
+	f = fopen(path, "w");
+	fprintf(f, "[\n");
+	first = 1;
+	for (unsigned int i = 0; i < sizeof(ec_fixed_vector_tests) / sizeof(ec_fixed_vector_tests[0]); i++) {
+		const ec_test_case *t = ec_fixed_vector_tests[i];
+		ec_params params;
+		ec_key_pair kp;
+		u8 pub[2 * 66], dg[MAX_DIGEST_SIZE], htag[MAX_DIGEST_SIZE], plen;
+		const hash_mapping *hm = NULL;
+		const u8 *in[6];
+		u32 il[5];
+		int ref_verdict;
+		static const char tag[] = "BIP0340/challenge";
+		if (!t || t->sig_type != BIP0340 || !wanted_curve(t->ec_str_p)) continue;
+		if (import_params(&params, t->ec_str_p)) return 1;
+		plen = (u8)BYTECEIL(params.ec_fp.p_bitlen);
+		if (ec_key_pair_import_from_priv_key_buf(&kp, &params, t->priv_key, t->priv_key_len, t->sig_type)) return 1;
+		if (ec_pub_key_export_to_aff_buf(&kp.pub_key, pub, (u8)(2 * plen))) return 1;
+		if (get_hash_by_type(t->hash_type, &hm) || !hm) return 1;
+		/* the challenge hash: H(H(tag) || H(tag) || r || x(Y) || m)  (sig/bip0340.c:45-69, :438-443) */
+		in[0] = (const u8 *)tag; il[0] = (u32)(sizeof(tag) - 1);
+		in[1] = NULL;
+		if (hm->hfunc_scattered(in, il, htag)) return 1;
+		in[0] = htag; il[0] = hm->digest_size;
+		in[1] = htag; il[1] = hm->digest_size;
+		in[2] = t->exp_sig; il[2] = plen;
+		in[3] = pub; il[3] = plen;
+		in[4] = (const u8 *)t->msg; il[4] = t->msglen;
+		in[5] = NULL;
+		if (hm->hfunc_scattered(in, il, dg)) return 1;
+		ref_verdict = ec_verify(t->exp_sig, t->exp_siglen, &kp.pub_key, (const u8 *)t->msg, t->msglen,
+					t->sig_type, t->hash_type, t->adata, t->adata_len);
+		fprintf(f, "%s {", first ? "" : ",\n");
+		first = 0;
+		jstr(f, "name", t->name, 0);
+		jstr(f, "curve", curve_name(t->ec_str_p), 0);
+		jstr(f, "hash", hash_name(t->hash_type), 0);
+		hex(f, "priv", t->priv_key, t->priv_key_len, 0);
+		hex(f, "pub", pub, (unsigned int)(2 * plen), 0);
+		hex(f, "msg", (const u8 *)t->msg, t->msglen, 0);
+		hex(f, "digest_challenge", dg, hm->digest_size, 0);
+		hex(f, "sig", t->exp_sig, t->exp_siglen, 0);
+		fprintf(f, "\"ref_verdict\": %d}", ref_verdict);
+	}
+	fprintf(f, "\n]\n");
+	fclose(f);
+
 	/* ---------------------------------------------------------------- Wycheproof ECDSA */
 	snprintf(path, sizeof(path), "%s/wycheproof_ecdsa.json", dir);
 	f = fopen(path, "w");

@@ -270,6 +270,39 @@ int hostsim_ecfsdsa_verify_batch(int curve_id, int w, uint32_t n, const uint8_t 
 	});
 }
 
+/* BIP0340 verification with the kernel's building blocks (digest_full_mod_q, bip0340_verify_tail) */
+int hostsim_bip0340_verify_batch(int curve_id, int w, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys,
+				 const uint8_t *digests, uint32_t hlen, int8_t *verdict)
+{
+	return dispatch(curve_id, [&](auto c) {
+		typedef decltype(c) C;
+		typedef Field<typename C::Fq> Fq;
+		typedef Field<typename C::Fp> F;
+		constexpr int N = C::N;
+		const std::vector<uint32_t> &tab = table_for<C>(w);
+		for (uint32_t i = 0; i < n; i++) {
+			const uint8_t *sg = sigs + (size_t)i * (C::PLEN + C::QLEN);
+			const uint8_t *pkb = pubkeys + (size_t)i * 2 * C::PLEN;
+			Aff<C> Y;
+			Fe<N> r, s, h, yraw;
+			load_be<N>(r, sg, C::PLEN);
+			load_be<N>(s, sg + C::PLEN, C::QLEN);
+			bool ok = !F::geq_mod(r) && !Fq::geq_mod(s);
+			load_be<N>(yraw, pkb + C::PLEN, C::PLEN);
+			ok = load_point<C>(Y, pkb) && ok;
+			if (yraw.w[0] & 1u) F::neg(Y.y, Y.y);
+			digest_full_mod_q<C>(h, digests + (size_t)i * hlen, hlen);
+			Fq::neg(h, h);
+			if (!ok) {
+				verdict[i] = -1;
+				continue;
+			}
+			verdict[i] = bip0340_verify_tail<C>(r, s, h, Y, tab.data(), w, ThreadInverter<C>()) == 0 ? 0 : -1;
+		}
+		return 0;
+	});
+}
+
 /* group-law unit test: out = P1 + P2 on affine wire points through add_full / add_mixed / xz_add_mixed (which = 0 / 1 / 3),
  * or 2*P1 through dbl (which = 2); infinity operands are encoded as all-zero wire points */
 int hostsim_point_op(int curve_id, int which, const uint8_t *p1, const uint8_t *p2, uint8_t *out, int8_t *status)
