@@ -419,6 +419,8 @@ class Ours:
         self.n = 1 << batch_log2
         self.rank, self.world, self.local_rank = rank, world, local_rank
         self.gather = gather if (world > 1 and self.kind != "verify") else ("nccl" if world > 1 else "none")
+        if world == 1 and os.environ.get("BENCH_FORCE_GATHER") and self.kind != "verify" and gather.startswith("peer"):
+            self.gather = gather     # diagnostic: the gather path with this GPU as its own (only) destination
         _, self.plen, self.qlen = CURVES[self.curve]
         self.dev = torch.device("cuda", local_rank)
         self.inputs = make_inputs(workload, self.n, rank)

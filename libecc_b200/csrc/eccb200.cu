@@ -485,6 +485,78 @@ extern "C" int eccb200_ipc_free(eccb200_ctx *ctx, void *d_ptr)
 	return 0;
 }
 
+/*
+ * Sliced form of smul_dev for the multi-GPU gather: the batch is cut into the pipeline's four-wave slices; slice c's
+ * scalar multiplication runs on the caller's stream and its normalisation — the kernel whose stores travel to the
+ * peers — on the context's high-priority stream behind it, so the NVLink traffic of slice c overlaps the arithmetic of
+ * slice c + 1 instead of arriving at the destination in one burst at the end of the step (eight GPUs storing 68 MB
+ * each into one root would otherwise queue on the root's 900 GB/s of ingress).  The arrival flags are published by the
+ * last slice's normalisation; the caller's stream then waits for it.
+ */
+static int smul_dev_sliced(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_scalars, const uint8_t *d_points,
+			   uint8_t *d_out, int8_t *d_status, cudaStream_t st, const GatherDst *gd,
+			   const uint32_t *d_wait_flags, int wait_count, uint32_t wait_value, uint32_t slice)
+{
+	return dispatch(ctx->curve_id, [&](auto c) {
+		typedef decltype(c) C;
+		constexpr size_t QL = C::QLEN, PL2 = 2 * (size_t)C::PLEN, JW = 3 * (size_t)C::N;
+		cudaStream_t H = ctx->hi[0];
+		scratch_enter(ctx, st);
+		const bool prof = ctx->profiling && ctx->ev_calls < eccb200_ctx::kProfCalls;
+		cudaEvent_t *pe = prof ? ctx->ev[ctx->ev_calls] : nullptr;
+		if (prof) cudaEventRecord(pe[0], st);
+		uint32_t idx = 0;
+		for (uint32_t lo = 0; lo < n; lo += slice, idx++) {
+			const uint32_t cnt = std::min(slice, n - lo);
+			const bool last = lo + cnt >= n;
+			uint32_t *jac = ctx->jac + (size_t)lo * JW;
+			if (d_points)
+				LaunchVar<C>::var(cnt, d_scalars + lo * QL, d_points + lo * PL2, jac, d_status + lo, st);
+			else
+				LaunchFixed<C>::fixed(cnt, d_scalars + lo * QL, ctx->table, ctx->w, jac, d_status + lo, st);
+			cudaEvent_t ev = ctx->kdone[idx % kStages];
+			cudaEventRecord(ev, st);
+			cudaStreamWaitEvent(H, ev, 0);
+			if (idx == 0 && d_wait_flags && wait_count > 0) {
+				k_flag_wait<<<1, 32, 0, H>>>(d_wait_flags, wait_count, wait_value);
+				ctx->launches += 1;
+			}
+			GatherDst g = gd ? *gd : GatherDst();
+			for (int j = 0; j < g.n; j++) {
+				g.out[j] += lo * PL2;
+				g.status[j] += lo;
+			}
+			g.signal = last ? 1 : 0;
+			LaunchMisc<C>::to_affine(affine_grid(ctx, cnt), cnt, jac, ctx->prefix + (size_t)lo * C::N, d_out + lo * PL2,
+						 d_status + lo, H, &g);
+			ctx->launches += 2;
+		}
+		if (prof) cudaEventRecord(pe[1], st); /* scalar multiplications done (the normalisations overlap them) */
+		cudaEventRecord(ctx->ndone[0], H);
+		cudaStreamWaitEvent(st, ctx->ndone[0], 0);
+		if (prof) {
+			cudaEventRecord(pe[2], st);
+			ctx->ev_kernels[ctx->ev_calls++] = 2;
+		}
+		scratch_leave(ctx, st);
+		CUDA_OK(cudaGetLastError());
+		return 0;
+	});
+}
+
+/* slices per gather call: ECCB200_GATHER_SLICE_WAVES waves of the fixed-base kernel each (default: the pipeline's
+ * chunk, four waves); 0 = one slice (the whole batch, normalisation behind the scalar multiplication on one stream) */
+static uint32_t gather_slice(const eccb200_ctx *ctx)
+{
+	static int waves = -1;
+	if (waves < 0) {
+		const char *e = getenv("ECCB200_GATHER_SLICE_WAVES");
+		waves = e ? atoi(e) : 4;
+		if (waves < 0 || waves > 64) waves = 4;
+	}
+	return waves ? (uint32_t)waves * (uint32_t)ctx->sm_count * 4u * 128u : 0u;
+}
+
 extern "C" int eccb200_prj_pt_mul_batch_dev_gather(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_scalars,
 						   const uint8_t *d_points, uint8_t *d_out, int8_t *d_status, int n_dst,
 						   uint8_t *const *dst_out, int8_t *const *dst_status,
@@ -510,6 +582,10 @@ extern "C" int eccb200_prj_pt_mul_batch_dev_gather(eccb200_ctx *ctx, uint32_t n,
 	gd.counter = ctx->gather_counter;
 	CUDA_OK(cudaSetDevice(ctx->device));
 	if (ensure_work(ctx, n)) return -1;
+	const uint32_t slice = gather_slice(ctx);
+	if (slice && n > slice)
+		return smul_dev_sliced(ctx, n, d_scalars, d_points, d_out, d_status, (cudaStream_t)stream,
+				       n_dst ? &gd : nullptr, d_wait_flags, wait_count, wait_value, slice);
 	return smul_dev(ctx, n, d_scalars, d_points, d_out, d_status, ctx->jac, ctx->prefix, (cudaStream_t)stream, nullptr,
 			nullptr, nullptr, n_dst ? &gd : nullptr, d_wait_flags, wait_count, wait_value);
 }

@@ -543,6 +543,8 @@ struct GatherDst {
 	int8_t *status[ECC_MAX_GATHER_DST];     /* [n_items] */
 	uint32_t *flag[ECC_MAX_GATHER_DST];     /* arrival flag of this rank at destination j */
 	uint32_t flag_value = 0;
+	int signal = 1;                         /* publish the flags when this launch has stored everything (the last
+	                                         * launch of a batch that is normalised in several slices) */
 	unsigned int *counter = nullptr;        /* local: CTAs finished (reset by the last one) */
 };
 
@@ -660,7 +662,7 @@ __global__ void __launch_bounds__(128) k_to_affine(uint32_t n, const uint32_t *_
 		}
 		if (e < T || e - T < tid) break;
 	}
-	if (MODE == 0 && gd.n > 0) {
+	if (MODE == 0 && gd.n > 0 && gd.signal) {
 		/* every thread's remote stores are ordered before the counter increment; the last CTA publishes the flags */
 		__threadfence_system();
 		__syncthreads();

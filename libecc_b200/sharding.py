@@ -84,7 +84,10 @@ class PeerGather:
             raise ValueError("at most 8 destinations")
         self.base, handle = eng.ipc_alloc(self.layout["total"])
         handles = [None] * world
-        dist.all_gather_object(handles, handle, group=group)
+        if world > 1:
+            dist.all_gather_object(handles, handle, group=group)
+        else:
+            handles[0] = handle      # single rank: the gather degenerates to stores into the own region
         self.peer = {}                       # rank -> mapped base pointer of that rank's region
         for r in set(self.dests) | {self.rank}:
             self.peer[r] = self.base if r == rank else eng.ipc_open(handles[r])
@@ -94,7 +97,8 @@ class PeerGather:
                     self.peer[r] = eng.ipc_open(handles[r])
         self.step_no = 0
         self._dst = {}
-        dist.barrier(group=group)            # every mapping exists before anybody stores
+        if world > 1:
+            dist.barrier(group=group)        # every mapping exists before anybody stores
 
     def step(self, p_scalars: int, p_points, p_out: int, p_status: int, stream: int):
         """One batch: K1, (wait for the buffer's release), K4 with the fused gather; on a destination rank also the
@@ -139,7 +143,8 @@ class PeerGather:
             if r != self.rank:
                 self.eng.ipc_close(p)
         self.peer = {}
-        dist.barrier(group=group)
+        if self.world > 1:
+            dist.barrier(group=group)
         if self.base:
             self.eng.ipc_free(self.base)
             self.base = 0
