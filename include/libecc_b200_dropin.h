@@ -7,7 +7,7 @@
  *     a shared libsign/libec, it interposes the reference's definition, so every caller — ECDSA sign/verify
  *     (src/sig/ecdsa_common.c:479,788,793), ECC-CDH (src/ecdh/ecccdh.c:80,209), all other schemes of src/sig — runs
  *     its scalar multiplications on the B200 without being recompiled.
- *   - `ec_verify` with the reference's exact signature (src/sig/sig_algs.h:85-88): ECDSA / DECDSA / ECFSDSA
+ *   - `ec_verify` with the reference's exact signature (src/sig/sig_algs.h:85-88): ECDSA / DECDSA / ECFSDSA / BIP0340
  *     verifications become ONE kernel launch each; every other scheme is forwarded to the reference's own ec_verify.
  *   - `prj_pt_mul_blind` (src/curves/prj_pt.h:62) is exported but NOT taken over by default: see its comment below.
  *   - `eccb200_dropin_prj_pt_mul_batch`: the same on arrays of reference structs (one launch for the batch).
@@ -122,7 +122,7 @@ void eccb200_dropin_allow_nonct_blind(int on);
  * ec_alg_type / hash_alg_type values):
  *     int ec_verify(const u8 *sig, u8 siglen, const ec_pub_key *pub_key, const u8 *m, u32 mlen,
  *                   ec_alg_type sig_type, hash_alg_type hash_type, const u8 *adata, u16 adata_len);
- * ECDSA (1), DECDSA (14) and ECFSDSA (5) without ancillary data on a supported curve: the message is hashed on the
+ * ECDSA (1), DECDSA (14), ECFSDSA (5) and BIP0340 (20) without ancillary data on a supported curve: the message is hashed on the
  * host with the reference's src/hash and the whole verification (steps 3-10 of __ecdsa_verify_finalize,
  * src/sig/ecdsa_common.c:760-810) is ONE launch of the verification kernel; 0 = valid, -1 = invalid.  Anything else is
  * forwarded unchanged to the next ec_verify in the process (the reference's own); -1 if there is none.
@@ -155,6 +155,14 @@ int eccb200_dropin_ecdsa_verify_batch(const uint8_t **s, const uint8_t *s_len, c
  * (src/sig/ecfsdsa.c:1057) in the ECFSDSA entry of ec_sig_maps[]; signatures are W_x || W_y || s and the digest is
  * H(W_x || W_y || m), computed with the reference's src/hash. */
 int eccb200_dropin_ecfsdsa_verify_batch(const uint8_t **s, const uint8_t *s_len, const eccb200_ec_pub_key **pub_keys,
+					const uint8_t **m, const uint32_t *m_len, uint32_t num, int sig_type,
+					int hash_type, const uint8_t **adata, const uint16_t *adata_len,
+					void *scratch_pad_area, uint32_t *scratch_pad_area_len);
+
+/* The same for BIP0340 (sig_type = BIP0340 = 20): a replacement for the reference's own bip0340_verify_batch
+ * (src/sig/bip0340.c:1296) in the BIP0340 entry of ec_sig_maps[] (src/sig/sig_algs_internal.h:615); signatures are
+ * r || s and the digest is the tagged challenge hash of r || x(Y) || m, computed with the reference's src/hash. */
+int eccb200_dropin_bip0340_verify_batch(const uint8_t **s, const uint8_t *s_len, const eccb200_ec_pub_key **pub_keys,
 					const uint8_t **m, const uint32_t *m_len, uint32_t num, int sig_type,
 					int hash_type, const uint8_t **adata, const uint16_t *adata_len,
 					void *scratch_pad_area, uint32_t *scratch_pad_area_len);

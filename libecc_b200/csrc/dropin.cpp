@@ -518,18 +518,33 @@ static get_hash_fn resolve_get_hash()
 	return f;
 }
 
-/* fs = false: ECDSA / DECDSA (signature r || s, digest H(m));  fs = true: ECFSDSA (signature W_x || W_y || s, digest
- * H(W_x || W_y || m), sig/ecfsdsa.c:482,529).  keep_verdicts: record the per-item verdicts for
- * eccb200_dropin_last_verdicts. */
-static int verify_batch_common(bool fs, const uint8_t **s, const uint8_t *s_len, const eccb200_ec_pub_key **pub_keys,
+/* The schemes served by the verification kernel and their ec_alg_type values (lib_ecc_types.h:22-80). */
+enum Scheme { kEcdsa = 0, kEcfsdsa = 1, kBip0340 = 2 };
+static bool scheme_of(int sig_type, Scheme *sc)
+{
+	if (sig_type == 1 || sig_type == 14) *sc = kEcdsa; /* ECDSA, DECDSA */
+	else if (sig_type == 5) *sc = kEcfsdsa;
+	else if (sig_type == 20) *sc = kBip0340;
+	else return false;
+	return true;
+}
+
+/*
+ * One batch through the verification kernel.
+ *   ECDSA / DECDSA  signature r || s,               digest H(m)
+ *   ECFSDSA         signature W_x || W_y || s,      digest H(W_x || W_y || m)            (sig/ecfsdsa.c:482,529)
+ *   BIP0340         signature r || s (r = x(kG)),   digest H(H(tag) || H(tag) || r || x(Y) || m), tag = "BIP0340/challenge"
+ *                                                                                         (sig/bip0340.c:45-69,438-443)
+ * Hashing uses the reference's own src/hash (hfunc_scattered of the hash mapping).
+ */
+static int verify_batch_common(Scheme sc, const uint8_t **s, const uint8_t *s_len, const eccb200_ec_pub_key **pub_keys,
 			       const uint8_t **m, const uint32_t *m_len, uint32_t num, int sig_type, int hash_type,
 			       const uint8_t **adata)
 {
 	t_verdicts.assign(num, -1);
 	if (num == 0) return -1; /* the reference's implementations reject an empty batch (sig/ecfsdsa.c:740) */
 	if (!s || !s_len || !pub_keys || !m || !m_len) return -1;
-	if (fs ? (sig_type != 5 /* ECFSDSA */) : (sig_type != 1 /* ECDSA */ && sig_type != 14 /* DECDSA */)) return -1;
-	if (adata) /* ECDSA takes no ancillary data: every entry must be NULL (sig/ecdsa.c:76-83) */
+	if (adata) /* none of the three schemes takes ancillary data: every entry must be NULL (sig/ecdsa.c:76-83) */
 		for (uint32_t i = 0; i < num; i++)
 			if (adata[i]) return -1;
 	get_hash_fn get_hash = resolve_get_hash();
@@ -537,6 +552,7 @@ static int verify_batch_common(bool fs, const uint8_t **s, const uint8_t *s_len,
 	const HashMappingHead *hm = nullptr;
 	if (get_hash(hash_type, &hm) || !hm || !hm->hfunc_scattered) return -1;
 	const uint32_t hlen = hm->digest_size;
+	if (hlen == 0 || hlen > 128) return -1;
 
 	/* the curve: the first key that identifies one; every other key must agree (sig/ecfsdsa.c:711) */
 	const CurveInfo *ci = nullptr;
@@ -550,11 +566,11 @@ static int verify_batch_common(bool fs, const uint8_t **s, const uint8_t *s_len,
 	if (!eng) return -1;
 	const int pl = ci->plen;
 	const size_t plen = (size_t)ci->plen, qlen = (size_t)ci->qlen;
-	const size_t siglen = fs ? 2 * plen + qlen : 2 * qlen;
-	/* page-locked staging owned by the slot: the engine's pipeline DMAs straight out of / into it */
+	const size_t siglen = sc == kEcfsdsa ? 2 * plen + qlen : (sc == kBip0340 ? plen + qlen : 2 * qlen);
 	/* ECDSA: the keys travel in the reference's projective form (X || Y || Z) and are normalised on the device in front
-	 * of the verification kernel; ECFSDSA keeps affine keys (Z != 1 ones go through eccb200_prj_pt_unique_batch) */
-	const size_t keylen = fs ? 2 * plen : 3 * plen;
+	 * of the verification kernel; the other two take affine keys (Z != 1 ones go through eccb200_prj_pt_unique_batch) */
+	const size_t keylen = sc == kEcdsa ? 3 * plen : 2 * plen;
+	/* page-locked staging owned by the slot: the engine's pipeline DMAs straight out of / into it */
 	uint8_t *sigs = engine.slot->st[0].get(num * siglen), *pubs = engine.slot->st[1].get(num * keylen),
 		*dig = engine.slot->st[2].get(num * (size_t)hlen);
 	int8_t *verdict = (int8_t *)engine.slot->st[3].get(num);
@@ -578,13 +594,16 @@ static int verify_batch_common(bool fs, const uint8_t **s, const uint8_t *s_len,
 				mixed.store(1);
 				continue;
 			}
-			if (s_len[i] != siglen) continue; /* siglen check, sig/ecdsa_common.c:645, sig/ecfsdsa.c:447 */
+			if (s_len[i] != siglen) continue; /* siglen check, sig/ecdsa_common.c:645, sig/ecfsdsa.c:447, sig/bip0340.c:421 */
 			memcpy(&sigs[i * siglen], s[i], siglen);
-			const unsigned char *inputs[3] = { fs ? s[i] : m[i], fs ? m[i] : nullptr, nullptr };
-			uint32_t ilens[2] = { fs ? (uint32_t)(2 * plen) : m_len[i], fs ? m_len[i] : 0 };
-			if (hm->hfunc_scattered(inputs, ilens, &dig[i * (size_t)hlen])) continue;
+			if (sc != kBip0340) {
+				const bool fs = sc == kEcfsdsa;
+				const unsigned char *inputs[3] = { fs ? s[i] : m[i], fs ? m[i] : nullptr, nullptr };
+				uint32_t ilens[2] = { fs ? (uint32_t)(2 * plen) : m_len[i], fs ? m_len[i] : 0 };
+				if (hm->hfunc_scattered(inputs, ilens, &dig[i * (size_t)hlen])) continue;
+			}
 			const eccb200_prj_pt *y = &pk->y;
-			if (!fs) {
+			if (sc == kEcdsa) {
 				fp_to_be(&pubs[i * keylen], &y->X, pl);
 				fp_to_be(&pubs[i * keylen + plen], &y->Y, pl);
 				fp_to_be(&pubs[i * keylen + 2 * plen], &y->Z, pl);
@@ -603,25 +622,46 @@ static int verify_batch_common(bool fs, const uint8_t **s, const uint8_t *s_len,
 	if (!prj_idx.empty()) {
 		std::vector<uint8_t> pb(prj_idx.size() * 3 * plen), ab(prj_idx.size() * 2 * plen);
 		std::vector<int8_t> st(prj_idx.size());
-		for (size_t k = 0; k < prj_idx.size(); k++) {
-			const eccb200_prj_pt *p = &pub_keys[prj_idx[k]]->y;
-			fp_to_be(&pb[k * 3 * plen], &p->X, pl);
-			fp_to_be(&pb[k * 3 * plen + plen], &p->Y, pl);
-			fp_to_be(&pb[k * 3 * plen + 2 * plen], &p->Z, pl);
-		}
+		parallel_for((uint32_t)prj_idx.size(), [&](uint32_t lo, uint32_t hi, unsigned) {
+			for (uint32_t k = lo; k < hi; k++) {
+				const eccb200_prj_pt *p = &pub_keys[prj_idx[k]]->y;
+				fp_to_be(&pb[k * 3 * plen], &p->X, pl);
+				fp_to_be(&pb[k * 3 * plen + plen], &p->Y, pl);
+				fp_to_be(&pb[k * 3 * plen + 2 * plen], &p->Z, pl);
+			}
+		});
 		if (eccb200_prj_pt_unique_batch(eng, (uint32_t)prj_idx.size(), pb.data(), ab.data(), st.data())) return -1;
 		for (size_t k = 0; k < prj_idx.size(); k++) {
 			uint32_t i = prj_idx[k];
 			if (st[k] == 0) memcpy(&pubs[i * 2 * plen], &ab[k * 2 * plen], 2 * plen);
-			else ok[i] = 0; /* off the curve.  ECFSDSA with a key at infinity is rejected too — a documented divergence:
-					 * the reference would accept it iff s*G == r.  (ECDSA keys are normalised on the
-					 * device, where a key at infinity continues with W' = u*G like the reference's ec_verify.) */
+			else ok[i] = 0; /* off the curve, or the point at infinity: BIP0340's prj_pt_unique fails on it
+					 * (sig/bip0340.c:428); ECFSDSA with a key at infinity is rejected too — a documented divergence
+					 * (the reference would accept it iff s*G == r).  ECDSA keys are normalised on the
+					 * device, where a key at infinity continues with W' = u*G like the reference's ec_verify. */
 		}
 	}
+	if (sc == kBip0340) {
+		/* the challenge hash needs x(Y) of the affine key: second marshalling pass */
+		static const char tag[] = "BIP0340/challenge";
+		uint8_t htag[128];
+		const unsigned char *tin[2] = { (const unsigned char *)tag, nullptr };
+		uint32_t tl[1] = { (uint32_t)(sizeof(tag) - 1) };
+		if (hm->hfunc_scattered(tin, tl, htag)) return -1;
+		parallel_for(num, [&](uint32_t lo, uint32_t hi, unsigned) {
+			for (uint32_t i = lo; i < hi; i++) {
+				if (!ok[i]) continue;
+				const unsigned char *in[6] = { htag, htag, s[i], &pubs[i * 2 * plen], m[i], nullptr };
+				uint32_t il[5] = { hlen, hlen, (uint32_t)plen, (uint32_t)plen, m_len[i] };
+				if (hm->hfunc_scattered(in, il, &dig[i * (size_t)hlen])) ok[i] = 0;
+			}
+		});
+	}
 	memset(verdict, 0xff, num);
-	if (fs ? eccb200_ecfsdsa_verify_batch(eng, num, sigs, pubs, dig, hlen, verdict)
-	       : eccb200_ecdsa_verify_prj_batch(eng, num, sigs, pubs, dig, hlen, verdict))
-		return -1;
+	int rc;
+	if (sc == kEcfsdsa) rc = eccb200_ecfsdsa_verify_batch(eng, num, sigs, pubs, dig, hlen, verdict);
+	else if (sc == kBip0340) rc = eccb200_bip0340_verify_batch(eng, num, sigs, pubs, dig, hlen, verdict);
+	else rc = eccb200_ecdsa_verify_prj_batch(eng, num, sigs, pubs, dig, hlen, verdict);
+	if (rc) return -1;
 	g_verifies += num;
 	int all = 0;
 	for (uint32_t i = 0; i < num; i++) {
@@ -641,7 +681,8 @@ extern "C" int eccb200_dropin_ecdsa_verify_batch(const uint8_t **s, const uint8_
 	(void)scratch_pad_area;
 	(void)scratch_pad_area_len;
 	(void)adata_len;
-	return verify_batch_common(false, s, s_len, pub_keys, m, m_len, num, sig_type, hash_type, adata);
+	if (sig_type != 1 /* ECDSA */ && sig_type != 14 /* DECDSA */) return -1;
+	return verify_batch_common(kEcdsa, s, s_len, pub_keys, m, m_len, num, sig_type, hash_type, adata);
 }
 
 /* ECFSDSA: a replacement for the reference's own ecfsdsa_verify_batch (sig/ecfsdsa.c:1057) in the same slot */
@@ -654,7 +695,22 @@ extern "C" int eccb200_dropin_ecfsdsa_verify_batch(const uint8_t **s, const uint
 	(void)scratch_pad_area;
 	(void)scratch_pad_area_len;
 	(void)adata_len;
-	return verify_batch_common(true, s, s_len, pub_keys, m, m_len, num, sig_type, hash_type, adata);
+	if (sig_type != 5 /* ECFSDSA */) return -1;
+	return verify_batch_common(kEcfsdsa, s, s_len, pub_keys, m, m_len, num, sig_type, hash_type, adata);
+}
+
+/* BIP0340: a replacement for the reference's own bip0340_verify_batch (sig/bip0340.c:1296) in the same slot */
+extern "C" int eccb200_dropin_bip0340_verify_batch(const uint8_t **s, const uint8_t *s_len,
+						   const eccb200_ec_pub_key **pub_keys, const uint8_t **m,
+						   const uint32_t *m_len, uint32_t num, int sig_type, int hash_type,
+						   const uint8_t **adata, const uint16_t *adata_len,
+						   void *scratch_pad_area, uint32_t *scratch_pad_area_len)
+{
+	(void)scratch_pad_area;
+	(void)scratch_pad_area_len;
+	(void)adata_len;
+	if (sig_type != 20 /* BIP0340 */) return -1;
+	return verify_batch_common(kBip0340, s, s_len, pub_keys, m, m_len, num, sig_type, hash_type, adata);
 }
 
 /*
@@ -680,8 +736,8 @@ extern "C" int eccb200_dropin_ec_verify(const uint8_t *sig, uint8_t siglen, cons
 					const uint8_t *m, uint32_t mlen, int sig_type, int hash_type,
 					const uint8_t *adata, uint16_t adata_len)
 {
-	const bool ecdsa = (sig_type == 1 || sig_type == 14), fs = (sig_type == 5);
-	bool ours = (ecdsa || fs) && !adata && adata_len == 0 && sig && pub_key && pub_key->magic == kPubKeyMagic &&
+	Scheme sc = kEcdsa;
+	bool ours = scheme_of(sig_type, &sc) && !adata && adata_len == 0 && sig && pub_key && pub_key->magic == kPubKeyMagic &&
 		    pub_key->key_type == sig_type && pt_ok(&pub_key->y) && identify(&pub_key->y) != nullptr &&
 		    resolve_get_hash() != nullptr;
 	if (ours) {
@@ -697,7 +753,7 @@ extern "C" int eccb200_dropin_ec_verify(const uint8_t *sig, uint8_t siglen, cons
 	const eccb200_ec_pub_key *pk[1] = { pub_key };
 	const uint8_t *mp[1] = { m };
 	const uint32_t ml[1] = { mlen };
-	return verify_batch_common(fs, sp, sl, pk, mp, ml, 1, sig_type, hash_type, nullptr);
+	return verify_batch_common(sc, sp, sl, pk, mp, ml, 1, sig_type, hash_type, nullptr);
 }
 
 extern "C" int ec_verify(const uint8_t *sig, uint8_t siglen, const eccb200_ec_pub_key *pub_key, const uint8_t *m,

@@ -43,7 +43,9 @@ struct eccb200_ctx {
 	int w = 0;           /* comb window */
 	int nwin = 0;
 	int sm_count = 0;
-	uint32_t chunk = 0; /* items per pipeline chunk: four full waves of K1 (4 * SMs * 4 CTAs * 128 threads) */
+	uint32_t wave = 0;     /* items of one full wave of K1: SMs * 4 CTAs * 128 threads */
+	uint32_t chunk_eq = 0; /* items per equal pipeline chunk: four waves (ECCB200_CHUNK_WAVES) */
+	uint32_t chunk = 0;    /* capacity of the stage buffers: the largest chunk (eight waves) */
 	uint32_t *table = nullptr;
 	/* work buffers (grown on demand) */
 	uint32_t cap = 0;
@@ -183,10 +185,19 @@ extern "C" int eccb200_ctx_create(eccb200_ctx **out, int curve_id, int device, i
 	ctx->device = device;
 	ctx->w = w;
 	ctx->sm_count = prop.multiProcessorCount;
-	{ /* pipeline chunk = full K1 waves (SMs x 4 CTAs x 128 items); ECCB200_CHUNK_WAVES overrides (tuning knob) */
+	{ /* pipeline chunk = full K1 waves (SMs x resident CTAs x 128 items; the residency is the kernel's real,
+	   * register-limited one: 5 for secp256r1 at 98 registers, 4 for the generic 256-bit primes — a chunk that is not a
+	   * whole number of waves leaves the SMs idle at its tail); ECCB200_CHUNK_WAVES overrides the wave count */
 		const char *cw = getenv("ECCB200_CHUNK_WAVES");
 		uint32_t waves = (cw && atoi(cw) > 0 && atoi(cw) <= 64) ? (uint32_t)atoi(cw) : 4u;
-		ctx->chunk = waves * (uint32_t)prop.multiProcessorCount * 4u * 128u;
+		int occ = 4;
+		dispatch(curve_id, [&](auto c) {
+			occ = LaunchFixed<decltype(c)>::fixed_ctas_per_sm();
+			return 0;
+		});
+		ctx->wave = (uint32_t)prop.multiProcessorCount * (uint32_t)occ * 128u;
+		ctx->chunk_eq = waves * ctx->wave;
+		ctx->chunk = std::max(8u, waves) * ctx->wave; /* stage capacity: the largest chunk the pipeline may cut */
 	}
 	int rc = dispatch(curve_id, [&](auto c) {
 		typedef decltype(c) C;
@@ -554,7 +565,7 @@ static uint32_t gather_slice(const eccb200_ctx *ctx)
 		waves = e ? atoi(e) : 4;
 		if (waves < 0 || waves > 64) waves = 4;
 	}
-	return waves ? (uint32_t)waves * (uint32_t)ctx->sm_count * 4u * 128u : 0u;
+	return waves ? (uint32_t)waves * ctx->wave : 0u;
 }
 
 extern "C" int eccb200_prj_pt_mul_batch_dev_gather(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_scalars,
@@ -756,6 +767,42 @@ template <class Launch>
 static int run_pipeline_body(eccb200_ctx *ctx, uint32_t n, std::vector<HostCol> &in, std::vector<HostCol> &out,
 			     Launch launch, bool ordered);
 
+/*
+ * Chunk boundaries of the host pipeline.
+ *  - unordered pipelines (the long K2 / K3 kernels): equal chunks of four waves;
+ *  - ordered ones (fixed base: short kernels, the copies are what shows): the chunk sizes ramp up 1, 2, 4 (, 8) waves so
+ *    that the first kernel starts after a 2.4 MB copy instead of a 9.7 MB one, run at four waves (eight for batches
+ *    beyond 64 waves: fewer per-chunk gaps) and ramp down 2, 1 so that the last device->host copy is short.
+ * Round 1 measured such shaping as a loss (every extra chunk exposed ~0.1 ms of the Fermat inversion of K4); with the
+ * safegcd inversion that latency is ~15 us and the shaping pays.  ECCB200_PIPE_SHAPE=0 restores equal
+ * chunks.
+ */
+static std::vector<uint32_t> pipeline_bounds(const eccb200_ctx *ctx, uint32_t n, bool ordered)
+{
+	static const bool shape = !(getenv("ECCB200_PIPE_SHAPE") && atoi(getenv("ECCB200_PIPE_SHAPE")) == 0);
+	std::vector<uint32_t> bounds{ 0 };
+	const uint32_t w = ctx->wave;
+	if (!ordered || !shape || n <= 2 * w) {
+		for (uint32_t lo = 0; lo < n;) {
+			lo += std::min(ctx->chunk_eq, n - lo);
+			bounds.push_back(lo);
+		}
+		return bounds;
+	}
+	const uint32_t maxw = std::min<uint32_t>(ctx->chunk / w, (n / w >= 64) ? 8u : 4u);
+	uint32_t lo = 0;
+	auto push = [&](uint32_t cnt) {
+		lo += cnt;
+		bounds.push_back(lo);
+	};
+	for (uint32_t u = 1; u < maxw && (uint64_t)(n - lo) > (uint64_t)(u + 3) * w; u *= 2) push(u * w); /* ramp up */
+	while ((uint64_t)(n - lo) > (uint64_t)(maxw + 3) * w) push(maxw * w);                                /* steady state */
+	if (n - lo > 3 * w) push(n - lo - 3 * w);                                                             /* ramp down */
+	if (n - lo > w) push(n - lo - w);
+	if (n - lo > 0) push(n - lo);
+	return bounds;
+}
+
 template <class Launch>
 static int run_pipeline(eccb200_ctx *ctx, uint32_t n, std::vector<HostCol> &in, std::vector<HostCol> &out,
 			Launch launch, bool ordered = false)
@@ -794,15 +841,7 @@ static int run_pipeline_body(eccb200_ctx *ctx, uint32_t n, std::vector<HostCol> 
 	}
 	const uint32_t kChunk = ctx->chunk;
 	if (ensure_stages(ctx, (size_t)kChunk * in_item, (size_t)kChunk * out_item)) return -1;
-	/* Chunk boundaries: equal chunks.  Shaping them was measured and dropped (secp256r1 fixed base, 2^20 items, e2e):
-	 * equal 4-wave chunks 342-350 M/s; quarter-size first chunk 322; quarter-size first and last 320; first quarter +
-	 * taper 2q, q, q/2 at the end 309 — every extra chunk costs more normalisation latency than the shorter fill and
-	 * drain give back. */
-	std::vector<uint32_t> bounds{ 0 };
-	for (uint32_t lo = 0; lo < n;) {
-		lo += std::min(kChunk, n - lo);
-		bounds.push_back(lo);
-	}
+	const std::vector<uint32_t> bounds = pipeline_bounds(ctx, n, ordered);
 	const uint32_t nchunks = (uint32_t)bounds.size() - 1;
 	bool all_pinned = true;
 	for (auto &c : in) all_pinned = all_pinned && c.pinned;

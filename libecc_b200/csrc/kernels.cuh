@@ -590,11 +590,12 @@ __global__ void __launch_bounds__(128) k_to_affine(uint32_t n, const uint32_t *_
 		}
 	}
 	Fe<N> inv;
-	__shared__ uint32_t sh_inv[ECC_CTA_INV_WORDS(N)];
-	cta_inverse_128<typename C::Fp>(inv, acc, sh_inv); /* one Fermat chain per CTA instead of one per thread */
+	__shared__ __align__(16) uint32_t sh_inv[ECC_CTA_INV_WORDS(N)]; /* reused by the gather stores below */
+	cta_inverse_128<typename C::Fp>(inv, acc, sh_inv); /* one inversion per CTA instead of one per thread */
 	if (active)
 	for (uint32_t e = last;; e -= T) {
-		Fe<N> z, pre, X, Y;
+		Fe<N> z, pre, X, Y, gx, gy; /* gx, gy, gst: what the gather stores for this item (MODE 0) */
+		int8_t gst = 0;
 		const uint32_t *b = jac + (size_t)e * (3 * N);
 		load_words<N>(z, b + 2 * N);
 		bool inf = F::is_zero(z);
@@ -630,12 +631,9 @@ __global__ void __launch_bounds__(128) k_to_affine(uint32_t n, const uint32_t *_
 				store_wire<N, PL>(out + (size_t)e * (2 * PL), t);
 				store_wire<N, PL>(out + (size_t)e * (2 * PL) + PL, zi);
 				if (MODE == 0) {
-					const int8_t st = err ? (int8_t)-1 : (int8_t)0;
-					for (int j = 0; j < gd.n; j++) {
-						store_wire<N, PL>(gd.out[j] + (size_t)e * (2 * PL), t);
-						store_wire<N, PL>(gd.out[j] + (size_t)e * (2 * PL) + PL, zi);
-						gd.status[j][e] = st;
-					}
+					gx = t;
+					gy = zi;
+					gst = err ? (int8_t)-1 : (int8_t)0;
 				}
 			}
 		} else {
@@ -652,11 +650,55 @@ __global__ void __launch_bounds__(128) k_to_affine(uint32_t n, const uint32_t *_
 				store_wire<N, PL>(out + (size_t)e * (2 * PL) + PL, zero);
 				if (!err) status[e] = 1;
 				if (MODE == 0) {
-					for (int j = 0; j < gd.n; j++) {
-						store_wire<N, PL>(gd.out[j] + (size_t)e * (2 * PL), zero);
-						store_wire<N, PL>(gd.out[j] + (size_t)e * (2 * PL) + PL, zero);
-						gd.status[j][e] = err ? (int8_t)-1 : (int8_t)1;
-					}
+					gx = zero;
+					gy = zero;
+					gst = err ? (int8_t)-1 : (int8_t)1;
+				}
+			}
+		}
+		if (MODE == 0 && gd.n > 0) {
+			/* the gather stores.  A fully active warp holds 32 consecutive items = 32 * 2*PL contiguous bytes per
+			 * destination: they are transposed through shared memory so that every store instruction writes 512
+			 * contiguous bytes (whole 128-byte lines on the NVLink) instead of 32 separate 16-byte pieces. */
+			const unsigned act = __activemask();
+			const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+			bool coop = (N % 4 == 0) && (PL == 4 * N) && act == 0xffffffffu;
+			if (coop) { /* all 32 lanes are here together: are they also on the same pass over the batch? */
+				const uint32_t first = e - (uint32_t)lane;
+				coop = __all_sync(0xffffffffu, first == __shfl_sync(0xffffffffu, first, 0));
+			}
+			if (coop) {
+				constexpr int W4 = 2 * N / 4;               /* uint4 per item */
+				uint4 *row = reinterpret_cast<uint4 *>(sh_inv) + warp * (32 * W4 + 2);
+#pragma unroll
+				for (int k = 0; k < N / 4; k++) {
+					uint4 vx, vy;
+					vx.x = bswap32(gx.w[N - 1 - 4 * k]);
+					vx.y = bswap32(gx.w[N - 2 - 4 * k]);
+					vx.z = bswap32(gx.w[N - 3 - 4 * k]);
+					vx.w = bswap32(gx.w[N - 4 - 4 * k]);
+					vy.x = bswap32(gy.w[N - 1 - 4 * k]);
+					vy.y = bswap32(gy.w[N - 2 - 4 * k]);
+					vy.z = bswap32(gy.w[N - 3 - 4 * k]);
+					vy.w = bswap32(gy.w[N - 4 - 4 * k]);
+					row[lane * W4 + k] = vx;
+					row[lane * W4 + N / 4 + k] = vy;
+				}
+				reinterpret_cast<int8_t *>(row + 32 * W4)[lane] = gst;
+				__syncwarp();
+				const size_t e0 = (size_t)(e - (uint32_t)lane); /* item of lane 0 (consecutive lanes, consecutive items) */
+				for (int j = 0; j < gd.n; j++) {
+					uint4 *dst = reinterpret_cast<uint4 *>(gd.out[j] + e0 * (2 * PL));
+#pragma unroll
+					for (int k = 0; k < W4; k++) dst[k * 32 + lane] = row[k * 32 + lane];
+					if (lane < 2) reinterpret_cast<uint4 *>(gd.status[j] + e0)[lane] = row[32 * W4 + lane];
+				}
+				__syncwarp();
+			} else {
+				for (int j = 0; j < gd.n; j++) {
+					store_wire<N, PL>(gd.out[j] + (size_t)e * (2 * PL), gx);
+					store_wire<N, PL>(gd.out[j] + (size_t)e * (2 * PL) + PL, gy);
+					gd.status[j][e] = gst;
 				}
 			}
 		}
@@ -1152,6 +1194,7 @@ static inline uint32_t grid_clustered(uint32_t n)
 template <class C> struct LaunchFixed {
 	static void fixed(uint32_t n, const uint8_t *scalars, const uint32_t *table, int w, uint32_t *jac,
 			  int8_t *status, cudaStream_t st);
+	static int fixed_ctas_per_sm(); /* resident CTAs of k_smul_fixed per SM (register-limited): the wave size */
 	static void fixed_tma(uint32_t n, const uint8_t *scalars, const uint32_t *table, int w, uint32_t *jac,
 			      int8_t *status, cudaStream_t st);
 	static void table_merge(uint32_t count, uint64_t first_entry, int w, int nwin_half, const uint32_t *half_table,
@@ -1202,6 +1245,15 @@ void LaunchFixed<C>::fixed(uint32_t n, const uint8_t *scalars, const uint32_t *t
 			   int8_t *status, cudaStream_t st)
 {
 	k_smul_fixed<C><<<grid_for(n), kThreads, 0, st>>>(n, scalars, table, w, jac, status);
+}
+template <class C> int LaunchFixed<C>::fixed_ctas_per_sm()
+{
+	int nb = 0;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_smul_fixed<C>, kThreads, 0) != cudaSuccess || nb < 1) {
+		cudaGetLastError();
+		nb = 4;
+	}
+	return nb;
 }
 template <class C>
 void LaunchFixed<C>::fixed_tma(uint32_t n, const uint8_t *scalars, const uint32_t *table, int w, uint32_t *jac,

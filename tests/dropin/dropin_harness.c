@@ -283,6 +283,50 @@ static int run_direct(const char *dropin_path)
 			}
 			CHECK(v[3] == -1 && v[7] == -1 && v[11] == -1, "corrupted ECFSDSA items not flagged");
 		}
+		/* ---- BIP0340 in the same slot and through the ec_verify shim: against the reference's ec_verify */
+		{
+			enum { NB3 = 20 };
+			static ec_key_pair kp[NB3];
+			static u8 sigs[NB3][2 * 66], msgs[NB3][40];
+			const u8 *sp[NB3], *mp[NB3];
+			const ec_pub_key *pk[NB3];
+			u8 sl[NB3], plen = (u8)BYTECEIL(params.ec_fp.p_bitlen);
+			u32 ml[NB3];
+			hash_alg_type ht = (c == 2) ? SHA384 : ((c == 5 || c == 7) ? SHA512 : SHA256);
+			vbatch_fn gpu_bipbatch = (vbatch_fn)dlsym(h, "eccb200_dropin_bip0340_verify_batch");
+			CHECK(gpu_bipbatch != NULL, "missing eccb200_dropin_bip0340_verify_batch");
+			int usable = gpu_bipbatch != NULL;
+			for (int i = 0; i < NB3 && usable; i++) {
+				if (ec_key_pair_gen(&kp[i], &params, BIP0340)) { usable = 0; break; }
+				ml[i] = (u32)(1 + (rnd8() % 39));
+				for (u32 j = 0; j < ml[i]; j++) msgs[i][j] = rnd8();
+				sl[i] = (u8)(plen + qlen);
+				if (ec_sign(sigs[i], sl[i], &kp[i], msgs[i], ml[i], BIP0340, ht, NULL, 0)) { usable = 0; break; }
+				sp[i] = sigs[i];
+				mp[i] = msgs[i];
+				pk[i] = &kp[i].pub_key;
+			}
+			if (usable) {
+				int r = gpu_bipbatch(sp, sl, pk, mp, ml, NB3, BIP0340, ht, NULL, NULL, NULL, NULL);
+				CHECK(r == 0, "%s bip0340 verify_batch: valid batch rejected", names[c]);
+				sigs[2][plen + 1] ^= 0x10; /* s */
+				sigs[6][3] ^= 1;           /* r */
+				msgs[9][0] ^= 1;
+				r = gpu_bipbatch(sp, sl, pk, mp, ml, NB3, BIP0340, ht, NULL, NULL, NULL, NULL);
+				CHECK(r == -1, "%s bip0340 verify_batch: corrupted batch accepted", names[c]);
+				signed char v[NB3];
+				CHECK(gpu_verdicts(v, NB3) == NB3, "verdict count");
+				for (int i = 0; i < NB3; i++) {
+					int want = ec_verify(sigs[i], sl[i], pk[i], msgs[i], ml[i], BIP0340, ht, NULL, 0) ? -1 : 0;
+					CHECK(v[i] == want, "%s bip0340 verdict[%d] = %d, reference ec_verify says %d", names[c], i, v[i], want);
+					int got = gpu_everify(sigs[i], sl[i], pk[i], msgs[i], ml[i], BIP0340, ht, NULL, 0) ? -1 : 0;
+					CHECK(got == want, "%s bip0340 ec_verify shim item %d: %d vs %d", names[c], i, got, want);
+				}
+				CHECK(v[2] == -1 && v[6] == -1 && v[9] == -1, "corrupted BIP0340 items not flagged");
+			} else {
+				printf("note: the reference does not sign BIP0340 on %s here; skipped\n", names[c]);
+			}
+		}
 		printf("direct %s done, failures so far %d\n", names[c], failures);
 	}
 	return failures != 0;
