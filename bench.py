@@ -11,9 +11,10 @@ GPUs) are measured by the same code on short runs and reported in the `extra` bl
 Ours arm, per step and per rank (one process per GPU; torchrun for N > 1) — the SAME timing protocol at every N:
   value  : inputs resident in HBM, eccb200_*_batch_dev on torch's current stream; per-step CUDA events with the L2
            flush between steps outside them; sum over the K steps, max over ranks.  For N > 1 the step includes the
-           result gather: the normalisation kernel of every rank stores its results straight into rank 0's gathered
-           buffer over NVLink (peer-mapped memory) and rank 0's step ends only when every rank's results have landed
-           (--gather peer-root, default; peer-all = every rank receives everything; nccl = one all_gather per step).
+           result gather (--gather peer-root, default): a copy-engine push of every rank's results into rank 0's
+           gathered buffer over NVLink (peer-mapped memory), pipelined one step behind the kernels, the last push waited
+           for inside the timed region; peer-all = every rank receives everything; fused-* = the normalisation kernel
+           stores into the peers itself; nccl = one all_gather per step.
   e2e    : the host-pointer C-ABI call (eccb200_prj_pt_mul_batch / eccb200_ecdsa_verify_msgs_batch) on host buffers:
            host->device copy of the step's inputs and device->host copy of its results inside the timed region.
   roofline: the dominant kernel's own duration (CUDA events recorded by the library around that kernel on the
@@ -447,9 +448,10 @@ class Ours:
         self.pg = None
         self.step_no = 0
         self.last_buf = 0
-        if self.gather.startswith("peer"):
+        if self.gather.startswith(("peer", "fused")):
             from libecc_b200.sharding import PeerGather
-            self.pg = PeerGather(self.eng, rank, world, n, mode="root" if self.gather == "peer-root" else "all")
+            self.pg = PeerGather(self.eng, rank, world, n, mode="root" if self.gather.endswith("root") else "all",
+                                 transport="ce" if self.gather.startswith("peer") else "fused")
         elif self.gather == "nccl":
             out_rec = 1 if self.kind == "verify" else 2 * plen
             self.res_bytes = n * out_rec + (0 if self.kind == "verify" else n)
@@ -468,7 +470,10 @@ class Ours:
                                             d["offsets"], d["digests"], out, stream)
         elif self.pg is not None:
             pts = d["points"].data_ptr() if self.kind == "var" else None
-            self.last_buf = self.pg.step(sc.data_ptr(), pts, self.d_out.data_ptr(), self.d_status.data_ptr(), stream)
+            if self.pg.transport == "ce":
+                self.last_buf = self.pg.step_ce(sc.data_ptr(), pts, self.dev)
+            else:
+                self.last_buf = self.pg.step(sc.data_ptr(), pts, self.d_out.data_ptr(), self.d_status.data_ptr(), stream)
         else:
             if self.gather == "nccl":
                 out, st = self.res[: n * 2 * self.plen], self.res[n * 2 * self.plen:].view(torch.int8)
@@ -505,12 +510,21 @@ class Ours:
             evs[s][1].record()
             if (s & 7) == 7:                        # reading waits for the kernels: let the host run 8 steps ahead
                 kernel_ms.append(eng.profile_read())
+        drain = None
+        if self.pg is not None and self.pg.transport == "ce":
+            # the pushes are pipelined one step behind the kernels: the last one is waited for inside the timed region
+            drain = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            drain[0].record()
+            self.pg.drain(self.dev)
+            drain[1].record()
         rest = eng.profile_read()
         if rest:
             kernel_ms.append(rest)
         self.sync_all()
         clocks = sampler.stop()
         step_ms = [a.elapsed_time(b) for a, b in evs]          # per-step events: the flush is outside them, at every N
+        if drain is not None:
+            step_ms[-1] += drain[0].elapsed_time(drain[1])
         total = torch.tensor([sum(step_ms)], dtype=torch.float64, device=self.dev)
         k2_ms = sum(k[1] for k in kernel_ms if len(k) > 1) / steps
         k1 = torch.tensor([sum(k[0] for k in kernel_ms if k) / steps, k2_ms, sum(step_ms) / steps], dtype=torch.float64,
@@ -540,6 +554,9 @@ class Ours:
                     self.res[n * 2 * self.plen:].view(torch.int8).cpu().numpy())
         if self.kind == "verify":
             return (self.d_out.cpu().numpy(),)
+        if self.pg is not None and self.pg.transport == "ce":     # the kernels wrote into the gather's own buffers
+            raw = self.eng.copy_to_host(self.pg.last_src, n * 2 * self.plen + n)
+            return raw[: n * 2 * self.plen].reshape(n, 2 * self.plen), raw[n * 2 * self.plen:].view(np.int8)
         return self.d_out.cpu().numpy().reshape(n, 2 * self.plen), self.d_status.cpu().numpy()
 
     def ensure_last_step_used_set_a(self):
@@ -581,9 +598,12 @@ class Ours:
         if self.kind != "fixed":
             return out
         slot = n * 2 * self.plen + n
-        mine = torch.cat([self.d_out if self.gather != "nccl" else self.res[: n * 2 * self.plen],
-                          (self.d_status if self.gather != "nccl" else self.res[n * 2 * self.plen:].view(torch.int8))
-                          .view(torch.uint8)])
+        if self.pg is not None and self.pg.transport == "ce":
+            mine = torch.from_numpy(self.eng.copy_to_host(self.pg.last_src, slot)).to(self.dev)
+        else:
+            mine = torch.cat([self.d_out if self.gather != "nccl" else self.res[: n * 2 * self.plen],
+                              (self.d_status if self.gather != "nccl" else self.res[n * 2 * self.plen:].view(torch.int8))
+                              .view(torch.uint8)])
         via_nccl = torch.empty(world * slot, dtype=torch.uint8, device=self.dev)
         dist.all_gather_into_tensor(via_nccl, mine)            # outside every timed region
         torch.cuda.synchronize()
@@ -721,8 +741,9 @@ def main():
     ap.add_argument("--workload", default="secp256r1_fixed_base", choices=sorted(WORKLOADS))
     ap.add_argument("--batch-log2", type=int, default=20, help="items per GPU per step (2^k)")
     ap.add_argument("--comb-window", type=int, default=0)
-    ap.add_argument("--gather", default="peer-root", choices=["peer-root", "peer-all", "nccl"],
-                    help="N > 1: how the per-step results are gathered")
+    ap.add_argument("--gather", default="peer-root", choices=["peer-root", "peer-all", "fused-root", "fused-all", "nccl"],
+                    help="N > 1: how the per-step results are gathered (peer-*: copy-engine pushes into peer memory, "
+                         "pipelined one step behind the kernels; fused-*: stores of the normalisation kernel itself)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other BASELINE.json configs")
     args = ap.parse_args()
@@ -775,12 +796,15 @@ def main():
 
     o._k4_ms = m["normalisation_ms"]
     roofline = o.roofline(m["kernel_ms"], m["ms_per_step"])
-    gather_desc = {"none": "none",
-                   "peer-root": "fused into the normalisation kernel: every rank's K4 stores its results straight into rank "
-                                "0's gathered buffer over NVLink (CUDA-IPC peer memory) and signals arrival; rank 0's step "
-                                "ends when all ranks' results have landed; double-buffered with acknowledgements; no "
-                                "collective kernel",
-                   "peer-all": "as peer-root, but every rank receives every rank's results (all-gather semantics)",
+    ce_desc = ("every rank's normalisation kernel writes its results locally; a copy-engine transfer on a side stream "
+               "(cudaMemcpyAsync to CUDA-IPC peer memory over NVLink, no SM involved) pushes them into {dst} gathered "
+               "buffer while the NEXT step's kernels run, then publishes an arrival counter; the destination waits for "
+               "step s-1's arrivals at the end of step s and for the last step's inside the timed region (drain); "
+               "double-buffered with acknowledgements; no collective kernel")
+    gather_desc = {"none": "none", "fused-root": "fused into the normalisation kernel (stores straight into rank 0's buffer)",
+                   "fused-all": "fused into the normalisation kernel (stores into every rank's buffer)",
+                   "peer-root": ce_desc.format(dst="rank 0's"),
+                   "peer-all": ce_desc.format(dst="every rank's"),
                    "nccl": "one nccl all_gather per step on the compute stream, inside the step's events"}[o.gather]
     line = {"metric": o.metric, "value": m["value"], "unit": o.unit, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True,

@@ -107,6 +107,12 @@ int eccb200_prj_pt_mul_batch_dev_gather(eccb200_ctx *ctx, uint32_t n, const uint
 					uint8_t *const *dst_out, int8_t *const *dst_status, uint32_t *const *dst_flag,
 					uint32_t flag_value, const uint32_t *d_wait_flags, int wait_count,
 					uint32_t wait_value, void *stream);
+/* Copy-engine form of the same gather: DMA `bytes` from d_src to up to 8 peer-mapped destinations on `stream` (NVLink,
+ * no SM involved), after the destinations' acknowledgements (d_wait_flags, in this GPU's memory) if wait_count > 0,
+ * then publish flag_value to *dst_flag[j].  Used pipelined: the push of step s overlaps the kernels of step s + 1. */
+int eccb200_push_results(eccb200_ctx *ctx, int n_dst, void *const *dst, const void *d_src, size_t bytes,
+			 uint32_t *const *dst_flag, uint32_t flag_value, const uint32_t *d_wait_flags, int wait_count,
+			 uint32_t wait_value, void *stream);
 /* Device memory that other processes on the box can map: cudaMalloc + cudaIpcGetMemHandle (zero-filled).  The
  * 64-byte handle is passed to the peers by any means (bench.py: torch.distributed); they map it with
  * eccb200_ipc_open (peer access over NVLink is enabled on first use) and unmap it with eccb200_ipc_close. */

@@ -37,7 +37,7 @@ ABI_SYMBOLS = [
     "eccb200_multi_prj_pt_mul_batch", "eccb200_multi_ecdsa_verify_batch",
     "eccb200_ecdsa_verify_msgs_batch_dev", "eccb200_copy_to_host", "eccb200_ecdsa_verify_keystate_batch",
     "eccb200_fp_addsub_batch", "eccb200_ecdsa_verify_prj_batch", "eccb200_bip0340_verify_batch",
-    "eccb200_bip0340_verify_batch_dev",
+    "eccb200_bip0340_verify_batch_dev", "eccb200_push_results",
 ]
 
 _lib = None
@@ -92,6 +92,7 @@ def load_library() -> ctypes.CDLL:
     vp, u64 = ctypes.c_void_p, ctypes.c_uint64
     lib.eccb200_prj_pt_mul_batch_dev_gather.argtypes = [vp, u32, u8p, u8p, u8p, i8p, ctypes.c_int, vp, vp, vp, u32,
                                                         vp, ctypes.c_int, u32, vp]
+    lib.eccb200_push_results.argtypes = [vp, ctypes.c_int, vp, vp, ctypes.c_size_t, vp, u32, vp, ctypes.c_int, u32, vp]
     lib.eccb200_ipc_alloc.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(vp), vp]
     lib.eccb200_ipc_open.argtypes = [vp, vp, ctypes.POINTER(vp)]
     lib.eccb200_ipc_close.argtypes = [vp, vp]
@@ -491,6 +492,16 @@ class Engine:
             p_wait_flags, wait_count, wait_value & 0xFFFFFFFF, ctypes.c_void_p(stream_handle)),
             "eccb200_prj_pt_mul_batch_dev_gather")
 
+    def push_results(self, dst_ptrs, p_src: int, nbytes: int, dst_flags, flag_value: int, p_wait_flags, wait_count: int,
+                     wait_value: int, stream_handle: int = 0):
+        k = len(dst_ptrs)
+        a_dst = (ctypes.c_void_p * k)(*[ctypes.c_void_p(x) for x in dst_ptrs])
+        a_fl = (ctypes.c_void_p * k)(*[ctypes.c_void_p(x) for x in dst_flags])
+        self._check(self.lib.eccb200_push_results(self._h, k, a_dst, ctypes.c_void_p(p_src), nbytes, a_fl,
+                                                  flag_value & 0xFFFFFFFF, p_wait_flags, wait_count,
+                                                  wait_value & 0xFFFFFFFF, ctypes.c_void_p(stream_handle)),
+                    "eccb200_push_results")
+
     def ipc_alloc(self, nbytes: int):
         p = ctypes.c_void_p()
         h = (ctypes.c_uint8 * 64)()
@@ -517,6 +528,11 @@ class Engine:
         a = (ctypes.c_void_p * len(flag_ptrs))(*[ctypes.c_void_p(x) for x in flag_ptrs])
         self._check(self.lib.eccb200_flag_signal(self._h, a, len(flag_ptrs), value & 0xFFFFFFFF,
                                                  ctypes.c_void_p(stream_handle)), "eccb200_flag_signal")
+
+    def prj_pt_mul_batch_dev_raw(self, n: int, p_scalars: int, p_points, p_out: int, p_status: int, stream_handle: int = 0):
+        """eccb200_prj_pt_mul_batch_dev on raw device addresses (ints)."""
+        self._check(self.lib.eccb200_prj_pt_mul_batch_dev(self._h, n, p_scalars, p_points, p_out, p_status,
+                                                          ctypes.c_void_p(stream_handle)), "eccb200_prj_pt_mul_batch_dev")
 
     def ecdsa_verify_batch_dev(self, d_sigs, d_pubkeys, d_digests, hlen: int, d_verdict, stream_handle: int = 0):
         n = d_sigs.numel() // (2 * self.qlen)

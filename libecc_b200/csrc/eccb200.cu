@@ -601,6 +601,35 @@ extern "C" int eccb200_prj_pt_mul_batch_dev_gather(eccb200_ctx *ctx, uint32_t n,
 			nullptr, nullptr, n_dst ? &gd : nullptr, d_wait_flags, wait_count, wait_value);
 }
 
+/*
+ * Copy-engine form of the gather: push `bytes` of local results to up to ECC_MAX_GATHER_DST peer-mapped buffers with
+ * DMA transfers (cudaMemcpyAsync on peer pointers: NVLink, no SM involved) on `stream`, then publish flag_value to the
+ * destinations' arrival flags.  If wait_count > 0 the transfers first wait for the destinations' acknowledgements
+ * (flags in this GPU's memory).  The caller orders `stream` behind the kernels that produce `d_src` (an event).
+ */
+extern "C" int eccb200_push_results(eccb200_ctx *ctx, int n_dst, void *const *dst, const void *d_src, size_t bytes,
+				    uint32_t *const *dst_flag, uint32_t flag_value, const uint32_t *d_wait_flags,
+				    int wait_count, uint32_t wait_value, void *stream)
+{
+	if (!ctx || !d_src || n_dst <= 0 || n_dst > ECC_MAX_GATHER_DST || !dst || !dst_flag) return fail("bad argument");
+	CUDA_OK(cudaSetDevice(ctx->device));
+	cudaStream_t st = (cudaStream_t)stream;
+	if (d_wait_flags && wait_count > 0) {
+		k_flag_wait<<<1, 32, 0, st>>>(d_wait_flags, wait_count, wait_value);
+		ctx->launches += 1;
+	}
+	FlagList fl;
+	for (int j = 0; j < n_dst; j++) {
+		if (!dst[j] || !dst_flag[j]) return fail("null destination");
+		CUDA_OK(cudaMemcpyAsync(dst[j], d_src, bytes, cudaMemcpyDeviceToDevice, st));
+		fl.p[j] = dst_flag[j];
+	}
+	k_flag_signal<<<1, 32, 0, st>>>(fl, n_dst, flag_value);
+	ctx->launches += 1;
+	CUDA_OK(cudaGetLastError());
+	return 0;
+}
+
 extern "C" int eccb200_flag_wait(eccb200_ctx *ctx, const uint32_t *d_flags, int count, uint32_t value, void *stream)
 {
 	if (!ctx || !d_flags || count <= 0 || count > 1024) return fail("bad argument");

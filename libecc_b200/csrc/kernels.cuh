@@ -608,12 +608,22 @@ __global__ void __launch_bounds__(128) k_to_affine(uint32_t n, const uint32_t *_
 			F::mul(zi, inv, pre);  /* 1/z_e */
 			F::mul(t, inv, z);
 			inv = t;               /* drop z_e from the running inverse */
-			if (MODE == 2) {
-				zi2 = zi;
-				zi3 = zi;
-			} else {
+			if (TABLE) { /* Montgomery-form output: 1/z^2, 1/z^3 stay in the Montgomery domain */
 				F::sqr(zi2, zi);
 				F::mul(zi3, zi2, zi);
+			} else {
+				/* byte output: take 1/z OUT of the Montgomery domain once (zp = z^-1 as a plain integer); products of
+				 * a plain factor and a Montgomery-form factor are plain, so X * zp^2 and Y * zp^3 come out as the
+				 * plain coordinates directly — one product less than normalising in the domain and leaving it twice */
+				Fe<N> zp;
+				F::from_mont(zp, zi);
+				if (MODE == 2) {
+					zi2 = zp;
+					zi3 = zp;
+				} else {
+					F::mul(zi2, zp, zi);
+					F::mul(zi3, zi2, zi);
+				}
 			}
 			F::mul(t, X, zi2);
 			X = t;
@@ -623,11 +633,11 @@ __global__ void __launch_bounds__(128) k_to_affine(uint32_t n, const uint32_t *_
 				store_words<N>(table_out + (size_t)e * (2 * N), X);
 				store_words<N>(table_out + (size_t)e * (2 * N) + N, Y);
 			} else if (MODE == 3) {
-				F::from_mont(t, X);
+				t = X;
 				store_wire<N, PL>(out + (size_t)e * PL, t);
 			} else {
-				F::from_mont(t, X);
-				F::from_mont(zi, Y);
+				t = X;
+				zi = Y;
 				store_wire<N, PL>(out + (size_t)e * (2 * PL), t);
 				store_wire<N, PL>(out + (size_t)e * (2 * PL) + PL, zi);
 				if (MODE == 0) {

@@ -75,8 +75,17 @@ def gather_destinations(world: int, mode: str):
 class PeerGather:
     """Per-rank state of the peer-memory gather for fixed-size batches of `n_items` results."""
 
-    def __init__(self, eng, rank: int, world: int, n_items: int, mode: str = "root", nbuf: int = 2, group=None):
+    def __init__(self, eng, rank: int, world: int, n_items: int, mode: str = "root", nbuf: int = 2, group=None,
+                 transport: str = "fused"):
+        """transport 'fused': the normalisation kernel stores into the destinations itself (step);
+        'ce': the kernel writes locally and a copy-engine transfer on a side stream pushes the slot to the destinations
+        while the NEXT batch computes (step_ce / drain)."""
         self.group = group
+        self.transport = transport
+        self.copy_stream = None
+        self.copy_done = {}
+        self.local = {}
+        self.last_src = 0
         self.eng, self.rank, self.world, self.n, self.nbuf = eng, rank, world, n_items, nbuf
         self.layout = gather_layout(world, n_items, eng.plen, nbuf)
         self.dests = gather_destinations(world, mode)
@@ -126,6 +135,71 @@ class PeerGather:
                 self.eng.flag_signal(acks[i:i + 8], c, stream)
         self.step_no += 1
         return b
+
+    # ---- copy-engine transport ---------------------------------------------------------------------------------
+    def step_ce(self, p_scalars: int, p_points, device=None):
+        """One batch on torch's current stream C with the push on the side stream X:
+          C: [wait until this buffer's previous push has left] K1, K4 -> the rank's own slot (a destination writes
+             straight into its region; a pure source into a local buffer of the same layout)
+          X: after K4: [wait for the destinations' release of the slot] DMA slot -> every other destination, then
+             publish arrive[rank] = c there
+          destination, on C: publish the own arrival, wait for every rank's PREVIOUS batch (its push overlapped this
+             batch's kernels), release it.  drain() closes the pipeline.  Returns the buffer index."""
+        c = self.step_no + 1
+        b = self.step_no % self.nbuf
+        L = self.layout
+        used = self.n * 2 * self.eng.plen + self.n
+        C = torch.cuda.current_stream(device)
+        if self.copy_stream is None:
+            self.copy_stream = torch.cuda.Stream(device=device)
+        X = self.copy_stream
+        if self.rank in self.dests:
+            src = self.base + slot_offset(L, b, self.rank)
+        else:
+            if b not in self.local:
+                self.local[b] = torch.empty(L["slot_bytes"], dtype=torch.uint8, device=device)
+            src = self.local[b].data_ptr()
+        if b in self.copy_done:
+            C.wait_event(self.copy_done[b])          # the push that last read this buffer has completed
+        self.eng.prj_pt_mul_batch_dev_raw(self.n, p_scalars, p_points, src, src + L["status_offset"], C.cuda_stream)
+        others = [d for d in self.dests if d != self.rank]
+        if others:
+            ev = torch.cuda.Event()
+            ev.record(C)
+            X.wait_event(ev)
+            need_ack = c - self.nbuf
+            wait_ptr, wait_cnt = self._ack_wait_ptr() if need_ack >= 1 else (None, 0)
+            self.eng.push_results([self.peer[d] + slot_offset(L, b, self.rank) for d in others], src, used,
+                                  [self.peer[d] + L["flags"] + 4 * self.rank for d in others], c, wait_ptr, wait_cnt,
+                                  max(need_ack, 0), X.cuda_stream)
+            done = torch.cuda.Event()
+            done.record(X)
+            self.copy_done[b] = done
+        if self.rank in self.dests:
+            self.eng.flag_signal([self.base + L["flags"] + 4 * self.rank], c, C.cuda_stream)   # own slot is written
+            if c >= 2:
+                self._consume(c - 1, C.cuda_stream)
+        self.last_src = src
+        self.step_no += 1
+        return b
+
+    def _consume(self, upto: int, stream: int):
+        """Destination: wait until every rank's batches up to `upto` have landed, then release them."""
+        L = self.layout
+        self.eng.flag_wait(self.base + L["flags"], self.world, upto, stream)
+        # ... a consumer of buffer (upto - 1) % nbuf would run here ...
+        acks = [self.peer[r] + L["ack"] + 4 * self.rank for r in range(self.world)]
+        for i in range(0, len(acks), 8):
+            self.eng.flag_signal(acks[i:i + 8], upto, stream)
+
+    def drain(self, device=None):
+        """Closes the pipeline of step_ce on the current stream: a destination waits for (and releases) the last
+        batch of every rank; a source waits until its last push has left."""
+        C = torch.cuda.current_stream(device)
+        if self.rank in self.dests and self.step_no >= 1:
+            self._consume(self.step_no, C.cuda_stream)
+        for ev in self.copy_done.values():
+            C.wait_event(ev)
 
     def _ack_wait_ptr(self):
         d = sorted(self.dests)

@@ -136,23 +136,33 @@ torch.cuda.set_device(rank)
 dev = torch.device("cuda", rank)
 dist.init_process_group("nccl", device_id=dev)
 curve, n = "SECP256R1", 50000
-for mode in ("root", "all"):
+for mode, transport in (("root", "fused"), ("all", "fused"), ("root", "ce"), ("all", "ce")):
     eng = libecc_b200.Engine(curve, device=rank, comb_window=12)
-    pg = PeerGather(eng, rank, world, n, mode=mode)
+    pg = PeerGather(eng, rank, world, n, mode=mode, transport=transport)
     d_out = torch.zeros(n * 64, dtype=torch.uint8, device=dev); d_st = torch.zeros(n, dtype=torch.int8, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
+    keep = []
     for step in range(5):
         sc = random_scalars(curve, n, tag=1000 * step + rank, below_q=False)
         d_sc = torch.from_numpy(sc).to(dev)
-        b = pg.step(d_sc.data_ptr(), None, d_out.data_ptr(), d_st.data_ptr(), stream)
+        keep.append(d_sc)                      # the pipelined transport runs behind the host
+        if transport == "ce":
+            b = pg.step_ce(d_sc.data_ptr(), None, dev)
+        else:
+            b = pg.step(d_sc.data_ptr(), None, d_out.data_ptr(), d_st.data_ptr(), stream)
+            torch.cuda.synchronize()
+    if transport == "ce":
+        pg.drain(dev)
         torch.cuda.synchronize()
-    mine = torch.cat([d_out, d_st.view(torch.uint8)])
+        mine = torch.from_numpy(eng.copy_to_host(pg.last_src, n * 65)).to(dev)
+    else:
+        mine = torch.cat([d_out, d_st.view(torch.uint8)])
     ref = torch.empty(world * mine.numel(), dtype=torch.uint8, device=dev)
     dist.all_gather_into_tensor(ref, mine)
     torch.cuda.synchronize()
     if rank in pg.dests:
         got = np.concatenate([eng.copy_to_host(pg.buffer_ptr(b, r), mine.numel()) for r in range(world)])
-        assert (got == ref.cpu().numpy()).all(), f"{mode}: gathered buffer differs from the NCCL all-gather"
+        assert (got == ref.cpu().numpy()).all(), f"{mode}/{transport}: gathered buffer differs from the NCCL all-gather"
         other = (rank + 1) % world
         want, wst = oracle_smul(curve, random_scalars(curve, n, tag=4000 + other, below_q=False)[:64])
         assert (got.reshape(world, -1)[other][: 64 * 64].reshape(64, 64) == want).all()
