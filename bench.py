@@ -780,10 +780,10 @@ def main():
             ok5 = o5.parity()
             g5 = o5.gather_checks()
             o5.close_gather()
+            o5.close()
             extra["config5_2^24_total"] = dict({"value": m5["value"], "ms_per_step": m5["ms_per_step"], "steps": 5,
                                                 "batch_per_gpu": 1 << per_gpu_log2, "global_batch": world << per_gpu_log2,
-                                                "kernel_ms_per_rank": m5["kernel_ms_per_rank"], "parity_spot_check": ok5}, **g5)
-            o5.close()
+                                                "per_rank": m5["kernel_ms_per_rank"], "parity_spot_check": ok5}, **g5)
 
     if world > 1:
         o.close_gather()            # collective: every rank unmaps its peers' regions before anybody frees its own

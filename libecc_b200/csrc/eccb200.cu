@@ -127,7 +127,9 @@ extern "C" const char *eccb200_curve_name(int curve_id)
  * inversion over many items */
 static uint32_t affine_grid(const eccb200_ctx *ctx, uint32_t n)
 {
-	uint32_t want = grid_for(n);
+	/* every thread should own at least ~8 items: the CTA-wide inversion (16 products per thread) is shared by the
+	 * items a thread walks, so a pipeline chunk of one wave is normalised by ~90 CTAs rather than by 592 nearly idle ones */
+	uint32_t want = (n + kThreads * 8 - 1) / (kThreads * 8);
 	static int per_sm = 0; /* CTAs of 128 threads per SM; ECCB200_AFFINE_CTAS overrides (tuning knob) */
 	if (!per_sm) {
 		const char *e = getenv("ECCB200_AFFINE_CTAS");
