@@ -759,7 +759,12 @@ def main():
     import torch.distributed as dist
 
     torch.cuda.set_device(local_rank)
+    numa_cpus = None
+    full_affinity = os.sched_getaffinity(0)
     if world > 1:
+        # one process per GPU on a two-socket box: keep this rank's host threads and pinned buffers on its GPU's node
+        import libecc_b200
+        numa_cpus = libecc_b200.load_library().eccb200_bind_thread_near_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     default_workload = args.workload == "secp256r1_fixed_base" and args.batch_log2 == 20
     o = Ours(args.workload, args.batch_log2, args.comb_window, rank, world, local_rank, args.gather)
@@ -813,7 +818,7 @@ def main():
                            l2="256 MiB buffer rewritten between timed iterations (outside the per-step events, at every N)",
                            comb_window=o.eng.comb_window, result_gather=gather_desc,
                            timing="sum of per-step CUDA-event intervals on the compute stream, max over ranks"),
-            "clocks": m["clocks"], "gpu_launches": m["launches"],
+            "clocks": m["clocks"], "gpu_launches": m["launches"], "host_cpus_bound_near_gpu": numa_cpus,
             "e2e": dict(e2e, same_results_as_device_leg=e2e["parity"]),
             "roofline": roofline, "parity_spot_check": parity}
     line.update(gchk)
@@ -852,6 +857,7 @@ def main():
             # the in-process multi-device C ABI (eccb200_multi_*): ONE host call shards 2^24 scalars over all GPUs of
             # the box, each GPU DMAs its shard's results straight into the caller's pinned output
             try:
+                os.sched_setaffinity(0, full_affinity)     # the library binds its per-device worker threads itself
                 extra["multi_device_c_abi"] = run_multi_abi(args.workload, world, 24)
             except Exception as exc:           # noqa: BLE001
                 extra["multi_device_c_abi"] = {"error": str(exc)[:300]}

@@ -292,6 +292,11 @@ int eccb200_ecdsa_sign_structured_batch(eccb200_ctx *ctx, uint32_t n, const uint
 					int alg, int hash_type, const uint8_t *nonces, const uint8_t *digests,
 					uint32_t hlen, uint8_t *sig_records, int8_t *status);
 
+/* Binds the calling host thread to the CPUs local to `device` (its PCI device's local_cpulist): page-locked memory
+ * the thread allocates afterwards and the copies it performs stay on the GPU's NUMA node.  Returns the number of CPUs
+ * bound to, 0 if nothing was changed, -1 on error.  The multi-device calls do this for their worker threads. */
+int eccb200_bind_thread_near_device(int device);
+
 /* Page-locked host memory for the host-pointer entry points (wrappers of cudaHostAlloc / cudaFreeHost so that a C
  * caller need not link the CUDA runtime).  NULL on failure. */
 void *eccb200_host_alloc(size_t bytes);

@@ -1799,6 +1799,54 @@ extern "C" int eccb200_imad_peak(int device, double *imad32_per_s, double *imad_
 	return 0;
 }
 
+/* ------------------------------------------------------------------------------------------ NUMA placement */
+/*
+ * Binds the CALLING host thread to the CPUs that are local to `device` (/sys/bus/pci/devices/<bdf>/local_cpulist,
+ * intersected with the thread's current affinity).  Page-locked memory the thread allocates afterwards, and the
+ * staging copies it performs, then sit on the GPU's NUMA node, so that eight GPUs of a two-socket box do not all DMA
+ * through one socket's memory controllers (measured: bench.py e2e at N = 8).  Returns the number of CPUs bound to, 0 if
+ * nothing was changed, -1 on error.
+ */
+#include <sched.h>
+extern "C" int eccb200_bind_thread_near_device(int device)
+{
+	char bdf[64] = { 0 };
+	if (cudaDeviceGetPCIBusId(bdf, (int)sizeof(bdf) - 1, device) != cudaSuccess) {
+		cudaGetLastError();
+		return fail("cudaDeviceGetPCIBusId failed");
+	}
+	for (char *p = bdf; *p; p++)
+		if (*p >= 'A' && *p <= 'F') *p = (char)(*p - 'A' + 'a');
+	std::string path = std::string("/sys/bus/pci/devices/") + bdf + "/local_cpulist";
+	FILE *f = fopen(path.c_str(), "r");
+	if (!f) return 0;
+	char line[4096] = { 0 };
+	const bool got = fgets(line, sizeof(line) - 1, f) != nullptr;
+	fclose(f);
+	if (!got) return 0;
+	cpu_set_t cur, want;
+	CPU_ZERO(&want);
+	if (sched_getaffinity(0, sizeof(cur), &cur)) return 0;
+	int count = 0;
+	for (char *tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+		int a = 0, b = 0;
+		if (sscanf(tok, "%d-%d", &a, &b) == 2) {
+		} else if (sscanf(tok, "%d", &a) == 1) {
+			b = a;
+		} else {
+			continue;
+		}
+		for (int c = a; c <= b && c < CPU_SETSIZE; c++)
+			if (CPU_ISSET(c, &cur)) {
+				CPU_SET(c, &want);
+				count++;
+			}
+	}
+	if (count == 0) return 0;
+	if (sched_setaffinity(0, sizeof(want), &want)) return 0;
+	return count;
+}
+
 /* ------------------------------------------------------------------------------------------ multi-device (one process) */
 /*
  * SURVEY.md §8(b) "multi-GPU fan-out is internal", §8(e): a C host hands ONE batch to the library and the library
@@ -1839,6 +1887,7 @@ extern "C" int eccb200_multi_create(eccb200_multi **out, int curve_id, const int
 	std::vector<std::thread> th;
 	for (size_t g = 0; g < devs.size(); g++) /* the comb tables are built concurrently, one host thread per device */
 		th.emplace_back([&, g] {
+			eccb200_bind_thread_near_device(devs[g]); /* the context's pinned staging lands on the GPU's NUMA node */
 			rc[g] = eccb200_ctx_create(&m->ctx[g], curve_id, devs[g], comb_window);
 			if (rc[g]) msg[g] = eccb200_last_error();
 		});
@@ -1871,6 +1920,7 @@ template <class Fn> static int multi_run(eccb200_multi *m, uint64_t n, Fn &&fn)
 		const uint64_t lo = n * g / G, hi = n * (g + 1) / G;
 		if (hi == lo) continue;
 		th.emplace_back([&, g, lo, hi] {
+			eccb200_bind_thread_near_device(m->ctx[g]->device);
 			rc[g] = fn(m->ctx[g], lo, (uint32_t)(hi - lo));
 			if (rc[g]) msg[g] = eccb200_last_error();
 		});
