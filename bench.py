@@ -377,6 +377,7 @@ def run_reference(args, rank: int):
     # bounded sample: ~10 s of CPU work per step, less when many steps are asked for (whole run <= ~2-3 min)
     step_s = max(1.0, min(10.0, 120.0 / max(1, args.steps)))
     per_step = int(min(n, max(probe, (probe / t) * step_s)))
+    per_step = min(n, 1 << max(per_step.bit_length() - 1, 0))   # a power of two: the sample size is stable across runs
     for _ in range(min(args.warmup, 1)):
         cpu_run(args.workload, inputs, 0, min(per_step, 4 * probe), threads)
     times = []
