@@ -292,6 +292,13 @@ int eccb200_ecdsa_sign_structured_batch(eccb200_ctx *ctx, uint32_t n, const uint
 					int alg, int hash_type, const uint8_t *nonces, const uint8_t *digests,
 					uint32_t hlen, uint8_t *sig_records, int8_t *status);
 
+/* The chunking rule of the host-pointer pipeline as a pure function (no GPU needed; unit-tested on the CPU): chunk
+ * boundaries 0 = b[0] < ... < b[k] = n for a batch of n items, given the items of one kernel wave, the equal-chunk size,
+ * the capacity of the stage buffers and whether the ramp-up / ramp-down shaping applies (fixed-base pipelines).  Writes
+ * at most cap boundaries, returns their number (k + 1). */
+int eccb200_pipeline_chunk_bounds(uint32_t n, uint32_t wave_items, uint32_t equal_chunk_items, uint32_t capacity_items,
+				  int shaped, uint32_t *bounds, int cap);
+
 /* Binds the calling host thread to the CPUs local to `device` (its PCI device's local_cpulist): page-locked memory
  * the thread allocates afterwards and the copies it performs stay on the GPU's NUMA node.  Returns the number of CPUs
  * bound to, 0 if nothing was changed, -1 on error.  The multi-device calls do this for their worker threads. */

@@ -38,6 +38,7 @@ ABI_SYMBOLS = [
     "eccb200_ecdsa_verify_msgs_batch_dev", "eccb200_copy_to_host", "eccb200_ecdsa_verify_keystate_batch",
     "eccb200_fp_addsub_batch", "eccb200_ecdsa_verify_prj_batch", "eccb200_bip0340_verify_batch",
     "eccb200_bip0340_verify_batch_dev", "eccb200_push_results", "eccb200_bind_thread_near_device",
+    "eccb200_pipeline_chunk_bounds",
 ]
 
 _lib = None
@@ -110,6 +111,7 @@ def load_library() -> ctypes.CDLL:
     lib.eccb200_ecdsa_verify_msgs_batch_dev.argtypes = [vp, ctypes.c_int, u32, u8p, u8p, u8p, vp, u8p, i8p, vp]
     lib.eccb200_copy_to_host.argtypes = [vp, vp, vp, ctypes.c_size_t]
     lib.eccb200_bind_thread_near_device.argtypes = [ctypes.c_int]
+    lib.eccb200_pipeline_chunk_bounds.argtypes = [u32, u32, u32, u32, ctypes.c_int, vp, ctypes.c_int]
     lib.eccb200_fp_addsub_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, u32, u8p, u8p, u8p]
     lib.eccb200_ecdsa_verify_prj_batch.argtypes = [vp, u32, u8p, u8p, u8p, u32, i8p]
     lib.eccb200_bip0340_verify_batch.argtypes = [vp, u32, u8p, u8p, u8p, u32, i8p]

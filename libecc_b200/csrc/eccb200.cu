@@ -808,19 +808,17 @@ static int run_pipeline_body(eccb200_ctx *ctx, uint32_t n, std::vector<HostCol> 
  * safegcd inversion that latency is ~15 us and the shaping pays.  ECCB200_PIPE_SHAPE=0 restores equal
  * chunks.
  */
-static std::vector<uint32_t> pipeline_bounds(const eccb200_ctx *ctx, uint32_t n, bool ordered)
+static std::vector<uint32_t> chunk_bounds(uint32_t n, uint32_t w, uint32_t chunk_eq, uint32_t capacity, bool shaped)
 {
-	static const bool shape = !(getenv("ECCB200_PIPE_SHAPE") && atoi(getenv("ECCB200_PIPE_SHAPE")) == 0);
 	std::vector<uint32_t> bounds{ 0 };
-	const uint32_t w = ctx->wave;
-	if (!ordered || !shape || n <= 2 * w) {
+	if (!shaped || n <= 2 * w) {
 		for (uint32_t lo = 0; lo < n;) {
-			lo += std::min(ctx->chunk_eq, n - lo);
+			lo += std::min(chunk_eq, n - lo);
 			bounds.push_back(lo);
 		}
 		return bounds;
 	}
-	const uint32_t maxw = std::min<uint32_t>(ctx->chunk / w, (n / w >= 64) ? 8u : 4u);
+	const uint32_t maxw = std::min<uint32_t>(capacity / w, (n / w >= 64) ? 8u : 4u);
 	uint32_t lo = 0;
 	auto push = [&](uint32_t cnt) {
 		lo += cnt;
@@ -832,6 +830,24 @@ static std::vector<uint32_t> pipeline_bounds(const eccb200_ctx *ctx, uint32_t n,
 	if (n - lo > w) push(n - lo - w);
 	if (n - lo > 0) push(n - lo);
 	return bounds;
+}
+
+static std::vector<uint32_t> pipeline_bounds(const eccb200_ctx *ctx, uint32_t n, bool ordered)
+{
+	static const bool shape = !(getenv("ECCB200_PIPE_SHAPE") && atoi(getenv("ECCB200_PIPE_SHAPE")) == 0);
+	return chunk_bounds(n, ctx->wave, ctx->chunk_eq, ctx->chunk, ordered && shape);
+}
+
+/* The chunking rule as a pure function (host logic, testable without a GPU): writes at most cap boundaries
+ * (0 = b[0] < b[1] < ... = n) and returns how many there are. */
+extern "C" int eccb200_pipeline_chunk_bounds(uint32_t n, uint32_t wave_items, uint32_t equal_chunk_items,
+					     uint32_t capacity_items, int shaped, uint32_t *bounds, int cap)
+{
+	if (!bounds || cap < 2 || wave_items == 0 || equal_chunk_items == 0 || capacity_items < wave_items)
+		return fail("bad argument");
+	const std::vector<uint32_t> b = chunk_bounds(n, wave_items, equal_chunk_items, capacity_items, shaped != 0);
+	for (size_t i = 0; i < b.size() && (int)i < cap; i++) bounds[i] = b[i];
+	return (int)b.size();
 }
 
 template <class Launch>
