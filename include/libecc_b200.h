@@ -239,6 +239,20 @@ int eccb200_ecfsdsa_verify_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t
 				     const uint8_t *d_digests, uint32_t hlen, int8_t *d_verdict, void *stream);
 
 /*
+ * Batched double-scalar multiplication W_i = a_i*G + b_i*Y_i with affine results: the sequence prj_pt_mul, prj_pt_mul,
+ * prj_pt_add, prj_pt_unique that every Schnorr-type verification of the reference runs before it hashes the recomputed
+ * point (ECSDSA / ECOSDSA src/sig/ecsdsa_common.c:493-497, ECKCDSA, ...), as ONE kernel launch per batch: comb for G,
+ * signed window for Y, shared inversions.  The hashing of W' stays with the caller (src/hash).
+ *   ab      : n * 2*qlen bytes a || b, any values (reduced mod q like the reference's ladder)
+ *   pubkeys : n * 2*plen bytes affine x || y;  out : n * 2*plen bytes affine W (zero unless status is OK)
+ *   status  : ECCB200_OK / ECCB200_INFINITY (prj_pt_unique would fail) / ECCB200_ERR (key not on the curve)
+ */
+int eccb200_double_smul_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *ab, const uint8_t *pubkeys, uint8_t *out,
+			      int8_t *status);
+int eccb200_double_smul_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_ab, const uint8_t *d_pubkeys,
+				  uint8_t *d_out, int8_t *d_status, void *stream);
+
+/*
  * BIP0340 (Schnorr over x-only keys) verification, per item like ec_verify(…, BIP0340, …)
  * (src/sig/bip0340.c:383-577): sigs [n][plen + qlen] = r || s with r a field element < p and s < q; pubkeys affine
  * x || y as for ECDSA (the kernel lifts the key to its even-y representative, :540-545); digests[i] = the tagged hash

@@ -38,7 +38,7 @@ ABI_SYMBOLS = [
     "eccb200_ecdsa_verify_msgs_batch_dev", "eccb200_copy_to_host", "eccb200_ecdsa_verify_keystate_batch",
     "eccb200_fp_addsub_batch", "eccb200_ecdsa_verify_prj_batch", "eccb200_bip0340_verify_batch",
     "eccb200_bip0340_verify_batch_dev", "eccb200_push_results", "eccb200_bind_thread_near_device",
-    "eccb200_pipeline_chunk_bounds",
+    "eccb200_pipeline_chunk_bounds", "eccb200_double_smul_batch", "eccb200_double_smul_batch_dev",
 ]
 
 _lib = None
@@ -115,6 +115,8 @@ def load_library() -> ctypes.CDLL:
     lib.eccb200_fp_addsub_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, u32, u8p, u8p, u8p]
     lib.eccb200_ecdsa_verify_prj_batch.argtypes = [vp, u32, u8p, u8p, u8p, u32, i8p]
     lib.eccb200_bip0340_verify_batch.argtypes = [vp, u32, u8p, u8p, u8p, u32, i8p]
+    lib.eccb200_double_smul_batch.argtypes = [vp, u32, u8p, u8p, u8p, i8p]
+    lib.eccb200_double_smul_batch_dev.argtypes = [vp, u32, u8p, u8p, u8p, i8p, vp]
     lib.eccb200_bip0340_verify_batch_dev.argtypes = [vp, u32, u8p, u8p, u8p, u32, i8p, vp]
     lib.eccb200_ecdsa_verify_keystate_batch.argtypes = [vp, u32, u8p, u8p, i8p, u8p, u32, i8p]
     lib.eccb200_host_alloc.argtypes = [ctypes.c_size_t]
@@ -359,6 +361,17 @@ class Engine:
         self._check(self.lib.eccb200_ecfsdsa_verify_batch(self._h, n, sg.ctypes.data, pk.ctypes.data, dg.ctypes.data,
                                                           hlen, verdict.ctypes.data), "eccb200_ecfsdsa_verify_batch")
         return verdict
+
+    def double_smul_batch(self, ab, pubkeys) -> Tuple[np.ndarray, np.ndarray]:
+        """W_i = a_i*G + b_i*Y_i (affine); ab [n][2*qlen] = a || b."""
+        sc = _as_u8(ab)
+        n = sc.size // (2 * self.qlen)
+        pk = _as_u8(pubkeys, n * 2 * self.plen)
+        out = np.zeros((n, 2 * self.plen), dtype=np.uint8)
+        status = np.zeros(n, dtype=np.int8)
+        self._check(self.lib.eccb200_double_smul_batch(self._h, n, sc.ctypes.data, pk.ctypes.data, out.ctypes.data,
+                                                       status.ctypes.data), "eccb200_double_smul_batch")
+        return out, status
 
     def bip0340_verify_batch(self, sigs, pubkeys, digests, hlen: int) -> np.ndarray:
         """sigs [n][plen + qlen] = r || s; digests[i] = tagged hash of r_i || x(Y_i) || m_i."""

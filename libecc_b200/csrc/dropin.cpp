@@ -672,6 +672,149 @@ static int verify_batch_common(Scheme sc, const uint8_t **s, const uint8_t *s_le
 	return all;
 }
 
+/* big-endian bytes -> nn-style little-endian 64-bit words (at most kMaxWords) */
+static void be_to_nn(eccb200_nn *out, const uint8_t *be, uint32_t len)
+{
+	memset(out, 0, sizeof(*out));
+	for (uint32_t j = 0; j < len && j < 8u * kMaxWords; j++) out->val[j / 8] |= (uint64_t)be[len - 1 - j] << (8 * (j % 8));
+	out->wlen = (uint8_t)((std::min<uint32_t>(len, 8u * kMaxWords) + 7) / 8);
+	out->magic = kNnMagic;
+}
+
+/*
+ * ECSDSA / ECOSDSA (sig/ecsdsa_common.c:425-609): these schemes hash the RECOMPUTED point, so the batch is split the way
+ * the reference's own code is: host — checks, e = -(OS2I(r) mod q); device — W' = sG + eY for the whole batch in one
+ * launch (eccb200_double_smul_batch); host — r' = H(W'x [|| W'y] || m) with the reference's src/hash, r' == r.
+ */
+static int verify_batch_ecsdsa(bool optimized, const uint8_t **s, const uint8_t *s_len, const eccb200_ec_pub_key **pub_keys,
+			       const uint8_t **m, const uint32_t *m_len, uint32_t num, int sig_type, int hash_type,
+			       const uint8_t **adata)
+{
+	t_verdicts.assign(num, -1);
+	if (num == 0) return -1;
+	if (!s || !s_len || !pub_keys || !m || !m_len) return -1;
+	if (adata)
+		for (uint32_t i = 0; i < num; i++)
+			if (adata[i]) return -1;
+	get_hash_fn get_hash = resolve_get_hash();
+	if (!get_hash) return -1;
+	const HashMappingHead *hm = nullptr;
+	if (get_hash(hash_type, &hm) || !hm || !hm->hfunc_scattered) return -1;
+	const uint32_t hlen = hm->digest_size;
+	if (hlen == 0 || hlen > 128) return -1;
+	const CurveInfo *ci = nullptr;
+	for (uint32_t i = 0; i < num && !ci; i++) {
+		const eccb200_ec_pub_key *pk = pub_keys[i];
+		if (pk && pk->magic == kPubKeyMagic && pk->key_type == sig_type && pt_ok(&pk->y)) ci = identify(&pk->y);
+	}
+	if (!ci) return -1;
+	Engine engine = acquire(ci->id, num);
+	eccb200_ctx *eng = engine.ctx;
+	if (!eng) return -1;
+	const int pl = ci->plen;
+	const size_t plen = (size_t)ci->plen, qlen = (size_t)ci->qlen;
+	const size_t siglen = (size_t)hlen + qlen; /* ECSDSA_SIGLEN: r is a digest, s a scalar (sig/ecsdsa_common.h) */
+	uint8_t *ab = engine.slot->st[0].get(num * 2 * qlen), *pubs = engine.slot->st[1].get(num * 2 * plen),
+		*wout = engine.slot->st[2].get(num * 2 * plen);
+	int8_t *status = (int8_t *)engine.slot->st[3].get(num);
+	if (!ab || !pubs || !wout || !status) return -1;
+	uint8_t qbe[72];
+	words_to_be(qbe, (int)qlen, ci->q);
+	std::vector<uint8_t> ok(num, 0);
+	std::atomic<int> mixed{ 0 };
+	std::vector<std::vector<uint32_t>> prj_parts(64);
+	parallel_for(num, [&](uint32_t lo, uint32_t hi, unsigned t) {
+		std::vector<uint32_t> &prj = prj_parts[t];
+		for (uint32_t i = lo; i < hi; i++) {
+			memset(&ab[i * 2 * qlen], 0, 2 * qlen);
+			memset(&pubs[i * 2 * plen], 0, 2 * plen);
+			const eccb200_ec_pub_key *pk = pub_keys[i];
+			if (!pk || pk->magic != kPubKeyMagic || pk->key_type != sig_type || !pt_ok(&pk->y)) continue;
+			if (!s[i] || (!m[i] && m_len[i])) continue;
+			const CurveInfo *c = identify(&pk->y);
+			if (!c) continue;
+			if (c != ci) {
+				mixed.store(1);
+				continue;
+			}
+			if (s_len[i] != siglen) continue;                       /* (:472) */
+			const uint8_t *sb = s[i] + hlen;
+			bool zero = true;
+			for (size_t j = 0; j < qlen; j++) zero = zero && sb[j] == 0;
+			if (zero || memcmp(sb, qbe, qlen) >= 0) continue;       /* 1. s in ]0, q[ (:475-478) */
+			eccb200_nn r;
+			be_to_nn(&r, s[i], hlen);
+			uint8_t rmod[72], e[72];
+			scalar_mod_to_be(rmod, &r, ci);                         /* 2. e = -(r mod q) mod q (:486-488) */
+			bool rz = true;
+			for (size_t j = 0; j < qlen; j++) rz = rz && rmod[j] == 0;
+			if (rz) continue;                                       /* 3. e == 0: reject (:491-492) */
+			int borrow = 0;
+			for (int j = (int)qlen - 1; j >= 0; j--) {
+				int d = (int)qbe[j] - (int)rmod[j] - borrow;
+				borrow = d < 0;
+				e[j] = (uint8_t)(d + (borrow << 8));
+			}
+			memcpy(&ab[i * 2 * qlen], sb, qlen);
+			memcpy(&ab[i * 2 * qlen + qlen], e, qlen);
+			const eccb200_prj_pt *y = &pk->y;
+			if (fp_is_small(&y->Z, 1)) {
+				fp_to_be(&pubs[i * 2 * plen], &y->X, pl);
+				fp_to_be(&pubs[i * 2 * plen + plen], &y->Y, pl);
+			} else {
+				prj.push_back(i);
+			}
+			ok[i] = 1;
+		}
+	});
+	if (mixed.load()) return -1;
+	std::vector<uint32_t> prj_idx;
+	for (auto &part : prj_parts) prj_idx.insert(prj_idx.end(), part.begin(), part.end());
+	if (!prj_idx.empty()) {
+		std::vector<uint8_t> pb(prj_idx.size() * 3 * plen), abuf(prj_idx.size() * 2 * plen);
+		std::vector<int8_t> st(prj_idx.size());
+		parallel_for((uint32_t)prj_idx.size(), [&](uint32_t lo, uint32_t hi, unsigned) {
+			for (uint32_t k = lo; k < hi; k++) {
+				const eccb200_prj_pt *p = &pub_keys[prj_idx[k]]->y;
+				fp_to_be(&pb[k * 3 * plen], &p->X, pl);
+				fp_to_be(&pb[k * 3 * plen + plen], &p->Y, pl);
+				fp_to_be(&pb[k * 3 * plen + 2 * plen], &p->Z, pl);
+			}
+		});
+		if (eccb200_prj_pt_unique_batch(eng, (uint32_t)prj_idx.size(), pb.data(), abuf.data(), st.data())) return -1;
+		for (size_t k = 0; k < prj_idx.size(); k++) {
+			uint32_t i = prj_idx[k];
+			if (st[k] == 0) memcpy(&pubs[i * 2 * plen], &abuf[k * 2 * plen], 2 * plen);
+			else ok[i] = 0; /* key off the curve; a key at infinity gives W' = sG in the reference — rejected here,
+					 * the same documented divergence as for ECFSDSA */
+		}
+	}
+	for (uint32_t i = 0; i < num; i++)
+		if (!ok[i]) { /* keep the batch launchable: rejected slots multiply the generator by zero */
+			memset(&ab[i * 2 * qlen], 0, 2 * qlen);
+			gen_to_be(&pubs[i * 2 * plen], ci);
+		}
+	if (eccb200_double_smul_batch(eng, num, ab, pubs, wout, status)) return -1; /* 4. W' = sG + eY (:495-498) */
+	g_verifies += num;
+	std::vector<int8_t> verdict(num, -1);
+	parallel_for(num, [&](uint32_t lo, uint32_t hi, unsigned) {
+		for (uint32_t i = lo; i < hi; i++) {
+			if (!ok[i] || status[i] != 0) continue; /* infinity: prj_pt_unique fails (:498) */
+			uint8_t rp[128];
+			const unsigned char *in[4] = { &wout[i * 2 * plen], optimized ? m[i] : &wout[i * 2 * plen + plen],
+						       optimized ? nullptr : m[i], nullptr };
+			uint32_t il[3] = { (uint32_t)plen, optimized ? m_len[i] : (uint32_t)plen, optimized ? 0u : m_len[i] };
+			if (hm->hfunc_scattered(in, il, rp)) continue;          /* 5. r' = H(W'x [|| W'y] || m) (:500-520) */
+			verdict[i] = memcmp(rp, s[i], hlen) == 0 ? 0 : -1;      /* 6. r == r' (sig/ecsdsa_common.c:606) */
+		}
+	});
+	int all = 0;
+	for (uint32_t i = 0; i < num; i++)
+		if (verdict[i]) all = -1;
+	t_verdicts.assign(verdict.begin(), verdict.end());
+	return all;
+}
+
 extern "C" int eccb200_dropin_ecdsa_verify_batch(const uint8_t **s, const uint8_t *s_len,
 						 const eccb200_ec_pub_key **pub_keys, const uint8_t **m,
 						 const uint32_t *m_len, uint32_t num, int sig_type, int hash_type,
@@ -697,6 +840,20 @@ extern "C" int eccb200_dropin_ecfsdsa_verify_batch(const uint8_t **s, const uint
 	(void)adata_len;
 	if (sig_type != 5 /* ECFSDSA */) return -1;
 	return verify_batch_common(kEcfsdsa, s, s_len, pub_keys, m, m_len, num, sig_type, hash_type, adata);
+}
+
+/* ECSDSA (sig_type 3) / ECOSDSA (4): the slot these two leave at unsupported_verify_batch in the reference */
+extern "C" int eccb200_dropin_ecsdsa_verify_batch(const uint8_t **s, const uint8_t *s_len,
+						  const eccb200_ec_pub_key **pub_keys, const uint8_t **m,
+						  const uint32_t *m_len, uint32_t num, int sig_type, int hash_type,
+						  const uint8_t **adata, const uint16_t *adata_len,
+						  void *scratch_pad_area, uint32_t *scratch_pad_area_len)
+{
+	(void)scratch_pad_area;
+	(void)scratch_pad_area_len;
+	(void)adata_len;
+	if (sig_type != 3 /* ECSDSA */ && sig_type != 4 /* ECOSDSA */) return -1;
+	return verify_batch_ecsdsa(sig_type == 4, s, s_len, pub_keys, m, m_len, num, sig_type, hash_type, adata);
 }
 
 /* BIP0340: a replacement for the reference's own bip0340_verify_batch (sig/bip0340.c:1296) in the same slot */
@@ -737,7 +894,9 @@ extern "C" int eccb200_dropin_ec_verify(const uint8_t *sig, uint8_t siglen, cons
 					const uint8_t *adata, uint16_t adata_len)
 {
 	Scheme sc = kEcdsa;
-	bool ours = scheme_of(sig_type, &sc) && !adata && adata_len == 0 && sig && pub_key && pub_key->magic == kPubKeyMagic &&
+	const bool post_hash = (sig_type == 3 || sig_type == 4); /* ECSDSA / ECOSDSA: hash of the recomputed point */
+	bool ours = (post_hash || scheme_of(sig_type, &sc)) && !adata && adata_len == 0 && sig && pub_key &&
+		    pub_key->magic == kPubKeyMagic &&
 		    pub_key->key_type == sig_type && pt_ok(&pub_key->y) && identify(&pub_key->y) != nullptr &&
 		    resolve_get_hash() != nullptr;
 	if (ours) {
@@ -753,6 +912,7 @@ extern "C" int eccb200_dropin_ec_verify(const uint8_t *sig, uint8_t siglen, cons
 	const eccb200_ec_pub_key *pk[1] = { pub_key };
 	const uint8_t *mp[1] = { m };
 	const uint32_t ml[1] = { mlen };
+	if (post_hash) return verify_batch_ecsdsa(sig_type == 4, sp, sl, pk, mp, ml, 1, sig_type, hash_type, nullptr);
 	return verify_batch_common(sc, sp, sl, pk, mp, ml, 1, sig_type, hash_type, nullptr);
 }
 

@@ -712,6 +712,28 @@ extern "C" int eccb200_ecfsdsa_verify_batch_dev(eccb200_ctx *ctx, uint32_t n, co
 	return ecfsdsa_dev(ctx, n, d_sigs, d_pubkeys, d_digests, hlen, d_verdict, (cudaStream_t)stream);
 }
 
+static int double_smul_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_ab, const uint8_t *d_pubkeys, uint8_t *d_out,
+			   int8_t *d_status, cudaStream_t st)
+{
+	if (n == 0) return 0;
+	return dispatch(ctx->curve_id, [&](auto c) {
+		typedef decltype(c) C;
+		LaunchVerify<C>::double_smul(n, d_ab, d_pubkeys, ctx->table, ctx->w, d_out, d_status, st);
+		ctx->launches += 1;
+		CUDA_OK(cudaGetLastError());
+		return 0;
+	});
+}
+
+extern "C" int eccb200_double_smul_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_ab, const uint8_t *d_pubkeys,
+					       uint8_t *d_out, int8_t *d_status, void *stream)
+{
+	if (!ctx || (n && (!d_ab || !d_pubkeys || !d_out || !d_status))) return fail("null argument");
+	if (misaligned16(ctx, { d_ab, d_pubkeys, d_out })) return fail(kAlignMsg);
+	CUDA_OK(cudaSetDevice(ctx->device));
+	return double_smul_dev(ctx, n, d_ab, d_pubkeys, d_out, d_status, (cudaStream_t)stream);
+}
+
 static int bip0340_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_sigs, const uint8_t *d_pubkeys,
 		       const uint8_t *d_digests, uint32_t hlen, int8_t *d_verdict, cudaStream_t st)
 {
@@ -1124,6 +1146,21 @@ extern "C" int eccb200_ecfsdsa_verify_batch(eccb200_ctx *ctx, uint32_t n, const 
 		const uint8_t *d = ctx->d_in[s];
 		return ecfsdsa_dev(ctx, cnt, d + (size_t)cnt * pk, d, d + (size_t)cnt * (pk + sg), hlen,
 				   (int8_t *)ctx->d_out[s], ctx->streams[s]);
+	});
+}
+
+extern "C" int eccb200_double_smul_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *ab, const uint8_t *pubkeys,
+					   uint8_t *out, int8_t *status)
+{
+	if (!ctx || (n && (!ab || !pubkeys || !out || !status))) return fail("null argument");
+	if (n == 0) return 0;
+	const size_t sc = 2 * (size_t)ctx->qlen, pk = 2 * (size_t)ctx->plen;
+	std::vector<HostCol> in = { { (uint8_t *)ab, sc, false }, { (uint8_t *)pubkeys, pk, false } };
+	std::vector<HostCol> outc = { { out, pk, false }, { (uint8_t *)status, 1, false } };
+	return run_pipeline(ctx, n, in, outc, [&](int s, uint32_t cnt) {
+		const uint8_t *d = ctx->d_in[s];
+		return double_smul_dev(ctx, cnt, d, d + (size_t)cnt * sc, ctx->d_out[s],
+				       (int8_t *)(ctx->d_out[s] + (size_t)cnt * pk), ctx->streams[s]);
 	});
 }
 

@@ -797,7 +797,8 @@ __global__ void ECC_CLUSTER_ATTR __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VE
 						      const uint8_t *__restrict__ digests, uint32_t hlen,
 						      const uint32_t *__restrict__ table, int w,
 						      int8_t *__restrict__ verdict,
-						      const int8_t *__restrict__ key_state)
+						      const int8_t *__restrict__ key_state,
+						      uint8_t *__restrict__ aux_out)
 {
 	/* key_state (optional, from the structured-key import): 0 = pubkeys[i] is a validated affine point, 1 = the key
 	 * is the point at infinity (pubkeys[i] ignored), -1 = the key or signature record was rejected */
@@ -837,6 +838,60 @@ __global__ void ECC_CLUSTER_ATTR __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VE
 		if (!active) return;
 		if (!run) code = 1;
 		verdict[idx] = code ? -1 : 0;
+		return;
+	}
+
+	if (SCHEME == 3) {
+		/*
+		 * Generic double-scalar multiplication W = a*G + b*Y with an affine result: the EC core of every remaining
+		 * Schnorr-type verification of the reference (ECSDSA / ECOSDSA sig/ecsdsa_common.c:493-497: W' = sG + eY;
+		 * ECKCDSA: W' = sY + eG; ...), i.e. the sequence prj_pt_mul, prj_pt_mul, prj_pt_add, prj_pt_unique.  Those
+		 * schemes hash the recomputed point, which stays on the host (src/hash); this kernel hands it W'.
+		 * sigs[i] = a || b (QLEN bytes each, any value: reduced mod q like the ladder does); verdict: 0 finite,
+		 * 1 infinity (prj_pt_unique fails on it), -1 key rejected; aux_out [n][2*PLEN] affine bytes (zero if not finite).
+		 */
+		typedef Field<typename C::Fp> F;
+		__shared__ uint32_t sh_inv3[ECC_CTA_INV_WORDS(N)];
+		const uint8_t *sg = sigs + (size_t)i0 * (2 * C::QLEN);
+		Fe<N> a, b;
+		Aff<C> Y;
+		load_wire<N, C::QLEN>(a, sg);
+		load_wire<N, C::QLEN>(b, sg + C::QLEN);
+		scalar_reduce<C>(a);
+		scalar_reduce<C>(b);
+		const bool key_ok = load_affine_checked<C>(Y, pubkeys + (size_t)i0 * (2 * C::PLEN));
+		if (!key_ok) {
+			Fq::set_zero(a);
+			Fq::set_zero(b);
+#pragma unroll
+			for (int j = 0; j < N; j++) {
+				Y.x.w[j] = C::GX_MONT(j);
+				Y.y.w[j] = C::GY_MONT(j);
+			}
+		}
+		Jac<C> aG, W;
+		comb_mul<C>(aG, a, table, w);
+		window_mul<C>(W, b, Y, &aG, [&](Fe<N> &o, const Fe<N> &v) {
+			cta_inverse_128<typename C::Fp, ECC_CLUSTER_INV>(o, v, sh_inv3);
+		});
+		const bool inf = EC<C>::is_inf(W);
+		Fe<N> z = W.Z, zi, zp, zi2, zi3, x, y;
+		if (inf) F::set_one(z);
+		cta_inverse_128<typename C::Fp, ECC_CLUSTER_INV>(zi, z, sh_inv3);
+		F::from_mont(zp, zi);        /* 1/z out of the Montgomery domain once: X * zp^2, Y * zp^3 are plain */
+		F::mul(zi2, zp, zi);
+		F::mul(zi3, zi2, zi);
+		F::mul(x, W.X, zi2);
+		F::mul(y, W.Y, zi3);
+		if (!active) return;
+		const bool fin = key_ok && !inf;
+		if (!fin) {
+			F::set_zero(x);
+			F::set_zero(y);
+		}
+		store_wire<N, C::PLEN>(aux_out + (size_t)idx * (2 * C::PLEN), x);
+		store_wire<N, C::PLEN>(aux_out + (size_t)idx * (2 * C::PLEN) + C::PLEN, y);
+		verdict[idx] = !key_ok ? (int8_t)-1 : (inf ? (int8_t)1 : (int8_t)0);
 		return;
 	}
 
@@ -1245,6 +1300,8 @@ template <class C> struct LaunchVerify {
 			    uint32_t hlen, const uint32_t *table, int w, int8_t *verdict, cudaStream_t st);
 	static void bip0340(uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys, const uint8_t *digests,
 			    uint32_t hlen, const uint32_t *table, int w, int8_t *verdict, cudaStream_t st);
+	static void double_smul(uint32_t n, const uint8_t *ab, const uint8_t *pubkeys, const uint32_t *table, int w,
+				uint8_t *out, int8_t *status, cudaStream_t st);
 	static void uv(uint32_t n, const uint8_t *sigs, const uint8_t *digests, uint32_t hlen, uint8_t *out,
 		       cudaStream_t st);
 };
@@ -1384,19 +1441,27 @@ void LaunchVerify<C>::verify(uint32_t n, const uint8_t *sigs, const uint8_t *pub
 			     const int8_t *key_state)
 {
 	k_ecdsa_verify<C><<<grid_clustered(n), kThreads, 0, st>>>(n, sigs, pubkeys, digests, hlen, table, w, verdict,
-							     key_state);
+							     key_state, nullptr);
 }
 template <class C>
 void LaunchVerify<C>::ecfsdsa(uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys, const uint8_t *digests,
 			      uint32_t hlen, const uint32_t *table, int w, int8_t *verdict, cudaStream_t st)
 {
-	k_ecdsa_verify<C, 1><<<grid_clustered(n), kThreads, 0, st>>>(n, sigs, pubkeys, digests, hlen, table, w, verdict, nullptr);
+	k_ecdsa_verify<C, 1><<<grid_clustered(n), kThreads, 0, st>>>(n, sigs, pubkeys, digests, hlen, table, w, verdict, nullptr,
+								nullptr);
 }
 template <class C>
 void LaunchVerify<C>::bip0340(uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys, const uint8_t *digests,
 			      uint32_t hlen, const uint32_t *table, int w, int8_t *verdict, cudaStream_t st)
 {
-	k_ecdsa_verify<C, 2><<<grid_clustered(n), kThreads, 0, st>>>(n, sigs, pubkeys, digests, hlen, table, w, verdict, nullptr);
+	k_ecdsa_verify<C, 2><<<grid_clustered(n), kThreads, 0, st>>>(n, sigs, pubkeys, digests, hlen, table, w, verdict, nullptr,
+								nullptr);
+}
+template <class C>
+void LaunchVerify<C>::double_smul(uint32_t n, const uint8_t *ab, const uint8_t *pubkeys, const uint32_t *table, int w,
+				  uint8_t *out, int8_t *status, cudaStream_t st)
+{
+	k_ecdsa_verify<C, 3><<<grid_clustered(n), kThreads, 0, st>>>(n, ab, pubkeys, nullptr, 0, table, w, status, nullptr, out);
 }
 template <class C>
 void LaunchVerify<C>::uv(uint32_t n, const uint8_t *sigs, const uint8_t *digests, uint32_t hlen, uint8_t *out,

@@ -783,6 +783,41 @@ static void *bip_verify_worker(void *arg)
 	return NULL;
 }
 
+/* W = a*G + b*Y as the reference's Schnorr-type verifications compute it (e.g. sig/ecsdsa_common.c:493-497:
+ * prj_pt_mul, prj_pt_mul, prj_pt_add, prj_pt_unique): 0 finite (affine bytes written), 1 infinity, -1 key rejected */
+static int double_smul_one(uint8_t *out, const uint8_t *ab, const uint8_t *pub, const curve_t *c)
+{
+	u64 a[MAXL], b[MAXL];
+	pt_t Y, G, aG, bY, W, Wa;
+	int n = c->n;
+	memset(out, 0, 2 * c->plen);
+	nn_from_be(a, n, ab, c->qlen);
+	nn_from_be(b, n, ab + c->qlen, c->qlen);
+	if (pt_import_aff(&Y, pub, c)) return -1;
+	memcpy(G.X, c->gx, sizeof(G.X));
+	memcpy(G.Y, c->gy, sizeof(G.Y));
+	memset(G.Z, 0, sizeof(G.Z));
+	G.Z[0] = 1;
+	if (pt_mul(&aG, a, n, &G, c)) return -1;
+	if (pt_mul(&bY, b, n, &Y, c)) return -1;
+	if (pt_add_cf(&W, &aG, &bY, c)) return -1;
+	if (pt_iszero(&W, c)) return 1;
+	if (pt_unique(&Wa, &W, c)) return -1;
+	nn_to_be(out, c->plen, Wa.X, n);
+	nn_to_be(out + c->plen, c->plen, Wa.Y, n);
+	return 0;
+}
+
+static void *double_smul_worker(void *arg)
+{
+	job_t *j = (job_t *)arg;
+	const curve_t *c = j->c;
+	for (uint32_t i = j->lo; i < j->hi; i++)
+		j->status[i] = (int8_t)double_smul_one(j->out + (size_t)i * 2 * c->plen, j->sigs + (size_t)i * 2 * c->qlen,
+						       j->pubkeys + (size_t)i * 2 * c->plen, c);
+	return NULL;
+}
+
 static void *fs_verify_worker(void *arg)
 {
 	job_t *j = (job_t *)arg;
@@ -923,6 +958,23 @@ int ora_ecfsdsa_verify_digest_batch(const char *curve, uint32_t n, const uint8_t
 	p.hlen = hlen;
 	p.status = verdict;
 	run_jobs(fs_verify_worker, &p, n, nthreads);
+	return 0;
+}
+
+/* W_i = a_i*G + b_i*Y_i, affine (ab: [n][2*qlen]) */
+int ora_double_smul_batch(const char *curve, uint32_t n, const uint8_t *ab, const uint8_t *pubkeys, uint8_t *out,
+			  int8_t *status, int nthreads)
+{
+	curve_t c;
+	job_t p;
+	if (curve_load(&c, curve)) return -1;
+	memset(&p, 0, sizeof(p));
+	p.c = &c;
+	p.sigs = ab;
+	p.pubkeys = pubkeys;
+	p.out = out;
+	p.status = status;
+	run_jobs(double_smul_worker, &p, n, nthreads);
 	return 0;
 }
 

@@ -30,6 +30,11 @@ int ora_ecdsa_verify_digest_batch(const char *curve, uint32_t n, const uint8_t *
 int ora_ecfsdsa_verify_digest_batch(const char *curve, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys,
 				    const uint8_t *digests, uint32_t hlen, int8_t *verdict, int nthreads);
 
+/* W_i = a_i*G + b_i*Y_i with affine results — the EC core of the reference's Schnorr-type verifications
+ * (sig/ecsdsa_common.c:493-497 ...); ab [n][2*qlen]; status 0 finite / 1 infinity / -1 key rejected. */
+int ora_double_smul_batch(const char *curve, uint32_t n, const uint8_t *ab, const uint8_t *pubkeys, uint8_t *out,
+			  int8_t *status, int nthreads);
+
 /* BIP0340 verification (sig/bip0340.c:383-577) on digests[i] = H(H(tag) || H(tag) || r_i || x(Y_i) || m_i) with
  * tag = "BIP0340/challenge"; sigs are [n][plen + qlen] (r = x coordinate, s). */
 int ora_bip0340_verify_digest_batch(const char *curve, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys,

@@ -362,6 +362,75 @@ int ref_bip0340_sign_batch(const char *curve, const char *hash, uint32_t n, cons
 	return run_sig_jobs(sign_worker, &p, n, nthreads);
 }
 
+/* Generic forms for any scheme of the reference, named like its ec_alg_type ("ECSDSA", "ECOSDSA", "ECKCDSA", ...):
+ * ec_sign / ec_verify per item; the signature length comes from ec_get_sig_len and is returned through *siglen_out. */
+static int ref_alg_by_name(const char *name, ec_alg_type *alg)
+{
+	static const struct { const char *n; ec_alg_type a; } tab[] = {
+		{ "ECDSA", ECDSA }, { "ECKCDSA", ECKCDSA }, { "ECSDSA", ECSDSA }, { "ECOSDSA", ECOSDSA },
+		{ "ECFSDSA", ECFSDSA }, { "ECGDSA", ECGDSA }, { "ECRDSA", ECRDSA }, { "DECDSA", DECDSA },
+		{ "BIP0340", BIP0340 },
+	};
+	for (unsigned i = 0; i < sizeof(tab) / sizeof(tab[0]); i++)
+		if (!strcmp(name, tab[i].n)) {
+			*alg = tab[i].a;
+			return 0;
+		}
+	return -1;
+}
+
+int ref_sig_len(const char *curve, const char *alg_name, const char *hash, uint32_t *siglen_out)
+{
+	ref_curve c;
+	ec_alg_type alg;
+	hash_alg_type ht;
+	u8 dlen, sl = 0;
+	if (ref_load_curve(&c, curve) || ref_alg_by_name(alg_name, &alg) || ref_hash_type(hash, &ht, &dlen)) return -1;
+	if (ec_get_sig_len(&c.params, alg, ht, &sl)) return -1;
+	*siglen_out = sl;
+	return 0;
+}
+
+int ref_sig_verify_batch(const char *curve, const char *alg_name, const char *hash, uint32_t n, const uint8_t *sigs,
+			 const uint8_t *pubkeys, const uint8_t *msgs, const uint64_t *off, int8_t *verdict, int nthreads)
+{
+	ref_curve c;
+	sig_job p;
+	u8 dlen, sl = 0;
+	memset(&p, 0, sizeof(p));
+	if (ref_load_curve(&c, curve) || ref_alg_by_name(alg_name, &p.alg) || ref_hash_type(hash, &p.ht, &dlen)) return -1;
+	if (ec_get_sig_len(&c.params, p.alg, p.ht, &sl)) return -1;
+	p.c = &c;
+	p.sigs = sigs;
+	p.pubkeys = pubkeys;
+	p.msgs = msgs;
+	p.off = off;
+	p.verdict = verdict;
+	p.siglen = sl;
+	return run_sig_jobs(verify_worker, &p, n, nthreads);
+}
+
+int ref_sig_sign_batch(const char *curve, const char *alg_name, const char *hash, uint32_t n, const uint8_t *privkeys,
+		       const uint8_t *msgs, const uint64_t *off, uint8_t *sigs_out, uint8_t *pubkeys_out, int8_t *status,
+		       int nthreads)
+{
+	ref_curve c;
+	sig_job p;
+	u8 dlen, sl = 0;
+	memset(&p, 0, sizeof(p));
+	if (ref_load_curve(&c, curve) || ref_alg_by_name(alg_name, &p.alg) || ref_hash_type(hash, &p.ht, &dlen)) return -1;
+	if (ec_get_sig_len(&c.params, p.alg, p.ht, &sl)) return -1;
+	p.c = &c;
+	p.privkeys = privkeys;
+	p.msgs = msgs;
+	p.off = off;
+	p.sigs_out = sigs_out;
+	p.pubkeys_out = pubkeys_out;
+	p.verdict = status;
+	p.siglen = sl;
+	return run_sig_jobs(sign_worker, &p, n, nthreads);
+}
+
 /* The reference's own batch entry point, ec_verify_batch(…, ECFSDSA, …) (sig/sig_algs.c:675 -> sig/ecfsdsa.c:1057):
  * one 0 / -1 answer for the whole batch.  use_scratch = 0: no scratch pad, the reference verifies the signatures one
  * after the other (sig/ecfsdsa.c:711); use_scratch = 1: its Bos-Coster multi-scalar multiplication (:842). */

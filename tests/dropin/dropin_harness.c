@@ -227,13 +227,14 @@ static int run_direct(const char *dropin_path)
 				u8 sg[3 * 66];
 				u8 sgl = 0;
 				unsigned long long v0 = gpu_vcount();
-				CHECK(!ec_key_pair_gen(&kq, &params, ECSDSA), "ecsdsa keygen");
-				CHECK(!ec_get_sig_len(&params, ECSDSA, ht, &sgl), "siglen");
-				CHECK(!ec_sign(sg, sgl, &kq, msgs[0], ml[0], ECSDSA, ht, NULL, 0), "ecsdsa sign");
-				CHECK(gpu_everify(sg, sgl, &kq.pub_key, msgs[0], ml[0], ECSDSA, ht, NULL, 0) == 0, "forwarded ECSDSA verify failed");
+				/* a scheme the layer does not serve (ECGDSA) is forwarded to the reference's own ec_verify */
+				CHECK(!ec_key_pair_gen(&kq, &params, ECGDSA), "ecgdsa keygen");
+				CHECK(!ec_get_sig_len(&params, ECGDSA, ht, &sgl), "siglen");
+				CHECK(!ec_sign(sg, sgl, &kq, msgs[0], ml[0], ECGDSA, ht, NULL, 0), "ecgdsa sign");
+				CHECK(gpu_everify(sg, sgl, &kq.pub_key, msgs[0], ml[0], ECGDSA, ht, NULL, 0) == 0, "forwarded ECGDSA verify failed");
 				sg[2] ^= 1;
-				CHECK(gpu_everify(sg, sgl, &kq.pub_key, msgs[0], ml[0], ECSDSA, ht, NULL, 0) == -1, "forwarded ECSDSA forgery accepted");
-				CHECK(gpu_vcount() == v0, "ECSDSA must be forwarded, not counted as a GPU verification");
+				CHECK(gpu_everify(sg, sgl, &kq.pub_key, msgs[0], ml[0], ECGDSA, ht, NULL, 0) == -1, "forwarded ECGDSA forgery accepted");
+				CHECK(gpu_vcount() == v0, "ECGDSA must be forwarded, not counted as a GPU verification");
 			}
 			/* ---- a public key that IS the point at infinity: the reference's ec_verify accepts the struct and goes on
 			 * with W' = u*G; shim and batch adapter must give the reference's verdict, whatever it is */
@@ -282,6 +283,49 @@ static int run_direct(const char *dropin_path)
 				CHECK(v[i] == want, "%s ecfsdsa verdict[%d] = %d, reference ec_verify says %d", names[c], i, v[i], want);
 			}
 			CHECK(v[3] == -1 && v[7] == -1 && v[11] == -1, "corrupted ECFSDSA items not flagged");
+		}
+		/* ---- ECSDSA / ECOSDSA: batch adapter (W' = sG + eY on the device, hashing of W' with the reference's src/hash)
+		 * and ec_verify shim against the reference's ec_verify */
+		for (int alt = 0; alt < 2; alt++) {
+			enum { NSD = 20 };
+			const ec_alg_type alg = alt ? ECOSDSA : ECSDSA;
+			static ec_key_pair kp[NSD];
+			static u8 sigs[NSD][64 + 66 + 8], msgs[NSD][40];
+			const u8 *sp[NSD], *mp[NSD];
+			const ec_pub_key *pk[NSD];
+			u8 sl[NSD], sgl = 0;
+			u32 ml[NSD];
+			hash_alg_type ht = (c == 2) ? SHA384 : ((c == 5 || c == 7) ? SHA512 : SHA256);
+			vbatch_fn gpu_sdbatch = (vbatch_fn)dlsym(h, "eccb200_dropin_ecsdsa_verify_batch");
+			CHECK(gpu_sdbatch != NULL, "missing eccb200_dropin_ecsdsa_verify_batch");
+			if (!gpu_sdbatch) break;
+			CHECK(!ec_get_sig_len(&params, alg, ht, &sgl), "siglen");
+			for (int i = 0; i < NSD; i++) {
+				CHECK(!ec_key_pair_gen(&kp[i], &params, alg), "ecsdsa keygen");
+				ml[i] = (u32)(1 + (rnd8() % 39));
+				for (u32 j = 0; j < ml[i]; j++) msgs[i][j] = rnd8();
+				sl[i] = sgl;
+				CHECK(!ec_sign(sigs[i], sl[i], &kp[i], msgs[i], ml[i], alg, ht, NULL, 0), "ec_sign ECSDSA");
+				sp[i] = sigs[i];
+				mp[i] = msgs[i];
+				pk[i] = &kp[i].pub_key;
+			}
+			int r = gpu_sdbatch(sp, sl, pk, mp, ml, NSD, alg, ht, NULL, NULL, NULL, NULL);
+			CHECK(r == 0, "%s ec%ssdsa verify_batch: valid batch rejected", names[c], alt ? "o" : "");
+			sigs[4][1] ^= 0x08;        /* r */
+			sigs[8][sgl - 1] ^= 1;     /* s */
+			msgs[12][0] ^= 1;
+			r = gpu_sdbatch(sp, sl, pk, mp, ml, NSD, alg, ht, NULL, NULL, NULL, NULL);
+			CHECK(r == -1, "%s ec%ssdsa verify_batch: corrupted batch accepted", names[c], alt ? "o" : "");
+			signed char v[NSD];
+			CHECK(gpu_verdicts(v, NSD) == NSD, "verdict count");
+			for (int i = 0; i < NSD; i++) {
+				int want = ec_verify(sigs[i], sl[i], pk[i], msgs[i], ml[i], alg, ht, NULL, 0) ? -1 : 0;
+				CHECK(v[i] == want, "%s ec%ssdsa verdict[%d] = %d, reference ec_verify says %d", names[c], alt ? "o" : "", i, v[i], want);
+				int got = gpu_everify(sigs[i], sl[i], pk[i], msgs[i], ml[i], alg, ht, NULL, 0) ? -1 : 0;
+				CHECK(got == want, "%s ec%ssdsa ec_verify shim item %d: %d vs %d", names[c], alt ? "o" : "", i, got, want);
+			}
+			CHECK(v[4] == -1 && v[8] == -1 && v[12] == -1, "corrupted EC(O)SDSA items not flagged");
 		}
 		/* ---- BIP0340 in the same slot and through the ec_verify shim: against the reference's ec_verify */
 		{

@@ -270,6 +270,35 @@ int hostsim_ecfsdsa_verify_batch(int curve_id, int w, uint32_t n, const uint8_t 
 	});
 }
 
+/* W = a*G + b*Y with the kernel's building blocks (comb + signed window + one normalisation), status like the kernel */
+int hostsim_double_smul_batch(int curve_id, int w, uint32_t n, const uint8_t *ab, const uint8_t *pubkeys, uint8_t *out,
+			      int8_t *status)
+{
+	return dispatch(curve_id, [&](auto c) {
+		typedef decltype(c) C;
+		constexpr int N = C::N;
+		const std::vector<uint32_t> &tab = table_for<C>(w);
+		for (uint32_t i = 0; i < n; i++) {
+			Fe<N> a, b;
+			Aff<C> Y;
+			load_be<N>(a, ab + (size_t)i * 2 * C::QLEN, C::QLEN);
+			load_be<N>(b, ab + (size_t)i * 2 * C::QLEN + C::QLEN, C::QLEN);
+			scalar_reduce<C>(a);
+			scalar_reduce<C>(b);
+			memset(out + (size_t)i * 2 * C::PLEN, 0, 2 * C::PLEN);
+			if (!load_point<C>(Y, pubkeys + (size_t)i * 2 * C::PLEN)) {
+				status[i] = -1;
+				continue;
+			}
+			Jac<C> aG, W;
+			comb_mul<C>(aG, a, tab.data(), w);
+			window_mul<C>(W, b, Y, &aG, ThreadInverter<C>());
+			status[i] = (int8_t)jac_to_wire<C>(W, out + (size_t)i * 2 * C::PLEN);
+		}
+		return 0;
+	});
+}
+
 /* BIP0340 verification with the kernel's building blocks (digest_full_mod_q, bip0340_verify_tail) */
 int hostsim_bip0340_verify_batch(int curve_id, int w, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys,
 				 const uint8_t *digests, uint32_t hlen, int8_t *verdict)
