@@ -1051,6 +1051,12 @@ extern "C" int eccb200_prj_pt_mul_batch(eccb200_ctx *ctx, uint32_t n, const uint
 		if (points) /* variable base: one long kernel per chunk, left unordered (see run_pipeline) */
 			return smul_dev(ctx, cnt, d_sc, d_pt, d_o, d_st, ctx->stage_jac[s], ctx->stage_prefix[s],
 					ctx->streams[s]);
+		/* ECCB200_PIPE_K4_INLINE=1: the normalisation stays on the chunk's own stream behind K1 and the next chunk's
+		 * K1 waits for it (no high-priority side stream) — the alternative measured in DESIGN.md §7 */
+		static const bool k4_inline = getenv("ECCB200_PIPE_K4_INLINE") && atoi(getenv("ECCB200_PIPE_K4_INLINE")) != 0;
+		if (k4_inline)
+			return smul_dev(ctx, cnt, d_sc, d_pt, d_o, d_st, ctx->stage_jac[s], ctx->stage_prefix[s],
+					ctx->streams[s]);
 		ctx->kdone_set = true;
 		return smul_dev(ctx, cnt, d_sc, d_pt, d_o, d_st, ctx->stage_jac[s], ctx->stage_prefix[s], ctx->streams[s],
 				ctx->kdone[s], ctx->hi[s], ctx->ndone[s]);
