@@ -1051,9 +1051,12 @@ extern "C" int eccb200_prj_pt_mul_batch(eccb200_ctx *ctx, uint32_t n, const uint
 		if (points) /* variable base: one long kernel per chunk, left unordered (see run_pipeline) */
 			return smul_dev(ctx, cnt, d_sc, d_pt, d_o, d_st, ctx->stage_jac[s], ctx->stage_prefix[s],
 					ctx->streams[s]);
-		/* ECCB200_PIPE_K4_INLINE=1: the normalisation stays on the chunk's own stream behind K1 and the next chunk's
-		 * K1 waits for it (no high-priority side stream) — the alternative measured in DESIGN.md §7 */
-		static const bool k4_inline = getenv("ECCB200_PIPE_K4_INLINE") && atoi(getenv("ECCB200_PIPE_K4_INLINE")) != 0;
+		/* Where the normalisation of a chunk runs (measured on 2^20 / 2^22 / 2^24 scalars): on the chunk's
+		 * own stream behind K1, the next chunk's K1 waiting for it (473 / 545 / 604 M/s end to end), or on a
+		 * high-priority side stream under the next chunk's K1 (455 / 555 / 608 M/s).  The first wins while the batch is
+		 * a handful of chunks, the second once the steady state dominates.  ECCB200_PIPE_K4_INLINE=0/1 forces one. */
+		static const int k4_force = getenv("ECCB200_PIPE_K4_INLINE") ? atoi(getenv("ECCB200_PIPE_K4_INLINE")) : -1;
+		const bool k4_inline = k4_force >= 0 ? k4_force != 0 : n <= 24u * ctx->wave;
 		if (k4_inline)
 			return smul_dev(ctx, cnt, d_sc, d_pt, d_o, d_st, ctx->stage_jac[s], ctx->stage_prefix[s],
 					ctx->streams[s]);

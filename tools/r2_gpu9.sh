@@ -8,7 +8,7 @@ NCU="ncu --clock-control none"
 $NCU --metrics gpu__time_duration.sum -s 320 -c 60 --csv --log-file gpurun_out/r02_launches_default.csv \
     python bench.py --steps 3 --warmup 1 --no-extra --no-cpu-baseline > gpurun_out/r02_ncu_bench.log 2>&1
 grep -c "k_smul_fixed\|k_to_affine" gpurun_out/r02_launches_default.csv
-$NCU --set full --import-source on --kernel-name-base demangled -k regex:"k_to_affine<.*, *0>" -s 1 -c 1 -o gpurun_out/r02_k4 -f \
+$NCU --set full --import-source on --kernel-name-base demangled -k regex:"k_to_affine<.*\(int\)0>" -s 1 -c 1 -o gpurun_out/r02_k4 -f \
     python bench.py --steps 2 --warmup 1 --no-extra --no-cpu-baseline > gpurun_out/r02_ncu_k4.log 2>&1
 python tools/ncu_summary.py gpurun_out/r02_k4.ncu-rep > gpurun_out/r02_ncu_k4_to_affine.csv 2> gpurun_out/r02_ncu_k4.err; rm -f gpurun_out/r02_k4.ncu-rep
 grep -E "Kernel Name|gpu__time_duration|fmaheavy|registers" gpurun_out/r02_ncu_k4_to_affine.csv | cut -c1-150
