@@ -62,6 +62,29 @@ def test_fused_gather_on_one_gpu(curve):
     eng.close()
 
 
+def test_copy_engine_push_on_one_gpu():
+    """eccb200_push_results with this GPU as its own destination: DMA of a result slot into two buffers, arrival flags
+    published behind the copies, acknowledgement wait in front of them."""
+    import torch
+    import libecc_b200
+    eng = libecc_b200.Engine("SECP256R1", device=0, comb_window=10)
+    dev = torch.device("cuda", 0)
+    nbytes = 3 * 65 * 1000 + 7
+    src = torch.randint(0, 256, (nbytes,), dtype=torch.uint8, device=dev)
+    base, _ = eng.ipc_alloc(4096 + 2 * ((nbytes + 255) // 256 * 256))
+    d0, d1 = base + 4096, base + 4096 + (nbytes + 255) // 256 * 256
+    s = torch.cuda.Stream(device=dev)
+    eng.flag_signal([base + 2048], 5, s.cuda_stream)                       # the "destination" has released step 5
+    eng.push_results([d0, d1], src.data_ptr(), nbytes, [base, base + 4], 6, base + 2048, 1, 5, s.cuda_stream)
+    eng.flag_wait(base, 2, 6, s.cuda_stream)
+    s.synchronize()
+    want = src.cpu().numpy()
+    assert (eng.copy_to_host(d0, nbytes) == want).all() and (eng.copy_to_host(d1, nbytes) == want).all()
+    assert list(eng.copy_to_host(base, 8).view(np.uint32)) == [6, 6]
+    eng.ipc_free(base)
+    eng.close()
+
+
 def test_dev_calls_on_two_streams_share_the_scratch_safely():
     """two *_dev calls on different streams used to race on the context's scratch buffers."""
     import torch
