@@ -122,7 +122,7 @@ void eccb200_dropin_allow_nonct_blind(int on);
  * ec_alg_type / hash_alg_type values):
  *     int ec_verify(const u8 *sig, u8 siglen, const ec_pub_key *pub_key, const u8 *m, u32 mlen,
  *                   ec_alg_type sig_type, hash_alg_type hash_type, const u8 *adata, u16 adata_len);
- * ECDSA (1), DECDSA (14), ECFSDSA (5), BIP0340 (20), ECSDSA (3) and ECOSDSA (4) without ancillary data on a supported curve: the message is hashed on the
+ * ECDSA (1), DECDSA (14), ECFSDSA (5), BIP0340 (20), ECSDSA (3), ECOSDSA (4) and ECKCDSA (2) without ancillary data on a supported curve: the message is hashed on the
  * host with the reference's src/hash and the whole verification (steps 3-10 of __ecdsa_verify_finalize,
  * src/sig/ecdsa_common.c:760-810) is ONE launch of the verification kernel; 0 = valid, -1 = invalid.  Anything else is
  * forwarded unchanged to the next ec_verify in the process (the reference's own); -1 if there is none.
@@ -174,6 +174,13 @@ int eccb200_dropin_ecsdsa_verify_batch(const uint8_t **s, const uint8_t *s_len, 
 				       const uint8_t **m, const uint32_t *m_len, uint32_t num, int sig_type,
 				       int hash_type, const uint8_t **adata, const uint16_t *adata_len,
 				       void *scratch_pad_area, uint32_t *scratch_pad_area_len);
+
+/* ECKCDSA (sig_type 2; src/sig/eckcdsa.c:543-832): h = H(z || m) and e = OS2I(r XOR h) mod q on the host, W' = sY + eG for
+ * the whole batch in one launch, r' = H(W'_x) on the host. */
+int eccb200_dropin_eckcdsa_verify_batch(const uint8_t **s, const uint8_t *s_len, const eccb200_ec_pub_key **pub_keys,
+					const uint8_t **m, const uint32_t *m_len, uint32_t num, int sig_type,
+					int hash_type, const uint8_t **adata, const uint16_t *adata_len,
+					void *scratch_pad_area, uint32_t *scratch_pad_area_len);
 
 /* Per-signature verdicts of the last eccb200_dropin_*_verify_batch call on this thread (0 / -1), for callers
  * that want to know WHICH signature failed; returns the number of verdicts copied. */

@@ -815,6 +815,146 @@ static int verify_batch_ecsdsa(bool optimized, const uint8_t **s, const uint8_t 
 	return all;
 }
 
+/*
+ * ECKCDSA (sig/eckcdsa.c:543-832): r_len = min(|H|, qlen); s in ]0, q[; h = H(z || m) with z = the first block_size
+ * bytes of Y_x || Y_y || 0...; e = OS2I(r XOR rightmost(h)) mod q; W' = sY + eG; r' = rightmost(H(W'_x)) == r.  Same
+ * split as ECSDSA: host for the hashes and the mod-q scalar, one device launch (eccb200_double_smul_batch with a = e
+ * on G and b = s on Y) for the whole batch.
+ */
+static int verify_batch_eckcdsa(const uint8_t **s, const uint8_t *s_len, const eccb200_ec_pub_key **pub_keys,
+				const uint8_t **m, const uint32_t *m_len, uint32_t num, int sig_type, int hash_type,
+				const uint8_t **adata)
+{
+	t_verdicts.assign(num, -1);
+	if (num == 0) return -1;
+	if (!s || !s_len || !pub_keys || !m || !m_len) return -1;
+	if (adata)
+		for (uint32_t i = 0; i < num; i++)
+			if (adata[i]) return -1;
+	get_hash_fn get_hash = resolve_get_hash();
+	if (!get_hash) return -1;
+	const HashMappingHead *hm = nullptr;
+	if (get_hash(hash_type, &hm) || !hm || !hm->hfunc_scattered) return -1;
+	const uint32_t hlen = hm->digest_size, zlen = hm->block_size;
+	if (hlen == 0 || hlen > 128 || zlen == 0) return -1;
+	const CurveInfo *ci = nullptr;
+	for (uint32_t i = 0; i < num && !ci; i++) {
+		const eccb200_ec_pub_key *pk = pub_keys[i];
+		if (pk && pk->magic == kPubKeyMagic && pk->key_type == sig_type && pt_ok(&pk->y)) ci = identify(&pk->y);
+	}
+	if (!ci) return -1;
+	Engine engine = acquire(ci->id, num);
+	eccb200_ctx *eng = engine.ctx;
+	if (!eng) return -1;
+	const int pl = ci->plen;
+	const size_t plen = (size_t)ci->plen, qlen = (size_t)ci->qlen;
+	const size_t rlen = std::min<size_t>(hlen, qlen), siglen = rlen + qlen; /* ECKCDSA_R_LEN / _SIGLEN (sig/eckcdsa.h:28-31) */
+	const size_t shift = hlen > rlen ? hlen - rlen : 0;
+	uint8_t *ab = engine.slot->st[0].get(num * 2 * qlen), *pubs = engine.slot->st[1].get(num * 2 * plen),
+		*wout = engine.slot->st[2].get(num * 2 * plen);
+	int8_t *status = (int8_t *)engine.slot->st[3].get(num);
+	if (!ab || !pubs || !wout || !status) return -1;
+	uint8_t qbe[72];
+	words_to_be(qbe, (int)qlen, ci->q);
+	std::vector<uint8_t> ok(num, 0);
+	std::atomic<int> mixed{ 0 };
+	std::vector<std::vector<uint32_t>> prj_parts(64);
+	/* pass 1: struct and range checks, affine keys (z needs them) */
+	parallel_for(num, [&](uint32_t lo, uint32_t hi, unsigned t) {
+		std::vector<uint32_t> &prj = prj_parts[t];
+		for (uint32_t i = lo; i < hi; i++) {
+			memset(&ab[i * 2 * qlen], 0, 2 * qlen);
+			memset(&pubs[i * 2 * plen], 0, 2 * plen);
+			const eccb200_ec_pub_key *pk = pub_keys[i];
+			if (!pk || pk->magic != kPubKeyMagic || pk->key_type != sig_type || !pt_ok(&pk->y)) continue;
+			if (!s[i] || (!m[i] && m_len[i])) continue;
+			const CurveInfo *c = identify(&pk->y);
+			if (!c) continue;
+			if (c != ci) {
+				mixed.store(1);
+				continue;
+			}
+			if (s_len[i] != siglen) continue;                       /* 1. (:589) */
+			const uint8_t *sb = s[i] + rlen;
+			bool zero = true;
+			for (size_t j = 0; j < qlen; j++) zero = zero && sb[j] == 0;
+			if (zero || memcmp(sb, qbe, qlen) >= 0) continue;       /* 2. s in ]0, q[ (:592-595) */
+			const eccb200_prj_pt *y = &pk->y;
+			if (fp_is_small(&y->Z, 1)) {
+				fp_to_be(&pubs[i * 2 * plen], &y->X, pl);
+				fp_to_be(&pubs[i * 2 * plen + plen], &y->Y, pl);
+			} else {
+				prj.push_back(i);
+			}
+			ok[i] = 1;
+		}
+	});
+	if (mixed.load()) return -1;
+	std::vector<uint32_t> prj_idx;
+	for (auto &part : prj_parts) prj_idx.insert(prj_idx.end(), part.begin(), part.end());
+	if (!prj_idx.empty()) {
+		std::vector<uint8_t> pb(prj_idx.size() * 3 * plen), abuf(prj_idx.size() * 2 * plen);
+		std::vector<int8_t> st(prj_idx.size());
+		parallel_for((uint32_t)prj_idx.size(), [&](uint32_t lo, uint32_t hi, unsigned) {
+			for (uint32_t k = lo; k < hi; k++) {
+				const eccb200_prj_pt *p = &pub_keys[prj_idx[k]]->y;
+				fp_to_be(&pb[k * 3 * plen], &p->X, pl);
+				fp_to_be(&pb[k * 3 * plen + plen], &p->Y, pl);
+				fp_to_be(&pb[k * 3 * plen + 2 * plen], &p->Z, pl);
+			}
+		});
+		if (eccb200_prj_pt_unique_batch(eng, (uint32_t)prj_idx.size(), pb.data(), abuf.data(), st.data())) return -1;
+		for (size_t k = 0; k < prj_idx.size(); k++) {
+			uint32_t i = prj_idx[k];
+			if (st[k] == 0) memcpy(&pubs[i * 2 * plen], &abuf[k * 2 * plen], 2 * plen);
+			else ok[i] = 0; /* off the curve, or infinity: prj_pt_to_aff fails on it (:614) */
+		}
+	}
+	/* pass 2: h = H(z || m), e = OS2I(r XOR rightmost(h)) mod q */
+	parallel_for(num, [&](uint32_t lo, uint32_t hi, unsigned) {
+		std::vector<uint8_t> z(zlen);
+		for (uint32_t i = lo; i < hi; i++) {
+			if (!ok[i]) {
+				memset(&ab[i * 2 * qlen], 0, 2 * qlen);
+				gen_to_be(&pubs[i * 2 * plen], ci); /* keep the batch launchable */
+				continue;
+			}
+			std::fill(z.begin(), z.end(), 0);
+			memcpy(z.data(), &pubs[i * 2 * plen], std::min<size_t>(zlen, 2 * plen)); /* 3. z (:601-625) */
+			uint8_t h[128], x[128];
+			const unsigned char *in[3] = { z.data(), m[i], nullptr };
+			uint32_t il[2] = { zlen, m_len[i] };
+			if (hm->hfunc_scattered(in, il, h)) {
+				ok[i] = 0;
+				continue;
+			}
+			for (size_t j = 0; j < rlen; j++) x[j] = (uint8_t)(h[shift + j] ^ s[i][j]); /* 4.-5. (:754-762) */
+			eccb200_nn t;
+			be_to_nn(&t, x, (uint32_t)rlen);
+			scalar_mod_to_be(&ab[i * 2 * qlen], &t, ci);                  /* e on G */
+			memcpy(&ab[i * 2 * qlen + qlen], s[i] + rlen, qlen);         /* s on Y */
+		}
+	});
+	if (eccb200_double_smul_batch(eng, num, ab, pubs, wout, status)) return -1; /* 6. W' = sY + eG (:770-773) */
+	g_verifies += num;
+	std::vector<int8_t> verdict(num, -1);
+	parallel_for(num, [&](uint32_t lo, uint32_t hi, unsigned) {
+		for (uint32_t i = lo; i < hi; i++) {
+			if (!ok[i] || status[i] != 0) continue; /* infinity: prj_pt_unique fails (:773) */
+			uint8_t rp[128];
+			const unsigned char *in[2] = { &wout[i * 2 * plen], nullptr };
+			uint32_t il[1] = { (uint32_t)plen };
+			if (hm->hfunc_scattered(in, il, rp)) continue;                /* 7. r' = H(W'_x) (:778-784) */
+			verdict[i] = memcmp(rp + shift, s[i], rlen) == 0 ? 0 : -1;   /* 8.-9. (:794-800) */
+		}
+	});
+	int all = 0;
+	for (uint32_t i = 0; i < num; i++)
+		if (verdict[i]) all = -1;
+	t_verdicts.assign(verdict.begin(), verdict.end());
+	return all;
+}
+
 extern "C" int eccb200_dropin_ecdsa_verify_batch(const uint8_t **s, const uint8_t *s_len,
 						 const eccb200_ec_pub_key **pub_keys, const uint8_t **m,
 						 const uint32_t *m_len, uint32_t num, int sig_type, int hash_type,
@@ -856,6 +996,20 @@ extern "C" int eccb200_dropin_ecsdsa_verify_batch(const uint8_t **s, const uint8
 	return verify_batch_ecsdsa(sig_type == 4, s, s_len, pub_keys, m, m_len, num, sig_type, hash_type, adata);
 }
 
+/* ECKCDSA (sig_type 2): also left at unsupported_verify_batch by the reference */
+extern "C" int eccb200_dropin_eckcdsa_verify_batch(const uint8_t **s, const uint8_t *s_len,
+						   const eccb200_ec_pub_key **pub_keys, const uint8_t **m,
+						   const uint32_t *m_len, uint32_t num, int sig_type, int hash_type,
+						   const uint8_t **adata, const uint16_t *adata_len,
+						   void *scratch_pad_area, uint32_t *scratch_pad_area_len)
+{
+	(void)scratch_pad_area;
+	(void)scratch_pad_area_len;
+	(void)adata_len;
+	if (sig_type != 2 /* ECKCDSA */) return -1;
+	return verify_batch_eckcdsa(s, s_len, pub_keys, m, m_len, num, sig_type, hash_type, adata);
+}
+
 /* BIP0340: a replacement for the reference's own bip0340_verify_batch (sig/bip0340.c:1296) in the same slot */
 extern "C" int eccb200_dropin_bip0340_verify_batch(const uint8_t **s, const uint8_t *s_len,
 						   const eccb200_ec_pub_key **pub_keys, const uint8_t **m,
@@ -894,7 +1048,8 @@ extern "C" int eccb200_dropin_ec_verify(const uint8_t *sig, uint8_t siglen, cons
 					const uint8_t *adata, uint16_t adata_len)
 {
 	Scheme sc = kEcdsa;
-	const bool post_hash = (sig_type == 3 || sig_type == 4); /* ECSDSA / ECOSDSA: hash of the recomputed point */
+	const bool post_hash = (sig_type == 2 || sig_type == 3 || sig_type == 4); /* ECKCDSA / ECSDSA / ECOSDSA: these hash
+										    * the recomputed point */
 	bool ours = (post_hash || scheme_of(sig_type, &sc)) && !adata && adata_len == 0 && sig && pub_key &&
 		    pub_key->magic == kPubKeyMagic &&
 		    pub_key->key_type == sig_type && pt_ok(&pub_key->y) && identify(&pub_key->y) != nullptr &&
@@ -912,6 +1067,7 @@ extern "C" int eccb200_dropin_ec_verify(const uint8_t *sig, uint8_t siglen, cons
 	const eccb200_ec_pub_key *pk[1] = { pub_key };
 	const uint8_t *mp[1] = { m };
 	const uint32_t ml[1] = { mlen };
+	if (sig_type == 2) return verify_batch_eckcdsa(sp, sl, pk, mp, ml, 1, sig_type, hash_type, nullptr);
 	if (post_hash) return verify_batch_ecsdsa(sig_type == 4, sp, sl, pk, mp, ml, 1, sig_type, hash_type, nullptr);
 	return verify_batch_common(sc, sp, sl, pk, mp, ml, 1, sig_type, hash_type, nullptr);
 }

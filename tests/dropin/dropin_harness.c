@@ -286,9 +286,9 @@ static int run_direct(const char *dropin_path)
 		}
 		/* ---- ECSDSA / ECOSDSA: batch adapter (W' = sG + eY on the device, hashing of W' with the reference's src/hash)
 		 * and ec_verify shim against the reference's ec_verify */
-		for (int alt = 0; alt < 2; alt++) {
+		for (int alt = 0; alt < 3; alt++) {
 			enum { NSD = 20 };
-			const ec_alg_type alg = alt ? ECOSDSA : ECSDSA;
+			const ec_alg_type alg = alt == 0 ? ECSDSA : (alt == 1 ? ECOSDSA : ECKCDSA);
 			static ec_key_pair kp[NSD];
 			static u8 sigs[NSD][64 + 66 + 8], msgs[NSD][40];
 			const u8 *sp[NSD], *mp[NSD];
@@ -296,8 +296,9 @@ static int run_direct(const char *dropin_path)
 			u8 sl[NSD], sgl = 0;
 			u32 ml[NSD];
 			hash_alg_type ht = (c == 2) ? SHA384 : ((c == 5 || c == 7) ? SHA512 : SHA256);
-			vbatch_fn gpu_sdbatch = (vbatch_fn)dlsym(h, "eccb200_dropin_ecsdsa_verify_batch");
-			CHECK(gpu_sdbatch != NULL, "missing eccb200_dropin_ecsdsa_verify_batch");
+			vbatch_fn gpu_sdbatch = (vbatch_fn)dlsym(h, alt == 2 ? "eccb200_dropin_eckcdsa_verify_batch"
+									      : "eccb200_dropin_ecsdsa_verify_batch");
+			CHECK(gpu_sdbatch != NULL, "missing eccb200_dropin_ec(k|s)cdsa_verify_batch");
 			if (!gpu_sdbatch) break;
 			CHECK(!ec_get_sig_len(&params, alg, ht, &sgl), "siglen");
 			for (int i = 0; i < NSD; i++) {
@@ -311,21 +312,21 @@ static int run_direct(const char *dropin_path)
 				pk[i] = &kp[i].pub_key;
 			}
 			int r = gpu_sdbatch(sp, sl, pk, mp, ml, NSD, alg, ht, NULL, NULL, NULL, NULL);
-			CHECK(r == 0, "%s ec%ssdsa verify_batch: valid batch rejected", names[c], alt ? "o" : "");
+			CHECK(r == 0, "%s scheme %d verify_batch: valid batch rejected", names[c], (int)alg);
 			sigs[4][1] ^= 0x08;        /* r */
 			sigs[8][sgl - 1] ^= 1;     /* s */
 			msgs[12][0] ^= 1;
 			r = gpu_sdbatch(sp, sl, pk, mp, ml, NSD, alg, ht, NULL, NULL, NULL, NULL);
-			CHECK(r == -1, "%s ec%ssdsa verify_batch: corrupted batch accepted", names[c], alt ? "o" : "");
+			CHECK(r == -1, "%s scheme %d verify_batch: corrupted batch accepted", names[c], (int)alg);
 			signed char v[NSD];
 			CHECK(gpu_verdicts(v, NSD) == NSD, "verdict count");
 			for (int i = 0; i < NSD; i++) {
 				int want = ec_verify(sigs[i], sl[i], pk[i], msgs[i], ml[i], alg, ht, NULL, 0) ? -1 : 0;
-				CHECK(v[i] == want, "%s ec%ssdsa verdict[%d] = %d, reference ec_verify says %d", names[c], alt ? "o" : "", i, v[i], want);
+				CHECK(v[i] == want, "%s scheme %d verdict[%d] = %d, reference ec_verify says %d", names[c], (int)alg, i, v[i], want);
 				int got = gpu_everify(sigs[i], sl[i], pk[i], msgs[i], ml[i], alg, ht, NULL, 0) ? -1 : 0;
-				CHECK(got == want, "%s ec%ssdsa ec_verify shim item %d: %d vs %d", names[c], alt ? "o" : "", i, got, want);
+				CHECK(got == want, "%s scheme %d ec_verify shim item %d: %d vs %d", names[c], (int)alg, i, got, want);
 			}
-			CHECK(v[4] == -1 && v[8] == -1 && v[12] == -1, "corrupted EC(O)SDSA items not flagged");
+			CHECK(v[4] == -1 && v[8] == -1 && v[12] == -1, "corrupted items of scheme %d not flagged", (int)alg);
 		}
 		/* ---- BIP0340 in the same slot and through the ec_verify shim: against the reference's ec_verify */
 		{
