@@ -1299,6 +1299,8 @@ static int hash_dev(eccb200_ctx *ctx, int hash_type, uint32_t n, const uint8_t *
 	return 0;
 }
 
+static inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+
 /* offsets[0] == 0 and non-decreasing: message i is msgs[offsets[i], offsets[i+1]) inside the offsets[n] bytes copied */
 static bool offsets_ok(const uint64_t *offsets, uint32_t n)
 {
@@ -1333,7 +1335,9 @@ extern "C" int eccb200_hash_batch(eccb200_ctx *ctx, int hash_type, uint32_t n, c
 	return rc;
 }
 
-/* ECDSA verification of raw messages: SHA-2 on the device, then K3.  One launch pair for the whole batch. */
+/* ECDSA verification of raw messages: hashing on the device, then K3 — per chunk of four waves, on two streams, so
+ * that the copies of one chunk overlap the kernels of the other (variable-length messages: a chunk's slice of `msgs`
+ * is msgs[offsets[lo], offsets[hi]); the hash kernel keeps addressing it with the caller's absolute offsets). */
 extern "C" int eccb200_ecdsa_verify_msgs_batch(eccb200_ctx *ctx, int hash_type, uint32_t n, const uint8_t *sigs,
 					       const uint8_t *pubkeys, const uint8_t *msgs, const uint64_t *offsets,
 					       int8_t *verdict)
@@ -1344,22 +1348,47 @@ extern "C" int eccb200_ecdsa_verify_msgs_batch(eccb200_ctx *ctx, int hash_type, 
 	if (n == 0) return 0;
 	if (!offsets_ok(offsets, n)) return fail("offsets must start at 0 and be non-decreasing");
 	CUDA_OK(cudaSetDevice(ctx->device));
-	const uint64_t total = offsets[n];
-	if (total && !msgs) return fail("null argument");
-	const size_t sg = (size_t)n * 2 * ctx->qlen, pk = (size_t)n * 2 * ctx->plen, dg = (((size_t)n * ds) + 15) & ~(size_t)15;
-	const size_t mb = ((size_t)total + 15) & ~(size_t)15, ob = (size_t)(n + 1) * sizeof(uint64_t);
+	if (offsets[n] && !msgs) return fail("null argument");
+	const uint32_t step = ctx->chunk_eq;
+	const size_t sgi = 2 * (size_t)ctx->qlen, pki = 2 * (size_t)ctx->plen;
+	size_t max_msg = 0;
+	for (uint32_t lo = 0; lo < n; lo += step) {
+		const uint32_t hi = (uint32_t)std::min<uint64_t>((uint64_t)lo + step, n);
+		max_msg = std::max<size_t>(max_msg, (size_t)(offsets[hi] - offsets[lo]));
+	}
+	const uint32_t cap = std::min(step, n);
+	const size_t b_sig = align16(cap * sgi), b_pk = align16(cap * pki), b_dg = align16((size_t)cap * ds),
+		     b_msg = align16(max_msg + 16), b_off = align16(((size_t)cap + 1) * sizeof(uint64_t)), b_v = align16(cap);
+	const size_t stage = b_sig + b_pk + b_dg + b_msg + b_off + b_v;
 	uint8_t *d = nullptr;
-	CUDA_OK(cudaMalloc(&d, sg + pk + dg + mb + ob + n + 16));
-	uint8_t *d_sig = d, *d_pk = d + sg, *d_dg = d + sg + pk, *d_msg = d_dg + dg, *d_off = d_msg + mb, *d_v = d_off + ob;
+	CUDA_OK(cudaMalloc(&d, 2 * stage));
 	int rc = 0;
-	if (cudaMemcpy(d_sig, sigs, sg, cudaMemcpyHostToDevice) != cudaSuccess ||
-	    cudaMemcpy(d_pk, pubkeys, pk, cudaMemcpyHostToDevice) != cudaSuccess ||
-	    (total && cudaMemcpy(d_msg, msgs, total, cudaMemcpyHostToDevice) != cudaSuccess) ||
-	    cudaMemcpy(d_off, offsets, ob, cudaMemcpyHostToDevice) != cudaSuccess)
-		rc = fail("H2D copy failed");
-	if (!rc) rc = hash_dev(ctx, hash_type, n, d_msg, (const uint64_t *)d_off, d_dg, 0);
-	if (!rc) rc = verify_dev(ctx, n, d_sig, d_pk, d_dg, (uint32_t)ds, (int8_t *)d_v, 0);
-	if (!rc && cudaMemcpy(verdict, d_v, n, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail("D2H copy failed");
+	uint32_t c = 0;
+	for (uint32_t lo = 0; lo < n && !rc; lo += step, c++) {
+		const uint32_t hi = (uint32_t)std::min<uint64_t>((uint64_t)lo + step, n), cnt = hi - lo;
+		cudaStream_t st = ctx->streams[c & 1];
+		uint8_t *base = d + (size_t)(c & 1) * stage;
+		uint8_t *d_sig = base, *d_pk = d_sig + b_sig, *d_dg = d_pk + b_pk, *d_msg = d_dg + b_dg, *d_off = d_msg + b_msg,
+			*d_v = d_off + b_off;
+		const size_t mbytes = (size_t)(offsets[hi] - offsets[lo]);
+		if (cudaMemcpyAsync(d_sig, sigs + lo * sgi, cnt * sgi, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+		    cudaMemcpyAsync(d_pk, pubkeys + lo * pki, cnt * pki, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+		    (mbytes && cudaMemcpyAsync(d_msg, msgs + offsets[lo], mbytes, cudaMemcpyHostToDevice, st) != cudaSuccess) ||
+		    cudaMemcpyAsync(d_off, offsets + lo, ((size_t)cnt + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st) !=
+			    cudaSuccess) {
+			rc = fail("H2D copy failed");
+			break;
+		}
+		/* the kernel adds the caller's absolute offsets to this base: the chunk's bytes start at offsets[lo] */
+		rc = hash_dev(ctx, hash_type, cnt, d_msg - offsets[lo], (const uint64_t *)d_off, d_dg, st);
+		if (!rc) rc = verify_dev(ctx, cnt, d_sig, d_pk, d_dg, (uint32_t)ds, (int8_t *)d_v, st);
+		if (!rc && cudaMemcpyAsync(verdict + lo, d_v, cnt, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+			rc = fail("D2H copy failed");
+	}
+	const std::string keep = g_err;
+	for (int s2 = 0; s2 < 2; s2++)
+		if (cudaStreamSynchronize(ctx->streams[s2]) != cudaSuccess && !rc) rc = fail("stream synchronisation failed");
+	if (rc && !keep.empty()) g_err = keep;
 	cudaFree(d);
 	return rc;
 }
@@ -1393,7 +1422,6 @@ extern "C" int eccb200_copy_to_host(eccb200_ctx *ctx, void *host_dst, const void
 /* ------------------------------------------------------------------------------------------ structured wire formats (§8f.2) */
 
 static inline uint32_t grid_bytes(uint64_t total) { return (uint32_t)((total + 255) / 256); }
-static inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
 /* device scratch of the structured-record entry points: one allocation, carved into 16-byte aligned pieces */
 struct DevArena {

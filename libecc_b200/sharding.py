@@ -72,16 +72,33 @@ def gather_destinations(world: int, mode: str):
     raise ValueError(mode)
 
 
+class _TorchStreams:
+    """Stream / event plumbing of the copy-engine transport (torch.cuda); the CPU tests substitute a recorder."""
+
+    def current(self, device):
+        return torch.cuda.current_stream(device)
+
+    def new(self, device):
+        return torch.cuda.Stream(device=device)
+
+    def event(self):
+        return torch.cuda.Event()
+
+    def empty(self, nbytes, device):
+        return torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+
 class PeerGather:
     """Per-rank state of the peer-memory gather for fixed-size batches of `n_items` results."""
 
     def __init__(self, eng, rank: int, world: int, n_items: int, mode: str = "root", nbuf: int = 2, group=None,
-                 transport: str = "fused"):
+                 transport: str = "fused", streams=None):
         """transport 'fused': the normalisation kernel stores into the destinations itself (step);
         'ce': the kernel writes locally and a copy-engine transfer on a side stream pushes the slot to the destinations
         while the NEXT batch computes (step_ce / drain)."""
         self.group = group
         self.transport = transport
+        self.streams = streams or _TorchStreams()
         self.copy_stream = None
         self.copy_done = {}
         self.local = {}
@@ -149,22 +166,22 @@ class PeerGather:
         b = self.step_no % self.nbuf
         L = self.layout
         used = self.n * 2 * self.eng.plen + self.n
-        C = torch.cuda.current_stream(device)
+        C = self.streams.current(device)
         if self.copy_stream is None:
-            self.copy_stream = torch.cuda.Stream(device=device)
+            self.copy_stream = self.streams.new(device)
         X = self.copy_stream
         if self.rank in self.dests:
             src = self.base + slot_offset(L, b, self.rank)
         else:
             if b not in self.local:
-                self.local[b] = torch.empty(L["slot_bytes"], dtype=torch.uint8, device=device)
+                self.local[b] = self.streams.empty(L["slot_bytes"], device)
             src = self.local[b].data_ptr()
         if b in self.copy_done:
             C.wait_event(self.copy_done[b])          # the push that last read this buffer has completed
         self.eng.prj_pt_mul_batch_dev_raw(self.n, p_scalars, p_points, src, src + L["status_offset"], C.cuda_stream)
         others = [d for d in self.dests if d != self.rank]
         if others:
-            ev = torch.cuda.Event()
+            ev = self.streams.event()
             ev.record(C)
             X.wait_event(ev)
             need_ack = c - self.nbuf
@@ -172,7 +189,7 @@ class PeerGather:
             self.eng.push_results([self.peer[d] + slot_offset(L, b, self.rank) for d in others], src, used,
                                   [self.peer[d] + L["flags"] + 4 * self.rank for d in others], c, wait_ptr, wait_cnt,
                                   max(need_ack, 0), X.cuda_stream)
-            done = torch.cuda.Event()
+            done = self.streams.event()
             done.record(X)
             self.copy_done[b] = done
         if self.rank in self.dests:
@@ -195,7 +212,7 @@ class PeerGather:
     def drain(self, device=None):
         """Closes the pipeline of step_ce on the current stream: a destination waits for (and releases) the last
         batch of every rank; a source waits until its last push has left."""
-        C = torch.cuda.current_stream(device)
+        C = self.streams.current(device)
         if self.rank in self.dests and self.step_no >= 1:
             self._consume(self.step_no, C.cuda_stream)
         for ev in self.copy_done.values():

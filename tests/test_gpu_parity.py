@@ -425,3 +425,14 @@ def test_ecdsa_verify_msgs_batch():
         got = engine(curve).ecdsa_verify_msgs_batch(hname, sigs, pubs, msgs)
         want = np.zeros(n, dtype=np.int8); want[bad] = -1
         assert (got == want).all()
+        if curve == "FRP256V1":
+            # the same tuples tiled past one pipeline chunk (4 waves = 303 104 items): variable-length messages whose
+            # offsets cross the chunk boundaries, empty messages included, and a ragged last chunk
+            reps = 530
+            blob = np.frombuffer(b"".join(msgs) * reps, dtype=np.uint8)
+            lens = np.tile(np.array([len(m) for m in msgs], dtype=np.uint64), reps)
+            off = np.zeros(n * reps + 1, dtype=np.uint64)
+            off[1:] = np.cumsum(lens)
+            big = engine(curve).ecdsa_verify_msgs_batch_raw(hname, np.tile(sigs, (reps, 1)), np.tile(pubs, (reps, 1)),
+                                                            blob, off)
+            assert big.shape[0] == n * reps and (big == np.tile(want, reps)).all()
