@@ -390,8 +390,10 @@ __global__ void __launch_bounds__(128) k_smul_fixed_tma(uint32_t n, const uint8_
 #ifndef ECC_MINB_VAR
 #define ECC_MINB_VAR 7
 #endif
+/* Round 2 (after the safegcd inversion), same sweep: ECC_MINB_VERIFY 5 / 6 / 7 / 8 -> 19.47 / 19.84 / 19.95 / 19.77 M/s
+ * (FRP256V1, messages); ECC_MINB_VAR 6 / 7 / 8 / 9 -> 22.76 / 22.52-22.86 / 22.81 / 22.86 M/s: flat within the noise. */
 #ifndef ECC_MINB_VERIFY
-#define ECC_MINB_VERIFY 6
+#define ECC_MINB_VERIFY 7
 #endif
 /* 12-word fields (P-384) need 1.5x the registers per element: keep their caps at 168 / 128 registers;
  * 18-word fields (P-521) get the full 255 (2 CTAs per SM) */
