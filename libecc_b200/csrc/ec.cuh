@@ -314,6 +314,21 @@ template <class C> struct EC {
 		F::sqr(r.ZZ, d.Z);
 		F::mul(r.ZZZ, r.ZZ, d.Z);
 	}
+	/* the i-th of the eight products of xz_add_mixed: the first ECC_K1_OOL_MULS of them call the out-of-line copy when
+	 * the translation unit inlines the multiplier (K1), see Field::mul_ool */
+#ifndef ECC_K1_OOL_MULS
+#define ECC_K1_OOL_MULS 0
+#endif
+	template <int I> static ECC_HD void xz_mul(E &r, const E &a, const E &b)
+	{
+#if defined(ECC_INLINE_MUL)
+		if (I < ECC_K1_OOL_MULS) {
+			F::mul_ool(r, a, b);
+			return;
+		}
+#endif
+		F::mul(r, a, b);
+	}
 	static ECC_HD void xz_add_mixed(XZ &r, const XZ &p, const A &q)
 	{
 		E u2, s2, pp_, rr, ppp, qv, t;
@@ -321,8 +336,8 @@ template <class C> struct EC {
 			xz_from_affine(r, q);
 			return;
 		}
-		F::mul(u2, q.x, p.ZZ);
-		F::mul(s2, q.y, p.ZZZ);
+		xz_mul<0>(u2, q.x, p.ZZ);
+		xz_mul<1>(s2, q.y, p.ZZZ);
 		F::sub(pp_, u2, p.X); /* P */
 		F::sub(rr, s2, p.Y);  /* R */
 		if (F::is_zero(pp_)) {
@@ -332,19 +347,19 @@ template <class C> struct EC {
 		}
 		E x3, y3;
 		F::sqr(t, pp_);        /* PP */
-		F::mul(ppp, pp_, t);   /* PPP */
-		F::mul(qv, p.X, t);    /* Q = X1 * PP */
+		xz_mul<2>(ppp, pp_, t);   /* PPP */
+		xz_mul<3>(qv, p.X, t);    /* Q = X1 * PP */
 		E zz3;
-		F::mul(zz3, p.ZZ, t);  /* ZZ3 = ZZ1 * PP */
+		xz_mul<4>(zz3, p.ZZ, t);  /* ZZ3 = ZZ1 * PP */
 		F::sqr(x3, rr);
 		F::sub(x3, x3, ppp);
 		F::sub(x3, x3, qv);
 		F::sub(x3, x3, qv);    /* X3 = R^2 - PPP - 2Q */
 		F::sub(t, qv, x3);
-		F::mul(y3, rr, t);
-		F::mul(t, p.Y, ppp);
+		xz_mul<5>(y3, rr, t);
+		xz_mul<6>(t, p.Y, ppp);
 		F::sub(y3, y3, t);     /* Y3 = R (Q - X3) - Y1 PPP */
-		F::mul(t, p.ZZZ, ppp); /* ZZZ3 = ZZZ1 * PPP */
+		xz_mul<7>(t, p.ZZZ, ppp); /* ZZZ3 = ZZZ1 * PPP */
 		r.ZZZ = t;
 		r.ZZ = zz3;
 		r.X = x3;
@@ -496,6 +511,16 @@ template <class C> ECC_HD void comb_mul(Jac<C> &out, const Fe<C::N> &k, const ui
 	for (int i = 0; i < nwin; i++) {
 		uint32_t d = kk.w[0] & mask;
 		shift_right<N>(kk, w);
+#if defined(__CUDA_ARCH__) && defined(ECC_COMB_PREFETCH)
+		/* the NEXT window's entry is requested into L2 while this window's addition runs: the gathers are random
+		 * accesses into a table of tens of GB, i.e. DRAM latency on the critical path of every window otherwise */
+		if (i + 1 < nwin) {
+			const uint32_t nd = kk.w[0] & mask;
+			const uint32_t *nxt = table + (((size_t)(i + 1) << w) + nd) * (2 * N);
+			asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
+			if ((2 * N * 4) % 128 != 0 && (2 * N * 4) > 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 2 * N - 1));
+		}
+#endif
 		if (d != 0) {
 			Aff<C> t;
 			load_table_entry<C>(t, table, ((size_t)i << w) + d);

@@ -175,6 +175,15 @@ template <class F> struct Field : FieldCore<F> {
 	using Core::sqr;
 	using Core::sub;
 
+	/* An out-of-line copy of the product for kernels that otherwise inline it (K1): calling it for some of the
+	 * products of the loop body keeps the body inside the instruction cache (ECC_K1_OOL_MULS, ec.cuh). */
+#if defined(__CUDA_ARCH__) && !defined(ECC_NO_PTX)
+	static __device__ __noinline__ E mul_ool_fn(E a, E b) { return Core::mul_fn(a, b); }
+	static __device__ __forceinline__ void mul_ool(E &r, const E &a, const E &b) { r = mul_ool_fn(a, b); }
+#else
+	static ECC_HD void mul_ool(E &r, const E &a, const E &b) { Core::mul(r, a, b); }
+#endif
+
 	static ECC_HD void set_zero(E &r)
 	{
 #pragma unroll
