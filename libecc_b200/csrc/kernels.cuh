@@ -303,8 +303,14 @@ __device__ __forceinline__ void cta_inverse_128(Fe<FT::N> &inv, const Fe<FT::N> 
 
 /* ------------------------------------------------------------------------------------------ K1: fixed base */
 
+/* minimum resident CTAs per SM of K1 (register cap).  Measured in round 2 and left at 1: secp256r1 needs 98 registers
+ * (4 CTAs); capping at 96 / 80 (5 / 6 CTAs, a few spills) gave 665 / 662 M/s against 663 — the kernel is bound by the
+ * integer pipes, not by latency hiding; secp384r1 loses 6 % at 96 registers. */
+#ifndef ECC_MINB_FIXED
+#define ECC_MINB_FIXED 1
+#endif
 template <class C>
-__global__ void __launch_bounds__(128) k_smul_fixed(uint32_t n, const uint8_t *__restrict__ scalars,
+__global__ void __launch_bounds__(128, ECC_MINB_FIXED) k_smul_fixed(uint32_t n, const uint8_t *__restrict__ scalars,
 						    const uint32_t *__restrict__ table, int w,
 						    uint32_t *__restrict__ jac, int8_t *__restrict__ status)
 {

@@ -2,7 +2,7 @@
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 for lib in $LIBS; do
-  for wl in secp256r1_fixed_base secp384r1_fixed_base; do
+  for wl in secp256r1_fixed_base frp256v1_fixed_base secp384r1_fixed_base secp521r1_fixed_base; do
     ECCB200_LIB=$PWD/libecc_b200/libecc_b200$lib.so timeout 600 python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/r2_ool${lib}_$wl.json 2> gpurun_out/r2_ool${lib}_$wl.err
     python - "$lib" "$wl" <<'PY'
 import json,sys
