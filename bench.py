@@ -485,6 +485,37 @@ class Ours:
             import torch.distributed as dist
             dist.all_gather_into_tensor(self.gathered, self.res)
 
+    def p2p_probe(self):
+        """Diagnostic (BENCH_P2P_PROBE=1, N > 1, copy-engine gather): every non-root rank in turn, alone, pushes its slot
+        to rank 0 five times; returns the GB/s per rank (rank 0: 0)."""
+        import torch.distributed as dist
+        torch = self.torch
+        pg, n = self.pg, self.n
+        used = n * 2 * self.plen + n
+        rate = 0.0
+        from libecc_b200.sharding import slot_offset
+        for r in range(1, self.world):
+            dist.barrier()
+            torch.cuda.synchronize()
+            if self.rank == r and pg is not None and 0 in pg.peer:
+                src = torch.empty(used, dtype=torch.uint8, device=self.dev)
+                st = torch.cuda.Stream(device=self.dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                dst = pg.peer[0] + slot_offset(pg.layout, 0, r)
+                scratch_flag = pg.base + 3072          # a word of the own flag page nobody reads
+                for it in range(6):
+                    if it == 1:
+                        e0.record(st)
+                    self.eng.push_results([dst], src.data_ptr(), used, [scratch_flag], 1, None, 0, 0, st.cuda_stream)
+                e1.record(st)
+                st.synchronize()
+                rate = 5 * used / (e0.elapsed_time(e1) / 1000.0) / 1e9
+        dist.barrier()
+        t = torch.tensor([rate], dtype=torch.float64, device=self.dev)
+        out = [torch.zeros_like(t) for _ in range(self.world)]
+        dist.all_gather(out, t)
+        return [round(float(x.item()), 1) for x in out]
+
     def sync_all(self):
         if self.world > 1:
             import torch.distributed as dist
@@ -770,6 +801,7 @@ def main():
     default_workload = args.workload == "secp256r1_fixed_base" and args.batch_log2 == 20
     o = Ours(args.workload, args.batch_log2, args.comb_window, rank, world, local_rank, args.gather)
     n = o.n
+    p2p = o.p2p_probe() if (world > 1 and o.pg is not None and os.environ.get("BENCH_P2P_PROBE")) else None
     m = o.measure_device(args.steps, args.warmup)
     parity = o.parity()
     gchk = o.gather_checks() if world > 1 else {}
@@ -823,6 +855,8 @@ def main():
             "e2e": dict(e2e, same_results_as_device_leg=e2e["parity"]),
             "roofline": roofline, "parity_spot_check": parity}
     line.update(gchk)
+    if p2p is not None:
+        line["p2p_push_GBps_per_rank_alone"] = p2p
     if m["kernel_ms_per_rank"]:
         line["per_rank"] = m["kernel_ms_per_rank"]
     if world == 1 and not args.no_cpu_baseline:
