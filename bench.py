@@ -59,6 +59,7 @@ WORKLOADS = {
     "secp521r1_ecdsa_verify": ("SECP521R1", "verify", "secp521r1 ECDSA ec_verify/sec", "ec_verify/s"),
 }
 SEED = 0x6C69626563632D31
+SETTLE_STEPS = 10     # untimed steps after the W warm-up steps (see Ours.measure_device)
 MSG_LEN = 32          # the ECDSA workloads verify MESSAGES (ec_verify hashes them): 32 random bytes each, SHA-256
 VERIFY_HASH = "SHA256"
 # comb window of the fixed-base table when --comb-window is not given: the widest table that pays on a B200
@@ -525,7 +526,9 @@ class Ours:
     def measure_device(self, steps: int, warmup: int) -> dict:
         torch, eng = self.torch, self.eng
         eng.profile_enable(True)
-        for _ in range(warmup):
+        # W warm-up steps as asked, plus SETTLE_STEPS more untimed ones: the timed region of the default run is ~30 ms, short
+        # enough for a clock ramp or a lazily established peer mapping to show in it (reported as config.settle_steps)
+        for _ in range(warmup + SETTLE_STEPS):
             self.step_dev()
             self.flush.zero_()
         self.sync_all()
@@ -659,6 +662,11 @@ class Ours:
         import libecc_b200
         torch, eng, inputs = self.torch, self.eng, self.inputs
         n = n_items or self.n
+        restore = None
+        if self.world == 1:
+            # the page-locked buffers and the calling thread belong on the GPU's NUMA node (N > 1: the whole rank is bound)
+            restore = os.sched_getaffinity(0)
+            libecc_b200.load_library().eccb200_bind_thread_near_device(self.local_rank)
         reps = (n + self.n - 1) // self.n
         wc = os.environ.get("BENCH_WC_INPUTS", "0") == "1"
 
@@ -703,6 +711,8 @@ class Ours:
             same = bool((res[0][:256] == want).all() and (res[1][:256] == wst).all())
             if reps > 1:                                  # tiled inputs: every tile must repeat the first one
                 same = same and bool((res[0][self.n: 2 * self.n] == res[0][: self.n]).all())
+        if restore is not None:
+            os.sched_setaffinity(0, restore)
         return {"value": val, "unit": self.unit, "h2d_bytes_per_step": n * self.in_item,
                 "d2h_bytes_per_step": n * self.out_item, "steps": steps, "items_per_gpu": n,
                 "host_buffers": "page-locked (eccb200_host_alloc)", "parity": same}
@@ -850,7 +860,8 @@ def main():
             "config": dict(workload_config(args.workload, args.batch_log2, world),
                            l2="256 MiB buffer rewritten between timed iterations (outside the per-step events, at every N)",
                            comb_window=o.eng.comb_window, result_gather=gather_desc,
-                           timing="sum of per-step CUDA-event intervals on the compute stream, max over ranks"),
+                           timing="sum of per-step CUDA-event intervals on the compute stream, max over ranks",
+                           settle_steps=SETTLE_STEPS),
             "clocks": m["clocks"], "gpu_launches": m["launches"], "host_cpus_bound_near_gpu": numa_cpus,
             "e2e": dict(e2e, same_results_as_device_leg=e2e["parity"]),
             "roofline": roofline, "parity_spot_check": parity}
