@@ -774,6 +774,46 @@ def run_extra(name: str, batch_log2: int, steps: int, warmup: int, local_rank: i
     return res
 
 
+def run_sign_and_ecdh(local_rank: int, batch_log2: int = 20) -> dict:
+    """End-to-end rates of the two §8f.1 / f.2 batch entry points (host pointers, page-locked buffers), each checked
+    against the oracle on a prefix: ECDSA signing with caller-supplied nonces and ECC-CDH derivation (secp256r1)."""
+    import libecc_b200
+    from common import ALL_CURVES as CURVES, ORDER, oracle_sign, oracle_smul
+    curve = "SECP256R1"
+    _, plen, qlen = CURVES[curve]
+    n = 1 << batch_log2
+    q = ORDER[curve]
+    pin = lambda a: (lambda h: (h.__setitem__(Ellipsis, a), h)[1])(libecc_b200.pinned_empty(a.shape, a.dtype))
+    d = splitmix_bytes(n * qlen, 9600).reshape(n, qlen); d[:, 0] &= 0x7F; d[:, -1] |= 1
+    k = splitmix_bytes(n * qlen, 9700).reshape(n, qlen); k[:, 0] &= 0x7F; k[:, -1] |= 1
+    dg = splitmix_bytes(n * 32, 9800).reshape(n, 32)
+    eng = libecc_b200.Engine(curve, device=local_rank, comb_window=DEFAULT_COMB.get(curve, 0))
+    out = {}
+    hd, hk, hdg = pin(d), pin(k), pin(dg)
+    h_sig, h_st = libecc_b200.pinned_empty((n, 2 * qlen), np.uint8), libecc_b200.pinned_empty(n, np.int8)
+    eng.ecdsa_sign_batch(hd, hk, hdg, 32, out=h_sig, status=h_st)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        sigs, st = eng.ecdsa_sign_batch(hd, hk, hdg, 32, out=h_sig, status=h_st)
+    dt = (time.perf_counter() - t0) / 3
+    want, wst = oracle_sign(curve, d[:256], k[:256], dg[:256], 32)
+    out["secp256r1_ecdsa_sign"] = {"e2e_value": n / dt, "unit": "ec_sign/s (nonces supplied, digests)", "items": n,
+                                   "parity_spot_check": bool((sigs[:256] == want).all() and (st[:256] == wst).all() and (st == 0).all())}
+    pubs, _ = eng.prj_pt_mul_batch(k)                       # peers' public keys k_i * G
+    hp = pin(pubs)
+    h_sh = libecc_b200.pinned_empty((n, plen), np.uint8)
+    eng.ecccdh_derive_batch(hd, hp, out=h_sh, status=h_st)
+    t0 = time.perf_counter()
+    for _ in range(2):
+        shared, st = eng.ecccdh_derive_batch(hd, hp, out=h_sh, status=h_st)
+    dt = (time.perf_counter() - t0) / 2
+    want, wst = oracle_smul(curve, d[:128], pubs[:128])
+    out["secp256r1_ecccdh_derive"] = {"e2e_value": n / dt, "unit": "shared secrets/s", "items": n,
+                                      "parity_spot_check": bool((shared[:128] == want[:, :plen]).all() and (st == 0).all())}
+    eng.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -898,6 +938,10 @@ def main():
                     extra[name] = run_extra(name, lg, st, wu, local_rank, with_cpu=not args.no_cpu_baseline)
                 except Exception as exc:       # noqa: BLE001
                     extra[name] = {"error": str(exc)[:300]}
+            try:
+                extra.update(run_sign_and_ecdh(local_rank))
+            except Exception as exc:           # noqa: BLE001
+                extra["sign_and_ecdh"] = {"error": str(exc)[:300]}
         else:
             o.close()
             # the in-process multi-device C ABI (eccb200_multi_*): ONE host call shards 2^24 scalars over all GPUs of

@@ -261,23 +261,23 @@ class Engine:
                                                             hlen, verdict.ctypes.data), "eccb200_ecdsa_verify_prj_batch")
         return verdict
 
-    def ecdsa_sign_batch(self, privkeys, nonces, digests, hlen: int) -> Tuple[np.ndarray, np.ndarray]:
+    def ecdsa_sign_batch(self, privkeys, nonces, digests, hlen: int, out=None, status=None) -> Tuple[np.ndarray, np.ndarray]:
         d = _as_u8(privkeys)
         n = d.size // self.qlen
         k = _as_u8(nonces, n * self.qlen)
         dg = _as_u8(digests, n * hlen)
-        sigs = np.zeros((n, 2 * self.qlen), dtype=np.uint8)
-        status = np.zeros(n, dtype=np.int8)
+        sigs = out if out is not None else np.zeros((n, 2 * self.qlen), dtype=np.uint8)
+        status = status if status is not None else np.zeros(n, dtype=np.int8)
         self._check(self.lib.eccb200_ecdsa_sign_batch(self._h, n, d.ctypes.data, k.ctypes.data, dg.ctypes.data, hlen,
                                                       sigs.ctypes.data, status.ctypes.data), "eccb200_ecdsa_sign_batch")
         return sigs, status
 
-    def ecccdh_derive_batch(self, privkeys, peer_pubkeys) -> Tuple[np.ndarray, np.ndarray]:
+    def ecccdh_derive_batch(self, privkeys, peer_pubkeys, out=None, status=None) -> Tuple[np.ndarray, np.ndarray]:
         d = _as_u8(privkeys)
         n = d.size // self.qlen
         pk = _as_u8(peer_pubkeys, n * 2 * self.plen)
-        shared = np.zeros((n, self.plen), dtype=np.uint8)
-        status = np.zeros(n, dtype=np.int8)
+        shared = out if out is not None else np.zeros((n, self.plen), dtype=np.uint8)
+        status = status if status is not None else np.zeros(n, dtype=np.int8)
         self._check(self.lib.eccb200_ecccdh_derive_batch(self._h, n, d.ctypes.data, pk.ctypes.data,
                                                          shared.ctypes.data, status.ctypes.data),
                     "eccb200_ecccdh_derive_batch")
