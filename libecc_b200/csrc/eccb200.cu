@@ -125,11 +125,13 @@ extern "C" const char *eccb200_curve_name(int curve_id)
 
 /* threads for the batched normalisation: enough to fill the machine, few enough that every thread amortises its
  * inversion over many items */
-static uint32_t affine_grid(const eccb200_ctx *ctx, uint32_t n)
+static uint32_t affine_grid(const eccb200_ctx *ctx, uint32_t n, bool for_throughput = false)
 {
-	/* every thread should own at least ~8 items: the CTA-wide inversion (16 products per thread) is shared by the
-	 * items a thread walks, so a pipeline chunk of one wave is normalised by ~90 CTAs rather than by 592 nearly idle ones */
-	uint32_t want = (n + kThreads * 8 - 1) / (kThreads * 8);
+	/* Two regimes.  On its own in a stream the kernel is latency-bound for small n (two passes of dependent items per
+	 * thread around one inversion): as many CTAs as the machine holds, one item per thread if need be.  Running UNDER the
+	 * next chunk's scalar multiplication (side stream of the host pipeline) its work is what counts: every thread then
+	 * owns at least ~8 items, which share the 16 products per thread of the CTA-wide inversion. */
+	uint32_t want = for_throughput ? (n + kThreads * 8 - 1) / (kThreads * 8) : grid_for(n);
 	static int per_sm = 0; /* CTAs of 128 threads per SM; ECCB200_AFFINE_CTAS overrides (tuning knob) */
 	if (!per_sm) {
 		const char *e = getenv("ECCB200_AFFINE_CTAS");
@@ -415,7 +417,7 @@ static int smul_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_scalars, cons
 		if (after_smul) cudaEventRecord(after_smul, st);
 		if (st_norm && after_smul && after_norm) {
 			cudaStreamWaitEvent(st_norm, after_smul, 0);
-			LaunchMisc<C>::to_affine(affine_grid(ctx, n), n, jac, prefix, d_out, d_status, st_norm);
+			LaunchMisc<C>::to_affine(affine_grid(ctx, n, true), n, jac, prefix, d_out, d_status, st_norm);
 			cudaEventRecord(after_norm, st_norm);
 			cudaStreamWaitEvent(st, after_norm, 0);
 		} else {
@@ -540,7 +542,7 @@ static int smul_dev_sliced(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_scalar
 				g.status[j] += lo;
 			}
 			g.signal = last ? 1 : 0;
-			LaunchMisc<C>::to_affine(affine_grid(ctx, cnt), cnt, jac, ctx->prefix + (size_t)lo * C::N, d_out + lo * PL2,
+			LaunchMisc<C>::to_affine(affine_grid(ctx, cnt, true), cnt, jac, ctx->prefix + (size_t)lo * C::N, d_out + lo * PL2,
 						 d_status + lo, H, &g);
 			ctx->launches += 2;
 		}
