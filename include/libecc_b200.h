@@ -70,8 +70,8 @@ const char *eccb200_curve_name(int curve_id);
  *   out     : n * 2*plen bytes affine big-endian x||y (zero for non-OK items)
  *   status  : n bytes, ECCB200_OK / ECCB200_INFINITY / ECCB200_ERR (point not on curve or coordinate >= p:
  *             the reference fails prj_pt_import_from_aff_buf :541-545 / prj_pt_mul :1767)
- * Host-pointer version: blocking, includes the host<->device copies (pipelined in 2^18-item chunks over three
- * streams).  Page-locked caller buffers (eccb200_host_alloc, cudaHostAlloc, cudaHostRegister) are DMA'd directly;
+ * Host-pointer version: blocking, includes the host<->device copies (pipelined over three streams in chunks of whole
+ * kernel waves that ramp up from one wave and down to one wave, see eccb200_pipeline_chunk_bounds).  Page-locked caller buffers (eccb200_host_alloc, cudaHostAlloc, cudaHostRegister) are DMA'd directly;
  * pageable ones are staged through the context's own pinned buffers at the cost of one memcpy each way.
  */
 int eccb200_prj_pt_mul_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *scalars, const uint8_t *points,

@@ -691,7 +691,7 @@ template <class C> ECC_HD void digest_to_scalar(Fe<C::N> &e, const uint8_t *h, u
 }
 
 /* u = e * s^-1 mod q, v = r * s^-1 mod q (plain form): the mod-q scalar preparation of __ecdsa_verify_finalize
- * (sig/ecdsa_common.c:781-791: nn_modinv, nn_mod_mul), with s^-1 by Fermat in the Montgomery domain of q. */
+ * (sig/ecdsa_common.c:781-791: nn_modinv, nn_mod_mul), with s^-1 by Field::inv in the Montgomery domain of q. */
 template <class C>
 ECC_HD void ecdsa_uv(Fe<C::N> &u, Fe<C::N> &v, const Fe<C::N> &r, const Fe<C::N> &s, const Fe<C::N> &e)
 {
@@ -707,7 +707,7 @@ ECC_HD void ecdsa_uv(Fe<C::N> &u, Fe<C::N> &v, const Fe<C::N> &r, const Fe<C::N>
  * ECDSA verification of one signature (r, s) on the reduced digest e under the public key Y (affine, validated,
  * Montgomery form).  Returns 0 = valid; 1 = r/s out of range, 2 = W' at infinity, 3 = r' != r (all map to -1).  Follows __ecdsa_verify_init's range checks (sig/ecdsa_common.c:653-658) and
  * __ecdsa_verify_finalize steps 5-10 (:781-810); differences that do not change the verdict:
- *   - s^-1 mod q by Fermat in the Montgomery domain of q instead of nn_modinv's xgcd (:781);
+ *   - s^-1 mod q by Field::inv (safegcd) in the Montgomery domain of q instead of nn_modinv's xgcd (:781);
  *   - W' = uG + vY stays Jacobian and "x(W') mod q == r" is tested without an inversion as X == c * Z^2 for the
  *     candidates c in {r, r+q} that are < p (:803-810);
  *   - uG through the comb table (K1), vY through the signed window (K2) instead of two ladders (:788,793).

@@ -165,11 +165,12 @@ template <class C> __device__ __forceinline__ bool load_affine_checked(Aff<C> &P
 /*
  * Simultaneous inversion across the 128 threads of a CTA: every thread passes a non-zero Montgomery-form element
  * `acc` and gets acc^-1 back.  Two shared-memory scans (inclusive prefix P and suffix S, 7 doubling steps), ONE warp
- * runs the ~330-product Fermat chain on the CTA product, and thread t computes inv_total * P[t-1] * S[t+1].
+ * runs the inversion (Field::inv: safegcd division steps, round 1: a ~330-product Fermat chain) on the CTA product,
+ * and thread t computes inv_total * P[t-1] * S[t+1].
  * Must be called by all 128 threads of the CTA (it synchronises).  Cost per thread: 16 products + 1/4 inversion.
  */
 /*
- * Experimental (off by default, -DECC_CLUSTER_INV=2|4|8): K2 / K3 run as thread-block clusters and ONE Fermat chain
+ * Experimental (off by default, -DECC_CLUSTER_INV=2|4|8): K2 / K3 run as thread-block clusters and ONE inversion chain
  * serves the whole cluster — the CTA totals are exchanged through distributed shared memory, rank 0 inverts their
  * product and hands every CTA the inverse of its own total.  The chain's share per thread drops from 330/4 to
  * 330/(4*CL) product-equivalents (roofline.py: cta_inv).  Not part of the validated default build.
@@ -793,7 +794,7 @@ __global__ void __launch_bounds__(128) k_prj_load(uint32_t n, const uint8_t *__r
 /*
  * One signature per thread.  Follows __ecdsa_verify_init (sig/ecdsa_common.c:645-658) and
  * __ecdsa_verify_finalize (:760-810) step by step; differences that do not change the verdict:
- *   - s^-1 mod q by Fermat in the Montgomery domain of q instead of nn_modinv's xgcd (:781);
+ *   - s^-1 mod q by Field::inv (safegcd) in the Montgomery domain of q instead of nn_modinv's xgcd (:781);
  *   - W' = uG + vY is kept Jacobian and "x(W') mod q == r" is tested without an inversion as
  *     X == c * Z^2 for the candidates c in {r, r+q} that are < p (:803-810);
  *   - uG via the comb table (K1), vY via the signed window (K2) instead of two ladders (:788,793).
@@ -991,7 +992,7 @@ __global__ void ECC_CLUSTER_ATTR __launch_bounds__(128, (C::N <= 8 ? ECC_MINB_VE
 /*
  * Second half of a batched ECDSA signature (__ecdsa_sign_finalize steps 6-11, sig/ecdsa_common.c:479-560), after K1
  * computed k*G and K4 normalised it:  r = x(kG) mod q,  s = k^-1 (e + r*d) mod q.
- * k^-1 mod q uses the same two-level simultaneous inversion as K4 (one Fermat chain mod q per CTA; the reference does
+ * k^-1 mod q uses the same two-level simultaneous inversion as K4 (one inversion mod q per CTA; the reference does
  * one nn_modinv_fermat per signature, :537).  status: 0 ok; 2 = the reference's "restart with a new nonce" cases
  * (r == 0 :487, e == r*d :513, s == 0 :545); -1 = d or k outside [1, q-1].
  */
