@@ -722,6 +722,17 @@ class Ours:
         n = self.n
         peak = imad_peak_measured(self.local_rank)
         work = work_per_item(self.workload, self.eng.comb_window)
+        traffic = ncu_dram_traffic(self.workload, self.batch_log2, self.eng.comb_window)
+        hbm = None
+        try:   # driver-written measured copy bandwidth of this pool's B200s
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+            if traffic:
+                gbs = traffic["bytes_per_launch"] / (kernel_ms / 1000.0) / 1e9
+                hbm = {"dram_GBps": gbs, "measured_peak_GBps": hbm_peak, "frac": gbs / hbm_peak,
+                       "note": "DRAM bytes of the ncu capture over the kernel's live duration: far from the HBM roof, the "
+                               "kernel is bound by the integer multiply-add pipe"}
+        except (OSError, ValueError, KeyError):
+            pass
         achieved = n * work["imad32_per_item"] / (kernel_ms / 1000.0) / 1e12
         executed = n * work["imad_executed_per_item"] / (kernel_ms / 1000.0) / 1e12
         return {"bound": "int-mad", "kernel": work["kernel"], "achieved": achieved, "peak": peak["timad32_per_s"],
@@ -730,7 +741,7 @@ class Ours:
                 "frac_note": "frac charges the generic CIOS cost (SURVEY.md 8d: 4(2n^2+n) IMAD32 per product) to every "
                              "product and so can exceed 1; frac_executed_imad_wide counts the IMAD.WIDE instructions "
                              "the kernel really issues and is the figure to compare with ncu's fmaheavy pipe utilisation",
-                "traffic": ncu_dram_traffic(self.workload, self.batch_log2, self.eng.comb_window),
+                "traffic": traffic, "hbm": hbm,
                 "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / step_ms,
                 "normalisation_kernel_ms": getattr(self, "_k4_ms", None),
                 "M_impl": work["M_impl"], "imad32_per_field_mul": work["imad32_per_mul"],

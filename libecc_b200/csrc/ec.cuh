@@ -533,7 +533,7 @@ template <class C> ECC_HD void comb_mul(Jac<C> &out, const Fe<C::N> &k, const ui
 }
 
 /* One field inversion for the calling thread alone: the inverter of the host build of the tests and of the one-off
- * table construction.  K2 / K3 pass an inverter that shares ONE Fermat chain among the 128 threads of the CTA
+ * table construction.  K2 / K3 pass an inverter that shares ONE inversion among the 128 threads of the CTA
  * (cta_inverse_128, kernels.cuh); an inverter of that kind must be called by every thread of the CTA. */
 template <class C> struct ThreadInverter {
 	ECC_HD void operator()(Fe<C::N> &r, const Fe<C::N> &a) const { Field<typename C::Fp>::inv(r, a); }
