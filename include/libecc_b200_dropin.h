@@ -132,6 +132,27 @@ int ec_verify(const uint8_t *sig, uint8_t siglen, const eccb200_ec_pub_key *pub_
 int eccb200_dropin_ec_verify(const uint8_t *sig, uint8_t siglen, const eccb200_ec_pub_key *pub_key, const uint8_t *m,
 			     uint32_t mlen, int sig_type, int hash_type, const uint8_t *adata, uint16_t adata_len);
 
+/*
+ * ec_verify_batch and is_verify_batch_mode_supported with the reference's prototypes (src/sig/sig_algs.h:90-93,
+ * src/sig/sig_algs.c:675-694, :937-958; scratch_pad_area is the reference's verify_batch_scratch_pad *, unused here):
+ *     int ec_verify_batch(const u8 **s, const u8 *s_len, const ec_pub_key **pub_keys, const u8 **m, const u32 *m_len,
+ *                         u32 num, ec_alg_type sig_type, hash_alg_type hash_type, const u8 **adata,
+ *                         const u16 *adata_len, verify_batch_scratch_pad *scratch_pad_area, u32 *scratch_pad_area_len);
+ *     int is_verify_batch_mode_supported(ec_alg_type sig_type, int *check);
+ * The seven schemes of the per-scheme adapters below (ECDSA, DECDSA, ECFSDSA, BIP0340, ECSDSA, ECOSDSA, ECKCDSA) are
+ * served by the device - five of them sit at unsupported_verify_batch in the reference (src/sig/sig_algs_internal.h:294);
+ * 0 iff ALL num signatures verify.  Other schemes, unknown curves and batches with ancillary data are forwarded to the
+ * next definition in the process (the reference's own); -1 if there is none.
+ */
+int ec_verify_batch(const uint8_t **s, const uint8_t *s_len, const eccb200_ec_pub_key **pub_keys, const uint8_t **m,
+		    const uint32_t *m_len, uint32_t num, int sig_type, int hash_type, const uint8_t **adata,
+		    const uint16_t *adata_len, void *scratch_pad_area, uint32_t *scratch_pad_area_len);
+int eccb200_dropin_ec_verify_batch(const uint8_t **s, const uint8_t *s_len, const eccb200_ec_pub_key **pub_keys,
+				   const uint8_t **m, const uint32_t *m_len, uint32_t num, int sig_type, int hash_type,
+				   const uint8_t **adata, const uint16_t *adata_len, void *scratch_pad_area,
+				   uint32_t *scratch_pad_area_len);
+int is_verify_batch_mode_supported(int sig_type, int *check);
+
 /* The same under non-clashing names (for callers that link the reference statically and choose per call). */
 int eccb200_dropin_prj_pt_mul(eccb200_prj_pt *out, const eccb200_nn *m, const eccb200_prj_pt *in);
 

@@ -1077,3 +1077,75 @@ extern "C" int ec_verify(const uint8_t *sig, uint8_t siglen, const eccb200_ec_pu
 {
 	return eccb200_dropin_ec_verify(sig, siglen, pub_key, m, mlen, sig_type, hash_type, adata, adata_len);
 }
+
+/*
+ * ec_verify_batch and is_verify_batch_mode_supported with the reference's exact prototypes (sig/sig_algs.h:90-93,
+ * sig/sig_algs.c:675-694 and :937-958).  The reference dispatches through ec_sig_maps[].verify_batch, where ECDSA,
+ * DECDSA, ECSDSA, ECOSDSA and ECKCDSA sit at unsupported_verify_batch (sig/sig_algs_internal.h:294); here those five
+ * and ECFSDSA / BIP0340 are served by the device; every other scheme, an unknown curve or a batch with ancillary data
+ * goes to the next definition in the process (the reference's own), -1 if there is none.
+ */
+typedef int (*ec_verify_batch_sig)(const uint8_t **, const uint8_t *, const eccb200_ec_pub_key **, const uint8_t **,
+				   const uint32_t *, uint32_t, int, int, const uint8_t **, const uint16_t *, void *,
+				   uint32_t *);
+typedef int (*batch_supported_sig)(int, int *);
+
+static bool batch_scheme_served(int sig_type)
+{
+	Scheme sc;
+	return scheme_of(sig_type, &sc) || sig_type == 2 || sig_type == 3 || sig_type == 4;
+}
+
+extern "C" int eccb200_dropin_ec_verify_batch(const uint8_t **s, const uint8_t *s_len,
+					      const eccb200_ec_pub_key **pub_keys, const uint8_t **m,
+					      const uint32_t *m_len, uint32_t num, int sig_type, int hash_type,
+					      const uint8_t **adata, const uint16_t *adata_len, void *scratch_pad_area,
+					      uint32_t *scratch_pad_area_len)
+{
+	bool ours = batch_scheme_served(sig_type) && num > 0 && s && s_len && pub_keys && m && m_len &&
+		    resolve_get_hash() != nullptr;
+	if (ours && adata)
+		for (uint32_t i = 0; i < num && ours; i++) ours = adata[i] == nullptr;
+	if (ours) { /* a curve this layer knows, named by the first well-formed key */
+		const CurveInfo *ci = nullptr;
+		for (uint32_t i = 0; i < num && !ci; i++) {
+			const eccb200_ec_pub_key *pk = pub_keys[i];
+			if (pk && pk->magic == kPubKeyMagic && pk->key_type == sig_type && pt_ok(&pk->y))
+				ci = identify(&pk->y);
+		}
+		const HashMappingHead *hm = nullptr;
+		ours = ci != nullptr && !resolve_get_hash()(hash_type, &hm) && hm && hm->hfunc_scattered;
+	}
+	if (!ours) {
+		static ec_verify_batch_sig next = (ec_verify_batch_sig)next_definition("ec_verify_batch");
+		return next ? next(s, s_len, pub_keys, m, m_len, num, sig_type, hash_type, adata, adata_len,
+				   scratch_pad_area, scratch_pad_area_len)
+			    : -1;
+	}
+	Scheme sc = kEcdsa;
+	if (sig_type == 2) return verify_batch_eckcdsa(s, s_len, pub_keys, m, m_len, num, sig_type, hash_type, adata);
+	if (sig_type == 3 || sig_type == 4)
+		return verify_batch_ecsdsa(sig_type == 4, s, s_len, pub_keys, m, m_len, num, sig_type, hash_type, adata);
+	scheme_of(sig_type, &sc);
+	return verify_batch_common(sc, s, s_len, pub_keys, m, m_len, num, sig_type, hash_type, adata);
+}
+
+extern "C" int ec_verify_batch(const uint8_t **s, const uint8_t *s_len, const eccb200_ec_pub_key **pub_keys,
+			       const uint8_t **m, const uint32_t *m_len, uint32_t num, int sig_type, int hash_type,
+			       const uint8_t **adata, const uint16_t *adata_len, void *scratch_pad_area,
+			       uint32_t *scratch_pad_area_len)
+{
+	return eccb200_dropin_ec_verify_batch(s, s_len, pub_keys, m, m_len, num, sig_type, hash_type, adata, adata_len,
+					      scratch_pad_area, scratch_pad_area_len);
+}
+
+extern "C" int is_verify_batch_mode_supported(int sig_type, int *check)
+{
+	if (!check) return -1;
+	if (batch_scheme_served(sig_type)) {
+		*check = 1;
+		return 0;
+	}
+	static batch_supported_sig next = (batch_supported_sig)next_definition("is_verify_batch_mode_supported");
+	return next ? next(sig_type, check) : -1;
+}

@@ -248,6 +248,26 @@ static int run_direct(const char *dropin_path)
 			/* the generic entry point still reports ECDSA batch as unsupported in the unmodified reference */
 			CHECK(ec_verify_batch(sp, sl, pk, mp, ml, NS, ECDSA, ht, NULL, NULL, NULL, NULL) == -1,
 			      "reference ec_verify_batch(ECDSA) unexpectedly supported");
+			/* ... while the drop-in's ec_verify_batch / is_verify_batch_mode_supported (the reference's prototypes)
+			 * serve it, and forward what the layer does not handle (ECGDSA: unsupported in the reference too) */
+			{
+				vbatch_fn gpu_generic = (vbatch_fn)dlsym(h, "ec_verify_batch");
+				int (*gpu_supported)(ec_alg_type, int *) = (int (*)(ec_alg_type, int *))dlsym(h, "is_verify_batch_mode_supported");
+				int chk = -1, refchk = -1;
+				CHECK(gpu_generic != NULL && gpu_supported != NULL, "missing ec_verify_batch / is_verify_batch_mode_supported");
+				CHECK(gpu_generic(sp, sl, pk, mp, ml, NS, ECDSA, ht, NULL, NULL, NULL, NULL) == -1, "generic batch: corrupted batch accepted");
+				sigs[5][3] ^= 0x20;
+				msgs[9][0] ^= 1;
+				unsigned long long v0 = gpu_vcount();
+				CHECK(gpu_generic(sp, sl, pk, mp, ml, NS, ECDSA, ht, NULL, NULL, NULL, NULL) == 0, "generic batch: valid batch rejected");
+				CHECK(gpu_vcount() == v0 + NS, "generic ec_verify_batch did not run on the GPU");
+				CHECK(gpu_supported(ECDSA, &chk) == 0 && chk == 1, "ECDSA batch mode not reported");
+				CHECK(is_verify_batch_mode_supported(ECDSA, &refchk) == 0 && refchk == 0, "reference reports ECDSA batch mode");
+				CHECK(gpu_supported(ECGDSA, &chk) == 0 && is_verify_batch_mode_supported(ECGDSA, &refchk) == 0 && chk == refchk,
+				      "forwarded is_verify_batch_mode_supported(ECGDSA) differs from the reference");
+				CHECK(gpu_generic(sp, sl, pk, mp, ml, NS, ECGDSA, ht, NULL, NULL, NULL, NULL) ==
+				      ec_verify_batch(sp, sl, pk, mp, ml, NS, ECGDSA, ht, NULL, NULL, NULL, NULL), "forwarded ec_verify_batch(ECGDSA) differs");
+			}
 		}
 		/* ---- ECFSDSA in the same slot: against the reference's ec_verify, item by item */
 		{

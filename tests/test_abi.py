@@ -13,7 +13,7 @@ from common import ROOT
 def declared_symbols(header):
     txt = open(os.path.join(ROOT, "include", header)).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return {m.group(1) for m in re.finditer(r"\b(eccb200_\w+|prj_pt_mul\w*|ec_verify)\s*\(", txt)}
+    return {m.group(1) for m in re.finditer(r"\b(eccb200_\w+|prj_pt_mul\w*|ec_verify\w*|is_verify_batch_mode_supported)\s*\(", txt)}
 
 
 def test_library_exports_every_declared_symbol():
@@ -27,7 +27,8 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/libecc_b200.h but not exported"
     drop = ctypes.CDLL(os.path.join(os.path.dirname(libecc_b200.LIB_PATH), "libecc_b200_dropin.so"))
     decl2 = declared_symbols("libecc_b200_dropin.h")
-    assert {"prj_pt_mul", "prj_pt_mul_blind", "ec_verify", "eccb200_dropin_ecdsa_verify_batch",
+    assert {"prj_pt_mul", "prj_pt_mul_blind", "ec_verify", "ec_verify_batch", "is_verify_batch_mode_supported",
+            "eccb200_dropin_ecdsa_verify_batch",
             "eccb200_dropin_ecfsdsa_verify_batch"} <= decl2
     for name in sorted(decl2):
         assert hasattr(drop, name), f"{name} declared in include/libecc_b200_dropin.h but not exported"
