@@ -239,6 +239,28 @@ int eccb200_ecfsdsa_verify_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t
 				     const uint8_t *d_digests, uint32_t hlen, int8_t *d_verdict, void *stream);
 
 /*
+ * ECFSDSA batch verification in the form the reference's verify_batch slot computes it (_ecfsdsa_verify_batch,
+ * src/sig/ecfsdsa.c:814-1055): ONE random linear combination for the whole batch,
+ *        (sum a_i s_i) G  +  sum a_i (-W_i)  +  sum (-a_i e_i) Y_i  ==  point at infinity,
+ * where the reference feeds its 2n+1 terms to the Bos-Coster heap (src/sig/sig_algs.c:1052) and this library runs them as
+ * a multi-scalar multiplication with the bucket method on the device (K6, libecc_b200/csrc/msm.cuh): ~26 mixed additions
+ * per signature instead of a full double-scalar multiplication.  Inputs as eccb200_ecfsdsa_verify_batch.
+ *   *all_valid = 1 iff every item is well formed (W_i and Y_i on the curve, s_i < q - the checks of the reference's loop,
+ *                :881-921, :941, :983) and the combination vanishes; 0 otherwise (an empty batch: 0, as :740).  Like the
+ *                reference's function this says nothing about WHICH signature is bad - eccb200_ecfsdsa_verify_batch does -
+ *                and a batch holding a forgery passes with probability 2^-128 (the coefficients a_i are 128 bits of a
+ *                ChaCha20 stream keyed by `seed`).
+ *   seed       : 32 bytes the signers cannot predict; NULL draws them from the operating system (getrandom).  A fixed
+ *                seed makes the call reproducible (tests).
+ * Returns 0 when the verification ran (whatever the verdict), -1 on an error (eccb200_last_error).
+ */
+int eccb200_ecfsdsa_verify_msm_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys,
+				     const uint8_t *digests, uint32_t hlen, const uint8_t *seed, int *all_valid);
+int eccb200_ecfsdsa_verify_msm_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_sigs, const uint8_t *d_pubkeys,
+					 const uint8_t *d_digests, uint32_t hlen, const uint8_t *seed, int *all_valid,
+					 void *stream);
+
+/*
  * Batched double-scalar multiplication W_i = a_i*G + b_i*Y_i with affine results: the sequence prj_pt_mul, prj_pt_mul,
  * prj_pt_add, prj_pt_unique that every Schnorr-type verification of the reference runs before it hashes the recomputed
  * point (ECSDSA / ECOSDSA src/sig/ecsdsa_common.c:493-497, ECKCDSA, ...), as ONE kernel launch per batch: comb for G,

@@ -31,6 +31,7 @@ ABI_SYMBOLS = [
     "eccb200_structured_pub_key_import_batch", "eccb200_structured_pub_key_export_batch",
     "eccb200_structured_key_pair_batch", "eccb200_ecdsa_verify_structured_batch", "eccb200_ecdsa_sign_structured_batch",
     "eccb200_ecfsdsa_verify_batch", "eccb200_ecfsdsa_verify_batch_dev",
+    "eccb200_ecfsdsa_verify_msm_batch", "eccb200_ecfsdsa_verify_msm_batch_dev",
     "eccb200_prj_pt_mul_batch_dev_gather", "eccb200_ipc_alloc", "eccb200_ipc_open", "eccb200_ipc_close",
     "eccb200_ipc_free", "eccb200_flag_wait", "eccb200_flag_signal",
     "eccb200_multi_create", "eccb200_multi_destroy", "eccb200_multi_device_count", "eccb200_multi_ctx",
@@ -90,6 +91,10 @@ def load_library() -> ctypes.CDLL:
                                                         u8p, u8p, u32, u8p, i8p]
     lib.eccb200_ecfsdsa_verify_batch.argtypes = [ctypes.c_void_p, u32, u8p, u8p, u8p, u32, i8p]
     lib.eccb200_ecfsdsa_verify_batch_dev.argtypes = [ctypes.c_void_p, u32, u8p, u8p, u8p, u32, i8p, ctypes.c_void_p]
+    lib.eccb200_ecfsdsa_verify_msm_batch.argtypes = [ctypes.c_void_p, u32, u8p, u8p, u8p, u32, u8p,
+                                                     ctypes.POINTER(ctypes.c_int)]
+    lib.eccb200_ecfsdsa_verify_msm_batch_dev.argtypes = [ctypes.c_void_p, u32, u8p, u8p, u8p, u32, u8p,
+                                                         ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
     vp, u64 = ctypes.c_void_p, ctypes.c_uint64
     lib.eccb200_prj_pt_mul_batch_dev_gather.argtypes = [vp, u32, u8p, u8p, u8p, i8p, ctypes.c_int, vp, vp, vp, u32,
                                                         vp, ctypes.c_int, u32, vp]
@@ -361,6 +366,34 @@ class Engine:
         self._check(self.lib.eccb200_ecfsdsa_verify_batch(self._h, n, sg.ctypes.data, pk.ctypes.data, dg.ctypes.data,
                                                           hlen, verdict.ctypes.data), "eccb200_ecfsdsa_verify_batch")
         return verdict
+
+    def ecfsdsa_verify_msm_batch(self, sigs, pubkeys, digests, hlen: int, seed: Optional[bytes] = None) -> bool:
+        """The whole batch as ONE multi-scalar multiplication (the reference's verify_batch form): True iff every
+        signature verifies.  seed: 32 bytes (None: from the OS)."""
+        sg = _as_u8(sigs)
+        n = sg.size // (2 * self.plen + self.qlen)
+        pk = _as_u8(pubkeys, n * 2 * self.plen)
+        dg = _as_u8(digests, n * hlen)
+        ok = ctypes.c_int(0)
+        sd = None
+        if seed is not None:
+            if len(seed) != 32:
+                raise ValueError("seed must be 32 bytes")
+            sd = ctypes.cast(ctypes.create_string_buffer(bytes(seed), 32), ctypes.c_void_p)
+        self._check(self.lib.eccb200_ecfsdsa_verify_msm_batch(self._h, n, sg.ctypes.data, pk.ctypes.data,
+                                                              dg.ctypes.data, hlen, sd, ctypes.byref(ok)),
+                    "eccb200_ecfsdsa_verify_msm_batch")
+        return ok.value == 1
+
+    def ecfsdsa_verify_msm_batch_dev(self, n: int, d_sigs: int, d_pubkeys: int, d_digests: int, hlen: int,
+                                     seed: Optional[bytes] = None, stream: int = 0) -> bool:
+        ok = ctypes.c_int(0)
+        sd = ctypes.cast(ctypes.create_string_buffer(bytes(seed), 32), ctypes.c_void_p) if seed is not None else None
+        self._check(self.lib.eccb200_ecfsdsa_verify_msm_batch_dev(self._h, n, ctypes.c_void_p(d_sigs),
+                                                                  ctypes.c_void_p(d_pubkeys), ctypes.c_void_p(d_digests),
+                                                                  hlen, sd, ctypes.byref(ok), ctypes.c_void_p(stream)),
+                    "eccb200_ecfsdsa_verify_msm_batch_dev")
+        return ok.value == 1
 
     def double_smul_batch(self, ab, pubkeys) -> Tuple[np.ndarray, np.ndarray]:
         """W_i = a_i*G + b_i*Y_i (affine); ab [n][2*qlen] = a || b."""

@@ -4,10 +4,12 @@
  */
 #include "../../include/libecc_b200.h"
 #include "kernels.cuh"
+#include "msm.cuh"
 #include "sha2.cuh"
 #include "wire.cuh"
 
 #include <cuda_runtime.h>
+#include <sys/random.h>
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -76,6 +78,11 @@ struct eccb200_ctx {
 	cudaEvent_t scratch_done = nullptr;
 	bool scratch_used = false;
 	unsigned int *gather_counter = nullptr; /* CTA counter of the fused K4 gather (kernels.cuh GatherDst) */
+	/* K6 (msm.cuh): work buffers of the multi-scalar-multiplication batch verification, grown on demand */
+	MsmBuffers msm = {};
+	uint32_t msm_cap_n = 0, msm_cap_total = 0;
+	uint8_t *msm_in = nullptr; /* device copy of the host-pointer entry point's inputs */
+	size_t msm_in_bytes = 0;
 	/* optional per-kernel timing of the device-pointer API (bench.py's roofline leg) */
 	bool profiling = false;
 	static const int kProfCalls = 64;
@@ -271,6 +278,17 @@ extern "C" int eccb200_ctx_create(eccb200_ctx **out, int curve_id, int device, i
 	return 0;
 }
 
+static void msm_release(eccb200_ctx *ctx)
+{
+	uint32_t *bufs[] = { ctx->msm.pts, ctx->msm.scal, ctx->msm.partial, ctx->msm.count, ctx->msm.offs, ctx->msm.fill,
+			     ctx->msm.list, ctx->msm.buckets, ctx->msm.parts, ctx->msm.winsum };
+	for (uint32_t *b : bufs)
+		if (b) cudaFree(b);
+	if (ctx->msm.flags) cudaFree(ctx->msm.flags);
+	ctx->msm = MsmBuffers{};
+	ctx->msm_cap_n = ctx->msm_cap_total = 0;
+}
+
 extern "C" void eccb200_ctx_destroy(eccb200_ctx *ctx)
 {
 	if (!ctx) return;
@@ -295,6 +313,8 @@ extern "C" void eccb200_ctx_destroy(eccb200_ctx *ctx)
 			for (int i = 0; i < 3; i++) cudaEventDestroy(ctx->ev[c][i]);
 	if (ctx->scratch_done) cudaEventDestroy(ctx->scratch_done);
 	if (ctx->gather_counter) cudaFree(ctx->gather_counter);
+	msm_release(ctx);
+	if (ctx->msm_in) cudaFree(ctx->msm_in);
 	if (ctx->table) cudaFree(ctx->table);
 	if (ctx->jac) cudaFree(ctx->jac);
 	if (ctx->prefix) cudaFree(ctx->prefix);
@@ -1190,6 +1210,145 @@ extern "C" int eccb200_bip0340_verify_batch(eccb200_ctx *ctx, uint32_t n, const 
 		return bip0340_dev(ctx, cnt, d + (size_t)cnt * pk, d, d + (size_t)cnt * (pk + sg), hlen,
 				   (int8_t *)ctx->d_out[s], ctx->streams[s]);
 	});
+}
+
+/* ------------------------------------------------------------------------------------------ K6: batch verification as one MSM */
+
+/* Window width of the bucket method: the c in [2, 16] that minimises (mixed additions of the accumulation) + (additions
+ * and conversions of the bucket reduction), in field products; ECCB200_MSM_WINDOW overrides (tests walk small c). */
+static int msm_pick_window(uint32_t n, int qbits)
+{
+	if (const char *e = getenv("ECCB200_MSM_WINDOW")) {
+		const int c = atoi(e);
+		if (c >= 2 && c <= 16) return c;
+	}
+	int best = 2;
+	double best_cost = 0;
+	for (int c = 2; c <= 16; c++) {
+		const double acc = (double)n * (msm_windows(128, c) + msm_windows(qbits, c)) * 10.0;
+		const double red = (double)msm_windows(qbits, c) * (double)(1u << (c - 1)) * (2 * 16.0 + 2.0);
+		if (c == 2 || acc + red < best_cost) {
+			best = c;
+			best_cost = acc + red;
+		}
+	}
+	return best;
+}
+
+static int msm_ensure(eccb200_ctx *ctx, uint32_t n, int c)
+{
+	const int qbits = (int)ctx->qlen * 8; /* upper bound of bitlen(q): only sizes buffers */
+	const int nwin = msm_windows(qbits, c), nwin_a = msm_windows(128, c);
+	const uint32_t nb = 1u << (c - 1), total = (uint32_t)nwin * nb;
+	if (n <= ctx->msm_cap_n && total <= ctx->msm_cap_total) return 0;
+	const uint32_t cap_n = std::max(n, ctx->msm_cap_n), cap_total = std::max(total, ctx->msm_cap_total);
+	cudaDeviceSynchronize();
+	msm_release(ctx);
+	const size_t N = (size_t)ctx->N, npts = 2 * (size_t)cap_n + 1;
+	/* list: every W_i owns at most nwin_a non-zero digits, every Y_i and the generator at most the full count; sized for
+	 * the narrowest window (most digits) any later call with this capacity may pick */
+	const size_t list_cap = (size_t)cap_n * (size_t)(msm_windows(128, 2) + msm_windows(qbits, 2)) + (size_t)msm_windows(qbits, 2);
+	(void)nwin_a;
+	MsmBuffers &b = ctx->msm;
+	if (cudaMalloc(&b.pts, npts * 2 * N * 4) != cudaSuccess || cudaMalloc(&b.scal, npts * N * 4) != cudaSuccess ||
+	    cudaMalloc(&b.partial, ((size_t)cap_n / 128 + 1) * N * 4) != cudaSuccess ||
+	    cudaMalloc(&b.count, (size_t)cap_total * 4) != cudaSuccess || cudaMalloc(&b.offs, (size_t)cap_total * 4) != cudaSuccess ||
+	    cudaMalloc(&b.fill, (size_t)cap_total * 4) != cudaSuccess || cudaMalloc(&b.list, list_cap * 4) != cudaSuccess ||
+	    cudaMalloc(&b.buckets, (size_t)cap_total * 3 * N * 4) != cudaSuccess ||
+	    cudaMalloc(&b.parts, (size_t)cap_total * 3 * N * 4) != cudaSuccess ||
+	    cudaMalloc(&b.winsum, (size_t)msm_windows(qbits, 2) * 3 * N * 4) != cudaSuccess ||
+	    cudaMalloc(&b.flags, 2 * sizeof(int)) != cudaSuccess) {
+		cudaGetLastError();
+		msm_release(ctx);
+		return fail("out of device memory for the multi-scalar-multiplication buffers");
+	}
+	ctx->msm_cap_n = cap_n;
+	ctx->msm_cap_total = cap_total;
+	return 0;
+}
+
+static int msm_seed(MsmKey &key, const uint8_t *seed)
+{
+	uint8_t buf[32];
+	if (seed) {
+		memcpy(buf, seed, 32);
+	} else {
+		size_t got = 0;
+		while (got < sizeof buf) {
+			const ssize_t r = getrandom(buf + got, sizeof buf - got, 0);
+			if (r <= 0) return fail("getrandom failed: no entropy for the batch coefficients");
+			got += (size_t)r;
+		}
+	}
+	for (int i = 0; i < 8; i++)
+		key.k[i] = (uint32_t)buf[4 * i] | ((uint32_t)buf[4 * i + 1] << 8) | ((uint32_t)buf[4 * i + 2] << 16) |
+			   ((uint32_t)buf[4 * i + 3] << 24);
+	return 0;
+}
+
+static int ecfsdsa_msm_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_sigs, const uint8_t *d_pubkeys,
+			   const uint8_t *d_digests, uint32_t hlen, const uint8_t *seed, int *all_valid, cudaStream_t st)
+{
+	*all_valid = 0;
+	if (n == 0) return 0; /* the reference's implementations reject an empty batch (sig/ecfsdsa.c:740) */
+	if (n > 0x3fffffffu) return fail("batch too large");
+	MsmKey key;
+	if (msm_seed(key, seed)) return -1;
+	int flags[2] = { 0, 0 };
+	int rc = dispatch(ctx->curve_id, [&](auto cv) {
+		typedef decltype(cv) C;
+		const int c = msm_pick_window(n, C::QBITS);
+		if (msm_ensure(ctx, n, c)) return -1;
+		scratch_enter(ctx, st);
+		ctx->launches += (uint64_t)LaunchMsm<C>::ecfsdsa(n, d_sigs, d_pubkeys, d_digests, hlen, key, c, ctx->msm, st);
+		CUDA_OK(cudaGetLastError());
+		CUDA_OK(cudaMemcpyAsync(flags, ctx->msm.flags, sizeof flags, cudaMemcpyDeviceToHost, st));
+		scratch_leave(ctx, st);
+		CUDA_OK(cudaStreamSynchronize(st));
+		return 0;
+	});
+	if (rc) return rc;
+	*all_valid = flags[1] == 1 ? 1 : 0;
+	return 0;
+}
+
+extern "C" int eccb200_ecfsdsa_verify_msm_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_sigs,
+						      const uint8_t *d_pubkeys, const uint8_t *d_digests, uint32_t hlen,
+						      const uint8_t *seed, int *all_valid, void *stream)
+{
+	if (!ctx || !all_valid || (n && (!d_sigs || !d_pubkeys || !d_digests))) return fail("null argument");
+	if (hlen == 0 || hlen > 128) return fail("bad digest length");
+	if (misaligned16(ctx, { d_sigs, d_pubkeys })) return fail(kAlignMsg);
+	CUDA_OK(cudaSetDevice(ctx->device));
+	return ecfsdsa_msm_dev(ctx, n, d_sigs, d_pubkeys, d_digests, hlen, seed, all_valid, (cudaStream_t)stream);
+}
+
+static inline size_t msm_align16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+extern "C" int eccb200_ecfsdsa_verify_msm_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *sigs,
+						  const uint8_t *pubkeys, const uint8_t *digests, uint32_t hlen,
+						  const uint8_t *seed, int *all_valid)
+{
+	if (!ctx || !all_valid || (n && (!sigs || !pubkeys || !digests))) return fail("null argument");
+	if (hlen == 0 || hlen > 128) return fail("bad digest length");
+	*all_valid = 0;
+	if (n == 0) return 0;
+	CUDA_OK(cudaSetDevice(ctx->device));
+	const size_t pk = 2 * (size_t)ctx->plen, sg = pk + (size_t)ctx->qlen;
+	const size_t b_sg = msm_align16((size_t)n * sg), b_pk = msm_align16((size_t)n * pk), b_dg = msm_align16((size_t)n * hlen);
+	if (ctx->msm_in_bytes < b_sg + b_pk + b_dg) {
+		if (ctx->msm_in) cudaFree(ctx->msm_in);
+		ctx->msm_in = nullptr;
+		ctx->msm_in_bytes = 0;
+		CUDA_OK(cudaMalloc(&ctx->msm_in, b_sg + b_pk + b_dg));
+		ctx->msm_in_bytes = b_sg + b_pk + b_dg;
+	}
+	cudaStream_t st = ctx->streams[0];
+	uint8_t *d = ctx->msm_in;
+	CUDA_OK(cudaMemcpyAsync(d, sigs, (size_t)n * sg, cudaMemcpyHostToDevice, st));
+	CUDA_OK(cudaMemcpyAsync(d + b_sg, pubkeys, (size_t)n * pk, cudaMemcpyHostToDevice, st));
+	CUDA_OK(cudaMemcpyAsync(d + b_sg + b_pk, digests, (size_t)n * hlen, cudaMemcpyHostToDevice, st));
+	return ecfsdsa_msm_dev(ctx, n, d, d + b_sg, d + b_sg + b_pk, hlen, seed, all_valid, st);
 }
 
 /* ------------------------------------------------------------------------------------------ sign / ECC-CDH (§8f) */

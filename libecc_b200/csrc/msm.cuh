@@ -1,0 +1,292 @@
+/*
+ * msm.cuh — K6: Schnorr-type batch verification as one multi-scalar multiplication on the device (the
+ * reference: _ecfsdsa_verify_batch sig/ecfsdsa.c:814-1055 with ec_verify_bos_coster sig/sig_algs.c:1052).
+ *
+ * Stages (all on one stream, nothing returns to the host in between):
+ *   prepare     one thread per signature: parse / validate like the reference's loop body, derive the coefficient a_i,
+ *               write the points -W_i and Y_i (affine, Montgomery words) with their scalars a_i and a_i e_i mod q, and
+ *               reduce a_i s_i mod q over the CTA                                       (k_msm_prepare, k_msm_ssum)
+ *   sort        counting sort of (point, window) pairs by bucket: histogram with atomics, one-CTA exclusive scan,
+ *               scatter with atomics                                         (k_msm_hist, k_msm_scan, k_msm_scatter)
+ *   accumulate  one thread per bucket: a chain of XYZZ mixed additions (madd-2008-s, 8M + 2S — the addition of the
+ *               fixed-base comb) over the bucket's points; this is where the time goes        (k_msm_accumulate)
+ *   reduce      running sums over ranges of 16 buckets, a tree per window, Horner over the windows on one thread
+ *                                                             (k_msm_reduce, k_msm_window_sum, k_msm_final)
+ *
+ * HBM layout: pts [2n+1][2N] words, scal [2n+1][N] words, list [<= n (nwin_a + nwin) + nwin] u32 (bit 31 = negate),
+ * count / offs / fill [nwin 2^(c-1)] u32, buckets [nwin 2^(c-1)][3N] words, parts [nwin 2^(c-1) / 16][3N], winsum [nwin][3N].
+ * Integer work on the multiplier pipe (one accumulate thread issues the same instruction stream as K1's loop body);
+ * DRAM traffic is ~26 random 64-byte point reads per signature, far from the HBM roof.
+ */
+#pragma once
+#include "kernels.cuh"
+#include "msm_core.cuh"
+
+namespace eccb200 {
+
+struct MsmBuffers {
+	uint32_t *pts, *scal, *partial, *count, *offs, *fill, *list, *buckets, *parts, *winsum;
+	int *flags; /* [0] = a malformed item was seen, [1] = the verdict (1 = the batch verifies) */
+};
+
+/* ECFSDSA: sigs [n][2 PLEN + QLEN], pubkeys [n][2 PLEN] affine, digests [n][hlen] = H(W_x || W_y || m) */
+template <class C>
+__global__ void __launch_bounds__(128) k_msm_prepare(uint32_t n, const uint8_t *__restrict__ sigs,
+						     const uint8_t *__restrict__ pubkeys,
+						     const uint8_t *__restrict__ digests, uint32_t hlen, MsmKey key,
+						     uint32_t *__restrict__ pts, uint32_t *__restrict__ scal,
+						     uint32_t *__restrict__ partial, int *__restrict__ flags)
+{
+	typedef Field<typename C::Fq> Fq;
+	constexpr int N = C::N;
+	__shared__ __align__(16) uint32_t sh[128 * N];
+	const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+	Fe<N> t;
+	Fq::set_zero(t);
+	if (idx < n) {
+		const uint8_t *sg = sigs + (size_t)idx * (2 * C::PLEN + C::QLEN);
+		Aff<C> W, Y, negW;
+		Fe<N> s, h, a, cY;
+		const bool w_ok = load_affine_checked<C>(W, sg);                          /* (sig/ecfsdsa.c:983) */
+		load_wire<N, C::QLEN>(s, sg + 2 * C::PLEN);
+		const bool s_ok = !Fq::geq_mod(s);                                       /* s < q (:919-921) */
+		const bool key_ok = load_affine_checked<C>(Y, pubkeys + (size_t)idx * (2 * C::PLEN)); /* (:941-942) */
+		digest_full_mod_q<C>(h, digests + (size_t)idx * hlen, hlen);             /* (:953-961) */
+		Fq::neg(h, h);                                                           /* (:962) */
+		msm_coefficient<N>(a, key, idx);
+		msm_terms<C>(negW, cY, t, W, s, h, a);
+		if (!(w_ok && s_ok && key_ok)) {
+			/* the reference returns -1 for the whole batch; the item still owns its slots: zero scalars */
+			atomicOr(flags, 1);
+			Fq::set_zero(a);
+			Fq::set_zero(cY);
+			Fq::set_zero(t);
+		}
+		msm_st<N>(pts + (size_t)idx * (2 * N), negW.x);
+		msm_st<N>(pts + (size_t)idx * (2 * N) + N, negW.y);
+		msm_st<N>(scal + (size_t)idx * N, a);
+		msm_st<N>(pts + ((size_t)n + idx) * (2 * N), Y.x);
+		msm_st<N>(pts + ((size_t)n + idx) * (2 * N) + N, Y.y);
+		msm_st<N>(scal + ((size_t)n + idx) * N, cY);
+	}
+	/* sum of a_i s_i mod q over the CTA */
+#pragma unroll
+	for (int j = 0; j < N; j++) sh[threadIdx.x * N + j] = t.w[j];
+	for (int step = 64; step > 0; step >>= 1) {
+		__syncthreads();
+		if ((int)threadIdx.x < step) {
+			Fe<N> o;
+#pragma unroll
+			for (int j = 0; j < N; j++) o.w[j] = sh[(threadIdx.x + step) * N + j];
+			Fq::add(t, t, o);
+#pragma unroll
+			for (int j = 0; j < N; j++) sh[threadIdx.x * N + j] = t.w[j];
+		}
+	}
+	if (threadIdx.x == 0) {
+#pragma unroll
+		for (int j = 0; j < N; j++) partial[(size_t)blockIdx.x * N + j] = t.w[j];
+	}
+}
+
+/* the generator's term: point 2n = G with the scalar sum a_i s_i mod q (one CTA) */
+template <class C>
+__global__ void __launch_bounds__(128) k_msm_ssum(uint32_t nparts, const uint32_t *__restrict__ partial, uint32_t n,
+						  uint32_t *__restrict__ pts, uint32_t *__restrict__ scal)
+{
+	typedef Field<typename C::Fq> Fq;
+	constexpr int N = C::N;
+	__shared__ __align__(16) uint32_t sh[128 * N];
+	Fe<N> t, o;
+	Fq::set_zero(t);
+	for (uint32_t i = threadIdx.x; i < nparts; i += blockDim.x) {
+#pragma unroll
+		for (int j = 0; j < N; j++) o.w[j] = partial[(size_t)i * N + j];
+		Fq::add(t, t, o);
+	}
+#pragma unroll
+	for (int j = 0; j < N; j++) sh[threadIdx.x * N + j] = t.w[j];
+	for (int step = 64; step > 0; step >>= 1) {
+		__syncthreads();
+		if ((int)threadIdx.x < step) {
+#pragma unroll
+			for (int j = 0; j < N; j++) o.w[j] = sh[(threadIdx.x + step) * N + j];
+			Fq::add(t, t, o);
+#pragma unroll
+			for (int j = 0; j < N; j++) sh[threadIdx.x * N + j] = t.w[j];
+		}
+	}
+	if (threadIdx.x == 0) {
+		Fe<N> gx, gy;
+#pragma unroll
+		for (int j = 0; j < N; j++) {
+			gx.w[j] = C::GX_MONT(j);
+			gy.w[j] = C::GY_MONT(j);
+		}
+		msm_st<N>(pts + (size_t)2 * n * (2 * N), gx);
+		msm_st<N>(pts + (size_t)2 * n * (2 * N) + N, gy);
+		msm_st<N>(scal + (size_t)2 * n * N, t);
+	}
+}
+
+template <class C>
+__global__ void __launch_bounds__(256) k_msm_hist(uint32_t npts, const uint32_t *__restrict__ scal, int c, int nwin,
+						  uint32_t *__restrict__ count)
+{
+	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= npts) return;
+	const uint32_t nb = 1u << (c - 1);
+	msm_digits(scal + (size_t)j * C::N, C::N, c, nwin, [&](int w, int d) {
+		atomicAdd(count + (size_t)w * nb + (uint32_t)((d < 0 ? -d : d) - 1), 1u);
+	});
+}
+
+/* exclusive prefix sum of count[0 .. total) by one CTA of 1024 threads (total = nwin * 2^(c-1) <= 2^20) */
+template <class C>
+__global__ void __launch_bounds__(1024) k_msm_scan(uint32_t total, const uint32_t *__restrict__ count,
+						   uint32_t *__restrict__ offs)
+{
+	__shared__ uint32_t sh[1024];
+	const uint32_t chunk = (total + 1023u) / 1024u, lo = threadIdx.x * chunk,
+		       hi = lo + chunk < total ? lo + chunk : total;
+	uint32_t sum = 0;
+	for (uint32_t i = lo; i < hi; i++) sum += count[i];
+	sh[threadIdx.x] = sum;
+	__syncthreads();
+	for (int step = 1; step < 1024; step <<= 1) { /* inclusive scan of the chunk sums */
+		const uint32_t v = (int)threadIdx.x >= step ? sh[threadIdx.x - step] : 0u;
+		__syncthreads();
+		sh[threadIdx.x] += v;
+		__syncthreads();
+	}
+	uint32_t run = sh[threadIdx.x] - sum;
+	for (uint32_t i = lo; i < hi; i++) {
+		offs[i] = run;
+		run += count[i];
+	}
+}
+
+template <class C>
+__global__ void __launch_bounds__(256) k_msm_scatter(uint32_t npts, const uint32_t *__restrict__ scal, int c, int nwin,
+						     const uint32_t *__restrict__ offs, uint32_t *__restrict__ fill,
+						     uint32_t *__restrict__ list)
+{
+	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= npts) return;
+	const uint32_t nb = 1u << (c - 1);
+	msm_digits(scal + (size_t)j * C::N, C::N, c, nwin, [&](int w, int d) {
+		const size_t g = (size_t)w * nb + (uint32_t)((d < 0 ? -d : d) - 1);
+		const uint32_t pos = offs[g] + atomicAdd(fill + g, 1u);
+		list[pos] = j | (d < 0 ? 0x80000000u : 0u);
+	});
+}
+
+/* one bucket per thread: the sum of its points, written as a Jacobian point (Z = 0: empty / cancelled bucket) */
+template <class C>
+__global__ void __launch_bounds__(128) k_msm_accumulate(uint32_t nbuckets, const uint32_t *__restrict__ offs,
+							const uint32_t *__restrict__ count,
+							const uint32_t *__restrict__ list,
+							const uint32_t *__restrict__ pts, uint32_t *__restrict__ buckets)
+{
+	typedef Field<typename C::Fp> F;
+	typedef EC<C> G;
+	constexpr int N = C::N;
+	const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= nbuckets) return;
+	const uint32_t o = offs[g], cnt = count[g];
+	typename G::XZ acc;
+	G::xz_set_inf(acc);
+	for (uint32_t k = 0; k < cnt; k++) {
+		const uint32_t e = list[o + k];
+		const uint32_t *pp = pts + (size_t)(e & 0x7fffffffu) * (2 * N);
+		Aff<C> P;
+		msm_ld<N>(P.x, pp);
+		msm_ld<N>(P.y, pp + N);
+		if (e >> 31) F::neg(P.y, P.y);
+		G::xz_add_mixed(acc, acc, P);
+	}
+	Jac<C> r;
+	G::xz_to_jac(r, acc);
+	msm_st_jac<C>(buckets, g, r);
+}
+
+template <class C>
+__global__ void __launch_bounds__(128) k_msm_reduce(uint32_t nparts, uint32_t per_window, uint32_t nb, uint32_t ch,
+						    const uint32_t *__restrict__ buckets, uint32_t *__restrict__ parts)
+{
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= nparts) return;
+	const uint32_t w = t / per_window, lo = (t % per_window) * ch;
+	Jac<C> r;
+	msm_reduce_range<C>(r, buckets, (size_t)w * nb, lo, ch);
+	msm_st_jac<C>(parts, t, r);
+}
+
+/* one CTA per window: the sum of its per_window partial results */
+template <class C>
+__global__ void __launch_bounds__(128) k_msm_window_sum(uint32_t per_window, const uint32_t *__restrict__ parts,
+							uint32_t *__restrict__ winsum)
+{
+	typedef EC<C> G;
+	constexpr int N = C::N;
+	__shared__ __align__(16) uint32_t sh[128 * 3 * N];
+	Jac<C> acc, o;
+	G::set_inf(acc);
+	for (uint32_t i = threadIdx.x; i < per_window; i += blockDim.x) {
+		msm_ld_jac<C>(o, parts, (size_t)blockIdx.x * per_window + i);
+		G::add_full(acc, acc, o);
+	}
+	msm_st_jac<C>(sh, threadIdx.x, acc);
+	for (int step = 64; step > 0; step >>= 1) {
+		__syncthreads();
+		if ((int)threadIdx.x < step) {
+			msm_ld_jac<C>(o, sh, threadIdx.x + step);
+			G::add_full(acc, acc, o);
+			msm_st_jac<C>(sh, threadIdx.x, acc);
+		}
+	}
+	if (threadIdx.x == 0) msm_st_jac<C>(winsum, blockIdx.x, acc);
+}
+
+/* Horner over the windows, then the verdict: the sum is the point at infinity and no item was malformed */
+template <class C>
+__global__ void k_msm_final(int nwin, int c, const uint32_t *__restrict__ winsum, int *__restrict__ flags)
+{
+	if (blockIdx.x || threadIdx.x) return;
+	Jac<C> acc;
+	msm_horner<C>(acc, winsum, nwin, c);
+	flags[1] = (EC<C>::is_inf(acc) && flags[0] == 0) ? 1 : 0;
+}
+
+template <class C> struct LaunchMsm {
+	/* enqueues the whole verification of n ECFSDSA signatures; flags[1] holds the verdict when the stream drains.
+	 * Returns the number of kernels launched. */
+	static int ecfsdsa(uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys, const uint8_t *digests, uint32_t hlen,
+			   const MsmKey &key, int c, const MsmBuffers &b, cudaStream_t st);
+};
+
+#if defined(ECC_TU_MSM)
+template <class C>
+int LaunchMsm<C>::ecfsdsa(uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys, const uint8_t *digests, uint32_t hlen,
+			  const MsmKey &key, int c, const MsmBuffers &b, cudaStream_t st)
+{
+	const int nwin = msm_windows(C::QBITS, c);
+	const uint32_t nb = 1u << (c - 1), total = (uint32_t)nwin * nb, ch = nb < 16u ? nb : 16u, per_window = nb / ch,
+		       nparts = (uint32_t)nwin * per_window, npts = 2 * n + 1, nblk = (n + 127) / 128;
+	cudaMemsetAsync(b.count, 0, (size_t)total * 4, st);
+	cudaMemsetAsync(b.fill, 0, (size_t)total * 4, st);
+	cudaMemsetAsync(b.flags, 0, 2 * sizeof(int), st);
+	k_msm_prepare<C><<<nblk, 128, 0, st>>>(n, sigs, pubkeys, digests, hlen, key, b.pts, b.scal, b.partial, b.flags);
+	k_msm_ssum<C><<<1, 128, 0, st>>>(nblk, b.partial, n, b.pts, b.scal);
+	k_msm_hist<C><<<(npts + 255) / 256, 256, 0, st>>>(npts, b.scal, c, nwin, b.count);
+	k_msm_scan<C><<<1, 1024, 0, st>>>(total, b.count, b.offs);
+	k_msm_scatter<C><<<(npts + 255) / 256, 256, 0, st>>>(npts, b.scal, c, nwin, b.offs, b.fill, b.list);
+	k_msm_accumulate<C><<<(total + 127) / 128, 128, 0, st>>>(total, b.offs, b.count, b.list, b.pts, b.buckets);
+	k_msm_reduce<C><<<(nparts + 127) / 128, 128, 0, st>>>(nparts, per_window, nb, ch, b.buckets, b.parts);
+	k_msm_window_sum<C><<<nwin, 128, 0, st>>>(per_window, b.parts, b.winsum);
+	k_msm_final<C><<<1, 32, 0, st>>>(nwin, c, b.winsum, b.flags);
+	return 9;
+}
+#endif
+
+} // namespace eccb200

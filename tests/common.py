@@ -88,7 +88,7 @@ def hostsim_lib() -> ctypes.CDLL:
     if "hostsim" not in _cache:
         src = os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")
         deps = [src] + [os.path.join(ROOT, "libecc_b200", "csrc", f) for f in
-                        ("fp.cuh", "ec.cuh", "curve_constants.inc", "sha3.cuh", "sha3_constants.inc")]
+                        ("fp.cuh", "ec.cuh", "msm_core.cuh", "curve_constants.inc", "sha3.cuh", "sha3_constants.inc")]
         if not os.path.exists(HOSTSIM_SO) or os.path.getmtime(HOSTSIM_SO) < max(os.path.getmtime(d) for d in deps):
             os.makedirs(os.path.dirname(HOSTSIM_SO), exist_ok=True)
             subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", src, "-o", HOSTSIM_SO],

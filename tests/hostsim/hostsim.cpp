@@ -11,6 +11,7 @@
  */
 #define ECC_COUNT_MULS
 #include "../../libecc_b200/csrc/ec.cuh"
+#include "../../libecc_b200/csrc/msm_core.cuh"
 #include "../../libecc_b200/csrc/sha3.cuh"
 #include <cstring>
 #include <vector>
@@ -384,6 +385,142 @@ int hostsim_point_op(int curve_id, int which, const uint8_t *p1, const uint8_t *
 		*status = (int8_t)jac_to_wire<C>(R, out);
 		return 0;
 	});
+}
+
+/*
+ * ECFSDSA batch verification as one multi-scalar multiplication: the stages of libecc_b200/csrc/msm.cuh run serially
+ * with the same building blocks (msm_core.cuh) — prepare, counting sort by bucket, bucket accumulation with the XYZZ
+ * mixed addition, range reduction, per-window sums, Horner.  all_valid like eccb200_ecfsdsa_verify_msm_batch.
+ * stats (optional, 4 entries): mixed additions of the accumulation, buckets, windows, field products in total.
+ */
+int hostsim_ecfsdsa_msm(int curve_id, int c, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys, const uint8_t *digests,
+			uint32_t hlen, const uint8_t *seed, int *all_valid, unsigned long long *stats)
+{
+	return dispatch(curve_id, [&](auto cv) {
+		typedef decltype(cv) C;
+		typedef Field<typename C::Fp> F;
+		typedef Field<typename C::Fq> Fq;
+		typedef EC<C> G;
+		constexpr int N = C::N;
+		*all_valid = 0;
+		if (n == 0 || c < 2 || c > 16) return n == 0 ? 0 : -1;
+		g_fe_mul_count = 0;
+		MsmKey key;
+		for (int i = 0; i < 8; i++)
+			key.k[i] = (uint32_t)seed[4 * i] | ((uint32_t)seed[4 * i + 1] << 8) | ((uint32_t)seed[4 * i + 2] << 16) |
+				   ((uint32_t)seed[4 * i + 3] << 24);
+		const int nwin = msm_windows(C::QBITS, c);
+		const uint32_t nb = 1u << (c - 1), total = (uint32_t)nwin * nb, ch = nb < 16u ? nb : 16u, per_window = nb / ch;
+		const size_t npts = 2 * (size_t)n + 1;
+		std::vector<uint32_t> pts(npts * 2 * N), scal(npts * N);
+		bool bad = false;
+		Fe<N> ssum;
+		Fq::set_zero(ssum);
+		/* prepare (k_msm_prepare / k_msm_ssum) */
+		for (uint32_t i = 0; i < n; i++) {
+			const uint8_t *sg = sigs + (size_t)i * (2 * C::PLEN + C::QLEN);
+			Aff<C> W, Y, negW;
+			Fe<N> s, h, a, cY, t;
+			const bool w_ok = load_point<C>(W, sg);
+			load_be<N>(s, sg + 2 * C::PLEN, C::QLEN);
+			const bool s_ok = !Fq::geq_mod(s);
+			const bool key_ok = load_point<C>(Y, pubkeys + (size_t)i * 2 * C::PLEN);
+			digest_full_mod_q<C>(h, digests + (size_t)i * hlen, hlen);
+			Fq::neg(h, h);
+			msm_coefficient<N>(a, key, i);
+			msm_terms<C>(negW, cY, t, W, s, h, a);
+			if (!(w_ok && s_ok && key_ok)) {
+				bad = true;
+				Fq::set_zero(a);
+				Fq::set_zero(cY);
+				Fq::set_zero(t);
+			}
+			msm_st<N>(&pts[(size_t)i * 2 * N], negW.x);
+			msm_st<N>(&pts[(size_t)i * 2 * N + N], negW.y);
+			msm_st<N>(&scal[(size_t)i * N], a);
+			msm_st<N>(&pts[((size_t)n + i) * 2 * N], Y.x);
+			msm_st<N>(&pts[((size_t)n + i) * 2 * N + N], Y.y);
+			msm_st<N>(&scal[((size_t)n + i) * N], cY);
+			Fq::add(ssum, ssum, t);
+		}
+		for (int j = 0; j < N; j++) {
+			pts[(size_t)2 * n * 2 * N + j] = C::GX_MONT(j);
+			pts[(size_t)2 * n * 2 * N + N + j] = C::GY_MONT(j);
+		}
+		msm_st<N>(&scal[(size_t)2 * n * N], ssum);
+		/* counting sort (k_msm_hist / k_msm_scan / k_msm_scatter) */
+		std::vector<uint32_t> count(total, 0), offs(total, 0), fill(total, 0);
+		for (size_t j = 0; j < npts; j++)
+			msm_digits(&scal[j * N], N, c, nwin, [&](int w, int d) { count[(size_t)w * nb + (uint32_t)((d < 0 ? -d : d) - 1)]++; });
+		uint32_t run = 0;
+		for (uint32_t g = 0; g < total; g++) {
+			offs[g] = run;
+			run += count[g];
+		}
+		std::vector<uint32_t> list(run ? run : 1);
+		for (size_t j = 0; j < npts; j++)
+			msm_digits(&scal[j * N], N, c, nwin, [&](int w, int d) {
+				const size_t g = (size_t)w * nb + (uint32_t)((d < 0 ? -d : d) - 1);
+				list[offs[g] + fill[g]++] = (uint32_t)j | (d < 0 ? 0x80000000u : 0u);
+			});
+		/* accumulate (k_msm_accumulate) */
+		std::vector<uint32_t> buckets((size_t)total * 3 * N);
+		for (uint32_t g = 0; g < total; g++) {
+			typename G::XZ acc;
+			G::xz_set_inf(acc);
+			for (uint32_t k = 0; k < count[g]; k++) {
+				const uint32_t e = list[offs[g] + k];
+				const uint32_t *pp = &pts[(size_t)(e & 0x7fffffffu) * 2 * N];
+				Aff<C> P;
+				msm_ld<N>(P.x, pp);
+				msm_ld<N>(P.y, pp + N);
+				if (e >> 31) F::neg(P.y, P.y);
+				G::xz_add_mixed(acc, acc, P);
+			}
+			Jac<C> r;
+			G::xz_to_jac(r, acc);
+			msm_st_jac<C>(buckets.data(), g, r);
+		}
+		/* reduce (k_msm_reduce / k_msm_window_sum / k_msm_final) */
+		std::vector<uint32_t> winsum((size_t)nwin * 3 * N);
+		for (int w = 0; w < nwin; w++) {
+			Jac<C> acc, part;
+			G::set_inf(acc);
+			for (uint32_t t = 0; t < per_window; t++) {
+				msm_reduce_range<C>(part, buckets.data(), (size_t)w * nb, t * ch, ch);
+				G::add_full(acc, acc, part);
+			}
+			msm_st_jac<C>(winsum.data(), (size_t)w, acc);
+		}
+		Jac<C> sum;
+		msm_horner<C>(sum, winsum.data(), nwin, c);
+		*all_valid = (G::is_inf(sum) && !bad) ? 1 : 0;
+		if (stats) {
+			stats[0] = run;
+			stats[1] = total;
+			stats[2] = (unsigned long long)nwin;
+			stats[3] = g_fe_mul_count;
+		}
+		return 0;
+	});
+}
+
+/* signed digits of a scalar (little-endian 32-bit words), for the recoding test: digits[w] for w < nwin; returns nwin */
+int hostsim_msm_digits(const uint32_t *k, int nwords, int bits, int c, int *digits)
+{
+	const int nwin = msm_windows(bits, c);
+	for (int w = 0; w < nwin; w++) digits[w] = 0;
+	msm_digits(k, nwords, c, nwin, [&](int w, int d) { digits[w] = d; });
+	return nwin;
+}
+
+void hostsim_msm_coefficient(const uint8_t *seed, uint64_t i, uint32_t out[4])
+{
+	MsmKey key;
+	for (int j = 0; j < 8; j++)
+		key.k[j] = (uint32_t)seed[4 * j] | ((uint32_t)seed[4 * j + 1] << 8) | ((uint32_t)seed[4 * j + 2] << 16) |
+			   ((uint32_t)seed[4 * j + 3] << 24);
+	msm_chacha20_block4(out, key, i);
 }
 
 unsigned long long hostsim_last_mul_count(void) { return g_fe_mul_count; }
