@@ -1222,14 +1222,19 @@ static int msm_pick_window(uint32_t n, int qbits)
 		const int c = atoi(e);
 		if (c >= 2 && c <= 16) return c;
 	}
+	/* time ~ max(total work / threads in flight, the longest chain one thread adds up): the chain is the expected load
+	 * of a bucket of the top window, which holds only t = (qbits - 1) mod c bits (msm_core.cuh) */
 	int best = 2;
 	double best_cost = 0;
 	for (int c = 2; c <= 16; c++) {
-		const double acc = (double)n * (msm_windows(128, c) + msm_windows(qbits, c)) * 10.0;
-		const double red = (double)msm_windows(qbits, c) * (double)(1u << (c - 1)) * (2 * 16.0 + 2.0);
-		if (c == 2 || acc + red < best_cost) {
+		const int nw = msm_windows(qbits - 1, c), nwa = msm_windows(msm_coefficient_bits(c), c), t = (qbits - 1) % c;
+		const double acc = (double)n * (nwa + nw) * 10.0;
+		const double red = (double)nw * (double)(1u << (c - 1)) * (2 * 16.0 + 2.0);
+		const double chain = (double)n / (double)(1u << t) * 10.0;
+		const double cost = std::max((acc + red) / 65536.0, chain);
+		if (c == 2 || cost < best_cost) {
 			best = c;
-			best_cost = acc + red;
+			best_cost = cost;
 		}
 	}
 	return best;
@@ -1238,7 +1243,7 @@ static int msm_pick_window(uint32_t n, int qbits)
 static int msm_ensure(eccb200_ctx *ctx, uint32_t n, int c)
 {
 	const int qbits = (int)ctx->qlen * 8; /* upper bound of bitlen(q): only sizes buffers */
-	const int nwin = msm_windows(qbits, c), nwin_a = msm_windows(128, c);
+	const int nwin = msm_windows(qbits - 1, c);
 	const uint32_t nb = 1u << (c - 1), total = (uint32_t)nwin * nb;
 	if (n <= ctx->msm_cap_n && total <= ctx->msm_cap_total) return 0;
 	const uint32_t cap_n = std::max(n, ctx->msm_cap_n), cap_total = std::max(total, ctx->msm_cap_total);
@@ -1247,8 +1252,8 @@ static int msm_ensure(eccb200_ctx *ctx, uint32_t n, int c)
 	const size_t N = (size_t)ctx->N, npts = 2 * (size_t)cap_n + 1;
 	/* list: every W_i owns at most nwin_a non-zero digits, every Y_i and the generator at most the full count; sized for
 	 * the narrowest window (most digits) any later call with this capacity may pick */
-	const size_t list_cap = (size_t)cap_n * (size_t)(msm_windows(128, 2) + msm_windows(qbits, 2)) + (size_t)msm_windows(qbits, 2);
-	(void)nwin_a;
+	const size_t list_cap = (size_t)cap_n * (size_t)(msm_windows(msm_coefficient_bits(2), 2) + msm_windows(qbits - 1, 2)) +
+				(size_t)msm_windows(qbits - 1, 2);
 	MsmBuffers &b = ctx->msm;
 	if (cudaMalloc(&b.pts, npts * 2 * N * 4) != cudaSuccess || cudaMalloc(&b.scal, npts * N * 4) != cudaSuccess ||
 	    cudaMalloc(&b.partial, ((size_t)cap_n / 128 + 1) * N * 4) != cudaSuccess ||
@@ -1256,7 +1261,7 @@ static int msm_ensure(eccb200_ctx *ctx, uint32_t n, int c)
 	    cudaMalloc(&b.fill, (size_t)cap_total * 4) != cudaSuccess || cudaMalloc(&b.list, list_cap * 4) != cudaSuccess ||
 	    cudaMalloc(&b.buckets, (size_t)cap_total * 3 * N * 4) != cudaSuccess ||
 	    cudaMalloc(&b.parts, (size_t)cap_total * 3 * N * 4) != cudaSuccess ||
-	    cudaMalloc(&b.winsum, (size_t)msm_windows(qbits, 2) * 3 * N * 4) != cudaSuccess ||
+	    cudaMalloc(&b.winsum, (size_t)msm_windows(qbits - 1, 2) * 3 * N * 4) != cudaSuccess ||
 	    cudaMalloc(&b.flags, 2 * sizeof(int)) != cudaSuccess) {
 		cudaGetLastError();
 		msm_release(ctx);

@@ -34,7 +34,7 @@ template <class C>
 __global__ void __launch_bounds__(128) k_msm_prepare(uint32_t n, const uint8_t *__restrict__ sigs,
 						     const uint8_t *__restrict__ pubkeys,
 						     const uint8_t *__restrict__ digests, uint32_t hlen, MsmKey key,
-						     uint32_t *__restrict__ pts, uint32_t *__restrict__ scal,
+						     int c, uint32_t *__restrict__ pts, uint32_t *__restrict__ scal,
 						     uint32_t *__restrict__ partial, int *__restrict__ flags)
 {
 	typedef Field<typename C::Fq> Fq;
@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(128) k_msm_prepare(uint32_t n, const uint8_t *
 	Fq::set_zero(t);
 	if (idx < n) {
 		const uint8_t *sg = sigs + (size_t)idx * (2 * C::PLEN + C::QLEN);
-		Aff<C> W, Y, negW;
+		Aff<C> W, Y, negW, Yf;
 		Fe<N> s, h, a, cY;
 		const bool w_ok = load_affine_checked<C>(W, sg);                          /* (sig/ecfsdsa.c:983) */
 		load_wire<N, C::QLEN>(s, sg + 2 * C::PLEN);
@@ -53,8 +53,8 @@ __global__ void __launch_bounds__(128) k_msm_prepare(uint32_t n, const uint8_t *
 		const bool key_ok = load_affine_checked<C>(Y, pubkeys + (size_t)idx * (2 * C::PLEN)); /* (:941-942) */
 		digest_full_mod_q<C>(h, digests + (size_t)idx * hlen, hlen);             /* (:953-961) */
 		Fq::neg(h, h);                                                           /* (:962) */
-		msm_coefficient<N>(a, key, idx);
-		msm_terms<C>(negW, cY, t, W, s, h, a);
+		msm_coefficient<N>(a, key, idx, c);
+		msm_terms<C>(negW, Yf, cY, t, W, Y, s, h, a);
 		if (!(w_ok && s_ok && key_ok)) {
 			/* the reference returns -1 for the whole batch; the item still owns its slots: zero scalars */
 			atomicOr(flags, 1);
@@ -65,8 +65,8 @@ __global__ void __launch_bounds__(128) k_msm_prepare(uint32_t n, const uint8_t *
 		msm_st<N>(pts + (size_t)idx * (2 * N), negW.x);
 		msm_st<N>(pts + (size_t)idx * (2 * N) + N, negW.y);
 		msm_st<N>(scal + (size_t)idx * N, a);
-		msm_st<N>(pts + ((size_t)n + idx) * (2 * N), Y.x);
-		msm_st<N>(pts + ((size_t)n + idx) * (2 * N) + N, Y.y);
+		msm_st<N>(pts + ((size_t)n + idx) * (2 * N), Yf.x);
+		msm_st<N>(pts + ((size_t)n + idx) * (2 * N) + N, Yf.y);
 		msm_st<N>(scal + ((size_t)n + idx) * N, cY);
 	}
 	/* sum of a_i s_i mod q over the CTA */
@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(128) k_msm_ssum(uint32_t nparts, const uint32_
 			gx.w[j] = C::GX_MONT(j);
 			gy.w[j] = C::GY_MONT(j);
 		}
+		if (msm_fold<C>(t)) Field<typename C::Fp>::neg(gy, gy);
 		msm_st<N>(pts + (size_t)2 * n * (2 * N), gx);
 		msm_st<N>(pts + (size_t)2 * n * (2 * N) + N, gy);
 		msm_st<N>(scal + (size_t)2 * n * N, t);
@@ -270,13 +271,13 @@ template <class C>
 int LaunchMsm<C>::ecfsdsa(uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys, const uint8_t *digests, uint32_t hlen,
 			  const MsmKey &key, int c, const MsmBuffers &b, cudaStream_t st)
 {
-	const int nwin = msm_windows(C::QBITS, c);
+	const int nwin = msm_windows(C::QBITS - 1, c);
 	const uint32_t nb = 1u << (c - 1), total = (uint32_t)nwin * nb, ch = nb < 16u ? nb : 16u, per_window = nb / ch,
 		       nparts = (uint32_t)nwin * per_window, npts = 2 * n + 1, nblk = (n + 127) / 128;
 	cudaMemsetAsync(b.count, 0, (size_t)total * 4, st);
 	cudaMemsetAsync(b.fill, 0, (size_t)total * 4, st);
 	cudaMemsetAsync(b.flags, 0, 2 * sizeof(int), st);
-	k_msm_prepare<C><<<nblk, 128, 0, st>>>(n, sigs, pubkeys, digests, hlen, key, b.pts, b.scal, b.partial, b.flags);
+	k_msm_prepare<C><<<nblk, 128, 0, st>>>(n, sigs, pubkeys, digests, hlen, key, c, b.pts, b.scal, b.partial, b.flags);
 	k_msm_ssum<C><<<1, 128, 0, st>>>(nblk, b.partial, n, b.pts, b.scal);
 	k_msm_hist<C><<<(npts + 255) / 256, 256, 0, st>>>(npts, b.scal, c, nwin, b.count);
 	k_msm_scan<C><<<1, 1024, 0, st>>>(total, b.count, b.offs);

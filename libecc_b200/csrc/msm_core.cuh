@@ -22,10 +22,10 @@ namespace eccb200 {
 /* ---------------------------------------------------------------------------------------------- coefficients a_i */
 
 /*
- * a_i = the first 128 bits of the ChaCha20 block (RFC 8439 block function) keyed by the per-call 256-bit seed, with
- * block counter i.  The reference draws a_i with nn_get_random_mod (sig/ecfsdsa.c:915); any coefficients the signer
- * cannot predict give the same guarantee, and 128-bit ones halve the work on the W_i (a forged batch passes with
- * probability 2^-128).
+ * a_i = the leading c * ceil(128 / c) - 1 bits (127 .. 139, see msm_coefficient_bits) of the ChaCha20 block (RFC 8439
+ * block function) keyed by the per-call 256-bit seed, with block counter i.  The reference draws a_i with
+ * nn_get_random_mod (sig/ecfsdsa.c:915); any coefficients the signer cannot predict give the same guarantee, and short
+ * ones halve the work on the W_i (a batch holding a forgery passes with probability <= 2^-127).
  */
 struct MsmKey {
 	uint32_t k[8];
@@ -39,7 +39,7 @@ struct MsmKey {
 		c += d; b ^= c; b = (b << 7) | (b >> 25);  \
 	} while (0)
 
-ECC_HD void msm_chacha20_block4(uint32_t out[4], const MsmKey &key, uint64_t counter)
+ECC_HD void msm_chacha20_block8(uint32_t out[8], const MsmKey &key, uint64_t counter)
 {
 	const uint32_t c0 = 0x61707865u, c1 = 0x3320646eu, c2 = 0x79622d32u, c3 = 0x6b206574u;
 	const uint32_t n0 = (uint32_t)counter, n1 = (uint32_t)(counter >> 32), n2 = 0x314d534du /* "MSM1" */, n3 = 0;
@@ -59,23 +59,59 @@ ECC_HD void msm_chacha20_block4(uint32_t out[4], const MsmKey &key, uint64_t cou
 	out[1] = x1 + c1;
 	out[2] = x2 + c2;
 	out[3] = x3 + c3;
-}
-
-template <int N> ECC_HD void msm_coefficient(Fe<N> &a, const MsmKey &key, uint64_t i)
-{
-	uint32_t o[4];
-	msm_chacha20_block4(o, key, i);
-#pragma unroll
-	for (int j = 0; j < N; j++) a.w[j] = j < 4 ? o[j] : 0u;
+	out[4] = x4 + key.k[0];
+	out[5] = x5 + key.k[1];
+	out[6] = x6 + key.k[2];
+	out[7] = x7 + key.k[3];
 }
 
 /* ---------------------------------------------------------------------------------------------- signed digits */
 
-/* windows of a scalar below 2^bits in signed base-2^c digits d_w in [-2^(c-1), 2^(c-1)] (one more for the last carry) */
-ECC_HD int msm_windows(int bits, int c) { return (bits + c - 1) / c + 1; }
+/*
+ * A scalar below 2^bits in signed base-2^c digits d_w in [-2^(c-1), 2^(c-1)] takes bits / c + 1 windows: the top
+ * window holds the remaining t = bits mod c bits plus the carry, at most 2^t <= 2^(c-1), so nothing is carried out.
+ * Two measures keep the top window from collecting points in a handful of buckets (one thread adds up one bucket):
+ *   - the coefficients a_i have c * ceil(128 / c) - 1 bits (>= 127): their top window is a full one minus one bit;
+ *   - the full-width scalars are folded to k <= (q - 1) / 2 by negating the point (msm_fold), so they have
+ *     bitlen(q) - 1 bits and, for every byte-aligned order at c = 16, a 15-bit top window.
+ */
+ECC_HD int msm_windows(int bits, int c) { return bits / c + 1; }
+ECC_HD int msm_coefficient_bits(int c) { return c * ((128 + c - 1) / c) - 1; }
+
+template <int N> ECC_HD void msm_coefficient(Fe<N> &a, const MsmKey &key, uint64_t i, int c)
+{
+	uint32_t o[8];
+	msm_chacha20_block8(o, key, i);
+	const int bits = msm_coefficient_bits(c); /* 127 .. 139 */
+#pragma unroll
+	for (int j = 0; j < N; j++) {
+		uint32_t v = j < 8 ? o[j < 8 ? j : 0] : 0u;
+		const int lo = 32 * j;
+		if (lo >= bits) v = 0;
+		else if (lo + 32 > bits) v &= (1u << (bits - lo)) - 1u;
+		a.w[j] = v;
+	}
+}
+
+/* k <- min(k, q - k); returns true when the point has to be negated (k and q - k are both below q; k = 0 stays) */
+template <class C> ECC_HD bool msm_fold(Fe<C::N> &k)
+{
+	typedef Field<typename C::Fq> Fq;
+	Fe<C::N> kn;
+	Fq::neg(kn, k); /* q - k, or 0 for k = 0 */
+	uint64_t bw = 0; /* borrow of kn - k: set iff kn < k */
+#pragma unroll
+	for (int i = 0; i < C::N; i++) {
+		const uint64_t t = (uint64_t)kn.w[i] - k.w[i] - bw;
+		bw = (t >> 32) & 1;
+	}
+	const bool take = bw != 0 && !Fq::is_zero(k);
+	if (take) k = kn;
+	return take;
+}
 
 /* calls f(w, d) for every non-zero digit of the nwords-word scalar k (k read through a pointer: global memory on the
- * device, so the dynamic word index costs nothing); 1 <= c <= 16 */
+ * device, so the dynamic word index costs nothing); 2 <= c <= 16 */
 template <class Fn> ECC_HD void msm_digits(const uint32_t *k, int nwords, int c, int nwin, Fn &&f)
 {
 	const uint32_t half = 1u << (c - 1), mask = (1u << c) - 1u;
@@ -161,13 +197,13 @@ template <class C> ECC_HD void msm_st_jac(uint32_t *buf, size_t idx, const Jac<C
 /*
  * ECFSDSA (sig/ecfsdsa.c:881-993): signature W_x || W_y || s, digest H(W_x || W_y || m).  Given the parsed, validated
  * pieces and the coefficient a, produce the two terms of the sum this signature owns,
- *       a * (-W)        (-W stored, so the 128-bit a is the scalar: the reference multiplies W by -a mod q, :985-987)
- *       (a * e) * Y     with e = -h mod q (:963-968)
+ *       a * (-W)        (-W stored, so the short a is the scalar: the reference multiplies W by -a mod q, :985-987)
+ *       (a * e) * Y     with e = -h mod q (:963-968), folded to a scalar <= (q - 1) / 2 on +-Y
  * and its share t = a * s mod q of the generator's scalar (:925-927).  All scalars in plain form.
  */
 template <class C>
-ECC_HD void msm_terms(Aff<C> &negW, Fe<C::N> &cY, Fe<C::N> &t, const Aff<C> &W, const Fe<C::N> &s, const Fe<C::N> &e_neg,
-		      const Fe<C::N> &a)
+ECC_HD void msm_terms(Aff<C> &negW, Aff<C> &Yf, Fe<C::N> &cY, Fe<C::N> &t, const Aff<C> &W, const Aff<C> &Y,
+		      const Fe<C::N> &s, const Fe<C::N> &e_neg, const Fe<C::N> &a)
 {
 	typedef Field<typename C::Fp> F;
 	typedef Field<typename C::Fq> Fq;
@@ -177,6 +213,8 @@ ECC_HD void msm_terms(Aff<C> &negW, Fe<C::N> &cY, Fe<C::N> &t, const Aff<C> &W, 
 	Fq::to_mont(am, a);      /* a R mod q */
 	Fq::mul(cY, am, e_neg);  /* a e mod q, plain */
 	Fq::mul(t, am, s);       /* a s mod q, plain */
+	Yf = Y;
+	if (msm_fold<C>(cY)) F::neg(Yf.y, Y.y);
 }
 
 /* ---------------------------------------------------------------------------------------------- bucket reduction */

@@ -391,7 +391,8 @@ int hostsim_point_op(int curve_id, int which, const uint8_t *p1, const uint8_t *
  * ECFSDSA batch verification as one multi-scalar multiplication: the stages of libecc_b200/csrc/msm.cuh run serially
  * with the same building blocks (msm_core.cuh) — prepare, counting sort by bucket, bucket accumulation with the XYZZ
  * mixed addition, range reduction, per-window sums, Horner.  all_valid like eccb200_ecfsdsa_verify_msm_batch.
- * stats (optional, 4 entries): mixed additions of the accumulation, buckets, windows, field products in total.
+ * stats (optional, 5 entries): mixed additions of the accumulation, buckets, windows, field products in total, the
+ * fullest bucket.
  */
 int hostsim_ecfsdsa_msm(int curve_id, int c, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys, const uint8_t *digests,
 			uint32_t hlen, const uint8_t *seed, int *all_valid, unsigned long long *stats)
@@ -409,7 +410,7 @@ int hostsim_ecfsdsa_msm(int curve_id, int c, uint32_t n, const uint8_t *sigs, co
 		for (int i = 0; i < 8; i++)
 			key.k[i] = (uint32_t)seed[4 * i] | ((uint32_t)seed[4 * i + 1] << 8) | ((uint32_t)seed[4 * i + 2] << 16) |
 				   ((uint32_t)seed[4 * i + 3] << 24);
-		const int nwin = msm_windows(C::QBITS, c);
+		const int nwin = msm_windows(C::QBITS - 1, c);
 		const uint32_t nb = 1u << (c - 1), total = (uint32_t)nwin * nb, ch = nb < 16u ? nb : 16u, per_window = nb / ch;
 		const size_t npts = 2 * (size_t)n + 1;
 		std::vector<uint32_t> pts(npts * 2 * N), scal(npts * N);
@@ -419,7 +420,7 @@ int hostsim_ecfsdsa_msm(int curve_id, int c, uint32_t n, const uint8_t *sigs, co
 		/* prepare (k_msm_prepare / k_msm_ssum) */
 		for (uint32_t i = 0; i < n; i++) {
 			const uint8_t *sg = sigs + (size_t)i * (2 * C::PLEN + C::QLEN);
-			Aff<C> W, Y, negW;
+			Aff<C> W, Y, negW, Yf;
 			Fe<N> s, h, a, cY, t;
 			const bool w_ok = load_point<C>(W, sg);
 			load_be<N>(s, sg + 2 * C::PLEN, C::QLEN);
@@ -427,8 +428,8 @@ int hostsim_ecfsdsa_msm(int curve_id, int c, uint32_t n, const uint8_t *sigs, co
 			const bool key_ok = load_point<C>(Y, pubkeys + (size_t)i * 2 * C::PLEN);
 			digest_full_mod_q<C>(h, digests + (size_t)i * hlen, hlen);
 			Fq::neg(h, h);
-			msm_coefficient<N>(a, key, i);
-			msm_terms<C>(negW, cY, t, W, s, h, a);
+			msm_coefficient<N>(a, key, i, c);
+			msm_terms<C>(negW, Yf, cY, t, W, Y, s, h, a);
 			if (!(w_ok && s_ok && key_ok)) {
 				bad = true;
 				Fq::set_zero(a);
@@ -438,14 +439,20 @@ int hostsim_ecfsdsa_msm(int curve_id, int c, uint32_t n, const uint8_t *sigs, co
 			msm_st<N>(&pts[(size_t)i * 2 * N], negW.x);
 			msm_st<N>(&pts[(size_t)i * 2 * N + N], negW.y);
 			msm_st<N>(&scal[(size_t)i * N], a);
-			msm_st<N>(&pts[((size_t)n + i) * 2 * N], Y.x);
-			msm_st<N>(&pts[((size_t)n + i) * 2 * N + N], Y.y);
+			msm_st<N>(&pts[((size_t)n + i) * 2 * N], Yf.x);
+			msm_st<N>(&pts[((size_t)n + i) * 2 * N + N], Yf.y);
 			msm_st<N>(&scal[((size_t)n + i) * N], cY);
 			Fq::add(ssum, ssum, t);
 		}
-		for (int j = 0; j < N; j++) {
-			pts[(size_t)2 * n * 2 * N + j] = C::GX_MONT(j);
-			pts[(size_t)2 * n * 2 * N + N + j] = C::GY_MONT(j);
+		{
+			Fe<N> gx, gy;
+			for (int j = 0; j < N; j++) {
+				gx.w[j] = C::GX_MONT(j);
+				gy.w[j] = C::GY_MONT(j);
+			}
+			if (msm_fold<C>(ssum)) F::neg(gy, gy);
+			msm_st<N>(&pts[(size_t)2 * n * 2 * N], gx);
+			msm_st<N>(&pts[(size_t)2 * n * 2 * N + N], gy);
 		}
 		msm_st<N>(&scal[(size_t)2 * n * N], ssum);
 		/* counting sort (k_msm_hist / k_msm_scan / k_msm_scatter) */
@@ -500,6 +507,9 @@ int hostsim_ecfsdsa_msm(int curve_id, int c, uint32_t n, const uint8_t *sigs, co
 			stats[1] = total;
 			stats[2] = (unsigned long long)nwin;
 			stats[3] = g_fe_mul_count;
+			unsigned long long mx = 0;
+			for (uint32_t g = 0; g < total; g++) mx = count[g] > mx ? count[g] : mx;
+			stats[4] = mx;
 		}
 		return 0;
 	});
@@ -514,13 +524,13 @@ int hostsim_msm_digits(const uint32_t *k, int nwords, int bits, int c, int *digi
 	return nwin;
 }
 
-void hostsim_msm_coefficient(const uint8_t *seed, uint64_t i, uint32_t out[4])
+void hostsim_msm_coefficient(const uint8_t *seed, uint64_t i, uint32_t out[8])
 {
 	MsmKey key;
 	for (int j = 0; j < 8; j++)
 		key.k[j] = (uint32_t)seed[4 * j] | ((uint32_t)seed[4 * j + 1] << 8) | ((uint32_t)seed[4 * j + 2] << 16) |
 			   ((uint32_t)seed[4 * j + 3] << 24);
-	msm_chacha20_block4(out, key, i);
+	msm_chacha20_block8(out, key, i);
 }
 
 unsigned long long hostsim_last_mul_count(void) { return g_fe_mul_count; }
