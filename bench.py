@@ -880,7 +880,7 @@ def run_ecfsdsa_msm(local_rank: int, batch_log2: int = 20, with_cpu: bool = True
     l0 = eng.kernel_launches
     ms_msm = timed(lambda: verdicts.append(eng.ecfsdsa_verify_msm_batch_dev(n, dS.data_ptr(), dP.data_ptr(), dD.data_ptr(),
                                                                             32, None, stream)), 5, 2)
-    launches = int(eng.kernel_launches - l0) // 7
+    launches = int(eng.kernel_launches - l0) // 7  # 5 timed + 2 warm-up calls
 
     def per_item():
         rc = lib.eccb200_ecfsdsa_verify_batch_dev(eng._h, n, dS.data_ptr(), dP.data_ptr(), dD.data_ptr(), 32,

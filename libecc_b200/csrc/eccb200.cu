@@ -281,7 +281,7 @@ extern "C" int eccb200_ctx_create(eccb200_ctx **out, int curve_id, int device, i
 static void msm_release(eccb200_ctx *ctx)
 {
 	uint32_t *bufs[] = { ctx->msm.pts, ctx->msm.scal, ctx->msm.partial, ctx->msm.count, ctx->msm.offs, ctx->msm.fill,
-			     ctx->msm.list, ctx->msm.buckets, ctx->msm.parts, ctx->msm.winsum };
+			     ctx->msm.list, ctx->msm.buckets, ctx->msm.parts, ctx->msm.winsum, ctx->msm.order, ctx->msm.aux };
 	for (uint32_t *b : bufs)
 		if (b) cudaFree(b);
 	if (ctx->msm.flags) cudaFree(ctx->msm.flags);
@@ -1218,15 +1218,20 @@ extern "C" int eccb200_bip0340_verify_batch(eccb200_ctx *ctx, uint32_t n, const 
  * and conversions of the bucket reduction), in field products; ECCB200_MSM_WINDOW overrides (tests walk small c). */
 static int msm_pick_window(uint32_t n, int qbits)
 {
+	/* the bucket scan handles up to 2^20 buckets (1024 tiles of 1024): wide orders stop below c = 16 */
+	auto fits = [&](int c) { return (uint64_t)msm_windows(qbits - 1, c) << (c - 1) <= (1u << 20); };
 	if (const char *e = getenv("ECCB200_MSM_WINDOW")) {
-		const int c = atoi(e);
-		if (c >= 2 && c <= 16) return c;
+		int c = atoi(e);
+		if (c >= 2 && c <= 16) {
+			while (!fits(c)) c--;
+			return c;
+		}
 	}
 	/* time ~ max(total work / threads in flight, the longest chain one thread adds up): the chain is the expected load
 	 * of a bucket of the top window, which holds only t = (qbits - 1) mod c bits (msm_core.cuh) */
 	int best = 2;
 	double best_cost = 0;
-	for (int c = 2; c <= 16; c++) {
+	for (int c = 2; c <= 16 && fits(c); c++) {
 		const int nw = msm_windows(qbits - 1, c), nwa = msm_windows(msm_coefficient_bits(c), c), t = (qbits - 1) % c;
 		const double acc = (double)n * (nwa + nw) * 10.0;
 		const double red = (double)nw * (double)(1u << (c - 1)) * (2 * 16.0 + 2.0);
@@ -1262,6 +1267,7 @@ static int msm_ensure(eccb200_ctx *ctx, uint32_t n, int c)
 	    cudaMalloc(&b.buckets, (size_t)cap_total * 3 * N * 4) != cudaSuccess ||
 	    cudaMalloc(&b.parts, (size_t)cap_total * 3 * N * 4) != cudaSuccess ||
 	    cudaMalloc(&b.winsum, (size_t)msm_windows(qbits - 1, 2) * 3 * N * 4) != cudaSuccess ||
+	    cudaMalloc(&b.order, (size_t)cap_total * 4) != cudaSuccess || cudaMalloc(&b.aux, 3072 * 4) != cudaSuccess ||
 	    cudaMalloc(&b.flags, 2 * sizeof(int)) != cudaSuccess) {
 		cudaGetLastError();
 		msm_release(ctx);
