@@ -825,16 +825,18 @@ def run_sign_and_ecdh(local_rank: int, batch_log2: int = 20) -> dict:
     return out
 
 
-def run_ecfsdsa_msm(local_rank: int, batch_log2: int = 20, with_cpu: bool = True) -> dict:
-    """§8f.4: ECFSDSA batch verification in the reference's verify_batch form (one random linear combination for the
-    whole batch, src/sig/ecfsdsa.c:814-1055) as a multi-scalar multiplication on the device (K6), next to the per-item
-    verification kernel on the same batch.  2^14 distinct signatures made here (k*G and d*G by the engine, the rest is
-    hashlib and integers), tiled to the batch size; FRP256V1 / SHA-256."""
+def run_schnorr_msm(local_rank: int, scheme: str = "ecfsdsa", batch_log2: int = 20, with_cpu: bool = True) -> dict:
+    """§8f.4: Schnorr-type batch verification in the reference's verify_batch form (one random linear combination for
+    the whole batch, src/sig/ecfsdsa.c:814-1055, src/sig/bip0340.c:1040-1290) as a multi-scalar multiplication on the
+    device (K6), next to the per-item verification kernel on the same batch.  2^14 distinct signatures made here (k*G and
+    d*G by the engine, the rest is hashlib and integers), tiled to the batch size.  ECFSDSA on FRP256V1, BIP0340 on
+    SECP256K1; SHA-256."""
     import hashlib
     import torch
     import libecc_b200
     from common import ALL_CURVES as CURVES, ORDER
-    curve = "FRP256V1"
+    bip = scheme == "bip0340"
+    curve = "SECP256K1" if bip else "FRP256V1"
     _, plen, qlen = CURVES[curve]
     q = ORDER[curve]
     n, m = 1 << batch_log2, 1 << 14
@@ -845,14 +847,22 @@ def run_ecfsdsa_msm(local_rank: int, batch_log2: int = 20, with_cpu: bool = True
     pubs, st1 = eng.prj_pt_mul_batch(d)
     W, st2 = eng.prj_pt_mul_batch(k)
     assert (st1 == 0).all() and (st2 == 0).all()
-    sigs = np.zeros((m, 2 * plen + qlen), np.uint8)
+    siglen = (plen if bip else 2 * plen) + qlen
+    sigs = np.zeros((m, siglen), np.uint8)
     dg = np.zeros((m, 32), np.uint8)
-    sigs[:, :2 * plen] = W
+    sigs[:, :siglen - qlen] = W[:, :siglen - qlen]
+    tag = hashlib.sha256(b"BIP0340/challenge").digest()
     for i in range(m):
-        h = hashlib.sha256(W[i].tobytes() + msgs[i].tobytes()).digest()
+        di, ki = int.from_bytes(d[i].tobytes(), "big"), int.from_bytes(k[i].tobytes(), "big")
+        if bip:
+            # sig/bip0340.c:239-330: the secret and the nonce are negated when their points have an odd y
+            if pubs[i, -1] & 1: di = q - di
+            if W[i, -1] & 1: ki = q - ki
+            h = hashlib.sha256(tag + tag + W[i, :plen].tobytes() + pubs[i, :plen].tobytes() + msgs[i].tobytes()).digest()
+        else:
+            h = hashlib.sha256(W[i].tobytes() + msgs[i].tobytes()).digest()
         dg[i] = np.frombuffer(h, np.uint8)
-        s_i = (int.from_bytes(k[i].tobytes(), "big") + int.from_bytes(h, "big") * int.from_bytes(d[i].tobytes(), "big")) % q
-        sigs[i, 2 * plen:] = np.frombuffer(s_i.to_bytes(qlen, "big"), np.uint8)
+        sigs[i, siglen - qlen:] = np.frombuffer(((ki + int.from_bytes(h, "big") * di) % q).to_bytes(qlen, "big"), np.uint8)
     reps = n // m
     S, P, D = np.tile(sigs, (reps, 1)), np.tile(pubs, (reps, 1)), np.tile(dg, (reps, 1))
     dev = torch.device("cuda", local_rank)
@@ -861,6 +871,9 @@ def run_ecfsdsa_msm(local_rank: int, batch_log2: int = 20, with_cpu: bool = True
     stream = torch.cuda.current_stream().cuda_stream
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     lib = eng.lib
+    msm_dev = lib.eccb200_bip0340_verify_msm_batch_dev if bip else lib.eccb200_ecfsdsa_verify_msm_batch_dev
+    item_dev = lib.eccb200_bip0340_verify_batch_dev if bip else lib.eccb200_ecfsdsa_verify_batch_dev
+    msm_host = eng.bip0340_verify_msm_batch if bip else eng.ecfsdsa_verify_msm_batch
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -877,31 +890,34 @@ def run_ecfsdsa_msm(local_rank: int, batch_log2: int = 20, with_cpu: bool = True
         return float(np.mean(ms))
 
     verdicts = []
+
+    def msm():
+        ok = ctypes.c_int(0)
+        assert msm_dev(eng._h, n, dS.data_ptr(), dP.data_ptr(), dD.data_ptr(), 32, None, ctypes.byref(ok), stream) == 0
+        verdicts.append(ok.value == 1)
     l0 = eng.kernel_launches
-    ms_msm = timed(lambda: verdicts.append(eng.ecfsdsa_verify_msm_batch_dev(n, dS.data_ptr(), dP.data_ptr(), dD.data_ptr(),
-                                                                            32, None, stream)), 5, 2)
+    ms_msm = timed(msm, 5, 2)
     launches = int(eng.kernel_launches - l0) // 7  # 5 timed + 2 warm-up calls
 
     def per_item():
-        rc = lib.eccb200_ecfsdsa_verify_batch_dev(eng._h, n, dS.data_ptr(), dP.data_ptr(), dD.data_ptr(), 32,
-                                                  dV.data_ptr(), stream)
-        assert rc == 0
+        assert item_dev(eng._h, n, dS.data_ptr(), dP.data_ptr(), dD.data_ptr(), 32, dV.data_ptr(), stream) == 0
     ms_item = timed(per_item, 3, 1)
     item_ok = bool((dV == 0).all().item())
     # end to end through the host-pointer call (page-locked inputs), the verdict is the only output
     pin = lambda a: (lambda h: (h.__setitem__(Ellipsis, a), h)[1])(libecc_b200.pinned_empty(a.shape, a.dtype))
     hS, hP, hD = pin(S), pin(P), pin(D)
-    eng.ecfsdsa_verify_msm_batch(hS, hP, hD, 32)
+    msm_host(hS, hP, hD, 32)
     t0 = time.perf_counter()
-    e2e_ok = [eng.ecfsdsa_verify_msm_batch(hS, hP, hD, 32) for _ in range(3)]
+    e2e_ok = [msm_host(hS, hP, hD, 32) for _ in range(3)]
     e2e_dt = (time.perf_counter() - t0) / 3
     # one flipped bit anywhere sinks the batch
     j = 777777 % n
     hS[j, -1] ^= 1
-    forged = eng.ecfsdsa_verify_msm_batch(hS, hP, hD, 32)
+    forged = msm_host(hS, hP, hD, 32)
     hS[j, -1] ^= 1
-    res = {"metric": "frp256v1 ECFSDSA verify_batch (one multi-scalar multiplication) signatures/sec", "unit": "ec_verify/s",
-           "value": n / (ms_msm * 1e-3), "ms_per_step": ms_msm, "batch": n, "steps": 5, "warmup": 2,
+    name = "BIP0340" if bip else "ECFSDSA"
+    res = {"metric": f"{curve.lower()} {name} verify_batch (one multi-scalar multiplication) signatures/sec",
+           "unit": "ec_verify/s", "value": n / (ms_msm * 1e-3), "ms_per_step": ms_msm, "batch": n, "steps": 5, "warmup": 2,
            "kernels_per_call": launches,
            "per_item_kernel_same_batch": {"value": n / (ms_item * 1e-3), "ms_per_step": ms_item, "all_valid": item_ok},
            "speedup_vs_per_item_kernel": ms_item / ms_msm,
@@ -911,9 +927,9 @@ def run_ecfsdsa_msm(local_rank: int, batch_log2: int = 20, with_cpu: bool = True
     if with_cpu:
         from common import oracle_lib, _buf
         v = np.zeros(256, np.int8)
-        assert oracle_lib().ora_ecfsdsa_verify_digest_batch(curve.encode(), 256, _buf(np.ascontiguousarray(sigs[:256])),
-                                                            _buf(np.ascontiguousarray(pubs[:256])),
-                                                            _buf(np.ascontiguousarray(dg[:256])), 32, _buf(v), 8) == 0
+        fn = oracle_lib().ora_bip0340_verify_digest_batch if bip else oracle_lib().ora_ecfsdsa_verify_digest_batch
+        assert fn(curve.encode(), 256, _buf(np.ascontiguousarray(sigs[:256])), _buf(np.ascontiguousarray(pubs[:256])),
+                  _buf(np.ascontiguousarray(dg[:256])), 32, _buf(v), 8) == 0
         res["parity_on_cpu_prefix"] = bool((v == 0).all())
     eng.close()
     return res
@@ -1047,10 +1063,11 @@ def main():
                 extra.update(run_sign_and_ecdh(local_rank))
             except Exception as exc:           # noqa: BLE001
                 extra["sign_and_ecdh"] = {"error": str(exc)[:300]}
-            try:
-                extra["frp256v1_ecfsdsa_verify_batch_msm"] = run_ecfsdsa_msm(local_rank, with_cpu=not args.no_cpu_baseline)
-            except Exception as exc:           # noqa: BLE001
-                extra["frp256v1_ecfsdsa_verify_batch_msm"] = {"error": str(exc)[:300]}
+            for key, sch in (("frp256v1_ecfsdsa_verify_batch_msm", "ecfsdsa"), ("secp256k1_bip0340_verify_batch_msm", "bip0340")):
+                try:
+                    extra[key] = run_schnorr_msm(local_rank, sch, with_cpu=not args.no_cpu_baseline)
+                except Exception as exc:       # noqa: BLE001
+                    extra[key] = {"error": str(exc)[:300]}
         else:
             o.close()
             # the in-process multi-device C ABI (eccb200_multi_*): ONE host call shards 2^24 scalars over all GPUs of

@@ -261,6 +261,19 @@ int eccb200_ecfsdsa_verify_msm_batch_dev(eccb200_ctx *ctx, uint32_t n, const uin
 					 void *stream);
 
 /*
+ * The same for BIP0340 (the reference's _bip0340_verify_batch, src/sig/bip0340.c:1040-1290): inputs as
+ * eccb200_bip0340_verify_batch (sigs [n][plen + qlen] = r || s, digests = the tagged challenge hashes).  The points R_i are
+ * lifted from r_i on the device (even y, src/sig/bip0340.c:1188-1196: one exponentiation per signature, p = 3 mod 4) and the
+ * keys taken at their even-y representative; a batch with an r_i that is no x coordinate of the curve is rejected, as
+ * aff_pt_y_from_x fails in the reference.  -1 on SECP224R1 (p = 1 mod 4: use eccb200_bip0340_verify_batch).
+ */
+int eccb200_bip0340_verify_msm_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys,
+				     const uint8_t *digests, uint32_t hlen, const uint8_t *seed, int *all_valid);
+int eccb200_bip0340_verify_msm_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_sigs, const uint8_t *d_pubkeys,
+					 const uint8_t *d_digests, uint32_t hlen, const uint8_t *seed, int *all_valid,
+					 void *stream);
+
+/*
  * Batched double-scalar multiplication W_i = a_i*G + b_i*Y_i with affine results: the sequence prj_pt_mul, prj_pt_mul,
  * prj_pt_add, prj_pt_unique that every Schnorr-type verification of the reference runs before it hashes the recomputed
  * point (ECSDSA / ECOSDSA src/sig/ecsdsa_common.c:493-497, ECKCDSA, ...), as ONE kernel launch per batch: comb for G,

@@ -32,6 +32,7 @@ ABI_SYMBOLS = [
     "eccb200_structured_key_pair_batch", "eccb200_ecdsa_verify_structured_batch", "eccb200_ecdsa_sign_structured_batch",
     "eccb200_ecfsdsa_verify_batch", "eccb200_ecfsdsa_verify_batch_dev",
     "eccb200_ecfsdsa_verify_msm_batch", "eccb200_ecfsdsa_verify_msm_batch_dev",
+    "eccb200_bip0340_verify_msm_batch", "eccb200_bip0340_verify_msm_batch_dev",
     "eccb200_prj_pt_mul_batch_dev_gather", "eccb200_ipc_alloc", "eccb200_ipc_open", "eccb200_ipc_close",
     "eccb200_ipc_free", "eccb200_flag_wait", "eccb200_flag_signal",
     "eccb200_multi_create", "eccb200_multi_destroy", "eccb200_multi_device_count", "eccb200_multi_ctx",
@@ -95,6 +96,8 @@ def load_library() -> ctypes.CDLL:
                                                      ctypes.POINTER(ctypes.c_int)]
     lib.eccb200_ecfsdsa_verify_msm_batch_dev.argtypes = [ctypes.c_void_p, u32, u8p, u8p, u8p, u32, u8p,
                                                          ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
+    lib.eccb200_bip0340_verify_msm_batch.argtypes = lib.eccb200_ecfsdsa_verify_msm_batch.argtypes
+    lib.eccb200_bip0340_verify_msm_batch_dev.argtypes = lib.eccb200_ecfsdsa_verify_msm_batch_dev.argtypes
     vp, u64 = ctypes.c_void_p, ctypes.c_uint64
     lib.eccb200_prj_pt_mul_batch_dev_gather.argtypes = [vp, u32, u8p, u8p, u8p, i8p, ctypes.c_int, vp, vp, vp, u32,
                                                         vp, ctypes.c_int, u32, vp]
@@ -367,11 +370,9 @@ class Engine:
                                                           hlen, verdict.ctypes.data), "eccb200_ecfsdsa_verify_batch")
         return verdict
 
-    def ecfsdsa_verify_msm_batch(self, sigs, pubkeys, digests, hlen: int, seed: Optional[bytes] = None) -> bool:
-        """The whole batch as ONE multi-scalar multiplication (the reference's verify_batch form): True iff every
-        signature verifies.  seed: 32 bytes (None: from the OS)."""
+    def _schnorr_msm(self, fn_name: str, siglen: int, sigs, pubkeys, digests, hlen: int, seed: Optional[bytes]) -> bool:
         sg = _as_u8(sigs)
-        n = sg.size // (2 * self.plen + self.qlen)
+        n = sg.size // siglen
         pk = _as_u8(pubkeys, n * 2 * self.plen)
         dg = _as_u8(digests, n * hlen)
         ok = ctypes.c_int(0)
@@ -380,10 +381,20 @@ class Engine:
             if len(seed) != 32:
                 raise ValueError("seed must be 32 bytes")
             sd = ctypes.cast(ctypes.create_string_buffer(bytes(seed), 32), ctypes.c_void_p)
-        self._check(self.lib.eccb200_ecfsdsa_verify_msm_batch(self._h, n, sg.ctypes.data, pk.ctypes.data,
-                                                              dg.ctypes.data, hlen, sd, ctypes.byref(ok)),
-                    "eccb200_ecfsdsa_verify_msm_batch")
+        self._check(getattr(self.lib, fn_name)(self._h, n, sg.ctypes.data, pk.ctypes.data, dg.ctypes.data, hlen, sd,
+                                               ctypes.byref(ok)), fn_name)
         return ok.value == 1
+
+    def ecfsdsa_verify_msm_batch(self, sigs, pubkeys, digests, hlen: int, seed: Optional[bytes] = None) -> bool:
+        """The whole batch as ONE multi-scalar multiplication (the reference's verify_batch form): True iff every
+        signature verifies.  seed: 32 bytes (None: from the OS)."""
+        return self._schnorr_msm("eccb200_ecfsdsa_verify_msm_batch", 2 * self.plen + self.qlen, sigs, pubkeys, digests,
+                                 hlen, seed)
+
+    def bip0340_verify_msm_batch(self, sigs, pubkeys, digests, hlen: int, seed: Optional[bytes] = None) -> bool:
+        """BIP0340 in the same form (sigs [n][plen + qlen] = r || s, digests = tagged challenge hashes)."""
+        return self._schnorr_msm("eccb200_bip0340_verify_msm_batch", self.plen + self.qlen, sigs, pubkeys, digests, hlen,
+                                 seed)
 
     def ecfsdsa_verify_msm_batch_dev(self, n: int, d_sigs: int, d_pubkeys: int, d_digests: int, hlen: int,
                                      seed: Optional[bytes] = None, stream: int = 0) -> bool:

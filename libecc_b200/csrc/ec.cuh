@@ -60,25 +60,32 @@ template <class C> struct EC {
 		for (int i = 0; i < N; i++) r.w[i] = C::A_MONT(i);
 	}
 
-	/* y^2 == x^3 + a x + b (all Montgomery form); affine form of prj_pt_is_on_curve (curves/prj_pt.c:144-190) */
-	static ECC_HD bool on_curve(const A &a)
+	/* u = x^3 + a x + b (Montgomery form): the right-hand side of the curve equation */
+	static ECC_HD void curve_rhs(E &u, const E &x)
 	{
-		E t, u, b;
-		F::sqr(t, a.x);
-		F::mul(u, t, a.x);      /* x^3 */
+		E t, b;
+		F::sqr(t, x);
+		F::mul(u, t, x);      /* x^3 */
 		if (C::A_KIND == 0) {
-			F::add(t, a.x, a.x);
-			F::add(t, t, a.x);  /* 3x */
+			F::add(t, x, x);
+			F::add(t, t, x);  /* 3x */
 			F::sub(u, u, t);
 		} else if (C::A_KIND == 2) {
 			E am;
 			load_a(am);
-			F::mul(t, am, a.x);
+			F::mul(t, am, x);
 			F::add(u, u, t);
 		}
 #pragma unroll
 		for (int i = 0; i < N; i++) b.w[i] = C::B_MONT(i);
 		F::add(u, u, b);
+	}
+
+	/* y^2 == x^3 + a x + b (all Montgomery form); affine form of prj_pt_is_on_curve (curves/prj_pt.c:144-190) */
+	static ECC_HD bool on_curve(const A &a)
+	{
+		E t, u;
+		curve_rhs(u, a.x);
 		F::sqr(t, a.y);
 		return F::eq(t, u);
 	}

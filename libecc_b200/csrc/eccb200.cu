@@ -1297,7 +1297,7 @@ static int msm_seed(MsmKey &key, const uint8_t *seed)
 	return 0;
 }
 
-static int ecfsdsa_msm_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_sigs, const uint8_t *d_pubkeys,
+static int schnorr_msm_dev(eccb200_ctx *ctx, int scheme, uint32_t n, const uint8_t *d_sigs, const uint8_t *d_pubkeys,
 			   const uint8_t *d_digests, uint32_t hlen, const uint8_t *seed, int *all_valid, cudaStream_t st)
 {
 	*all_valid = 0;
@@ -1311,7 +1311,9 @@ static int ecfsdsa_msm_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_sigs, 
 		const int c = msm_pick_window(n, C::QBITS);
 		if (msm_ensure(ctx, n, c)) return -1;
 		scratch_enter(ctx, st);
-		ctx->launches += (uint64_t)LaunchMsm<C>::ecfsdsa(n, d_sigs, d_pubkeys, d_digests, hlen, key, c, ctx->msm, st);
+		const int launched = LaunchMsm<C>::verify(scheme, n, d_sigs, d_pubkeys, d_digests, hlen, key, c, ctx->msm, st);
+		if (launched < 0) return fail("BIP0340 batch verification by multi-scalar multiplication needs p = 3 mod 4 (not this curve)");
+		ctx->launches += (uint64_t)launched;
 		CUDA_OK(cudaGetLastError());
 		CUDA_OK(cudaMemcpyAsync(flags, ctx->msm.flags, sizeof flags, cudaMemcpyDeviceToHost, st));
 		scratch_leave(ctx, st);
@@ -1323,29 +1325,41 @@ static int ecfsdsa_msm_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_sigs, 
 	return 0;
 }
 
-extern "C" int eccb200_ecfsdsa_verify_msm_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_sigs,
-						      const uint8_t *d_pubkeys, const uint8_t *d_digests, uint32_t hlen,
-						      const uint8_t *seed, int *all_valid, void *stream)
+static int schnorr_msm_dev_checked(eccb200_ctx *ctx, int scheme, uint32_t n, const uint8_t *d_sigs, const uint8_t *d_pubkeys,
+				   const uint8_t *d_digests, uint32_t hlen, const uint8_t *seed, int *all_valid, void *stream)
 {
 	if (!ctx || !all_valid || (n && (!d_sigs || !d_pubkeys || !d_digests))) return fail("null argument");
 	if (hlen == 0 || hlen > 128) return fail("bad digest length");
 	if (misaligned16(ctx, { d_sigs, d_pubkeys })) return fail(kAlignMsg);
 	CUDA_OK(cudaSetDevice(ctx->device));
-	return ecfsdsa_msm_dev(ctx, n, d_sigs, d_pubkeys, d_digests, hlen, seed, all_valid, (cudaStream_t)stream);
+	return schnorr_msm_dev(ctx, scheme, n, d_sigs, d_pubkeys, d_digests, hlen, seed, all_valid, (cudaStream_t)stream);
+}
+
+extern "C" int eccb200_ecfsdsa_verify_msm_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_sigs,
+						      const uint8_t *d_pubkeys, const uint8_t *d_digests, uint32_t hlen,
+						      const uint8_t *seed, int *all_valid, void *stream)
+{
+	return schnorr_msm_dev_checked(ctx, 1, n, d_sigs, d_pubkeys, d_digests, hlen, seed, all_valid, stream);
+}
+
+extern "C" int eccb200_bip0340_verify_msm_batch_dev(eccb200_ctx *ctx, uint32_t n, const uint8_t *d_sigs,
+						      const uint8_t *d_pubkeys, const uint8_t *d_digests, uint32_t hlen,
+						      const uint8_t *seed, int *all_valid, void *stream)
+{
+	return schnorr_msm_dev_checked(ctx, 2, n, d_sigs, d_pubkeys, d_digests, hlen, seed, all_valid, stream);
 }
 
 static inline size_t msm_align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
-extern "C" int eccb200_ecfsdsa_verify_msm_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *sigs,
-						  const uint8_t *pubkeys, const uint8_t *digests, uint32_t hlen,
-						  const uint8_t *seed, int *all_valid)
+static int schnorr_msm_host(eccb200_ctx *ctx, int scheme, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys,
+			    const uint8_t *digests, uint32_t hlen, const uint8_t *seed, int *all_valid)
 {
 	if (!ctx || !all_valid || (n && (!sigs || !pubkeys || !digests))) return fail("null argument");
 	if (hlen == 0 || hlen > 128) return fail("bad digest length");
 	*all_valid = 0;
 	if (n == 0) return 0;
 	CUDA_OK(cudaSetDevice(ctx->device));
-	const size_t pk = 2 * (size_t)ctx->plen, sg = pk + (size_t)ctx->qlen;
+	const size_t pk = 2 * (size_t)ctx->plen, sg = (scheme == 2 ? (size_t)ctx->plen : pk) + (size_t)ctx->qlen;
 	const size_t b_sg = msm_align16((size_t)n * sg), b_pk = msm_align16((size_t)n * pk), b_dg = msm_align16((size_t)n * hlen);
 	if (ctx->msm_in_bytes < b_sg + b_pk + b_dg) {
 		if (ctx->msm_in) cudaFree(ctx->msm_in);
@@ -1359,7 +1373,21 @@ extern "C" int eccb200_ecfsdsa_verify_msm_batch(eccb200_ctx *ctx, uint32_t n, co
 	CUDA_OK(cudaMemcpyAsync(d, sigs, (size_t)n * sg, cudaMemcpyHostToDevice, st));
 	CUDA_OK(cudaMemcpyAsync(d + b_sg, pubkeys, (size_t)n * pk, cudaMemcpyHostToDevice, st));
 	CUDA_OK(cudaMemcpyAsync(d + b_sg + b_pk, digests, (size_t)n * hlen, cudaMemcpyHostToDevice, st));
-	return ecfsdsa_msm_dev(ctx, n, d, d + b_sg, d + b_sg + b_pk, hlen, seed, all_valid, st);
+	return schnorr_msm_dev(ctx, scheme, n, d, d + b_sg, d + b_sg + b_pk, hlen, seed, all_valid, st);
+}
+
+extern "C" int eccb200_ecfsdsa_verify_msm_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *sigs,
+						  const uint8_t *pubkeys, const uint8_t *digests, uint32_t hlen,
+						  const uint8_t *seed, int *all_valid)
+{
+	return schnorr_msm_host(ctx, 1, n, sigs, pubkeys, digests, hlen, seed, all_valid);
+}
+
+extern "C" int eccb200_bip0340_verify_msm_batch(eccb200_ctx *ctx, uint32_t n, const uint8_t *sigs,
+						  const uint8_t *pubkeys, const uint8_t *digests, uint32_t hlen,
+						  const uint8_t *seed, int *all_valid)
+{
+	return schnorr_msm_host(ctx, 2, n, sigs, pubkeys, digests, hlen, seed, all_valid);
 }
 
 /* ------------------------------------------------------------------------------------------ sign / ECC-CDH (§8f) */

@@ -479,6 +479,47 @@ template <class F> struct Field : FieldCore<F> {
 		r = acc;
 	}
 
+	/*
+	 * r = a^((m+1)/4) (Montgomery in, Montgomery out): for a prime m = 3 mod 4 this is a square root of a whenever a
+	 * is a square; returns r^2 == a.  4-bit fixed window over the constant exponent (m >> 2) + 1.  The reference's
+	 * fp_sqrt (fp/fp_sqrt.c, Tonelli-Shanks) returns the same pair {r, m - r}; callers pick by parity.
+	 */
+	static ECC_HD bool sqrt_3mod4(E &r, const E &a)
+	{
+		uint32_t ex[N];
+		uint64_t cy = 1;
+#pragma unroll
+		for (int i = 0; i < N; i++) {
+			const uint32_t hi = i + 1 < N ? F::P(i + 1 < N ? i + 1 : 0) : 0u;
+			const uint64_t t = (uint64_t)((F::P(i) >> 2) | (hi << 30)) + cy;
+			ex[i] = (uint32_t)t;
+			cy = t >> 32;
+		}
+		E tbl[16];
+		set_one(tbl[0]);
+		tbl[1] = a;
+#pragma unroll 1
+		for (int i = 2; i < 16; i++) mul(tbl[i], tbl[i - 1], a);
+		E acc;
+		set_one(acc);
+#pragma unroll 1
+		for (int wi = N - 1; wi >= 0; wi--) {
+			uint32_t ew = 0;
+#pragma unroll
+			for (int k = 0; k < N; k++) ew = (k == wi) ? ex[k] : ew;
+#pragma unroll 1
+			for (int nb = 7; nb >= 0; nb--) {
+#pragma unroll 1
+				for (int q = 0; q < 4; q++) sqr(acc, acc);
+				mul(acc, acc, tbl[(ew >> (4 * nb)) & 15u]);
+			}
+		}
+		r = acc;
+		E chk;
+		sqr(chk, acc);
+		return eq(chk, a);
+	}
+
       private:
 	static ECC_HD uint32_t pm2_word(int i)
 	{

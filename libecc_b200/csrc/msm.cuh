@@ -11,11 +11,11 @@
  *                                    (k_msm_hist, k_msm_scan_*, k_msm_scatter, k_msm_order_hist / k_msm_order_scatter)
  *   accumulate  one thread per bucket: a chain of XYZZ mixed additions (madd-2008-s, 8M + 2S — the addition of the
  *               fixed-base comb) over the bucket's points; this is where the time goes        (k_msm_accumulate)
- *   reduce      running sums over ranges of 8 buckets, a tree per window, Horner over the windows on one thread
+ *   reduce      running sums over ranges of 16 buckets, a tree per window, Horner over the windows on one thread
  *                                                             (k_msm_reduce, k_msm_window_sum, k_msm_final)
  *
  * HBM layout: pts [2n+1][2N] words, scal [2n+1][N] words, list [<= n (nwin_a + nwin) + nwin] u32 (bit 31 = negate),
- * count / offs / fill [nwin 2^(c-1)] u32, buckets [nwin 2^(c-1)][3N] words, parts [nwin 2^(c-1) / 8][3N], winsum [nwin][3N].
+ * count / offs / fill [nwin 2^(c-1)] u32, buckets [nwin 2^(c-1)][3N] words, parts [nwin 2^(c-1) / 16][3N], winsum [nwin][3N].
  * Integer work on the multiplier pipe (one accumulate thread issues the same instruction stream as K1's loop body);
  * DRAM traffic is ~26 random 64-byte point reads per signature, far from the HBM roof.
  */
@@ -32,14 +32,20 @@ struct MsmBuffers {
 	int *flags; /* [0] = a malformed item was seen, [1] = the verdict (1 = the batch verifies) */
 };
 
-/* ECFSDSA: sigs [n][2 PLEN + QLEN], pubkeys [n][2 PLEN] affine, digests [n][hlen] = H(W_x || W_y || m) */
-template <class C>
+/*
+ * SCHEME 1, ECFSDSA: sigs [n][2 PLEN + QLEN] = W_x || W_y || s, digests [n][hlen] = H(W_x || W_y || m)
+ * SCHEME 2, BIP0340: sigs [n][PLEN + QLEN] = r || s with r = x(R), digests = the tagged challenge hash; R is lifted from r
+ *                    and the key to its even-y representative (sig/bip0340.c:1166-1215)
+ * pubkeys [n][2 PLEN] affine.
+ */
+template <class C, int SCHEME>
 __global__ void __launch_bounds__(128) k_msm_prepare(uint32_t n, const uint8_t *__restrict__ sigs,
 						     const uint8_t *__restrict__ pubkeys,
 						     const uint8_t *__restrict__ digests, uint32_t hlen, MsmKey key,
 						     int c, uint32_t *__restrict__ pts, uint32_t *__restrict__ scal,
 						     uint32_t *__restrict__ partial, int *__restrict__ flags)
 {
+	typedef Field<typename C::Fp> F;
 	typedef Field<typename C::Fq> Fq;
 	constexpr int N = C::N;
 	__shared__ __align__(16) uint32_t sh[128 * N];
@@ -47,15 +53,30 @@ __global__ void __launch_bounds__(128) k_msm_prepare(uint32_t n, const uint8_t *
 	Fe<N> t;
 	Fq::set_zero(t);
 	if (idx < n) {
-		const uint8_t *sg = sigs + (size_t)idx * (2 * C::PLEN + C::QLEN);
 		Aff<C> W, Y, negW, Yf;
 		Fe<N> s, h, a, cY;
-		const bool w_ok = load_affine_checked<C>(W, sg);                          /* (sig/ecfsdsa.c:983) */
-		load_wire<N, C::QLEN>(s, sg + 2 * C::PLEN);
-		const bool s_ok = !Fq::geq_mod(s);                                       /* s < q (:919-921) */
-		const bool key_ok = load_affine_checked<C>(Y, pubkeys + (size_t)idx * (2 * C::PLEN)); /* (:941-942) */
-		digest_full_mod_q<C>(h, digests + (size_t)idx * hlen, hlen);             /* (:953-961) */
-		Fq::neg(h, h);                                                           /* (:962) */
+		bool w_ok, s_ok, key_ok;
+		const uint8_t *pkb = pubkeys + (size_t)idx * (2 * C::PLEN);
+		if (SCHEME == 2) {
+			const uint8_t *sg = sigs + (size_t)idx * (C::PLEN + C::QLEN);
+			Fe<N> r, yraw;
+			load_wire<N, C::PLEN>(r, sg);
+			load_wire<N, C::QLEN>(s, sg + C::PLEN);
+			w_ok = !F::geq_mod(r);                                   /* fp_import_from_buf (sig/bip0340.c:1168) */
+			if (!w_ok) F::set_zero(r);
+			w_ok = msm_lift_x<C>(W, r) && w_ok;                      /* (:1188-1196) */
+			load_wire<N, C::PLEN>(yraw, pkb + C::PLEN);
+			key_ok = load_affine_checked<C>(Y, pkb);
+			if (yraw.w[0] & 1u) F::neg(Y.y, Y.y);                    /* (:1208-1213) */
+		} else {
+			const uint8_t *sg = sigs + (size_t)idx * (2 * C::PLEN + C::QLEN);
+			w_ok = load_affine_checked<C>(W, sg);                    /* (sig/ecfsdsa.c:983) */
+			load_wire<N, C::QLEN>(s, sg + 2 * C::PLEN);
+			key_ok = load_affine_checked<C>(Y, pkb);                 /* (:941-942) */
+		}
+		s_ok = !Fq::geq_mod(s);                                          /* s < q (sig/ecfsdsa.c:919-921, sig/bip0340.c:1171-1172) */
+		digest_full_mod_q<C>(h, digests + (size_t)idx * hlen, hlen);     /* (sig/ecfsdsa.c:953-961) */
+		Fq::neg(h, h);                                                   /* (:962) */
 		msm_coefficient<N>(a, key, idx, c);
 		msm_terms<C>(negW, Yf, cY, t, W, Y, s, h, a);
 		if (!(w_ok && s_ok && key_ok)) {
@@ -335,26 +356,34 @@ __global__ void k_msm_final(int nwin, int c, const uint32_t *__restrict__ winsum
 }
 
 template <class C> struct LaunchMsm {
-	/* enqueues the whole verification of n ECFSDSA signatures; flags[1] holds the verdict when the stream drains.
-	 * Returns the number of kernels launched. */
-	static int ecfsdsa(uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys, const uint8_t *digests, uint32_t hlen,
-			   const MsmKey &key, int c, const MsmBuffers &b, cudaStream_t st);
+	/* enqueues the whole verification of n signatures (scheme 1 ECFSDSA, 2 BIP0340); flags[1] holds the verdict when the
+	 * stream drains.  Returns the number of kernels launched, -1 when the scheme cannot run on this curve (BIP0340 needs
+	 * p = 3 mod 4 for the lift of r). */
+	static int verify(int scheme, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys, const uint8_t *digests,
+			  uint32_t hlen, const MsmKey &key, int c, const MsmBuffers &b, cudaStream_t st);
 };
 
 #if defined(ECC_TU_MSM)
 template <class C>
-int LaunchMsm<C>::ecfsdsa(uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys, const uint8_t *digests, uint32_t hlen,
-			  const MsmKey &key, int c, const MsmBuffers &b, cudaStream_t st)
+int LaunchMsm<C>::verify(int scheme, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys, const uint8_t *digests,
+			 uint32_t hlen, const MsmKey &key, int c, const MsmBuffers &b, cudaStream_t st)
 {
+	if (scheme == 2 && !msm_lift_supported<C>()) return -1;
 	const int nwin = msm_windows(C::QBITS - 1, c);
-	const uint32_t nb = 1u << (c - 1), total = (uint32_t)nwin * nb, ch = nb < 8u ? nb : 8u, per_window = nb / ch,
+	const uint32_t nb = 1u << (c - 1), total = (uint32_t)nwin * nb, ch = nb < 16u ? nb : 16u, per_window = nb / ch,
 		       nparts = (uint32_t)nwin * per_window, npts = 2 * n + 1, nblk = (n + 127) / 128,
 		       tiles = (total + 1023u) / 1024u;
 	cudaMemsetAsync(b.count, 0, (size_t)total * 4, st);
 	cudaMemsetAsync(b.fill, 0, (size_t)total * 4, st);
 	cudaMemsetAsync(b.aux, 0, 3072 * 4, st);
 	cudaMemsetAsync(b.flags, 0, 2 * sizeof(int), st);
-	k_msm_prepare<C><<<nblk, 128, 0, st>>>(n, sigs, pubkeys, digests, hlen, key, c, b.pts, b.scal, b.partial, b.flags);
+	if (scheme == 2) {
+		if constexpr (msm_lift_supported<C>())
+			k_msm_prepare<C, 2><<<nblk, 128, 0, st>>>(n, sigs, pubkeys, digests, hlen, key, c, b.pts, b.scal, b.partial,
+								   b.flags);
+	} else {
+		k_msm_prepare<C, 1><<<nblk, 128, 0, st>>>(n, sigs, pubkeys, digests, hlen, key, c, b.pts, b.scal, b.partial, b.flags);
+	}
 	k_msm_ssum<C><<<1, 128, 0, st>>>(nblk, b.partial, n, b.pts, b.scal);
 	k_msm_hist<C><<<(npts + 255) / 256, 256, 0, st>>>(npts, b.scal, c, nwin, b.count);
 	k_msm_scan_tiles<C><<<tiles, 256, 0, st>>>(total, b.count, b.offs, b.aux);

@@ -217,6 +217,26 @@ ECC_HD void msm_terms(Aff<C> &negW, Aff<C> &Yf, Fe<C::N> &cY, Fe<C::N> &t, const
 	if (msm_fold<C>(cY)) F::neg(Yf.y, Y.y);
 }
 
+/*
+ * BIP0340 (sig/bip0340.c:1166-1200): the signature carries only r = x(R); the batch form needs the point, so R is lifted
+ * from r with the even y (aff_pt_y_from_x + the parity choice, :1188-1196).  r: plain integer < p.  Returns false when
+ * r^3 + a r + b is not a square (the reference's fp_sqrt fails and the batch is rejected).  Primes p = 3 mod 4 only
+ * (every curve of this library except SECP224R1): one exponentiation instead of Tonelli-Shanks.
+ */
+template <class C> ECC_HD bool msm_lift_x(Aff<C> &R, const Fe<C::N> &r)
+{
+	typedef Field<typename C::Fp> F;
+	Fe<C::N> v, y, yp;
+	F::to_mont(R.x, r);
+	EC<C>::curve_rhs(v, R.x);
+	const bool ok = F::sqrt_3mod4(y, v);
+	F::from_mont(yp, y);
+	if (yp.w[0] & 1u) F::neg(y, y);
+	R.y = y;
+	return ok;
+}
+template <class C> ECC_HD constexpr bool msm_lift_supported() { return (C::Fp::P(0) & 3u) == 3u; }
+
 /* ---------------------------------------------------------------------------------------------- bucket reduction */
 
 /*

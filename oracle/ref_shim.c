@@ -434,15 +434,15 @@ int ref_sig_sign_batch(const char *curve, const char *alg_name, const char *hash
 /* The reference's own batch entry point, ec_verify_batch(…, ECFSDSA, …) (sig/sig_algs.c:675 -> sig/ecfsdsa.c:1057):
  * one 0 / -1 answer for the whole batch.  use_scratch = 0: no scratch pad, the reference verifies the signatures one
  * after the other (sig/ecfsdsa.c:711); use_scratch = 1: its Bos-Coster multi-scalar multiplication (:842). */
-int ref_ecfsdsa_verify_batch_all(const char *curve, const char *hash, uint32_t n, const uint8_t *sigs,
-				 const uint8_t *pubkeys, const uint8_t *msgs, const uint64_t *off, int use_scratch)
+static int verify_batch_all(ec_alg_type alg, const char *curve, const char *hash, uint32_t n, const uint8_t *sigs,
+			    const uint8_t *pubkeys, const uint8_t *msgs, const uint64_t *off, int use_scratch)
 {
 	ref_curve c;
 	hash_alg_type ht;
 	u8 dlen;
 	int ret = -1;
 	if (ref_load_curve(&c, curve) || ref_hash_type(hash, &ht, &dlen) || n == 0) return -2;
-	const uint32_t siglen = 2 * c.plen + c.qlen;
+	const uint32_t siglen = (alg == BIP0340 ? c.plen : 2 * c.plen) + c.qlen;
 	ec_pub_key *pks = (ec_pub_key *)calloc(n, sizeof(ec_pub_key));
 	const ec_pub_key **pkp = (const ec_pub_key **)calloc(n, sizeof(void *));
 	const u8 **sp = (const u8 **)calloc(n, sizeof(void *)), **mp = (const u8 **)calloc(n, sizeof(void *));
@@ -451,8 +451,7 @@ int ref_ecfsdsa_verify_batch_all(const char *curve, const char *hash, uint32_t n
 	u32 scratch_len = 0;
 	verify_batch_scratch_pad *scratch = NULL;
 	for (uint32_t i = 0; i < n; i++) {
-		if (ec_pub_key_import_from_aff_buf(&pks[i], &c.params, pubkeys + (size_t)i * 2 * c.plen, (u8)(2 * c.plen),
-						   ECFSDSA))
+		if (ec_pub_key_import_from_aff_buf(&pks[i], &c.params, pubkeys + (size_t)i * 2 * c.plen, (u8)(2 * c.plen), alg))
 			goto out;
 		pkp[i] = &pks[i];
 		sp[i] = sigs + (size_t)i * siglen;
@@ -466,10 +465,23 @@ int ref_ecfsdsa_verify_batch_all(const char *curve, const char *hash, uint32_t n
 		scratch_len = (u32)((2 * (size_t)n + 1) * sizeof(verify_batch_scratch_pad));
 		scratch = (verify_batch_scratch_pad *)calloc(1, scratch_len);
 	}
-	ret = ec_verify_batch(sp, sl, pkp, mp, ml, n, ECFSDSA, ht, NULL, NULL, scratch, &scratch_len) ? -1 : 0;
+	ret = ec_verify_batch(sp, sl, pkp, mp, ml, n, alg, ht, NULL, NULL, scratch, &scratch_len) ? -1 : 0;
 out:
 	free(pks); free(pkp); free(sp); free(mp); free(sl); free(ml); free(scratch);
 	return ret;
+}
+
+int ref_ecfsdsa_verify_batch_all(const char *curve, const char *hash, uint32_t n, const uint8_t *sigs,
+				 const uint8_t *pubkeys, const uint8_t *msgs, const uint64_t *off, int use_scratch)
+{
+	return verify_batch_all(ECFSDSA, curve, hash, n, sigs, pubkeys, msgs, off, use_scratch);
+}
+
+/* the same through the BIP0340 entry of ec_sig_maps[] (_bip0340_verify_batch, sig/bip0340.c:1040) */
+int ref_bip0340_verify_batch_all(const char *curve, const char *hash, uint32_t n, const uint8_t *sigs,
+				 const uint8_t *pubkeys, const uint8_t *msgs, const uint64_t *off, int use_scratch)
+{
+	return verify_batch_all(BIP0340, curve, hash, n, sigs, pubkeys, msgs, off, use_scratch);
 }
 
 /* ---------------------------------------------------------------- structured key / signature records (sig/ec_key.c) */

@@ -394,8 +394,8 @@ int hostsim_point_op(int curve_id, int which, const uint8_t *p1, const uint8_t *
  * stats (optional, 5 entries): mixed additions of the accumulation, buckets, windows, field products in total, the
  * fullest bucket.
  */
-int hostsim_ecfsdsa_msm(int curve_id, int c, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys, const uint8_t *digests,
-			uint32_t hlen, const uint8_t *seed, int *all_valid, unsigned long long *stats)
+int hostsim_schnorr_msm(int scheme, int curve_id, int c, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys,
+			const uint8_t *digests, uint32_t hlen, const uint8_t *seed, int *all_valid, unsigned long long *stats)
 {
 	return dispatch(curve_id, [&](auto cv) {
 		typedef decltype(cv) C;
@@ -405,6 +405,7 @@ int hostsim_ecfsdsa_msm(int curve_id, int c, uint32_t n, const uint8_t *sigs, co
 		constexpr int N = C::N;
 		*all_valid = 0;
 		if (n == 0 || c < 2 || c > 16) return n == 0 ? 0 : -1;
+		if (scheme == 2 && !msm_lift_supported<C>()) return -1;
 		g_fe_mul_count = 0;
 		MsmKey key;
 		for (int i = 0; i < 8; i++)
@@ -419,13 +420,28 @@ int hostsim_ecfsdsa_msm(int curve_id, int c, uint32_t n, const uint8_t *sigs, co
 		Fq::set_zero(ssum);
 		/* prepare (k_msm_prepare / k_msm_ssum) */
 		for (uint32_t i = 0; i < n; i++) {
-			const uint8_t *sg = sigs + (size_t)i * (2 * C::PLEN + C::QLEN);
 			Aff<C> W, Y, negW, Yf;
 			Fe<N> s, h, a, cY, t;
-			const bool w_ok = load_point<C>(W, sg);
-			load_be<N>(s, sg + 2 * C::PLEN, C::QLEN);
+			bool w_ok, key_ok;
+			const uint8_t *pkb = pubkeys + (size_t)i * 2 * C::PLEN;
+			if (scheme == 2) {
+				const uint8_t *sg = sigs + (size_t)i * (C::PLEN + C::QLEN);
+				Fe<N> r, yraw;
+				load_be<N>(r, sg, C::PLEN);
+				load_be<N>(s, sg + C::PLEN, C::QLEN);
+				w_ok = !F::geq_mod(r);
+				if (!w_ok) F::set_zero(r);
+				w_ok = msm_lift_x<C>(W, r) && w_ok;
+				load_be<N>(yraw, pkb + C::PLEN, C::PLEN);
+				key_ok = load_point<C>(Y, pkb);
+				if (yraw.w[0] & 1u) F::neg(Y.y, Y.y);
+			} else {
+				const uint8_t *sg = sigs + (size_t)i * (2 * C::PLEN + C::QLEN);
+				w_ok = load_point<C>(W, sg);
+				load_be<N>(s, sg + 2 * C::PLEN, C::QLEN);
+				key_ok = load_point<C>(Y, pkb);
+			}
 			const bool s_ok = !Fq::geq_mod(s);
-			const bool key_ok = load_point<C>(Y, pubkeys + (size_t)i * 2 * C::PLEN);
 			digest_full_mod_q<C>(h, digests + (size_t)i * hlen, hlen);
 			Fq::neg(h, h);
 			msm_coefficient<N>(a, key, i, c);
@@ -512,6 +528,36 @@ int hostsim_ecfsdsa_msm(int curve_id, int c, uint32_t n, const uint8_t *sigs, co
 			stats[4] = mx;
 		}
 		return 0;
+	});
+}
+
+int hostsim_ecfsdsa_msm(int curve_id, int c, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys, const uint8_t *digests,
+			uint32_t hlen, const uint8_t *seed, int *all_valid, unsigned long long *stats)
+{
+	return hostsim_schnorr_msm(1, curve_id, c, n, sigs, pubkeys, digests, hlen, seed, all_valid, stats);
+}
+
+int hostsim_bip0340_msm(int curve_id, int c, uint32_t n, const uint8_t *sigs, const uint8_t *pubkeys, const uint8_t *digests,
+			uint32_t hlen, const uint8_t *seed, int *all_valid, unsigned long long *stats)
+{
+	return hostsim_schnorr_msm(2, curve_id, c, n, sigs, pubkeys, digests, hlen, seed, all_valid, stats);
+}
+
+/* square root modulo p = 3 mod 4 as the lift of r uses it: out = sqrt(a) (either root), returns 1 when a is a square, 0
+ * when not, -1 for p = 1 mod 4.  a, out: PLEN big-endian bytes, plain integers. */
+int hostsim_fp_sqrt(int curve_id, const uint8_t *a, uint8_t *out)
+{
+	return dispatch(curve_id, [&](auto cv) {
+		typedef decltype(cv) C;
+		typedef Field<typename C::Fp> F;
+		if (!msm_lift_supported<C>()) return -1;
+		Fe<C::N> x, xm, r, rp;
+		load_be<C::N>(x, a, C::PLEN);
+		F::to_mont(xm, x);
+		const bool ok = F::sqrt_3mod4(r, xm);
+		F::from_mont(rp, r);
+		store_be<C::N>(out, rp, C::PLEN);
+		return ok ? 1 : 0;
 	});
 }
 

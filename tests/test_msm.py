@@ -142,6 +142,80 @@ def test_work_per_signature():
     assert fullest <= 20
 
 
+# ------------------------------------------------------------------------------------------------------------- BIP0340
+
+
+def host_msm_bip(curve, c, sigs, pubs, dg, hlen, seed=SEED):
+    lib = hostsim_lib()
+    ok = ctypes.c_int(-1)
+    sg = np.ascontiguousarray(sigs, dtype=np.uint8)
+    rc = lib.hostsim_bip0340_msm(ALL_CURVES[curve][0], c, sg.shape[0], _buf(sg), _buf(np.ascontiguousarray(pubs)),
+                                 _buf(np.ascontiguousarray(dg)), hlen, seed, ctypes.byref(ok), None)
+    return rc, ok.value
+
+
+def test_square_root_of_the_lift():
+    from common import PRIME
+    lib = hostsim_lib()
+    g = rng(9500)
+    for curve in ("SECP256K1", "FRP256V1", "SECP384R1", "SECP521R1", "BRAINPOOLP512R1", "SECP192R1"):
+        p = PRIME[curve]
+        plen = ALL_CURVES[curve][1]
+        assert p % 4 == 3
+        for x in [0, 1, 4, p - 1] + [int.from_bytes(g.bytes(plen), "big") % p for _ in range(12)]:
+            out = (ctypes.c_uint8 * plen)()
+            rc = lib.hostsim_fp_sqrt(ALL_CURVES[curve][0], x.to_bytes(plen, "big"), out)
+            is_square = x == 0 or pow(x, (p - 1) // 2, p) == 1
+            assert rc == (1 if is_square else 0), (curve, x)
+            if is_square:
+                assert pow(int.from_bytes(bytes(out), "big"), 2, p) == x
+    out = (ctypes.c_uint8 * 28)()
+    assert lib.hostsim_fp_sqrt(ALL_CURVES["SECP224R1"][0], bytes(28), out) == -1      # p = 1 mod 4: not served
+
+
+@pytest.mark.parametrize("curve,hash_name,c", [("SECP256K1", "SHA256", 5), ("FRP256V1", "SHA256", 4),
+                                               ("SECP256R1", "SHA512", 8), ("SECP384R1", "SHA384", 6)])
+def test_host_bip0340_algorithm_against_reference(curve, hash_name, c):
+    if ref_lib() is None:
+        pytest.skip("compiled reference not available")
+    import test_bip0340 as tb
+    _, plen, qlen = ALL_CURVES[curve]
+    sigs, pubs, dg, hlen, want = tb.workload(curve, 28, 9600, hash_name)
+    good = np.flatnonzero(want == 0)            # includes the items whose key was negated: the scheme only sees x(Y)
+    assert host_msm_bip(curve, c, sigs[good], pubs[good], dg[good], hlen) == (0, 1)
+    for bad in np.flatnonzero(want != 0):
+        idx = np.concatenate([good[:5], [bad], good[5:9]])
+        assert host_msm_bip(curve, c, sigs[idx], pubs[idx], dg[idx], hlen) == (0, 0), (curve, int(bad))
+    assert host_msm_bip(curve, c, sigs[good[:1]], pubs[good[:1]], dg[good[:1]], hlen) == (0, 1)
+    rep = np.repeat(good[:3], 12)
+    assert host_msm_bip(curve, 2, sigs[rep], pubs[rep], dg[rep], hlen) == (0, 1)
+    # the reference's own batch entry point on the same valid batch, and with one corrupted signature
+    ref = ref_lib()
+    privs = __import__("common").random_scalars(curve, 10, tag=9700)
+    msgs = [b"bip batch %d" % i for i in range(10)]
+    s2, p2 = tb.ref_sign(curve, hash_name, privs, msgs)
+    blob, off = tb.pack(msgs)
+    d2 = np.stack([tb.challenge(hash_name, s2[i, :plen], p2[i, :plen], msgs[i]) for i in range(10)])
+    for scratch in (0, 1):
+        assert ref.ref_bip0340_verify_batch_all(curve.encode(), hash_name.encode(), 10, _buf(s2), _buf(p2), _buf(blob),
+                                                _buf(off), scratch) == 0
+    assert host_msm_bip(curve, c, s2, p2, d2, d2.shape[1]) == (0, 1)
+    s2[4, -1] ^= 1
+    # NOTE: only the reference's scratch-pad-free form (_bip0340_verify_batch_no_memory: the same linear combination,
+    # summed directly) is the anchor on corrupted batches.  Its Bos-Coster form (with a scratch pad) was observed here to
+    # return 0 for a batch whose s_4 is corrupted - ec_verify_bos_coster (sig/sig_algs.c:1052) leaves its loop as soon as
+    # the two largest scalars are equal and then multiplies by their difference, 0 - so it is deliberately not asserted.
+    assert ref.ref_bip0340_verify_batch_all(curve.encode(), hash_name.encode(), 10, _buf(s2), _buf(p2), _buf(blob),
+                                            _buf(off), 0) == -1
+    assert (tb.ref_verify(curve, hash_name, s2, p2, msgs) == [0, 0, 0, 0, -1, 0, 0, 0, 0, 0]).all()
+    assert host_msm_bip(curve, c, s2, p2, d2, d2.shape[1]) == (0, 0)
+
+
+def test_host_bip0340_msm_not_on_secp224r1():
+    assert host_msm_bip("SECP224R1", 4, np.zeros((1, 56), np.uint8), np.zeros((1, 56), np.uint8),
+                        np.zeros((1, 32), np.uint8), 32)[0] == -1
+
+
 # ------------------------------------------------------------------------------------------------------------- GPU
 
 
@@ -200,4 +274,44 @@ def test_gpu_msm_full_size_properties(log2n):
         assert eng.ecfsdsa_verify_msm_batch(S, P, D, hlen) is False, (kind, i)
         arr[i, -1] ^= 1
     assert eng.ecfsdsa_verify_msm_batch(S, P, D, hlen, SEED) is True
+    eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("curve", [c for c in ALL_CURVES])
+def test_gpu_bip0340_msm_against_reference(curve, monkeypatch):
+    import libecc_b200
+    import test_bip0340 as tb
+    if ref_lib() is None:
+        pytest.skip("compiled reference not available")
+    eng = libecc_b200.Engine(curve, comb_window=8)
+    sigs, pubs, dg, hlen, want = tb.workload(curve, 96, 9800)
+    good = np.flatnonzero(want == 0)
+    if curve == "SECP224R1":            # p = 1 mod 4: the lift of r is not served, the per-item kernel is
+        with pytest.raises(libecc_b200.EccB200Error, match="3 mod 4"):
+            eng.bip0340_verify_msm_batch(sigs[good], pubs[good], dg[good], hlen, SEED)
+        assert (eng.bip0340_verify_batch(sigs, pubs, dg, hlen) == want).all()
+        eng.close()
+        return
+    for c in (None, 3, 9, 16):
+        if c is None:
+            monkeypatch.delenv("ECCB200_MSM_WINDOW", raising=False)
+        else:
+            monkeypatch.setenv("ECCB200_MSM_WINDOW", str(c))
+        assert eng.bip0340_verify_msm_batch(sigs[good], pubs[good], dg[good], hlen, SEED) is True, (curve, c)
+        assert eng.bip0340_verify_msm_batch(sigs[good], pubs[good], dg[good], hlen) is True
+        assert eng.bip0340_verify_msm_batch(sigs, pubs, dg, hlen, SEED) is False
+        for bad in np.flatnonzero(want != 0)[:7]:
+            idx = np.concatenate([good[:9], [bad], good[9:30]])
+            assert eng.bip0340_verify_msm_batch(sigs[idx], pubs[idx], dg[idx], hlen, SEED) is False, (curve, c, int(bad))
+        rep = np.repeat(good[:4], 40)
+        assert eng.bip0340_verify_msm_batch(sigs[rep], pubs[rep], dg[rep], hlen, SEED) is True
+    monkeypatch.delenv("ECCB200_MSM_WINDOW", raising=False)
+    assert (eng.bip0340_verify_batch(sigs, pubs, dg, hlen) == want).all()
+    # 2^16 tiled signatures: accepted as a whole; one flipped bit sinks the batch
+    idx = np.resize(good, 1 << 16)
+    S, P, D = sigs[idx].copy(), pubs[idx].copy(), dg[idx].copy()
+    assert eng.bip0340_verify_msm_batch(S, P, D, hlen) is True
+    S[31337, -1] ^= 1
+    assert eng.bip0340_verify_msm_batch(S, P, D, hlen) is False
     eng.close()
