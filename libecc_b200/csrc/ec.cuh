@@ -281,6 +281,10 @@ template <class C> struct EC {
 		r.Z = z3;
 	}
 
+	/* out-of-line copy of add_full for code that adds up many points outside the hot loops (bucket reduction of the
+	 * multi-scalar multiplication): one body per kernel instead of one per call site */
+	static ECC_NOINLINE void add_full_ool(J &r, const J &p, const J &q) { add_full(r, p, q); }
+
 	static ECC_HD void neg(J &r, const J &p)
 	{
 		r.X = p.X;

@@ -331,14 +331,14 @@ __global__ void __launch_bounds__(128) k_msm_window_sum(uint32_t per_window, con
 	G::set_inf(acc);
 	for (uint32_t i = threadIdx.x; i < per_window; i += blockDim.x) {
 		msm_ld_jac<C>(o, parts, (size_t)blockIdx.x * per_window + i);
-		G::add_full(acc, acc, o);
+		G::add_full_ool(acc, acc, o);
 	}
 	msm_st_jac<C>(sh, threadIdx.x, acc);
 	for (int step = 64; step > 0; step >>= 1) {
 		__syncthreads();
 		if ((int)threadIdx.x < step) {
 			msm_ld_jac<C>(o, sh, threadIdx.x + step);
-			G::add_full(acc, acc, o);
+			G::add_full_ool(acc, acc, o);
 			msm_st_jac<C>(sh, threadIdx.x, acc);
 		}
 	}

@@ -253,8 +253,8 @@ ECC_HD void msm_reduce_range(Jac<C> &out, const uint32_t *buckets, size_t first_
 	G::set_inf(tot);
 	for (uint32_t b = ch; b-- > 0;) {
 		msm_ld_jac<C>(bk, buckets, first_bucket + lo + b);
-		G::add_full(run, run, bk);
-		G::add_full(tot, tot, run);
+		G::add_full_ool(run, run, bk);
+		G::add_full_ool(tot, tot, run);
 	}
 	if (lo) {
 		Jac<C> m;
@@ -263,9 +263,9 @@ ECC_HD void msm_reduce_range(Jac<C> &out, const uint32_t *buckets, size_t first_
 		while (!((lo >> top) & 1u)) top--;
 		for (int bit = top; bit >= 0; bit--) {
 			G::dbl(m, m);
-			if ((lo >> bit) & 1u) G::add_full(m, m, run);
+			if ((lo >> bit) & 1u) G::add_full_ool(m, m, run);
 		}
-		G::add_full(tot, tot, m);
+		G::add_full_ool(tot, tot, m);
 	}
 	out = tot;
 }
@@ -279,7 +279,7 @@ template <class C> ECC_HD void msm_horner(Jac<C> &acc, const uint32_t *winsum, i
 	for (int w = nwin - 2; w >= 0; w--) {
 		for (int i = 0; i < c; i++) G::dbl(acc, acc);
 		msm_ld_jac<C>(s, winsum, (size_t)w);
-		G::add_full(acc, acc, s);
+		G::add_full_ool(acc, acc, s);
 	}
 }
 
