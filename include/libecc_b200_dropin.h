@@ -214,6 +214,11 @@ unsigned long long eccb200_dropin_call_count(void);
 /* Signatures verified on the GPU by this layer (ec_verify shim and verify_batch adapters). */
 unsigned long long eccb200_dropin_verify_count(void);
 
+/* ECFSDSA / BIP0340 batches of at least 16384 signatures (ECCB200_DROPIN_MSM_MIN) are first checked as ONE multi-scalar
+ * multiplication (eccb200_*_verify_msm_batch, include/libecc_b200.h); a batch that passes is settled there, a batch that
+ * fails goes through the per-item kernel to find the culprit.  This counts the batches settled by the fast path. */
+unsigned long long eccb200_dropin_msm_batches(void);
+
 /* Device the drop-in layer uses (default 0; also settable with the ECCB200_DEVICE environment variable). */
 int eccb200_dropin_set_device(int device);
 

@@ -139,6 +139,7 @@ struct CurveEngines {
 CurveEngines g_eng[32]; /* indexed by the reference's ec_curve_type (< 32 here) */
 std::atomic<unsigned long long> g_calls{ 0 };   /* scalar multiplications served (eccb200_dropin_call_count) */
 std::atomic<unsigned long long> g_verifies{ 0 }; /* signatures verified on the GPU (eccb200_dropin_verify_count) */
+std::atomic<unsigned long long> g_msm_batches{ 0 }; /* batches settled by the multi-scalar-multiplication fast path */
 std::atomic<int> g_device{ -1 };
 std::atomic<int> g_blind_on_gpu{ -1 };
 
@@ -500,6 +501,8 @@ extern "C" int prj_pt_mul_blind(eccb200_prj_pt *out, const eccb200_nn *m, const 
 }
 
 extern "C" unsigned long long eccb200_dropin_call_count(void) { return g_calls.load(); }
+extern "C" unsigned long long eccb200_dropin_msm_batches(void) { return g_msm_batches.load(); }
+
 extern "C" unsigned long long eccb200_dropin_verify_count(void) { return g_verifies.load(); }
 
 extern "C" uint32_t eccb200_dropin_last_verdicts(int8_t *verdicts, uint32_t cap)
@@ -527,6 +530,20 @@ static bool scheme_of(int sig_type, Scheme *sc)
 	else if (sig_type == 20) *sc = kBip0340;
 	else return false;
 	return true;
+}
+
+/* batches settled by the multi-scalar-multiplication fast path (eccb200_dropin_msm_batches) and its threshold: below
+ * it the fixed cost of the bucket method (14 launches, a serial Horner tail of ~1 ms) outweighs one wave of the per-item
+ * kernel; ECCB200_DROPIN_MSM_MIN overrides (0 disables the fast path). */
+static uint32_t msm_min_batch()
+{
+	static const uint32_t v = [] {
+		const char *e = getenv("ECCB200_DROPIN_MSM_MIN");
+		if (!e) return 16384u;
+		const long long x = atoll(e);
+		return x <= 0 ? 0xffffffffu : (uint32_t)std::min<long long>(x, 0xffffffffll);
+	}();
+	return v;
 }
 
 /*
@@ -657,10 +674,46 @@ static int verify_batch_common(Scheme sc, const uint8_t **s, const uint8_t *s_le
 		});
 	}
 	memset(verdict, 0xff, num);
-	int rc;
-	if (sc == kEcfsdsa) rc = eccb200_ecfsdsa_verify_batch(eng, num, sigs, pubs, dig, hlen, verdict);
-	else if (sc == kBip0340) rc = eccb200_bip0340_verify_batch(eng, num, sigs, pubs, dig, hlen, verdict);
-	else rc = eccb200_ecdsa_verify_prj_batch(eng, num, sigs, pubs, dig, hlen, verdict);
+	int rc = 0;
+	/*
+	 * ECFSDSA / BIP0340, large batches: first the whole batch as ONE multi-scalar multiplication (K6 — what the reference's
+	 * own verify_batch computes with Bos-Coster, ~7x cheaper on the device than n individual verifications).  When it
+	 * passes, every signature is valid; when it fails (or an item was already refused above, or s = 0, which the per-item
+	 * ECFSDSA check excludes and the combination does not), the per-item kernel runs to say WHICH one is bad.
+	 */
+	bool settled = false;
+	if ((sc == kEcfsdsa || sc == kBip0340) && num >= msm_min_batch()) {
+		bool clean = true;
+		for (uint32_t i = 0; i < num && clean; i++) clean = ok[i] != 0;
+		if (clean && sc == kEcfsdsa) {
+			std::atomic<int> zero_s{ 0 };
+			parallel_for(num, [&](uint32_t lo, uint32_t hi, unsigned) {
+				for (uint32_t i = lo; i < hi; i++) {
+					const uint8_t *sb = &sigs[i * siglen + 2 * plen];
+					uint8_t acc = 0;
+					for (size_t j = 0; j < qlen; j++) acc |= sb[j];
+					if (!acc) zero_s.store(1);
+				}
+			});
+			clean = zero_s.load() == 0;
+		}
+		if (clean) {
+			int all_valid = 0;
+			const int r = sc == kEcfsdsa
+					      ? eccb200_ecfsdsa_verify_msm_batch(eng, num, sigs, pubs, dig, hlen, nullptr, &all_valid)
+					      : eccb200_bip0340_verify_msm_batch(eng, num, sigs, pubs, dig, hlen, nullptr, &all_valid);
+			if (r == 0 && all_valid == 1) { /* r != 0: not served on this curve (BIP0340 on SECP224R1) */
+				memset(verdict, 0, num);
+				settled = true;
+				g_msm_batches += 1;
+			}
+		}
+	}
+	if (!settled) {
+		if (sc == kEcfsdsa) rc = eccb200_ecfsdsa_verify_batch(eng, num, sigs, pubs, dig, hlen, verdict);
+		else if (sc == kBip0340) rc = eccb200_bip0340_verify_batch(eng, num, sigs, pubs, dig, hlen, verdict);
+		else rc = eccb200_ecdsa_verify_prj_batch(eng, num, sigs, pubs, dig, hlen, verdict);
+	}
 	if (rc) return -1;
 	g_verifies += num;
 	int all = 0;

@@ -81,6 +81,7 @@ struct eccb200_ctx {
 	/* K6 (msm.cuh): work buffers of the multi-scalar-multiplication batch verification, grown on demand */
 	MsmBuffers msm = {};
 	uint32_t msm_cap_n = 0, msm_cap_total = 0;
+	size_t msm_cap_list = 0;
 	uint8_t *msm_in = nullptr; /* device copy of the host-pointer entry point's inputs */
 	size_t msm_in_bytes = 0;
 	/* optional per-kernel timing of the device-pointer API (bench.py's roofline leg) */
@@ -287,6 +288,7 @@ static void msm_release(eccb200_ctx *ctx)
 	if (ctx->msm.flags) cudaFree(ctx->msm.flags);
 	ctx->msm = MsmBuffers{};
 	ctx->msm_cap_n = ctx->msm_cap_total = 0;
+	ctx->msm_cap_list = 0;
 }
 
 extern "C" void eccb200_ctx_destroy(eccb200_ctx *ctx)
@@ -1250,20 +1252,19 @@ static int msm_ensure(eccb200_ctx *ctx, uint32_t n, int c)
 	const int qbits = (int)ctx->qlen * 8; /* upper bound of bitlen(q): only sizes buffers */
 	const int nwin = msm_windows(qbits - 1, c);
 	const uint32_t nb = 1u << (c - 1), total = (uint32_t)nwin * nb;
-	if (n <= ctx->msm_cap_n && total <= ctx->msm_cap_total) return 0;
+	/* list: every W_i owns at most ceil(128 / c) non-zero digits, every Y_i and the generator at most nwin */
+	const size_t list_need = (size_t)n * (size_t)(msm_windows(msm_coefficient_bits(c), c) + nwin) + (size_t)nwin;
+	if (n <= ctx->msm_cap_n && total <= ctx->msm_cap_total && list_need <= ctx->msm_cap_list) return 0;
 	const uint32_t cap_n = std::max(n, ctx->msm_cap_n), cap_total = std::max(total, ctx->msm_cap_total);
+	const size_t cap_list = std::max(list_need, ctx->msm_cap_list);
 	cudaDeviceSynchronize();
 	msm_release(ctx);
 	const size_t N = (size_t)ctx->N, npts = 2 * (size_t)cap_n + 1;
-	/* list: every W_i owns at most nwin_a non-zero digits, every Y_i and the generator at most the full count; sized for
-	 * the narrowest window (most digits) any later call with this capacity may pick */
-	const size_t list_cap = (size_t)cap_n * (size_t)(msm_windows(msm_coefficient_bits(2), 2) + msm_windows(qbits - 1, 2)) +
-				(size_t)msm_windows(qbits - 1, 2);
 	MsmBuffers &b = ctx->msm;
 	if (cudaMalloc(&b.pts, npts * 2 * N * 4) != cudaSuccess || cudaMalloc(&b.scal, npts * N * 4) != cudaSuccess ||
 	    cudaMalloc(&b.partial, ((size_t)cap_n / 128 + 1) * N * 4) != cudaSuccess ||
 	    cudaMalloc(&b.count, (size_t)cap_total * 4) != cudaSuccess || cudaMalloc(&b.offs, (size_t)cap_total * 4) != cudaSuccess ||
-	    cudaMalloc(&b.fill, (size_t)cap_total * 4) != cudaSuccess || cudaMalloc(&b.list, list_cap * 4) != cudaSuccess ||
+	    cudaMalloc(&b.fill, (size_t)cap_total * 4) != cudaSuccess || cudaMalloc(&b.list, cap_list * 4) != cudaSuccess ||
 	    cudaMalloc(&b.buckets, (size_t)cap_total * 3 * N * 4) != cudaSuccess ||
 	    cudaMalloc(&b.parts, (size_t)cap_total * 3 * N * 4) != cudaSuccess ||
 	    cudaMalloc(&b.winsum, (size_t)msm_windows(qbits - 1, 2) * 3 * N * 4) != cudaSuccess ||
@@ -1275,6 +1276,7 @@ static int msm_ensure(eccb200_ctx *ctx, uint32_t n, int c)
 	}
 	ctx->msm_cap_n = cap_n;
 	ctx->msm_cap_total = cap_total;
+	ctx->msm_cap_list = cap_list;
 	return 0;
 }
 
@@ -1302,7 +1304,7 @@ static int schnorr_msm_dev(eccb200_ctx *ctx, int scheme, uint32_t n, const uint8
 {
 	*all_valid = 0;
 	if (n == 0) return 0; /* the reference's implementations reject an empty batch (sig/ecfsdsa.c:740) */
-	if (n > 0x3fffffffu) return fail("batch too large");
+	if (n > (1u << 26)) return fail("batch too large for one multi-scalar multiplication (2^26 signatures): split it");
 	MsmKey key;
 	if (msm_seed(key, seed)) return -1;
 	int flags[2] = { 0, 0 };

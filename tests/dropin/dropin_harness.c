@@ -458,26 +458,32 @@ static double now_s(void)
 	return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
-static int run_bench(const char *dropin_path, const char *curve, u32 n)
+static int run_bench(const char *dropin_path, const char *curve, u32 n, const char *scheme, u32 bad_every)
 {
 	void *h = dlopen(dropin_path, RTLD_NOW | RTLD_LOCAL);
 	if (!h) return 1;
-	vbatch_fn gpu_vbatch = (vbatch_fn)dlsym(h, "eccb200_dropin_ecdsa_verify_batch");
+	const ec_alg_type alg = !strcmp(scheme, "ECFSDSA") ? ECFSDSA : (!strcmp(scheme, "BIP0340") ? BIP0340 : ECDSA);
+	const char *fn = alg == ECFSDSA ? "eccb200_dropin_ecfsdsa_verify_batch"
+					: (alg == BIP0340 ? "eccb200_dropin_bip0340_verify_batch" : "eccb200_dropin_ecdsa_verify_batch");
+	vbatch_fn gpu_vbatch = (vbatch_fn)dlsym(h, fn);
 	verdicts_fn gpu_verdicts = (verdicts_fn)dlsym(h, "eccb200_dropin_last_verdicts");
+	count_fn msm_batches = (count_fn)dlsym(h, "eccb200_dropin_msm_batches");
+	CHECK(gpu_vbatch && gpu_verdicts && msm_batches, "missing drop-in symbols");
 	ec_params params;
 	CHECK(!load_params(&params, curve), "params");
-	const u8 qlen = (u8)BYTECEIL(params.ec_gen_order_bitlen);
+	u8 siglen = 0;
+	CHECK(!ec_get_sig_len(&params, alg, SHA256, &siglen), "siglen");
 	enum { POOL = 2048, ML = 32 };
 	static ec_key_pair kp[POOL];
-	static u8 psig[POOL][2 * 66], pmsg[POOL][ML];
+	static u8 psig[POOL][3 * 66], pmsg[POOL][ML];
 	for (int i = 0; i < POOL; i++) { /* signatures made by the reference */
-		CHECK(!ec_key_pair_gen(&kp[i], &params, ECDSA), "keygen");
+		CHECK(!ec_key_pair_gen(&kp[i], &params, alg), "keygen");
 		for (int j = 0; j < ML; j++) pmsg[i][j] = rnd8();
-		CHECK(!ec_sign(psig[i], (u8)(2 * qlen), &kp[i], pmsg[i], ML, ECDSA, SHA256, NULL, 0), "sign");
+		CHECK(!ec_sign(psig[i], siglen, &kp[i], pmsg[i], ML, alg, SHA256, NULL, 0), "sign");
 	}
 	/* n independent items: every item owns its ec_pub_key struct, signature and message bytes (tiled from the pool) */
 	ec_pub_key *keys = (ec_pub_key *)malloc((size_t)n * sizeof(ec_pub_key));
-	u8 *sigs = (u8 *)malloc((size_t)n * 2 * qlen), *msgs = (u8 *)malloc((size_t)n * ML);
+	u8 *sigs = (u8 *)malloc((size_t)n * siglen), *msgs = (u8 *)malloc((size_t)n * ML);
 	const u8 **sp = malloc((size_t)n * sizeof(*sp)), **mp = malloc((size_t)n * sizeof(*mp));
 	const ec_pub_key **pk = malloc((size_t)n * sizeof(*pk));
 	u8 *sl = malloc(n);
@@ -486,31 +492,34 @@ static int run_bench(const char *dropin_path, const char *curve, u32 n)
 	if (!keys || !sigs || !msgs || !sp || !mp || !pk || !sl || !ml || !v) return 1;
 	for (u32 i = 0; i < n; i++) {
 		keys[i] = kp[i % POOL].pub_key;
-		memcpy(sigs + (size_t)i * 2 * qlen, psig[i % POOL], 2 * qlen);
+		memcpy(sigs + (size_t)i * siglen, psig[i % POOL], siglen);
 		memcpy(msgs + (size_t)i * ML, pmsg[i % POOL], ML);
-		if (i % 64 == 13) sigs[(size_t)i * 2 * qlen + 7] ^= 2; /* 1/64 invalid */
-		sp[i] = sigs + (size_t)i * 2 * qlen;
+		if (bad_every && i % bad_every == 13) sigs[(size_t)i * siglen + siglen - 3] ^= 2; /* s corrupted */
+		sp[i] = sigs + (size_t)i * siglen;
 		mp[i] = msgs + (size_t)i * ML;
 		pk[i] = &keys[i];
-		sl[i] = (u8)(2 * qlen);
+		sl[i] = siglen;
 		ml[i] = ML;
 	}
+	const int has_bad = bad_every && n > 13;
+	const unsigned long long msm0 = msm_batches();
 	double best = 1e9;
 	for (int rep = 0; rep < 4; rep++) {
 		double t0 = now_s();
-		int r = gpu_vbatch(sp, sl, pk, mp, ml, n, ECDSA, SHA256, NULL, NULL, NULL, NULL);
+		int r = gpu_vbatch(sp, sl, pk, mp, ml, n, alg, SHA256, NULL, NULL, NULL, NULL);
 		double t = now_s() - t0;
-		CHECK(r == -1, "the batch contains invalid signatures");
+		CHECK(r == (has_bad ? -1 : 0), "batch verdict %d", r);
 		if (rep > 0 && t < best) best = t; /* first call builds the comb table and the staging buffers */
 		printf("bench rep %d: %.4f s\n", rep, t);
 	}
 	CHECK(gpu_verdicts(v, n) == n, "verdicts");
 	u32 bad = 0;
-	for (u32 i = 0; i < n; i++) bad += (v[i] != ((i % 64 == 13) ? -1 : 0));
+	for (u32 i = 0; i < n; i++) bad += (v[i] != ((bad_every && i % bad_every == 13) ? -1 : 0));
 	CHECK(bad == 0, "%u verdicts wrong", bad);
-	printf("DROPIN_BENCH {\"call\": \"eccb200_dropin_ecdsa_verify_batch\", \"curve\": \"%s\", \"items\": %u, "
-	       "\"seconds_best\": %.5f, \"verify_per_s\": %.1f, \"struct_bytes_per_key\": %u, \"wrong_verdicts\": %u}\n",
-	       curve, n, best, (double)n / best, (unsigned)sizeof(ec_pub_key), bad);
+	printf("DROPIN_BENCH {\"call\": \"%s\", \"curve\": \"%s\", \"items\": %u, \"invalid_every\": %u, "
+	       "\"seconds_best\": %.5f, \"verify_per_s\": %.1f, \"struct_bytes_per_key\": %u, \"wrong_verdicts\": %u, "
+	       "\"batches_settled_by_multi_scalar_multiplication\": %llu}\n",
+	       fn, curve, n, bad_every, best, (double)n / best, (unsigned)sizeof(ec_pub_key), bad, msm_batches() - msm0);
 	return failures != 0;
 }
 
@@ -566,9 +575,11 @@ int main(int argc, char **argv)
 	if (argc >= 2 && !strcmp(argv[1], "preload")) rc = run_preload();
 	else if (argc >= 3 && !strcmp(argv[1], "direct")) rc = run_direct(argv[2]);
 	else if (argc >= 3 && !strcmp(argv[1], "threads")) rc = run_threads(argv[2]);
-	else if (argc >= 5 && !strcmp(argv[1], "bench")) rc = run_bench(argv[2], argv[3], (u32)strtoul(argv[4], NULL, 10));
+	else if (argc >= 5 && !strcmp(argv[1], "bench"))
+		rc = run_bench(argv[2], argv[3], (u32)strtoul(argv[4], NULL, 10), argc >= 6 ? argv[5] : "ECDSA",
+			       argc >= 7 ? (u32)strtoul(argv[6], NULL, 10) : 64);
 	else {
-		printf("usage: %s direct <dropin.so> | threads <dropin.so> | bench <dropin.so> <curve> <items> | preload\n", argv[0]);
+		printf("usage: %s direct <dropin.so> | threads <dropin.so> | bench <dropin.so> <curve> <items> [ECDSA|ECFSDSA|BIP0340 [invalid_every, 0 = none]] | preload\n", argv[0]);
 		return 2;
 	}
 	printf(rc ? "HARNESS FAILED (%d failures)\n" : "HARNESS OK (%d failures)\n", failures);

@@ -33,3 +33,23 @@ def test_reference_code_runs_on_gpu_through_interposed_prj_pt_mul():
     r = subprocess.run([HARNESS, "preload"], capture_output=True, text=True, timeout=900, env=env)
     print(r.stdout[-3000:], r.stderr[-2000:])
     assert r.returncode == 0 and "HARNESS OK" in r.stdout
+
+
+@pytest.mark.parametrize("scheme,curve", [("ECFSDSA", "FRP256V1"), ("BIP0340", "SECP256K1"), ("BIP0340", "SECP224R1"),
+                                          ("ECFSDSA", "SECP384R1")])
+def test_verify_batch_adapters_use_the_multi_scalar_fast_path(scheme, curve):
+    """ECFSDSA / BIP0340 verify_batch adapters on real structs: a valid batch is settled by ONE multi-scalar
+    multiplication (K6), a batch with invalid signatures falls through to the per-item kernel, which names them; the
+    harness checks every verdict.  BIP0340 on SECP224R1 (p = 1 mod 4) is not served by K6 and stays per item."""
+    _need()
+    import json
+    env = dict(os.environ, ECCB200_DROPIN_MSM_MIN="256")
+    for invalid_every, settled in ((0, 0 if curve == "SECP224R1" else 3), (64, 0)):
+        r = subprocess.run([HARNESS, "bench", DROPIN, curve, "4096", scheme, str(invalid_every)], capture_output=True,
+                           text=True, timeout=900, env=env)
+        print(r.stdout[-2000:], r.stderr[-1000:])
+        assert r.returncode == 0 and "HARNESS OK" in r.stdout
+        line = json.loads(r.stdout.split("DROPIN_BENCH ", 1)[1].splitlines()[0])
+        assert line["wrong_verdicts"] == 0
+        # all four timed calls of a valid batch are settled by the fast path, none of a batch with invalid signatures
+        assert line["batches_settled_by_multi_scalar_multiplication"] == (4 if settled else 0)
