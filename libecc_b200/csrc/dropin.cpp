@@ -593,15 +593,25 @@ static int verify_batch_common(Scheme sc, const uint8_t **s, const uint8_t *s_le
 	int8_t *verdict = (int8_t *)engine.slot->st[3].get(num);
 	if (!sigs || !pubs || !dig || !verdict) return -1;
 	std::vector<uint8_t> ok(num, 0);
-	std::atomic<int> mixed{ 0 };
-	std::vector<std::vector<uint32_t>> prj_parts(64);
+	std::atomic<int> mixed{ 0 }, any_prj{ 0 };
+	/* ECFSDSA / BIP0340 take affine keys; an ec_pub_key made by ec_key_pair_gen holds a projective point with Z != 1.
+	 * Those batches write X || Y || Z for every item into a page-locked staging buffer and go through ONE batched
+	 * prj_pt_unique on the device (pipelined DMA in and out of the staging) before the verification. */
+	uint8_t *prj = nullptr;
+	int8_t *prj_st = nullptr;
+	if (sc != kEcdsa) {
+		prj = engine.slot->st[4].get(num * 3 * plen);
+		prj_st = (int8_t *)engine.slot->st[5].get(num);
+		if (!prj || !prj_st) return -1;
+	}
 	/* marshalling: struct checks, byte-order conversion and the reference's own hash, on several host threads */
-	parallel_for(num, [&](uint32_t lo, uint32_t hi, unsigned t) {
-		std::vector<uint32_t> &prj = prj_parts[t];
+	parallel_for(num, [&](uint32_t lo, uint32_t hi, unsigned) {
+		bool saw_prj = false;
 		for (uint32_t i = lo; i < hi; i++) {
 			memset(&sigs[i * siglen], 0, siglen);
 			memset(&pubs[i * keylen], 0, keylen);
 			memset(&dig[i * (size_t)hlen], 0, hlen);
+			if (prj) memset(&prj[i * 3 * plen], 0, 3 * plen);
 			const eccb200_ec_pub_key *pk = pub_keys[i];
 			if (!pk || pk->magic != kPubKeyMagic || pk->key_type != sig_type || !pt_ok(&pk->y)) continue;
 			if (!s[i] || (!m[i] && m_len[i])) continue;
@@ -624,38 +634,36 @@ static int verify_batch_common(Scheme sc, const uint8_t **s, const uint8_t *s_le
 				fp_to_be(&pubs[i * keylen], &y->X, pl);
 				fp_to_be(&pubs[i * keylen + plen], &y->Y, pl);
 				fp_to_be(&pubs[i * keylen + 2 * plen], &y->Z, pl);
-			} else if (fp_is_small(&y->Z, 1)) {
-				fp_to_be(&pubs[i * 2 * plen], &y->X, pl);
-				fp_to_be(&pubs[i * 2 * plen + plen], &y->Y, pl);
 			} else {
-				prj.push_back(i); /* not (x, y, 1): goes through the batched prj_pt_unique below */
+				const bool affine = fp_is_small(&y->Z, 1);
+				if (affine) {
+					fp_to_be(&pubs[i * 2 * plen], &y->X, pl);
+					fp_to_be(&pubs[i * 2 * plen + plen], &y->Y, pl);
+				}
+				saw_prj = saw_prj || !affine;
+				fp_to_be(&prj[i * 3 * plen], &y->X, pl);
+				fp_to_be(&prj[i * 3 * plen + plen], &y->Y, pl);
+				fp_to_be(&prj[i * 3 * plen + 2 * plen], &y->Z, pl);
 			}
 			ok[i] = 1;
 		}
+		if (saw_prj) any_prj.store(1);
 	});
 	if (mixed.load()) return -1; /* all keys must share the curve parameters */
-	std::vector<uint32_t> prj_idx;
-	for (auto &part : prj_parts) prj_idx.insert(prj_idx.end(), part.begin(), part.end());
-	if (!prj_idx.empty()) {
-		std::vector<uint8_t> pb(prj_idx.size() * 3 * plen), ab(prj_idx.size() * 2 * plen);
-		std::vector<int8_t> st(prj_idx.size());
-		parallel_for((uint32_t)prj_idx.size(), [&](uint32_t lo, uint32_t hi, unsigned) {
-			for (uint32_t k = lo; k < hi; k++) {
-				const eccb200_prj_pt *p = &pub_keys[prj_idx[k]]->y;
-				fp_to_be(&pb[k * 3 * plen], &p->X, pl);
-				fp_to_be(&pb[k * 3 * plen + plen], &p->Y, pl);
-				fp_to_be(&pb[k * 3 * plen + 2 * plen], &p->Z, pl);
-			}
+	if (sc != kEcdsa && any_prj.load()) {
+		/* every item's key through the batched prj_pt_unique (items refused above carry Z = 0 and are ignored) */
+		if (eccb200_prj_pt_unique_batch(eng, num, prj, pubs, prj_st)) return -1;
+		parallel_for(num, [&](uint32_t lo, uint32_t hi, unsigned) {
+			for (uint32_t i = lo; i < hi; i++)
+				if (ok[i] && prj_st[i] != 0) {
+					ok[i] = 0; /* off the curve, or the point at infinity: BIP0340's prj_pt_unique fails on it
+						    * (sig/bip0340.c:428); ECFSDSA with a key at infinity is rejected too — a documented
+						    * divergence (the reference would accept it iff s*G == r).  ECDSA keys are
+						    * normalised on the device, where a key at infinity continues with W' = u*G like the
+						    * reference's ec_verify. */
+					memset(&pubs[i * 2 * plen], 0, 2 * plen);
+				}
 		});
-		if (eccb200_prj_pt_unique_batch(eng, (uint32_t)prj_idx.size(), pb.data(), ab.data(), st.data())) return -1;
-		for (size_t k = 0; k < prj_idx.size(); k++) {
-			uint32_t i = prj_idx[k];
-			if (st[k] == 0) memcpy(&pubs[i * 2 * plen], &ab[k * 2 * plen], 2 * plen);
-			else ok[i] = 0; /* off the curve, or the point at infinity: BIP0340's prj_pt_unique fails on it
-					 * (sig/bip0340.c:428); ECFSDSA with a key at infinity is rejected too — a documented divergence
-					 * (the reference would accept it iff s*G == r).  ECDSA keys are normalised on the
-					 * device, where a key at infinity continues with W' = u*G like the reference's ec_verify. */
-		}
 	}
 	if (sc == kBip0340) {
 		/* the challenge hash needs x(Y) of the affine key: second marshalling pass */
