@@ -8,7 +8,8 @@
  *     (src/sig/ecdsa_common.c:479,788,793), ECC-CDH (src/ecdh/ecccdh.c:80,209), all other schemes of src/sig — runs
  *     its scalar multiplications on the B200 without being recompiled.
  *   - `ec_verify` with the reference's exact signature (src/sig/sig_algs.h:85-88): ECDSA / DECDSA / ECFSDSA / BIP0340
- *     verifications become ONE kernel launch each; every other scheme is forwarded to the reference's own ec_verify.
+ *     verifications become ONE kernel launch each, the eight other short-Weierstrass schemes (ECKCDSA, ECSDSA, ECOSDSA,
+ *     ECGDSA, ECRDSA, SM2, BIGN, DBIGN) one launch plus their host hashes; EdDSA is forwarded to the reference's own.
  *   - `prj_pt_mul_blind` (src/curves/prj_pt.h:62) is exported but NOT taken over by default: see its comment below.
  *   - `eccb200_dropin_prj_pt_mul_batch`: the same on arrays of reference structs (one launch for the batch).
  *   - `eccb200_dropin_ecdsa_verify_batch`: a function with the signature of the reference's per-scheme
@@ -122,10 +123,14 @@ void eccb200_dropin_allow_nonct_blind(int on);
  * ec_alg_type / hash_alg_type values):
  *     int ec_verify(const u8 *sig, u8 siglen, const ec_pub_key *pub_key, const u8 *m, u32 mlen,
  *                   ec_alg_type sig_type, hash_alg_type hash_type, const u8 *adata, u16 adata_len);
- * ECDSA (1), DECDSA (14), ECFSDSA (5), BIP0340 (20), ECSDSA (3), ECOSDSA (4) and ECKCDSA (2) without ancillary data on a supported curve: the message is hashed on the
- * host with the reference's src/hash and the whole verification (steps 3-10 of __ecdsa_verify_finalize,
- * src/sig/ecdsa_common.c:760-810) is ONE launch of the verification kernel; 0 = valid, -1 = invalid.  Anything else is
- * forwarded unchanged to the next ec_verify in the process (the reference's own); -1 if there is none.
+ * ECDSA (1), DECDSA (14), ECFSDSA (5) and BIP0340 (20) without ancillary data on a supported curve: the message is
+ * hashed on the host with the reference's src/hash and the whole verification (steps 3-10 of __ecdsa_verify_finalize,
+ * src/sig/ecdsa_common.c:760-810) is ONE launch of the verification kernel; 0 = valid, -1 = invalid.
+ * ECKCDSA (2), ECSDSA (3), ECOSDSA (4), ECGDSA (6), ECRDSA (7), SM2 (8), BIGN (18) and DBIGN (19): the EC core
+ * W' = a*G + b*Y is one launch of the double-scalar kernel, the scheme's mod-q scalar preparation, hashes and comparison
+ * run on the host around it (SM2 and BIGN with their ancillary data: the signer's ID, the hash OID record).
+ * Anything else - another scheme, an unknown curve, ancillary data on a scheme that takes none, SM2 / BIGN without
+ * theirs - is forwarded unchanged to the next ec_verify in the process (the reference's own); -1 if there is none.
  */
 int ec_verify(const uint8_t *sig, uint8_t siglen, const eccb200_ec_pub_key *pub_key, const uint8_t *m, uint32_t mlen,
 	      int sig_type, int hash_type, const uint8_t *adata, uint16_t adata_len);
@@ -139,10 +144,11 @@ int eccb200_dropin_ec_verify(const uint8_t *sig, uint8_t siglen, const eccb200_e
  *                         u32 num, ec_alg_type sig_type, hash_alg_type hash_type, const u8 **adata,
  *                         const u16 *adata_len, verify_batch_scratch_pad *scratch_pad_area, u32 *scratch_pad_area_len);
  *     int is_verify_batch_mode_supported(ec_alg_type sig_type, int *check);
- * The seven schemes of the per-scheme adapters below (ECDSA, DECDSA, ECFSDSA, BIP0340, ECSDSA, ECOSDSA, ECKCDSA) are
- * served by the device - five of them sit at unsupported_verify_batch in the reference (src/sig/sig_algs_internal.h:294);
- * 0 iff ALL num signatures verify.  Other schemes, unknown curves and batches with ancillary data are forwarded to the
- * next definition in the process (the reference's own); -1 if there is none.
+ * The twelve schemes of the per-scheme adapters below (ECDSA, DECDSA, ECFSDSA, BIP0340, ECSDSA, ECOSDSA, ECKCDSA, ECGDSA,
+ * ECRDSA, SM2, BIGN, DBIGN) are served by the device - ten of them sit at unsupported_verify_batch in the reference
+ * (src/sig/sig_algs_internal.h:294); 0 iff ALL num signatures verify.  Other schemes (EdDSA), unknown curves and batches
+ * with ancillary data on a scheme that takes none are forwarded to the next definition in the process (the reference's
+ * own); -1 if there is none.
  */
 int ec_verify_batch(const uint8_t **s, const uint8_t *s_len, const eccb200_ec_pub_key **pub_keys, const uint8_t **m,
 		    const uint32_t *m_len, uint32_t num, int sig_type, int hash_type, const uint8_t **adata,
@@ -202,6 +208,35 @@ int eccb200_dropin_eckcdsa_verify_batch(const uint8_t **s, const uint8_t *s_len,
 					const uint8_t **m, const uint32_t *m_len, uint32_t num, int sig_type,
 					int hash_type, const uint8_t **adata, const uint16_t *adata_len,
 					void *scratch_pad_area, uint32_t *scratch_pad_area_len);
+
+/*
+ * ECGDSA (6; src/sig/ecgdsa.c:413-600), ECRDSA (7; src/sig/ecrdsa.c:417-600), SM2 (8; src/sig/sm2.c:518-700) and
+ * BIGN (18) / DBIGN (19; src/sig/bign_common.c:742-990), all left at unsupported_verify_batch by the reference.  Host:
+ * range checks and the mod-q scalars - ECGDSA u = r^-1 e, v = r^-1 s; ECRDSA u = h^-1 s, v = -h^-1 r; SM2 (s, r + s);
+ * BIGN (s1 + h, s0 + 2^(8l)) - with ONE inversion mod q per chunk of items (Montgomery's trick) where the reference does
+ * one nn_modinv per signature; device: W' = u*G + v*Y for the whole batch in one launch; host: W'_x mod q == r
+ * (ECGDSA, ECRDSA), (e + W'_x) mod q == r with e = H(Z || m) and Z built from adata[i] = the signer's ID (SM2),
+ * BELT-HASH(OID || W' || H(m)) == s0 with the OID record in adata[i] (BIGN).  adata / adata_len are read per item for SM2
+ * and BIGN (an item without its ancillary data is rejected, as the reference's ec_verify rejects it) and must be NULL
+ * entries for ECGDSA / ECRDSA.  ECRDSA follows the reference's default build (digest byte-reversed, RFC flavour); set
+ * ECCB200_ECRDSA_ISO14888_3=1 next to a libecc built with USE_ISO14888_3_ECRDSA (src/sig/ecrdsa.c:545-547).
+ */
+int eccb200_dropin_ecgdsa_verify_batch(const uint8_t **s, const uint8_t *s_len, const eccb200_ec_pub_key **pub_keys,
+				       const uint8_t **m, const uint32_t *m_len, uint32_t num, int sig_type,
+				       int hash_type, const uint8_t **adata, const uint16_t *adata_len,
+				       void *scratch_pad_area, uint32_t *scratch_pad_area_len);
+int eccb200_dropin_ecrdsa_verify_batch(const uint8_t **s, const uint8_t *s_len, const eccb200_ec_pub_key **pub_keys,
+				       const uint8_t **m, const uint32_t *m_len, uint32_t num, int sig_type,
+				       int hash_type, const uint8_t **adata, const uint16_t *adata_len,
+				       void *scratch_pad_area, uint32_t *scratch_pad_area_len);
+int eccb200_dropin_sm2_verify_batch(const uint8_t **s, const uint8_t *s_len, const eccb200_ec_pub_key **pub_keys,
+				    const uint8_t **m, const uint32_t *m_len, uint32_t num, int sig_type, int hash_type,
+				    const uint8_t **adata, const uint16_t *adata_len, void *scratch_pad_area,
+				    uint32_t *scratch_pad_area_len);
+int eccb200_dropin_bign_verify_batch(const uint8_t **s, const uint8_t *s_len, const eccb200_ec_pub_key **pub_keys,
+				     const uint8_t **m, const uint32_t *m_len, uint32_t num, int sig_type, int hash_type,
+				     const uint8_t **adata, const uint16_t *adata_len, void *scratch_pad_area,
+				     uint32_t *scratch_pad_area_len);
 
 /* Per-signature verdicts of the last eccb200_dropin_*_verify_batch call on this thread (0 / -1), for callers
  * that want to know WHICH signature failed; returns the number of verdicts copied. */

@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -734,279 +735,694 @@ static int verify_batch_common(Scheme sc, const uint8_t **s, const uint8_t *s_le
 }
 
 /* big-endian bytes -> nn-style little-endian 64-bit words (at most kMaxWords) */
-static void be_to_nn(eccb200_nn *out, const uint8_t *be, uint32_t len)
-{
-	memset(out, 0, sizeof(*out));
-	for (uint32_t j = 0; j < len && j < 8u * kMaxWords; j++) out->val[j / 8] |= (uint64_t)be[len - 1 - j] << (8 * (j % 8));
-	out->wlen = (uint8_t)((std::min<uint32_t>(len, 8u * kMaxWords) + 7) / 8);
-	out->magic = kNnMagic;
-}
+/*
+ * Arithmetic modulo the group order q on the host, for the scalar preparations that multiply or invert (the
+ * reference's nn_mod_mul / nn_modinv / nn_mod_add of sig/ecgdsa.c:563-569, sig/ecrdsa.c:556-570, sig/sm2.c:657,
+ * sig/bign_common.c:906-916): Montgomery products on 64-bit limbs (R = 2^(64 n)), inverses by Fermat (q is prime),
+ * shared among the items of a chunk with Montgomery's trick.  Values are little-endian limb arrays of n <= 9 words.
+ */
+struct ModQ {
+	int n = 0;
+	size_t qlen = 0;
+	uint64_t q[9] = { 0 }, r2[9] = { 0 }, one[9] = { 0 }, n0 = 0;
+
+	explicit ModQ(const CurveInfo *ci) : n(ci->n64), qlen((size_t)ci->qlen)
+	{
+		for (int i = 0; i < n; i++) q[i] = ci->q[i];
+		uint64_t x = 1; /* -q^-1 mod 2^64 by Newton */
+		for (int i = 0; i < 6; i++) x *= 2 - q[0] * x;
+		n0 = 0 - x;
+		uint64_t t[9] = { 1 }; /* 2^k mod q by doublings: k = 64n gives R, k = 128n gives R^2 */
+		for (int k = 0; k < 128 * n; k++) {
+			add(t, t, t);
+			if (k == 64 * n - 1) memcpy(one, t, sizeof(one));
+		}
+		memcpy(r2, t, sizeof(r2));
+	}
+	bool is_zero(const uint64_t *a) const
+	{
+		uint64_t v = 0;
+		for (int i = 0; i < n; i++) v |= a[i];
+		return v == 0;
+	}
+	bool geq_q(const uint64_t *a) const
+	{
+		for (int i = n - 1; i >= 0; i--)
+			if (a[i] != q[i]) return a[i] > q[i];
+		return true;
+	}
+	bool eq(const uint64_t *a, const uint64_t *b) const { return memcmp(a, b, (size_t)n * 8) == 0; }
+	void sub_q_if(uint64_t *a, uint64_t top) const /* a + top * 2^(64n) in [0, 2q) -> [0, q) */
+	{
+		if (!top && !geq_q(a)) return;
+		unsigned __int128 bw = 0;
+		for (int i = 0; i < n; i++) {
+			unsigned __int128 d = (unsigned __int128)a[i] - q[i] - (uint64_t)bw;
+			a[i] = (uint64_t)d;
+			bw = (d >> 64) & 1;
+		}
+	}
+	void add(uint64_t *o, const uint64_t *a, const uint64_t *b) const /* a, b < q */
+	{
+		unsigned __int128 c = 0;
+		for (int i = 0; i < n; i++) {
+			c += (unsigned __int128)a[i] + b[i];
+			o[i] = (uint64_t)c;
+			c >>= 64;
+		}
+		sub_q_if(o, (uint64_t)c);
+	}
+	void neg(uint64_t *o, const uint64_t *a) const /* a < q */
+	{
+		if (is_zero(a)) {
+			memset(o, 0, (size_t)n * 8);
+			return;
+		}
+		unsigned __int128 bw = 0;
+		for (int i = 0; i < n; i++) {
+			unsigned __int128 d = (unsigned __int128)q[i] - a[i] - (uint64_t)bw;
+			o[i] = (uint64_t)d;
+			bw = (d >> 64) & 1;
+		}
+	}
+	/* o = a * b / R mod q; one operand < q, the other < R (o may alias a or b) */
+	void mul(uint64_t *o, const uint64_t *a, const uint64_t *b) const
+	{
+		uint64_t t[11] = { 0 };
+		for (int i = 0; i < n; i++) {
+			unsigned __int128 c = 0;
+			for (int j = 0; j < n; j++) {
+				c += (unsigned __int128)a[i] * b[j] + t[j];
+				t[j] = (uint64_t)c;
+				c >>= 64;
+			}
+			c += t[n];
+			t[n] = (uint64_t)c;
+			t[n + 1] = (uint64_t)(c >> 64);
+			const uint64_t m = t[0] * n0;
+			c = ((unsigned __int128)m * q[0] + t[0]) >> 64;
+			for (int j = 1; j < n; j++) {
+				c += (unsigned __int128)m * q[j] + t[j];
+				t[j - 1] = (uint64_t)c;
+				c >>= 64;
+			}
+			c += t[n];
+			t[n - 1] = (uint64_t)c;
+			t[n] = t[n + 1] + (uint64_t)(c >> 64);
+		}
+		sub_q_if(t, t[n]);
+		memcpy(o, t, (size_t)n * 8);
+	}
+	void to_mont(uint64_t *o, const uint64_t *a) const { mul(o, a, r2); }
+	void from_mont(uint64_t *o, const uint64_t *a) const
+	{
+		const uint64_t u[9] = { 1 };
+		mul(o, a, u);
+	}
+	void inv_mont(uint64_t *o, const uint64_t *a) const /* a^(q-2), Montgomery form in and out; a != 0 */
+	{
+		uint64_t e[9], acc[9], base[9];
+		memcpy(e, q, sizeof(e));
+		for (int i = 0, borrow = 2; i < n && borrow; i++) { /* e = q - 2 */
+			const uint64_t old = e[i];
+			e[i] = old - (uint64_t)borrow;
+			borrow = old < (uint64_t)borrow ? 1 : 0;
+		}
+		memcpy(acc, one, sizeof(acc));
+		memcpy(base, a, (size_t)n * 8);
+		for (int i = 0; i < 64 * n; i++) {
+			if ((e[i / 64] >> (i % 64)) & 1) mul(acc, acc, base);
+			mul(base, base, base);
+		}
+		memcpy(o, acc, (size_t)n * 8);
+	}
+	/* simultaneous inversion of k nonzero plain values (v: k * 9 words, in place, plain in and out) */
+	void inv_many(uint64_t *v, size_t k) const
+	{
+		if (!k) return;
+		std::vector<uint64_t> pre(k * 9);
+		uint64_t acc[9], t[9];
+		memcpy(acc, one, sizeof(acc));
+		for (size_t i = 0; i < k; i++) {
+			to_mont(&v[i * 9], &v[i * 9]);
+			memcpy(&pre[i * 9], acc, sizeof(acc)); /* product of the values before i */
+			mul(acc, acc, &v[i * 9]);
+		}
+		inv_mont(acc, acc);
+		for (size_t i = k; i-- > 0;) {
+			mul(t, acc, &pre[i * 9]);      /* v_i^-1 (Montgomery form) */
+			mul(acc, acc, &v[i * 9]);      /* drop v_i from the running inverse */
+			from_mont(&v[i * 9], t);
+		}
+	}
+	/* big-endian bytes of any length -> value mod q (nn_init_from_buf + nn_mod): Horner over 8n-byte chunks, a chunk
+	 * (< R) reduced by a round trip through the Montgomery domain, h * R mod q = to_mont(h) */
+	void from_be_mod(uint64_t *o, const uint8_t *be, size_t len) const
+	{
+		const size_t cb = (size_t)n * 8;
+		uint64_t h[9] = { 0 };
+		size_t pos = 0;
+		size_t first = len % cb ? len % cb : (len ? cb : 0);
+		while (pos < len) {
+			const size_t take = pos == 0 ? first : cb;
+			uint64_t c[9] = { 0 };
+			for (size_t j = 0; j < take; j++) c[j / 8] |= (uint64_t)be[pos + take - 1 - j] << (8 * (j % 8));
+			to_mont(c, c);
+			from_mont(c, c);
+			to_mont(h, h);
+			add(h, h, c);
+			pos += take;
+		}
+		memcpy(o, h, sizeof(h));
+	}
+	/* big-endian qlen bytes -> limbs, NOT reduced (for the range checks) */
+	void from_be(uint64_t *o, const uint8_t *be) const
+	{
+		memset(o, 0, 9 * 8);
+		for (size_t j = 0; j < qlen; j++) o[j / 8] |= (uint64_t)be[qlen - 1 - j] << (8 * (j % 8));
+	}
+	void to_be(uint8_t *out, const uint64_t *a) const { words_to_be(out, (int)qlen, a); }
+	bool in_open_range(const uint64_t *a) const { return !is_zero(a) && !geq_q(a); } /* a in ]0, q[ */
+};
 
 /*
- * ECSDSA / ECOSDSA (sig/ecsdsa_common.c:425-609): these schemes hash the RECOMPUTED point, so the batch is split the way
- * the reference's own code is: host — checks, e = -(OS2I(r) mod q); device — W' = sG + eY for the whole batch in one
- * launch (eccb200_double_smul_batch); host — r' = H(W'x [|| W'y] || m) with the reference's src/hash, r' == r.
+ * The verifications built on W' = a*G + b*Y (prj_pt_mul, prj_pt_mul, prj_pt_add, prj_pt_unique in the reference),
+ * batched: ONE launch of eccb200_double_smul_batch per batch, the rest of the scheme on the host the way the reference
+ * splits it — signature checks and the mod-q scalar preparation in front, the comparison (or the hash of the recomputed
+ * point, src/hash) behind.  A scheme describes its three host steps; the skeleton (verify_batch_double_smul) does the
+ * struct checks, brings the keys to affine form (on the device when they are projective), launches, collects verdicts.
  */
-static int verify_batch_ecsdsa(bool optimized, const uint8_t **s, const uint8_t *s_len, const eccb200_ec_pub_key **pub_keys,
-			       const uint8_t **m, const uint32_t *m_len, uint32_t num, int sig_type, int hash_type,
-			       const uint8_t **adata)
-{
-	t_verdicts.assign(num, -1);
-	if (num == 0) return -1;
-	if (!s || !s_len || !pub_keys || !m || !m_len) return -1;
-	if (adata)
-		for (uint32_t i = 0; i < num; i++)
-			if (adata[i]) return -1;
-	get_hash_fn get_hash = resolve_get_hash();
-	if (!get_hash) return -1;
-	const HashMappingHead *hm = nullptr;
-	if (get_hash(hash_type, &hm) || !hm || !hm->hfunc_scattered) return -1;
-	const uint32_t hlen = hm->digest_size;
-	if (hlen == 0 || hlen > 128) return -1;
+struct DsBatch {
 	const CurveInfo *ci = nullptr;
-	for (uint32_t i = 0; i < num && !ci; i++) {
-		const eccb200_ec_pub_key *pk = pub_keys[i];
-		if (pk && pk->magic == kPubKeyMagic && pk->key_type == sig_type && pt_ok(&pk->y)) ci = identify(&pk->y);
-	}
-	if (!ci) return -1;
-	Engine engine = acquire(ci->id, num);
-	eccb200_ctx *eng = engine.ctx;
-	if (!eng) return -1;
-	const int pl = ci->plen;
-	const size_t plen = (size_t)ci->plen, qlen = (size_t)ci->qlen;
-	const size_t siglen = (size_t)hlen + qlen; /* ECSDSA_SIGLEN: r is a digest, s a scalar (sig/ecsdsa_common.h) */
-	uint8_t *ab = engine.slot->st[0].get(num * 2 * qlen), *pubs = engine.slot->st[1].get(num * 2 * plen),
-		*wout = engine.slot->st[2].get(num * 2 * plen);
-	int8_t *status = (int8_t *)engine.slot->st[3].get(num);
-	if (!ab || !pubs || !wout || !status) return -1;
-	uint8_t qbe[72];
-	words_to_be(qbe, (int)qlen, ci->q);
-	std::vector<uint8_t> ok(num, 0);
-	std::atomic<int> mixed{ 0 };
-	std::vector<std::vector<uint32_t>> prj_parts(64);
-	parallel_for(num, [&](uint32_t lo, uint32_t hi, unsigned t) {
-		std::vector<uint32_t> &prj = prj_parts[t];
-		for (uint32_t i = lo; i < hi; i++) {
-			memset(&ab[i * 2 * qlen], 0, 2 * qlen);
-			memset(&pubs[i * 2 * plen], 0, 2 * plen);
-			const eccb200_ec_pub_key *pk = pub_keys[i];
-			if (!pk || pk->magic != kPubKeyMagic || pk->key_type != sig_type || !pt_ok(&pk->y)) continue;
-			if (!s[i] || (!m[i] && m_len[i])) continue;
-			const CurveInfo *c = identify(&pk->y);
-			if (!c) continue;
-			if (c != ci) {
-				mixed.store(1);
-				continue;
-			}
-			if (s_len[i] != siglen) continue;                       /* (:472) */
-			const uint8_t *sb = s[i] + hlen;
-			bool zero = true;
-			for (size_t j = 0; j < qlen; j++) zero = zero && sb[j] == 0;
-			if (zero || memcmp(sb, qbe, qlen) >= 0) continue;       /* 1. s in ]0, q[ (:475-478) */
-			eccb200_nn r;
-			be_to_nn(&r, s[i], hlen);
-			uint8_t rmod[72], e[72];
-			scalar_mod_to_be(rmod, &r, ci);                         /* 2. e = -(r mod q) mod q (:486-488) */
-			bool rz = true;
-			for (size_t j = 0; j < qlen; j++) rz = rz && rmod[j] == 0;
-			if (rz) continue;                                       /* 3. e == 0: reject (:491-492) */
-			int borrow = 0;
-			for (int j = (int)qlen - 1; j >= 0; j--) {
-				int d = (int)qbe[j] - (int)rmod[j] - borrow;
-				borrow = d < 0;
-				e[j] = (uint8_t)(d + (borrow << 8));
-			}
-			memcpy(&ab[i * 2 * qlen], sb, qlen);
-			memcpy(&ab[i * 2 * qlen + qlen], e, qlen);
-			const eccb200_prj_pt *y = &pk->y;
-			if (fp_is_small(&y->Z, 1)) {
-				fp_to_be(&pubs[i * 2 * plen], &y->X, pl);
-				fp_to_be(&pubs[i * 2 * plen + plen], &y->Y, pl);
-			} else {
-				prj.push_back(i);
-			}
-			ok[i] = 1;
-		}
-	});
-	if (mixed.load()) return -1;
-	std::vector<uint32_t> prj_idx;
-	for (auto &part : prj_parts) prj_idx.insert(prj_idx.end(), part.begin(), part.end());
-	if (!prj_idx.empty()) {
-		std::vector<uint8_t> pb(prj_idx.size() * 3 * plen), abuf(prj_idx.size() * 2 * plen);
-		std::vector<int8_t> st(prj_idx.size());
-		parallel_for((uint32_t)prj_idx.size(), [&](uint32_t lo, uint32_t hi, unsigned) {
-			for (uint32_t k = lo; k < hi; k++) {
-				const eccb200_prj_pt *p = &pub_keys[prj_idx[k]]->y;
-				fp_to_be(&pb[k * 3 * plen], &p->X, pl);
-				fp_to_be(&pb[k * 3 * plen + plen], &p->Y, pl);
-				fp_to_be(&pb[k * 3 * plen + 2 * plen], &p->Z, pl);
-			}
-		});
-		if (eccb200_prj_pt_unique_batch(eng, (uint32_t)prj_idx.size(), pb.data(), abuf.data(), st.data())) return -1;
-		for (size_t k = 0; k < prj_idx.size(); k++) {
-			uint32_t i = prj_idx[k];
-			if (st[k] == 0) memcpy(&pubs[i * 2 * plen], &abuf[k * 2 * plen], 2 * plen);
-			else ok[i] = 0; /* key off the curve; a key at infinity gives W' = sG in the reference — rejected here,
-					 * the same documented divergence as for ECFSDSA */
-		}
-	}
-	for (uint32_t i = 0; i < num; i++)
-		if (!ok[i]) { /* keep the batch launchable: rejected slots multiply the generator by zero */
-			memset(&ab[i * 2 * qlen], 0, 2 * qlen);
-			gen_to_be(&pubs[i * 2 * plen], ci);
-		}
-	if (eccb200_double_smul_batch(eng, num, ab, pubs, wout, status)) return -1; /* 4. W' = sG + eY (:495-498) */
-	g_verifies += num;
-	std::vector<int8_t> verdict(num, -1);
-	parallel_for(num, [&](uint32_t lo, uint32_t hi, unsigned) {
-		for (uint32_t i = lo; i < hi; i++) {
-			if (!ok[i] || status[i] != 0) continue; /* infinity: prj_pt_unique fails (:498) */
-			uint8_t rp[128];
-			const unsigned char *in[4] = { &wout[i * 2 * plen], optimized ? m[i] : &wout[i * 2 * plen + plen],
-						       optimized ? nullptr : m[i], nullptr };
-			uint32_t il[3] = { (uint32_t)plen, optimized ? m_len[i] : (uint32_t)plen, optimized ? 0u : m_len[i] };
-			if (hm->hfunc_scattered(in, il, rp)) continue;          /* 5. r' = H(W'x [|| W'y] || m) (:500-520) */
-			verdict[i] = memcmp(rp, s[i], hlen) == 0 ? 0 : -1;      /* 6. r == r' (sig/ecsdsa_common.c:606) */
-		}
-	});
-	int all = 0;
-	for (uint32_t i = 0; i < num; i++)
-		if (verdict[i]) all = -1;
-	t_verdicts.assign(verdict.begin(), verdict.end());
-	return all;
+	const HashMappingHead *hm = nullptr;
+	uint32_t hlen = 0, num = 0;
+	size_t plen = 0, qlen = 0;
+	const uint8_t **s = nullptr;
+	const uint8_t *s_len = nullptr;
+	const eccb200_ec_pub_key **pub_keys = nullptr;
+	const uint8_t **m = nullptr;
+	const uint32_t *m_len = nullptr;
+	const uint8_t **adata = nullptr;
+	const uint16_t *adata_len = nullptr;
+	uint8_t *ab = nullptr;   /* [num][2 qlen]  a || b, big-endian */
+	uint8_t *pubs = nullptr; /* [num][2 plen]  affine keys, big-endian */
+	std::vector<uint8_t> ok; /* item still alive */
+	const ModQ *mq = nullptr;
+	uint8_t *a_of(uint32_t i) const { return ab + (size_t)i * 2 * qlen; }
+	uint8_t *b_of(uint32_t i) const { return ab + (size_t)i * 2 * qlen + qlen; }
+	const uint8_t *key_of(uint32_t i) const { return pubs + (size_t)i * 2 * plen; }
+	const uint8_t *id_of(uint32_t i) const { return adata ? adata[i] : nullptr; }
+	uint16_t id_len_of(uint32_t i) const { return adata_len ? adata_len[i] : 0; }
+};
+
+struct DsScheme {
+	virtual ~DsScheme() {}
+	/* false: ancillary data makes the call one the layer does not serve (the caller forwards it) */
+	virtual bool takes_adata() const { return false; }
+	/* the scheme hashes the affine key (a key at infinity then fails prj_pt_to_aff in the reference); otherwise a
+	 * key at infinity verifies like the reference: b * infinity = infinity, W' = a*G */
+	virtual bool needs_affine_key() const { return false; }
+	virtual bool setup(DsBatch &) { return true; }                          /* per batch: lengths, side buffers */
+	virtual size_t siglen(const DsBatch &) const = 0;
+	virtual bool sig_ok(const DsBatch &, uint32_t i) const = 0;             /* range checks of *_verify_init */
+	virtual void scalars(DsBatch &, uint32_t lo, uint32_t hi) = 0;          /* fills a || b; may clear ok[i] */
+	virtual bool accept(const DsBatch &, uint32_t i, const uint8_t *W) = 0; /* W = affine x || y of W', finite */
+};
+
+static bool be_in_open_range(const uint8_t *v, const uint8_t *qbe, size_t qlen) /* v in ]0, q[ */
+{
+	bool zero = true;
+	for (size_t j = 0; j < qlen; j++) zero = zero && v[j] == 0;
+	return !zero && memcmp(v, qbe, qlen) < 0;
 }
 
-/*
- * ECKCDSA (sig/eckcdsa.c:543-832): r_len = min(|H|, qlen); s in ]0, q[; h = H(z || m) with z = the first block_size
- * bytes of Y_x || Y_y || 0...; e = OS2I(r XOR rightmost(h)) mod q; W' = sY + eG; r' = rightmost(H(W'_x)) == r.  Same
- * split as ECSDSA: host for the hashes and the mod-q scalar, one device launch (eccb200_double_smul_batch with a = e
- * on G and b = s on Y) for the whole batch.
- */
-static int verify_batch_eckcdsa(const uint8_t **s, const uint8_t *s_len, const eccb200_ec_pub_key **pub_keys,
-				const uint8_t **m, const uint32_t *m_len, uint32_t num, int sig_type, int hash_type,
-				const uint8_t **adata)
-{
-	t_verdicts.assign(num, -1);
-	if (num == 0) return -1;
-	if (!s || !s_len || !pub_keys || !m || !m_len) return -1;
-	if (adata)
-		for (uint32_t i = 0; i < num; i++)
-			if (adata[i]) return -1;
-	get_hash_fn get_hash = resolve_get_hash();
-	if (!get_hash) return -1;
-	const HashMappingHead *hm = nullptr;
-	if (get_hash(hash_type, &hm) || !hm || !hm->hfunc_scattered) return -1;
-	const uint32_t hlen = hm->digest_size, zlen = hm->block_size;
-	if (hlen == 0 || hlen > 128 || zlen == 0) return -1;
-	const CurveInfo *ci = nullptr;
-	for (uint32_t i = 0; i < num && !ci; i++) {
-		const eccb200_ec_pub_key *pk = pub_keys[i];
-		if (pk && pk->magic == kPubKeyMagic && pk->key_type == sig_type && pt_ok(&pk->y)) ci = identify(&pk->y);
-	}
-	if (!ci) return -1;
-	Engine engine = acquire(ci->id, num);
-	eccb200_ctx *eng = engine.ctx;
-	if (!eng) return -1;
-	const int pl = ci->plen;
-	const size_t plen = (size_t)ci->plen, qlen = (size_t)ci->qlen;
-	const size_t rlen = std::min<size_t>(hlen, qlen), siglen = rlen + qlen; /* ECKCDSA_R_LEN / _SIGLEN (sig/eckcdsa.h:28-31) */
-	const size_t shift = hlen > rlen ? hlen - rlen : 0;
-	uint8_t *ab = engine.slot->st[0].get(num * 2 * qlen), *pubs = engine.slot->st[1].get(num * 2 * plen),
-		*wout = engine.slot->st[2].get(num * 2 * plen);
-	int8_t *status = (int8_t *)engine.slot->st[3].get(num);
-	if (!ab || !pubs || !wout || !status) return -1;
+/* ECSDSA / ECOSDSA (sig/ecsdsa_common.c:425-609): r = H(W_x [|| W_y] || m) is a digest, s a scalar;
+ * e = -(OS2I(r) mod q); W' = sG + eY; accept iff H(W'_x [|| W'_y] || m) == r. */
+struct EcsdsaScheme : DsScheme {
+	bool optimized;
 	uint8_t qbe[72];
-	words_to_be(qbe, (int)qlen, ci->q);
-	std::vector<uint8_t> ok(num, 0);
-	std::atomic<int> mixed{ 0 };
-	std::vector<std::vector<uint32_t>> prj_parts(64);
-	/* pass 1: struct and range checks, affine keys (z needs them) */
-	parallel_for(num, [&](uint32_t lo, uint32_t hi, unsigned t) {
-		std::vector<uint32_t> &prj = prj_parts[t];
+	explicit EcsdsaScheme(bool opt) : optimized(opt) {}
+	bool setup(DsBatch &b) override
+	{
+		words_to_be(qbe, (int)b.qlen, b.ci->q);
+		return true;
+	}
+	size_t siglen(const DsBatch &b) const override { return (size_t)b.hlen + b.qlen; } /* ECSDSA_SIGLEN (:472) */
+	bool sig_ok(const DsBatch &b, uint32_t i) const override
+	{
+		return be_in_open_range(b.s[i] + b.hlen, qbe, b.qlen);                      /* 1. s in ]0, q[ (:475-478) */
+	}
+	void scalars(DsBatch &b, uint32_t lo, uint32_t hi) override
+	{
 		for (uint32_t i = lo; i < hi; i++) {
-			memset(&ab[i * 2 * qlen], 0, 2 * qlen);
-			memset(&pubs[i * 2 * plen], 0, 2 * plen);
-			const eccb200_ec_pub_key *pk = pub_keys[i];
-			if (!pk || pk->magic != kPubKeyMagic || pk->key_type != sig_type || !pt_ok(&pk->y)) continue;
-			if (!s[i] || (!m[i] && m_len[i])) continue;
-			const CurveInfo *c = identify(&pk->y);
-			if (!c) continue;
-			if (c != ci) {
-				mixed.store(1);
+			if (!b.ok[i]) continue;
+			uint64_t r[9], e[9];
+			b.mq->from_be_mod(r, b.s[i], b.hlen);                               /* 2. e = -(r mod q) (:486-488) */
+			if (b.mq->is_zero(r)) {                                             /* 3. e == 0: reject (:491-492) */
+				b.ok[i] = 0;
 				continue;
 			}
-			if (s_len[i] != siglen) continue;                       /* 1. (:589) */
-			const uint8_t *sb = s[i] + rlen;
-			bool zero = true;
-			for (size_t j = 0; j < qlen; j++) zero = zero && sb[j] == 0;
-			if (zero || memcmp(sb, qbe, qlen) >= 0) continue;       /* 2. s in ]0, q[ (:592-595) */
-			const eccb200_prj_pt *y = &pk->y;
-			if (fp_is_small(&y->Z, 1)) {
-				fp_to_be(&pubs[i * 2 * plen], &y->X, pl);
-				fp_to_be(&pubs[i * 2 * plen + plen], &y->Y, pl);
-			} else {
-				prj.push_back(i);
-			}
-			ok[i] = 1;
-		}
-	});
-	if (mixed.load()) return -1;
-	std::vector<uint32_t> prj_idx;
-	for (auto &part : prj_parts) prj_idx.insert(prj_idx.end(), part.begin(), part.end());
-	if (!prj_idx.empty()) {
-		std::vector<uint8_t> pb(prj_idx.size() * 3 * plen), abuf(prj_idx.size() * 2 * plen);
-		std::vector<int8_t> st(prj_idx.size());
-		parallel_for((uint32_t)prj_idx.size(), [&](uint32_t lo, uint32_t hi, unsigned) {
-			for (uint32_t k = lo; k < hi; k++) {
-				const eccb200_prj_pt *p = &pub_keys[prj_idx[k]]->y;
-				fp_to_be(&pb[k * 3 * plen], &p->X, pl);
-				fp_to_be(&pb[k * 3 * plen + plen], &p->Y, pl);
-				fp_to_be(&pb[k * 3 * plen + 2 * plen], &p->Z, pl);
-			}
-		});
-		if (eccb200_prj_pt_unique_batch(eng, (uint32_t)prj_idx.size(), pb.data(), abuf.data(), st.data())) return -1;
-		for (size_t k = 0; k < prj_idx.size(); k++) {
-			uint32_t i = prj_idx[k];
-			if (st[k] == 0) memcpy(&pubs[i * 2 * plen], &abuf[k * 2 * plen], 2 * plen);
-			else ok[i] = 0; /* off the curve, or infinity: prj_pt_to_aff fails on it (:614) */
+			b.mq->neg(e, r);
+			memcpy(b.a_of(i), b.s[i] + b.hlen, b.qlen);                         /* 4. W' = sG + eY (:495-498) */
+			b.mq->to_be(b.b_of(i), e);
 		}
 	}
-	/* pass 2: h = H(z || m), e = OS2I(r XOR rightmost(h)) mod q */
-	parallel_for(num, [&](uint32_t lo, uint32_t hi, unsigned) {
+	bool accept(const DsBatch &b, uint32_t i, const uint8_t *W) override
+	{
+		uint8_t rp[128];
+		const unsigned char *in[4] = { W, optimized ? b.m[i] : W + b.plen, optimized ? nullptr : b.m[i], nullptr };
+		uint32_t il[3] = { (uint32_t)b.plen, optimized ? b.m_len[i] : (uint32_t)b.plen, optimized ? 0u : b.m_len[i] };
+		if (b.hm->hfunc_scattered(in, il, rp)) return false;                        /* 5. r' (:500-520) */
+		return memcmp(rp, b.s[i], b.hlen) == 0;                                     /* 6. r == r' (:606) */
+	}
+};
+
+/* ECKCDSA (sig/eckcdsa.c:543-832): r_len = min(|H|, qlen); s in ]0, q[; h = H(z || m) with z = the first block_size
+ * bytes of Y_x || Y_y || 0...; e = OS2I(r XOR rightmost(h)) mod q; W' = sY + eG; r' = rightmost(H(W'_x)) == r. */
+struct EckcdsaScheme : DsScheme {
+	uint8_t qbe[72];
+	size_t rlen = 0, shift = 0, zlen = 0;
+	bool needs_affine_key() const override { return true; } /* z (:601-625): prj_pt_to_aff fails on infinity (:614) */
+	bool setup(DsBatch &b) override
+	{
+		words_to_be(qbe, (int)b.qlen, b.ci->q);
+		zlen = b.hm->block_size;
+		rlen = std::min<size_t>(b.hlen, b.qlen); /* ECKCDSA_R_LEN (sig/eckcdsa.h:28-31) */
+		shift = b.hlen > rlen ? b.hlen - rlen : 0;
+		return zlen != 0;
+	}
+	size_t siglen(const DsBatch &b) const override { return rlen + b.qlen; }            /* 1. (:589) */
+	bool sig_ok(const DsBatch &b, uint32_t i) const override
+	{
+		return be_in_open_range(b.s[i] + rlen, qbe, b.qlen);                         /* 2. s in ]0, q[ (:592-595) */
+	}
+	void scalars(DsBatch &b, uint32_t lo, uint32_t hi) override
+	{
 		std::vector<uint8_t> z(zlen);
 		for (uint32_t i = lo; i < hi; i++) {
-			if (!ok[i]) {
-				memset(&ab[i * 2 * qlen], 0, 2 * qlen);
-				gen_to_be(&pubs[i * 2 * plen], ci); /* keep the batch launchable */
-				continue;
-			}
+			if (!b.ok[i]) continue;
 			std::fill(z.begin(), z.end(), 0);
-			memcpy(z.data(), &pubs[i * 2 * plen], std::min<size_t>(zlen, 2 * plen)); /* 3. z (:601-625) */
+			memcpy(z.data(), b.key_of(i), std::min<size_t>(zlen, 2 * b.plen));   /* 3. z (:601-625) */
 			uint8_t h[128], x[128];
-			const unsigned char *in[3] = { z.data(), m[i], nullptr };
-			uint32_t il[2] = { zlen, m_len[i] };
-			if (hm->hfunc_scattered(in, il, h)) {
-				ok[i] = 0;
+			const unsigned char *in[3] = { z.data(), b.m[i], nullptr };
+			uint32_t il[2] = { (uint32_t)zlen, b.m_len[i] };
+			if (b.hm->hfunc_scattered(in, il, h)) {
+				b.ok[i] = 0;
 				continue;
 			}
-			for (size_t j = 0; j < rlen; j++) x[j] = (uint8_t)(h[shift + j] ^ s[i][j]); /* 4.-5. (:754-762) */
-			eccb200_nn t;
-			be_to_nn(&t, x, (uint32_t)rlen);
-			scalar_mod_to_be(&ab[i * 2 * qlen], &t, ci);                  /* e on G */
-			memcpy(&ab[i * 2 * qlen + qlen], s[i] + rlen, qlen);         /* s on Y */
+			for (size_t j = 0; j < rlen; j++) x[j] = (uint8_t)(h[shift + j] ^ b.s[i][j]); /* 4.-5. (:754-762) */
+			uint64_t e[9];
+			b.mq->from_be_mod(e, x, rlen);
+			b.mq->to_be(b.a_of(i), e);                                           /* e on G */
+			memcpy(b.b_of(i), b.s[i] + rlen, b.qlen);                            /* s on Y: 6. W' = sY + eG (:770-773) */
+		}
+	}
+	bool accept(const DsBatch &b, uint32_t i, const uint8_t *W) override
+	{
+		uint8_t rp[128];
+		const unsigned char *in[2] = { W, nullptr };
+		uint32_t il[1] = { (uint32_t)b.plen };
+		if (b.hm->hfunc_scattered(in, il, rp)) return false;                         /* 7. r' = H(W'_x) (:778-784) */
+		return memcmp(rp + shift, b.s[i], rlen) == 0;                                /* 8.-9. (:794-800) */
+	}
+};
+
+/* x(W') mod q == r, r given as qlen big-endian bytes (nn_mod of the affine x, then nn_cmp) */
+static bool x_mod_q_equals(const DsBatch &b, const uint8_t *W, const uint8_t *r_be)
+{
+	uint64_t x[9], r[9];
+	b.mq->from_be_mod(x, W, b.plen);
+	b.mq->from_be(r, r_be);
+	return b.mq->eq(x, r);
+}
+
+/* leftmost min(8 hlen, bitlen(q)) bits of a digest as an integer mod q: the truncation ECDSA and ECGDSA share
+ * (sig/ecgdsa.c:545-560: nn_rshift_fixedlen by 8 hlen - bitlen(q), nn_mod) */
+static void digest_truncated_mod_q(const DsBatch &b, uint64_t *e, const uint8_t *h, int qbits)
+{
+	uint8_t buf[128];
+	const int hbits = 8 * (int)b.hlen;
+	const int rshift = hbits > qbits ? hbits - qbits : 0;
+	/* h >> rshift, big-endian, still hlen bytes */
+	const int bytes = rshift / 8, bits = rshift % 8;
+	memset(buf, 0, sizeof(buf));
+	for (int j = (int)b.hlen - 1; j >= bytes; j--) {
+		unsigned v = h[j - bytes] >> bits;
+		if (bits && j - bytes - 1 >= 0) v |= (unsigned)h[j - bytes - 1] << (8 - bits);
+		buf[j] = (uint8_t)v;
+	}
+	b.mq->from_be_mod(e, buf, b.hlen);
+}
+
+static int order_bits(const CurveInfo *ci)
+{
+	for (int i = ci->n64 - 1; i >= 0; i--)
+		if (ci->q[i]) return 64 * i + 64 - __builtin_clzll(ci->q[i]);
+	return 0;
+}
+
+/* ECGDSA (sig/ecgdsa.c:413-600): r, s in ]0, q[; e = truncated H(m) mod q; u = r^-1 e, v = r^-1 s; W' = uG + vY;
+ * accept iff W'_x mod q == r.  ECRDSA (sig/ecrdsa.c:417-600): s in ]0, q[, r != 0; h = OS2I(H(m)) mod q (the digest
+ * byte-reversed unless the reference was built with USE_ISO14888_3_ECRDSA, :545-547), 0 replaced by 1; e = h^-1;
+ * u = e s, v = -e r; the same W' and comparison.  One inversion mod q per chunk of items (Montgomery's trick). */
+struct EcgdsaScheme : DsScheme {
+	bool rdsa, iso_rdsa = false;
+	int qbits = 0;
+	explicit EcgdsaScheme(bool r) : rdsa(r) {}
+	bool setup(DsBatch &b) override
+	{
+		qbits = order_bits(b.ci);
+		const char *e = getenv("ECCB200_ECRDSA_ISO14888_3");
+		iso_rdsa = e && atoi(e) != 0;
+		return true;
+	}
+	size_t siglen(const DsBatch &b) const override { return 2 * b.qlen; } /* EC[GR]DSA_SIGLEN (ecgdsa.c:440, ecrdsa.c:443) */
+	bool sig_ok(const DsBatch &b, uint32_t i) const override
+	{
+		uint64_t r[9], s[9];
+		b.mq->from_be(r, b.s[i]);
+		b.mq->from_be(s, b.s[i] + b.qlen);
+		/* (ecgdsa.c:451-457).  ECRDSA's init compares s with q twice and never r (ecrdsa.c:453-456); an r >= q then
+		 * fails at the final comparison with r' < q, so rejecting it here gives the same verdict. */
+		return b.mq->in_open_range(r) && b.mq->in_open_range(s);
+	}
+	void scalars(DsBatch &b, uint32_t lo, uint32_t hi) override
+	{
+		const size_t cnt = hi - lo;
+		std::vector<uint64_t> den(cnt * 9), e(cnt * 9);
+		std::vector<uint32_t> idx;
+		idx.reserve(cnt);
+		for (uint32_t i = lo; i < hi; i++) {
+			if (!b.ok[i]) continue;
+			uint8_t h[128];
+			const unsigned char *in[2] = { b.m[i], nullptr };
+			uint32_t il[1] = { b.m_len[i] };
+			if (b.hm->hfunc_scattered(in, il, h)) {                              /* 2. h = H(m) */
+				b.ok[i] = 0;
+				continue;
+			}
+			const size_t k = idx.size();
+			if (rdsa) {
+				if (!iso_rdsa) std::reverse(h, h + b.hlen);                  /* (ecrdsa.c:545-547) */
+				b.mq->from_be_mod(&den[k * 9], h, b.hlen);                   /* 3. h mod q, 0 -> 1 (:550-555) */
+				if (b.mq->is_zero(&den[k * 9])) den[k * 9] = 1;
+			} else {
+				digest_truncated_mod_q(b, &e[k * 9], h, qbits);              /* 3. e (ecgdsa.c:545-560) */
+				b.mq->from_be(&den[k * 9], b.s[i]);                          /* r, to be inverted (:563) */
+			}
+			idx.push_back(i);
+		}
+		b.mq->inv_many(den.data(), idx.size());
+		for (size_t k = 0; k < idx.size(); k++) {
+			const uint32_t i = idx[k];
+			uint64_t inv[9], r[9], s[9], u[9], v[9];
+			b.mq->to_mont(inv, &den[k * 9]);
+			b.mq->from_be(r, b.s[i]);
+			b.mq->from_be(s, b.s[i] + b.qlen);
+			if (rdsa) {
+				b.mq->mul(u, inv, s);                                        /* 4. u = e s (ecrdsa.c:559) */
+				b.mq->mul(v, inv, r);                                        /* 5. v = -e r (:568-569) */
+				b.mq->neg(v, v);
+			} else {
+				b.mq->mul(u, inv, &e[k * 9]);                                /* 4. u = r^-1 e (ecgdsa.c:564) */
+				b.mq->mul(v, inv, s);                                        /* 5. v = r^-1 s (:568) */
+			}
+			b.mq->to_be(b.a_of(i), u);                                           /* 6. W' = uG + vY */
+			b.mq->to_be(b.b_of(i), v);
+		}
+	}
+	bool accept(const DsBatch &b, uint32_t i, const uint8_t *W) override
+	{
+		return x_mod_q_equals(b, W, b.s[i]);                                         /* 7.-8. r' = W'_x mod q == r */
+	}
+};
+
+/* SM2 (sig/sm2.c:518-700): r, s in ]0, q[; t = r + s mod q != 0; W' = sG + tY finite; Z = H(ENTL || ID || a || b ||
+ * G_x || G_y || Y_x || Y_y) with the ID in the ancillary data (:140-200); e = OS2I(H(Z || m)) mod q;
+ * accept iff (e + W'_x) mod q == r. */
+struct Sm2Scheme : DsScheme {
+	bool takes_adata() const override { return true; }
+	bool needs_affine_key() const override { return true; } /* Z hashes it (prj_pt_export_to_aff_buf, :190) */
+	size_t siglen(const DsBatch &b) const override { return 2 * b.qlen; }            /* SM2_SIGLEN (:546) */
+	bool sig_ok(const DsBatch &b, uint32_t i) const override
+	{
+		uint64_t r[9], s[9];
+		if (!b.id_of(i) || b.id_len_of(i) > 8191) return false;                      /* sm2_compute_Z (:149-151) */
+		b.mq->from_be(r, b.s[i]);
+		b.mq->from_be(s, b.s[i] + b.qlen);
+		return b.mq->in_open_range(r) && b.mq->in_open_range(s);                     /* 1. (:553-557) */
+	}
+	void scalars(DsBatch &b, uint32_t lo, uint32_t hi) override
+	{
+		for (uint32_t i = lo; i < hi; i++) {
+			if (!b.ok[i]) continue;
+			uint64_t r[9], s[9], t[9];
+			b.mq->from_be(r, b.s[i]);
+			b.mq->from_be(s, b.s[i] + b.qlen);
+			b.mq->add(t, r, s);                                                  /* 3. t = r + s mod q (:657) */
+			if (b.mq->is_zero(t)) {                                              /* 4. (:660-661) */
+				b.ok[i] = 0;
+				continue;
+			}
+			memcpy(b.a_of(i), b.s[i] + b.qlen, b.qlen);                          /* 6. W' = sG + tY (:669-671) */
+			b.mq->to_be(b.b_of(i), t);
+		}
+	}
+	bool accept(const DsBatch &b, uint32_t i, const uint8_t *W) override
+	{
+		const eccb200_ec_shortw_crv *crv = b.pub_keys[i]->y.crv;
+		if (!fp_ok(&crv->a) || !fp_ok(&crv->b)) return false;
+		const int pl = (int)b.plen;
+		uint8_t entl[2], ca[72], cb[72], g[144], Z[128], h[128];
+		const uint16_t entlen = (uint16_t)(b.id_len_of(i) * 8);
+		entl[0] = (uint8_t)(entlen >> 8);
+		entl[1] = (uint8_t)entlen;
+		fp_to_be(ca, &crv->a, pl);
+		fp_to_be(cb, &crv->b, pl);
+		gen_to_be(g, b.ci);
+		const unsigned char *zin[7] = { entl, b.id_of(i), ca, cb, g, b.key_of(i), nullptr };
+		uint32_t zl[6] = { 2, b.id_len_of(i), (uint32_t)pl, (uint32_t)pl, (uint32_t)(2 * pl), (uint32_t)(2 * pl) };
+		if (b.hm->hfunc_scattered(zin, zl, Z)) return false;                         /* Z (:160-196) */
+		const unsigned char *in[3] = { Z, b.m[i], nullptr };
+		uint32_t il[2] = { b.hlen, b.m_len[i] };
+		if (b.hm->hfunc_scattered(in, il, h)) return false;                          /* 2. h = H(Z || m) */
+		uint64_t e[9], x[9], r[9];
+		b.mq->from_be_mod(e, h, b.hlen);                                             /* 5. e (:664-666) */
+		b.mq->from_be_mod(x, W, b.plen);                                             /* 8. r' = (e + W'_x) mod q (:679-684) */
+		b.mq->add(x, x, e);
+		b.mq->from_be(r, b.s[i]);
+		return b.mq->eq(x, r);                                                       /* 9. (:687-688) */
+	}
+};
+
+/* BIGN / DBIGN (sig/bign_common.c:742-990), little-endian byte strings: signature s0 (l = qlen / 2 bytes) || s1 (qlen
+ * bytes), s1 < q; h = OS2I_le(H(m)) mod q; W = ((s1 + h) mod q) G + ((s0 + 2^(8l)) mod q) Y finite;
+ * t = first l bytes of BELT-HASH(OID || first 2l bytes of LE(W_x) || LE(W_y) || H(m)), the OID in the ancillary data
+ * (:97-121); accept iff t == s0. */
+struct BignScheme : DsScheme {
+	size_t l = 0;
+	const HashMappingHead *belt = nullptr;
+	std::vector<uint8_t> digests; /* H(m_i), needed again behind the launch */
+	bool takes_adata() const override { return true; }
+	bool setup(DsBatch &b) override
+	{
+		l = b.qlen / 2; /* BIGN_S0_LEN (sig/bign_common.h:34) */
+		get_hash_fn get_hash = resolve_get_hash();
+		if (!get_hash || get_hash(16 /* BELT_HASH, lib_ecc_types.h:130 */, &belt) || !belt || !belt->hfunc_scattered) return false;
+		if (belt->digest_size > 64) return false;
+		digests.assign((size_t)b.num * b.hlen, 0);
+		return true;
+	}
+	size_t siglen(const DsBatch &b) const override { return l + b.qlen; }            /* BIGN_SIGLEN (:775) */
+	static bool oid_of(const uint8_t *adata, uint16_t adata_len, const uint8_t **oid, uint16_t *oid_len)
+	{
+		if (!adata || adata_len < 4) return false;                                   /* bign_get_oid_from_adata (:97-112) */
+		const uint32_t ol = ((uint32_t)adata[0] << 8) | adata[1], tl = ((uint32_t)adata[2] << 8) | adata[3];
+		if (ol + tl > (uint32_t)(adata_len - 4)) return false; /* the reference's sum is an int: no wrap */
+		*oid = adata + 4;
+		*oid_len = (uint16_t)ol;
+		return true;
+	}
+	bool sig_ok(const DsBatch &b, uint32_t i) const override
+	{
+		const uint8_t *oid;
+		uint16_t ol;
+		if (!b.id_of(i) || b.id_len_of(i) == 0) return false;                        /* (:763) */
+		if (!oid_of(b.id_of(i), b.id_len_of(i), &oid, &ol)) return false;            /* fails at finalize (:929) */
+		uint8_t be[72];
+		uint64_t s1[9];
+		for (size_t j = 0; j < b.qlen; j++) be[j] = b.s[i][l + b.qlen - 1 - j];
+		b.mq->from_be(s1, be);
+		return !b.mq->geq_q(s1);                                                     /* 1. s1 < q (:790-791) */
+	}
+	void scalars(DsBatch &b, uint32_t lo, uint32_t hi) override
+	{
+		uint64_t two_l[9] = { 0 }; /* 2^(8l) mod q (:909-912): 8l < bitlen(q) whenever qlen >= 2 */
+		{
+			uint8_t be[72] = { 0 };
+			be[0] = 1;
+			b.mq->from_be_mod(two_l, be, l + 1);
+		}
+		for (uint32_t i = lo; i < hi; i++) {
+			if (!b.ok[i]) continue;
+			uint8_t *hd = &digests[(size_t)i * b.hlen], hr[128], be[72];
+			const unsigned char *in[2] = { b.m[i], nullptr };
+			uint32_t il[1] = { b.m_len[i] };
+			if (b.hm->hfunc_scattered(in, il, hd)) {                             /* 2. h = H(m) */
+				b.ok[i] = 0;
+				continue;
+			}
+			std::reverse_copy(hd, hd + b.hlen, hr);                              /* (:898-900) */
+			uint64_t h[9], s1[9], s0[9], u[9], v[9];
+			b.mq->from_be_mod(h, hr, b.hlen);
+			for (size_t j = 0; j < b.qlen; j++) be[j] = b.s[i][l + b.qlen - 1 - j];
+			b.mq->from_be(s1, be);
+			b.mq->add(u, h, s1);                                                 /* (s1 + h) mod q (:906) */
+			for (size_t j = 0; j < l; j++) be[j] = b.s[i][l - 1 - j];
+			b.mq->from_be_mod(s0, be, l);
+			b.mq->add(v, two_l, s0);                                             /* (s0 + 2^(8l)) mod q (:909-913) */
+			b.mq->to_be(b.a_of(i), u);                                           /* 3. W (:916-918) */
+			b.mq->to_be(b.b_of(i), v);
+		}
+	}
+	bool accept(const DsBatch &b, uint32_t i, const uint8_t *W) override
+	{
+		const uint8_t *oid = nullptr;
+		uint16_t ol = 0;
+		if (!oid_of(b.id_of(i), b.id_len_of(i), &oid, &ol)) return false;
+		uint8_t le[144], hb[64], t[72];
+		for (size_t j = 0; j < b.plen; j++) {                                        /* FE2OS(W_x) || FE2OS(W_y) (:932-936) */
+			le[j] = W[b.plen - 1 - j];
+			le[b.plen + j] = W[2 * b.plen - 1 - j];
+		}
+		const unsigned char *in[4] = { oid, le, &digests[(size_t)i * b.hlen], nullptr };
+		uint32_t il[3] = { ol, (uint32_t)(2 * l), b.hlen };
+		if (belt->hfunc_scattered(in, il, hb)) return false;                         /* 6. (:927-944) */
+		memset(t, 0, sizeof(t));
+		memcpy(t, hb, std::min<size_t>(l, belt->digest_size));                       /* (:946-947) */
+		return memcmp(t, b.s[i], l) == 0;                                            /* 10. t == s0 (:950-951) */
+	}
+};
+
+static int verify_batch_double_smul(DsScheme &sch, const uint8_t **s, const uint8_t *s_len,
+				    const eccb200_ec_pub_key **pub_keys, const uint8_t **m, const uint32_t *m_len,
+				    uint32_t num, int sig_type, int hash_type, const uint8_t **adata,
+				    const uint16_t *adata_len)
+{
+	t_verdicts.assign(num, -1);
+	if (num == 0) return -1;
+	if (!s || !s_len || !pub_keys || !m || !m_len) return -1;
+	if (adata && !sch.takes_adata())
+		for (uint32_t i = 0; i < num; i++)
+			if (adata[i]) return -1;
+	get_hash_fn get_hash = resolve_get_hash();
+	if (!get_hash) return -1;
+	DsBatch b;
+	if (get_hash(hash_type, &b.hm) || !b.hm || !b.hm->hfunc_scattered) return -1;
+	b.hlen = b.hm->digest_size;
+	if (b.hlen == 0 || b.hlen > 128) return -1;
+	for (uint32_t i = 0; i < num && !b.ci; i++) {
+		const eccb200_ec_pub_key *pk = pub_keys[i];
+		if (pk && pk->magic == kPubKeyMagic && pk->key_type == sig_type && pt_ok(&pk->y)) b.ci = identify(&pk->y);
+	}
+	if (!b.ci) return -1;
+	const CurveInfo *ci = b.ci;
+	Engine engine = acquire(ci->id, num);
+	eccb200_ctx *eng = engine.ctx;
+	if (!eng) return -1;
+	const ModQ mq(ci);
+	const int pl = ci->plen;
+	const size_t plen = (size_t)ci->plen, qlen = (size_t)ci->qlen;
+	b.num = num;
+	b.plen = plen;
+	b.qlen = qlen;
+	b.s = s;
+	b.s_len = s_len;
+	b.pub_keys = pub_keys;
+	b.m = m;
+	b.m_len = m_len;
+	b.adata = adata;
+	b.adata_len = adata_len;
+	b.mq = &mq;
+	b.ab = engine.slot->st[0].get(num * 2 * qlen);
+	b.pubs = engine.slot->st[1].get(num * 2 * plen);
+	uint8_t *wout = engine.slot->st[2].get(num * 2 * plen);
+	int8_t *status = (int8_t *)engine.slot->st[3].get(num);
+	if (!b.ab || !b.pubs || !wout || !status) return -1;
+	if (!sch.setup(b)) return -1;
+	const size_t siglen = sch.siglen(b);
+	b.ok.assign(num, 0);
+	std::vector<uint8_t> key_inf(num, 0);
+	std::atomic<int> mixed{ 0 };
+	std::vector<std::vector<uint32_t>> prj_parts(64);
+	/* pass 1: struct and signature checks; affine keys are marshalled, projective ones listed for the device */
+	parallel_for(num, [&](uint32_t lo, uint32_t hi, unsigned t) {
+		std::vector<uint32_t> &prj = prj_parts[t];
+		for (uint32_t i = lo; i < hi; i++) {
+			memset(b.a_of(i), 0, 2 * qlen);
+			memset(&b.pubs[i * 2 * plen], 0, 2 * plen);
+			const eccb200_ec_pub_key *pk = pub_keys[i];
+			if (!pk || pk->magic != kPubKeyMagic || pk->key_type != sig_type || !pt_ok(&pk->y)) continue;
+			if (!s[i] || (!m[i] && m_len[i])) continue;
+			const CurveInfo *c = identify(&pk->y);
+			if (!c) continue;
+			if (c != ci) {
+				mixed.store(1);
+				continue;
+			}
+			if (s_len[i] != siglen) continue;
+			if (!sch.sig_ok(b, i)) continue;
+			const eccb200_prj_pt *y = &pk->y;
+			if (fp_is_small(&y->Z, 1)) {
+				fp_to_be(&b.pubs[i * 2 * plen], &y->X, pl);
+				fp_to_be(&b.pubs[i * 2 * plen + plen], &y->Y, pl);
+			} else {
+				prj.push_back(i);
+			}
+			b.ok[i] = 1;
 		}
 	});
-	if (eccb200_double_smul_batch(eng, num, ab, pubs, wout, status)) return -1; /* 6. W' = sY + eG (:770-773) */
+	if (mixed.load()) return -1;
+	std::vector<uint32_t> prj_idx;
+	for (auto &part : prj_parts) prj_idx.insert(prj_idx.end(), part.begin(), part.end());
+	if (!prj_idx.empty()) {
+		std::vector<uint8_t> pb(prj_idx.size() * 3 * plen), abuf(prj_idx.size() * 2 * plen);
+		std::vector<int8_t> st(prj_idx.size());
+		parallel_for((uint32_t)prj_idx.size(), [&](uint32_t lo, uint32_t hi, unsigned) {
+			for (uint32_t k = lo; k < hi; k++) {
+				const eccb200_prj_pt *p = &pub_keys[prj_idx[k]]->y;
+				fp_to_be(&pb[k * 3 * plen], &p->X, pl);
+				fp_to_be(&pb[k * 3 * plen + plen], &p->Y, pl);
+				fp_to_be(&pb[k * 3 * plen + 2 * plen], &p->Z, pl);
+			}
+		});
+		if (eccb200_prj_pt_unique_batch(eng, (uint32_t)prj_idx.size(), pb.data(), abuf.data(), st.data())) return -1;
+		for (size_t k = 0; k < prj_idx.size(); k++) {
+			const uint32_t i = prj_idx[k];
+			if (st[k] == 0) memcpy(&b.pubs[i * 2 * plen], &abuf[k * 2 * plen], 2 * plen);
+			else if (st[k] == 1 && !sch.needs_affine_key()) key_inf[i] = 1; /* b * infinity = infinity: W' = a*G */
+			else b.ok[i] = 0; /* off the curve; or infinity where the scheme exports the affine key */
+		}
+	}
+	/* pass 2: the scheme's scalars a, b */
+	parallel_for(num, [&](uint32_t lo, uint32_t hi, unsigned) { sch.scalars(b, lo, hi); });
+	for (uint32_t i = 0; i < num; i++) {
+		if (!b.ok[i]) { /* keep the batch launchable: rejected slots multiply the generator by zero */
+			memset(b.a_of(i), 0, 2 * qlen);
+			gen_to_be(&b.pubs[i * 2 * plen], ci);
+		} else if (key_inf[i]) {
+			memset(b.b_of(i), 0, qlen);
+			gen_to_be(&b.pubs[i * 2 * plen], ci);
+		}
+	}
+	if (eccb200_double_smul_batch(eng, num, b.ab, b.pubs, wout, status)) return -1;
 	g_verifies += num;
+	/* pass 3: the scheme's acceptance test on the affine W' */
 	std::vector<int8_t> verdict(num, -1);
 	parallel_for(num, [&](uint32_t lo, uint32_t hi, unsigned) {
 		for (uint32_t i = lo; i < hi; i++) {
-			if (!ok[i] || status[i] != 0) continue; /* infinity: prj_pt_unique fails (:773) */
-			uint8_t rp[128];
-			const unsigned char *in[2] = { &wout[i * 2 * plen], nullptr };
-			uint32_t il[1] = { (uint32_t)plen };
-			if (hm->hfunc_scattered(in, il, rp)) continue;                /* 7. r' = H(W'_x) (:778-784) */
-			verdict[i] = memcmp(rp + shift, s[i], rlen) == 0 ? 0 : -1;   /* 8.-9. (:794-800) */
+			if (!b.ok[i] || status[i] != 0) continue; /* W' at infinity: prj_pt_unique / the explicit test fails */
+			verdict[i] = sch.accept(b, i, &wout[i * 2 * plen]) ? 0 : -1;
 		}
 	});
 	int all = 0;
@@ -1014,6 +1430,34 @@ static int verify_batch_eckcdsa(const uint8_t **s, const uint8_t *s_len, const e
 		if (verdict[i]) all = -1;
 	t_verdicts.assign(verdict.begin(), verdict.end());
 	return all;
+}
+
+/* the scheme object for an ec_alg_type served through verify_batch_double_smul (lib_ecc_types.h:22-80), or null */
+static std::unique_ptr<DsScheme> ds_scheme_of(int sig_type)
+{
+	switch (sig_type) {
+	case 2: return std::unique_ptr<DsScheme>(new EckcdsaScheme());
+	case 3: return std::unique_ptr<DsScheme>(new EcsdsaScheme(false));
+	case 4: return std::unique_ptr<DsScheme>(new EcsdsaScheme(true)); /* ECOSDSA */
+	case 6: return std::unique_ptr<DsScheme>(new EcgdsaScheme(false));
+	case 7: return std::unique_ptr<DsScheme>(new EcgdsaScheme(true)); /* ECRDSA */
+	case 8: return std::unique_ptr<DsScheme>(new Sm2Scheme());
+	case 18:
+	case 19: return std::unique_ptr<DsScheme>(new BignScheme()); /* BIGN, DBIGN (deterministic nonce: same verification) */
+	default: return nullptr;
+	}
+}
+
+static int verify_batch_ds(const uint8_t **s, const uint8_t *s_len, const eccb200_ec_pub_key **pub_keys, const uint8_t **m,
+			   const uint32_t *m_len, uint32_t num, int sig_type, int hash_type, const uint8_t **adata,
+			   const uint16_t *adata_len)
+{
+	std::unique_ptr<DsScheme> sch = ds_scheme_of(sig_type);
+	if (!sch) {
+		t_verdicts.assign(num, -1);
+		return -1;
+	}
+	return verify_batch_double_smul(*sch, s, s_len, pub_keys, m, m_len, num, sig_type, hash_type, adata, adata_len);
 }
 
 extern "C" int eccb200_dropin_ecdsa_verify_batch(const uint8_t **s, const uint8_t *s_len,
@@ -1052,9 +1496,8 @@ extern "C" int eccb200_dropin_ecsdsa_verify_batch(const uint8_t **s, const uint8
 {
 	(void)scratch_pad_area;
 	(void)scratch_pad_area_len;
-	(void)adata_len;
 	if (sig_type != 3 /* ECSDSA */ && sig_type != 4 /* ECOSDSA */) return -1;
-	return verify_batch_ecsdsa(sig_type == 4, s, s_len, pub_keys, m, m_len, num, sig_type, hash_type, adata);
+	return verify_batch_ds(s, s_len, pub_keys, m, m_len, num, sig_type, hash_type, adata, adata_len);
 }
 
 /* ECKCDSA (sig_type 2): also left at unsupported_verify_batch by the reference */
@@ -1066,10 +1509,31 @@ extern "C" int eccb200_dropin_eckcdsa_verify_batch(const uint8_t **s, const uint
 {
 	(void)scratch_pad_area;
 	(void)scratch_pad_area_len;
-	(void)adata_len;
 	if (sig_type != 2 /* ECKCDSA */) return -1;
-	return verify_batch_eckcdsa(s, s_len, pub_keys, m, m_len, num, sig_type, hash_type, adata);
+	return verify_batch_ds(s, s_len, pub_keys, m, m_len, num, sig_type, hash_type, adata, adata_len);
 }
+
+/*
+ * ECGDSA (6), ECRDSA (7), SM2 (8), BIGN (18) / DBIGN (19): all left at unsupported_verify_batch by the reference
+ * (sig/sig_algs_internal.h).  Their EC core W' = a*G + b*Y is one device launch for the batch; the mod-q scalar
+ * preparation (with ONE inversion per chunk of items where the scheme inverts), the hashes and the comparison stay on the
+ * host.  SM2 and BIGN read their ancillary data (the signer's ID; the hash OID) from adata[i] / adata_len[i].
+ */
+#define ECCB200_DS_ADAPTER(name, cond)                                                                                  \
+	extern "C" int name(const uint8_t **s, const uint8_t *s_len, const eccb200_ec_pub_key **pub_keys, const uint8_t **m, \
+			    const uint32_t *m_len, uint32_t num, int sig_type, int hash_type, const uint8_t **adata,      \
+			    const uint16_t *adata_len, void *scratch_pad_area, uint32_t *scratch_pad_area_len)            \
+	{                                                                                                               \
+		(void)scratch_pad_area;                                                                                 \
+		(void)scratch_pad_area_len;                                                                             \
+		if (!(cond)) return -1;                                                                                 \
+		return verify_batch_ds(s, s_len, pub_keys, m, m_len, num, sig_type, hash_type, adata, adata_len);       \
+	}
+ECCB200_DS_ADAPTER(eccb200_dropin_ecgdsa_verify_batch, sig_type == 6)
+ECCB200_DS_ADAPTER(eccb200_dropin_ecrdsa_verify_batch, sig_type == 7)
+ECCB200_DS_ADAPTER(eccb200_dropin_sm2_verify_batch, sig_type == 8)
+ECCB200_DS_ADAPTER(eccb200_dropin_bign_verify_batch, sig_type == 18 || sig_type == 19)
+#undef ECCB200_DS_ADAPTER
 
 /* BIP0340: a replacement for the reference's own bip0340_verify_batch (sig/bip0340.c:1296) in the same slot */
 extern "C" int eccb200_dropin_bip0340_verify_batch(const uint8_t **s, const uint8_t *s_len,
@@ -1109,9 +1573,11 @@ extern "C" int eccb200_dropin_ec_verify(const uint8_t *sig, uint8_t siglen, cons
 					const uint8_t *adata, uint16_t adata_len)
 {
 	Scheme sc = kEcdsa;
-	const bool post_hash = (sig_type == 2 || sig_type == 3 || sig_type == 4); /* ECKCDSA / ECSDSA / ECOSDSA: these hash
-										    * the recomputed point */
-	bool ours = (post_hash || scheme_of(sig_type, &sc)) && !adata && adata_len == 0 && sig && pub_key &&
+	std::unique_ptr<DsScheme> ds = ds_scheme_of(sig_type); /* the schemes built on W' = a*G + b*Y with host steps around */
+	/* ancillary data: SM2 and BIGN need theirs (a call without is left to the reference, which rejects it); a call
+	 * of any other scheme that carries some is forwarded untouched */
+	const bool adata_fits = ds && ds->takes_adata() ? adata != nullptr : (!adata && adata_len == 0);
+	bool ours = (ds || scheme_of(sig_type, &sc)) && adata_fits && sig && pub_key &&
 		    pub_key->magic == kPubKeyMagic &&
 		    pub_key->key_type == sig_type && pt_ok(&pub_key->y) && identify(&pub_key->y) != nullptr &&
 		    resolve_get_hash() != nullptr;
@@ -1128,8 +1594,9 @@ extern "C" int eccb200_dropin_ec_verify(const uint8_t *sig, uint8_t siglen, cons
 	const eccb200_ec_pub_key *pk[1] = { pub_key };
 	const uint8_t *mp[1] = { m };
 	const uint32_t ml[1] = { mlen };
-	if (sig_type == 2) return verify_batch_eckcdsa(sp, sl, pk, mp, ml, 1, sig_type, hash_type, nullptr);
-	if (post_hash) return verify_batch_ecsdsa(sig_type == 4, sp, sl, pk, mp, ml, 1, sig_type, hash_type, nullptr);
+	const uint8_t *ap[1] = { adata };
+	const uint16_t al[1] = { adata_len };
+	if (ds) return verify_batch_double_smul(*ds, sp, sl, pk, mp, ml, 1, sig_type, hash_type, adata ? ap : nullptr, al);
 	return verify_batch_common(sc, sp, sl, pk, mp, ml, 1, sig_type, hash_type, nullptr);
 }
 
@@ -1154,7 +1621,7 @@ typedef int (*batch_supported_sig)(int, int *);
 static bool batch_scheme_served(int sig_type)
 {
 	Scheme sc;
-	return scheme_of(sig_type, &sc) || sig_type == 2 || sig_type == 3 || sig_type == 4;
+	return scheme_of(sig_type, &sc) || ds_scheme_of(sig_type) != nullptr;
 }
 
 extern "C" int eccb200_dropin_ec_verify_batch(const uint8_t **s, const uint8_t *s_len,
@@ -1163,9 +1630,10 @@ extern "C" int eccb200_dropin_ec_verify_batch(const uint8_t **s, const uint8_t *
 					      const uint8_t **adata, const uint16_t *adata_len, void *scratch_pad_area,
 					      uint32_t *scratch_pad_area_len)
 {
+	std::unique_ptr<DsScheme> ds = ds_scheme_of(sig_type);
 	bool ours = batch_scheme_served(sig_type) && num > 0 && s && s_len && pub_keys && m && m_len &&
 		    resolve_get_hash() != nullptr;
-	if (ours && adata)
+	if (ours && adata && !(ds && ds->takes_adata())) /* ancillary data on a scheme that has none: not ours */
 		for (uint32_t i = 0; i < num && ours; i++) ours = adata[i] == nullptr;
 	if (ours) { /* a curve this layer knows, named by the first well-formed key */
 		const CurveInfo *ci = nullptr;
@@ -1184,9 +1652,7 @@ extern "C" int eccb200_dropin_ec_verify_batch(const uint8_t **s, const uint8_t *
 			    : -1;
 	}
 	Scheme sc = kEcdsa;
-	if (sig_type == 2) return verify_batch_eckcdsa(s, s_len, pub_keys, m, m_len, num, sig_type, hash_type, adata);
-	if (sig_type == 3 || sig_type == 4)
-		return verify_batch_ecsdsa(sig_type == 4, s, s_len, pub_keys, m, m_len, num, sig_type, hash_type, adata);
+	if (ds) return verify_batch_double_smul(*ds, s, s_len, pub_keys, m, m_len, num, sig_type, hash_type, adata, adata_len);
 	scheme_of(sig_type, &sc);
 	return verify_batch_common(sc, s, s_len, pub_keys, m, m_len, num, sig_type, hash_type, adata);
 }

@@ -99,6 +99,24 @@ def hostsim_lib() -> ctypes.CDLL:
     return _cache["hostsim"]
 
 
+STUB_SO = os.path.join(ROOT, "tests", "hostsim", "_build", "libecc_b200_stub.so")
+
+
+def engine_stub_so() -> str:
+    """Path of the TEST-ONLY stand-in for libecc_b200.so (tests/hostsim/engine_stub.cpp: the engine entry points the
+    drop-in calls, served by the host build of the device algorithms), built on demand.  Preloaded in front of the
+    C harness it lets the CPU suite run the drop-in's host logic against the unmodified reference."""
+    src = os.path.join(ROOT, "tests", "hostsim", "engine_stub.cpp")
+    deps = [src, os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")] + [
+        os.path.join(ROOT, "libecc_b200", "csrc", f) for f in
+        ("fp.cuh", "ec.cuh", "msm_core.cuh", "curve_constants.inc", "sha3.cuh", "sha3_constants.inc")]
+    if not os.path.exists(STUB_SO) or os.path.getmtime(STUB_SO) < max(os.path.getmtime(d) for d in deps):
+        os.makedirs(os.path.dirname(STUB_SO), exist_ok=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", src, "-o", STUB_SO, "-lpthread"],
+                       check=True, capture_output=True)
+    return STUB_SO
+
+
 def golden(name: str):
     path = os.path.join(GOLDEN, name)
     if path.endswith(".gz"):
