@@ -655,15 +655,21 @@ static int verify_batch_common(Scheme sc, const uint8_t **s, const uint8_t *s_le
 		/* every item's key through the batched prj_pt_unique (items refused above carry Z = 0 and are ignored) */
 		if (eccb200_prj_pt_unique_batch(eng, num, prj, pubs, prj_st)) return -1;
 		parallel_for(num, [&](uint32_t lo, uint32_t hi, unsigned) {
-			for (uint32_t i = lo; i < hi; i++)
-				if (ok[i] && prj_st[i] != 0) {
-					ok[i] = 0; /* off the curve, or the point at infinity: BIP0340's prj_pt_unique fails on it
-						    * (sig/bip0340.c:428); ECFSDSA with a key at infinity is rejected too — a documented
-						    * divergence (the reference would accept it iff s*G == r).  ECDSA keys are
-						    * normalised on the device, where a key at infinity continues with W' = u*G like the
-						    * reference's ec_verify. */
-					memset(&pubs[i * 2 * plen], 0, 2 * plen);
+			for (uint32_t i = lo; i < hi; i++) {
+				if (!ok[i] || prj_st[i] == 0) continue;
+				if (sc == kEcfsdsa && prj_st[i] == 1) {
+					/* ECFSDSA, key at infinity: the reference goes on with e*Y = infinity, W' = s*G
+					 * (sig/ecfsdsa.c:594-600 on the complete formulas) and accepts iff s*G == r.  Same here: the
+					 * item runs with e = 0 (an all-zero digest) on a dummy base. */
+					gen_to_be(&pubs[i * 2 * plen], ci);
+					memset(&dig[i * (size_t)hlen], 0, hlen);
+					continue;
 				}
+				ok[i] = 0; /* off the curve; or BIP0340 with a key at infinity: prj_pt_unique fails on it
+					    * (sig/bip0340.c:428).  ECDSA keys are normalised on the device, where a key at infinity
+					    * continues with W' = u*G like the reference's ec_verify. */
+				memset(&pubs[i * 2 * plen], 0, 2 * plen);
+			}
 		});
 	}
 	if (sc == kBip0340) {
@@ -734,7 +740,6 @@ static int verify_batch_common(Scheme sc, const uint8_t **s, const uint8_t *s_le
 	return all;
 }
 
-/* big-endian bytes -> nn-style little-endian 64-bit words (at most kMaxWords) */
 /*
  * Arithmetic modulo the group order q on the host, for the scalar preparations that multiply or invert (the
  * reference's nn_mod_mul / nn_modinv / nn_mod_add of sig/ecgdsa.c:563-569, sig/ecrdsa.c:556-570, sig/sm2.c:657,

@@ -319,6 +319,31 @@ static int run_direct(const char *dropin_path)
 				CHECK(v[i] == want, "%s ecfsdsa verdict[%d] = %d, reference ec_verify says %d", names[c], i, v[i], want);
 			}
 			CHECK(v[3] == -1 && v[7] == -1 && v[11] == -1, "corrupted ECFSDSA items not flagged");
+			/* a key at infinity: e*Y = infinity, W' = s*G (sig/ecfsdsa.c:597-600), so (r = k*G, s = k) verifies under it
+			 * in the reference whatever the message; the layer must agree, and reject it once s is off by one */
+			{
+				static ec_pub_key kinf;
+				nn k;
+				prj_pt R;
+				u8 sg[3 * 66], kb[66];
+				const u8 *sp1[1] = { sg }, *mp1[1] = { msgs[0] };
+				const ec_pub_key *pk1[1] = { &kinf };
+				kinf = kp[0].pub_key;
+				CHECK(!prj_pt_zero(&kinf.y), "zero key");
+				for (int j = 0; j < qlen; j++) kb[j] = rnd8();
+				CHECK(!nn_init_from_buf(&k, kb, qlen) && !nn_mod(&k, &k, &params.ec_gen_order), "k");
+				CHECK(!prj_pt_mul(&R, &k, &params.ec_gen) && !prj_pt_export_to_aff_buf(&R, sg, (u32)(2 * plen)), "kG");
+				CHECK(!nn_export_to_buf(sg + 2 * plen, qlen, &k), "s = k");
+				for (int pass = 0; pass < 2; pass++) {
+					int want = ec_verify(sg, sl[0], &kinf, msgs[0], ml[0], ECFSDSA, ht, NULL, 0);
+					CHECK(want == (pass ? -1 : 0), "%s: reference verdict %d on the crafted ECFSDSA signature, pass %d", names[c], want, pass);
+					CHECK(gpu_everify(sg, sl[0], &kinf, msgs[0], ml[0], ECFSDSA, ht, NULL, 0) == want,
+					      "%s ECFSDSA key at infinity: shim differs from the reference (%d)", names[c], want);
+					CHECK(gpu_fsbatch(sp1, sl, pk1, mp1, ml, 1, ECFSDSA, ht, NULL, NULL, NULL, NULL) == want,
+					      "%s ECFSDSA key at infinity: batch adapter differs from the reference (%d)", names[c], want);
+					sg[2 * plen + qlen - 1] ^= 1;
+				}
+			}
 		}
 		/* ---- ECSDSA / ECOSDSA: batch adapter (W' = sG + eY on the device, hashing of W' with the reference's src/hash)
 		 * and ec_verify shim against the reference's ec_verify */
