@@ -36,7 +36,7 @@ template <class C> static int import_prj(Aff<C> &P, const uint8_t *b)
 	F::to_mont(X, x);
 	F::to_mont(Y, y);
 	F::to_mont(Z, z);
-	if (F::is_zero(Z)) return (F::is_zero(X) && !F::is_zero(Y)) ? 1 : -1; /* Y^2 * 0 == X^3: X must be 0 */
+	if (F::is_zero(Z)) return F::is_zero(X) ? 1 : -1; /* Y^2 * 0 == X^3: X must be 0 (k_prj_load accepts any Y then) */
 	Fe<N> zi;
 	F::inv(zi, Z);
 	F::mul(P.x, X, zi);
