@@ -14,6 +14,9 @@
 #include <dlfcn.h>
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <string>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -211,9 +214,12 @@ void release_all()
 /* host threads for the marshalling loops of the batch entry points */
 template <class F> void parallel_for(uint32_t n, F f)
 {
-	unsigned hw = std::thread::hardware_concurrency();
-	if (const char *e = getenv("ECCB200_DROPIN_THREADS")) hw = (unsigned)atoi(e);
-	unsigned T = std::min<unsigned>(std::min<unsigned>(hw ? hw : 1, 32u), n / 2048u + 1u);
+	unsigned hw = std::thread::hardware_concurrency(), cap = 32u;
+	if (const char *e = getenv("ECCB200_DROPIN_THREADS")) { /* an explicit request may exceed the default cap of 32 */
+		hw = (unsigned)atoi(e);
+		cap = 128u;
+	}
+	unsigned T = std::min<unsigned>(std::min<unsigned>(hw ? hw : 1, cap), n / 2048u + 1u);
 	if (T <= 1) {
 		f(0u, n, 0u);
 		return;
@@ -325,9 +331,14 @@ int mul_batch(eccb200_prj_pt *out, const eccb200_nn *m, const eccb200_prj_pt *in
 		if (ret) memcpy(ret, rc.data(), n * sizeof(int));
 		return -1;
 	}
+	auto engine_failed = [&]() { /* no per-item result exists: every item reports -1 */
+		if (ret)
+			for (uint32_t i = 0; i < n; i++) ret[i] = -1;
+		return -1;
+	};
 	Engine engine = acquire(ci->id, n);
 	eccb200_ctx *eng = engine.ctx;
-	if (!eng) return -1;
+	if (!eng) return engine_failed();
 	const size_t plen = (size_t)ci->plen, qlen = (size_t)ci->qlen;
 	const int pl = ci->plen;
 	std::vector<uint8_t> scalars(n * qlen), points(n * 2 * plen), outb(n * 2 * plen);
@@ -349,7 +360,7 @@ int mul_batch(eccb200_prj_pt *out, const eccb200_nn *m, const eccb200_prj_pt *in
 			fp_to_be(&pb[k * 3 * plen + plen], &p->Y, pl);
 			fp_to_be(&pb[k * 3 * plen + 2 * plen], &p->Z, pl);
 		}
-		if (eccb200_prj_pt_unique_batch(eng, (uint32_t)prj_idx.size(), pb.data(), ab.data(), st.data())) return -1;
+		if (eccb200_prj_pt_unique_batch(eng, (uint32_t)prj_idx.size(), pb.data(), ab.data(), st.data())) return engine_failed();
 		for (size_t k = 0; k < prj_idx.size(); k++) {
 			uint32_t i = prj_idx[k];
 			if (st[k] < 0) rc[i] = -1;                      /* not on the curve: prj_pt_mul fails (:1767) */
@@ -382,7 +393,7 @@ int mul_batch(eccb200_prj_pt *out, const eccb200_nn *m, const eccb200_prj_pt *in
 		if (rc[i]) gen_to_be(&points[i * 2 * plen], ci); /* keep the batch launchable: rejected slots get G */
 	if (eccb200_prj_pt_mul_batch(eng, n, scalars.data(), all_gen ? nullptr : points.data(), outb.data(),
 				     status.data()))
-		return -1;
+		return engine_failed();
 	for (uint32_t i = 0; i < n; i++) {
 		if (rc[i] == 0 && status[i] < 0) rc[i] = -1;
 		if (rc[i]) {
@@ -1309,6 +1320,27 @@ struct BignScheme : DsScheme {
 	}
 };
 
+/* ECCB200_DROPIN_TIMING=1: wall-clock time of the phases of a batch on stderr (where the host side of an adapter goes) */
+struct PhaseClock {
+	bool on;
+	std::chrono::steady_clock::time_point t0;
+	std::string line;
+	PhaseClock() : on(getenv("ECCB200_DROPIN_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+	void lap(const char *name)
+	{
+		if (!on) return;
+		const auto t1 = std::chrono::steady_clock::now();
+		char buf[64];
+		snprintf(buf, sizeof buf, " %s %.2f ms", name, std::chrono::duration<double, std::milli>(t1 - t0).count());
+		line += buf;
+		t0 = t1;
+	}
+	void report(uint32_t n) const
+	{
+		if (on) fprintf(stderr, "dropin timing (%u items):%s\n", n, line.c_str());
+	}
+};
+
 static int verify_batch_double_smul(DsScheme &sch, const uint8_t **s, const uint8_t *s_len,
 				    const eccb200_ec_pub_key **pub_keys, const uint8_t **m, const uint32_t *m_len,
 				    uint32_t num, int sig_type, int hash_type, const uint8_t **adata,
@@ -1358,14 +1390,21 @@ static int verify_batch_double_smul(DsScheme &sch, const uint8_t **s, const uint
 	const size_t siglen = sch.siglen(b);
 	b.ok.assign(num, 0);
 	std::vector<uint8_t> key_inf(num, 0);
-	std::atomic<int> mixed{ 0 };
-	std::vector<std::vector<uint32_t>> prj_parts(64);
-	/* pass 1: struct and signature checks; affine keys are marshalled, projective ones listed for the device */
-	parallel_for(num, [&](uint32_t lo, uint32_t hi, unsigned t) {
-		std::vector<uint32_t> &prj = prj_parts[t];
+	std::atomic<int> mixed{ 0 }, any_prj{ 0 };
+	/* an ec_pub_key made by ec_key_pair_gen holds a projective point with Z != 1: X || Y || Z of every item goes into
+	 * page-locked staging and, if any key needs it, through ONE batched prj_pt_unique on the device, which writes the
+	 * affine keys straight into the staging the double-scalar launch reads (as verify_batch_common does) */
+	uint8_t *prj = engine.slot->st[4].get(num * 3 * plen);
+	int8_t *prj_st = (int8_t *)engine.slot->st[5].get(num);
+	if (!prj || !prj_st) return -1;
+	PhaseClock clk;
+	/* pass 1: struct and signature checks, key marshalling */
+	parallel_for(num, [&](uint32_t lo, uint32_t hi, unsigned) {
+		bool saw_prj = false;
 		for (uint32_t i = lo; i < hi; i++) {
 			memset(b.a_of(i), 0, 2 * qlen);
 			memset(&b.pubs[i * 2 * plen], 0, 2 * plen);
+			memset(&prj[i * 3 * plen], 0, 3 * plen);
 			const eccb200_ec_pub_key *pk = pub_keys[i];
 			if (!pk || pk->magic != kPubKeyMagic || pk->key_type != sig_type || !pt_ok(&pk->y)) continue;
 			if (!s[i] || (!m[i] && m_len[i])) continue;
@@ -1378,39 +1417,36 @@ static int verify_batch_double_smul(DsScheme &sch, const uint8_t **s, const uint
 			if (s_len[i] != siglen) continue;
 			if (!sch.sig_ok(b, i)) continue;
 			const eccb200_prj_pt *y = &pk->y;
-			if (fp_is_small(&y->Z, 1)) {
+			const bool affine = fp_is_small(&y->Z, 1);
+			if (affine) {
 				fp_to_be(&b.pubs[i * 2 * plen], &y->X, pl);
 				fp_to_be(&b.pubs[i * 2 * plen + plen], &y->Y, pl);
-			} else {
-				prj.push_back(i);
 			}
+			saw_prj = saw_prj || !affine;
+			fp_to_be(&prj[i * 3 * plen], &y->X, pl);
+			fp_to_be(&prj[i * 3 * plen + plen], &y->Y, pl);
+			fp_to_be(&prj[i * 3 * plen + 2 * plen], &y->Z, pl);
 			b.ok[i] = 1;
 		}
+		if (saw_prj) any_prj.store(1);
 	});
 	if (mixed.load()) return -1;
-	std::vector<uint32_t> prj_idx;
-	for (auto &part : prj_parts) prj_idx.insert(prj_idx.end(), part.begin(), part.end());
-	if (!prj_idx.empty()) {
-		std::vector<uint8_t> pb(prj_idx.size() * 3 * plen), abuf(prj_idx.size() * 2 * plen);
-		std::vector<int8_t> st(prj_idx.size());
-		parallel_for((uint32_t)prj_idx.size(), [&](uint32_t lo, uint32_t hi, unsigned) {
-			for (uint32_t k = lo; k < hi; k++) {
-				const eccb200_prj_pt *p = &pub_keys[prj_idx[k]]->y;
-				fp_to_be(&pb[k * 3 * plen], &p->X, pl);
-				fp_to_be(&pb[k * 3 * plen + plen], &p->Y, pl);
-				fp_to_be(&pb[k * 3 * plen + 2 * plen], &p->Z, pl);
+	clk.lap("checks");
+	if (any_prj.load()) {
+		/* every item's key through the batched prj_pt_unique (items refused above carry Z = 0 and are ignored) */
+		if (eccb200_prj_pt_unique_batch(eng, num, prj, b.pubs, prj_st)) return -1;
+		parallel_for(num, [&](uint32_t lo, uint32_t hi, unsigned) {
+			for (uint32_t i = lo; i < hi; i++) {
+				if (!b.ok[i] || prj_st[i] == 0) continue;
+				if (prj_st[i] == 1 && !sch.needs_affine_key()) key_inf[i] = 1; /* b * infinity = infinity: W' = a*G */
+				else b.ok[i] = 0; /* off the curve; or infinity where the scheme exports the affine key */
 			}
 		});
-		if (eccb200_prj_pt_unique_batch(eng, (uint32_t)prj_idx.size(), pb.data(), abuf.data(), st.data())) return -1;
-		for (size_t k = 0; k < prj_idx.size(); k++) {
-			const uint32_t i = prj_idx[k];
-			if (st[k] == 0) memcpy(&b.pubs[i * 2 * plen], &abuf[k * 2 * plen], 2 * plen);
-			else if (st[k] == 1 && !sch.needs_affine_key()) key_inf[i] = 1; /* b * infinity = infinity: W' = a*G */
-			else b.ok[i] = 0; /* off the curve; or infinity where the scheme exports the affine key */
-		}
 	}
+	clk.lap("keys");
 	/* pass 2: the scheme's scalars a, b */
 	parallel_for(num, [&](uint32_t lo, uint32_t hi, unsigned) { sch.scalars(b, lo, hi); });
+	clk.lap("scalars");
 	for (uint32_t i = 0; i < num; i++) {
 		if (!b.ok[i]) { /* keep the batch launchable: rejected slots multiply the generator by zero */
 			memset(b.a_of(i), 0, 2 * qlen);
@@ -1421,6 +1457,7 @@ static int verify_batch_double_smul(DsScheme &sch, const uint8_t **s, const uint
 		}
 	}
 	if (eccb200_double_smul_batch(eng, num, b.ab, b.pubs, wout, status)) return -1;
+	clk.lap("device");
 	g_verifies += num;
 	/* pass 3: the scheme's acceptance test on the affine W' */
 	std::vector<int8_t> verdict(num, -1);
@@ -1434,6 +1471,8 @@ static int verify_batch_double_smul(DsScheme &sch, const uint8_t **s, const uint
 	for (uint32_t i = 0; i < num; i++)
 		if (verdict[i]) all = -1;
 	t_verdicts.assign(verdict.begin(), verdict.end());
+	clk.lap("accept");
+	clk.report(num);
 	return all;
 }
 
