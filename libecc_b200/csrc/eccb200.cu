@@ -84,6 +84,9 @@ struct eccb200_ctx {
 	size_t msm_cap_list = 0;
 	uint8_t *msm_in = nullptr; /* device copy of the host-pointer entry point's inputs */
 	size_t msm_in_bytes = 0;
+	uint8_t *unique_io = nullptr; /* device buffer of eccb200_prj_pt_unique_batch (in || out || status), grown on demand:
+	                               * a cudaMalloc / cudaFree pair per call cost up to a second on a busy allocator */
+	size_t unique_io_bytes = 0;
 	/* optional per-kernel timing of the device-pointer API (bench.py's roofline leg) */
 	bool profiling = false;
 	static const int kProfCalls = 64;
@@ -317,6 +320,7 @@ extern "C" void eccb200_ctx_destroy(eccb200_ctx *ctx)
 	if (ctx->gather_counter) cudaFree(ctx->gather_counter);
 	msm_release(ctx);
 	if (ctx->msm_in) cudaFree(ctx->msm_in);
+	if (ctx->unique_io) cudaFree(ctx->unique_io);
 	if (ctx->table) cudaFree(ctx->table);
 	if (ctx->jac) cudaFree(ctx->jac);
 	if (ctx->prefix) cudaFree(ctx->prefix);
@@ -1878,25 +1882,28 @@ extern "C" int eccb200_prj_pt_unique_batch(eccb200_ctx *ctx, uint32_t n, const u
 	CUDA_OK(cudaSetDevice(ctx->device));
 	if (ensure_work(ctx, n)) return -1;
 	const size_t in_b = (size_t)n * 3 * ctx->plen, out_b = (size_t)n * 2 * ctx->plen;
-	uint8_t *d = nullptr;
-	CUDA_OK(cudaMalloc(&d, in_b + out_b + n));
-	int rc = 0;
-	if (cudaMemcpy(d, prj, in_b, cudaMemcpyHostToDevice) != cudaSuccess) rc = fail("H2D copy failed");
-	if (!rc)
-		rc = dispatch(ctx->curve_id, [&](auto c) {
-			typedef decltype(c) C;
-			scratch_enter(ctx, 0);
-			LaunchMisc<C>::prj_unique(affine_grid(ctx, n), n, d, ctx->jac, ctx->prefix, d + in_b,
-						  (int8_t *)(d + in_b + out_b), 0);
-			scratch_leave(ctx, 0);
-			ctx->launches += 2;
-			CUDA_OK(cudaGetLastError());
-			CUDA_OK(cudaMemcpy(out, d + in_b, out_b, cudaMemcpyDeviceToHost));
-			CUDA_OK(cudaMemcpy(status, d + in_b + out_b, n, cudaMemcpyDeviceToHost));
-			return 0;
-		});
-	cudaFree(d);
-	return rc;
+	if (ctx->unique_io_bytes < in_b + out_b + n) {
+		cudaDeviceSynchronize();
+		if (ctx->unique_io) cudaFree(ctx->unique_io);
+		ctx->unique_io = nullptr;
+		ctx->unique_io_bytes = 0;
+		CUDA_OK(cudaMalloc(&ctx->unique_io, in_b + out_b + n));
+		ctx->unique_io_bytes = in_b + out_b + n;
+	}
+	uint8_t *d = ctx->unique_io;
+	if (cudaMemcpy(d, prj, in_b, cudaMemcpyHostToDevice) != cudaSuccess) return fail("H2D copy failed");
+	return dispatch(ctx->curve_id, [&](auto c) {
+		typedef decltype(c) C;
+		scratch_enter(ctx, 0);
+		LaunchMisc<C>::prj_unique(affine_grid(ctx, n), n, d, ctx->jac, ctx->prefix, d + in_b,
+					  (int8_t *)(d + in_b + out_b), 0);
+		scratch_leave(ctx, 0);
+		ctx->launches += 2;
+		CUDA_OK(cudaGetLastError());
+		CUDA_OK(cudaMemcpy(out, d + in_b, out_b, cudaMemcpyDeviceToHost));
+		CUDA_OK(cudaMemcpy(status, d + in_b + out_b, n, cudaMemcpyDeviceToHost));
+		return 0;
+	});
 }
 
 extern "C" int eccb200_fp_mul_monty_batch(eccb200_ctx *ctx, int which, uint32_t n, const uint8_t *a, const uint8_t *b,
