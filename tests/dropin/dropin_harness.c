@@ -10,12 +10,15 @@
  * Modes:
  *   direct   the drop-in is dlopen'ed privately; its prj_pt_mul / batch / verify_batch entry points are compared with
  *            the reference's own functions on identical inputs.
+ *   kats     every fixed-vector case of the reference's own self tests (src/tests/ec_self_tests_core.h) through the
+ *            drop-in's ec_verify and a one-item ec_verify_batch, judged by the reference's ec_verify.
  *   preload  run with LD_PRELOAD=libecc_b200_dropin.so: the reference's ec_sign / ec_verify / ECC-CDH code then
  *            calls the interposed prj_pt_mul, i.e. the GPU, without being recompiled; results must still satisfy
  *            the reference's known-answer expectations.
  */
 #define _GNU_SOURCE
 #include "libsig.h"
+#include "tests/ec_self_tests_core.h" /* the reference's own known-answer vectors (src/tests): ec_fixed_vector_tests[] */
 #include <dlfcn.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -530,6 +533,81 @@ static int run_direct(const char *dropin_path)
 	return failures != 0;
 }
 
+
+/* kats mode: every fixed-vector test case of the reference's self tests (src/tests/ec_self_tests_core.h:4915-, the table
+ * `ec_self_tests vectors` walks) through the drop-in's ec_verify: the expected signature must verify, a flipped message
+ * bit must not, both exactly as the reference's own ec_verify says; schemes / curves the layer does not serve (EdDSA,
+ * GOST and other curves) are forwarded and still agree.  Prints how many cases ran on the GPU per scheme. */
+static int run_kats(const char *dropin_path)
+{
+	void *h = dlopen(dropin_path, RTLD_NOW | RTLD_LOCAL);
+	if (!h) {
+		printf("FAIL dlopen %s: %s\n", dropin_path, dlerror());
+		return 1;
+	}
+	everify_fn gpu_everify = (everify_fn)dlsym(h, "eccb200_dropin_ec_verify");
+	count_fn gpu_vcount = (count_fn)dlsym(h, "eccb200_dropin_verify_count");
+	vbatch_fn gpu_generic = (vbatch_fn)dlsym(h, "ec_verify_batch");
+	if (!gpu_everify || !gpu_vcount || !gpu_generic) {
+		printf("FAIL missing drop-in symbols\n");
+		return 1;
+	}
+	const unsigned ncases = (unsigned)(sizeof(ec_fixed_vector_tests) / sizeof(ec_fixed_vector_tests[0]));
+	unsigned served[32] = { 0 }, total[32] = { 0 }, ran = 0;
+	for (unsigned t = 0; t < ncases; t++) {
+		const ec_test_case *c = ec_fixed_vector_tests[t];
+		ec_params params;
+		ec_key_pair kp;
+		static u8 msg[4096];
+		if (c->msglen > sizeof(msg) || c->msglen == 0) continue;
+		if (import_params(&params, c->ec_str_p)) continue;
+		const int eddsa = c->sig_type == EDDSA25519 || c->sig_type == EDDSA25519CTX || c->sig_type == EDDSA25519PH ||
+				  c->sig_type == EDDSA448 || c->sig_type == EDDSA448PH;
+		/* key import as the reference's own self test does it (src/tests/ec_self_tests_core.c:752-783) */
+		if (eddsa ? eddsa_import_key_pair_from_priv_key_buf(&kp, c->priv_key, c->priv_key_len, &params, c->sig_type)
+			  : ec_key_pair_import_from_priv_key_buf(&kp, &params, c->priv_key, c->priv_key_len, c->sig_type))
+			continue;
+		memcpy(msg, c->msg, c->msglen);
+		const unsigned long long v0 = gpu_vcount();
+		int want = ec_verify(c->exp_sig, c->exp_siglen, &kp.pub_key, msg, c->msglen, c->sig_type, c->hash_type, c->adata, c->adata_len);
+		int got = gpu_everify(c->exp_sig, c->exp_siglen, &kp.pub_key, msg, c->msglen, c->sig_type, c->hash_type, c->adata, c->adata_len);
+		CHECK(want == 0, "%s: the reference rejects its own expected signature (%d)", c->name, want);
+		CHECK(got == want, "%s: drop-in ec_verify %d, reference %d", c->name, got, want);
+		msg[c->msglen / 2] ^= 0x04;
+		want = ec_verify(c->exp_sig, c->exp_siglen, &kp.pub_key, msg, c->msglen, c->sig_type, c->hash_type, c->adata, c->adata_len);
+		got = gpu_everify(c->exp_sig, c->exp_siglen, &kp.pub_key, msg, c->msglen, c->sig_type, c->hash_type, c->adata, c->adata_len);
+		CHECK(want == -1 && got == want, "%s (message altered): drop-in %d, reference %d", c->name, got, want);
+		msg[c->msglen / 2] ^= 0x04;
+		/* the same case as a batch of one through the generic ec_verify_batch (adata as arrays) */
+		{
+			const u8 *sp[1] = { c->exp_sig }, *mp[1] = { msg }, *ap[1] = { c->adata };
+			const ec_pub_key *pk[1] = { &kp.pub_key };
+			u8 sl[1] = { c->exp_siglen };
+			u32 ml[1] = { c->msglen };
+			u16 al[1] = { c->adata_len };
+			int chk = 0;
+			int (*gpu_supported)(ec_alg_type, int *) = (int (*)(ec_alg_type, int *))dlsym(h, "is_verify_batch_mode_supported");
+			if (gpu_supported && !gpu_supported(c->sig_type, &chk) && chk && gpu_vcount() > v0) {
+				static verify_batch_scratch_pad pad[16];
+				u32 padlen = sizeof(pad);
+				int b = gpu_generic(sp, sl, pk, mp, ml, 1, c->sig_type, c->hash_type, c->adata ? ap : NULL, c->adata ? al : NULL, pad, &padlen);
+				CHECK(b == 0, "%s: generic ec_verify_batch of one rejects the expected signature (%d)", c->name, b);
+			}
+		}
+		if ((unsigned)c->sig_type < 32) {
+			total[c->sig_type]++;
+			if (gpu_vcount() > v0) served[c->sig_type]++;
+		}
+		ran++;
+	}
+	printf("kats: %u of %u fixed-vector cases of the reference's self tests ran; served by the GPU per ec_alg_type:", ran, ncases);
+	for (int a = 0; a < 32; a++)
+		if (total[a]) printf(" %d:%u/%u", a, served[a], total[a]);
+	printf("\n");
+	CHECK(ran >= 100, "too few known-answer cases ran (%u)", ran);
+	return failures != 0;
+}
+
 /* threads mode: the reference's functions are re-entrant; several host threads call the drop-in at once */
 typedef struct {
 	mul_fn mul;
@@ -737,11 +815,12 @@ int main(int argc, char **argv)
 	if (argc >= 2 && !strcmp(argv[1], "preload")) rc = run_preload();
 	else if (argc >= 3 && !strcmp(argv[1], "direct")) rc = run_direct(argv[2]);
 	else if (argc >= 3 && !strcmp(argv[1], "threads")) rc = run_threads(argv[2]);
+	else if (argc >= 3 && !strcmp(argv[1], "kats")) rc = run_kats(argv[2]);
 	else if (argc >= 5 && !strcmp(argv[1], "bench"))
 		rc = run_bench(argv[2], argv[3], (u32)strtoul(argv[4], NULL, 10), argc >= 6 ? argv[5] : "ECDSA",
 			       argc >= 7 ? (u32)strtoul(argv[6], NULL, 10) : 64);
 	else {
-		printf("usage: %s direct <dropin.so> | threads <dropin.so> | bench <dropin.so> <curve> <items> [ECDSA|ECFSDSA|BIP0340|ECSDSA|ECOSDSA|ECKCDSA|ECGDSA|ECRDSA|SM2|BIGN [invalid_every, 0 = none]] | preload\n", argv[0]);
+		printf("usage: %s direct <dropin.so> | kats <dropin.so> | threads <dropin.so> | bench <dropin.so> <curve> <items> [ECDSA|ECFSDSA|BIP0340|ECSDSA|ECOSDSA|ECKCDSA|ECGDSA|ECRDSA|SM2|BIGN [invalid_every, 0 = none]] | preload\n", argv[0]);
 		return 2;
 	}
 	printf(rc ? "HARNESS FAILED (%d failures)\n" : "HARNESS OK (%d failures)\n", failures);
