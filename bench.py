@@ -362,7 +362,10 @@ def run_reference(args, rank: int):
         return
     curve, kind, metric, unit = WORKLOADS[args.workload]
     n = 1 << args.batch_log2
-    config = workload_config(args.workload, args.batch_log2, 1)
+    # this arm times the reference's CPU path on the repo arm's workload: the same `config` object as that arm prints
+    world = max(1, args.gpus)
+    comb = args.comb_window or DEFAULT_COMB.get(curve, 0) or ENGINE_DEFAULT_COMB
+    config = line_config(args.workload, args.batch_log2, world, comb, resolve_gather(kind, world, args.gather))
     if kind == "var":
         # no GPU on this arm: derive the points with the CPU oracle on the bounded sample only
         from common import oracle_smul
@@ -406,6 +409,34 @@ def workload_config(workload: str, batch_log2: int, world: int) -> dict:
             "curve": curve, "batch_per_gpu": n, "global_batch": n * world}
 
 
+ENGINE_DEFAULT_COMB = 22   # the library's default fixed-base window (eccb200_ctx_create with comb_window = 0)
+_CE_DESC = ("every rank's normalisation kernel writes its results locally; a copy-engine transfer on a side stream "
+            "(cudaMemcpyAsync to CUDA-IPC peer memory over NVLink, no SM involved) pushes them into {dst} gathered "
+            "buffer while the NEXT step's kernels run, then publishes an arrival counter; the destination waits for "
+            "step s-1's arrivals at the end of step s and for the last step's inside the timed region (drain); "
+            "double-buffered with acknowledgements; no collective kernel")
+GATHER_DESC = {"none": "none", "fused-root": "fused into the normalisation kernel (stores straight into rank 0's buffer)",
+               "fused-all": "fused into the normalisation kernel (stores into every rank's buffer)",
+               "peer-root": _CE_DESC.format(dst="rank 0's"),
+               "peer-all": _CE_DESC.format(dst="every rank's"),
+               "nccl": "one nccl all_gather per step on the compute stream, inside the step's events"}
+
+
+def resolve_gather(kind: str, world: int, gather: str) -> str:
+    """The result-gather mode a run uses (Ours.__init__): none on one GPU, NCCL for the one-byte verdicts."""
+    return gather if (world > 1 and kind != "verify") else ("nccl" if world > 1 else "none")
+
+
+def line_config(workload: str, batch_log2: int, world: int, comb_window: int, gather: str) -> dict:
+    """The `config` object of the JSON line - the SAME for the repo arm and for `--impl reference`, which times the
+    reference's CPU path on this arm's workload (the device-side entries describe the repo arm's run)."""
+    return dict(workload_config(workload, batch_log2, world),
+                l2="256 MiB buffer rewritten between timed iterations (outside the per-step events, at every N)",
+                comb_window=comb_window, result_gather=GATHER_DESC[gather],
+                timing="sum of per-step CUDA-event intervals on the compute stream, max over ranks",
+                settle_steps=SETTLE_STEPS)
+
+
 # ------------------------------------------------------------------------------------------------ ours
 
 class Ours:
@@ -421,7 +452,7 @@ class Ours:
         self.curve, self.kind, self.metric, self.unit = WORKLOADS[workload]
         self.n = 1 << batch_log2
         self.rank, self.world, self.local_rank = rank, world, local_rank
-        self.gather = gather if (world > 1 and self.kind != "verify") else ("nccl" if world > 1 else "none")
+        self.gather = resolve_gather(self.kind, world, gather)
         if world == 1 and os.environ.get("BENCH_FORCE_GATHER") and self.kind != "verify" and gather.startswith("peer"):
             self.gather = gather     # diagnostic: the gather path with this GPU as its own (only) destination
         _, self.plen, self.qlen = CURVES[self.curve]
@@ -1005,24 +1036,10 @@ def main():
 
     o._k4_ms = m["normalisation_ms"]
     roofline = o.roofline(m["kernel_ms"], m["ms_per_step"])
-    ce_desc = ("every rank's normalisation kernel writes its results locally; a copy-engine transfer on a side stream "
-               "(cudaMemcpyAsync to CUDA-IPC peer memory over NVLink, no SM involved) pushes them into {dst} gathered "
-               "buffer while the NEXT step's kernels run, then publishes an arrival counter; the destination waits for "
-               "step s-1's arrivals at the end of step s and for the last step's inside the timed region (drain); "
-               "double-buffered with acknowledgements; no collective kernel")
-    gather_desc = {"none": "none", "fused-root": "fused into the normalisation kernel (stores straight into rank 0's buffer)",
-                   "fused-all": "fused into the normalisation kernel (stores into every rank's buffer)",
-                   "peer-root": ce_desc.format(dst="rank 0's"),
-                   "peer-all": ce_desc.format(dst="every rank's"),
-                   "nccl": "one nccl all_gather per step on the compute stream, inside the step's events"}[o.gather]
     line = {"metric": o.metric, "value": m["value"], "unit": o.unit, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": dict(workload_config(args.workload, args.batch_log2, world),
-                           l2="256 MiB buffer rewritten between timed iterations (outside the per-step events, at every N)",
-                           comb_window=o.eng.comb_window, result_gather=gather_desc,
-                           timing="sum of per-step CUDA-event intervals on the compute stream, max over ranks",
-                           settle_steps=SETTLE_STEPS),
+            "config": line_config(args.workload, args.batch_log2, world, o.eng.comb_window, o.gather),
             "clocks": m["clocks"], "gpu_launches": m["launches"], "host_cpus_bound_near_gpu": numa_cpus,
             "e2e": dict(e2e, same_results_as_device_leg=e2e["parity"]),
             "roofline": roofline, "parity_spot_check": parity}
