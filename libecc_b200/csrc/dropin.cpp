@@ -106,6 +106,8 @@ const CurveInfo *identify(const eccb200_prj_pt *pt)
  * only created when a batch of at least kBigBatch items arrives.  Nothing is created for curves that are never used;
  * eccb200_dropin_release() frees everything.
  */
+constexpr uint32_t kMaxBatch = 1u << 28; /* items per call: keeps every 32-bit size product below 2^32 (a batch of that
+                                         * size is 210 GB of ec_pub_key structs - split it) */
 constexpr int kSmallSlots = 4;
 constexpr uint32_t kBigBatch = 1u << 15;
 
@@ -315,7 +317,7 @@ void fp_set_word(eccb200_fp *dst, const eccb200_fp *tmpl, uint64_t v)
 int mul_batch(eccb200_prj_pt *out, const eccb200_nn *m, const eccb200_prj_pt *in, uint32_t n, int *ret)
 {
 	if (n == 0) return 0;
-	if (!out || !m || !in) return -1;
+	if (!out || !m || !in || n > kMaxBatch) return -1;
 	g_calls += n;
 	std::vector<int> rc(n, -1);
 	const CurveInfo *ci = nullptr;
@@ -570,6 +572,10 @@ static int verify_batch_common(Scheme sc, const uint8_t **s, const uint8_t *s_le
 			       const uint8_t **m, const uint32_t *m_len, uint32_t num, int sig_type, int hash_type,
 			       const uint8_t **adata)
 {
+	if (num > kMaxBatch) {
+		t_verdicts.clear();
+		return -1;
+	}
 	t_verdicts.assign(num, -1);
 	if (num == 0) return -1; /* the reference's implementations reject an empty batch (sig/ecfsdsa.c:740) */
 	if (!s || !s_len || !pub_keys || !m || !m_len) return -1;
@@ -1346,6 +1352,10 @@ static int verify_batch_double_smul(DsScheme &sch, const uint8_t **s, const uint
 				    uint32_t num, int sig_type, int hash_type, const uint8_t **adata,
 				    const uint16_t *adata_len)
 {
+	if (num > kMaxBatch) {
+		t_verdicts.clear();
+		return -1;
+	}
 	t_verdicts.assign(num, -1);
 	if (num == 0) return -1;
 	if (!s || !s_len || !pub_keys || !m || !m_len) return -1;
