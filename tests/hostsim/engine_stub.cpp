@@ -64,7 +64,7 @@ int eccb200_ctx_create(eccb200_ctx **ctx, int curve_id, int device, int comb_win
 	(void)comb_window;
 	static std::mutex mu; /* hostsim builds its comb tables lazily and without locks: build here, serialised */
 	std::lock_guard<std::mutex> lk(mu);
-	const int w = 5;
+	const int w = 4;
 	if (!ctx || dispatch(curve_id, [&](auto c) {
 		    table_for<decltype(c)>(w);
 		    return 0;
