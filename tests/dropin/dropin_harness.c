@@ -449,6 +449,13 @@ static int run_direct(const char *dropin_path)
 			sigs[4][1] ^= 0x08;              /* first half: r (s0 for BIGN) */
 			sigs[8][sgl - 2] ^= 1;           /* second half: s (s1) */
 			msgs[12][0] ^= 1;
+			{ /* second half := q - first half (SM2: r + s = q, t = 0, sig/sm2.c:660; elsewhere just another forgery) */
+				nn a, d;
+				if (!nn_init_from_buf(&a, sigs[10], qlen) && !nn_mod(&a, &a, &params.ec_gen_order) &&
+				    !nn_sub(&d, &params.ec_gen_order, &a) && sgl >= 2 * qlen) {
+					CHECK(!nn_export_to_buf(sigs[10], qlen, &a) && !nn_export_to_buf(sigs[10] + qlen, qlen, &d), "r + s = q");
+				}
+			}
 			memset(sigs[14], 0xff, sgl);     /* out of range */
 			memset(sigs[15], 0, sgl);        /* zero */
 			static ec_pub_key kinf, koff;    /* a key at infinity, a key off the curve */
@@ -480,8 +487,8 @@ static int run_direct(const char *dropin_path)
 				CHECK(got == want, "%s scheme %d ec_verify shim item %d: %d vs %d", names[c], (int)alg, i, got, want);
 				if (i < 4) CHECK(gpu_vcount() == v1 + 1, "%s scheme %d ec_verify shim did not run on the GPU", names[c], (int)alg);
 			}
-			CHECK(v[4] == -1 && v[8] == -1 && v[12] == -1 && v[14] == -1 && v[15] == -1 && v[17] == -1,
-			      "corrupted items of scheme %d not flagged", (int)alg);
+			CHECK(v[4] == -1 && v[8] == -1 && v[12] == -1 && v[14] == -1 && v[15] == -1 && v[17] == -1 &&
+			      (sgl < 2 * qlen || v[10] == -1), "corrupted items of scheme %d not flagged", (int)alg);
 			CHECK(v[0] == 0 && v[1] == 0 && v[ad ? 13 : 19] == 0, "valid items of scheme %d rejected", (int)alg);
 		}
 		/* ---- BIP0340 in the same slot and through the ec_verify shim: against the reference's ec_verify */
