@@ -116,6 +116,10 @@ static int run_direct(const char *dropin_path)
 		}
 	}
 	const char *only = getenv("HARNESS_CURVES"); /* optional comma-separated subset (the CPU run of the tests) */
+	/* HARNESS_SECTIONS: optional subset of the sections below, letters m (multiplications), e (ECDSA), f (ECFSDSA),
+	 * s (ECSDSA / ECOSDSA / ECKCDSA), d (ECGDSA / ECRDSA / SM2 / BIGN / DBIGN), b (BIP0340); default: all */
+	const char *sect = getenv("HARNESS_SECTIONS");
+#define SECTION(ch) (!sect || strchr(sect, (ch)))
 	for (int c = 0; c < 8; c++) {
 		ec_params params;
 		if (only && !strstr(only, names[c])) continue;
@@ -126,7 +130,7 @@ static int run_direct(const char *dropin_path)
 		CHECK(!prj_pt_dbl(&tmp, &params.ec_gen), "dbl");
 		CHECK(!prj_pt_add(&base2, &tmp, &params.ec_gen), "add"); /* 3G with Z != 1 */
 		u16 lens[5] = { qlen, 1, (u16)(qlen + 8), 72, (u16)(2 * qlen) };
-		for (int t = 0; t < 10; t++) {
+		for (int t = 0; t < 10 && SECTION('m'); t++) {
 			u8 kb[160];
 			u16 kl = lens[t % 5];
 			for (u16 i = 0; i < kl; i++) kb[i] = rnd8();
@@ -155,7 +159,7 @@ static int run_direct(const char *dropin_path)
 			compare("prj_pt_mul(out==in)", names[c], r1, &o_ref, r2, &alias);
 		}
 		/* ---- edge scalars: 0, 1, q-1, q, q+1 */
-		{
+		if (SECTION('m')) {
 			nn q, one, k;
 			prj_pt o_ref, o_gpu;
 			CHECK(!nn_copy(&q, &params.ec_gen_order) && !nn_init(&one, 0) && !nn_one(&one), "nn setup");
@@ -182,7 +186,7 @@ static int run_direct(const char *dropin_path)
 			CHECK(gpu_mul(&o_gpu, &one, &junk) == -1, "%s: uninitialised input accepted", names[c]);
 		}
 		/* ---- batch on arrays of structs */
-		{
+		if (SECTION('m')) {
 			enum { NB = 64 };
 			static prj_pt in[NB], out[NB], ref_out[NB];
 			static nn ks[NB];
@@ -202,7 +206,7 @@ static int run_direct(const char *dropin_path)
 			}
 		}
 		/* ---- ECDSA verify_batch slot */
-		{
+		if (SECTION('e')) {
 			enum { NS = 48 };
 			static ec_key_pair kp[NS];
 			static u8 sigs[NS][2 * 66], msgs[NS][40];
@@ -289,7 +293,7 @@ static int run_direct(const char *dropin_path)
 			}
 		}
 		/* ---- ECFSDSA in the same slot: against the reference's ec_verify, item by item */
-		{
+		if (SECTION('f')) {
 			enum { NF = 24 };
 			static ec_key_pair kp[NF];
 			static u8 sigs[NF][3 * 66], msgs[NF][40];
@@ -350,7 +354,7 @@ static int run_direct(const char *dropin_path)
 		}
 		/* ---- ECSDSA / ECOSDSA: batch adapter (W' = sG + eY on the device, hashing of W' with the reference's src/hash)
 		 * and ec_verify shim against the reference's ec_verify */
-		for (int alt = 0; alt < 3; alt++) {
+		for (int alt = 0; alt < 3 && SECTION('s'); alt++) {
 			enum { NSD = 20 };
 			const ec_alg_type alg = alt == 0 ? ECSDSA : (alt == 1 ? ECOSDSA : ECKCDSA);
 			static ec_key_pair kp[NSD];
@@ -395,7 +399,7 @@ static int run_direct(const char *dropin_path)
 		/* ---- ECGDSA / ECRDSA / SM2 / BIGN / DBIGN: W' = a*G + b*Y on the device, mod-q scalar preparation (one shared
 		 * inversion per chunk), hashes and comparison on the host; batch adapters, the generic ec_verify_batch and the
 		 * ec_verify shim against the reference's ec_verify, with the ancillary data SM2 (signer ID) and BIGN (hash OID) need */
-		for (int alt = 0; alt < 5; alt++) {
+		for (int alt = 0; alt < 5 && SECTION('d'); alt++) {
 			enum { NG = 20 };
 			const ec_alg_type algs[5] = { ECGDSA, ECRDSA, SM2, BIGN, DBIGN };
 			const char *fns[5] = { "eccb200_dropin_ecgdsa_verify_batch", "eccb200_dropin_ecrdsa_verify_batch",
@@ -492,7 +496,7 @@ static int run_direct(const char *dropin_path)
 			CHECK(v[0] == 0 && v[1] == 0 && v[ad ? 13 : 19] == 0, "valid items of scheme %d rejected", (int)alg);
 		}
 		/* ---- BIP0340 in the same slot and through the ec_verify shim: against the reference's ec_verify */
-		{
+		if (SECTION('b')) {
 			enum { NB3 = 20 };
 			static ec_key_pair kp[NB3];
 			static u8 sigs[NB3][2 * 66], msgs[NB3][40];
@@ -566,6 +570,8 @@ static int run_kats(const char *dropin_path)
 		ec_params params;
 		ec_key_pair kp;
 		static u8 msg[4096];
+		/* HARNESS_KATS_THIN (the CPU run of the tests): every third of the 47 ECDSA / DECDSA cases, all of the others */
+		if (getenv("HARNESS_KATS_THIN") && (c->sig_type == ECDSA || c->sig_type == DECDSA) && (t % 3)) continue;
 		if (c->msglen > sizeof(msg) || c->msglen == 0) continue;
 		if (import_params(&params, c->ec_str_p)) continue;
 		const int eddsa = c->sig_type == EDDSA25519 || c->sig_type == EDDSA25519CTX || c->sig_type == EDDSA25519PH ||
@@ -613,7 +619,7 @@ static int run_kats(const char *dropin_path)
 	for (int a = 0; a < 32; a++)
 		if (total[a]) printf(" %d:%u/%u", a, served[a], total[a]);
 	printf("\n");
-	CHECK(ran >= 100, "too few known-answer cases ran (%u)", ran);
+	CHECK(ran >= (getenv("HARNESS_KATS_THIN") ? 90u : 120u), "too few known-answer cases ran (%u)", ran);
 	return failures != 0;
 }
 
