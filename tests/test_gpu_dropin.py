@@ -1,4 +1,5 @@
-"""The drop-in layer (include/libecc_b200_dropin.h) exercised with REAL reference structs by the C harness
+"""The drop-in layer (include/libecc_b200_dropin.h: prj_pt_mul, ec_verify, ec_verify_batch and the verify_batch slots of all
+twelve short-Weierstrass schemes) exercised with REAL reference structs by the C harness
 tests/dropin/dropin_harness.c (built against the reference's headers in the build container, shipped prebuilt):
   direct   drop-in prj_pt_mul / prj_pt_mul_blind / batch / ECDSA verify_batch vs the reference's own functions;
   preload  the unmodified reference's ec_sign / ec_verify / ECC-CDH running with prj_pt_mul interposed by the GPU."""
@@ -53,3 +54,20 @@ def test_verify_batch_adapters_use_the_multi_scalar_fast_path(scheme, curve):
         assert line["wrong_verdicts"] == 0
         # all four timed calls of a valid batch are settled by the fast path, none of a batch with invalid signatures
         assert line["batches_settled_by_multi_scalar_multiplication"] == (4 if settled else 0)
+
+
+@pytest.mark.parametrize("scheme", ["ECGDSA", "SM2", "BIGN"])
+def test_double_scalar_scheme_adapters_on_a_large_batch(scheme):
+    """The verify_batch adapters of the double-scalar schemes on 40 000 real ec_pub_key structs (the big engine slot,
+    several marshalling threads, projective keys normalised on the device, 1 signature in 64 corrupted): every verdict
+    equals the expected one.  The eight-curve, item-by-item comparison with the reference's ec_verify is the direct mode
+    above; tests/test_dropin_host.py replays it on the host build."""
+    _need()
+    import json
+    env = dict(os.environ, HARNESS_POOL="256", HARNESS_REPS="2")
+    r = subprocess.run([HARNESS, "bench", DROPIN, "FRP256V1", "40000", scheme, "64"], capture_output=True, text=True,
+                       timeout=600, env=env)
+    print(r.stdout[-2000:], r.stderr[-1000:])
+    assert r.returncode == 0 and "HARNESS OK" in r.stdout
+    line = json.loads(r.stdout.split("DROPIN_BENCH ", 1)[1].splitlines()[0])
+    assert line["wrong_verdicts"] == 0 and line["items"] == 40000
