@@ -28,3 +28,28 @@ def test_bench_reads_an_existing_traffic_file():
     t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
     entries = t if isinstance(t, list) else t.get("entries", t)
     assert entries, "profiles/ncu_traffic.json is empty"
+
+
+def test_reference_citations_point_at_existing_lines():
+    """`path:line` citations of the reference in the documents, headers and sources name files that exist and are long
+    enough (checked where /root/reference is present: the build container)."""
+    import pytest
+    ref = "/root/reference/"
+    if not os.path.isdir(os.path.join(ref, "src")):
+        pytest.skip("the reference sources are not on this machine")
+    files = ["DESIGN.md", "INTEGRATION.md", "README.md", "include/libecc_b200.h", "include/libecc_b200_dropin.h",
+             "oracle/ecc_oracle.c", "oracle/ref_shim.c", "tests/dropin/dropin_harness.c"]
+    files += [os.path.join("libecc_b200", "csrc", f) for f in
+              ("dropin.cpp", "ec.cuh", "kernels.cuh", "fp.cuh", "msm.cuh", "msm_core.cuh", "eccb200.cu", "wire.cuh")]
+    pat = re.compile(r"((?:src/)?(?:sig|curves|fp|nn|hash|ecdh|tests|utils|words|wycheproof_tests)/[A-Za-z0-9_\-./]+\.[ch]):(\d+)")
+    bad, total = [], 0
+    for f in files:
+        for m in pat.finditer(open(os.path.join(ROOT, f), errors="ignore").read()):
+            path, line = m.group(1), int(m.group(2))
+            full = os.path.join(ref, path if path.startswith("src/") else "src/" + path)
+            total += 1
+            if not os.path.exists(full):
+                bad.append((f, path, "missing"))
+            elif line > sum(1 for _ in open(full, errors="ignore")):
+                bad.append((f, path, line))
+    assert total > 200 and not bad, bad
