@@ -102,6 +102,18 @@ def host_info() -> dict:
             break
         except OSError:
             continue
+    # CPUs' worth of time the container may use: "<quota> <period>" in cpu.max ("max" = unlimited).  A box that shows
+    # 128 hardware threads under a 16-CPU quota runs the 128 baseline threads at the rate of 16 cores: that, not the
+    # thread count, is what separates the 4.5 k/s and 24.8 k/s reference rates seen on two boxes of the pool.
+    info["effective_cpus"] = float(info["affinity_cpus"])
+    try:
+        parts = info.get("cgroup_cpu_limit", "").split()
+        if len(parts) == 2 and parts[0] != "max" and float(parts[1]) > 0:
+            info["effective_cpus"] = min(info["effective_cpus"], float(parts[0]) / float(parts[1]))
+        elif len(parts) == 1 and parts[0] not in ("max", "-1") and float(parts[0]) > 0:   # cgroup v1 quota, 100 ms period
+            info["effective_cpus"] = min(info["effective_cpus"], float(parts[0]) / 100000.0)
+    except ValueError:
+        pass
     return info
 
 

@@ -32,6 +32,8 @@ def test_reference_arm_prints_the_repo_arms_config():
     assert line["e2e"] == {"value": line["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = line["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == line["value"]
+    # the host description says how many CPUs' worth of time the threads really had (cgroup quota)
+    assert 1 <= cb["host"]["effective_cpus"] <= cb["host"]["affinity_cpus"]
 
 
 def test_reference_arm_config_at_eight_ranks_names_the_gather():
