@@ -104,7 +104,7 @@ def host_info() -> dict:
             continue
     # CPUs' worth of time the container may use: "<quota> <period>" in cpu.max ("max" = unlimited).  A box that shows
     # 128 hardware threads under a 16-CPU quota runs the 128 baseline threads at the rate of 16 cores: that, not the
-    # thread count, is what separates the 4.5 k/s and 24.8 k/s reference rates seen on two boxes of the pool.
+    # thread count, sets the reference rate (4.5 k/s under a 16-CPU quota on the pool's one-GPU boxes).
     info["effective_cpus"] = float(info["affinity_cpus"])
     try:
         parts = info.get("cgroup_cpu_limit", "").split()
