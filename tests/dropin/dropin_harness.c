@@ -12,6 +12,7 @@
  *            the reference's own functions on identical inputs.
  *   kats     every fixed-vector case of the reference's own self tests (src/tests/ec_self_tests_core.h) through the
  *            drop-in's ec_verify and a one-item ec_verify_batch, judged by the reference's ec_verify.
+ *   fuzz     mutated signatures / keys / ancillary data of every served scheme: drop-in verdict == reference verdict.
  *   preload  run with LD_PRELOAD=libecc_b200_dropin.so: the reference's ec_sign / ec_verify / ECC-CDH code then
  *            calls the interposed prj_pt_mul, i.e. the GPU, without being recompiled; results must still satisfy
  *            the reference's known-answer expectations.
@@ -623,6 +624,109 @@ static int run_kats(const char *dropin_path)
 	return failures != 0;
 }
 
+
+/* fuzz mode (host logic, differential): reference-made signatures of every scheme the layer serves are mutated - single
+ * bit flips, halves forced to 0 / q - 1 / q / all-ones, lengths off by one, altered or missing ancillary data, keys at
+ * infinity / off the curve / of another scheme / with a broken magic - and every mutant goes through the reference's
+ * ec_verify and the drop-in's: the two verdicts must be equal.  Deterministic (seeded); `iters` mutants per scheme. */
+static int run_fuzz(const char *dropin_path, const char *curve, u32 iters)
+{
+	void *h = dlopen(dropin_path, RTLD_NOW | RTLD_LOCAL);
+	if (!h) return 1;
+	everify_fn gpu_everify = (everify_fn)dlsym(h, "eccb200_dropin_ec_verify");
+	count_fn gpu_vcount = (count_fn)dlsym(h, "eccb200_dropin_verify_count");
+	if (!gpu_everify || !gpu_vcount) return 1;
+	ec_params params;
+	CHECK(!load_params(&params, curve), "params");
+	for (const char *c = curve; *c; c++) rng_state = rng_state * 31 + (unsigned char)*c; /* another sequence per curve */
+	const u8 qlen = (u8)BYTECEIL(params.ec_gen_order_bitlen);
+	u8 qb[66], qm1[66];
+	nn t;
+	CHECK(!nn_export_to_buf(qb, qlen, &params.ec_gen_order), "q");
+	CHECK(!nn_init(&t, 0) && !nn_dec(&t, &params.ec_gen_order) && !nn_export_to_buf(qm1, qlen, &t), "q - 1");
+	static const ec_alg_type algs[12] = { ECDSA, DECDSA, ECFSDSA, BIP0340, ECKCDSA, ECSDSA, ECOSDSA, ECGDSA, ECRDSA, SM2, BIGN, DBIGN };
+	static const u8 sm2_id[] = "fuzz@libecc-b200";
+	static const u8 bign_ad[] = { 0x00, 0x0b, 0x00, 0x04, 0x06, 0x09, 0x2a, 0x70, 0x00, 0x02, 0x00, 0x22, 0x65, 0x1f, 0x51,
+				      0xde, 0xad, 0xbe, 0xef };
+	unsigned long long accepted = 0, total = 0, on_gpu = 0;
+	for (int a = 0; a < 12; a++) {
+		const ec_alg_type alg = algs[a];
+		const int needs_ad = alg == SM2 || alg == BIGN || alg == DBIGN;
+		const u8 *ad = alg == SM2 ? sm2_id : (needs_ad ? bign_ad : NULL);
+		const u16 adl = alg == SM2 ? (u16)(sizeof(sm2_id) - 1) : (needs_ad ? (u16)sizeof(bign_ad) : 0);
+		enum { NK = 3 };
+		static ec_key_pair kp[NK];
+		static u8 sig0[NK][3 * 66], msg0[NK][40];
+		u32 ml0[NK];
+		u8 sgl = 0;
+		int usable = !ec_get_sig_len(&params, alg, SHA256, &sgl) && sgl <= 3 * 66 - 2;
+		for (int i = 0; i < NK && usable; i++) {
+			ml0[i] = (u32)(1 + (rnd8() % 39));
+			for (u32 j = 0; j < ml0[i]; j++) msg0[i][j] = rnd8();
+			usable = !ec_key_pair_gen(&kp[i], &params, alg) && !ec_sign(sig0[i], sgl, &kp[i], msg0[i], ml0[i], alg, SHA256, ad, adl);
+		}
+		if (!usable) {
+			printf("note: scheme %d not usable on %s here; skipped\n", (int)alg, curve);
+			continue;
+		}
+		for (u32 it = 0; it < iters; it++) {
+			const int k = (int)(rnd8() % NK);
+			u8 sig[3 * 66 + 2], msg[40], adbuf[32];
+			static ec_pub_key pk;
+			const u8 *adp = ad;
+			u16 adlen = adl;
+			u8 sl = sgl;
+			u32 ml = ml0[k];
+			memset(sig, 0, sizeof(sig));
+			memcpy(sig, sig0[k], sgl);
+			memcpy(msg, msg0[k], ml);
+			pk = kp[k].pub_key;
+			const unsigned half = sgl / 2u, kind = rnd8() % 16u, which = rnd8() & 1u;
+			const unsigned off = which ? (unsigned)(sgl - qlen) : 0u; /* the scalar-sized field at either end */
+			switch (kind) {
+			case 0: break;                                                    /* untouched: must still verify */
+			case 1: sig[rnd8() % sgl] ^= (u8)(1u << (rnd8() & 7)); break;     /* one bit of the signature */
+			case 2: msg[rnd8() % ml] ^= (u8)(1u << (rnd8() & 7)); break;      /* one bit of the message */
+			case 3: memset(sig + off, 0, qlen); break;                        /* field := 0 */
+			case 4: memcpy(sig + off, qb, qlen); break;                       /* field := q */
+			case 5: memcpy(sig + off, qm1, qlen); break;                      /* field := q - 1 */
+			case 6: memset(sig + off, 0xff, qlen); break;                     /* field := 2^(8 qlen) - 1 */
+			case 7: sl = (u8)(sgl - 1); break;                                /* one byte short */
+			case 8: sl = (u8)(sgl + 1); break;                                /* one byte long */
+			case 9: memset(sig, 0, half); break;                              /* leading half zero */
+			case 10:                                                          /* ancillary data altered / shortened / absent */
+				if (needs_ad) {
+					const unsigned m3 = rnd8() % 3u;
+					memcpy(adbuf, ad, adl);
+					if (m3 == 0) { adbuf[rnd8() % adl] ^= 1; adp = adbuf; }
+					else if (m3 == 1) { adp = adbuf; adlen = (u16)(rnd8() % adl); }
+					else { adp = NULL; adlen = 0; }
+				} else if (rnd8() & 1) { /* a scheme that takes none is handed some: forwarded, must still agree */
+					adbuf[0] = 1;
+					adp = adbuf;
+					adlen = 1;
+				}
+				break;
+			case 11: CHECK(!prj_pt_zero(&pk.y), "zero key"); break;           /* key at infinity */
+			case 12: pk.y.X.fp_val.val[0] ^= 4; break;                        /* key off the curve */
+			case 13: pk.key_type = algs[(a + 1) % 12]; break;                 /* key of another scheme */
+			case 14: pk.magic ^= 1; break;                                    /* not an initialised key */
+			default: ml = 0; break;                                           /* empty message */
+			}
+			const unsigned long long v0 = gpu_vcount();
+			const int want = ec_verify(sig, sl, &pk, msg, ml, alg, SHA256, adp, adlen);
+			const int got = gpu_everify(sig, sl, &pk, msg, ml, alg, SHA256, adp, adlen);
+			CHECK(want == got, "%s scheme %d mutation %u (iteration %u): drop-in %d, reference %d", curve, (int)alg, kind, it, got, want);
+			if (kind == 0) CHECK(want == 0, "%s scheme %d: untouched signature rejected", curve, (int)alg);
+			total++;
+			accepted += want == 0;
+			on_gpu += gpu_vcount() > v0;
+		}
+	}
+	printf("fuzz %s: %llu mutants, %llu accepted by both, %llu judged by the engine path, the rest forwarded\n", curve, total, accepted, on_gpu);
+	return failures != 0;
+}
+
 /* threads mode: the reference's functions are re-entrant; several host threads call the drop-in at once */
 typedef struct {
 	mul_fn mul;
@@ -831,11 +935,12 @@ int main(int argc, char **argv)
 	else if (argc >= 3 && !strcmp(argv[1], "direct")) rc = run_direct(argv[2]);
 	else if (argc >= 3 && !strcmp(argv[1], "threads")) rc = run_threads(argv[2]);
 	else if (argc >= 3 && !strcmp(argv[1], "kats")) rc = run_kats(argv[2]);
+	else if (argc >= 5 && !strcmp(argv[1], "fuzz")) rc = run_fuzz(argv[2], argv[3], (u32)strtoul(argv[4], NULL, 10));
 	else if (argc >= 5 && !strcmp(argv[1], "bench"))
 		rc = run_bench(argv[2], argv[3], (u32)strtoul(argv[4], NULL, 10), argc >= 6 ? argv[5] : "ECDSA",
 			       argc >= 7 ? (u32)strtoul(argv[6], NULL, 10) : 64);
 	else {
-		printf("usage: %s direct <dropin.so> | kats <dropin.so> | threads <dropin.so> | bench <dropin.so> <curve> <items> [ECDSA|ECFSDSA|BIP0340|ECSDSA|ECOSDSA|ECKCDSA|ECGDSA|ECRDSA|SM2|BIGN [invalid_every, 0 = none]] | preload\n", argv[0]);
+		printf("usage: %s direct <dropin.so> | kats <dropin.so> | fuzz <dropin.so> <curve> <mutants per scheme> | threads <dropin.so> | bench <dropin.so> <curve> <items> [ECDSA|ECFSDSA|BIP0340|ECSDSA|ECOSDSA|ECKCDSA|ECGDSA|ECRDSA|SM2|BIGN [invalid_every, 0 = none]] | preload\n", argv[0]);
 		return 2;
 	}
 	printf(rc ? "HARNESS FAILED (%d failures)\n" : "HARNESS OK (%d failures)\n", failures);

@@ -6,6 +6,7 @@ harness runs on the real engine in tests/test_gpu_dropin.py; this file keeps hos
 A subset of the curves keeps the CPU suite short (the GPU run covers all eight)."""
 import json
 import os
+import re
 import subprocess
 
 import pytest
@@ -94,3 +95,16 @@ def test_ecrdsa_iso14888_3_switch_changes_the_digest_byte_order():
     r = _run(["bench", DROPIN, "FRP256V1", "64", "ECRDSA", "0"], [engine_stub_so()],
              extra_env={"HARNESS_POOL": "64", "HARNESS_REPS": "2"})
     assert r.returncode == 0 and "HARNESS OK" in r.stdout
+
+
+@pytest.mark.parametrize("curve,mutants", [("FRP256V1", "150"), ("SECP224R1", "60")])
+def test_mutated_signatures_keys_and_ancillary_data_get_the_reference_verdict(curve, mutants):
+    """Differential fuzzing of the host logic: reference-made signatures of the twelve served schemes with single bit
+    flips, fields forced to 0 / q - 1 / q / all-ones, lengths off by one, altered / shortened / missing ancillary data,
+    keys at infinity / off the curve / of another scheme / uninitialised, empty messages - the drop-in's ec_verify must
+    return what the reference's ec_verify returns for every mutant."""
+    r = _run(["fuzz", DROPIN, curve, mutants], [engine_stub_so()])
+    assert r.returncode == 0 and "HARNESS OK" in r.stdout
+    line = [l for l in r.stdout.splitlines() if l.startswith("fuzz ")][0]
+    total, accepted, engine = (int(x) for x in re.findall(r"(\d+) (?:mutants|accepted|judged)", line))
+    assert total >= 11 * int(mutants) and 0 < accepted < total // 4 and engine > total // 2

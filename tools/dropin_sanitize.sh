@@ -18,6 +18,7 @@ export ASAN_OPTIONS=detect_leaks=0 HARNESS_POOL=64 HARNESS_REPS=2 HARNESS_KATS_T
 HARNESS_CURVES=FRP256V1,SECP521R1 LD_PRELOAD="$ASAN $STUB/libecc_b200_stub.so" run $H direct /tmp/libecc_b200_dropin_asan.so
 LD_PRELOAD="$ASAN $STUB/libecc_b200_stub.so" run $H kats /tmp/libecc_b200_dropin_asan.so
 LD_PRELOAD="$ASAN $STUB/libecc_b200_stub.so" run $H threads /tmp/libecc_b200_dropin_asan.so
+for c in FRP256V1 SECP521R1 SECP224R1; do LD_PRELOAD="$ASAN $STUB/libecc_b200_stub.so" run $H fuzz /tmp/libecc_b200_dropin_asan.so $c 300; done
 for sc in ECDSA ECFSDSA BIP0340 ECSDSA ECKCDSA ECGDSA ECRDSA SM2 BIGN; do
   LD_PRELOAD="$ASAN $STUB/libecc_b200_stub.so" run $H bench /tmp/libecc_b200_dropin_asan.so FRP256V1 2600 $sc 64
   LD_PRELOAD="$TSAN $STUB/libecc_b200_stub.so" run $H bench /tmp/libecc_b200_dropin_tsan.so FRP256V1 2600 $sc 64
