@@ -12,6 +12,7 @@
  *            the reference's own functions on identical inputs.
  *   kats     every fixed-vector case of the reference's own self tests (src/tests/ec_self_tests_core.h) through the
  *            drop-in's ec_verify and a one-item ec_verify_batch, judged by the reference's ec_verify.
+ *   fuzzmul  prj_pt_mul on random scalars of every nn width and on projective / infinite / off-curve / aliased points.
  *   fuzz     mutated signatures / keys / ancillary data of every served scheme: drop-in verdict == reference verdict.
  *   preload  run with LD_PRELOAD=libecc_b200_dropin.so: the reference's ec_sign / ec_verify / ECC-CDH code then
  *            calls the interposed prj_pt_mul, i.e. the GPU, without being recompiled; results must still satisfy
@@ -727,6 +728,54 @@ static int run_fuzz(const char *dropin_path, const char *curve, u32 iters)
 	return failures != 0;
 }
 
+
+/* fuzzmul mode: prj_pt_mul on random scalars of every nn width (0 to 27 words, top words set) and on reference-made
+ * points in projective form (Z != 1), at infinity, off the curve, with out == in - return code, infinity flag and
+ * affine coordinates must equal the reference's. */
+static int run_fuzzmul(const char *dropin_path, const char *curve, u32 iters)
+{
+	void *h = dlopen(dropin_path, RTLD_NOW | RTLD_LOCAL);
+	if (!h) return 1;
+	mul_fn gpu_mul = (mul_fn)dlsym(h, "prj_pt_mul");
+	if (!gpu_mul) return 1;
+	ec_params params;
+	CHECK(!load_params(&params, curve), "params");
+	for (const char *c = curve; *c; c++) rng_state = rng_state * 131 + (unsigned char)*c;
+	prj_pt base;
+	CHECK(!prj_pt_copy(&base, &params.ec_gen), "copy");
+	for (u32 it = 0; it < iters; it++) {
+		u8 kb[216];
+		const u16 kl = (u16)(rnd8() % 5 == 0 ? 216 - (rnd8() % 9) : (rnd8() % 80));
+		for (u16 i = 0; i < kl; i++) kb[i] = rnd8();
+		if (kl && (rnd8() & 3) == 0) kb[0] = 0xff; /* the top word really used */
+		nn k;
+		prj_pt in, o_ref, o_gpu;
+		CHECK(!nn_init_from_buf(&k, kb, kl), "nn_init_from_buf(%u)", kl);
+		CHECK(!prj_pt_copy(&in, &base), "copy");
+		const unsigned kind = rnd8() % 12u;
+		if (kind == 0) CHECK(!prj_pt_zero(&in), "zero");
+		else if (kind == 1) in.Y.fp_val.val[0] ^= 8;           /* off the curve */
+		else if (kind == 2) CHECK(!prj_pt_copy(&in, &params.ec_gen), "G"); /* the fixed-base path */
+		const int r1 = prj_pt_mul(&o_ref, &k, &in);
+		int r2;
+		if (kind == 3) { /* out == in */
+			prj_pt alias;
+			CHECK(!prj_pt_copy(&alias, &in), "copy");
+			r2 = gpu_mul(&alias, &k, &alias);
+			o_gpu = alias;
+		} else {
+			r2 = gpu_mul(&o_gpu, &k, &in);
+		}
+		compare("fuzzmul", curve, r1, &o_ref, r2, &o_gpu);
+		if (!r1 && (rnd8() & 1)) { /* walk on: the next base is this (projective, blinded) result, unless it is infinity */
+			int z = 0;
+			if (!prj_pt_iszero(&o_ref, &z) && !z) base = o_ref;
+		}
+	}
+	printf("fuzzmul %s: %u multiplications agree with the reference\n", curve, iters);
+	return failures != 0;
+}
+
 /* threads mode: the reference's functions are re-entrant; several host threads call the drop-in at once */
 typedef struct {
 	mul_fn mul;
@@ -935,12 +984,13 @@ int main(int argc, char **argv)
 	else if (argc >= 3 && !strcmp(argv[1], "direct")) rc = run_direct(argv[2]);
 	else if (argc >= 3 && !strcmp(argv[1], "threads")) rc = run_threads(argv[2]);
 	else if (argc >= 3 && !strcmp(argv[1], "kats")) rc = run_kats(argv[2]);
+	else if (argc >= 5 && !strcmp(argv[1], "fuzzmul")) rc = run_fuzzmul(argv[2], argv[3], (u32)strtoul(argv[4], NULL, 10));
 	else if (argc >= 5 && !strcmp(argv[1], "fuzz")) rc = run_fuzz(argv[2], argv[3], (u32)strtoul(argv[4], NULL, 10));
 	else if (argc >= 5 && !strcmp(argv[1], "bench"))
 		rc = run_bench(argv[2], argv[3], (u32)strtoul(argv[4], NULL, 10), argc >= 6 ? argv[5] : "ECDSA",
 			       argc >= 7 ? (u32)strtoul(argv[6], NULL, 10) : 64);
 	else {
-		printf("usage: %s direct <dropin.so> | kats <dropin.so> | fuzz <dropin.so> <curve> <mutants per scheme> | threads <dropin.so> | bench <dropin.so> <curve> <items> [ECDSA|ECFSDSA|BIP0340|ECSDSA|ECOSDSA|ECKCDSA|ECGDSA|ECRDSA|SM2|BIGN [invalid_every, 0 = none]] | preload\n", argv[0]);
+		printf("usage: %s direct <dropin.so> | kats <dropin.so> | fuzz <dropin.so> <curve> <mutants per scheme> | fuzzmul <dropin.so> <curve> <iterations> | threads <dropin.so> | bench <dropin.so> <curve> <items> [ECDSA|ECFSDSA|BIP0340|ECSDSA|ECOSDSA|ECKCDSA|ECGDSA|ECRDSA|SM2|BIGN [invalid_every, 0 = none]] | preload\n", argv[0]);
 		return 2;
 	}
 	printf(rc ? "HARNESS FAILED (%d failures)\n" : "HARNESS OK (%d failures)\n", failures);

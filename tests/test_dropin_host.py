@@ -108,3 +108,12 @@ def test_mutated_signatures_keys_and_ancillary_data_get_the_reference_verdict(cu
     line = [l for l in r.stdout.splitlines() if l.startswith("fuzz ")][0]
     total, accepted, engine = (int(x) for x in re.findall(r"(\d+) (?:mutants|accepted|judged)", line))
     assert total >= 11 * int(mutants) and 0 < accepted < total // 4 and engine > total // 2
+
+
+@pytest.mark.parametrize("curve", ["SECP256R1", "BRAINPOOLP384R1", "SECP192R1"])
+def test_prj_pt_mul_on_random_scalar_widths_and_point_forms(curve):
+    """prj_pt_mul of the drop-in on nn scalars of every width (0 to 27 words) and on projective (blinded by the reference),
+    infinite, off-curve and aliased points, walking from result to result: return code, infinity flag and coordinates as
+    the reference's prj_pt_mul gives them.  (Eleven curves x 1500 iterations were run once: profiles/r02_s3_host_sanitizers.md.)"""
+    r = _run(["fuzzmul", DROPIN, curve, "250"], [engine_stub_so()])
+    assert r.returncode == 0 and "HARNESS OK" in r.stdout and "250 multiplications agree" in r.stdout
