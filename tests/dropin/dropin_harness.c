@@ -636,7 +636,20 @@ static int run_fuzz(const char *dropin_path, const char *curve, u32 iters)
 	if (!h) return 1;
 	everify_fn gpu_everify = (everify_fn)dlsym(h, "eccb200_dropin_ec_verify");
 	count_fn gpu_vcount = (count_fn)dlsym(h, "eccb200_dropin_verify_count");
-	if (!gpu_everify || !gpu_vcount) return 1;
+	vbatch_fn gpu_generic = (vbatch_fn)dlsym(h, "ec_verify_batch");
+	verdicts_fn gpu_verdicts = (verdicts_fn)dlsym(h, "eccb200_dropin_last_verdicts");
+	if (!gpu_everify || !gpu_vcount || !gpu_generic || !gpu_verdicts) return 1;
+	/* the same mutants, sixteen at a time, also go through ec_verify_batch: per-item verdicts and the 0 / -1 of the call */
+	enum { FB = 16 };
+	static u8 b_sig[FB][3 * 66 + 2], b_msg[FB][40], b_ad[FB][32];
+	static ec_pub_key b_pk[FB];
+	const u8 *b_sp[FB], *b_mp[FB], *b_ap[FB];
+	const ec_pub_key *b_pkp[FB];
+	u8 b_sl[FB];
+	u32 b_ml[FB];
+	u16 b_al[FB];
+	int b_want[FB];
+	unsigned long long batches = 0;
 	ec_params params;
 	CHECK(!load_params(&params, curve), "params");
 	for (const char *c = curve; *c; c++) rng_state = rng_state * 31 + (unsigned char)*c; /* another sequence per curve */
@@ -670,6 +683,7 @@ static int run_fuzz(const char *dropin_path, const char *curve, u32 iters)
 			printf("note: scheme %d not usable on %s here; skipped\n", (int)alg, curve);
 			continue;
 		}
+		int nb = 0;
 		for (u32 it = 0; it < iters; it++) {
 			const int k = (int)(rnd8() % NK);
 			u8 sig[3 * 66 + 2], msg[40], adbuf[32];
@@ -722,9 +736,42 @@ static int run_fuzz(const char *dropin_path, const char *curve, u32 iters)
 			total++;
 			accepted += want == 0;
 			on_gpu += gpu_vcount() > v0;
+			if (!(adp && !needs_ad)) { /* (a batch with ancillary data on a scheme that takes none is forwarded whole) */
+				memcpy(b_sig[nb], sig, sizeof(sig));
+				memcpy(b_msg[nb], msg, sizeof(msg));
+				if (adp) memcpy(b_ad[nb], adp, adlen);
+				b_pk[nb] = pk;
+				b_sp[nb] = b_sig[nb];
+				b_mp[nb] = b_msg[nb];
+				b_ap[nb] = adp ? b_ad[nb] : NULL;
+				b_pkp[nb] = &b_pk[nb];
+				b_sl[nb] = sl;
+				b_ml[nb] = ml;
+				b_al[nb] = adlen;
+				b_want[nb] = want;
+				nb++;
+			}
+			if (nb == FB) {
+				const unsigned long long b0 = gpu_vcount();
+				const int rb = gpu_generic(b_sp, b_sl, b_pkp, b_mp, b_ml, FB, alg, SHA256, needs_ad ? b_ap : NULL,
+							   needs_ad ? b_al : NULL, NULL, NULL);
+				if (gpu_vcount() == b0 + FB) { /* judged by the engine path (a batch without one usable key is forwarded) */
+					signed char v[FB];
+					int all = 0;
+					CHECK(gpu_verdicts(v, FB) == FB, "verdict count");
+					for (int i = 0; i < FB; i++) {
+						CHECK(v[i] == b_want[i], "%s scheme %d batch item %d: %d, reference ec_verify %d", curve, (int)alg, i, v[i], b_want[i]);
+						if (b_want[i]) all = -1;
+					}
+					CHECK(rb == all, "%s scheme %d: ec_verify_batch returned %d, items say %d", curve, (int)alg, rb, all);
+					batches++;
+				}
+				nb = 0;
+			}
 		}
 	}
-	printf("fuzz %s: %llu mutants, %llu accepted by both, %llu judged by the engine path, the rest forwarded\n", curve, total, accepted, on_gpu);
+	printf("fuzz %s: %llu mutants, %llu accepted by both, %llu judged by the engine path, the rest forwarded; %llu batches of %d through ec_verify_batch\n",
+	       curve, total, accepted, on_gpu, batches, (int)FB);
 	return failures != 0;
 }
 
