@@ -58,6 +58,7 @@ def test_generated_streams(tag, n, mod):
 def test_header_is_up_to_date():
     """fp_ptx.cuh on disk is what the generator produces now."""
     path = os.path.join(ROOT, "libecc_b200", "csrc", "fp_ptx.cuh")
-    before = open(path).read()
+    before, st = open(path).read(), os.stat(path)
     gen_fp_ptx.main()
     assert open(path).read() == before
+    os.utime(path, ns=(st.st_atime_ns, st.st_mtime_ns))   # same bytes: keep the timestamp, or every test run forces a rebuild
