@@ -630,8 +630,14 @@ static int run_kats(const char *dropin_path)
  * bit flips, halves forced to 0 / q - 1 / q / all-ones, lengths off by one, altered or missing ancillary data, keys at
  * infinity / off the curve / of another scheme / with a broken magic - and every mutant goes through the reference's
  * ec_verify and the drop-in's: the two verdicts must be equal.  Deterministic (seeded); `iters` mutants per scheme. */
-static int run_fuzz(const char *dropin_path, const char *curve, u32 iters)
+static int run_fuzz(const char *dropin_path, const char *curve, u32 iters, const char *hash_name)
 {
+	const hash_mapping *fuzz_hm = NULL;
+	if (get_hash_by_name(hash_name, &fuzz_hm) || !fuzz_hm) {
+		printf("FAIL unknown hash %s\n", hash_name);
+		return 1;
+	}
+	const hash_alg_type HT = fuzz_hm->type; /* digests shorter and longer than the order exercise the truncation rules */
 	void *h = dlopen(dropin_path, RTLD_NOW | RTLD_LOCAL);
 	if (!h) return 1;
 	everify_fn gpu_everify = (everify_fn)dlsym(h, "eccb200_dropin_ec_verify");
@@ -673,11 +679,11 @@ static int run_fuzz(const char *dropin_path, const char *curve, u32 iters)
 		static u8 sig0[NK][3 * 66], msg0[NK][40];
 		u32 ml0[NK];
 		u8 sgl = 0;
-		int usable = !ec_get_sig_len(&params, alg, SHA256, &sgl) && sgl <= 3 * 66 - 2;
+		int usable = !ec_get_sig_len(&params, alg, HT, &sgl) && sgl <= 3 * 66 - 2;
 		for (int i = 0; i < NK && usable; i++) {
 			ml0[i] = (u32)(1 + (rnd8() % 39));
 			for (u32 j = 0; j < ml0[i]; j++) msg0[i][j] = rnd8();
-			usable = !ec_key_pair_gen(&kp[i], &params, alg) && !ec_sign(sig0[i], sgl, &kp[i], msg0[i], ml0[i], alg, SHA256, ad, adl);
+			usable = !ec_key_pair_gen(&kp[i], &params, alg) && !ec_sign(sig0[i], sgl, &kp[i], msg0[i], ml0[i], alg, HT, ad, adl);
 		}
 		if (!usable) {
 			printf("note: scheme %d not usable on %s here; skipped\n", (int)alg, curve);
@@ -729,8 +735,8 @@ static int run_fuzz(const char *dropin_path, const char *curve, u32 iters)
 			default: ml = 0; break;                                           /* empty message */
 			}
 			const unsigned long long v0 = gpu_vcount();
-			const int want = ec_verify(sig, sl, &pk, msg, ml, alg, SHA256, adp, adlen);
-			const int got = gpu_everify(sig, sl, &pk, msg, ml, alg, SHA256, adp, adlen);
+			const int want = ec_verify(sig, sl, &pk, msg, ml, alg, HT, adp, adlen);
+			const int got = gpu_everify(sig, sl, &pk, msg, ml, alg, HT, adp, adlen);
 			CHECK(want == got, "%s scheme %d mutation %u (iteration %u): drop-in %d, reference %d", curve, (int)alg, kind, it, got, want);
 			if (kind == 0) CHECK(want == 0, "%s scheme %d: untouched signature rejected", curve, (int)alg);
 			total++;
@@ -753,7 +759,7 @@ static int run_fuzz(const char *dropin_path, const char *curve, u32 iters)
 			}
 			if (nb == FB) {
 				const unsigned long long b0 = gpu_vcount();
-				const int rb = gpu_generic(b_sp, b_sl, b_pkp, b_mp, b_ml, FB, alg, SHA256, needs_ad ? b_ap : NULL,
+				const int rb = gpu_generic(b_sp, b_sl, b_pkp, b_mp, b_ml, FB, alg, HT, needs_ad ? b_ap : NULL,
 							   needs_ad ? b_al : NULL, NULL, NULL);
 				if (gpu_vcount() == b0 + FB) { /* judged by the engine path (a batch without one usable key is forwarded) */
 					signed char v[FB];
@@ -770,8 +776,8 @@ static int run_fuzz(const char *dropin_path, const char *curve, u32 iters)
 			}
 		}
 	}
-	printf("fuzz %s: %llu mutants, %llu accepted by both, %llu judged by the engine path, the rest forwarded; %llu batches of %d through ec_verify_batch\n",
-	       curve, total, accepted, on_gpu, batches, (int)FB);
+	printf("fuzz %s %s: %llu mutants, %llu accepted by both, %llu judged by the engine path, the rest forwarded; %llu batches of %d through ec_verify_batch\n",
+	       curve, hash_name, total, accepted, on_gpu, batches, (int)FB);
 	return failures != 0;
 }
 
@@ -1032,12 +1038,12 @@ int main(int argc, char **argv)
 	else if (argc >= 3 && !strcmp(argv[1], "threads")) rc = run_threads(argv[2]);
 	else if (argc >= 3 && !strcmp(argv[1], "kats")) rc = run_kats(argv[2]);
 	else if (argc >= 5 && !strcmp(argv[1], "fuzzmul")) rc = run_fuzzmul(argv[2], argv[3], (u32)strtoul(argv[4], NULL, 10));
-	else if (argc >= 5 && !strcmp(argv[1], "fuzz")) rc = run_fuzz(argv[2], argv[3], (u32)strtoul(argv[4], NULL, 10));
+	else if (argc >= 5 && !strcmp(argv[1], "fuzz")) rc = run_fuzz(argv[2], argv[3], (u32)strtoul(argv[4], NULL, 10), argc >= 6 ? argv[5] : "SHA256");
 	else if (argc >= 5 && !strcmp(argv[1], "bench"))
 		rc = run_bench(argv[2], argv[3], (u32)strtoul(argv[4], NULL, 10), argc >= 6 ? argv[5] : "ECDSA",
 			       argc >= 7 ? (u32)strtoul(argv[6], NULL, 10) : 64);
 	else {
-		printf("usage: %s direct <dropin.so> | kats <dropin.so> | fuzz <dropin.so> <curve> <mutants per scheme> | fuzzmul <dropin.so> <curve> <iterations> | threads <dropin.so> | bench <dropin.so> <curve> <items> [ECDSA|ECFSDSA|BIP0340|ECSDSA|ECOSDSA|ECKCDSA|ECGDSA|ECRDSA|SM2|BIGN [invalid_every, 0 = none]] | preload\n", argv[0]);
+		printf("usage: %s direct <dropin.so> | kats <dropin.so> | fuzz <dropin.so> <curve> <mutants per scheme> [hash name] | fuzzmul <dropin.so> <curve> <iterations> | threads <dropin.so> | bench <dropin.so> <curve> <items> [ECDSA|ECFSDSA|BIP0340|ECSDSA|ECOSDSA|ECKCDSA|ECGDSA|ECRDSA|SM2|BIGN [invalid_every, 0 = none]] | preload\n", argv[0]);
 		return 2;
 	}
 	printf(rc ? "HARNESS FAILED (%d failures)\n" : "HARNESS OK (%d failures)\n", failures);

@@ -97,13 +97,15 @@ def test_ecrdsa_iso14888_3_switch_changes_the_digest_byte_order():
     assert r.returncode == 0 and "HARNESS OK" in r.stdout
 
 
-@pytest.mark.parametrize("curve,mutants", [("FRP256V1", "150"), ("SECP224R1", "60")])
-def test_mutated_signatures_keys_and_ancillary_data_get_the_reference_verdict(curve, mutants):
+@pytest.mark.parametrize("curve,mutants,hash_name", [("FRP256V1", "150", "SHA256"), ("SECP224R1", "60", "SHA384"),
+                                                    ("SECP384R1", "40", "SHA224")])
+def test_mutated_signatures_keys_and_ancillary_data_get_the_reference_verdict(curve, mutants, hash_name):
     """Differential fuzzing of the host logic: reference-made signatures of the twelve served schemes with single bit
     flips, fields forced to 0 / q - 1 / q / all-ones, lengths off by one, altered / shortened / missing ancillary data,
     keys at infinity / off the curve / of another scheme / uninitialised, empty messages - the drop-in's ec_verify must
-    return what the reference's ec_verify returns for every mutant."""
-    r = _run(["fuzz", DROPIN, curve, mutants], [engine_stub_so()])
+    return what the reference's ec_verify returns for every mutant (digests longer and shorter than the order: the
+    truncation rules of ECDSA / ECGDSA / ECKCDSA); the same mutants in batches of sixteen through ec_verify_batch."""
+    r = _run(["fuzz", DROPIN, curve, mutants, hash_name], [engine_stub_so()])
     assert r.returncode == 0 and "HARNESS OK" in r.stdout
     line = [l for l in r.stdout.splitlines() if l.startswith("fuzz ")][0]
     total, accepted, engine = (int(x) for x in re.findall(r"(\d+) (?:mutants|accepted|judged)", line))
